@@ -1,0 +1,186 @@
+/* statecatcher_b200 — C-ABI of the B200-native LucyRNN + CTC (+RNN-T) training hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces a piece
+ * of PyTorch/Triton work that the reference performs inside
+ *   /root/reference/lucyrnn.py   LucyRNN.forward            (lines 89-191)
+ *   /root/reference/lucyrnn.py   LucyRNNCell.forward        (lines 44-70)
+ *   /root/reference/lucyrnn_triton.py  fused_decay_scan     (lines 158-177, retired)
+ *   /root/reference/model.py     compute_loss CTC branch    (lines 68-71)
+ *   /root/reference/model.py     compute_loss RNN-T branch  (lines 73-105)
+ * The reference has no FFI of its own (pure Python); the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md (statecatcher_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *   - all pointers are raw DEVICE pointers unless a parameter says "host";
+ *   - nothing is allocated, no static mutable state, every call is re-entrant;
+ *   - every call takes the cudaStream_t to launch on (as void*), and only enqueues work;
+ *   - sizes/strides are int64_t counted in ELEMENTS, not bytes;
+ *   - dtype codes: SC_F32 = 0, SC_BF16 = 1 (storage type of activations; all arithmetic
+ *     accumulates in fp32);
+ *   - return value: 0 = ok, >0 = a cudaError_t from the launch, <0 = SC_E_* argument error.
+ *     No C++ exception crosses this boundary.
+ */
+#ifndef STATECATCHER_B200_H
+#define STATECATCHER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_F32 0
+#define SC_BF16 1
+
+#define SC_E_BADARG (-1)   /* null pointer / negative size / unsupported flag  */
+#define SC_E_ALIGN  (-2)   /* pointer or stride breaks the kernel's alignment   */
+#define SC_E_DTYPE  (-3)   /* unknown dtype code                                */
+#define SC_E_SHAPE  (-4)   /* shape outside what the kernel family supports     */
+#define SC_E_UNSUP  (-5)   /* valid request this build cannot serve             */
+
+/* gate column blocks inside the 5H-wide gate tensor G (r, the dead gate of
+ * lucyrnn.py:50/56, is never computed): order follows lucyrnn.py:49 minus r. */
+#define SC_GATE_Z 0
+#define SC_GATE_K 1
+#define SC_GATE_V 2
+#define SC_GATE_P 3   /* 'h_pre' chunk */
+#define SC_GATE_Q 4   /* decay logits  */
+
+#define SC_SCAN_CKPT 16  /* timesteps between saved S checkpoints of the fused scan */
+
+int sc_version(void);                    /* ABI version, bumps on any signature change */
+const char* sc_error_string(int code);   /* static string for an SC_E_* / cudaError_t  */
+int sc_build_info(char* buf, int64_t n); /* "sm_100a nvcc 12.9 ..." into a host buffer */
+
+/* ---------------------------------------------------------------- K1: projections ----
+ * Replaces nn.Linear input_proj / W_fused / output_proj (lucyrnn.py:15, 23, 85; 113, 116,
+ * 186) and their autograd backward.
+ * fwd  : Y[M,N]  = A[M,K] . W[N,K]^T + bias[N]           (bias may be NULL)
+ * dgrad: dA[M,K] = dY[M,N] . W[N,K]
+ * wgrad: dW[N,K] (+)= dY[M,N]^T . A[M,K]   fp32 output; accumulate!=0 adds into dW
+ * lda/ldw/ldy are row strides in elements.  in_dtype applies to A, W (and dY), out_dtype
+ * to the result; bias and dW are always fp32.  W is fp32 when in_dtype==SC_F32 and bf16
+ * when in_dtype==SC_BF16.  impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05/TMA. */
+int sc_gemm_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                void* Y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                int in_dtype, int out_dtype, int impl, void* stream);
+int sc_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw,
+                  void* dA, int64_t ldda, int64_t M, int64_t N, int64_t K,
+                  int in_dtype, int out_dtype, int impl, void* stream);
+int sc_gemm_wgrad(const void* dY, int64_t lddy, const void* A, int64_t lda,
+                  float* dW, int64_t lddw, int64_t M, int64_t N, int64_t K,
+                  int in_dtype, int accumulate, int impl, void* stream);
+/* bytes of scratch the tcgen05 path wants for the given problem (0 for SIMT). */
+int64_t sc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+/* ---------------------------------------------------------------- row-wise helpers ---
+ * cast  : dst[i] = (dst_dtype) src[i] over a [rows, cols] matrix with row strides.
+ * colsum: out[n] (+)= sum_m X[m,n]   (bias gradients), fp32 out.
+ * layernorm fwd/bwd over the last dim H: nn.LayerNorm(H) of lucyrnn.py:17-20 (eps 1e-5). */
+int sc_cast(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd, int dst_dtype,
+            int64_t rows, int64_t cols, void* stream);
+int sc_colsum(const void* X, int64_t ldx, int dtype, float* out, int64_t M, int64_t N,
+              int accumulate, void* stream);
+int sc_layernorm_fwd(const void* X, int64_t ldx, const float* w, const float* b,
+                     void* Y, int64_t ldy, float* mean, float* rstd,
+                     int64_t M, int64_t H, int dtype, void* stream);
+int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* w,
+                     const float* mean, const float* rstd, void* dX, int64_t lddx,
+                     float* dw, float* db, int64_t M, int64_t H, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- K2: fused scan -----
+ * The whole recurrent part of one layer for fused_ops=True, layer_norm=False (the
+ * configuration model.py:232-245 wires).  Replaces the decay-scan loop
+ * (lucyrnn.py:153-158 / lucyrnn_triton.py:158-177) AND the per-timestep cell loop
+ * (lucyrnn.py:160-166 -> 44-70) AND the step path (lucyrnn.py:172-184):
+ *   d=sigmoid(q); S_t=d_t*S_{t-1}+k_t*v_t;
+ *   train_mode=1: S_{-1}=0,  s'_t=d_t*S_t+k_t*v_t, sT = s0 is NOT written (caller aliases)
+ *   train_mode=0: S_{-1}=s0, s'_t=S_t,             sT = S_{T-1}
+ *   c=tanh(p+s'); zh=sigmoid(z); h_t=(1-zh)*c+zh*h_{t-1}, h_{-1}=h0; Hout[b,t,:]=h_t.
+ * G    [B,T,5H] gate pre-activations, block g at columns [g*H,(g+1)*H), row stride ldg.
+ * h0,s0[B,H] fp32 carried state; hT,sT [B,H] fp32 outputs (sT may be NULL in train mode).
+ * Hout [B,T,H] row stride ldh.  Sckpt [B, ceil(T/SC_SCAN_CKPT), H] fp32: S before the first
+ * step of each checkpoint interval (saved for the backward's recompute; may be NULL).
+ * H must be a multiple of 8 (bf16) / 4 (fp32) and pointers 16-byte aligned. */
+int sc_lucy_scan_fwd(const void* G, int64_t ldg, const float* h0, const float* s0,
+                     void* Hout, int64_t ldh, float* hT, float* sT, float* Sckpt,
+                     int64_t B, int64_t T, int64_t H, int dtype, int train_mode, void* stream);
+/* Reverse-time adjoint.  dHout [B,T,H] is dL/dHout; writes dG
+ * [B,T,5H] (same block order) and ADDS the per-column sums of dG into dbias[5H] (fp32,
+ * the caller zeroes or pre-loads it).  No gradient is produced for h0/s0 (the carried
+ * state is detached between segments, model.py:60-61). */
+int sc_lucy_scan_bwd(const void* G, int64_t ldg, const void* Hout, int64_t ldh,
+                     const float* h0, const float* s0, const float* Sckpt,
+                     const void* dHout, int64_t lddh, void* dG, int64_t lddg, float* dbias,
+                     int64_t B, int64_t T, int64_t H, int dtype, int train_mode, void* stream);
+
+/* ---------------------------------------------------------------- K2': split scans ---
+ * General path (layer_norm=True and/or fused_ops=False and/or decay_mode='prefix_sum'):
+ * the S scan and the h scan as separate kernels so LayerNorm / W_h can sit between them.
+ * sscan: S scan + second application; A[b,t,:] = addend[b,t,:] + s'_t where addend is the
+ *        'h_pre' chunk (fused, lucyrnn.py:54) or u (unfused, lucyrnn.py:62).
+ *        decay_mode 0 = learned sigmoid(q) (lucyrnn.py:124), 1 = prefix_sum with
+ *        lambda_decay (lucyrnn.py:126-142; training path only).  S_all [B,T,H] fp32 saved.
+ * hscan: c=tanh(An); zh=sigmoid(Zn); h_t=(1-zh)c+zh*h_{t-1}. */
+int sc_lucy_sscan_fwd(const void* k, const void* v, const void* q, int64_t ldg,
+                      const void* addend, int64_t ldadd, const float* s0,
+                      void* A, int64_t lda, float* S_all, float* sT,
+                      int64_t B, int64_t T, int64_t H, int dtype, int train_mode,
+                      int decay_mode, float lambda_decay, void* stream);
+int sc_lucy_sscan_bwd(const void* k, const void* v, const void* q, int64_t ldg,
+                      const float* S_all, const float* s0, const void* dA, int64_t ldda,
+                      void* dk, void* dv, void* dq, int64_t lddg,
+                      int64_t B, int64_t T, int64_t H, int dtype, int train_mode,
+                      int decay_mode, float lambda_decay, void* stream);
+int sc_lucy_hscan_fwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn,
+                      const float* h0, void* Hout, int64_t ldh, float* hT,
+                      int64_t B, int64_t T, int64_t H, int dtype, void* stream);
+int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn,
+                      const void* Hout, int64_t ldh, const float* h0,
+                      const void* dHout, int64_t lddh, void* dAn, int64_t lddan,
+                      void* dZn, int64_t lddzn,
+                      int64_t B, int64_t T, int64_t H, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- K3: CTC ------------
+ * Replaces log_softmax + nn.CTCLoss(blank, zero_infinity=True) forward and backward
+ * (model.py:70-71, train.py:142; ATen ctc_loss).  logits[b,t,:] at
+ * logits + b*stride_b + t*stride_t (V contiguous) — so both the (B,T,V) encoder output and
+ * the (T,B,V) transposed view nn.CTCLoss receives are accepted.  Rows need not be
+ * normalised (log-softmax is folded in and is idempotent).
+ * targets [B,Umax] int64 (row stride ldt), in_lens/tgt_lens [B] int64.
+ * Workspaces (caller-allocated, fp32): lse [B,T], lplat/alpha/beta [B,T,S] with
+ * S = 2*Umax+1.  nll [B] = per-utterance negative log-likelihood (+inf if infeasible);
+ * loss [1] = reduction of nll: reduction 0 none (loss untouched), 1 mean
+ * = mean_b(nll_b/max(U_b,1)), 2 sum; infeasible utterances contribute 0 (zero_infinity). */
+int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+               const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+               const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+               int64_t blank, float* lse, float* lplat, float* alpha, float* beta,
+               float* nll, float* loss, int reduction, void* stream);
+/* dlogits[b,t,:] = gout * scale_b * (softmax - occupancy) for t < T_b, exactly 0 for
+ * t >= T_b and for infeasible utterances.  grad_out: device fp32, [1] for mean/sum, [B]
+ * for reduction none.  dlogits strides like logits. */
+int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+               const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+               const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+               int64_t blank, const float* lse, const float* alpha, const float* beta,
+               const float* nll, const float* grad_out, int reduction,
+               void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------- K4: RNN-T ----------
+ * Replaces warp_rnnt.RNNTLoss as called at model.py:97-105 (gather=True): transducer
+ * alpha/beta over the T x (U+1) lattice swept by anti-diagonals.
+ * log_probs [B,T,U1,V] normalised fp32 (U1 = Umax+1), labels [B,Umax] int64.
+ * Workspaces fp32: lpb, lpl, alpha, beta [B,T,U1].  nll [B].  grad (may be NULL)
+ * [B,T,U1,V] receives d(sum_b w_b*nll_b)/dlog_probs with w = grad_w[B] (non-zero at the
+ * blank and label column of each live node; the buffer is fully written). */
+int sc_rnnt_fwd_bwd(const float* log_probs, const int64_t* labels, int64_t ldl,
+                    const int64_t* frame_lens, const int64_t* label_lens,
+                    int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank,
+                    float* lpb, float* lpl, float* alpha, float* beta, float* nll,
+                    const float* grad_w, float* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STATECATCHER_B200_H */

@@ -1,0 +1,13 @@
+"""statecatcher_b200 — B200-native LucyRNN + CTC (+RNN-T) training hot path.
+
+Python host code over hand-written sm_100a CUDA kernels behind a C-ABI
+(include/statecatcher_b200.h).  No Triton, no multi-backend dispatch, no CPU fallback.
+"""
+from .lucyrnn_conf import LucyRNNConfig
+from .lucyrnn import LucyRNN, LucyRNNCell, LucyRNNtriton
+from .ctc import CTCLoss, ctc_loss, ctc_loss_from_logits
+from .glue import LucyASRModel, assert_all_detached, compute_loss, detach_states
+
+__all__ = ["LucyRNNConfig", "LucyRNN", "LucyRNNCell", "LucyRNNtriton", "CTCLoss", "ctc_loss",
+           "ctc_loss_from_logits", "LucyASRModel", "compute_loss", "detach_states",
+           "assert_all_detached"]

@@ -1,0 +1,111 @@
+"""ctypes binding of the C-ABI in include/statecatcher_b200.h.
+
+This is the reference-side stub a maintainer would add: raw device
+pointers (``tensor.data_ptr()``), sizes and the current CUDA stream go straight through
+``extern "C"`` entry points of ``csrc/libstatecatcher_b200.so``.  There is no CPU fallback:
+if the library is missing the import fails loudly, and every non-zero return code raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libstatecatcher_b200.so")
+
+SC_F32, SC_BF16 = 0, 1
+SC_SCAN_CKPT = 16
+
+P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
+
+# name -> argtypes, exactly as declared in include/statecatcher_b200.h
+SIGNATURES = {
+    "sc_version": [],
+    "sc_error_string": [I32],
+    "sc_build_info": [c_char_p, I64],
+    "sc_gemm_fwd": [P, I64, P, I64, P, P, I64, I64, I64, I64, I32, I32, I32, P],
+    "sc_gemm_dgrad": [P, I64, P, I64, P, I64, I64, I64, I64, I32, I32, I32, P],
+    "sc_gemm_wgrad": [P, I64, P, I64, P, I64, I64, I64, I64, I32, I32, I32, P],
+    "sc_gemm_workspace_bytes": [I64, I64, I64],
+    "sc_cast": [P, I64, I32, P, I64, I32, I64, I64, P],
+    "sc_colsum": [P, I64, I32, P, I64, I64, I32, P],
+    "sc_layernorm_fwd": [P, I64, P, P, P, I64, P, P, I64, I64, I32, P],
+    "sc_layernorm_bwd": [P, I64, P, I64, P, P, P, P, I64, P, P, I64, I64, I32, P],
+    "sc_lucy_scan_fwd": [P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I32, I32, P],
+    "sc_lucy_scan_bwd": [P, I64, P, I64, P, P, P, P, I64, P, I64, P, I64, I64, I64, I32, I32, P],
+    "sc_lucy_sscan_fwd": [P, P, P, I64, P, I64, P, P, I64, P, P, I64, I64, I64, I32, I32, I32, F32, P],
+    "sc_lucy_sscan_bwd": [P, P, P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I64, I32, I32, I32, F32, P],
+    "sc_lucy_hscan_fwd": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I32, P],
+    "sc_lucy_hscan_bwd": [P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I64, I64, I64, I32, P],
+    "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, I32, P],
+    "sc_ctc_bwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, I32,
+                   P, I64, I64, I32, P],
+    "sc_rnnt_fwd_bwd": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, P],
+}
+_RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m statecatcher_b200.build` "
+            "(statecatcher_b200 has no CPU or PyTorch fallback path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if an export is missing
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, I32)
+    _lib = lib
+    return lib
+
+
+class StatecatcherError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().sc_error_string(rc).decode()
+        raise StatecatcherError(f"{what} failed with code {rc}: {msg}")
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return SC_F32
+    if t.dtype == torch.bfloat16:
+        return SC_BF16
+    raise TypeError(f"statecatcher_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: statecatcher_b200 runs on sm_100a CUDA devices only "
+            "(no CPU fallback; the CPU oracle lives in oracle/ and is test-only)")
+
+
+# launch counter: bench.py's "gpu_launches" claim is read from here
+launches = 0
+
+
+def call(name: str, *args):
+    global launches
+    launches += 1
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,142 @@
+// Shared device helpers for the statecatcher_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/statecatcher_b200.h"
+
+#define SC_CHECK_ARG(cond, code) do { if (!(cond)) return (code); } while (0)
+#define SC_LAUNCH_RET() do { cudaError_t e__ = cudaGetLastError(); return (int)e__; } while (0)
+
+namespace sc {
+
+typedef __nv_bfloat16 bf16;
+
+__host__ __device__ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int code = SC_F32; };
+template <> struct DT<bf16>  { static constexpr int code = SC_BF16; };
+
+// ---- scalar load/store with conversion to/from fp32 -------------------------------
+__device__ __forceinline__ float ld_f(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_f(const bf16* p) { return __bfloat162float(__ldg(p)); }
+__device__ __forceinline__ void st_f(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_f(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- vector of N consecutive elements <-> float[N] ---------------------------------
+// N*sizeof(T) must be 4, 8 or 16 bytes and the address aligned to it.
+template <int BYTES> struct RawVec;
+template <> struct RawVec<4>  { typedef uint32_t type; };
+template <> struct RawVec<8>  { typedef uint2 type; };
+template <> struct RawVec<16> { typedef uint4 type; };
+
+template <typename T, int N> struct Vec {
+  typedef typename RawVec<sizeof(T) * N>::type raw_t;
+  raw_t raw;
+};
+
+// streaming (read-once) global load: read-only path, do not allocate in L1
+__device__ __forceinline__ uint32_t ldg_stream(const uint32_t* p) {
+  uint32_t r; asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p)); return r;
+}
+__device__ __forceinline__ uint2 ldg_stream(const uint2* p) {
+  uint2 r; asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r;
+}
+__device__ __forceinline__ void stg_stream(uint32_t* p, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream(uint2* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream(uint4* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T, int N>
+__device__ __forceinline__ Vec<T, N> vload(const T* p) {
+  Vec<T, N> v;
+  v.raw = ldg_stream(reinterpret_cast<const typename Vec<T, N>::raw_t*>(p));
+  return v;
+}
+template <typename T, int N>
+__device__ __forceinline__ void vstore(T* p, const Vec<T, N>& v) {
+  stg_stream(reinterpret_cast<typename Vec<T, N>::raw_t*>(p), v.raw);
+}
+
+template <int N>
+__device__ __forceinline__ void unpack(const Vec<float, N>& v, float (&f)[N]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v.raw);
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = __uint_as_float(w[i]);
+}
+template <int N>
+__device__ __forceinline__ void unpack(const Vec<bf16, N>& v, float (&f)[N]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v.raw);
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    f[2 * i]     = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <int N>
+__device__ __forceinline__ Vec<float, N> pack(const float (&f)[N], float*) {
+  Vec<float, N> v;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v.raw);
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = __float_as_uint(f[i]);
+  return v;
+}
+template <int N>
+__device__ __forceinline__ Vec<bf16, N> pack(const float (&f)[N], bf16*) {
+  Vec<bf16, N> v;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v.raw);
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return v;
+}
+
+// ---- activations ------------------------------------------------------------------
+// PRECISE=true : ex2/rcp based, abs error ~1e-7 (fp32 parity path, rtol 1e-4 contract)
+// PRECISE=false: one MUFU.TANH each (abs error ~5e-4, below bf16 resolution of the outputs);
+//                keeps the bf16 scan off the MUFU roofline (3 instead of 6 MUFU / element).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+template <bool PRECISE> __device__ __forceinline__ float sigmoidf_(float x) {
+  if (PRECISE) return __fdividef(1.0f, 1.0f + __expf(-x));
+  return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f);
+}
+template <bool PRECISE> __device__ __forceinline__ float tanhf_(float x) {
+  if (PRECISE) {
+    // 1 - 2/(e^{2x}+1); saturates correctly for |x| large (e^{2x} -> inf or 0)
+    float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+  }
+  return tanh_approx(x);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace sc

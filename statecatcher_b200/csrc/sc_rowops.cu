@@ -1,0 +1,187 @@
+// Row-wise helpers around the projections: dtype cast, bias-gradient column sums and the
+// LayerNorm forward/backward of lucyrnn.py:17-20 (nn.LayerNorm(H), eps=1e-5) used when
+// config.layer_norm=True.  All HBM-bound, coalesced along the contiguous dimension.
+#include "sc_common.cuh"
+
+namespace sc {
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd,
+                            int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    st_f(dst + r * ldd + c, ld_f(src + r * lds + c));
+  }
+}
+
+__global__ void zero_kernel(float* __restrict__ p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+// out[n] += sum over a chunk of rows; one thread per column, coalesced across columns
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int64_t ldx, float* __restrict__ out,
+                              int64_t M, int64_t N, int64_t rows_per_block) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int64_t m = m0;
+  for (; m + 3 < m1; m += 4) {
+    a0 += ld_f(X + m * ldx + n); a1 += ld_f(X + (m + 1) * ldx + n);
+    a2 += ld_f(X + (m + 2) * ldx + n); a3 += ld_f(X + (m + 3) * ldx + n);
+  }
+  for (; m < m1; ++m) a0 += ld_f(X + m * ldx + n);
+  atomicAdd(out + n, (a0 + a1) + (a2 + a3));
+}
+
+constexpr int LN_WARPS = 4;
+constexpr float LN_EPS = 1e-5f;
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const T* __restrict__ X, int64_t ldx, const float* __restrict__ w,
+                     const float* __restrict__ b, T* __restrict__ Y, int64_t ldy,
+                     float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T* x = X + row * ldx;
+  float s = 0.f;
+  for (int i = lane; i < H; i += 32) s += ld_f(x + i);
+  const float mu = warp_sum(s) / (float)H;
+  float v = 0.f;
+  for (int i = lane; i < H; i += 32) { const float d = ld_f(x + i) - mu; v = fmaf(d, d, v); }
+  const float rs = rsqrtf(warp_sum(v) / (float)H + LN_EPS);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  T* y = Y + row * ldy;
+  for (int i = lane; i < H; i += 32) st_f(y + i, (ld_f(x + i) - mu) * rs * w[i] + b[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
+                     const float* __restrict__ w, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
+                     float* __restrict__ dw, float* __restrict__ db, int64_t M, int H,
+                     int64_t rows_per_block) {
+  extern __shared__ float sm[];        // dw[H], db[H] block partials
+  float* sdw = sm;
+  float* sdb = sm + H;
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  for (int64_t row = m0 + warp; row < m1; row += LN_WARPS) {
+    const T* x = X + row * ldx;
+    const T* dy = dY + row * lddy;
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < H; i += 32) {
+      const float g = ld_f(dy + i) * w[i];
+      const float xh = (ld_f(x + i) - mu) * rs;
+      s1 += g; s2 = fmaf(g, xh, s2);
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    T* dx = dX + row * lddx;
+    for (int i = lane; i < H; i += 32) {
+      const float dyi = ld_f(dy + i);
+      const float xh = (ld_f(x + i) - mu) * rs;
+      st_f(dx + i, rs * (dyi * w[i] - s1 - xh * s2));
+      atomicAdd(sdw + i, dyi * xh);
+      atomicAdd(sdb + i, dyi);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dw + i, sdw[i]);
+    atomicAdd(db + i, sdb[i]);
+  }
+}
+
+}  // namespace sc
+
+using namespace sc;
+
+extern "C" int sc_cast(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd, int dst_dtype,
+                       int64_t rows, int64_t cols, void* stream) {
+  SC_CHECK_ARG(rows >= 0 && cols >= 0, SC_E_BADARG);
+  if (rows * cols == 0) return 0;
+  SC_CHECK_ARG(src && dst, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)min((int64_t)148 * 16, cdiv(rows * cols, 256));
+  if (src_dtype == SC_F32 && dst_dtype == SC_BF16)
+    cast_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols);
+  else if (src_dtype == SC_BF16 && dst_dtype == SC_F32)
+    cast_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols);
+  else if (src_dtype == SC_F32 && dst_dtype == SC_F32)
+    cast_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols);
+  else if (src_dtype == SC_BF16 && dst_dtype == SC_BF16)
+    cast_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols);
+  else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_colsum(const void* X, int64_t ldx, int dtype, float* out, int64_t M, int64_t N,
+                         int accumulate, void* stream) {
+  SC_CHECK_ARG(M >= 0 && N >= 0, SC_E_BADARG);
+  if (N == 0) return 0;
+  SC_CHECK_ARG(out && (M == 0 || X), SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) zero_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(out, N);
+  if (M > 0) {
+    const int64_t col_blocks = cdiv(N, 128);
+    int64_t row_blocks = cdiv(148 * 8, col_blocks);
+    if (row_blocks > cdiv(M, 64)) row_blocks = cdiv(M, 64);
+    const int64_t rpb = cdiv(M, row_blocks);
+    dim3 grid((unsigned)col_blocks, (unsigned)cdiv(M, rpb));
+    if (dtype == SC_F32) colsum_kernel<float><<<grid, 128, 0, st>>>((const float*)X, ldx, out, M, N, rpb);
+    else if (dtype == SC_BF16) colsum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)X, ldx, out, M, N, rpb);
+    else return SC_E_DTYPE;
+  }
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_layernorm_fwd(const void* X, int64_t ldx, const float* w, const float* b,
+                                void* Y, int64_t ldy, float* mean, float* rstd,
+                                int64_t M, int64_t H, int dtype, void* stream) {
+  SC_CHECK_ARG(M >= 0 && H > 0 && H < (1 << 24), SC_E_BADARG);
+  if (M == 0) return 0;
+  SC_CHECK_ARG(X && w && b && Y && mean && rstd, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)cdiv(M, LN_WARPS);
+  if (dtype == SC_F32)
+    layernorm_fwd_kernel<float><<<blocks, LN_WARPS * 32, 0, st>>>((const float*)X, ldx, w, b, (float*)Y, ldy, mean, rstd, M, (int)H);
+  else if (dtype == SC_BF16)
+    layernorm_fwd_kernel<bf16><<<blocks, LN_WARPS * 32, 0, st>>>((const bf16*)X, ldx, w, b, (bf16*)Y, ldy, mean, rstd, M, (int)H);
+  else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* w,
+                                const float* mean, const float* rstd, void* dX, int64_t lddx,
+                                float* dw, float* db, int64_t M, int64_t H, int dtype, void* stream) {
+  SC_CHECK_ARG(M >= 0 && H > 0 && H <= 24 * 1024, SC_E_BADARG);
+  if (M == 0) return 0;
+  SC_CHECK_ARG(dY && X && w && mean && rstd && dX && dw && db, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = 148 * 4;
+  if (blocks > cdiv(M, LN_WARPS)) blocks = cdiv(M, LN_WARPS);
+  const int64_t rpb = cdiv(M, blocks);
+  blocks = cdiv(M, rpb);
+  const size_t smem = 2 * (size_t)H * sizeof(float);
+  if (dtype == SC_F32) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<float><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const float*)dY, lddy, (const float*)X, ldx, w, mean, rstd,
+        (float*)dX, lddx, dw, db, M, (int)H, rpb);
+  } else if (dtype == SC_BF16) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<bf16><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const bf16*)dY, lddy, (const bf16*)X, ldx, w, mean, rstd,
+        (bf16*)dX, lddx, dw, db, M, (int)H, rpb);
+  } else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}

@@ -1,0 +1,158 @@
+"""Thin tensor-level wrappers over the C-ABI calls (allocation + pointer plumbing only).
+
+Every function here enqueues hand-written sm_100a kernels on the current torch stream via
+``_lib.call``; none of them falls back to PyTorch arithmetic.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, dt, ptr, stream
+
+GEMM_IMPL = 0  # 0 auto (tcgen05 when the shape tiles, else SIMT), 1 SIMT, 2 tcgen05
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row stride (elements) of a 2-D tensor whose last dim is contiguous."""
+    assert t.dim() == 2 and (t.size(1) <= 1 or t.stride(1) == 1), (t.shape, t.stride())
+    return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
+
+
+def gemm_fwd(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype=None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ w[N,K]^T + bias[N]."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.dtype == w.dtype
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype or a.dtype, device=a.device)
+    call("sc_gemm_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(out), _ld(out), M, N, K,
+         dt(a), dt(out), GEMM_IMPL, stream())
+    return out
+
+
+def gemm_dgrad(dy: torch.Tensor, w: torch.Tensor, out_dtype=None, out=None) -> torch.Tensor:
+    """out[M,K] = dy[M,N] @ w[N,K]."""
+    M, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N and dy.dtype == w.dtype
+    if out is None:
+        out = torch.empty(M, K, dtype=out_dtype or dy.dtype, device=dy.device)
+    call("sc_gemm_dgrad", ptr(dy), _ld(dy), ptr(w), _ld(w), ptr(out), _ld(out), M, N, K,
+         dt(dy), dt(out), GEMM_IMPL, stream())
+    return out
+
+
+def gemm_wgrad(dy: torch.Tensor, a: torch.Tensor, out: Optional[torch.Tensor] = None,
+               accumulate: bool = False) -> torch.Tensor:
+    """out[N,K] (+)= dy[M,N]^T @ a[M,K]   (fp32 out)."""
+    M, N = dy.shape
+    K = a.shape[1]
+    assert a.shape[0] == M and dy.dtype == a.dtype
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+        accumulate = False
+    call("sc_gemm_wgrad", ptr(dy), _ld(dy), ptr(a), _ld(a), ptr(out), _ld(out), M, N, K,
+         dt(dy), int(accumulate), GEMM_IMPL, stream())
+    return out
+
+
+def cast(src: torch.Tensor, dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    s2 = src if src.dim() == 2 else src.reshape(-1, src.shape[-1])
+    if out is None:
+        out = torch.empty(s2.shape, dtype=dtype, device=src.device)
+    o2 = out if out.dim() == 2 else out.view(-1, out.shape[-1])
+    call("sc_cast", ptr(s2), _ld(s2), dt(s2), ptr(o2), _ld(o2), dt(o2), s2.shape[0], s2.shape[1], stream())
+    return out.view(src.shape) if out.dim() != src.dim() else out
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+        accumulate = False
+    call("sc_colsum", ptr(x), _ld(x), dt(x), ptr(out), M, N, int(accumulate), stream())
+    return out
+
+
+def layernorm_fwd(x, w, b, out=None):
+    M, H = x.shape
+    if out is None:
+        out = torch.empty(M, H, dtype=x.dtype, device=x.device)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    call("sc_layernorm_fwd", ptr(x), _ld(x), ptr(w), ptr(b), ptr(out), _ld(out), ptr(mean), ptr(rstd),
+         M, H, dt(x), stream())
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx=None):
+    """Returns dx, dw, db (dw/db fresh fp32)."""
+    M, H = x.shape
+    if dx is None:
+        dx = torch.empty(M, H, dtype=x.dtype, device=x.device)
+    dw = torch.zeros(H, dtype=torch.float32, device=x.device)
+    db = torch.zeros(H, dtype=torch.float32, device=x.device)
+    call("sc_layernorm_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(w), ptr(mean), ptr(rstd),
+         ptr(dx), _ld(dx), ptr(dw), ptr(db), M, H, dt(x), stream())
+    return dx, dw, db
+
+
+def n_ckpt(T: int) -> int:
+    return (T + _lib.SC_SCAN_CKPT - 1) // _lib.SC_SCAN_CKPT
+
+
+def scan_fwd(G, B, T, H, h0, s0, train_mode: bool):
+    """G [B*T,5H] -> Hout [B*T,H], hT, sT(None in train mode), Sckpt."""
+    dev = G.device
+    Hout = torch.empty(B * T, H, dtype=G.dtype, device=dev)
+    hT = torch.empty(B, H, dtype=torch.float32, device=dev)
+    sT = None if train_mode else torch.empty(B, H, dtype=torch.float32, device=dev)
+    ck = torch.empty(B, max(n_ckpt(T), 1), H, dtype=torch.float32, device=dev)
+    call("sc_lucy_scan_fwd", ptr(G), _ld(G), ptr(h0), ptr(s0), ptr(Hout), H, ptr(hT), ptr(sT), ptr(ck),
+         B, T, H, dt(G), int(train_mode), stream())
+    return Hout, hT, sT, ck
+
+
+def scan_bwd(G, Hout, h0, s0, ck, dHout, B, T, H, train_mode: bool):
+    """-> dG [B*T,5H] (same dtype as G), dbias5 [5H] fp32."""
+    dev = G.device
+    dG = torch.empty(B * T, 5 * H, dtype=G.dtype, device=dev)
+    dbias = torch.zeros(5 * H, dtype=torch.float32, device=dev)
+    call("sc_lucy_scan_bwd", ptr(G), _ld(G), ptr(Hout), _ld(Hout), ptr(h0), ptr(s0), ptr(ck),
+         ptr(dHout), _ld(dHout), ptr(dG), 5 * H, ptr(dbias), B, T, H, dt(G), int(train_mode), stream())
+    return dG, dbias
+
+
+def sscan_fwd(k, v, q, addend, s0, B, T, H, train_mode, decay_mode, lam):
+    dev = k.device
+    assert _ld(k) == _ld(v) == _ld(q)
+    A = torch.empty(B * T, H, dtype=k.dtype, device=dev)
+    S_all = torch.empty(B * T, H, dtype=torch.float32, device=dev)
+    sT = None if train_mode else torch.empty(B, H, dtype=torch.float32, device=dev)
+    call("sc_lucy_sscan_fwd", ptr(k), ptr(v), ptr(q), _ld(k), ptr(addend), _ld(addend), ptr(s0),
+         ptr(A), H, ptr(S_all), ptr(sT), B, T, H, dt(k), int(train_mode), int(decay_mode), float(lam), stream())
+    return A, S_all, sT
+
+
+def sscan_bwd(k, v, q, S_all, s0, dA, dk, dv, dq, B, T, H, train_mode, decay_mode, lam):
+    assert _ld(k) == _ld(v) == _ld(q) and _ld(dk) == _ld(dv) == _ld(dq)
+    call("sc_lucy_sscan_bwd", ptr(k), ptr(v), ptr(q), _ld(k), ptr(S_all), ptr(s0), ptr(dA), _ld(dA),
+         ptr(dk), ptr(dv), ptr(dq), _ld(dk), B, T, H, dt(k), int(train_mode), int(decay_mode), float(lam), stream())
+
+
+def hscan_fwd(An, Zn, h0, B, T, H):
+    dev = An.device
+    Hout = torch.empty(B * T, H, dtype=An.dtype, device=dev)
+    hT = torch.empty(B, H, dtype=torch.float32, device=dev)
+    call("sc_lucy_hscan_fwd", ptr(An), _ld(An), ptr(Zn), _ld(Zn), ptr(h0), ptr(Hout), H, ptr(hT),
+         B, T, H, dt(An), stream())
+    return Hout, hT
+
+
+def hscan_bwd(An, Zn, Hout, h0, dHout, dAn, dZn, B, T, H):
+    call("sc_lucy_hscan_bwd", ptr(An), _ld(An), ptr(Zn), _ld(Zn), ptr(Hout), _ld(Hout), ptr(h0),
+         ptr(dHout), _ld(dHout), ptr(dAn), _ld(dAn), ptr(dZn), _ld(dZn), B, T, H, dt(An), stream())

@@ -1,0 +1,305 @@
+"""GPU parity tests, kernel level: every C-ABI kernel family against the CPU oracle
+(oracle/, fp64) on the same seeded inputs.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc_oracle, lucy_oracle as LO
+
+pytestmark = pytest.mark.gpu
+
+# fp32 contract: rtol 1e-4 (BASELINE.json north_star).  bf16: looser, stated bound 3e-2 of
+# the tensor's max magnitude (the reference's own fp32->bf16-autocast drift is ~1e-2 rel-L2).
+F32_RTOL, F32_ATOL = 1e-4, 2e-5
+BF16_REL = 3e-2
+
+
+def _close(got, want, dtype, what=""):
+    got = got.detach().double().cpu().numpy()
+    want = np.asarray(want, dtype=np.float64)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(got, want, rtol=F32_RTOL, atol=F32_ATOL * max(1.0, np.abs(want).max()), err_msg=what)
+    else:
+        scale = max(np.abs(want).max(), 1e-3)
+        assert np.abs(got - want).max() <= BF16_REL * scale, (what, np.abs(got - want).max(), scale)
+
+
+def _ops():
+    from statecatcher_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------ K1 projections ---
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 50, 19), (300, 130, 80), (513, 257, 129), (2048, 256, 256)])
+def test_gemm_family(cuda_device, dtype, M, N, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g).to(dtype)
+    w = torch.randn(N, K, generator=g).to(dtype)
+    dy = torch.randn(M, N, generator=g).to(dtype)
+    bias = torch.randn(N, generator=g)
+    A, W, DY = a.double(), w.double(), dy.double()
+    y = ops.gemm_fwd(a.cuda(), w.cuda(), bias.cuda())
+    _close(y, A @ W.T + bias.double(), dtype, "fwd")
+    da = ops.gemm_dgrad(dy.cuda(), w.cuda())
+    _close(da, DY @ W, dtype, "dgrad")
+    dw = ops.gemm_wgrad(dy.cuda(), a.cuda())
+    assert dw.dtype == torch.float32
+    _close(dw, DY.T @ A, torch.float32 if dtype == torch.float32 else dtype, "wgrad")
+    # accumulate flag
+    base = torch.randn(N, K, generator=g).cuda()
+    dw2 = ops.gemm_wgrad(dy.cuda(), a.cuda(), out=base.clone(), accumulate=True)
+    _close(dw2, DY.T @ A + base.double().cpu(), torch.float32 if dtype == torch.float32 else dtype, "wgrad acc")
+
+
+def test_gemm_strided_views(cuda_device):
+    """Column-block views (ld != width) as the layer code passes them."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(70, 5 * 24, generator=g).cuda()
+    w = torch.randn(5 * 24, 24, generator=g).cuda()
+    blk = big[:, 24:48]
+    y = ops.gemm_dgrad(blk, w[24:48])
+    _close(y, blk.double().cpu() @ w[24:48].double().cpu(), torch.float32)
+    out = torch.zeros(70, 3 * 16).cuda()
+    ops.gemm_fwd(big[:, :24], torch.randn(16, 24, generator=g).cuda(), None, out=out[:, 16:32])
+    assert out[:, :16].abs().max() == 0 and out[:, 32:].abs().max() == 0
+
+
+# ------------------------------------------------------------------ row helpers ------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_layernorm_cast_colsum(cuda_device, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    M, H = 77, 48
+    x = (torch.randn(M, H, generator=g) * 2 + 0.5).to(dtype)
+    w = torch.randn(H, generator=g)
+    b = torch.randn(H, generator=g)
+    dy = torch.randn(M, H, generator=g).to(dtype)
+    xd = x.double().requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd, (H,), wd, bd, 1e-5)
+    ref.backward(dy.double())
+    y, mean, rstd = ops.layernorm_fwd(x.cuda(), w.cuda(), b.cuda())
+    _close(y, ref.detach(), dtype, "ln fwd")
+    dx, dw, db = ops.layernorm_bwd(dy.cuda(), x.cuda(), w.cuda(), mean, rstd)
+    _close(dx, xd.grad, dtype, "ln dx")
+    _close(dw, wd.grad, dtype, "ln dw")
+    _close(db, bd.grad, dtype, "ln db")
+    _close(ops.colsum(dy.cuda()), dy.double().sum(0), dtype, "colsum")
+    c = ops.cast(x.float().cuda(), torch.bfloat16)
+    assert torch.equal(c.cpu(), x.float().to(torch.bfloat16))       # round-to-nearest-even, bit exact
+
+
+# ------------------------------------------------------------------ K2 fused scan ----
+def _scan_reference(G, h0, s0, training, g_out):
+    """fp64 closed form + autograd (oracle) for the fused scan stage."""
+    B, T, H5 = G.shape
+    H = H5 // 5
+    Gd = G.double().requires_grad_(True)
+    z, k, v, p, q = [Gd[..., i * H:(i + 1) * H] for i in range(5)]
+    d = torch.sigmoid(q)
+    kv = k * v
+    S = LO._linear_scan(d, kv, torch.zeros(B, H, dtype=torch.float64) if training else s0.double())
+    sp = d * S + kv if training else S
+    c = torch.tanh(p + sp)
+    zh = torch.sigmoid(z)
+    Hout = LO._linear_scan(zh, (1 - zh) * c, h0.double())
+    (Hout * g_out.double()).sum().backward()
+    return Hout.detach(), S.detach(), Gd.grad
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("training", [True, False], ids=["train", "step"])
+@pytest.mark.parametrize("B,T,H", [(1, 1, 8), (3, 17, 24), (2, 48, 64), (5, 100, 40)])
+def test_fused_scan_fwd_bwd(cuda_device, dtype, training, B, T, H):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    G = torch.randn(B, T, 5 * H, generator=g).to(dtype)
+    h0 = torch.randn(B, H, generator=g) * 0.5
+    s0 = torch.randn(B, H, generator=g) * 0.5
+    go = torch.randn(B, T, H, generator=g).to(dtype)
+    Href, Sref, dGref = _scan_reference(G.float(), h0, s0, training, go.float())
+    Gc = G.cuda().view(B * T, 5 * H)
+    Hout, hT, sT, ck = ops.scan_fwd(Gc, B, T, H, h0.cuda(), s0.cuda(), training)
+    _close(Hout.view(B, T, H), Href, dtype, "Hout")
+    _close(hT, Href[:, -1], dtype, "hT")
+    if not training:
+        _close(sT, Sref[:, -1], dtype, "sT")
+    dG, dbias = ops.scan_bwd(Gc, Hout, h0.cuda(), s0.cuda(), ck, go.cuda().view(B * T, H), B, T, H, training)
+    _close(dG.view(B, T, 5 * H), dGref, dtype, "dG")
+    _close(dbias, dG.double().sum(0).cpu(), torch.float32, "dbias = column sums of dG")
+
+
+def test_step_path_state_handoff_is_bit_exact(cuda_device):
+    """Segment-boundary handoff: one 96-step segment == three 32-step segments with carried
+    (h, s), bit for bit, in the step path (both states carried in fp32)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    B, T, H = 4, 96, 64
+    G = torch.randn(B, T, 5 * H, generator=g).cuda()
+    h0 = torch.randn(B, H, generator=g).cuda()
+    s0 = torch.randn(B, H, generator=g).cuda()
+    full, hT, sT, _ = ops.scan_fwd(G.view(B * T, 5 * H), B, T, H, h0, s0, False)
+    h, s, parts = h0, s0, []
+    for i in range(3):
+        seg = G[:, 32 * i:32 * (i + 1)].contiguous().view(B * 32, 5 * H)
+        o, h, s, _ = ops.scan_fwd(seg, B, 32, H, h, s, False)
+        parts.append(o.view(B, 32, H))
+    assert torch.equal(torch.cat(parts, 1), full.view(B, T, H))
+    assert torch.equal(h, hT) and torch.equal(s, sT)
+
+
+def test_fused_scan_large_properties(cuda_device):
+    """cfg2-sized layer (B=64,T=3000,H=1024, bf16): no oracle at this size, so check
+    size-independent facts: the training path equals the step path started from s0=0 with
+    the second application removed... (not equal) -> instead: (a) determinism, (b) h bounded by
+    construction (convex combination of tanh values and h0), (c) split-segment equality."""
+    ops = _ops()
+    B, T, H = 64, 3000, 1024
+    g = torch.Generator(device="cuda").manual_seed(1)
+    G = torch.randn(B * T, 5 * H, generator=g, device="cuda", dtype=torch.bfloat16)
+    h0 = torch.zeros(B, H, device="cuda")
+    s0 = torch.zeros(B, H, device="cuda")
+    o1, hT1, _, ck = ops.scan_fwd(G, B, T, H, h0, s0, True)
+    o2, hT2, _, _ = ops.scan_fwd(G, B, T, H, h0, s0, True)
+    assert torch.equal(o1, o2) and torch.equal(hT1, hT2)
+    assert o1.float().abs().max() <= 1.0 + 1e-2
+    # step path: 3000 = 1504 + 1496 split must be bit exact
+    G3 = G.view(B, T, 5 * H)
+    f, hf, sf, _ = ops.scan_fwd(G, B, T, H, h0, s0, False)
+    a, ha, sa, _ = ops.scan_fwd(G3[:, :1504].contiguous().view(-1, 5 * H), B, 1504, H, h0, s0, False)
+    b, hb, sb, _ = ops.scan_fwd(G3[:, 1504:].contiguous().view(-1, 5 * H), B, 1496, H, ha, sa, False)
+    assert torch.equal(hb, hf) and torch.equal(sb, sf)
+    assert torch.equal(b.view(B, 1496, H), f.view(B, T, H)[:, 1504:])
+    # backward runs at full size and is finite
+    go = torch.randn(B * T, H, generator=g, device="cuda", dtype=torch.bfloat16)
+    dG, db = ops.scan_bwd(G, o1, h0, s0, ck, go, B, T, H, True)
+    assert torch.isfinite(dG.float()).all() and torch.isfinite(db).all()
+
+
+# ------------------------------------------------------------------ K2' split scans --
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("mode", ["train", "step", "prefix"])
+def test_split_scans(cuda_device, dtype, mode):
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    B, T, H = 3, 19, 24
+    training = mode != "step"
+    dmode = 1 if mode == "prefix" else 0
+    lam = 0.05
+    k, v, q, add = [torch.randn(B, T, H, generator=g).to(dtype) for _ in range(4)]
+    s0 = torch.randn(B, H, generator=g)
+    h0 = torch.randn(B, H, generator=g)
+    dA = torch.randn(B, T, H, generator=g).to(dtype)
+    kd, vd, qd, ad = [t.double().requires_grad_(True) for t in (k, v, q, add)]
+    d = torch.sigmoid(qd)
+    kv = kd * vd
+    if dmode:
+        S = LO._prefix_sum_scan(kv, lam)
+    else:
+        S = LO._linear_scan(d, kv, torch.zeros(B, H, dtype=torch.float64) if training else s0.double())
+    A = ad + (d * S + kv if training else S)
+    (A * dA.double()).sum().backward()
+    c = lambda t: t.cuda().view(B * T, H)                      # noqa: E731
+    Ag, S_all, sT = ops.sscan_fwd(c(k), c(v), c(q), c(add), s0.cuda(), B, T, H, training, dmode, lam)
+    _close(Ag.view(B, T, H), A.detach(), dtype, "A")
+    _close(S_all.view(B, T, H), S.detach(), dtype, "S_all")
+    dk, dv, dq = [torch.empty(B * T, H, dtype=dtype, device="cuda") for _ in range(3)]
+    ops.sscan_bwd(c(k), c(v), c(q), S_all, s0.cuda(), c(dA), dk, dv, dq, B, T, H, training, dmode, lam)
+    _close(dk.view(B, T, H), kd.grad, dtype, "dk")
+    _close(dv.view(B, T, H), vd.grad, dtype, "dv")
+    _close(dq.view(B, T, H), qd.grad, dtype, "dq")
+    # h scan
+    An, Zn, go = [torch.randn(B, T, H, generator=g).to(dtype) for _ in range(3)]
+    and_, znd = An.double().requires_grad_(True), Zn.double().requires_grad_(True)
+    zh = torch.sigmoid(znd)
+    Hout = LO._linear_scan(zh, (1 - zh) * torch.tanh(and_), h0.double())
+    (Hout * go.double()).sum().backward()
+    Hg, hT = ops.hscan_fwd(c(An), c(Zn), h0.cuda(), B, T, H)
+    _close(Hg.view(B, T, H), Hout.detach(), dtype, "Hout")
+    _close(hT, Hout[:, -1].detach(), dtype, "hT")
+    dAn, dZn = [torch.empty(B * T, H, dtype=dtype, device="cuda") for _ in range(2)]
+    ops.hscan_bwd(c(An), c(Zn), Hg, h0.cuda(), c(go), dAn, dZn, B, T, H)
+    _close(dAn.view(B, T, H), and_.grad, dtype, "dAn")
+    _close(dZn.view(B, T, H), znd.grad, dtype, "dZn")
+
+
+# ------------------------------------------------------------------ K3 CTC -----------
+CTC_CASES = ["basic", "repeats_tight", "infeasible", "empty_target", "zero_frames", "all_empty", "long"]
+
+
+@pytest.mark.parametrize("layout", ["btv", "tbv"])
+@pytest.mark.parametrize("case", CTC_CASES)
+def test_ctc_golden(cuda_device, case, layout):
+    from conftest import load_golden
+    from statecatcher_b200 import ctc_loss
+    G = load_golden("ctc_cases")
+    logits = torch.tensor(G[case + "/logits"]).cuda()
+    if layout == "tbv":
+        x = logits.transpose(0, 1).contiguous().requires_grad_(True)
+        inp = x
+    else:
+        x = logits.clone().requires_grad_(True)
+        inp = x.transpose(0, 1)
+    tokens = torch.tensor(G[case + "/tokens"]).cuda()
+    in_lens, tgt_lens = G[case + "/in_lens"].tolist(), G[case + "/tgt_lens"].tolist()
+    loss = ctc_loss(inp, tokens, in_lens, tgt_lens, blank=0, reduction="mean", zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), G[case + "/loss"], rtol=1e-4, atol=1e-6)
+    grad = x.grad if layout == "btv" else x.grad.transpose(0, 1)
+    np.testing.assert_allclose(grad.cpu().numpy(), G[case + "/grad"], rtol=1e-4, atol=2e-6)
+    # bit-exact structural facts: zero beyond T_b, zero rows for infeasible utterances
+    nll = ctc_loss(inp.detach(), tokens, in_lens, tgt_lens, reduction="none", zero_infinity=True)
+    np.testing.assert_allclose(nll.cpu().numpy(), G[case + "/nll"], rtol=1e-4, atol=1e-5)
+    for b, Tb in enumerate(in_lens):
+        assert (grad[b, Tb:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_ctc_random_vs_oracle(cuda_device, dtype):
+    from statecatcher_b200 import CTCLoss
+    g = torch.Generator().manual_seed(5)
+    B, T, V, U = 6, 40, 29, 9
+    logits = (torch.randn(B, T, V, generator=g) * 3).to(dtype)
+    tgt_lens = [9, 0, 5, 9, 1, 7]
+    in_lens = [40, 40, 33, 17, 40, 2]                     # last one infeasible (2 < 7)
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    loss_ref, nll_ref, grad_ref = ctc_oracle.ctc_loss_and_grad(logits.float().numpy(), tokens.numpy(), in_lens, tgt_lens)
+    x = logits.cuda().requires_grad_(True)
+    crit = CTCLoss(blank=0, zero_infinity=True)
+    loss = crit(x.transpose(0, 1), tokens.cuda(), in_lens, tgt_lens)
+    (loss * 3.0).backward()                               # upstream scale must flow through
+    np.testing.assert_allclose(loss.item(), loss_ref, rtol=2e-4)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(x.grad.cpu().numpy(), 3.0 * grad_ref, rtol=2e-4, atol=1e-6)
+    else:
+        assert np.abs(x.grad.float().cpu().numpy() - 3.0 * grad_ref).max() <= BF16_REL * np.abs(3.0 * grad_ref).max()
+    assert (x.grad[5] == 0).all() and (x.grad[2, 33:] == 0).all()
+    # tensor lengths, int32 targets, sum reduction
+    x2 = logits.cuda().requires_grad_(True)
+    from statecatcher_b200 import ctc_loss
+    l2 = ctc_loss(x2.transpose(0, 1), tokens.int().cuda(), torch.tensor(in_lens).cuda(), torch.tensor(tgt_lens),
+                  reduction="sum", zero_infinity=True)
+    np.testing.assert_allclose(l2.item(), np.where(np.isfinite(nll_ref), nll_ref, 0).sum(), rtol=2e-4)
+
+
+def test_ctc_large_properties(cuda_device):
+    """cfg2-sized CTC (B=64,T=3000,V=1024,U<=150): rows of dlogits sum to ~0, exact zeros
+    beyond T_b, loss finite and reproducible."""
+    from statecatcher_b200 import ctc_loss_from_logits
+    B, T, V, U = 64, 3000, 1024, 150
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(B, T, V, generator=g, device="cuda").requires_grad_(True)
+    tokens = torch.randint(1, V, (B, U), generator=g, device="cuda")
+    tgt = [75 + (7 * b) % 76 for b in range(B)]
+    inl = [T] * B
+    inl[3] = 1700
+    inl[5], tgt[5] = 0, 0
+    l1 = ctc_loss_from_logits(x, tokens, inl, tgt)
+    l1.backward()
+    l2 = ctc_loss_from_logits(x.detach(), tokens, inl, tgt)
+    assert torch.isfinite(l1) and l1.item() == l2.item()
+    assert (x.grad[3, 1700:] == 0).all() and (x.grad[5] == 0).all()
+    assert x.grad.sum(-1).abs().max().item() < 1e-5

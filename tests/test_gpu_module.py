@@ -1,0 +1,153 @@
+"""GPU parity tests, module level: the LucyRNN nn.Module + CTC head driven the way
+model.py:60-71 / train.py:460-580 drive the reference (two segments, detached carried
+state), against (a) the golden vectors produced by the unmodified reference and (b) the
+fp64 oracle.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cfg_kwargs, golden_lucy_names, load_golden
+from oracle import lucy_oracle as LO
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(G, compute_dtype=None):
+    import statecatcher_b200 as sb
+    cfg = sb.LucyRNNConfig(**golden_cfg_kwargs(G))
+    model = sb.LucyRNN(cfg, compute_dtype=compute_dtype).cuda()
+    sd = {k[len("param/"):]: torch.tensor(v) for k, v in G.items() if k.startswith("param/")}
+    model.load_state_dict(sd, strict=True)
+    return sb, cfg, model
+
+
+@pytest.mark.parametrize("name", golden_lucy_names())
+def test_module_matches_reference_golden_fp32(cuda_device, name):
+    G = load_golden("lucy_" + name)
+    sb, cfg, model = _build(G)
+    crit = sb.CTCLoss(blank=0, zero_infinity=True)
+    state = None
+    for seg in range(2):
+        model.zero_grad(set_to_none=True)
+        x = torch.tensor(G[f"seg{seg}/x"]).cuda()
+        if state:
+            state = sb.detach_states(state)
+            np.testing.assert_array_equal(torch.stack(state[0]).cpu().numpy(), prev_h)   # bit-exact handoff
+        res = model(x, state) if state is not None else model(x)
+        logits, state = res if cfg.return_last_states else (res, None)
+        want = G[f"seg{seg}/logits"]
+        np.testing.assert_allclose(logits.detach().cpu().numpy(), want, rtol=1e-4, atol=2e-5 * max(1, np.abs(want).max()))
+        if state is not None:
+            prev_h = torch.stack(state[0]).detach().cpu().numpy()
+            np.testing.assert_allclose(prev_h, G[f"seg{seg}/h_out"], rtol=1e-4, atol=2e-5)
+            np.testing.assert_allclose(torch.stack(state[1]).detach().cpu().numpy(), G[f"seg{seg}/s_out"], rtol=1e-4, atol=2e-5)
+        loss = crit(logits.transpose(0, 1), torch.tensor(G[f"seg{seg}/tokens"]).cuda(),
+                    G[f"seg{seg}/in_lens"].tolist(), G[f"seg{seg}/tgt_lens"].tolist())
+        np.testing.assert_allclose(loss.item(), G[f"seg{seg}/loss"], rtol=1e-4, atol=1e-6)
+        loss.backward()
+        for k, p in model.named_parameters():
+            want = G[f"seg{seg}/grad/" + k]
+            got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
+            scale = max(1e-3, np.abs(want).max())
+            assert np.abs(got - want).max() <= 2e-4 * scale, (name, seg, k, np.abs(got - want).max(), scale)
+        if cfg.fused_ops:                                  # dead r gate: exact zeros
+            H = cfg.hidden_dim
+            assert (model.layers[0].W_fused.weight.grad[:H] == 0).all()
+            assert (model.layers[0].W_fused.bias.grad[:H] == 0).all()
+
+
+def test_training_path_s_passthrough_and_list_mutation(cuda_device):
+    """lucyrnn.py:165: training path returns the caller's s tensors untouched; the passed
+    lists are the returned lists (lucyrnn.py:107, 188-191)."""
+    G = load_golden("lucy_train_fused_noln")
+    sb, cfg, model = _build(G)
+    B, H = 3, cfg.hidden_dim
+    h = [torch.randn(B, H).cuda() for _ in range(cfg.num_layers)]
+    s = [torch.randn(B, H).cuda() for _ in range(cfg.num_layers)]
+    s_ids = [t.data_ptr() for t in s]
+    x = torch.tensor(G["seg0/x"]).cuda()
+    _, (h2, s2) = model(x, (h, s))
+    assert h2 is h and s2 is s
+    assert [t.data_ptr() for t in s2] == s_ids
+
+
+def test_module_errors(cuda_device):
+    import statecatcher_b200 as sb
+    with pytest.raises(ValueError):
+        sb.LucyRNN(sb.LucyRNNConfig(5, 8, 1, 4, kernel_impl="cuda"))
+    m = sb.LucyRNN(sb.LucyRNNConfig(5, 8, 1, 4, decay_mode="bogus")).cuda()
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 3, 5).cuda())
+    m = sb.LucyRNN(sb.LucyRNNConfig(5, 8, 1, 4)).cuda()
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(1, 3, 5).cuda(), None, torch.ones(1, 3, 1).cuda())
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 3, 5))                              # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("name", ["medium_train_fused_noln", "medium_train_fused_ln", "step_fused_noln"])
+def test_module_bf16_within_stated_bound(cuda_device, name):
+    """bf16 compute path vs the fp32 golden: stated bound rel-L2 <= 3e-2 on logits and
+    <= 6e-2 on weight grads (the reference's own fp32->bf16 autocast drift is 1e-2/1.5e-2)."""
+    G = load_golden("lucy_" + name)
+    sb, cfg, model = _build(G, compute_dtype=torch.bfloat16)
+    crit = sb.CTCLoss(blank=0, zero_infinity=True)
+    x = torch.tensor(G["seg0/x"]).cuda()
+    logits, state = model(x)
+    rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)   # noqa: E731
+    assert logits.dtype == torch.bfloat16
+    assert rel(logits.float().detach().cpu().numpy(), G["seg0/logits"]) <= 3e-2
+    assert state[0][0].dtype == torch.float32
+    loss = crit(logits.transpose(0, 1), torch.tensor(G["seg0/tokens"]).cuda(),
+                G["seg0/in_lens"].tolist(), G["seg0/tgt_lens"].tolist())
+    assert abs(loss.item() - G["seg0/loss"]) <= 3e-2 * abs(G["seg0/loss"])
+    loss.backward()
+    for k, p in model.named_parameters():
+        want = G["seg0/grad/" + k]
+        if np.abs(want).max() == 0:
+            continue
+        assert rel(p.grad.cpu().numpy(), want) <= 6e-2, (k, rel(p.grad.cpu().numpy(), want))
+
+
+def test_autocast_selects_bf16_path(cuda_device):
+    G = load_golden("lucy_medium_train_fused_noln")
+    sb, cfg, model = _build(G)
+    x = torch.tensor(G["seg0/x"]).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, _ = model(x)
+    assert logits.dtype == torch.bfloat16
+    logits32, _ = model(x)
+    assert logits32.dtype == torch.float32
+
+
+def test_compute_loss_glue_carries_state(cuda_device):
+    """compute_loss (model.py:37-110 mirror) over 3 segments == oracle train_segments."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(0)
+    cfg = sb.LucyRNNConfig(input_dim=12, hidden_dim=16, num_layers=2, vocab_size=9, fused_ops=True, layer_norm=False)
+    model = sb.LucyASRModel(cfg).cuda()
+    ocfg = LO.OracleConfig(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    P = LO.random_params(ocfg, 3, dtype=torch.float32)
+    model.encoder.load_state_dict(P)
+    Pd = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    g = torch.Generator().manual_seed(8)
+    B, T = 4, 21
+    xs = [torch.randn(B, T, 12, generator=g) for _ in range(3)]
+    toks = [torch.randint(1, 9, (B, 5), generator=g) for _ in range(3)]
+    inl, tgl = [[T, T - 3, T, 10]] * 3, [[5, 3, 0, 4]] * 3
+    ref_losses, _, ref_state = LO.train_segments(Pd, ocfg, [x.double() for x in xs], toks, inl, tgl, looped=False)
+    crit = sb.CTCLoss(blank=0, zero_infinity=True)
+    state = None
+    for i in range(3):
+        mask = torch.ones(B, T, dtype=torch.bool).cuda()
+        loss, state, enc_out, _ = sb.compute_loss("ctc", crit, model, xs[i].cuda(), mask, toks[i].cuda(), inl[i], tgl[i],
+                                                  blank_id=0, input_state=state)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), ref_losses[i].item(), rtol=1e-4)
+    for k, p in model.encoder.named_parameters():
+        want = Pd[k].grad.numpy() if Pd[k].grad is not None else None
+        if want is None:
+            continue
+        scale = max(1e-3, np.abs(want).max())
+        assert np.abs(p.grad.cpu().numpy() - want).max() <= 2e-4 * scale, k      # grads accumulated over 3 segments
+    np.testing.assert_allclose(torch.stack(state[0]).cpu().numpy(), torch.stack(ref_state[0]).detach().numpy(), rtol=1e-4, atol=2e-5)
