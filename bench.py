@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+  python bench.py --impl reference --gpus N --steps K ...   # reference CPU algorithm (oracle port)
+
+Metric (BASELINE.json): train frames/sec of LucyRNN fwd + bwd + CTC with carried state.
+One "step" = one 30 s segment of every stream of the rank: detach carried state ->
+LucyRNN forward -> fused log-softmax+CTC -> backward (all weight gradients; + the bucketed
+NCCL gradient all-reduce when N>1).  The optimizer is outside the path.
+Workload at N=1 = configs[1]: 6-layer h=1024, V=1024, bf16, B=64 streams, T=3000 frames x 80
+fbank, fused_ops=True, layer_norm=False (what model.py:232-245 wires).  N>1 = configs[2]:
+the same per-rank shape on every rank (weak scaling, 64*N streams).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: model + data shape
+    "cfg2": dict(L=6, H=1024, F=80, V=1024, B=64, T=3000, dtype="bf16", umin=75, umax=150),
+    "cfg1": dict(L=2, H=256, F=80, V=1024, B=8, T=1000, dtype="f32", umin=25, umax=50),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--layer-norm", action="store_true", help="layer_norm=True variant (general path)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+def synth_batch(W, seed, device="cpu"):
+    """SURVEY.md 8d synthetic inputs: x~N(0,1); labels in [1,V); U_b~U[umin,umax]; all streams
+    full length except one shortened and one finished (zero features, in_len=0, U=0)."""
+    g = torch.Generator().manual_seed(seed)
+    B, T, F, V = W["B"], W["T"], W["F"], W["V"]
+    x = torch.randn(B, T, F, generator=g)
+    tgt = torch.randint(W["umin"], W["umax"] + 1, (B,), generator=g).tolist()
+    inl = [T] * B
+    if B > 2:
+        inl[1] = int(torch.randint(T // 2, T + 1, (1,), generator=g))
+        inl[2], tgt[2] = 0, 0
+        x[2].zero_()
+    tokens = torch.randint(1, V, (B, max(tgt)), generator=g)
+    return x, tokens, inl, tgt
+
+
+def init_reference_like(model, seed, out_std=0.02):
+    torch.manual_seed(seed)
+    for layer in model.layers:
+        layer.init_weights()
+    torch.nn.init.normal_(model.output_proj.weight, 0.0, out_std)
+    torch.nn.init.zeros_(model.output_proj.bias)
+
+
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(W, layer_norm, steps, warmup, target_seconds, B=None, T=None):
+    """The reference's CPU algorithm (oracle.lucy_oracle.forward_looped: per-timestep cell loop
+    with re-projection, lucyrnn.py:109-170) + nn.CTCLoss + backward, fp32, all host threads,
+    on a bounded sample of the workload.  Returns frames/s and a description."""
+    from oracle import lucy_oracle as LO
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    cfg = LO.OracleConfig(input_dim=W["F"], hidden_dim=W["H"], num_layers=W["L"], vocab_size=W["V"],
+                          is_training=True, fused_ops=True, layer_norm=layer_norm)
+    P = LO.reference_init_params(cfg, 1234)
+    for p in P.values():
+        p.requires_grad_(True)
+    B = B or min(W["B"], 8)
+    crit = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+
+    def run(Tn, nsteps):
+        g = torch.Generator().manual_seed(7)
+        state, t0 = None, time.perf_counter()
+        for _ in range(nsteps):
+            x = torch.randn(B, Tn, W["F"], generator=g)
+            U = max(1, Tn // 25)
+            tok = torch.randint(1, W["V"], (B, U), generator=g)
+            for p in P.values():
+                p.grad = None
+            if state:
+                state = LO.detach_states(state)
+            logits, state = LO.forward_looped(P, cfg, x, state)
+            loss = crit(logits.log_softmax(-1).transpose(0, 1), tok, [Tn] * B, [U] * B)
+            loss.backward()
+        return time.perf_counter() - t0
+
+    if T is None:
+        probe_T = 8
+        dt = run(probe_T, 1)                       # calibrate (also warms the thread pool)
+        per_frame_step = dt / probe_T
+        T = int(max(8, min(W["T"], target_seconds / max(per_frame_step, 1e-6) / max(steps + warmup, 1))))
+    if warmup:
+        run(T, warmup)
+    dt = run(T, steps)
+    fps = B * T * steps / dt
+    sample = (f"{W['L']}x{W['H']} V={W['V']} fp32 fused_ops=True layer_norm={layer_norm}, B={B}, T={T} frames, "
+              f"{steps} carried segment(s); reference loop structure (lucyrnn.py:109-170) restated in oracle/lucy_oracle.py")
+    return fps, cores, sample, dt / steps * 1e3, B, T
+
+
+def reference_arm(args, W):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fps, cores, sample, ms, B, T = cpu_reference_run(W, args.layer_norm, args.steps, args.warmup,
+                                                     target_seconds=max(20.0, 8.0 * args.steps))
+    line = {
+        "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, W, 1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, W, world):
+    return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + CTC (V={W['V']}), {W['dtype']} training, "
+                        f"batch {W['B']} streams/GPU x {W['T']} frames x {W['F']} fbank, carried state "
+                        f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
+            "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": True,
+            "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
+            "l2_policy": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2",
+            "optimizer": "excluded (SURVEY.md 8d); zero_grad included"}
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    W = dict(WORKLOADS[args.workload])
+    if args.impl == "reference":
+        return reference_arm(args, W)
+
+    import torch.distributed as dist
+    import statecatcher_b200 as sb
+    from statecatcher_b200 import _lib
+    from statecatcher_b200.dp import StreamDataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cd = torch.bfloat16 if W["dtype"] == "bf16" else torch.float32
+    cfg = sb.LucyRNNConfig(input_dim=W["F"], hidden_dim=W["H"], num_layers=W["L"], vocab_size=W["V"],
+                           is_training=True, fused_ops=True, layer_norm=bool(args.layer_norm))
+    enc = sb.LucyRNN(cfg, compute_dtype=cd)
+    init_reference_like(enc, 1234)                 # same weights on every rank
+    enc = enc.to(dev)
+    model = StreamDataParallel(enc) if world > 1 else enc
+
+    # a few distinct synthetic segments per rank, cycled (streams of this rank: seed by rank)
+    NSEG = 2
+    host = [synth_batch(W, 1234 + rank * 100 + i) for i in range(NSEG)]
+    xh = [h[0].pin_memory() for h in host]
+    tokh = [h[1].pin_memory() for h in host]
+    xd = [h[0].to(dev) for h in host]
+    tokd = [h[1].to(dev) for h in host]
+    inld = [torch.tensor(h[2], device=dev) for h in host]
+    tgld = [torch.tensor(h[3], device=dev) for h in host]
+    frames_step = W["B"] * W["T"]
+    state = {"s": None}
+
+    def step_resident(i):
+        j = i % NSEG
+        st = sb.detach_states(state["s"]) if state["s"] else None
+        model.zero_grad(set_to_none=True)
+        logits, state["s"] = model(xd[j], st) if st else model(xd[j])
+        loss = sb.ctc_loss_from_logits(logits, tokd[j], inld[j], tgld[j], zero_infinity=True)
+        loss.backward()
+        return loss
+
+    xbuf = torch.empty_like(xd[0])
+    tokbuf = [torch.empty_like(t) for t in tokd]
+
+    def step_e2e(i):
+        j = i % NSEG
+        xbuf.copy_(xh[j], non_blocking=True)                       # H2D features from pinned host
+        tokbuf[j].copy_(tokh[j], non_blocking=True)                # H2D labels
+        st = sb.detach_states(state["s"]) if state["s"] else None
+        model.zero_grad(set_to_none=True)
+        logits, state["s"] = model(xbuf, st) if st else model(xbuf)
+        loss = sb.ctc_loss_from_logits(logits, tokbuf[j], host[j][2], host[j][3], zero_infinity=True)  # list lengths -> H2D
+        loss.backward()
+        return loss.item()                                          # D2H result read
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    # ---- timed region (device-resident inputs), per-call CUDA events recorded alongside ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.launches = 0
+    _lib.kernels = 0
+    _lib.profile = []
+    ms = timed(step_resident, args.steps)
+    prof, _lib.profile = _lib.profile, None
+    launches = _lib.kernels
+    clocks = sampler.stop() if rank == 0 else None
+    value = frames_step * world * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers ----
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = frames_step * world * args.steps / (ms_e2e * 1e-3)
+    h2d = xh[0].numel() * 4 + tokh[0].numel() * 8 + 2 * W["B"] * 8
+    d2h = 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline per kernel family from the events recorded inside the timed region ----
+    pk = peaks()
+    e = 2 if cd == torch.bfloat16 else 4
+    fam = {}
+    for name, work, ev0, ev1 in prof:
+        d = fam.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0})
+        d["ms"] += ev0.elapsed_time(ev1)
+        d["work"] += work
+        d["n"] += 1
+    live_frames = sum(sum(min(t, W["T"]) for t in h[2]) for h in host) / NSEG
+    umean = sum(sum(h[3]) for h in host) / NSEG / W["B"]
+
+    def roof(names, bound, work_override=None):
+        t = sum(fam[n]["ms"] for n in names if n in fam)
+        n = sum(fam[nm]["n"] for nm in names if nm in fam)
+        if t <= 0:
+            return None
+        work = work_override if work_override is not None else sum(fam[nm]["work"] for nm in names if nm in fam)
+        if bound == "hbm":
+            ach, peak, unit = work / (t * 1e-3) / 1e9, pk["hbm"], "GB/s"
+        else:
+            ach, peak, unit = work / (t * 1e-3) / 1e12, pk["tf_sust"], "TFLOP/s"
+        return {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "peak_source": pk["src"] + (" sustained bf16" if bound == "tensor" else " copy"),
+                "ms_per_step": t / args.steps, "launches_per_step": n / args.steps, "traffic": None}
+
+    ctc_bytes = (3 * W["V"] * e + 8 * (2 * umean + 1)) * live_frames * args.steps
+    roofs = {
+        "scan_fwd": roof(["sc_lucy_scan_fwd"], "hbm"),
+        "scan_bwd": roof(["sc_lucy_scan_bwd"], "hbm"),
+        "ctc": roof(["sc_ctc_fwd", "sc_ctc_bwd"], "hbm", ctc_bytes),
+        "gemm": roof(["sc_gemm_fwd", "sc_gemm_dgrad", "sc_gemm_wgrad"], "tensor"),
+    }
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tr = json.load(open(tp))
+        for k, v in roofs.items():
+            if v and k in tr:
+                v["traffic"] = tr[k]
+    roofs = {k: v for k, v in roofs.items() if v}
+    dominant = max(roofs, key=lambda k: roofs[k]["ms_per_step"]) if roofs else None
+    roofline = dict(roofs[dominant], kernel=dominant) if dominant else None
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        fps, cores, sample, _, _, _ = cpu_reference_run(W, bool(args.layer_norm), 1, 0, args.cpu_seconds)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": W["dtype"], "data": "synthetic",
+        "config": workload_config(args, W, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "roofline_by_kernel": roofs,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

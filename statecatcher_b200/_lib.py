@@ -101,11 +101,49 @@ def require_cuda(t: torch.Tensor, name: str):
             "(no CPU fallback; the CPU oracle lives in oracle/ and is test-only)")
 
 
-# launch counter: bench.py's "gpu_launches" claim is read from here
+# ---- instrumentation read by bench.py ------------------------------------------------
+# launches = C-ABI calls made; kernels = CUDA kernels those calls enqueue (each entry point
+# launches a fixed, documented number of kernels); profile = None, or a list that receives
+# (name, algorithmic work, start event, end event) per call for the roofline accounting.
 launches = 0
+kernels = 0
+profile = None
+
+KERNELS_PER_CALL = {
+    "sc_gemm_fwd": 1, "sc_gemm_dgrad": 1, "sc_gemm_wgrad": 1, "sc_cast": 1, "sc_colsum": 2,
+    "sc_layernorm_fwd": 1, "sc_layernorm_bwd": 1, "sc_lucy_scan_fwd": 1, "sc_lucy_scan_bwd": 1,
+    "sc_lucy_sscan_fwd": 1, "sc_lucy_sscan_bwd": 1, "sc_lucy_hscan_fwd": 1, "sc_lucy_hscan_bwd": 1,
+    "sc_ctc_fwd": 3, "sc_ctc_bwd": 1, "sc_rnnt_fwd_bwd": 3,
+}
+_ESZ = {SC_F32: 4, SC_BF16: 2}
+
+
+def _work(name, a):
+    """Algorithmic work of one call: FLOPs for the projections, HBM bytes for the scans
+    (fwd 6H*e, bwd 12H*e bytes per frame and layer)."""
+    if name == "sc_gemm_fwd":
+        return 2.0 * a[7] * a[8] * a[9]
+    if name in ("sc_gemm_dgrad", "sc_gemm_wgrad"):
+        return 2.0 * a[6] * a[7] * a[8]
+    if name == "sc_lucy_scan_fwd":
+        return 6.0 * a[11] * _ESZ[a[12]] * a[9] * a[10]
+    if name == "sc_lucy_scan_bwd":
+        return 12.0 * a[14] * _ESZ[a[15]] * a[12] * a[13]
+    return 0.0
 
 
 def call(name: str, *args):
-    global launches
+    global launches, kernels
     launches += 1
-    check(getattr(load(), name)(*args), name)
+    kernels += KERNELS_PER_CALL.get(name, 1)
+    fn = getattr(load(), name)
+    if profile is None:
+        check(fn(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    check(rc, name)
+    profile.append((name, _work(name, args), e0, e1))

@@ -38,6 +38,7 @@ __device__ __forceinline__ int64_t ext_label(const int64_t* tg, int s, int64_t b
 }
 
 constexpr int CTC_WARPS = 8;
+constexpr int CTC_RENORM = 16;   // alpha/beta columns are re-centred every this many steps
 
 // ---- pass 1 ------------------------------------------------------------------------
 template <typename T>
@@ -103,6 +104,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
                                       float* __restrict__ alpha, float* __restrict__ beta,
                                       float* __restrict__ nll) {
   extern __shared__ float sm[];       // 2 lines of (Smax + 4) floats, 2 pad cells either side
+  __shared__ float red[32];
   const int b = blockIdx.x, dir = blockIdx.y;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
@@ -135,6 +137,11 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
   __syncthreads();
   float* prev = bufA;
   float* cur = bufB;
+  // Log-space values drift to magnitude ~T*log(V); every CTC_RENORM steps the column is
+  // re-centred on its maximum so fp32 keeps ~1e-6 absolute resolution for any T.  The removed
+  // offsets only matter for the likelihood (summed in double); the gradient pass normalises
+  // each frame's occupancies itself (sum_s exp(alpha+beta-lp) is the same for every t).
+  double csum = 0.0;
   for (int i = 1; i < Tb; ++i) {
     const int t = t_first + i * step;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
@@ -152,14 +159,27 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
         v = lse3(prev[s], p1, p2) + e;
       }
       cur[s] = v;
-      out_b[(int64_t)t * Smax + s] = v;
     }
+    if ((i % CTC_RENORM) == 0) {
+      float m = NEG_INF;
+      for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, cur[s]);   // own nodes only
+      m = warp_max(m);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+      __syncthreads();
+      m = NEG_INF;
+      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m = fmaxf(m, red[w]);
+      if (m > NEG_INF) {
+        for (int s = threadIdx.x; s < S; s += blockDim.x) cur[s] -= m;
+        csum += (double)m;
+      }
+    }
+    for (int s = threadIdx.x; s < S; s += blockDim.x) out_b[(int64_t)t * Smax + s] = cur[s];
     __syncthreads();
     float* tmp = prev; prev = cur; cur = tmp;
   }
   if (dir == 0 && threadIdx.x == 0) {
     const float ll = lse2(prev[S - 1], S > 1 ? prev[S - 2] : NEG_INF);
-    nll[b] = -ll;   // +inf when infeasible
+    nll[b] = (ll == NEG_INF) ? INFINITY : (float)(-(csum + (double)ll));   // +inf when infeasible
   }
 }
 
@@ -213,13 +233,27 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
   const int64_t* tg = targets + (int64_t)b * ldt;
   const float* al = alpha + row * Smax;
   const float* be = beta + row * Smax;
+  // occupancy_s = exp(alpha+beta-lp)_s / sum_s' exp(alpha+beta-lp)_s'   (the sum is exp(-nll)
+  // for every frame; normalising per frame keeps it exact under the re-centred alpha/beta)
+  float vmax = NEG_INF;
   for (int s = lane; s < S; s += 32) {
-    const float ab = al[s] + be[s];
-    if (ab > NEG_INF) {
-      const int64_t lab = ext_label(tg, s, blank);
-      const float lp = ld_f(x + lab) - l;
-      atomicAdd(r + lab, -__expf(ab + n - lp));
-    }
+    const float lp = ld_f(x + ext_label(tg, s, blank)) - l;
+    vmax = fmaxf(vmax, al[s] + be[s] - lp);
+  }
+  vmax = warp_max(vmax);
+  float zsum = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const float lp = ld_f(x + ext_label(tg, s, blank)) - l;
+    const float v = al[s] + be[s] - lp;
+    if (v > NEG_INF) zsum += __expf(v - vmax);
+  }
+  zsum = warp_sum(zsum);
+  const float inv = (zsum > 0.f) ? 1.f / zsum : 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const int64_t lab = ext_label(tg, s, blank);
+    const float lp = ld_f(x + lab) - l;
+    const float v = al[s] + be[s] - lp;
+    if (v > NEG_INF) atomicAdd(r + lab, -__expf(v - vmax) * inv);
   }
   __syncwarp();
   float scale;
