@@ -1,10 +1,429 @@
-// K1 (bf16 training path): tcgen05 + TMA GEMM — placeholder until the kernel lands.
+// K1 (bf16 training path): persistent, warp-specialised tcgen05 + TMA GEMM for sm_100a.
+//
+// Replaces the cuBLAS calls behind nn.Linear forward/backward for input_proj, W_fused and
+// output_proj (lucyrnn.py:15, 23, 85; 113, 116, 186).  One kernel template serves the three
+// contractions of a linear layer, all written as  D[i,j] = sum_r A(i,r) * B(j,r):
+//   fwd   : i=m, j=n, r=k   A = X  [m,k] (K-major)    B = W  [n,k] (K-major)   D = Y  (+bias[j])
+//   dgrad : i=m, j=k, r=n   A = dY [m,n] (K-major)    B = W  [n,k] (MN-major)  D = dX
+//   wgrad : i=n, j=k, r=m   A = dY [m,n] (MN-major)   B = X  [m,k] (MN-major)  D = dW (fp32, split-R)
+// "MN-major" operands are consumed straight from their row-major activation layout through
+// the UMMA descriptor's major bit — no transposed copies of activations are ever made.
+//
+// Structure per CTA (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer — cp.async.bulk.tensor 128B-swizzled tiles into a 4-stage ring
+//   warp 1   : MMA issuer   — one thread issues tcgen05.mma (M=128, N=256, K=16, bf16->fp32)
+//              into one of two 256-column TMEM accumulator stages; tcgen05.commit releases
+//              smem stages / publishes the accumulator through mbarriers
+//   warps 2-5: epilogue     — tcgen05.ld (32 lanes x 32 columns per instruction), bias add,
+//              bf16/fp32 conversion, 16-byte global stores (or fp32 red.add for split-R wgrad)
+// The epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM).
 #include "sc_common.cuh"
+#include <cuda.h>
+
 namespace sc {
-bool tc_gemm_fwd_ok(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const void*, const void*, const void*) { return false; }
-int tc_gemm_fwd(const void*, int64_t, const void*, int64_t, const float*, void*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t) { return SC_E_UNSUP; }
-bool tc_gemm_dgrad_ok(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const void*, const void*, const void*) { return false; }
-int tc_gemm_dgrad(const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t) { return SC_E_UNSUP; }
-bool tc_gemm_wgrad_ok(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, const void*, const void*, const void*) { return false; }
-int tc_gemm_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t) { return SC_E_UNSUP; }
+
+constexpr int TM = 128;          // tile rows   (UMMA M)
+constexpr int TN = 256;          // tile cols   (UMMA N)
+constexpr int TK = 64;           // reduction elements per stage = one 128-byte swizzle row
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * TK * 2;              // 16 KB
+constexpr int B_BYTES = TN * TK * 2;              // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ATOM_BYTES = TK * 128;              // one [TK x 64-element] MN-major box = 8 KB
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---------------------------------------------------------------- PTX wrappers -------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error surfaces through the C-ABI return code)
+// instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
+//   [46,48) version = 1 (sm_100)   [61,64) layout type = 2 (SWIZZLE_128B)
+// K-major tile  [rows][64 elems] : 8-row atoms of 1024 B stacked along rows -> SBO = 1024, LBO unused.
+// MN-major tile : boxes of [TK rows][64 elems]; SBO = 1024 (next 8 reduction rows),
+//                 LBO = ATOM_BYTES (next 64 elements along M/N = next TMA box).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct GemmParams {
+  int64_t I, J, R;          // output rows, output cols, reduction length
+  int tiles_i, tiles_j, splits, kb_per_split, kb_total;
+  void* D; int64_t ldd;
+  const float* bias;
+};
+
+// EPI: 0 = bf16 store (+bias), 1 = fp32 store (+bias), 2 = fp32 atomic accumulate (split-R)
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024-B aligned tiles
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then tmem ptr
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int64_t total = (int64_t)p.tiles_i * p.tiles_j * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = (int)(w % p.splits);
+        const int64_t tile = w / p.splits;
+        const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(full(stage), STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &mapA, full(stage), kb * TK, ti * TM);
+          } else {
+#pragma unroll
+            for (int a = 0; a < TM / 64; ++a) tma_load_2d(sa + a * ATOM_BYTES, &mapA, full(stage), ti * TM + a * 64, kb * TK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &mapB, full(stage), kb * TK, tj * TN);
+          } else {
+#pragma unroll
+            for (int b = 0; b < TN / 64; ++b) tma_load_2d(sb + b * ATOM_BYTES, &mapB, full(stage), tj * TN + b * 64, kb * TK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+      // a_major bit15, b_major bit16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = (int)(w % p.splits);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(tempty(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TK / UK; ++k) {
+            const uint64_t ad = A_MN ? make_desc(sa + k * UK * 128, ATOM_BYTES, 1024)
+                                     : make_desc(sa + k * UK * 2, 0, 1024);
+            const uint64_t bd = B_MN ? make_desc(sb + k * UK * 128, ATOM_BYTES, 1024)
+                                     : make_desc(sb + k * UK * 2, 0, 1024);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty(stage));                    // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull(acc));                        // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                             // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      const int64_t tile = w / p.splits;
+      const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)ti * TM + q * 32 + lane;
+      const int64_t col0 = (int64_t)tj * TN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
+#pragma unroll 1
+      for (int c = 0; c < TN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int64_t col = col0 + c * 32;
+        if (row < p.I && col < p.J) {
+          if (EPI == 0) {
+            bf16* out = reinterpret_cast<bf16*>(p.D) + row * p.ldd + col;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              if (col + v * 8 < p.J) {                  // J is a multiple of 8
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+                  if (p.bias) { f0 += __ldg(p.bias + col + v * 8 + 2 * e); f1 += __ldg(p.bias + col + v * 8 + 2 * e + 1); }
+                  __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(out + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          } else if (EPI == 1) {
+            float* out = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              if (col + v * 4 < p.J) {                  // J is a multiple of 4
+                float4 o;
+                o.x = __uint_as_float(r[v * 4 + 0]); o.y = __uint_as_float(r[v * 4 + 1]);
+                o.z = __uint_as_float(r[v * 4 + 2]); o.w = __uint_as_float(r[v * 4 + 3]);
+                if (p.bias) {
+                  o.x += __ldg(p.bias + col + v * 4 + 0); o.y += __ldg(p.bias + col + v * 4 + 1);
+                  o.z += __ldg(p.bias + col + v * 4 + 2); o.w += __ldg(p.bias + col + v * 4 + 3);
+                }
+                *reinterpret_cast<float4*>(out + v * 4) = o;
+              }
+            }
+          } else {
+            float* out = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
+#pragma unroll
+            for (int v = 0; v < 32; ++v)
+              if (col + v < p.J) atomicAdd(out + v, __uint_as_float(r[v]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major matrix [rows, cols] (cols contiguous, row stride ld
+// elements) with a [box_rows x 64-element] box and 128-byte swizzle; OOB reads return zeros.
+static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static bool tc_common_ok(const void* a, const void* b, const void* d, int64_t lda, int64_t ldb, int64_t ldd,
+                         int64_t I, int64_t J, int64_t R, int d_align_elems) {
+  if (I < 1 || J < 8 || R < 8) return false;
+  if ((lda % 8) || (ldb % 8) || (ldd % d_align_elems) || (J % 8)) return false;
+  if (!aligned16(a) || !aligned16(b) || !aligned16(d)) return false;
+  if (I >= ((int64_t)1 << 31) || J >= ((int64_t)1 << 31) || R >= ((int64_t)1 << 31)) return false;
+  // worth the fixed cost only when a tile is reasonably filled
+  return I * J >= 64 * 64 && get_encode() != nullptr;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                     const float* bias, int64_t I, int64_t J, int64_t R, int splits, cudaStream_t st) {
+  CUtensorMap mapA, mapB;
+  bool ok = A_MN ? make_map(&mapA, A, R, I, lda, TK) : make_map(&mapA, A, I, R, lda, TM);
+  ok = ok && (B_MN ? make_map(&mapB, B, R, J, ldb, TK) : make_map(&mapB, B, J, R, ldb, TN));
+  if (!ok) return SC_E_UNSUP;
+  GemmParams p;
+  p.I = I; p.J = J; p.R = R;
+  p.tiles_i = (int)cdiv(I, TM); p.tiles_j = (int)cdiv(J, TN);
+  p.kb_total = (int)cdiv(R, TK);
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (int)cdiv(p.kb_total, splits);
+  p.splits = (int)cdiv(p.kb_total, p.kb_per_split);
+  p.D = D; p.ldd = ldd; p.bias = bias;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int64_t total = (int64_t)p.tiles_i * p.tiles_j * p.splits;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  SC_LAUNCH_RET();
+}
+
+__global__ void zero2d_kernel(float* __restrict__ p, int64_t ld, int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[(i / cols) * ld + (i % cols)] = 0.f;
+}
+
+bool tc_gemm_fwd_ok(int64_t lda, int64_t ldw, int64_t ldy, int64_t M, int64_t N, int64_t K, int in_dtype,
+                    int out_dtype, const void* A, const void* W, const void* Y) {
+  if (in_dtype != SC_BF16) return false;
+  return tc_common_ok(A, W, Y, lda, ldw, ldy, M, N, K, out_dtype == SC_BF16 ? 8 : 4);
+}
+int tc_gemm_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* Y, int64_t ldy,
+                int64_t M, int64_t N, int64_t K, int out_dtype, cudaStream_t st) {
+  if (out_dtype == SC_BF16) return launch_tc<false, false, 0>(A, lda, W, ldw, Y, ldy, bias, M, N, K, 1, st);
+  return launch_tc<false, false, 1>(A, lda, W, ldw, Y, ldy, bias, M, N, K, 1, st);
+}
+
+bool tc_gemm_dgrad_ok(int64_t lddy, int64_t ldw, int64_t ldda, int64_t M, int64_t N, int64_t K, int in_dtype,
+                      int out_dtype, const void* dY, const void* W, const void* dA) {
+  if (in_dtype != SC_BF16) return false;
+  return tc_common_ok(dY, W, dA, lddy, ldw, ldda, M, K, N, out_dtype == SC_BF16 ? 8 : 4);
+}
+int tc_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dA, int64_t ldda,
+                  int64_t M, int64_t N, int64_t K, int out_dtype, cudaStream_t st) {
+  // dA[m,k] = sum_n dY[m,n] W[n,k] : A = dY (K-major over n), B(j=k, r=n) = W[n,k] (MN-major)
+  if (out_dtype == SC_BF16) return launch_tc<false, true, 0>(dY, lddy, W, ldw, dA, ldda, nullptr, M, K, N, 1, st);
+  return launch_tc<false, true, 1>(dY, lddy, W, ldw, dA, ldda, nullptr, M, K, N, 1, st);
+}
+
+bool tc_gemm_wgrad_ok(int64_t lddy, int64_t lda, int64_t lddw, int64_t M, int64_t N, int64_t K, int in_dtype,
+                      const void* dY, const void* A, const void* dW) {
+  if (in_dtype != SC_BF16) return false;
+  // N (rows of dW) comes from dY's columns via TMA: needs N % 8 for the map's 16-B row stride
+  return (N % 8 == 0) && tc_common_ok(dY, A, dW, lddy, lda, lddw, N, K, M, 1) && M >= 64;
+}
+int tc_gemm_wgrad(const void* dY, int64_t lddy, const void* A, int64_t lda, float* dW, int64_t lddw,
+                  int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
+  // dW[n,k] = sum_m dY[m,n] A[m,k] : both operands MN-major, reduction over m, split across CTAs
+  const int64_t tiles = cdiv(N, TM) * cdiv(K, TN);
+  const int64_t kb = cdiv(M, TK);
+  int64_t splits = cdiv(4 * num_sms(), tiles);            // ~4 work items per SM
+  if (splits > kb / 8) splits = kb / 8;                   // keep >= 8 k-blocks per item
+  if (splits < 1) splits = 1;
+  if (!accumulate)
+    zero2d_kernel<<<(unsigned)min((int64_t)2048, cdiv(N * K, 256)), 256, 0, st>>>(dW, lddw, N, K);
+  return launch_tc<true, true, 2>(dY, lddy, A, lda, dW, lddw, nullptr, N, K, M, (int)splits, st);
+}
+
+}  // namespace sc
