@@ -46,7 +46,7 @@ extern "C" {
 #define SC_GATE_P 3   /* 'h_pre' chunk */
 #define SC_GATE_Q 4   /* decay logits  */
 
-#define SC_SCAN_CKPT 16  /* timesteps between saved S checkpoints of the fused scan */
+#define SC_SCAN_CKPT 8   /* timesteps between saved S checkpoints of the fused scan */
 
 int sc_version(void);                    /* ABI version, bumps on any signature change */
 const char* sc_error_string(int code);   /* static string for an SC_E_* / cudaError_t  */
@@ -76,9 +76,15 @@ int64_t sc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 /* ---------------------------------------------------------------- row-wise helpers ---
  * cast  : dst[i] = (dst_dtype) src[i] over a [rows, cols] matrix with row strides.
  * colsum: out[n] (+)= sum_m X[m,n]   (bias gradients), fp32 out.
- * layernorm fwd/bwd over the last dim H: nn.LayerNorm(H) of lucyrnn.py:17-20 (eps 1e-5). */
+ * layernorm fwd/bwd over the last dim H: nn.LayerNorm(H) of lucyrnn.py:17-20 (eps 1e-5);
+ * the backward ADDS into dw/db (caller zeroes them). */
 int sc_cast(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd, int dst_dtype,
             int64_t rows, int64_t cols, void* stream);
+/* split: dst[r, c] = bf16(src[r,c]), dst[r, cols + c] = bf16(src[r,c] - dst[r,c]); dst is
+ * bf16 [rows, 2*cols] (row stride ldd).  Used to push fp32 weight-space products through
+ * the bf16 tensor-core GEMM without losing the low mantissa bits (projection folding). */
+int sc_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols,
+                  void* stream);
 int sc_colsum(const void* X, int64_t ldx, int dtype, float* out, int64_t M, int64_t N,
               int accumulate, void* stream);
 int sc_layernorm_fwd(const void* X, int64_t ldx, const float* w, const float* b,

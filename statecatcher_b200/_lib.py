@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libstatecatcher_b200.so")
 
 SC_F32, SC_BF16 = 0, 1
-SC_SCAN_CKPT = 16
+SC_SCAN_CKPT = 8
 
 P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
 
@@ -31,6 +31,7 @@ SIGNATURES = {
     "sc_gemm_wgrad": [P, I64, P, I64, P, I64, I64, I64, I64, I32, I32, I32, P],
     "sc_gemm_workspace_bytes": [I64, I64, I64],
     "sc_cast": [P, I64, I32, P, I64, I32, I64, I64, P],
+    "sc_split_bf16": [P, I64, P, I64, I64, I64, P],
     "sc_colsum": [P, I64, I32, P, I64, I64, I32, P],
     "sc_layernorm_fwd": [P, I64, P, P, P, I64, P, P, I64, I64, I32, P],
     "sc_layernorm_bwd": [P, I64, P, I64, P, P, P, P, I64, P, P, I64, I64, I32, P],

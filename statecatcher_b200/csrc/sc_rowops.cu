@@ -15,6 +15,21 @@ __global__ void cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __restr
   }
 }
 
+// hi = bf16(x), lo = bf16(x - hi): a two-term bf16 expansion (16 mantissa bits) of an fp32
+// matrix, written side by side as [rows, 2*cols] so one bf16 tensor-core GEMM over the
+// doubled reduction dimension reproduces the fp32 product to ~1e-5.
+__global__ void split_bf16_kernel(const float* __restrict__ src, int64_t lds, bf16* __restrict__ dst, int64_t ldd,
+                                  int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    const float x = src[r * lds + c];
+    const bf16 hi = __float2bfloat16_rn(x);
+    dst[r * ldd + c] = hi;
+    dst[r * ldd + cols + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
+  }
+}
+
 __global__ void zero_kernel(float* __restrict__ p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
@@ -183,5 +198,15 @@ extern "C" int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int
     layernorm_bwd_kernel<bf16><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const bf16*)dY, lddy, (const bf16*)X, ldx, w, mean, rstd,
         (bf16*)dX, lddx, dw, db, M, (int)H, rpb);
   } else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols,
+                             void* stream) {
+  SC_CHECK_ARG(rows >= 0 && cols >= 0, SC_E_BADARG);
+  if (rows * cols == 0) return 0;
+  SC_CHECK_ARG(src && dst && ldd >= 2 * cols, SC_E_BADARG);
+  const unsigned blocks = (unsigned)min((int64_t)148 * 16, cdiv(rows * cols, 256));
+  split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, rows, cols);
   SC_LAUNCH_RET();
 }

@@ -13,6 +13,7 @@
 // The backward recomputes S inside SC_SCAN_CKPT-step intervals from checkpoints the forward
 // leaves behind instead of storing S for every timestep.
 #include "sc_common.cuh"
+#include <stdlib.h>
 
 namespace sc {
 
@@ -430,7 +431,20 @@ static int launch_scan_bwd(const void* G, int64_t ldg, const void* Hout, int64_t
 
 }  // namespace sc
 
+namespace sc {
+int scan_fwd_tma_dispatch(const void*, int64_t, const float*, const float*, void*, int64_t, float*, float*, float*,
+                          int64_t, int64_t, int64_t, int, int, cudaStream_t);
+int scan_bwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const float*, const float*, const void*, int64_t,
+                          void*, int64_t, float*, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+}
 using namespace sc;
+
+// SC_SCAN_GENERIC=1 in the environment forces the register-prefetch kernels (A/B measurements)
+static bool scan_force_generic() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SC_SCAN_GENERIC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 
 static bool scan_args_ok(int64_t B, int64_t T, int64_t H) {
   return B > 0 && T >= 0 && H > 0 && B * T < (int64_t)1 << 31 && H < (1 << 24);
@@ -444,6 +458,10 @@ extern "C" int sc_lucy_scan_fwd(const void* G, int64_t ldg, const float* h0, con
   SC_CHECK_ARG(scan_args_ok(B, T, H), SC_E_SHAPE);
   SC_CHECK_ARG(T == 0 || (G && Hout), SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!scan_force_generic() && Sckpt != nullptr) {
+    const int rc = scan_fwd_tma_dispatch(G, ldg, h0, s0, Hout, ldh, hT, sT, Sckpt, B, T, H, dtype, train_mode, st);
+    if (rc != SC_E_UNSUP) return rc;
+  }
   if (dtype == SC_BF16) {
     SC_CHECK_ARG(H % 2 == 0 && ldg % 2 == 0 && ldh % 2 == 0, SC_E_ALIGN);
     SC_CHECK_ARG(((uintptr_t)G & 3) == 0 && ((uintptr_t)Hout & 3) == 0, SC_E_ALIGN);
@@ -464,6 +482,10 @@ extern "C" int sc_lucy_scan_bwd(const void* G, int64_t ldg, const void* Hout, in
   if (T == 0) return 0;
   SC_CHECK_ARG(G && Hout && dHout && dG, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!scan_force_generic()) {
+    const int rc = scan_bwd_tma_dispatch(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, dtype, train_mode, st);
+    if (rc != SC_E_UNSUP) return rc;
+  }
   if (dtype == SC_BF16) {
     SC_CHECK_ARG(H % 2 == 0 && ldg % 2 == 0 && ldh % 2 == 0 && lddh % 2 == 0 && lddg % 2 == 0, SC_E_ALIGN);
     SC_CHECK_ARG((((uintptr_t)G | (uintptr_t)Hout | (uintptr_t)dHout | (uintptr_t)dG) & 3) == 0, SC_E_ALIGN);

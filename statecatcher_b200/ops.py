@@ -69,6 +69,14 @@ def cast(src: torch.Tensor, dtype, out: Optional[torch.Tensor] = None) -> torch.
     return out.view(src.shape) if out.dim() != src.dim() else out
 
 
+def split_bf16(src: torch.Tensor) -> torch.Tensor:
+    """fp32 [R,C] -> bf16 [R,2C] = [hi | lo] two-term expansion."""
+    R, C = src.shape
+    out = torch.empty(R, 2 * C, dtype=torch.bfloat16, device=src.device)
+    call("sc_split_bf16", ptr(src), _ld(src), ptr(out), 2 * C, R, C, stream())
+    return out
+
+
 def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
     M, N = x.shape
     if out is None:

@@ -112,7 +112,7 @@ def _scan_reference(G, h0, s0, training, g_out):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("training", [True, False], ids=["train", "step"])
-@pytest.mark.parametrize("B,T,H", [(1, 1, 8), (3, 17, 24), (2, 48, 64), (5, 100, 40)])
+@pytest.mark.parametrize("B,T,H", [(1, 1, 8), (3, 17, 24), (2, 48, 64), (5, 100, 40), (2, 37, 12), (2, 37, 6), (3, 70, 520)])
 def test_fused_scan_fwd_bwd(cuda_device, dtype, training, B, T, H):
     ops = _ops()
     g = torch.Generator().manual_seed(B * 1000 + T)
