@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--layer-norm", action="store_true", help="layer_norm=True variant (general path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="per-call timing table of the last timed step on stderr")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -313,11 +314,17 @@ def main():
     pk = peaks()
     e = 2 if cd == torch.bfloat16 else 4
     fam = {}
-    for name, work, ev0, ev1 in prof:
+    for name, work, ev0, ev1, _shape in prof:
         d = fam.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0})
         d["ms"] += ev0.elapsed_time(ev1)
         d["work"] += work
         d["n"] += 1
+    if args.detail:
+        per_step = len(prof) // args.steps
+        for name, work, ev0, ev1, shape in prof[-per_step:]:
+            t = ev0.elapsed_time(ev1)
+            rate = (work / (t * 1e-3) / 1e12) if t > 0 else 0
+            print(f"  {name:20s} {str(shape):28s} {t:8.3f} ms  {rate:8.1f} T(FLOP|B)/s", file=sys.stderr)
     live_frames = sum(sum(min(t, W["T"]) for t in h[2]) for h in host) / NSEG
     umean = sum(sum(h[3]) for h in host) / NSEG / W["B"]
 

@@ -133,6 +133,14 @@ def _work(name, a):
     return 0.0
 
 
+def _shape(name, a):
+    if name == "sc_gemm_fwd":
+        return (a[7], a[8], a[9])
+    if name in ("sc_gemm_dgrad", "sc_gemm_wgrad"):
+        return (a[6], a[7], a[8])
+    return ()
+
+
 def call(name: str, *args):
     global launches, kernels
     launches += 1
@@ -147,4 +155,4 @@ def call(name: str, *args):
     rc = fn(*args)
     e1.record()
     check(rc, name)
-    profile.append((name, _work(name, args), e0, e1))
+    profile.append((name, _work(name, args), e0, e1, _shape(name, args)))

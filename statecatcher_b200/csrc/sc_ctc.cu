@@ -38,7 +38,8 @@ __device__ __forceinline__ int64_t ext_label(const int64_t* tg, int s, int64_t b
 }
 
 constexpr int CTC_WARPS = 8;
-constexpr int CTC_RENORM = 16;   // alpha/beta columns are re-centred every this many steps
+constexpr int CTC_RENORM = 16;
+constexpr int CTC_PF = 8;        // emission prefetch depth of the alpha/beta recursion   // alpha/beta columns are re-centred every this many steps
 
 // ---- pass 1 ------------------------------------------------------------------------
 template <typename T>
@@ -142,24 +143,24 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
   // offsets only matter for the likelihood (summed in double); the gradient pass normalises
   // each frame's occupancies itself (sum_s exp(alpha+beta-lp) is the same for every t).
   double csum = 0.0;
-  for (int i = 1; i < Tb; ++i) {
-    const int t = t_first + i * step;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      const float e = lp_b[(int64_t)t * Smax + s];
-      float v;
-      if (dir == 0) {
-        bool skip = false;
-        if ((s & 1) && s >= 2) skip = tg[s >> 1] != tg[(s >> 1) - 1];
-        v = lse3(prev[s], prev[s - 1], skip ? prev[s - 2] : NEG_INF) + e;
-      } else {
-        bool skip = false;
-        if ((s & 1) && s + 2 < S) skip = tg[s >> 1] != tg[(s >> 1) + 1];
-        const float p1 = (s + 1 < S) ? prev[s + 1] : NEG_INF;
-        const float p2 = (skip && s + 2 < S) ? prev[s + 2] : NEG_INF;
-        v = lse3(prev[s], p1, p2) + e;
-      }
-      cur[s] = v;
+  // one lattice step for node s with emission e (reads prev, writes cur)
+  auto node = [&](int s, float e) {
+    float v;
+    if (dir == 0) {
+      bool skip = false;
+      if ((s & 1) && s >= 2) skip = tg[s >> 1] != tg[(s >> 1) - 1];
+      v = lse3(prev[s], prev[s - 1], skip ? prev[s - 2] : NEG_INF) + e;
+    } else {
+      bool skip = false;
+      if ((s & 1) && s + 2 < S) skip = tg[s >> 1] != tg[(s >> 1) + 1];
+      const float p1 = (s + 1 < S) ? prev[s + 1] : NEG_INF;
+      const float p2 = (skip && s + 2 < S) ? prev[s + 2] : NEG_INF;
+      v = lse3(prev[s], p1, p2) + e;
     }
+    cur[s] = v;
+  };
+  // re-centre the freshly written column (every CTC_RENORM steps), publish it, flip buffers
+  auto finish = [&](int i, int t) {
     if ((i % CTC_RENORM) == 0) {
       float m = NEG_INF;
       for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, cur[s]);   // own nodes only
@@ -176,6 +177,37 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     for (int s = threadIdx.x; s < S; s += blockDim.x) out_b[(int64_t)t * Smax + s] = cur[s];
     __syncthreads();
     float* tmp = prev; prev = cur; cur = tmp;
+  };
+  if (S <= (int)blockDim.x) {
+    // one node per thread: the emission stream is independent of the recursion, so it is
+    // prefetched CTC_PF steps ahead into registers and the serial chain never waits on HBM
+    const int s = threadIdx.x;
+    const bool has = s < S;
+    float ring[CTC_PF];
+#pragma unroll
+    for (int j = 0; j < CTC_PF; ++j) {
+      const int i = 1 + j;
+      ring[j] = (has && i < Tb) ? __ldg(lp_b + (int64_t)(t_first + i * step) * Smax + s) : 0.f;
+    }
+    for (int i0 = 1; i0 < Tb; i0 += CTC_PF) {
+#pragma unroll
+      for (int j = 0; j < CTC_PF; ++j) {
+        const int i = i0 + j;
+        if (i < Tb) {
+          const float e = ring[j];
+          const int ip = i + CTC_PF;
+          ring[j] = (has && ip < Tb) ? __ldg(lp_b + (int64_t)(t_first + ip * step) * Smax + s) : 0.f;
+          if (has) node(s, e);
+          finish(i, t_first + i * step);
+        }
+      }
+    }
+  } else {
+    for (int i = 1; i < Tb; ++i) {
+      const int t = t_first + i * step;
+      for (int s = threadIdx.x; s < S; s += blockDim.x) node(s, lp_b[(int64_t)t * Smax + s]);
+      finish(i, t);
+    }
   }
   if (dir == 0 && threadIdx.x == 0) {
     const float ll = lse2(prev[S - 1], S > 1 ? prev[S - 2] : NEG_INF);

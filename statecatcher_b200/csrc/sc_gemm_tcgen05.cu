@@ -9,12 +9,13 @@
 // "MN-major" operands are consumed straight from their row-major activation layout through
 // the UMMA descriptor's major bit — no transposed copies of activations are ever made.
 //
-// Structure per CTA (one persistent CTA per SM, 192 threads):
+// Structure per CTA (one persistent CTA per SM, 320 threads):
 //   warp 0   : TMA producer — cp.async.bulk.tensor 128B-swizzled tiles into a 4-stage ring
 //   warp 1   : MMA issuer   — one thread issues tcgen05.mma (M=128, N=256, K=16, bf16->fp32)
 //              into one of two 256-column TMEM accumulator stages; tcgen05.commit releases
 //              smem stages / publishes the accumulator through mbarriers
-//   warps 2-5: epilogue     — tcgen05.ld (32 lanes x 32 columns per instruction), bias add,
+//   warps 2-9: epilogue     — tcgen05.ld (32 lanes x 32 columns per instruction), bias add
+//              from a shared-memory copy staged once per tile,
 //              bf16/fp32 conversion, 16-byte global stores (or fp32 red.add for split-R wgrad)
 // The epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM).
 #include "sc_common.cuh"
@@ -31,8 +32,9 @@ constexpr int A_BYTES = TM * TK * 2;              // 16 KB
 constexpr int B_BYTES = TN * TK * 2;              // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ATOM_BYTES = TK * 128;              // one [TK x 64-element] MN-major box = 8 KB
-constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                     // two warps per TMEM lane quarter, 128 columns each
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * TN * 4 /*bias*/;
 constexpr uint32_t TMEM_COLS = 512;
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
@@ -79,7 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -158,24 +160,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                   // which 128-column half of the tile
+    const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
+    float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
       const int64_t tile = w / p.splits;
       const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      const int64_t col0 = (int64_t)tj * TN;
+      if (EPI != 2 && p.bias != nullptr) {
+        // stage this tile's bias once (double-buffered with the accumulator stage)
+        sbias[acc * TN + et] = (col0 + et < p.J) ? __ldg(p.bias + col0 + et) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      }
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const int64_t row = (int64_t)ti * TM + q * 32 + lane;
-      const int64_t col0 = (int64_t)tj * TN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
 #pragma unroll 1
-      for (int c = 0; c < TN / 32; ++c) {
+      for (int cc = 0; cc < TN / 64; ++cc) {
+        const int c = half * (TN / 64) + cc;
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
         const int64_t col = col0 + c * 32;
         if (row < p.I && col < p.J) {
+          if (EPI != 2 && p.bias != nullptr) {
+            const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 b4 = bv[v];
+              r[v * 4 + 0] = __float_as_uint(__uint_as_float(r[v * 4 + 0]) + b4.x);
+              r[v * 4 + 1] = __float_as_uint(__uint_as_float(r[v * 4 + 1]) + b4.y);
+              r[v * 4 + 2] = __float_as_uint(__uint_as_float(r[v * 4 + 2]) + b4.z);
+              r[v * 4 + 3] = __float_as_uint(__uint_as_float(r[v * 4 + 3]) + b4.w);
+            }
+          }
           if (EPI == 0) {
             bf16* out = reinterpret_cast<bf16*>(p.D) + row * p.ldd + col;
 #pragma unroll
@@ -184,9 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-                  if (p.bias) { f0 += __ldg(p.bias + col + v * 8 + 2 * e); f1 += __ldg(p.bias + col + v * 8 + 2 * e + 1); }
-                  __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
                   pk[e] = *reinterpret_cast<uint32_t*>(&h);
                 }
                 *reinterpret_cast<uint4*>(out + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -197,14 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               if (col + v * 4 < p.J) {                  // J is a multiple of 4
-                float4 o;
-                o.x = __uint_as_float(r[v * 4 + 0]); o.y = __uint_as_float(r[v * 4 + 1]);
-                o.z = __uint_as_float(r[v * 4 + 2]); o.w = __uint_as_float(r[v * 4 + 3]);
-                if (p.bias) {
-                  o.x += __ldg(p.bias + col + v * 4 + 0); o.y += __ldg(p.bias + col + v * 4 + 1);
-                  o.z += __ldg(p.bias + col + v * 4 + 2); o.w += __ldg(p.bias + col + v * 4 + 3);
-                }
-                *reinterpret_cast<float4*>(out + v * 4) = o;
+                *reinterpret_cast<float4*>(out + v * 4) =
+                    make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
+                                __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
               }
             }
           } else {

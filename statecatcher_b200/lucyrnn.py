@@ -209,18 +209,26 @@ class _LucyLayerFn(torch.autograd.Function):
     # forward and the same ratio backward; `u` is never materialised.  The backward maps the
     # gradient of Wc back onto W_fused / input_proj exactly (chain rule in weight space, the
     # fp32 dWc carried through the bf16 tensor cores as a two-term hi/lo expansion).
+    # The bias rides along as one extra input column: with x_ext = [x | 1] and
+    # Win_ext = [W_in | b_in | 0..] (padded to a multiple of 8 columns for TMA alignment),
+    # Wc_ext = Wf . Win_ext holds Wc in its first `in` columns and Wf b_in in column `in`, and
+    # the same extension makes the backward's weight-space GEMMs produce db_in and the
+    # dbc (x) b_in outer-product term of dWf with no separate matrix-vector kernels.
     @staticmethod
     def _forward_folded(ctx, meta, x2, h0, s0, p, B, T, Fin):
         H, cd = meta.H, meta.dtype
-        Wf32 = p("W_fused.weight").detach()[H:]
-        Wfb = _w(Wf32, cd)                                            # [5H,H]  bf16
-        Winb = _w(p("input_proj.weight"), cd)                         # [H,in]  bf16
-        Wc = ops.gemm_dgrad(Wfb, Winb)                                # [5H,in] = Wf . W_in
-        bc = ops.gemm_fwd(p("input_proj.bias").detach().view(1, H), Wf32,
-                          p("W_fused.bias").detach()[H:]).view(-1)    # Wf b_in + bf  (fp32)
+        dev = x2.device
+        PADC = 8
+        Wfb = _w(p("W_fused.weight").detach()[H:], cd)                # [5H,H]  bf16
+        Win_ext = torch.zeros(H, Fin + PADC, dtype=cd, device=dev)    # [W_in | b_in | 0]
+        ops.cast(p("input_proj.weight").detach(), cd, out=Win_ext[:, :Fin])
+        ops.cast(p("input_proj.bias").detach().view(H, 1), cd, out=Win_ext[:, Fin:Fin + 1])
+        Wc_ext = ops.gemm_dgrad(Wfb, Win_ext, out_dtype=torch.float32)  # [5H, in+8] = Wf . Win_ext
+        Wc = ops.cast(Wc_ext[:, :Fin], cd)                            # [5H,in] bf16, contiguous
+        bc = Wc_ext[:, Fin] + p("W_fused.bias").detach()[H:]          # Wf b_in + bf  (fp32)
         G = ops.gemm_fwd(x2, Wc, bc)                                  # [M,5H]
         Hout, hT, sT, ck = ops.scan_fwd(G, B, T, H, h0, s0, meta.train_mode)
-        ctx.save_for_backward(x2, G, Hout, h0, s0, ck, Wc, Wfb, Winb, Wf32, p("input_proj.bias").detach())
+        ctx.save_for_backward(x2, G, Hout, h0, s0, ck, Wc, Wfb, Win_ext)
         ctx.meta, ctx.sv, ctx.shape = meta, {}, (B, T, Fin)
         if sT is None:
             sT = h0.new_empty(0)
@@ -232,25 +240,27 @@ class _LucyLayerFn(torch.autograd.Function):
         meta = ctx.meta
         B, T, Fin = ctx.shape
         H = meta.H
-        x2, G, Hout, h0, s0, ck, Wc, Wfb, Winb, Wf32, b_in = ctx.saved_tensors
+        x2, G, Hout, h0, s0, ck, Wc, Wfb, Win_ext = ctx.saved_tensors
         dev = g2.device
+        E = Win_ext.shape[1]                                          # in + pad
         grads = [None] * len(meta.names)
         gi = meta.index
         dG, dbg = ops.scan_bwd(G, Hout, h0, s0, ck, g2, B, T, H, meta.train_mode)
-        dWc = ops.gemm_wgrad(dG, x2)                                  # [5H,in] fp32
+        dWc_ext = torch.zeros(5 * H, E, dtype=torch.float32, device=dev)   # [dWc | dbc | 0]
+        ops.gemm_wgrad(dG, x2, out=dWc_ext[:, :Fin], accumulate=True)
+        dWc_ext[:, Fin].copy_(dbg)
         dx = ops.gemm_dgrad(dG, Wc).view(B, T, Fin) if ctx.needs_input_grad[1] else None
-        hl = ops.split_bf16(dWc)                                      # [5H, 2in] = [hi | lo]
-        Win2 = torch.cat([Winb, Winb], dim=1)                         # [H, 2in]
+        hl = ops.split_bf16(dWc_ext)                                  # [5H, 2E] = [hi | lo]
+        Win2 = torch.cat([Win_ext, Win_ext], dim=1)                   # [H, 2E]
         dWf = torch.empty(6 * H, H, dtype=torch.float32, device=dev)
         dWf[:H].zero_()                                               # dead r gate: exact zeros
-        ops.gemm_fwd(hl, Win2, None, out=dWf[H:])                     # dWc . W_in^T
-        dWf[H:].addr_(dbg, b_in)                                      # + d(bc)/dWf = dbc (x) b_in
-        both = ops.gemm_wgrad(Wfb, hl)                                # Wf^T [hi|lo] -> [H, 2in]
+        ops.gemm_fwd(hl, Win2, None, out=dWf[H:])                     # dWc W_in^T + dbc (x) b_in
+        both = ops.gemm_wgrad(Wfb, hl)                                # Wf^T [hi|lo] -> [H, 2E]
         dbf = torch.zeros(6 * H, dtype=torch.float32, device=dev)
         dbf[H:].copy_(dbg)
         grads[gi["W_fused.weight"]], grads[gi["W_fused.bias"]] = dWf, dbf
-        grads[gi["input_proj.weight"]] = both[:, :Fin] + both[:, Fin:]
-        grads[gi["input_proj.bias"]] = ops.gemm_dgrad(dbg.view(1, -1), Wf32).view(-1)   # Wf^T dbc
+        grads[gi["input_proj.weight"]] = both[:, :Fin] + both[:, E:E + Fin]
+        grads[gi["input_proj.bias"]] = both[:, Fin] + both[:, E + Fin]
         return (None, dx, None, None, *grads)
 
     @staticmethod
