@@ -144,18 +144,21 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
   // each frame's occupancies itself (sum_s exp(alpha+beta-lp) is the same for every t).
   double csum = 0.0;
   // one lattice step for node s with emission e (reads prev, writes cur)
-  auto node = [&](int s, float e) {
+  // skip transition s-2 -> s (alpha) / s+2 -> s (beta) is a per-node constant: allowed iff
+  // l'_s is a label that differs from the label two nodes away
+  auto skip_ok = [&](int s) -> bool {
+    if (!(s & 1)) return false;
+    if (dir == 0) return s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1];
+    return s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1];
+  };
+  // one lattice step for node s with emission e (reads prev, writes cur)
+  auto node = [&](int s, float e, bool skip) {
     float v;
     if (dir == 0) {
-      bool skip = false;
-      if ((s & 1) && s >= 2) skip = tg[s >> 1] != tg[(s >> 1) - 1];
       v = lse3(prev[s], prev[s - 1], skip ? prev[s - 2] : NEG_INF) + e;
     } else {
-      bool skip = false;
-      if ((s & 1) && s + 2 < S) skip = tg[s >> 1] != tg[(s >> 1) + 1];
-      const float p1 = (s + 1 < S) ? prev[s + 1] : NEG_INF;
-      const float p2 = (skip && s + 2 < S) ? prev[s + 2] : NEG_INF;
-      v = lse3(prev[s], p1, p2) + e;
+      // pad cells right of S-1 hold -inf, so s+1 / s+2 need no bounds test
+      v = lse3(prev[s], prev[s + 1], skip ? prev[s + 2] : NEG_INF) + e;
     }
     cur[s] = v;
   };
@@ -183,6 +186,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     // prefetched CTC_PF steps ahead into registers and the serial chain never waits on HBM
     const int s = threadIdx.x;
     const bool has = s < S;
+    const bool skip = has && skip_ok(s);
     float ring[CTC_PF];
 #pragma unroll
     for (int j = 0; j < CTC_PF; ++j) {
@@ -197,7 +201,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
           const float e = ring[j];
           const int ip = i + CTC_PF;
           ring[j] = (has && ip < Tb) ? __ldg(lp_b + (int64_t)(t_first + ip * step) * Smax + s) : 0.f;
-          if (has) node(s, e);
+          if (has) node(s, e, skip);
           finish(i, t_first + i * step);
         }
       }
@@ -205,7 +209,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
   } else {
     for (int i = 1; i < Tb; ++i) {
       const int t = t_first + i * step;
-      for (int s = threadIdx.x; s < S; s += blockDim.x) node(s, lp_b[(int64_t)t * Smax + s]);
+      for (int s = threadIdx.x; s < S; s += blockDim.x) node(s, lp_b[(int64_t)t * Smax + s], skip_ok(s));
       finish(i, t);
     }
   }

@@ -127,3 +127,24 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src or f.endswith(".py") and "import" not in src.split("/root/reference")[0][-40:], f
+
+
+def test_shims_resolve_to_the_package():
+    """model.py:7-9 import lucyrnn / lucyrnn_conf / lucyrnn_triton by bare module name."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "shims"))
+    saved = {k: sys.modules.pop(k) for k in ("lucyrnn", "lucyrnn_conf", "lucyrnn_triton") if k in sys.modules}
+    try:
+        import statecatcher_b200 as sb
+        assert importlib.import_module("lucyrnn").LucyRNN is sb.LucyRNN
+        assert importlib.import_module("lucyrnn_conf").LucyRNNConfig is sb.LucyRNNConfig
+        tri = importlib.import_module("lucyrnn_triton").LucyRNNtriton
+        assert issubclass(tri, sb.LucyRNN)
+        m = tri(sb.LucyRNNConfig(80, 16, 1, 9, kernel_impl="triton", fused_ops=True, layer_norm=False))
+        assert m.config.kernel_impl == "triton"
+    finally:
+        sys.path.remove(os.path.join(ROOT, "shims"))
+        for k in ("lucyrnn", "lucyrnn_conf", "lucyrnn_triton"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
