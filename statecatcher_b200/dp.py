@@ -101,7 +101,7 @@ class StreamDataParallel(nn.Module):
         grads = [p.grad for p in b.params if p.grad is not None]
         if not grads:
             return
-        b.flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+        b.flat = torch.cat([g.reshape(-1) for g in grads])
         b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         self.n_allreduce += 1
 

@@ -1,0 +1,119 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic of the path — stream
+partitioning, bucketed asynchronous gradient all-reduce launched from post-accumulate-grad
+hooks, end-of-backward join, global-'mean' loss equivalence, no_sync accumulation.
+The wrapped module here is the CPU oracle network (tests may use oracle/); the CUDA module
+itself cannot run without a GPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from oracle import lucy_oracle as LO
+from statecatcher_b200.dp import StreamDataParallel, partition_streams
+
+
+def test_partition_streams():
+    assert [list(partition_streams(512, 8, r))[:1] + [len(partition_streams(512, 8, r))] for r in (0, 7)] == [[0, 64], [448, 64]]
+    parts = [partition_streams(10, 4, r) for r in range(4)]
+    assert sorted(i for p in parts for i in p) == list(range(10))
+    assert [len(p) for p in parts] == [3, 3, 2, 2]
+    with pytest.raises(ValueError):
+        partition_streams(4, 2, 2)
+
+
+class _OracleNet(nn.Module):
+    """LucyRNN + CTC on the CPU via the oracle's closed form, parameters as nn.Parameters
+    (including the dead W_r gate rows that never receive a gradient)."""
+
+    def __init__(self, cfg, seed):
+        super().__init__()
+        self.cfg = cfg
+        P = LO.random_params(cfg, seed, dtype=torch.float64)
+        self.names = list(P)
+        self.params = nn.ParameterList([nn.Parameter(P[k]) for k in self.names])
+
+    def forward(self, x, state=None):
+        P = dict(zip(self.names, self.params))
+        return LO.forward_closed(P, self.cfg, x, state)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        cfg = LO.OracleConfig(input_dim=6, hidden_dim=8, num_layers=2, vocab_size=7, fused_ops=False, layer_norm=True)
+        net = _OracleNet(cfg, 5)
+        ddp = StreamDataParallel(net, bucket_mb=0.0005)            # tiny buckets -> several all-reduces
+        assert len(ddp.buckets) > 3
+        g = torch.Generator().manual_seed(11)
+        B, T = 4, 9                                                # global batch: 4 streams, 2 per rank
+        xs = [torch.randn(B, T, 6, generator=g, dtype=torch.float64) for _ in range(2)]
+        toks = [torch.randint(1, 7, (B, 3), generator=g) for _ in range(2)]
+        inl, tgl = [T, T - 2, T, T], [3, 2, 3, 1]
+        mine = partition_streams(B, world, rank)
+        sl = slice(mine.start, mine.stop)
+        crit = nn.CTCLoss(blank=0, zero_infinity=True)
+        state = None
+        for i in range(2):                                         # two carried segments
+            if state:
+                state = LO.detach_states(state)
+            logits, state = ddp(xs[i][sl], state)
+            loss = crit(logits.log_softmax(-1).transpose(0, 1), toks[i][sl], inl[sl], tgl[sl])
+            loss.backward()                                        # grads accumulate over segments
+        assert ddp.n_allreduce >= 3
+        grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in zip(net.names, net.params)}
+        # no_sync: local accumulation only
+        for p in net.params:
+            p.grad = None
+        with ddp.no_sync():
+            logits, _ = ddp(xs[0][sl])
+            crit(logits.log_softmax(-1).transpose(0, 1), toks[0][sl], inl[sl], tgl[sl]).backward()
+        local_only = net.params[0].grad.clone()
+        if rank == 0:
+            torch.save({"grads": grads, "state_h": [t.detach() for t in state[0]], "local_only": local_only}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stream_data_parallel_matches_single_process(tmp_path):
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    # single process over the concatenated batch (reduction='mean' over the GLOBAL batch)
+    cfg = LO.OracleConfig(input_dim=6, hidden_dim=8, num_layers=2, vocab_size=7, fused_ops=False, layer_norm=True)
+    net = _OracleNet(cfg, 5)
+    g = torch.Generator().manual_seed(11)
+    B, T = 4, 9
+    xs = [torch.randn(B, T, 6, generator=g, dtype=torch.float64) for _ in range(2)]
+    toks = [torch.randint(1, 7, (B, 3), generator=g) for _ in range(2)]
+    inl, tgl = [T, T - 2, T, T], [3, 2, 3, 1]
+    crit = nn.CTCLoss(blank=0, zero_infinity=True)
+    state = None
+    for i in range(2):
+        if state:
+            state = LO.detach_states(state)
+        logits, state = net(xs[i], state)
+        crit(logits.log_softmax(-1).transpose(0, 1), toks[i], inl, tgl).backward()
+    for k, p in zip(net.names, net.params):
+        if p.grad is None:
+            assert got["grads"][k] is None, k                       # dead r-gate params stay grad-less
+            continue
+        torch.testing.assert_close(got["grads"][k], p.grad, rtol=1e-9, atol=1e-12, msg=k)
+    # rank 0 carried only ITS streams' state: equals rows 0..1 of the single-process state
+    for a, b in zip(got["state_h"], state[0]):
+        torch.testing.assert_close(a, b[:2].detach(), rtol=1e-9, atol=1e-12)
+    # no_sync grad differs from the synchronised one (it is the local shard's only)
+    assert not torch.allclose(got["local_only"], got["grads"][net.names[0]])
