@@ -91,12 +91,27 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
   const int S = 2 * (int)tgt_lens[b] + 1;
   const int64_t* tg = targets + (int64_t)b * ldt;
   float* out = lplat + row * Smax;
-  for (int s = lane; s < S; s += 32) out[s] = ld_f(x + ext_label(tg, s, blank)) - l;
+  // emissions in log2 units (the recursion runs on ex2/lg2 directly)
+  for (int s = lane; s < S; s += 32) out[s] = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
 }
 
 // ---- pass 2 ------------------------------------------------------------------------
 // dir 0 = alpha (forward in t), dir 1 = beta (backward in t).  Both include the emission of
-// their own timestep, as in the oracle (ctc_oracle.py) and ATen.
+// their own timestep, as in the oracle (ctc_oracle.py) and ATen.  Everything here is in
+// LOG2 units (lplat is written pre-scaled by log2(e)) so the serial chain is
+// LDS -> max -> ex2 -> add -> lg2 -> add -> STS -> barrier with no multiplies and no branches:
+// the first version spent ~1300 cycles per timestep in ~90 dependent SASS instructions
+// (profiles/r01_ncu_ctc_alpha_beta_hotlines_before.txt).
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// log2(2^a + 2^b + 2^c); all -inf in -> -inf out, without a branch
+__device__ __forceinline__ float lse3_2(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, fmaxf(b, c)), -1e30f);
+  return m + lg2f(ex2f(a - m) + ex2f(b - m) + ex2f(c - m));
+}
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
 __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
                                       const int64_t* __restrict__ targets, int64_t ldt,
                                       const int64_t* __restrict__ in_lens,
@@ -117,16 +132,22 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
     return;
   }
-  // per-thread skip permission for each owned node (nodes tid, tid+blockDim, ...)
   for (int i = threadIdx.x; i < 2 * LINE; i += blockDim.x) sm[i] = NEG_INF;
   __syncthreads();
   float* bufA = sm + 2;
   float* bufB = sm + LINE + 2;
   const float* lp_b = lplat + (int64_t)b * Tn * Smax;
   float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
-
   const int t_first = dir == 0 ? 0 : Tb - 1;
   const int step = dir == 0 ? 1 : -1;
+  const int nb = dir == 0 ? -1 : 1;   // neighbour direction: alpha looks at s-1,s-2; beta at s+1,s+2
+  // skip transition (two nodes away) is a per-node constant: allowed iff l'_s is a label that
+  // differs from the label two nodes away
+  auto skip_ok = [&](int s) -> bool {
+    if (!(s & 1)) return false;
+    if (dir == 0) return s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1];
+    return s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1];
+  };
   // init column
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     float v = NEG_INF;
@@ -136,86 +157,82 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     out_b[(int64_t)t_first * Smax + s] = v;
   }
   __syncthreads();
-  float* prev = bufA;
-  float* cur = bufB;
-  // Log-space values drift to magnitude ~T*log(V); every CTC_RENORM steps the column is
+  // Log-space values drift to magnitude ~T*log2(V); every CTC_RENORM steps the column is
   // re-centred on its maximum so fp32 keeps ~1e-6 absolute resolution for any T.  The removed
   // offsets only matter for the likelihood (summed in double); the gradient pass normalises
-  // each frame's occupancies itself (sum_s exp(alpha+beta-lp) is the same for every t).
+  // each frame's occupancies itself (sum_s 2^(alpha+beta-lp) is the same for every t).
   double csum = 0.0;
-  // one lattice step for node s with emission e (reads prev, writes cur)
-  // skip transition s-2 -> s (alpha) / s+2 -> s (beta) is a per-node constant: allowed iff
-  // l'_s is a label that differs from the label two nodes away
-  auto skip_ok = [&](int s) -> bool {
-    if (!(s & 1)) return false;
-    if (dir == 0) return s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1];
-    return s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1];
-  };
-  // one lattice step for node s with emission e (reads prev, writes cur)
-  auto node = [&](int s, float e, bool skip) {
-    float v;
-    if (dir == 0) {
-      v = lse3(prev[s], prev[s - 1], skip ? prev[s - 2] : NEG_INF) + e;
-    } else {
-      // pad cells right of S-1 hold -inf, so s+1 / s+2 need no bounds test
-      v = lse3(prev[s], prev[s + 1], skip ? prev[s + 2] : NEG_INF) + e;
-    }
-    cur[s] = v;
-  };
-  // re-centre the freshly written column (every CTC_RENORM steps), publish it, flip buffers
-  auto finish = [&](int i, int t) {
-    if ((i % CTC_RENORM) == 0) {
-      float m = NEG_INF;
-      for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, cur[s]);   // own nodes only
-      m = warp_max(m);
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-      __syncthreads();
-      m = NEG_INF;
-      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m = fmaxf(m, red[w]);
-      if (m > NEG_INF) {
-        for (int s = threadIdx.x; s < S; s += blockDim.x) cur[s] -= m;
-        csum += (double)m;
-      }
-    }
-    for (int s = threadIdx.x; s < S; s += blockDim.x) out_b[(int64_t)t * Smax + s] = cur[s];
+  auto block_max = [&](float m) -> float {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
-    float* tmp = prev; prev = cur; cur = tmp;
+    float r = NEG_INF;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) r = fmaxf(r, red[w]);
+    return r;
   };
+  const float* final_buf;
   if (S <= (int)blockDim.x) {
-    // one node per thread: the emission stream is independent of the recursion, so it is
-    // prefetched CTC_PF steps ahead into registers and the serial chain never waits on HBM
+    // ---- fast path: one node per thread, emissions prefetched CTC_PF steps ahead ----
     const int s = threadIdx.x;
     const bool has = s < S;
     const bool skip = has && skip_ok(s);
+    const int64_t stride = (int64_t)step * Smax;
+    const float* lpp = lp_b + (int64_t)t_first * Smax + (has ? s : 0);     // emission pointer of step 0
+    float* op = out_b + (int64_t)t_first * Smax + (has ? s : 0);
     float ring[CTC_PF];
 #pragma unroll
-    for (int j = 0; j < CTC_PF; ++j) {
-      const int i = 1 + j;
-      ring[j] = (has && i < Tb) ? __ldg(lp_b + (int64_t)(t_first + i * step) * Smax + s) : 0.f;
-    }
-    for (int i0 = 1; i0 < Tb; i0 += CTC_PF) {
+    for (int j = 0; j < CTC_PF; ++j) ring[j] = (has && 1 + j < Tb) ? __ldg(lpp + (int64_t)(1 + j) * stride) : 0.f;
+    const float* lpf = lpp + (int64_t)(1 + CTC_PF) * stride;               // next address to prefetch
+    int i = 1;
+    for (int blk = 0; i < Tb; ++blk) {
 #pragma unroll
       for (int j = 0; j < CTC_PF; ++j) {
-        const int i = i0 + j;
         if (i < Tb) {
+          const float* src = (j & 1) ? bufB : bufA;                        // CTC_PF is even: parity is static
+          float* dst = (j & 1) ? bufA : bufB;
           const float e = ring[j];
-          const int ip = i + CTC_PF;
-          ring[j] = (has && ip < Tb) ? __ldg(lp_b + (int64_t)(t_first + ip * step) * Smax + s) : 0.f;
-          if (has) node(s, e, skip);
-          finish(i, t_first + i * step);
+          ring[j] = (has && i + CTC_PF < Tb) ? __ldg(lpf) : 0.f;
+          lpf += stride;
+          op += stride;
+          float v = NEG_INF;
+          if (has) v = lse3_2(src[s], src[s + nb], skip ? src[s + 2 * nb] : NEG_INF) + e;
+          if (j == CTC_PF - 1 && ((blk * CTC_PF + CTC_PF) % CTC_RENORM) == 0) {
+            const float m = block_max(v);
+            if (m > NEG_INF) { v -= m; csum += (double)m; }
+          }
+          if (has) { dst[s] = v; *op = v; }
+          __syncthreads();
+          ++i;
         }
       }
     }
+    final_buf = ((Tb - 1) & 1) ? bufB : bufA;
   } else {
+    // ---- general path: several nodes per thread ----
+    float* prev = bufA;
+    float* cur = bufB;
     for (int i = 1; i < Tb; ++i) {
       const int t = t_first + i * step;
-      for (int s = threadIdx.x; s < S; s += blockDim.x) node(s, lp_b[(int64_t)t * Smax + s], skip_ok(s));
-      finish(i, t);
+      for (int s = threadIdx.x; s < S; s += blockDim.x)
+        cur[s] = lse3_2(prev[s], prev[s + nb], skip_ok(s) ? prev[s + 2 * nb] : NEG_INF) + lp_b[(int64_t)t * Smax + s];
+      if ((i % CTC_RENORM) == 0) {
+        float m = NEG_INF;
+        for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, cur[s]);
+        m = block_max(m);
+        if (m > NEG_INF) {
+          for (int s = threadIdx.x; s < S; s += blockDim.x) cur[s] -= m;
+          csum += (double)m;
+        }
+      }
+      for (int s = threadIdx.x; s < S; s += blockDim.x) out_b[(int64_t)t * Smax + s] = cur[s];
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
     }
+    final_buf = prev;
   }
   if (dir == 0 && threadIdx.x == 0) {
-    const float ll = lse2(prev[S - 1], S > 1 ? prev[S - 2] : NEG_INF);
-    nll[b] = (ll == NEG_INF) ? INFINITY : (float)(-(csum + (double)ll));   // +inf when infeasible
+    const float ll2 = lse3_2(final_buf[S - 1], S > 1 ? final_buf[S - 2] : NEG_INF, NEG_INF);
+    nll[b] = (ll2 == NEG_INF) ? INFINITY : (float)(-(csum + (double)ll2) * (double)LN2);   // +inf when infeasible
   }
 }
 
@@ -247,7 +264,7 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
                 const float* __restrict__ beta, const float* __restrict__ nll,
                 const float* __restrict__ grad_out, int reduction,
                 TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
-  extern __shared__ float sm[];                     // CTC_WARPS rows of V floats
+  extern __shared__ __align__(16) float sm[];        // per warp: V floats (row) + Spad floats (lattice)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * CTC_WARPS + warp;
   if (row >= (int64_t)B * Tn) return;
@@ -255,48 +272,74 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
   int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
   TO* dx = dlogits + b * dstride_b + t * dstride_t;
   const float n = nll[b];
-  if (t >= Tb || !isfinite(n)) {
-    for (int i = lane; i < V; i += 32) st_f(dx + i, 0.f);
+  constexpr int VWI = 16 / sizeof(TI), VWO = 16 / sizeof(TO);
+  const bool vec_out = (V % VWO == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  if (t >= Tb || !isfinite(n)) {                      // exact zeros (App. B)
+    if (vec_out) {
+      for (int i = lane * VWO; i < V; i += 32 * VWO) *reinterpret_cast<uint4*>(dx + i) = make_uint4(0, 0, 0, 0);
+    } else {
+      for (int i = lane; i < V; i += 32) st_f(dx + i, 0.f);
+    }
     return;
   }
+  const int Spad = (Smax + 3) & ~3;
+  float* r = sm + (int64_t)warp * (V + Spad);
+  float* vb = r + V;
   const TI* x = logits + b * stride_b + t * stride_t;
-  float* r = sm + (int64_t)warp * V;
-  const float l = lse[row];
-  for (int i = lane; i < V; i += 32) r[i] = __expf(ld_f(x + i) - l);
-  __syncwarp();
+  const float l2 = lse[row] * LOG2E;
+  // softmax row -> shared memory
+  if ((V % VWI == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+    for (int i = lane * VWI; i < V; i += 32 * VWI) {
+      float f[VWI];
+      Vec<TI, VWI> raw; raw.raw = __ldg(reinterpret_cast<const uint4*>(x + i));
+      unpack(raw, f);
+#pragma unroll
+      for (int j = 0; j < VWI; ++j) r[i + j] = ex2f(fmaf(f[j], LOG2E, -l2));
+    }
+  } else {
+    for (int i = lane; i < V; i += 32) r[i] = ex2f(fmaf(ld_f(x + i), LOG2E, -l2));
+  }
   const int U = (int)tgt_lens[b];
   const int S = 2 * U + 1;
   const int64_t* tg = targets + (int64_t)b * ldt;
   const float* al = alpha + row * Smax;
   const float* be = beta + row * Smax;
-  // occupancy_s = exp(alpha+beta-lp)_s / sum_s' exp(alpha+beta-lp)_s'   (the sum is exp(-nll)
-  // for every frame; normalising per frame keeps it exact under the re-centred alpha/beta)
+  // occupancy_s = 2^(alpha+beta-lp)_s / sum_s' 2^(alpha+beta-lp)_s'  (log2 units; the sum is
+  // 2^(-nll*log2e) for every frame, normalising per frame keeps it exact under re-centring)
   float vmax = NEG_INF;
   for (int s = lane; s < S; s += 32) {
-    const float lp = ld_f(x + ext_label(tg, s, blank)) - l;
-    vmax = fmaxf(vmax, al[s] + be[s] - lp);
+    const float lp2 = fmaf(ld_f(x + ext_label(tg, s, blank)), LOG2E, -l2);
+    const float v = al[s] + be[s] - lp2;
+    vb[s] = v;
+    vmax = fmaxf(vmax, v);
   }
   vmax = warp_max(vmax);
   float zsum = 0.f;
   for (int s = lane; s < S; s += 32) {
-    const float lp = ld_f(x + ext_label(tg, s, blank)) - l;
-    const float v = al[s] + be[s] - lp;
-    if (v > NEG_INF) zsum += __expf(v - vmax);
+    const float pv = ex2f(vb[s] - vmax);            // own slots only: no sync needed
+    vb[s] = pv;
+    zsum += pv;
   }
   zsum = warp_sum(zsum);
   const float inv = (zsum > 0.f) ? 1.f / zsum : 0.f;
-  for (int s = lane; s < S; s += 32) {
-    const int64_t lab = ext_label(tg, s, blank);
-    const float lp = ld_f(x + lab) - l;
-    const float v = al[s] + be[s] - lp;
-    if (v > NEG_INF) atomicAdd(r + lab, -__expf(v - vmax) * inv);
-  }
+  __syncwarp();
+  for (int s = lane; s < S; s += 32) atomicAdd(r + ext_label(tg, s, blank), -vb[s] * inv);
   __syncwarp();
   float scale;
   if (reduction == 1) scale = grad_out[0] / ((float)B * fmaxf((float)U, 1.f));
   else if (reduction == 2) scale = grad_out[0];
   else scale = grad_out[b];
-  for (int i = lane; i < V; i += 32) st_f(dx + i, scale * r[i]);
+  if (vec_out) {
+    for (int i = lane * VWO; i < V; i += 32 * VWO) {
+      float f[VWO];
+#pragma unroll
+      for (int j = 0; j < VWO; ++j) f[j] = scale * r[i + j];
+      const Vec<TO, VWO> o = pack(f, (TO*)nullptr);
+      *reinterpret_cast<uint4*>(dx + i) = o.raw;
+    }
+  } else {
+    for (int i = lane; i < V; i += 32) st_f(dx + i, scale * r[i]);
+  }
 }
 
 }  // namespace sc
@@ -346,7 +389,7 @@ static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_
                            int64_t blank, const float* lse, const float* alpha, const float* beta,
                            const float* nll, const float* grad_out, int reduction, void* dlogits,
                            int64_t dstride_b, int64_t dstride_t, cudaStream_t st) {
-  const size_t smem = (size_t)CTC_WARPS * V * sizeof(float);
+  const size_t smem = (size_t)CTC_WARPS * (V + ((Smax + 3) & ~3)) * sizeof(float);
   if (smem > 200 * 1024) return SC_E_SHAPE;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ctc_grad_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
