@@ -181,8 +181,15 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     float* op = out_b + (int64_t)t_first * Smax + (has ? s : 0);
     float ring[CTC_PF];
 #pragma unroll
-    for (int j = 0; j < CTC_PF; ++j) ring[j] = (has && 1 + j < Tb) ? __ldg(lpp + (int64_t)(1 + j) * stride) : 0.f;
-    const float* lpf = lpp + (int64_t)(1 + CTC_PF) * stride;               // next address to prefetch
+    // loads are unconditional (addresses clamped to the last live frame): a predicated load
+    // merged with a default value makes the compiler wait for it in the same step
+    const float* lp_last = lpp + (int64_t)(Tb - 1) * stride;
+    // slot of step i is (i-1) % CTC_PF.  Step i consumes its slot and refills the slot freed by
+    // step i-1 (never the register it is reading, so the load lands in place and nothing in
+    // this step depends on it); prologue fills steps 1..CTC_PF-1.
+    for (int j = 0; j < CTC_PF - 1; ++j) ring[j] = __ldg((1 + j < Tb) ? lpp + (int64_t)(1 + j) * stride : lp_last);
+    ring[CTC_PF - 1] = 0.f;
+    const float* lpf = lpp + (int64_t)CTC_PF * stride;                     // address of step i+CTC_PF-1 at i=1
     int i = 1;
     for (int blk = 0; i < Tb; ++blk) {
 #pragma unroll
@@ -191,7 +198,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
           const float* src = (j & 1) ? bufB : bufA;                        // CTC_PF is even: parity is static
           float* dst = (j & 1) ? bufA : bufB;
           const float e = ring[j];
-          ring[j] = (has && i + CTC_PF < Tb) ? __ldg(lpf) : 0.f;
+          ring[(j + CTC_PF - 1) % CTC_PF] = __ldg((i + CTC_PF - 1 < Tb) ? lpf : lp_last);
           lpf += stride;
           op += stride;
           float v = NEG_INF;
