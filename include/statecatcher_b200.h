@@ -154,8 +154,8 @@ int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn
  * the (T,B,V) transposed view nn.CTCLoss receives are accepted.  Rows need not be
  * normalised (log-softmax is folded in and is idempotent).
  * targets [B,Umax] int64 (row stride ldt), in_lens/tgt_lens [B] int64.
- * Workspaces (caller-allocated, fp32): lse [B,T], lplat/alpha/beta [B,T,S] with
- * S = 2*Umax+1.  nll [B] = per-utterance negative log-likelihood (+inf if infeasible);
+ * Workspaces (caller-allocated, fp32, 16-byte aligned): lse [B,T], lplat/alpha/beta [B,T,S]
+ * with S = 2*Umax+1 rounded up to a multiple of 4 (alpha/beta are in log2 units).  nll [B] = per-utterance negative log-likelihood (+inf if infeasible);
  * loss [1] = reduction of nll: reduction 0 none (loss untouched), 1 mean
  * = mean_b(nll_b/max(U_b,1)), 2 sum; infeasible utterances contribute 0 (zero_infinity). */
 int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,

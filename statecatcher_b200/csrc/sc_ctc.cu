@@ -17,6 +17,7 @@
 //      infeasible utterances (zero_infinity).
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
+#include "sc_tma.cuh"
 
 namespace sc {
 
@@ -39,7 +40,7 @@ __device__ __forceinline__ int64_t ext_label(const int64_t* tg, int s, int64_t b
 
 constexpr int CTC_WARPS = 8;
 constexpr int CTC_RENORM = 16;
-constexpr int CTC_PF = 8;        // emission prefetch depth of the alpha/beta recursion   // alpha/beta columns are re-centred every this many steps
+constexpr int CTC_EB = 16;       // rows of emissions per bulk-copied shared-memory block   // alpha/beta columns are re-centred every this many steps
 
 // ---- pass 1 ------------------------------------------------------------------------
 template <typename T>
@@ -119,8 +120,9 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
                                       int Tn, int Smax, int64_t blank,
                                       float* __restrict__ alpha, float* __restrict__ beta,
                                       float* __restrict__ nll) {
-  extern __shared__ float sm[];       // 2 lines of (Smax + 4) floats, 2 pad cells either side
+  extern __shared__ __align__(128) float sm[];   // 2 lines of (Smax + 4) floats (2 pad cells either side) + emission blocks
   __shared__ float red[32];
+  __shared__ __align__(8) uint64_t ebar[2];
   const int b = blockIdx.x, dir = blockIdx.y;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
@@ -133,6 +135,11 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     return;
   }
   for (int i = threadIdx.x; i < 2 * LINE; i += blockDim.x) sm[i] = NEG_INF;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   float* bufA = sm + 2;
   float* bufB = sm + LINE + 2;
@@ -148,15 +155,6 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     if (dir == 0) return s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1];
     return s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1];
   };
-  // init column
-  for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    float v = NEG_INF;
-    if (dir == 0) { if (s < 2) v = lp_b[(int64_t)t_first * Smax + s]; }
-    else          { if (s >= S - 2) v = lp_b[(int64_t)t_first * Smax + s]; }
-    bufA[s] = v;
-    out_b[(int64_t)t_first * Smax + s] = v;
-  }
-  __syncthreads();
   // Log-space values drift to magnitude ~T*log2(V); every CTC_RENORM steps the column is
   // re-centred on its maximum so fp32 keeps ~1e-6 absolute resolution for any T.  The removed
   // offsets only matter for the likelihood (summed in double); the gradient pass normalises
@@ -172,38 +170,63 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
   };
   const float* final_buf;
   if (S <= (int)blockDim.x) {
-    // ---- fast path: one node per thread, emissions prefetched CTC_PF steps ahead ----
+    // ---- fast path: one node per thread; emissions staged by bulk async copies ----
+    // The emission stream lplat[b, t, :] is independent of the recursion.  Register prefetch
+    // (LDG 8 steps ahead) stalls the chain anyway: the 6 scoreboard slots of a warp are
+    // shared by LDS/MUFU/LDG, so a consumer ends up waiting on a much younger load (measured:
+    // 1.41 ms with, 0.60 ms without the loads).  Instead CTC_EB consecutive rows (one
+    // contiguous block of lplat) are landed in shared memory by cp.async.bulk on an mbarrier,
+    // double-buffered, and the recursion only ever issues LDS.
     const int s = threadIdx.x;
     const bool has = s < S;
     const bool skip = has && skip_ok(s);
+    float* ebuf = sm + 2 * LINE;                               // 2 buffers of CTC_EB rows x Smax
+    const int nvis = (Tb + CTC_EB - 1) / CTC_EB;               // blocks of rows, visited in scan order
+    auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
+    auto rows_of = [&](int blk) { const int r = Tb - blk * CTC_EB; return r < CTC_EB ? r : CTC_EB; };
+    auto issue = [&](int vi) {
+      const int blk = blk_of(vi);
+      const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
+      const uint32_t bar = smem_u32(&ebar[vi & 1]);
+      mbar_expect_tx(bar, bytes);
+      bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * CTC_EB * Smax), lp_b + (int64_t)blk * CTC_EB * Smax, bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+      issue(0);
+      if (nvis > 1) issue(1);
+    }
+    int vi = 0, pos = 0, rows = rows_of(blk_of(0));
+    mbar_wait(smem_u32(&ebar[0]), 0);
+    auto emission = [&]() -> float {                           // row `pos` of the current visit, node s
+      const int r = dir == 0 ? pos : rows - 1 - pos;
+      return ebuf[((size_t)(vi & 1) * CTC_EB + r) * Smax + (has ? s : 0)];
+    };
+    // init column (step 0)
+    {
+      float v = NEG_INF;
+      if (has && (dir == 0 ? s < 2 : s >= S - 2)) v = emission();
+      if (has) { bufA[s] = v; out_b[(int64_t)t_first * Smax + s] = v; }
+    }
+    __syncthreads();
     const int64_t stride = (int64_t)step * Smax;
-    const float* lpp = lp_b + (int64_t)t_first * Smax + (has ? s : 0);     // emission pointer of step 0
     float* op = out_b + (int64_t)t_first * Smax + (has ? s : 0);
-    float ring[CTC_PF];
-#pragma unroll
-    // loads are unconditional (addresses clamped to the last live frame): a predicated load
-    // merged with a default value makes the compiler wait for it in the same step
-    const float* lp_last = lpp + (int64_t)(Tb - 1) * stride;
-    // slot of step i is (i-1) % CTC_PF.  Step i consumes its slot and refills the slot freed by
-    // step i-1 (never the register it is reading, so the load lands in place and nothing in
-    // this step depends on it); prologue fills steps 1..CTC_PF-1.
-    for (int j = 0; j < CTC_PF - 1; ++j) ring[j] = __ldg((1 + j < Tb) ? lpp + (int64_t)(1 + j) * stride : lp_last);
-    ring[CTC_PF - 1] = 0.f;
-    const float* lpf = lpp + (int64_t)CTC_PF * stride;                     // address of step i+CTC_PF-1 at i=1
     int i = 1;
-    for (int blk = 0; i < Tb; ++blk) {
+    while (i < Tb) {
 #pragma unroll
-      for (int j = 0; j < CTC_PF; ++j) {
+      for (int j = 0; j < 2; ++j) {                            // unrolled by 2: static buffer parity
         if (i < Tb) {
-          const float* src = (j & 1) ? bufB : bufA;                        // CTC_PF is even: parity is static
-          float* dst = (j & 1) ? bufA : bufB;
-          const float e = ring[j];
-          ring[(j + CTC_PF - 1) % CTC_PF] = __ldg((i + CTC_PF - 1 < Tb) ? lpf : lp_last);
-          lpf += stride;
+          const float* src = j ? bufB : bufA;
+          float* dst = j ? bufA : bufB;
+          if (++pos == rows) {                                 // block exhausted (uniform)
+            if (threadIdx.x == 0 && vi + 2 < nvis) issue(vi + 2);   // its buffer is free: all threads passed the barrier
+            ++vi; pos = 0; rows = rows_of(blk_of(vi));
+            mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+          }
+          const float e = emission();
           op += stride;
           float v = NEG_INF;
           if (has) v = lse3_2(src[s], src[s + nb], skip ? src[s + 2 * nb] : NEG_INF) + e;
-          if (j == CTC_PF - 1 && ((blk * CTC_PF + CTC_PF) % CTC_RENORM) == 0) {
+          if ((i % CTC_RENORM) == 0) {
             const float m = block_max(v);
             if (m > NEG_INF) { v -= m; csum += (double)m; }
           }
@@ -216,6 +239,15 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     final_buf = ((Tb - 1) & 1) ? bufB : bufA;
   } else {
     // ---- general path: several nodes per thread ----
+    // init column
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      float v = NEG_INF;
+      if (dir == 0) { if (s < 2) v = lp_b[(int64_t)t_first * Smax + s]; }
+      else          { if (s >= S - 2) v = lp_b[(int64_t)t_first * Smax + s]; }
+      bufA[s] = v;
+      out_b[(int64_t)t_first * Smax + s] = v;
+    }
+    __syncthreads();
     float* prev = bufA;
     float* cur = bufB;
     for (int i = 1; i < Tb; ++i) {
@@ -271,7 +303,7 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
                 const float* __restrict__ beta, const float* __restrict__ nll,
                 const float* __restrict__ grad_out, int reduction,
                 TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
-  extern __shared__ __align__(16) float sm[];        // per warp: V floats (row) + Spad floats (lattice)
+  extern __shared__ __align__(128) float sm[];       // per warp: V floats (row) + Spad floats (lattice)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * CTC_WARPS + warp;
   if (row >= (int64_t)B * Tn) return;
@@ -364,7 +396,7 @@ extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t
   SC_CHECK_ARG(T == 0 || (logits && lse && lplat && alpha && beta), SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && V < (1 << 30) && Umax < (1 << 20), SC_E_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Smax = (int)(2 * Umax + 1);
+  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);      // row width of lplat/alpha/beta (16-B rows)
   if (T > 0) {
     const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
     if (dtype == SC_F32)
@@ -377,7 +409,8 @@ extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t
   }
   int threads = ((Smax + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  const size_t smem = 2 * (size_t)(Smax + 4) * sizeof(float);
+  // two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
+  const size_t smem = (2 * (size_t)(Smax + 4) + (Smax <= 1024 ? 2 * (size_t)CTC_EB * Smax : 0)) * sizeof(float);
   SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -421,7 +454,7 @@ extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t
   SC_CHECK_ARG(logits && in_lens && tgt_lens && lse && alpha && beta && nll && grad_out && dlogits, SC_E_BADARG);
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Smax = (int)(2 * Umax + 1);
+  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
 #define SC_CTC_GRAD(TI, TO) launch_ctc_grad<TI, TO>(logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, \
     B, T, V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, st)
   if (dtype == SC_F32 && out_dtype == SC_F32) return SC_CTC_GRAD(float, float);

@@ -46,7 +46,7 @@ class _CTCFn(torch.autograd.Function):
         # x: logical (T,B,V), V contiguous
         T, B, V = x.shape
         dev = x.device
-        S = 2 * Umax + 1
+        S = (2 * Umax + 1 + 3) & ~3          # lattice row width, padded to 16-byte rows
         f32 = dict(dtype=torch.float32, device=dev)
         lse = torch.empty(B, max(T, 1), **f32)
         lplat = torch.empty(B, max(T, 1), S, **f32)

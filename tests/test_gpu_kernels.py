@@ -286,6 +286,44 @@ def test_ctc_random_vs_oracle(cuda_device, dtype):
     np.testing.assert_allclose(l2.item(), np.where(np.isfinite(nll_ref), nll_ref, 0).sum(), rtol=2e-4)
 
 
+def test_ctc_long_labels_general_path(cuda_device):
+    """2U+1 > 1024 lattice nodes (several nodes per thread) and T not a multiple of the
+    emission block: general recursion path vs torch CPU ctc_loss (library pin, fp64)."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(12)
+    B, T, V, U = 2, 1300, 11, 600
+    logits = torch.randn(B, T, V, generator=g)
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl, tgl = [T, 1237], [600, 520]
+    xd = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(xd.log_softmax(-1).transpose(0, 1), tokens, inl, tgl, zero_infinity=True)
+    ref.backward()
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-7)
+
+
+@pytest.mark.parametrize("T", [1, 2, 15, 16, 17, 31, 33, 100])
+def test_ctc_emission_block_boundaries(cuda_device, T):
+    """Sequence lengths around the 16-row emission block of the alpha/beta kernel."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(T)
+    B, V, U = 3, 9, 4
+    logits = torch.randn(B, T, V, generator=g) * 2
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl = [T, max(1, T - 1), max(1, T // 2)]
+    tgl = [min(U, T), min(2, T), 1]
+    _, _, grad_ref = ctc_oracle.ctc_loss_and_grad(logits.numpy(), tokens.numpy(), inl, tgl)
+    loss_ref, _, _ = ctc_oracle.ctc_loss_and_grad(logits.numpy(), tokens.numpy(), inl, tgl)
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), grad_ref, rtol=2e-4, atol=2e-6)
+
+
 def test_ctc_large_properties(cuda_device):
     """cfg2-sized CTC (B=64,T=3000,V=1024,U<=150): rows of dlogits sum to ~0, exact zeros
     beyond T_b, loss finite and reproducible."""
