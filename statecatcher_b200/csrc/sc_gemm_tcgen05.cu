@@ -62,7 +62,7 @@ struct GemmParams {
 
 // EPI: 0 = bf16 store (+bias), 1 = fp32 store (+bias), 2 = fp32 atomic accumulate (split-R)
 template <bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -80,7 +80,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    // empty: released by the MMA commits of BOTH CTAs of the pair (each multicasts half of B into the other)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 2); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -89,19 +90,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                   // peer's barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int64_t total = (int64_t)p.tiles_i * p.tiles_j * p.splits;
+  // A cluster = 2 CTAs working on vertically adjacent tiles (ti = 2*pair + rank, same tj): they
+  // share the B tile — each CTA fetches half of it and TMA-multicasts it into both — which cuts
+  // L2->SM operand traffic per k-block from 48 KB to 32 KB per SM (the single-CTA version ran
+  // at the ~12 TB/s L2 limit: 23 GB of operand reads per 2-TFLOP GEMM).
+  const uint32_t rank = cluster_ctarank();
+  const int pairs_i = (p.tiles_i + 1) / 2;
+  const int64_t total = (int64_t)pairs_i * p.tiles_j * p.splits;
+  const int64_t w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int64_t w = w0; w < total; w += wstep) {
         const int split = (int)(w % p.splits);
         const int64_t tile = w / p.splits;
-        const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+        const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -114,11 +123,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int a = 0; a < TM / 64; ++a) tma_load_2d(sa + a * ATOM_BYTES, &mapA, full(stage), ti * TM + a * 64, kb * TK);
           }
+          // this CTA's half of the B tile, multicast to both CTAs of the pair
           if (!B_MN) {
-            tma_load_2d(sb, &mapB, full(stage), kb * TK, tj * TN);
+            tma_load_2d_mc(sb + rank * (B_BYTES / 2), &mapB, full(stage), kb * TK, tj * TN + (int)rank * (TN / 2), 0x3);
           } else {
 #pragma unroll
-            for (int b = 0; b < TN / 64; ++b) tma_load_2d(sb + b * ATOM_BYTES, &mapB, full(stage), tj * TN + b * 64, kb * TK);
+            for (int b = 0; b < TN / 128; ++b) {
+              const int bb = (int)rank * (TN / 128) + b;
+              tma_load_2d_mc(sb + bb * ATOM_BYTES, &mapB, full(stage), tj * TN + bb * 64, kb * TK, 0x3);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -133,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                              ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int64_t w = w0; w < total; w += wstep) {
         const int split = (int)(w % p.splits);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -152,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                      : make_desc(sb + k * UK * 2, 0, 1024);
             umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty(stage));                    // smem stage reusable once these MMAs retire
+          umma_commit_mc(empty(stage), 0x3);            // stage reusable (here AND in the peer) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull(acc));                        // accumulator complete -> epilogue
@@ -166,9 +179,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
     float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int64_t w = w0; w < total; w += wstep) {
       const int64_t tile = w / p.splits;
-      const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
       const int64_t col0 = (int64_t)tj * TN;
       if (EPI != 2 && p.bias != nullptr) {
         // stage this tile's bias once (double-buffered with the accumulator stage)
@@ -238,6 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                   // no CTA leaves while the peer can still signal it
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -275,7 +289,7 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
                      const float* bias, int64_t I, int64_t J, int64_t R, int splits, cudaStream_t st) {
   CUtensorMap mapA, mapB;
   bool ok = A_MN ? make_map(&mapA, A, R, I, lda, TK) : make_map(&mapA, A, I, R, lda, TM);
-  ok = ok && (B_MN ? make_map(&mapB, B, R, J, ldb, TK) : make_map(&mapB, B, J, R, ldb, TN));
+  ok = ok && (B_MN ? make_map(&mapB, B, R, J, ldb, TK) : make_map(&mapB, B, J, R, ldb, TN / 2));
   if (!ok) return SC_E_UNSUP;
   GemmParams p;
   p.I = I; p.J = J; p.R = R;
@@ -292,8 +306,9 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int64_t total = (int64_t)p.tiles_i * p.tiles_j * p.splits;
-  const int grid = (int)(total < num_sms() ? total : num_sms());
+  const int64_t total = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.splits;   // work items per CTA pair
+  const int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
+  const int grid = (int)(2 * clusters);
   gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
   SC_LAUNCH_RET();
 }
