@@ -176,15 +176,22 @@ int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype
 /* ---------------------------------------------------------------- K4: RNN-T ----------
  * Replaces warp_rnnt.RNNTLoss as called at model.py:97-105 (gather=True): transducer
  * alpha/beta over the T x (U+1) lattice swept by anti-diagonals.
- * log_probs [B,T,U1,V] normalised fp32 (U1 = Umax+1), labels [B,Umax] int64.
- * Workspaces fp32: lpb, lpl, alpha, beta [B,T,U1].  nll [B].  grad (may be NULL)
- * [B,T,U1,V] receives d(sum_b w_b*nll_b)/dlog_probs with w = grad_w[B] (non-zero at the
- * blank and label column of each live node; the buffer is fully written). */
-int sc_rnnt_fwd_bwd(const float* log_probs, const int64_t* labels, int64_t ldl,
-                    const int64_t* frame_lens, const int64_t* label_lens,
-                    int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank,
-                    float* lpb, float* lpl, float* alpha, float* beta, float* nll,
-                    const float* grad_w, float* grad, void* stream);
+ * log_probs [B,T,U1,V] normalised fp32, contiguous (U1 = Umax+1 <= 1024), labels [B,Umax]
+ * int64 (row stride ldl), frame_lens/label_lens [B] int64.
+ * Workspaces fp32, 16-byte aligned, SKEWED layout [B, T+U1, U1p] with U1p = U1 rounded up to a
+ * multiple of 4 and row d = t+u: eb (blank log-probs), el (label log-probs), alpha, beta.
+ * fwd: fills the workspaces and nll[B] (0 for utterances with no frames).
+ * bwd: grad [B,T,U1,V] := d(sum_b grad_w[b]*nll_b)/dlog_probs — fully written (zeros except
+ * the blank and label entry of each live node). */
+int sc_rnnt_fwd(const float* log_probs, const int64_t* labels, int64_t ldl,
+                const int64_t* frame_lens, const int64_t* label_lens,
+                int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank,
+                float* eb, float* el, float* alpha, float* beta, float* nll, void* stream);
+int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* frame_lens,
+                const int64_t* label_lens, int64_t B, int64_t T, int64_t U1, int64_t V,
+                int64_t blank, const float* eb, const float* el, const float* alpha,
+                const float* beta, const float* nll, const float* grad_w, float* grad,
+                void* stream);
 
 #ifdef __cplusplus
 }

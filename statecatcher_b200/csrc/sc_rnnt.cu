@@ -1,5 +1,262 @@
-// K4: RNN-T wavefront loss — placeholder until the kernel lands.
+// K4: RNN-T (transducer) loss and gradient — anti-diagonal wavefront alpha/beta (sm_100a).
+//
+// Replaces the external `warp_rnnt.RNNTLoss` the reference calls at model.py:97-105 with
+// gather=True (only the blank and the label log-prob of every lattice node matter).  The
+// reference call itself is unpinned; the algorithm is Graves 2012,
+// restated in oracle/rnnt_oracle.py and cross-checked against torchaudio.
+//
+// Layout: every per-node array is stored SKEWED, [B][D = T+U1][U1p], row d = t+u holding the
+// nodes of one anti-diagonal, so that the wavefront reads and writes one contiguous row per
+// step (coalesced, and bulk-copyable):
+//   eb[d][u] = log_probs[t,u,blank],  el[d][u] = log_probs[t,u,label_{u+1}]   (t = d-u)
+// Passes:  (1) rnnt_gather: one thread per node pulls its two log-probs out of the V-wide row;
+// (2) rnnt_alpha_beta: one CTA per (utterance, direction), node column u on thread u, the
+// previous diagonal in a double-buffered shared-memory line, one __syncthreads per
+// diagonal, emission rows landed by cp.async.bulk in blocks of RNNT_EB diagonals;
+// (3) rnnt_grad: one thread per node scatters the two non-zero gradient entries.
 #include "sc_common.cuh"
-extern "C" int sc_rnnt_fwd_bwd(const float*, const int64_t*, int64_t, const int64_t*, const int64_t*,
-                               int64_t, int64_t, int64_t, int64_t, int64_t, float*, float*, float*, float*,
-                               float*, const float*, float*, void*) { return SC_E_UNSUP; }
+#include "sc_tma.cuh"
+
+namespace sc {
+
+#define NEG_INF (-INFINITY)
+constexpr int RNNT_EB = 16;
+
+__device__ __forceinline__ float lse2n(float a, float b) {
+  const float m = fmaxf(fmaxf(a, b), -1e30f);
+  return m + __logf(__expf(a - m) + __expf(b - m));
+}
+
+__global__ void rnnt_gather_kernel(const float* __restrict__ lp, const int64_t* __restrict__ labels, int64_t ldl,
+                                   const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
+                                   int B, int Tn, int U1, int V, int U1p, int64_t blank,
+                                   float* __restrict__ eb, float* __restrict__ el) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Tn * U1) return;
+  const int u = (int)(i % U1);
+  const int t = (int)((i / U1) % Tn);
+  const int b = (int)(i / ((int64_t)U1 * Tn));
+  int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
+  const int64_t Ub = label_lens[b];
+  if (t >= Tb || u > Ub) return;
+  const float* row = lp + i * V;
+  const int64_t D = Tn + U1;
+  const int64_t o = ((int64_t)b * D + (t + u)) * U1p + u;
+  eb[o] = __ldg(row + blank);
+  el[o] = (u < Ub) ? __ldg(row + labels[(int64_t)b * ldl + u]) : NEG_INF;
+}
+
+// dir 0: alpha over diagonals 0..Tb+Ub-1;  dir 1: beta over diagonals Tb+Ub-1..0
+__global__ void rnnt_alpha_beta_kernel(const float* __restrict__ eb, const float* __restrict__ el,
+                                       const int64_t* __restrict__ frame_lens,
+                                       const int64_t* __restrict__ label_lens, int Tn, int U1, int U1p,
+                                       float* __restrict__ alpha, float* __restrict__ beta,
+                                       float* __restrict__ nll) {
+  extern __shared__ __align__(128) float sm[];   // 2 lines of (U1p + 4) + 2 x 2 blocks of RNNT_EB emission rows
+  __shared__ __align__(8) uint64_t ebar[2];
+  const int b = blockIdx.x, dir = blockIdx.y;
+  int64_t Tb64 = frame_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64, Ub = (int)label_lens[b];
+  if (Tb <= 0) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = 0.f;        // no frames: zero loss, zero gradient
+    return;
+  }
+  const int LINE = U1p + 4;
+  const int64_t D = Tn + U1;
+  const int nd = Tb + Ub;                                    // live diagonals 0..nd-1
+  const int u = threadIdx.x;
+  for (int i = threadIdx.x; i < 2 * LINE; i += blockDim.x) sm[i] = NEG_INF;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float* lineA = sm + 2;
+  float* lineB = sm + LINE + 2;
+  float* stage = sm + 2 * LINE;                              // [2 buffers][2 arrays][RNNT_EB][U1p]
+  const float* eb_b = eb + (int64_t)b * D * U1p;
+  const float* el_b = el + (int64_t)b * D * U1p;
+  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * D * U1p;
+
+  // emission rows are consumed in scan order in blocks of RNNT_EB diagonals
+  const int nvis = (nd + RNNT_EB - 1) / RNNT_EB;
+  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
+  auto rows_of = [&](int blk) { const int r = nd - blk * RNNT_EB; return r < RNNT_EB ? r : RNNT_EB; };
+  auto issue = [&](int vi) {
+    const int blk = blk_of(vi);
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)U1p * 4u;
+    const uint32_t bar = smem_u32(&ebar[vi & 1]);
+    mbar_expect_tx(bar, 2 * bytes);
+    float* dst = stage + (size_t)(vi & 1) * 2 * RNNT_EB * U1p;
+    bulk_load_1d(smem_u32(dst), eb_b + (int64_t)blk * RNNT_EB * U1p, bytes, bar);
+    bulk_load_1d(smem_u32(dst + RNNT_EB * U1p), el_b + (int64_t)blk * RNNT_EB * U1p, bytes, bar);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  // row access by absolute diagonal index (must lie in the current or the previous visit's block)
+  int vi = 0;
+  mbar_wait(smem_u32(&ebar[0]), 0);
+  auto row_ptr = [&](int d, int arr, int v) -> const float* {
+    return stage + ((size_t)(v & 1) * 2 + arr) * RNNT_EB * U1p + (size_t)(d % RNNT_EB) * U1p;
+  };
+  const bool col_live = u <= Ub;
+  float own = NEG_INF;                                       // this column's value on the previous diagonal
+  float* prev = lineA;
+  float* cur = lineB;
+  if (dir == 0) {
+    // alpha(t,u) = lse(alpha(t-1,u) + eb[t-1,u], alpha(t,u-1) + el[t,u-1]); both emissions sit on row d-1
+    for (int d = 0; d < nd; ++d) {
+      if (d >= 1 && (d - 1) % RNNT_EB == 0) {
+        // step d reads row d-1, the first row of block k.  Everyone has passed the barrier of
+        // step d-1 (last reader of block k-1), so that buffer can take block k+1.
+        const int k = (d - 1) / RNNT_EB;
+        if (k >= 1 && threadIdx.x == 0 && k + 1 < nvis) issue(k + 1);
+        mbar_wait(smem_u32(&ebar[k & 1]), (uint32_t)((k >> 1) & 1));
+        vi = k;
+      }
+      const int t = d - u;
+      float v = NEG_INF;
+      if (col_live && t >= 0 && t < Tb) {
+        if (d == 0) {
+          v = 0.f;
+        } else {
+          // selects, not arithmetic masking: slots of non-existent nodes are uninitialised
+          const float down = (t > 0) ? own + row_ptr(d - 1, 0, vi)[u] : NEG_INF;
+          const float left = (u > 0) ? prev[u - 1] + row_ptr(d - 1, 1, vi)[u - 1] : NEG_INF;
+          v = lse2n(down, left);
+        }
+      }
+      if (u < U1p) { cur[u] = v; out_b[(int64_t)d * U1p + u] = v; }
+      own = v;
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
+    if (threadIdx.x == 0) {
+      // final node (Tb-1, Ub) lives on diagonal nd-1, column Ub: prev holds that diagonal
+      const float a = prev[Ub];
+      const float e = eb_b[(int64_t)(nd - 1) * U1p + Ub];
+      nll[b] = -(a + e);
+    }
+  } else {
+    // beta(t,u) = lse(beta(t+1,u) + eb[t,u], beta(t,u+1) + el[t,u]); emissions sit on the node's own row d
+    for (int d = nd - 1; d >= 0; --d) {
+      const int blk = d / RNNT_EB;
+      const int v_of_blk = nvis - 1 - blk;
+      if (v_of_blk != vi) {                                  // crossed into an older block of rows
+        // the buffer of visit vi (block blk+1) is free after the barrier that ended step d+1
+        if (threadIdx.x == 0 && vi + 2 < nvis) issue(vi + 2);
+        vi = v_of_blk;
+        mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+      }
+      const int t = d - u;
+      float v = NEG_INF;
+      if (col_live && t >= 0 && t < Tb) {
+        const float e_b = row_ptr(d, 0, vi)[u];
+        if (t == Tb - 1 && u == Ub) {
+          v = e_b;
+        } else {
+          const float e_l = row_ptr(d, 1, vi)[u];
+          const float right = (u < Ub) ? prev[u + 1] + e_l : NEG_INF;
+          const float down = (t + 1 < Tb) ? own + e_b : NEG_INF;
+          v = lse2n(down, right);
+        }
+      }
+      if (u < U1p) { cur[u] = v; out_b[(int64_t)d * U1p + u] = v; }
+      own = v;
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
+  }
+}
+
+__global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __restrict__ el,
+                                 const float* __restrict__ alpha, const float* __restrict__ beta,
+                                 const float* __restrict__ nll, const float* __restrict__ grad_w,
+                                 const int64_t* __restrict__ labels, int64_t ldl,
+                                 const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
+                                 int B, int Tn, int U1, int V, int U1p, int64_t blank, float* __restrict__ grad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Tn * U1) return;
+  const int u = (int)(i % U1);
+  const int t = (int)((i / U1) % Tn);
+  const int b = (int)(i / ((int64_t)U1 * Tn));
+  int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
+  const int64_t Ub = label_lens[b];
+  if (t >= Tb || u > Ub) return;
+  const int64_t D = Tn + U1;
+  const int64_t base = (int64_t)b * D * U1p;
+  const int64_t o = base + (int64_t)(t + u) * U1p + u;
+  const float a = alpha[o];
+  if (a == NEG_INF) return;
+  const float ll = -nll[b];
+  const float w = grad_w[b];
+  float* g = grad + i * V;
+  // blank: (t,u) -> (t+1,u); at the final node it terminates the path
+  float nb = NEG_INF;
+  if (t + 1 < Tb) nb = beta[base + (int64_t)(t + 1 + u) * U1p + u];
+  else if (u == Ub) nb = 0.f;
+  if (nb > NEG_INF) g[blank] = -w * __expf(a + eb[o] + nb - ll);
+  if (u < Ub) {
+    const float nl = beta[base + (int64_t)(t + u + 1) * U1p + (u + 1)];
+    if (nl > NEG_INF) {
+      const int64_t lab = labels[(int64_t)b * ldl + u];
+      const float gv = -w * __expf(a + el[o] + nl - ll);
+      if (lab == blank) g[blank] += gv; else g[lab] = gv;
+    }
+  }
+}
+
+}  // namespace sc
+
+using namespace sc;
+
+static bool rnnt_args_ok(int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank) {
+  return B > 0 && T >= 0 && U1 >= 1 && U1 <= 1024 && V > 0 && blank >= 0 && blank < V &&
+         B * T * U1 < ((int64_t)1 << 40) && B * (T + U1) * U1 < ((int64_t)1 << 31);
+}
+
+extern "C" int sc_rnnt_fwd(const float* log_probs, const int64_t* labels, int64_t ldl,
+                           const int64_t* frame_lens, const int64_t* label_lens,
+                           int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank,
+                           float* eb, float* el, float* alpha, float* beta, float* nll, void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank), SC_E_SHAPE);
+  SC_CHECK_ARG(frame_lens && label_lens && nll && (U1 == 1 || labels), SC_E_BADARG);
+  SC_CHECK_ARG(T == 0 || (log_probs && eb && el && alpha && beta), SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int U1p = (int)((U1 + 3) & ~(int64_t)3);
+  if (T > 0) {
+    const int64_t n = B * T * U1;
+    rnnt_gather_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(log_probs, labels, ldl, frame_lens, label_lens,
+        (int)B, (int)T, (int)U1, (int)V, U1p, blank, eb, el);
+  }
+  int threads = ((U1p + 31) / 32) * 32;
+  const size_t smem = (2 * (size_t)(U1p + 4) + 4 * (size_t)RNNT_EB * U1p) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rnnt_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  rnnt_alpha_beta_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(eb, el, frame_lens, label_lens, (int)T, (int)U1,
+      U1p, alpha, beta, nll);
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* frame_lens,
+                           const int64_t* label_lens, int64_t B, int64_t T, int64_t U1, int64_t V,
+                           int64_t blank, const float* eb, const float* el, const float* alpha,
+                           const float* beta, const float* nll, const float* grad_w, float* grad,
+                           void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank), SC_E_SHAPE);
+  if (T == 0) return 0;
+  SC_CHECK_ARG(frame_lens && label_lens && eb && el && alpha && beta && nll && grad_w && grad, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int U1p = (int)((U1 + 3) & ~(int64_t)3);
+  cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)(B * T * U1 * V), st);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t n = B * T * U1;
+  rnnt_grad_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(eb, el, alpha, beta, nll, grad_w, labels, ldl, frame_lens,
+      label_lens, (int)B, (int)T, (int)U1, (int)V, U1p, blank, grad);
+  SC_LAUNCH_RET();
+}

@@ -1,0 +1,106 @@
+"""RNN-T head on the sm_100a wavefront kernels (K4).
+
+Reference call sites: train.py:39/144 (`from warp_rnnt import RNNTLoss`, used as the
+criterion) and model.py:73-105 (`criterion(log_probs=..., labels=..., frames_lengths=...,
+labels_lengths=..., blank_id=..., compact=..., gather=True)`), joiners model.py:112-200.
+warp_rnnt is absent from the reference tree, its requirements and this image, and that call
+matches no published API, so PARITY IS UNPINNED: the loss implemented here
+is the standard transducer negative log-likelihood (Graves 2012), checked against
+oracle/rnnt_oracle.py and torchaudio.functional.rnnt_loss.
+
+``RNNTLoss`` keeps the keyword signature of the reference call.  ``reduction`` defaults to
+'mean' over the batch so the value can be ``.backward()``-ed as train.py:526-536 does.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import call, ptr, stream
+from .ctc import _lens
+from .lucyrnn import _LinearFn, _compute_dtype
+
+
+class _RNNTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_probs, labels, frame_lens, label_lens, blank):
+        B, T, U1, V = log_probs.shape
+        dev = log_probs.device
+        U1p = (U1 + 3) & ~3
+        ws = lambda: torch.empty(B, T + U1, U1p, dtype=torch.float32, device=dev)   # noqa: E731
+        eb, el, alpha, beta = ws(), ws(), ws(), ws()
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        ldl = labels.stride(0) if labels.numel() else max(U1 - 1, 1)
+        call("sc_rnnt_fwd", ptr(log_probs), ptr(labels), ldl, ptr(frame_lens), ptr(label_lens),
+             B, T, U1, V, blank, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), stream())
+        ctx.save_for_backward(labels, frame_lens, label_lens, eb, el, alpha, beta, nll)
+        ctx.cfg = (B, T, U1, V, blank, ldl)
+        return nll
+
+    @staticmethod
+    def backward(ctx, gnll):
+        labels, frame_lens, label_lens, eb, el, alpha, beta, nll = ctx.saved_tensors
+        B, T, U1, V, blank, ldl = ctx.cfg
+        grad = torch.empty(B, T, U1, V, dtype=torch.float32, device=nll.device)
+        w = gnll.to(torch.float32).contiguous()
+        call("sc_rnnt_bwd", ptr(labels), ldl, ptr(frame_lens), ptr(label_lens), B, T, U1, V, blank,
+             ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), ptr(w), ptr(grad), stream())
+        return grad, None, None, None, None
+
+
+def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
+              reduction: str = "mean") -> torch.Tensor:
+    """log_probs [B,T,U+1,V] normalised (log_softmax of the joint), labels [B,U]."""
+    _lib.require_cuda(log_probs, "rnnt_loss input")
+    if log_probs.dim() != 4:
+        raise ValueError("rnnt_loss expects (B,T,U+1,V) log-probs (compact packing is not implemented)")
+    x = log_probs.float().contiguous()
+    B, T, U1, V = x.shape
+    fl, _ = _lens(frames_lengths, x.device, B, "frames_lengths")
+    ll, _ = _lens(labels_lengths, x.device, B, "labels_lengths")
+    lab = labels.to(device=x.device, dtype=torch.int64).contiguous()
+    if lab.dim() != 2 or lab.size(0) != B or lab.size(1) < U1 - 1:
+        raise ValueError("labels must be (B,U) with U >= log_probs.size(2)-1")
+    nll = _RNNTFn.apply(x, lab, fl, ll, int(blank))
+    if reduction == "mean":
+        return nll.mean()
+    if reduction == "sum":
+        return nll.sum()
+    if reduction in (None, "none"):
+        return nll
+    raise ValueError(f"unknown reduction {reduction!r}")
+
+
+def RNNTLoss(log_probs, labels, frames_lengths, labels_lengths, blank_id: int = 0, compact: bool = False,
+             gather: bool = True, reduction: str = "mean", **_unused):
+    """Callable with the keyword signature model.py:97-105 uses on `warp_rnnt.RNNTLoss`."""
+    if compact:
+        raise NotImplementedError("compact=True (packed (sum T*U, V) layout, model.py:147-200) is not implemented")
+    return rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank=blank_id, reduction=reduction)
+
+
+class RNNTPredictorJoiner(nn.Module):
+    """model.py:112-145: Embedding -> Linear predictor, Linear encoder projection, broadcast
+    add, tanh, Linear to vocab.  The three Linear layers run on the K1 GEMM kernels."""
+
+    def __init__(self, enc_out_dim: int, pred_emb_dim: int, join_dim: int, vocab_size: int, debug: bool = False):
+        super().__init__()
+        self.embedding = nn.Embedding(vocab_size, pred_emb_dim)
+        self.enc_proj = nn.Linear(enc_out_dim, join_dim)
+        self.pred_proj = nn.Linear(pred_emb_dim, join_dim)
+        self.joiner = nn.Linear(join_dim, vocab_size)
+        self.debug = debug
+
+    def _lin(self, x, layer):
+        cd = _compute_dtype(x, None)
+        if x.dtype != cd:
+            x = x.to(cd)
+        return _LinearFn.apply(x.contiguous(), layer.weight, layer.bias, cd)
+
+    def forward(self, enc_out: torch.Tensor, prefix: torch.Tensor):
+        pred_emb = self.embedding(prefix)                        # (B, U+1, E)
+        enc = self._lin(enc_out, self.enc_proj)                  # (B, T, J)
+        pred = self._lin(pred_emb, self.pred_proj)               # (B, U+1, J)
+        joint = torch.tanh(enc.unsqueeze(2) + pred.unsqueeze(1))  # (B, T, U+1, J)
+        return self._lin(joint, self.joiner)                     # (B, T, U+1, V)

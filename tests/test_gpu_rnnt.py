@@ -1,0 +1,87 @@
+"""GPU: RNN-T wavefront loss (K4) vs the numpy oracle (oracle/rnnt_oracle.py, Graves 2012)
+and the torchaudio golden vectors.  Parity with the reference's own warp_rnnt call is
+UNPINNED; the tolerance contract is fp32 rtol 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import rnnt_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["basic", "single", "wide"])
+def test_rnnt_golden_torchaudio(cuda_device, case):
+    import statecatcher_b200 as sb
+    G = load_golden("rnnt_cases")
+    logits = torch.tensor(G[case + "/logits"]).cuda().requires_grad_(True)
+    lp = logits.log_softmax(-1)
+    nll = sb.rnnt_loss(lp, torch.tensor(G[case + "/targets"]).long().cuda(), G[case + "/frame_lens"].tolist(),
+                       G[case + "/label_lens"].tolist(), blank=0, reduction="none")
+    np.testing.assert_allclose(nll.detach().cpu().numpy(), G[case + "/nll"], rtol=1e-4, atol=1e-5)
+    nll.sum().backward()                      # through torch's log_softmax backward -> d/dlogits
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), G[case + "/grad"], rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("B,T,U,V", [(1, 1, 0, 3), (2, 5, 1, 4), (3, 37, 9, 11), (2, 70, 40, 6), (4, 33, 17, 29)])
+def test_rnnt_random_vs_oracle(cuda_device, B, T, U, V):
+    import statecatcher_b200 as sb
+    g = torch.Generator().manual_seed(B * 100 + T)
+    lp = torch.randn(B, T, U + 1, V, generator=g).log_softmax(-1)
+    labels = torch.randint(1, V, (B, max(U, 1)), generator=g)
+    fl = [T] + [int(torch.randint(1, T + 1, (1,), generator=g)) for _ in range(B - 1)]
+    ll = [U] + [int(torch.randint(0, U + 1, (1,), generator=g)) for _ in range(B - 1)]
+    nll_ref, grad_ref = rnnt_oracle.rnnt_loss_and_grad(lp.numpy(), labels.numpy(), fl, ll, blank=0)
+    x = lp.cuda().requires_grad_(True)
+    w = torch.rand(B, generator=g) + 0.5
+    nll = sb.rnnt_loss(x, labels.cuda(), fl, ll, blank=0, reduction="none")
+    (nll * w.cuda()).sum().backward()
+    np.testing.assert_allclose(nll.detach().cpu().numpy(), nll_ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), grad_ref * w.numpy()[:, None, None, None], rtol=2e-4, atol=2e-6)
+    # structure: only blank/label entries of live nodes are non-zero; dead frames all zero
+    for b in range(B):
+        assert (x.grad[b, fl[b]:] == 0).all()
+        assert (x.grad[b, :, ll[b] + 1:] == 0).all()
+
+
+def test_rnnt_reference_call_signature_and_zero_frames(cuda_device):
+    """The keyword call of model.py:97-105 (blank_id=, compact=, gather=True); an utterance with
+    no frames contributes zero loss and zero gradient."""
+    import statecatcher_b200 as sb
+    g = torch.Generator().manual_seed(1)
+    B, T, U, V = 3, 12, 4, 8
+    lp = torch.randn(B, T, U + 1, V, generator=g).log_softmax(-1).cuda().requires_grad_(True)
+    labels = torch.randint(1, V, (B, U), generator=g).cuda()
+    loss = sb.RNNTLoss(log_probs=lp, labels=labels, frames_lengths=[T, 0, 7], labels_lengths=[U, 0, 2],
+                       blank_id=0, compact=False, gather=True)
+    assert loss.dim() == 0
+    loss.backward()
+    assert (lp.grad[1] == 0).all() and torch.isfinite(lp.grad).all()
+    with pytest.raises(NotImplementedError):
+        sb.RNNTLoss(log_probs=lp, labels=labels, frames_lengths=[T] * B, labels_lengths=[U] * B, compact=True)
+
+
+def test_rnnt_joiner_and_large_lattice(cuda_device):
+    """Joiner (model.py:112-145) -> log_softmax -> loss on a cfg4-shaped small batch:
+    J=512, V=1024, E=64, T=300, U<=60: finite, reproducible, gradients reach every joiner
+    parameter; loss equals the oracle on one utterance."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(0)
+    B, T, U, V, J, E = 2, 300, 60, 1024, 512, 64
+    joiner = sb.RNNTPredictorJoiner(enc_out_dim=V, pred_emb_dim=E, join_dim=J, vocab_size=V).cuda()
+    enc_out = torch.randn(B, T, V, device="cuda") * 0.1
+    tokens = torch.randint(1, V, (B, U), device="cuda")
+    prefix = torch.cat([torch.zeros(B, 1, dtype=torch.long, device="cuda"), tokens], 1)
+    logits = joiner(enc_out, prefix)
+    assert logits.shape == (B, T, U + 1, V)
+    lp = logits.float().log_softmax(-1)
+    fl, ll = [T, 211], [U, 37]
+    nll = sb.rnnt_loss(lp, tokens, fl, ll, reduction="none")
+    nll2 = sb.rnnt_loss(lp.detach(), tokens, fl, ll, reduction="none")
+    assert torch.isfinite(nll).all() and torch.equal(nll.detach(), nll2)
+    nll.mean().backward()
+    for n, p in joiner.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    ref, _ = rnnt_oracle.rnnt_loss_and_grad(lp[1:2].detach().cpu().numpy(), tokens[1:2].cpu().numpy(), [211], [37])
+    np.testing.assert_allclose(nll[1].item(), ref[0], rtol=1e-4)
