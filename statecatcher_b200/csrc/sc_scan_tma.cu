@@ -14,13 +14,14 @@
 // dispatcher in sc_scan.cu picks this path when H and the strides satisfy TMA alignment.
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
+#include <stdlib.h>
 
 namespace sc {
 
 constexpr int TC = SC_SCAN_CKPT;     // timesteps per stage == checkpoint interval
 constexpr int CB = 256;              // channels per CTA (bf16: 512-byte rows)
-constexpr int VEC = 2;               // channels per thread
-constexpr int SCAN_THREADS = CB / VEC;
+// channels per thread (VEC) is a template parameter: 1 doubles the resident warps per SM (16
+// instead of 8), 2 halves the instruction count per channel
 
 template <typename T> struct TmaType;
 template <> struct TmaType<bf16>  { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
@@ -40,7 +41,7 @@ static bool make_scan_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// shared-memory element access: thread owns channels [2*tid, 2*tid+1] of a [TC][CB] box
+// shared-memory element access: thread owns channels [VEC*tid, VEC*tid+VEC) of a [TC][CB] box
 __device__ __forceinline__ void lds2(const bf16* row, int tid, float (&f)[2]) {
   const uint32_t w = reinterpret_cast<const uint32_t*>(row)[tid];
   f[0] = __uint_as_float(w << 16);
@@ -50,10 +51,16 @@ __device__ __forceinline__ void lds2(const float* row, int tid, float (&f)[2]) {
   const float2 w = reinterpret_cast<const float2*>(row)[tid];
   f[0] = w.x; f[1] = w.y;
 }
+__device__ __forceinline__ void lds2(const bf16* row, int tid, float (&f)[1]) {
+  f[0] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(row)[tid] << 16);
+}
+__device__ __forceinline__ void lds2(const float* row, int tid, float (&f)[1]) { f[0] = row[tid]; }
+template <typename T> __device__ __forceinline__ void stg_vec(T* p, const float (&f)[2]) { vstore<T, 2>(p, pack(f, (T*)nullptr)); }
+template <typename T> __device__ __forceinline__ void stg_vec(T* p, const float (&f)[1]) { st_f(p, f[0]); }
 
 // ------------------------------------------------------------------ forward ----------
-template <typename T, int NST, bool TRAIN, bool PRECISE>
-__global__ void __launch_bounds__(SCAN_THREADS)
+template <typename T, int VEC, int NST, bool TRAIN, bool PRECISE>
+__global__ void __launch_bounds__(CB / VEC)
 lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* __restrict__ h0,
                          const float* __restrict__ s0, T* __restrict__ Hout, int64_t ldh,
                          float* __restrict__ hT, float* __restrict__ sT, float* __restrict__ Sckpt,
@@ -109,7 +116,7 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
 #pragma unroll
     for (int u = 0; u < TC; ++u) {
       if (t0 + u < Tn) {
-        float z[2], k[2], v[2], p[2], q[2], out[2];
+        float z[VEC], k[VEC], v[VEC], p[VEC], q[VEC], out[VEC];
         lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
         lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
         lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
@@ -126,7 +133,7 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
           h[i] = fmaf(zh, h[i] - cc, cc);
           out[i] = h[i];
         }
-        if (live) vstore<T, VEC>(ho + (int64_t)(t0 + u) * ldh, pack(out, (T*)nullptr));
+        if (live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
       }
     }
   }
@@ -141,8 +148,8 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
 
 // ------------------------------------------------------------------ backward ---------
 // Stage = 5 gate boxes + dHout box + Hout box shifted one row back (h_{t-1}).
-template <typename T, int NST, bool TRAIN, bool PRECISE>
-__global__ void __launch_bounds__(SCAN_THREADS)
+template <typename T, int VEC, int NST, bool TRAIN, bool PRECISE>
+__global__ void __launch_bounds__(CB / VEC)
 lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapH,
                          const __grid_constant__ CUtensorMap mapDH, const float* __restrict__ h0,
                          const float* __restrict__ Sckpt, T* __restrict__ dG, int64_t lddg,
@@ -189,14 +196,22 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
     for (int g = 0; g < 5; ++g) acc[g][i] = 0.f;
   }
   T* dg = dG + (int64_t)b * Tn * lddg + ch;
+  float Snext[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) Snext[i] = live ? Sckpt[((int64_t)b * nchunk + nchunk - 1) * H + ch + i] : 0.f;
 
   for (int it = 0; it < nchunk; ++it) {
     const int chunk = nchunk - 1 - it;
     __syncthreads();
     if (tid == 0 && it + NST - 1 < nchunk) issue(it + NST - 1);
+    // checkpoint of THIS interval was fetched one iteration ago; fetch the next one now so its
+    // HBM latency hides behind this interval's work (it was 24 % of the stall samples)
     float Sin[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) Sin[i] = live ? Sckpt[((int64_t)b * nchunk + chunk) * H + ch + i] : 0.f;
+    for (int i = 0; i < VEC; ++i) {
+      Sin[i] = Snext[i];
+      Snext[i] = (live && chunk > 0) ? Sckpt[((int64_t)b * nchunk + chunk - 1) * H + ch + i] : 0.f;
+    }
     mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
     const int t0 = chunk * TC;
@@ -208,7 +223,7 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
       for (int i = 0; i < VEC; ++i) S[i] = Sin[i];
 #pragma unroll
       for (int u = 0; u < TC; ++u) {
-        float k[2], v[2], q[2];
+        float k[VEC], v[VEC], q[VEC];
         lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
         lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
         lds2(st + (SC_GATE_Q * TC + u) * CB, tid, q);
@@ -226,15 +241,18 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
     for (int u = TC - 1; u >= 0; --u) {
       const int t = t0 + u;
       if (t < Tn) {
-        float z[2], k[2], v[2], p[2], go[2], hp[2];
+        float z[VEC], k[VEC], v[VEC], p[VEC], go[VEC], hp[VEC];
         lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
         lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
         lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
         lds2(st + (SC_GATE_P * TC + u) * CB, tid, p);
         lds2(st + (5 * TC + u) * CB, tid, go);
         lds2(st + (6 * TC + u) * CB, tid, hp);
-        if (t == 0) { hp[0] = hfirst[0]; hp[1] = hfirst[1]; }
-        float dz[2], dk[2], dv[2], dp[2], dq[2];
+        if (t == 0) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) hp[i] = hfirst[i];
+        }
+        float dz[VEC], dk[VEC], dv[VEC], dp[VEC], dq[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           const float d = dl[u][i];
@@ -269,11 +287,11 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
         }
         if (live) {
           T* row = dg + (int64_t)t * lddg;
-          vstore<T, VEC>(row + (int64_t)SC_GATE_Z * H, pack(dz, (T*)nullptr));
-          vstore<T, VEC>(row + (int64_t)SC_GATE_K * H, pack(dk, (T*)nullptr));
-          vstore<T, VEC>(row + (int64_t)SC_GATE_V * H, pack(dv, (T*)nullptr));
-          vstore<T, VEC>(row + (int64_t)SC_GATE_P * H, pack(dp, (T*)nullptr));
-          vstore<T, VEC>(row + (int64_t)SC_GATE_Q * H, pack(dq, (T*)nullptr));
+          stg_vec<T>(row + (int64_t)SC_GATE_Z * H, dz);
+          stg_vec<T>(row + (int64_t)SC_GATE_K * H, dk);
+          stg_vec<T>(row + (int64_t)SC_GATE_V * H, dv);
+          stg_vec<T>(row + (int64_t)SC_GATE_P * H, dp);
+          stg_vec<T>(row + (int64_t)SC_GATE_Q * H, dq);
         }
       }
     }
@@ -290,13 +308,20 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
 template <typename T>
 static bool tma_ok(const void* G, int64_t ldg, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t H) {
   constexpr int per16 = 16 / (int)sizeof(T);
-  if (H % per16 != 0 || H % VEC != 0) return false;
+  if (H % per16 != 0) return false;
   if (ldg % per16 || lda % per16 || ldb % per16) return false;
   if (!aligned16(G) || !aligned16(a) || !aligned16(b)) return false;
   return get_encode() != nullptr;
 }
 
-template <typename T, bool PRECISE>
+// SC_SCAN_VEC=1|2 in the environment overrides the channels-per-thread choice (A/B measurements)
+static int scan_vec_choice() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SC_SCAN_VEC"); v = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0; }
+  return v;
+}
+
+template <typename T, int VEC, bool PRECISE>
 static int scan_fwd_tma(const void* G, int64_t ldg, const float* h0, const float* s0, void* Hout, int64_t ldh,
                         float* hT, float* sT, float* Sckpt, int64_t B, int64_t Tn, int64_t H, int train,
                         cudaStream_t st) {
@@ -306,8 +331,8 @@ static int scan_fwd_tma(const void* G, int64_t ldg, const float* h0, const float
   if (!make_scan_map<T>(&mapG, G, B * Tn, 5 * H, ldg, TC)) return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
   const unsigned grid = (unsigned)(B * cblocks);
-  auto kt = lucy_scan_fwd_tma_kernel<T, NST, true, PRECISE>;
-  auto ks = lucy_scan_fwd_tma_kernel<T, NST, false, PRECISE>;
+  auto kt = lucy_scan_fwd_tma_kernel<T, VEC, NST, true, PRECISE>;
+  auto ks = lucy_scan_fwd_tma_kernel<T, VEC, NST, false, PRECISE>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -315,12 +340,12 @@ static int scan_fwd_tma(const void* G, int64_t ldg, const float* h0, const float
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  if (train) kt<<<grid, SCAN_THREADS, smem, st>>>(mapG, h0, s0, (T*)Hout, ldh, hT, sT, Sckpt, (int)Tn, (int)H, cblocks);
-  else       ks<<<grid, SCAN_THREADS, smem, st>>>(mapG, h0, s0, (T*)Hout, ldh, hT, sT, Sckpt, (int)Tn, (int)H, cblocks);
+  if (train) kt<<<grid, CB / VEC, smem, st>>>(mapG, h0, s0, (T*)Hout, ldh, hT, sT, Sckpt, (int)Tn, (int)H, cblocks);
+  else       ks<<<grid, CB / VEC, smem, st>>>(mapG, h0, s0, (T*)Hout, ldh, hT, sT, Sckpt, (int)Tn, (int)H, cblocks);
   SC_LAUNCH_RET();
 }
 
-template <typename T, bool PRECISE>
+template <typename T, int VEC, bool PRECISE>
 static int scan_bwd_tma(const void* G, int64_t ldg, const void* Hout, int64_t ldh, const float* h0,
                         const float* Sckpt, const void* dHout, int64_t lddh, void* dG, int64_t lddg,
                         float* dbias, int64_t B, int64_t Tn, int64_t H, int train, cudaStream_t st) {
@@ -332,8 +357,8 @@ static int scan_bwd_tma(const void* G, int64_t ldg, const void* Hout, int64_t ld
     return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
   const unsigned grid = (unsigned)(B * cblocks);
-  auto kt = lucy_scan_bwd_tma_kernel<T, NST, true, PRECISE>;
-  auto ks = lucy_scan_bwd_tma_kernel<T, NST, false, PRECISE>;
+  auto kt = lucy_scan_bwd_tma_kernel<T, VEC, NST, true, PRECISE>;
+  auto ks = lucy_scan_bwd_tma_kernel<T, VEC, NST, false, PRECISE>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -341,8 +366,8 @@ static int scan_bwd_tma(const void* G, int64_t ldg, const void* Hout, int64_t ld
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  if (train) kt<<<grid, SCAN_THREADS, smem, st>>>(mapG, mapH, mapDH, h0, Sckpt, (T*)dG, lddg, dbias, (int)Tn, (int)H, cblocks);
-  else       ks<<<grid, SCAN_THREADS, smem, st>>>(mapG, mapH, mapDH, h0, Sckpt, (T*)dG, lddg, dbias, (int)Tn, (int)H, cblocks);
+  if (train) kt<<<grid, CB / VEC, smem, st>>>(mapG, mapH, mapDH, h0, Sckpt, (T*)dG, lddg, dbias, (int)Tn, (int)H, cblocks);
+  else       ks<<<grid, CB / VEC, smem, st>>>(mapG, mapH, mapDH, h0, Sckpt, (T*)dG, lddg, dbias, (int)Tn, (int)H, cblocks);
   SC_LAUNCH_RET();
 }
 
@@ -353,11 +378,12 @@ int scan_fwd_tma_dispatch(const void* G, int64_t ldg, const float* h0, const flo
   if (T == 0 || B * T >= ((int64_t)1 << 31) - TC) return SC_E_UNSUP;
   if (dtype == SC_BF16) {
     if (!tma_ok<bf16>(G, ldg, Hout, ldh, Hout, ldh, H)) return SC_E_UNSUP;
-    return scan_fwd_tma<bf16, false>(G, ldg, h0, s0, Hout, ldh, hT, sT, Sckpt, B, T, H, train, st);
+    if (scan_vec_choice() == 1) return scan_fwd_tma<bf16, 1, false>(G, ldg, h0, s0, Hout, ldh, hT, sT, Sckpt, B, T, H, train, st);
+    return scan_fwd_tma<bf16, 2, false>(G, ldg, h0, s0, Hout, ldh, hT, sT, Sckpt, B, T, H, train, st);
   }
   if (dtype == SC_F32) {
     if (!tma_ok<float>(G, ldg, Hout, ldh, Hout, ldh, H)) return SC_E_UNSUP;
-    return scan_fwd_tma<float, true>(G, ldg, h0, s0, Hout, ldh, hT, sT, Sckpt, B, T, H, train, st);
+    return scan_fwd_tma<float, 2, true>(G, ldg, h0, s0, Hout, ldh, hT, sT, Sckpt, B, T, H, train, st);
   }
   return SC_E_DTYPE;
 }
@@ -368,11 +394,12 @@ int scan_bwd_tma_dispatch(const void* G, int64_t ldg, const void* Hout, int64_t 
   if (T == 0 || B * T >= ((int64_t)1 << 31) - TC) return SC_E_UNSUP;
   if (dtype == SC_BF16) {
     if (!tma_ok<bf16>(G, ldg, Hout, ldh, dHout, lddh, H) || (lddg % 2) || ((uintptr_t)dG & 3)) return SC_E_UNSUP;
-    return scan_bwd_tma<bf16, false>(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, train, st);
+    if (scan_vec_choice() == 1) return scan_bwd_tma<bf16, 1, false>(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, train, st);
+    return scan_bwd_tma<bf16, 2, false>(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, train, st);
   }
   if (dtype == SC_F32) {
     if (!tma_ok<float>(G, ldg, Hout, ldh, dHout, lddh, H) || (lddg % 2) || ((uintptr_t)dG & 7)) return SC_E_UNSUP;
-    return scan_bwd_tma<float, true>(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, train, st);
+    return scan_bwd_tma<float, 2, true>(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, train, st);
   }
   return SC_E_DTYPE;
 }
