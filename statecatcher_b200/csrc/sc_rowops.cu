@@ -75,6 +75,73 @@ layernorm_fwd_kernel(const T* __restrict__ X, int64_t ldx, const float* __restri
   for (int i = lane; i < H; i += 32) st_f(y + i, (ld_f(x + i) - mu) * rs * w[i] + b[i]);
 }
 
+// Backward: dx per row (two warp reductions) and dw/db column sums.  Each lane owns the same
+// columns (lane + 32*j) for every row it visits, so the column sums live in registers (NJ per
+// lane) and touch shared/global memory once per block — the first version used two shared-memory
+// atomics per element and ran at 0.8 TB/s.  NJ = ceil(H/32) <= LN_MAXJ; larger H takes the
+// generic atomic kernel below.
+constexpr int LN_MAXJ = 32;
+
+template <typename T, int NJ>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_reg_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
+                         const float* __restrict__ w, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
+                         float* __restrict__ dw, float* __restrict__ db, int64_t M, int H,
+                         int64_t rows_per_block) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  float aw[NJ], ab[NJ], wv[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    aw[j] = 0.f; ab[j] = 0.f;
+    const int i = lane + 32 * j;
+    wv[j] = (i < H) ? w[i] : 0.f;
+  }
+  for (int64_t row = m0 + warp; row < m1; row += LN_WARPS) {
+    const T* x = X + row * ldx;
+    const T* dy = dY + row * lddy;
+    const float mu = mean[row], rs = rstd[row];
+    float dyv[NJ], xh[NJ];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int i = lane + 32 * j;
+      dyv[j] = (i < H) ? ld_f(dy + i) : 0.f;
+      xh[j] = (i < H) ? (ld_f(x + i) - mu) * rs : 0.f;
+      const float g = dyv[j] * wv[j];
+      s1 += g; s2 = fmaf(g, xh[j], s2);
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    T* dx = dX + row * lddx;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int i = lane + 32 * j;
+      if (i < H) st_f(dx + i, rs * (dyv[j] * wv[j] - s1 - xh[j] * s2));
+      aw[j] = fmaf(dyv[j], xh[j], aw[j]);
+      ab[j] += dyv[j];
+    }
+  }
+  // block partials through shared memory, then one global atomic per column per block
+  extern __shared__ float sm[];
+  float* sdw = sm;
+  float* sdb = sm + H;
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int i = lane + 32 * j;
+    if (i < H) { atomicAdd(sdw + i, aw[j]); atomicAdd(sdb + i, ab[j]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dw + i, sdw[i]);
+    atomicAdd(db + i, sdb[i]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
@@ -116,6 +183,27 @@ layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict
     atomicAdd(dw + i, sdw[i]);
     atomicAdd(db + i, sdb[i]);
   }
+}
+
+template <typename T>
+static void launch_ln_bwd(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* w, const float* mean,
+                          const float* rstd, void* dX, int64_t lddx, float* dw, float* db, int64_t M, int H,
+                          int64_t blocks, int64_t rpb, size_t smem, cudaStream_t st) {
+#define SC_LN_BWD(NJ) do { \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_reg_kernel<T, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    layernorm_bwd_reg_kernel<T, NJ><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
+        (T*)dX, lddx, dw, db, M, H, rpb); } while (0)
+  const int nj = (H + 31) / 32;
+  if (nj <= 2) SC_LN_BWD(2);
+  else if (nj <= 8) SC_LN_BWD(8);
+  else if (nj <= 16) SC_LN_BWD(16);
+  else if (nj <= LN_MAXJ) SC_LN_BWD(32);
+  else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<T><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd,
+        (T*)dX, lddx, dw, db, M, H, rpb);
+  }
+#undef SC_LN_BWD
 }
 
 }  // namespace sc
@@ -189,15 +277,9 @@ extern "C" int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int
   const int64_t rpb = cdiv(M, blocks);
   blocks = cdiv(M, rpb);
   const size_t smem = 2 * (size_t)H * sizeof(float);
-  if (dtype == SC_F32) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layernorm_bwd_kernel<float><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const float*)dY, lddy, (const float*)X, ldx, w, mean, rstd,
-        (float*)dX, lddx, dw, db, M, (int)H, rpb);
-  } else if (dtype == SC_BF16) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layernorm_bwd_kernel<bf16><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const bf16*)dY, lddy, (const bf16*)X, ldx, w, mean, rstd,
-        (bf16*)dX, lddx, dw, db, M, (int)H, rpb);
-  } else return SC_E_DTYPE;
+  if (dtype == SC_F32) launch_ln_bwd<float>(dY, lddy, X, ldx, w, mean, rstd, dX, lddx, dw, db, M, (int)H, blocks, rpb, smem, st);
+  else if (dtype == SC_BF16) launch_ln_bwd<bf16>(dY, lddy, X, ldx, w, mean, rstd, dX, lddx, dw, db, M, (int)H, blocks, rpb, smem, st);
+  else return SC_E_DTYPE;
   SC_LAUNCH_RET();
 }
 
