@@ -436,6 +436,14 @@ int scan_fwd_tma_dispatch(const void*, int64_t, const float*, const float*, void
                           int64_t, int64_t, int64_t, int, int, cudaStream_t);
 int scan_bwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const float*, const float*, const void*, int64_t,
                           void*, int64_t, float*, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+int sscan_fwd_tma_dispatch(const void*, const void*, const void*, int64_t, const void*, int64_t, const float*, void*, int64_t,
+                           float*, float*, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+int sscan_bwd_tma_dispatch(const void*, const void*, const void*, int64_t, const float*, const float*, const void*, int64_t,
+                           void*, void*, void*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+int hscan_fwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const float*, void*, int64_t, float*, int64_t, int64_t,
+                           int64_t, int, cudaStream_t);
+int hscan_bwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*, const void*, int64_t,
+                           void*, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
 }
 using namespace sc;
 
@@ -510,6 +518,10 @@ extern "C" int sc_lucy_sscan_fwd(const void* k, const void* v, const void* q, in
   }
   SC_CHECK_ARG(k && v && q && addend && A && S_all, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!scan_force_generic() && decay_mode == 0) {
+    const int rc = sscan_fwd_tma_dispatch(k, v, q, ldg, addend, ldadd, s0, A, lda, S_all, sT, B, T, H, dtype, train_mode, st);
+    if (rc != SC_E_UNSUP) return rc;
+  }
   const unsigned blocks = (unsigned)cdiv(B * H, 128);
   if (dtype == SC_BF16)
     sscan_fwd_kernel<bf16, false><<<blocks, 128, 0, st>>>((const bf16*)k, (const bf16*)v, (const bf16*)q, ldg,
@@ -532,6 +544,10 @@ extern "C" int sc_lucy_sscan_bwd(const void* k, const void* v, const void* q, in
   if (T == 0) return 0;
   SC_CHECK_ARG(k && v && q && S_all && dA && dk && dv && dq, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!scan_force_generic() && decay_mode == 0) {
+    const int rc = sscan_bwd_tma_dispatch(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, B, T, H, dtype, train_mode, st);
+    if (rc != SC_E_UNSUP) return rc;
+  }
   const unsigned blocks = (unsigned)cdiv(B * H, 128);
   if (dtype == SC_BF16) {
     if (decay_mode == 1)
@@ -558,6 +574,10 @@ extern "C" int sc_lucy_hscan_fwd(const void* An, int64_t ldan, const void* Zn, i
   SC_CHECK_ARG(h0 && hT, SC_E_BADARG);
   SC_CHECK_ARG(T == 0 || (An && Zn && Hout), SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!scan_force_generic() && T > 0) {
+    const int rc = hscan_fwd_tma_dispatch(An, ldan, Zn, ldzn, h0, Hout, ldh, hT, B, T, H, dtype, st);
+    if (rc != SC_E_UNSUP) return rc;
+  }
   const unsigned blocks = (unsigned)cdiv(B * H, 128);
   if (dtype == SC_BF16)
     hscan_fwd_kernel<bf16, false><<<blocks, 128, 0, st>>>((const bf16*)An, ldan, (const bf16*)Zn, ldzn, h0, (bf16*)Hout, ldh, hT, (int)B, (int)T, (int)H);
@@ -576,6 +596,10 @@ extern "C" int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, i
   if (T == 0) return 0;
   SC_CHECK_ARG(An && Zn && Hout && h0 && dHout && dAn && dZn, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!scan_force_generic()) {
+    const int rc = hscan_bwd_tma_dispatch(An, ldan, Zn, ldzn, Hout, ldh, h0, dHout, lddh, dAn, lddan, dZn, lddzn, B, T, H, dtype, st);
+    if (rc != SC_E_UNSUP) return rc;
+  }
   const unsigned blocks = (unsigned)cdiv(B * H, 128);
   if (dtype == SC_BF16)
     hscan_bwd_kernel<bf16, false><<<blocks, 128, 0, st>>>((const bf16*)An, ldan, (const bf16*)Zn, ldzn, (const bf16*)Hout, ldh, h0,

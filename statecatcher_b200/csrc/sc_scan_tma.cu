@@ -15,6 +15,7 @@
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
 #include <stdlib.h>
+#include <initializer_list>
 
 namespace sc {
 
@@ -304,6 +305,323 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
   }
 }
 
+// ------------------------------------------------------------------ split scans ------
+// TMA-staged versions of the general-path kernels of sc_scan.cu (layer_norm=True /
+// fused_ops=False): same thread/CTA mapping and stage ring as the fused kernels above.
+constexpr int SV = 2;                 // channels per thread in the split kernels
+constexpr int SPLIT_THREADS = CB / SV;
+
+struct ScanBlock {
+  int tid, b, c0, ch, nchunk;
+  bool live;
+  uint32_t sbase;
+};
+__device__ __forceinline__ ScanBlock scan_block(int Tn, int H, int cblocks, const uint8_t* smem) {
+  ScanBlock k;
+  k.tid = threadIdx.x;
+  k.b = blockIdx.x / cblocks;
+  k.c0 = (blockIdx.x % cblocks) * CB;
+  k.ch = k.c0 + k.tid * SV;
+  k.live = k.ch < H;
+  k.nchunk = (Tn + TC - 1) / TC;
+  k.sbase = smem_u32(smem);
+  return k;
+}
+template <int NST>
+__device__ __forceinline__ void scan_bars_init(uint64_t* bars, int tid) {
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+// S scan + second application.  A = addend + s'.  Learned decay only (prefix_sum keeps the
+// simple kernel).  Stage = k, v, q, addend boxes.
+template <typename T, int NST, bool TRAIN, bool PRECISE>
+__global__ void __launch_bounds__(SPLIT_THREADS)
+sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
+                     const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapAdd,
+                     const float* __restrict__ s0, T* __restrict__ A, int64_t lda, float* __restrict__ S_all,
+                     float* __restrict__ sT, int Tn, int H, int cblocks) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int STAGE = 4 * BOX;
+  __shared__ __align__(8) uint64_t bars[NST];
+  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  scan_bars_init<NST>(bars, k.tid);
+  auto issue = [&](int chunk) {
+    const int st = chunk % NST;
+    const uint32_t bar = smem_u32(&bars[st]);
+    mbar_expect_tx(bar, STAGE);
+    const int row = k.b * Tn + chunk * TC;
+    const uint32_t d = k.sbase + st * STAGE;
+    tma_load_2d(d, &mapK, bar, k.c0, row);
+    tma_load_2d(d + BOX, &mapV, bar, k.c0, row);
+    tma_load_2d(d + 2 * BOX, &mapQ, bar, k.c0, row);
+    tma_load_2d(d + 3 * BOX, &mapAdd, bar, k.c0, row);
+  };
+  if (k.tid == 0)
+    for (int c = 0; c < NST - 1 && c < k.nchunk; ++c) issue(c);
+  float S[SV];
+#pragma unroll
+  for (int i = 0; i < SV; ++i) S[i] = (TRAIN || !k.live) ? 0.f : s0[(int64_t)k.b * H + k.ch + i];
+  T* ao = A + (int64_t)k.b * Tn * lda + k.ch;
+  float* so = S_all + (int64_t)k.b * Tn * H + k.ch;
+  for (int c = 0; c < k.nchunk; ++c) {
+    __syncthreads();
+    if (k.tid == 0 && c + NST - 1 < k.nchunk) issue(c + NST - 1);
+    mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
+    const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
+    const int t0 = c * TC;
+#pragma unroll
+    for (int u = 0; u < TC; ++u) {
+      if (t0 + u < Tn) {
+        float kk[SV], vv[SV], qq[SV], ad[SV], out[SV];
+        lds2(st + (0 * TC + u) * CB, k.tid, kk);
+        lds2(st + (1 * TC + u) * CB, k.tid, vv);
+        lds2(st + (2 * TC + u) * CB, k.tid, qq);
+        lds2(st + (3 * TC + u) * CB, k.tid, ad);
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const float d = sigmoidf_<PRECISE>(qq[i]);
+          const float kv = kk[i] * vv[i];
+          S[i] = fmaf(d, S[i], kv);
+          out[i] = ad[i] + (TRAIN ? fmaf(d, S[i], kv) : S[i]);
+        }
+        if (k.live) {
+          stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
+          *reinterpret_cast<float2*>(so + (int64_t)(t0 + u) * H) = make_float2(S[0], S[1]);
+        }
+      }
+    }
+  }
+  if (k.live && !TRAIN && sT != nullptr) {
+#pragma unroll
+    for (int i = 0; i < SV; ++i) sT[(int64_t)k.b * H + k.ch + i] = S[i];
+  }
+}
+
+// Reverse-time adjoint of the S scan.  Stage = k, v, q, dA boxes + an fp32 S box of TC+1 rows
+// starting one row early (S_{t-1} .. S_{t+TC-1}).
+template <typename T, int NST, bool TRAIN, bool PRECISE>
+__global__ void __launch_bounds__(SPLIT_THREADS)
+sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
+                     const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapDA,
+                     const __grid_constant__ CUtensorMap mapS, const float* __restrict__ s0,
+                     T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dq, int64_t lddg,
+                     int Tn, int H, int cblocks) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int SBOX = (TC + 1) * CB * 4;
+  constexpr int STAGE = 4 * BOX + SBOX;
+  __shared__ __align__(8) uint64_t bars[NST];
+  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  scan_bars_init<NST>(bars, k.tid);
+  auto issue = [&](int it) {
+    const int chunk = k.nchunk - 1 - it;
+    const int st = it % NST;
+    const uint32_t bar = smem_u32(&bars[st]);
+    mbar_expect_tx(bar, STAGE);
+    const int row = k.b * Tn + chunk * TC;
+    const uint32_t d = k.sbase + st * STAGE;
+    tma_load_2d(d, &mapK, bar, k.c0, row);
+    tma_load_2d(d + BOX, &mapV, bar, k.c0, row);
+    tma_load_2d(d + 2 * BOX, &mapQ, bar, k.c0, row);
+    tma_load_2d(d + 3 * BOX, &mapDA, bar, k.c0, row);
+    tma_load_2d(d + 4 * BOX, &mapS, bar, k.c0, row - 1);
+  };
+  if (k.tid == 0)
+    for (int it = 0; it < NST - 1 && it < k.nchunk; ++it) issue(it);
+  float ds[SV], sfirst[SV];
+#pragma unroll
+  for (int i = 0; i < SV; ++i) {
+    ds[i] = 0.f;
+    sfirst[i] = (TRAIN || !k.live) ? 0.f : s0[(int64_t)k.b * H + k.ch + i];
+  }
+  const int64_t obase = (int64_t)k.b * Tn * lddg + k.ch;
+  for (int it = 0; it < k.nchunk; ++it) {
+    const int chunk = k.nchunk - 1 - it;
+    __syncthreads();
+    if (k.tid == 0 && it + NST - 1 < k.nchunk) issue(it + NST - 1);
+    mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
+    const uint8_t* sp = smem + (it % NST) * STAGE;
+    const T* st = reinterpret_cast<const T*>(sp);
+    const float* ss = reinterpret_cast<const float*>(sp + 4 * BOX);     // row r holds S_{t0-1+r}
+    const int t0 = chunk * TC;
+#pragma unroll
+    for (int u = TC - 1; u >= 0; --u) {
+      const int t = t0 + u;
+      if (t < Tn) {
+        float kk[SV], vv[SV], qq[SV], da[SV], St[SV], Sp[SV], ok[SV], ov[SV], oq[SV];
+        lds2(st + (0 * TC + u) * CB, k.tid, kk);
+        lds2(st + (1 * TC + u) * CB, k.tid, vv);
+        lds2(st + (2 * TC + u) * CB, k.tid, qq);
+        lds2(st + (3 * TC + u) * CB, k.tid, da);
+        lds2(ss + (u + 1) * CB, k.tid, St);
+        lds2(ss + u * CB, k.tid, Sp);
+        if (t == 0) {
+#pragma unroll
+          for (int i = 0; i < SV; ++i) Sp[i] = sfirst[i];
+        }
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const float d = sigmoidf_<PRECISE>(qq[i]);
+          float sig, dkv, dd;
+          if (TRAIN) {
+            sig = fmaf(d, da[i], ds[i]);
+            dkv = da[i] + sig;
+            dd = fmaf(St[i], da[i], Sp[i] * sig);
+          } else {
+            sig = da[i] + ds[i];
+            dkv = sig;
+            dd = Sp[i] * sig;
+          }
+          ds[i] = d * sig;
+          ok[i] = dkv * vv[i];
+          ov[i] = dkv * kk[i];
+          oq[i] = dd * d * (1.f - d);
+        }
+        if (k.live) {
+          const int64_t o = obase + (int64_t)t * lddg;
+          stg_vec<T>(dk + o, ok);
+          stg_vec<T>(dv + o, ov);
+          stg_vec<T>(dq + o, oq);
+        }
+      }
+    }
+  }
+}
+
+// h scan.  Stage = An, Zn boxes.
+template <typename T, int NST, bool PRECISE>
+__global__ void __launch_bounds__(SPLIT_THREADS)
+hscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapZ,
+                     const float* __restrict__ h0, T* __restrict__ Hout, int64_t ldh, float* __restrict__ hT,
+                     int Tn, int H, int cblocks) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int STAGE = 2 * BOX;
+  __shared__ __align__(8) uint64_t bars[NST];
+  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  scan_bars_init<NST>(bars, k.tid);
+  auto issue = [&](int chunk) {
+    const int st = chunk % NST;
+    const uint32_t bar = smem_u32(&bars[st]);
+    mbar_expect_tx(bar, STAGE);
+    const int row = k.b * Tn + chunk * TC;
+    tma_load_2d(k.sbase + st * STAGE, &mapA, bar, k.c0, row);
+    tma_load_2d(k.sbase + st * STAGE + BOX, &mapZ, bar, k.c0, row);
+  };
+  if (k.tid == 0)
+    for (int c = 0; c < NST - 1 && c < k.nchunk; ++c) issue(c);
+  float h[SV];
+#pragma unroll
+  for (int i = 0; i < SV; ++i) h[i] = k.live ? h0[(int64_t)k.b * H + k.ch + i] : 0.f;
+  T* ho = Hout + (int64_t)k.b * Tn * ldh + k.ch;
+  for (int c = 0; c < k.nchunk; ++c) {
+    __syncthreads();
+    if (k.tid == 0 && c + NST - 1 < k.nchunk) issue(c + NST - 1);
+    mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
+    const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
+    const int t0 = c * TC;
+#pragma unroll
+    for (int u = 0; u < TC; ++u) {
+      if (t0 + u < Tn) {
+        float an[SV], zn[SV], out[SV];
+        lds2(st + u * CB, k.tid, an);
+        lds2(st + (TC + u) * CB, k.tid, zn);
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const float cc = tanhf_<PRECISE>(an[i]);
+          const float zh = sigmoidf_<PRECISE>(zn[i]);
+          h[i] = fmaf(zh, h[i] - cc, cc);
+          out[i] = h[i];
+        }
+        if (k.live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
+      }
+    }
+  }
+  if (k.live) {
+#pragma unroll
+    for (int i = 0; i < SV; ++i) hT[(int64_t)k.b * H + k.ch + i] = h[i];
+  }
+}
+
+// Reverse-time adjoint of the h scan.  Stage = An, Zn, dHout boxes + Hout shifted one row back.
+template <typename T, int NST, bool PRECISE>
+__global__ void __launch_bounds__(SPLIT_THREADS)
+hscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapZ,
+                     const __grid_constant__ CUtensorMap mapDH, const __grid_constant__ CUtensorMap mapH,
+                     const float* __restrict__ h0, T* __restrict__ dAn, int64_t lddan, T* __restrict__ dZn,
+                     int64_t lddzn, int Tn, int H, int cblocks) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int STAGE = 4 * BOX;
+  __shared__ __align__(8) uint64_t bars[NST];
+  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  scan_bars_init<NST>(bars, k.tid);
+  auto issue = [&](int it) {
+    const int chunk = k.nchunk - 1 - it;
+    const int st = it % NST;
+    const uint32_t bar = smem_u32(&bars[st]);
+    mbar_expect_tx(bar, STAGE);
+    const int row = k.b * Tn + chunk * TC;
+    const uint32_t d = k.sbase + st * STAGE;
+    tma_load_2d(d, &mapA, bar, k.c0, row);
+    tma_load_2d(d + BOX, &mapZ, bar, k.c0, row);
+    tma_load_2d(d + 2 * BOX, &mapDH, bar, k.c0, row);
+    tma_load_2d(d + 3 * BOX, &mapH, bar, k.c0, row - 1);
+  };
+  if (k.tid == 0)
+    for (int it = 0; it < NST - 1 && it < k.nchunk; ++it) issue(it);
+  float gz[SV], hfirst[SV];
+#pragma unroll
+  for (int i = 0; i < SV; ++i) {
+    gz[i] = 0.f;
+    hfirst[i] = k.live ? h0[(int64_t)k.b * H + k.ch + i] : 0.f;
+  }
+  T* oa = dAn + (int64_t)k.b * Tn * lddan + k.ch;
+  T* oz = dZn + (int64_t)k.b * Tn * lddzn + k.ch;
+  for (int it = 0; it < k.nchunk; ++it) {
+    const int chunk = k.nchunk - 1 - it;
+    __syncthreads();
+    if (k.tid == 0 && it + NST - 1 < k.nchunk) issue(it + NST - 1);
+    mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
+    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
+    const int t0 = chunk * TC;
+#pragma unroll
+    for (int u = TC - 1; u >= 0; --u) {
+      const int t = t0 + u;
+      if (t < Tn) {
+        float an[SV], zn[SV], go[SV], hp[SV], da[SV], dz[SV];
+        lds2(st + u * CB, k.tid, an);
+        lds2(st + (TC + u) * CB, k.tid, zn);
+        lds2(st + (2 * TC + u) * CB, k.tid, go);
+        lds2(st + (3 * TC + u) * CB, k.tid, hp);
+        if (t == 0) {
+#pragma unroll
+          for (int i = 0; i < SV; ++i) hp[i] = hfirst[i];
+        }
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const float cc = tanhf_<PRECISE>(an[i]);
+          const float zh = sigmoidf_<PRECISE>(zn[i]);
+          const float gam = go[i] + gz[i];
+          gz[i] = zh * gam;
+          const float omz = 1.f - zh;
+          da[i] = gam * omz * fmaf(-cc, cc, 1.f);
+          dz[i] = gam * (hp[i] - cc) * zh * omz;
+        }
+        if (k.live) {
+          stg_vec<T>(oa + (int64_t)t * lddan, da);
+          stg_vec<T>(oz + (int64_t)t * lddzn, dz);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host -------------
 template <typename T>
 static bool tma_ok(const void* G, int64_t ldg, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t H) {
@@ -401,6 +719,131 @@ int scan_bwd_tma_dispatch(const void* G, int64_t ldg, const void* Hout, int64_t 
     if (!tma_ok<float>(G, ldg, Hout, ldh, dHout, lddh, H) || (lddg % 2) || ((uintptr_t)dG & 7)) return SC_E_UNSUP;
     return scan_bwd_tma<float, 2, true>(G, ldg, Hout, ldh, h0, Sckpt, dHout, lddh, dG, lddg, dbias, B, T, H, train, st);
   }
+  return SC_E_DTYPE;
+}
+
+
+// ---- split-scan dispatch (SC_E_UNSUP -> caller uses the simple kernels) ----
+template <typename T>
+static bool split_ok(std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds, int64_t H, int64_t B,
+                     int64_t Tn) {
+  constexpr int per16 = 16 / (int)sizeof(T);
+  if (H % per16 != 0 || Tn == 0 || B * Tn >= ((int64_t)1 << 31) - TC - 1) return false;
+  for (const void* p : ptrs) if (!aligned16(p)) return false;
+  for (int64_t l : lds) if (l % per16) return false;
+  return get_encode() != nullptr;
+}
+template <typename K>
+static int set_smem(K kern, int smem) {
+  return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+template <typename T, bool PRECISE>
+static int sscan_fwd_tma_t(const void* k, const void* v, const void* q, int64_t ldg, const void* addend, int64_t ldadd,
+                           const float* s0, void* A, int64_t lda, float* S_all, float* sT, int64_t B, int64_t Tn,
+                           int64_t H, int train, cudaStream_t st) {
+  if (!split_ok<T>({k, v, q, addend, A, S_all}, {ldg, ldadd, lda}, H, B, Tn)) return SC_E_UNSUP;
+  constexpr int NST = 4;
+  constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
+  CUtensorMap mk, mv, mq, ma;
+  if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
+      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, TC) || !make_scan_map<T>(&ma, addend, B * Tn, H, ldadd, TC))
+    return SC_E_UNSUP;
+  const int cblocks = (int)cdiv(H, CB);
+  const unsigned grid = (unsigned)(B * cblocks);
+  auto kt = sscan_fwd_tma_kernel<T, NST, true, PRECISE>;
+  auto ks = sscan_fwd_tma_kernel<T, NST, false, PRECISE>;
+  int e = set_smem(kt, smem); if (e) return e;
+  e = set_smem(ks, smem); if (e) return e;
+  if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, ma, s0, (T*)A, lda, S_all, sT, (int)Tn, (int)H, cblocks);
+  else       ks<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, ma, s0, (T*)A, lda, S_all, sT, (int)Tn, (int)H, cblocks);
+  SC_LAUNCH_RET();
+}
+int sscan_fwd_tma_dispatch(const void* k, const void* v, const void* q, int64_t ldg, const void* addend, int64_t ldadd,
+                           const float* s0, void* A, int64_t lda, float* S_all, float* sT, int64_t B, int64_t T,
+                           int64_t H, int dtype, int train, cudaStream_t st) {
+  if (dtype == SC_BF16) return sscan_fwd_tma_t<bf16, false>(k, v, q, ldg, addend, ldadd, s0, A, lda, S_all, sT, B, T, H, train, st);
+  if (dtype == SC_F32) return sscan_fwd_tma_t<float, true>(k, v, q, ldg, addend, ldadd, s0, A, lda, S_all, sT, B, T, H, train, st);
+  return SC_E_DTYPE;
+}
+
+template <typename T, bool PRECISE>
+static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t ldg, const float* S_all, const float* s0,
+                           const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, int64_t B,
+                           int64_t Tn, int64_t H, int train, cudaStream_t st) {
+  if (!split_ok<T>({k, v, q, dA, S_all}, {ldg, ldda}, H, B, Tn) || (lddg % 2) ||
+      (((uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dq) & (2 * sizeof(T) - 1)))
+    return SC_E_UNSUP;
+  constexpr int NST = 3;
+  constexpr int smem = NST * (4 * TC * CB * (int)sizeof(T) + (TC + 1) * CB * 4);
+  CUtensorMap mk, mv, mq, mda, ms;
+  if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
+      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mda, dA, B * Tn, H, ldda, TC) ||
+      !make_scan_map<float>(&ms, S_all, B * Tn, H, H, TC + 1))
+    return SC_E_UNSUP;
+  const int cblocks = (int)cdiv(H, CB);
+  const unsigned grid = (unsigned)(B * cblocks);
+  auto kt = sscan_bwd_tma_kernel<T, NST, true, PRECISE>;
+  auto ks = sscan_bwd_tma_kernel<T, NST, false, PRECISE>;
+  int e = set_smem(kt, smem); if (e) return e;
+  e = set_smem(ks, smem); if (e) return e;
+  if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, (int)Tn, (int)H, cblocks);
+  else       ks<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, (int)Tn, (int)H, cblocks);
+  SC_LAUNCH_RET();
+}
+int sscan_bwd_tma_dispatch(const void* k, const void* v, const void* q, int64_t ldg, const float* S_all, const float* s0,
+                           const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, int64_t B,
+                           int64_t T, int64_t H, int dtype, int train, cudaStream_t st) {
+  if (dtype == SC_BF16) return sscan_bwd_tma_t<bf16, false>(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, B, T, H, train, st);
+  if (dtype == SC_F32) return sscan_bwd_tma_t<float, true>(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, B, T, H, train, st);
+  return SC_E_DTYPE;
+}
+
+template <typename T, bool PRECISE>
+static int hscan_fwd_tma_t(const void* An, int64_t ldan, const void* Zn, int64_t ldzn, const float* h0, void* Hout,
+                           int64_t ldh, float* hT, int64_t B, int64_t Tn, int64_t H, cudaStream_t st) {
+  if (!split_ok<T>({An, Zn}, {ldan, ldzn}, H, B, Tn) || (ldh % 2) || ((uintptr_t)Hout & (2 * sizeof(T) - 1))) return SC_E_UNSUP;
+  constexpr int NST = 4;
+  constexpr int smem = NST * 2 * TC * CB * (int)sizeof(T);
+  CUtensorMap ma, mz;
+  if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TC) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TC)) return SC_E_UNSUP;
+  const int cblocks = (int)cdiv(H, CB);
+  auto kk = hscan_fwd_tma_kernel<T, NST, PRECISE>;
+  int e = set_smem(kk, smem); if (e) return e;
+  kk<<<(unsigned)(B * cblocks), SPLIT_THREADS, smem, st>>>(ma, mz, h0, (T*)Hout, ldh, hT, (int)Tn, (int)H, cblocks);
+  SC_LAUNCH_RET();
+}
+int hscan_fwd_tma_dispatch(const void* An, int64_t ldan, const void* Zn, int64_t ldzn, const float* h0, void* Hout,
+                           int64_t ldh, float* hT, int64_t B, int64_t T, int64_t H, int dtype, cudaStream_t st) {
+  if (dtype == SC_BF16) return hscan_fwd_tma_t<bf16, false>(An, ldan, Zn, ldzn, h0, Hout, ldh, hT, B, T, H, st);
+  if (dtype == SC_F32) return hscan_fwd_tma_t<float, true>(An, ldan, Zn, ldzn, h0, Hout, ldh, hT, B, T, H, st);
+  return SC_E_DTYPE;
+}
+
+template <typename T, bool PRECISE>
+static int hscan_bwd_tma_t(const void* An, int64_t ldan, const void* Zn, int64_t ldzn, const void* Hout, int64_t ldh,
+                           const float* h0, const void* dHout, int64_t lddh, void* dAn, int64_t lddan, void* dZn,
+                           int64_t lddzn, int64_t B, int64_t Tn, int64_t H, cudaStream_t st) {
+  if (!split_ok<T>({An, Zn, Hout, dHout}, {ldan, ldzn, ldh, lddh}, H, B, Tn) || (lddan % 2) || (lddzn % 2) ||
+      (((uintptr_t)dAn | (uintptr_t)dZn) & (2 * sizeof(T) - 1)))
+    return SC_E_UNSUP;
+  constexpr int NST = 3;
+  constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
+  CUtensorMap ma, mz, mdh, mh;
+  if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TC) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TC) ||
+      !make_scan_map<T>(&mdh, dHout, B * Tn, H, lddh, TC) || !make_scan_map<T>(&mh, Hout, B * Tn, H, ldh, TC))
+    return SC_E_UNSUP;
+  const int cblocks = (int)cdiv(H, CB);
+  auto kk = hscan_bwd_tma_kernel<T, NST, PRECISE>;
+  int e = set_smem(kk, smem); if (e) return e;
+  kk<<<(unsigned)(B * cblocks), SPLIT_THREADS, smem, st>>>(ma, mz, mdh, mh, h0, (T*)dAn, lddan, (T*)dZn, lddzn, (int)Tn, (int)H, cblocks);
+  SC_LAUNCH_RET();
+}
+int hscan_bwd_tma_dispatch(const void* An, int64_t ldan, const void* Zn, int64_t ldzn, const void* Hout, int64_t ldh,
+                           const float* h0, const void* dHout, int64_t lddh, void* dAn, int64_t lddan, void* dZn,
+                           int64_t lddzn, int64_t B, int64_t T, int64_t H, int dtype, cudaStream_t st) {
+  if (dtype == SC_BF16) return hscan_bwd_tma_t<bf16, false>(An, ldan, Zn, ldzn, Hout, ldh, h0, dHout, lddh, dAn, lddan, dZn, lddzn, B, T, H, st);
+  if (dtype == SC_F32) return hscan_bwd_tma_t<float, true>(An, ldan, Zn, ldzn, Hout, ldh, h0, dHout, lddh, dAn, lddan, dZn, lddzn, B, T, H, st);
   return SC_E_DTYPE;
 }
 
