@@ -142,6 +142,97 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
   }
 }
 
+// Vectorised variant for H % 256 == 0: a lane owns 8 consecutive columns per 256-column
+// group (16-byte loads for bf16, 2 x 16 for fp32), NV = H/256 groups.
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void ld8<bf16>(const bf16* p, float (&f)[8]) {
+  Vec<bf16, 8> v; v.raw = __ldg(reinterpret_cast<const uint4*>(p)); unpack(v, f);
+}
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&f)[8]);
+template <> __device__ __forceinline__ void st8<bf16>(bf16* p, const float (&f)[8]) {
+  const Vec<bf16, 8> v = pack(f, (bf16*)nullptr);
+  *reinterpret_cast<uint4*>(p) = v.raw;
+}
+template <> __device__ __forceinline__ void st8<float>(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_vec_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
+                         const float* __restrict__ w, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
+                         float* __restrict__ dw, float* __restrict__ db, int64_t M, int H,
+                         int64_t rows_per_block) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  float aw[NV][8], ab[NV][8], wv[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      aw[j][e] = 0.f; ab[j][e] = 0.f;
+      wv[j][e] = w[(lane + 32 * j) * 8 + e];
+    }
+  for (int64_t row = m0 + warp; row < m1; row += LN_WARPS) {
+    const T* x = X + row * ldx;
+    const T* dy = dY + row * lddy;
+    const float mu = mean[row], rs = rstd[row];
+    float dyv[NV][8], xh[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      ld8<T>(dy + (lane + 32 * j) * 8, dyv[j]);
+      ld8<T>(x + (lane + 32 * j) * 8, xh[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[j][e] = (xh[j][e] - mu) * rs;
+        const float g = dyv[j][e] * wv[j][e];
+        s1 += g; s2 = fmaf(g, xh[j][e], s2);
+      }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    T* dx = dX + row * lddx;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o[e] = rs * (dyv[j][e] * wv[j][e] - s1 - xh[j][e] * s2);
+        aw[j][e] = fmaf(dyv[j][e], xh[j][e], aw[j][e]);
+        ab[j][e] += dyv[j][e];
+      }
+      st8<T>(dx + (lane + 32 * j) * 8, o);
+    }
+  }
+  extern __shared__ float sm[];
+  float* sdw = sm;
+  float* sdb = sm + H;
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(sdw + (lane + 32 * j) * 8 + e, aw[j][e]);
+      atomicAdd(sdb + (lane + 32 * j) * 8 + e, ab[j][e]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dw + i, sdw[i]);
+    atomicAdd(db + i, sdb[i]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
@@ -193,6 +284,21 @@ static void launch_ln_bwd(const void* dY, int64_t lddy, const void* X, int64_t l
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_reg_kernel<T, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     layernorm_bwd_reg_kernel<T, NJ><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
         (T*)dX, lddx, dw, db, M, H, rpb); } while (0)
+  const bool vec_ok = (H % 256 == 0) && H <= 1024 && (lddy % 8 == 0) && (ldx % 8 == 0) && (lddx % 8 == 0) &&
+                      aligned16(dY) && aligned16(X) && aligned16(dX);
+#define SC_LN_BWD_V(NV) do { \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_vec_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    layernorm_bwd_vec_kernel<T, NV><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
+        (T*)dX, lddx, dw, db, M, H, rpb); } while (0)
+  if (vec_ok) {
+    switch (H / 256) {
+      case 1: SC_LN_BWD_V(1); return;
+      case 2: SC_LN_BWD_V(2); return;
+      case 3: SC_LN_BWD_V(3); return;
+      default: SC_LN_BWD_V(4); return;
+    }
+  }
+#undef SC_LN_BWD_V
   const int nj = (H + 31) / 32;
   if (nj <= 2) SC_LN_BWD(2);
   else if (nj <= 8) SC_LN_BWD(8);
