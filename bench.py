@@ -229,13 +229,13 @@ def main():
 
     # a few distinct synthetic segments per rank, cycled (streams of this rank: seed by rank)
     NSEG = 2
-    host = [synth_batch(W, 1234 + rank * 100 + i) for i in range(NSEG)]
-    xh = [h[0].pin_memory() for h in host]
-    tokh = [h[1].pin_memory() for h in host]
-    xd = [h[0].to(dev) for h in host]
-    tokd = [h[1].to(dev) for h in host]
-    inld = [torch.tensor(h[2], device=dev) for h in host]
-    tgld = [torch.tensor(h[3], device=dev) for h in host]
+    hostb = [synth_batch(W, 1234 + rank * 100 + i) for i in range(NSEG)]
+    xh = [h[0].pin_memory() for h in hostb]
+    tokh = [h[1].pin_memory() for h in hostb]
+    xd = [h[0].to(dev) for h in hostb]
+    tokd = [h[1].to(dev) for h in hostb]
+    inld = [torch.tensor(h[2], device=dev) for h in hostb]
+    tgld = [torch.tensor(h[3], device=dev) for h in hostb]
     frames_step = W["B"] * W["T"]
     state = {"s": None}
 
@@ -258,7 +258,7 @@ def main():
         st = sb.detach_states(state["s"]) if state["s"] else None
         model.zero_grad(set_to_none=True)
         logits, state["s"] = model(xbuf, st) if st else model(xbuf)
-        loss = sb.ctc_loss_from_logits(logits, tokbuf[j], host[j][2], host[j][3], zero_infinity=True)  # list lengths -> H2D
+        loss = sb.ctc_loss_from_logits(logits, tokbuf[j], hostb[j][2], hostb[j][3], zero_infinity=True)  # list lengths -> H2D
         loss.backward()
         return loss.item()                                          # D2H result read
 
@@ -267,12 +267,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host["ms"] = (time.perf_counter() - t0) * 1e3 / steps     # host time to ENQUEUE one step
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -292,6 +296,7 @@ def main():
     _lib.kernels = 0
     _lib.profile = []
     ms = timed(step_resident, args.steps)
+    host_enqueue_ms = host["ms"]
     prof, _lib.profile = _lib.profile, None
     launches = _lib.kernels
     clocks = sampler.stop() if rank == 0 else None
@@ -325,8 +330,8 @@ def main():
             t = ev0.elapsed_time(ev1)
             rate = (work / (t * 1e-3) / 1e12) if t > 0 else 0
             print(f"  {name:20s} {str(shape):28s} {t:8.3f} ms  {rate:8.1f} T(FLOP|B)/s", file=sys.stderr)
-    live_frames = sum(sum(min(t, W["T"]) for t in h[2]) for h in host) / NSEG
-    umean = sum(sum(h[3]) for h in host) / NSEG / W["B"]
+    live_frames = sum(sum(min(t, W["T"]) for t in h[2]) for h in hostb) / NSEG
+    umean = sum(sum(h[3]) for h in hostb) / NSEG / W["B"]
 
     def roof(names, bound, work_override=None):
         t = sum(fam[n]["ms"] for n in names if n in fam)
@@ -374,6 +379,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": roofline,
         "roofline_by_kernel": roofs,
         "cpu_baseline": cpu,

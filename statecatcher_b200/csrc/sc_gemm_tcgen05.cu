@@ -58,8 +58,36 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 struct GemmParams {
   int64_t I, J, R;          // output rows, output cols, reduction length
   int tiles_i, tiles_j, splits, kb_per_split, kb_total;
+  int64_t sk_per_cluster;   // > 0: stream-K — each CTA pair owns this many consecutive (tile, k-block) units
   void* D; int64_t ldd;
   const float* bias;
+};
+
+// Work decomposition, identical in all three warp roles.  Tiled mode: item w -> (tile pair,
+// split) with a fixed k-block range.  Stream-K mode (wgrad): the (tile pair, k-block) iteration
+// space is cut into equal contiguous ranges, one per CTA pair, so every pair does the same
+// number of k-blocks whatever the tile count; partial tiles are summed by the red.add epilogue.
+struct WorkIter {
+  int64_t w, wend, wstep;      // tiled: item index; stream-K: cursor in k-block units
+  __device__ __forceinline__ bool next(const GemmParams& p, uint32_t rank, int& ti, int& tj, int& kb0, int& kb1) {
+    if (w >= wend) return false;
+    if (p.sk_per_cluster > 0) {
+      const int64_t tile = w / p.kb_total;
+      kb0 = (int)(w % p.kb_total);
+      const int64_t room = wend - w;
+      kb1 = (int)((int64_t)p.kb_total - kb0 < room ? (int64_t)p.kb_total : kb0 + room);
+      tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
+      w += kb1 - kb0;
+    } else {
+      const int split = (int)(w % p.splits);
+      const int64_t tile = w / p.splits;
+      tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
+      kb0 = split * p.kb_per_split;
+      kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      w += wstep;
+    }
+    return true;
+  }
 };
 
 // EPI: 0 = bf16 store (+bias), 1 = fp32 store (+bias), 2 = fp32 atomic accumulate (split-R)
@@ -103,18 +131,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pairs_i = (p.tiles_i + 1) / 2;
   const int64_t total = (int64_t)pairs_i * p.tiles_j * p.splits;
-  const int64_t w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
+  WorkIter it0;
+  if (p.sk_per_cluster > 0) {
+    const int64_t units = (int64_t)pairs_i * p.tiles_j * p.kb_total;
+    it0.w = (int64_t)(blockIdx.x >> 1) * p.sk_per_cluster;
+    it0.wend = it0.w + p.sk_per_cluster < units ? it0.w + p.sk_per_cluster : units;
+    it0.wstep = 0;
+  } else {
+    it0.w = blockIdx.x >> 1; it0.wend = total; it0.wstep = gridDim.x >> 1;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t w = w0; w < total; w += wstep) {
-        const int split = (int)(w % p.splits);
-        const int64_t tile = w / p.splits;
-        const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      WorkIter it = it0;
+      int ti, tj, kb0, kb1;
+      while (it.next(p, rank, ti, tj, kb0, kb1)) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
@@ -148,10 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                              ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t w = w0; w < total; w += wstep) {
-        const int split = (int)(w % p.splits);
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      WorkIter it = it0;
+      int ti, tj, kb0, kb1;
+      while (it.next(p, rank, ti, tj, kb0, kb1)) {
         mbar_wait(tempty(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TN;
@@ -181,9 +213,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
     float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int64_t w = w0; w < total; w += wstep) {
-      const int64_t tile = w / p.splits;
-      const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
+    WorkIter it = it0;
+    int ti, tj, kb0, kb1;
+    while (it.next(p, rank, ti, tj, kb0, kb1)) {
       const int64_t col0 = (int64_t)tj * TN;
       if (EPI != 2 && p.bias != nullptr) {
         // stage this tile's bias once (double-buffered with the accumulator stage)
@@ -342,6 +374,7 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   p.kb_per_split = (int)cdiv(p.kb_total, splits);
   p.splits = (int)cdiv(p.kb_total, p.kb_per_split);
   p.D = D; p.ldd = ldd; p.bias = bias;
+  p.sk_per_cluster = 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -349,7 +382,15 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
     attr_set = true;
   }
   const int64_t total = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.splits;   // work items per CTA pair
-  const int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
+  int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
+  if (EPI == 2 && splits > 1) {
+    // stream-K: equal share of the (tile pair, k-block) space per CTA pair, >= 8 k-blocks each
+    const int64_t units = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.kb_total;
+    clusters = num_sms() / 2;
+    if (clusters > units / 8) clusters = units / 8 > 0 ? units / 8 : 1;
+    p.sk_per_cluster = cdiv(units, clusters);
+    clusters = cdiv(units, p.sk_per_cluster);
+  }
   const int grid = (int)(2 * clusters);
   gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, mapD, p);
   SC_LAUNCH_RET();
