@@ -58,34 +58,46 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 struct GemmParams {
   int64_t I, J, R;          // output rows, output cols, reduction length
   int tiles_i, tiles_j, splits, kb_per_split, kb_total;
-  int64_t sk_per_cluster;   // > 0: stream-K — each CTA pair owns this many consecutive (tile, k-block) units
+  int64_t sk_chunk, sk_units;   // sk_chunk > 0: stream-K in chunks of that many k-blocks over sk_units in total
   void* D; int64_t ldd;
   const float* bias;
 };
 
 // Work decomposition, identical in all three warp roles.  Tiled mode: item w -> (tile pair,
-// split) with a fixed k-block range.  Stream-K mode (wgrad): the (tile pair, k-block) iteration
-// space is cut into equal contiguous ranges, one per CTA pair, so every pair does the same
-// number of k-blocks whatever the tile count; partial tiles are summed by the red.add epilogue.
+// split) with a fixed k-block range.  Stream-K mode (wgrad): the tile-major (tile pair,
+// k-block) space is cut into equal chunks of sk_chunk k-blocks dealt round-robin to the CTA
+// pairs (chunk c, c+P, c+2P, ...), with the chunk count a multiple of the pair count: every
+// pair does the same number of k-blocks whatever the tile count, while pairs running at the
+// same time still work on neighbouring tiles and k-ranges (operand reuse in L2 — a contiguous
+// range per pair measured 2.2 ms vs 1.65 ms because it broke exactly that).  Chunks that
+// straddle a tile boundary are processed as two pieces; partial tiles meet in the red.add
+// epilogue.
 struct WorkIter {
-  int64_t w, wend, wstep;      // tiled: item index; stream-K: cursor in k-block units
+  int64_t w, wend, wstep;      // tiled: item index; stream-K: chunk index
+  int64_t cur, cend;           // stream-K: cursor inside the current chunk (k-block units)
   __device__ __forceinline__ bool next(const GemmParams& p, uint32_t rank, int& ti, int& tj, int& kb0, int& kb1) {
-    if (w >= wend) return false;
-    if (p.sk_per_cluster > 0) {
-      const int64_t tile = w / p.kb_total;
-      kb0 = (int)(w % p.kb_total);
-      const int64_t room = wend - w;
+    if (p.sk_chunk > 0) {
+      if (cur >= cend) {                       // fetch the next chunk of this pair
+        if (w >= wend) return false;
+        cur = w * p.sk_chunk;
+        cend = cur + p.sk_chunk < p.sk_units ? cur + p.sk_chunk : p.sk_units;
+        w += wstep;
+      }
+      const int64_t tile = cur / p.kb_total;
+      kb0 = (int)(cur % p.kb_total);
+      const int64_t room = cend - cur;
       kb1 = (int)((int64_t)p.kb_total - kb0 < room ? (int64_t)p.kb_total : kb0 + room);
       tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
-      w += kb1 - kb0;
-    } else {
-      const int split = (int)(w % p.splits);
-      const int64_t tile = w / p.splits;
-      tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
-      kb0 = split * p.kb_per_split;
-      kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-      w += wstep;
+      cur += kb1 - kb0;
+      return true;
     }
+    if (w >= wend) return false;
+    const int split = (int)(w % p.splits);
+    const int64_t tile = w / p.splits;
+    tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
+    kb0 = split * p.kb_per_split;
+    kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    w += wstep;
     return true;
   }
 };
@@ -132,14 +144,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int pairs_i = (p.tiles_i + 1) / 2;
   const int64_t total = (int64_t)pairs_i * p.tiles_j * p.splits;
   WorkIter it0;
-  if (p.sk_per_cluster > 0) {
-    const int64_t units = (int64_t)pairs_i * p.tiles_j * p.kb_total;
-    it0.w = (int64_t)(blockIdx.x >> 1) * p.sk_per_cluster;
-    it0.wend = it0.w + p.sk_per_cluster < units ? it0.w + p.sk_per_cluster : units;
-    it0.wstep = 0;
-  } else {
-    it0.w = blockIdx.x >> 1; it0.wend = total; it0.wstep = gridDim.x >> 1;
-  }
+  it0.w = blockIdx.x >> 1; it0.wstep = gridDim.x >> 1; it0.cur = 0; it0.cend = 0;
+  it0.wend = p.sk_chunk > 0 ? (p.sk_units + p.sk_chunk - 1) / p.sk_chunk : total;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -374,7 +380,7 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   p.kb_per_split = (int)cdiv(p.kb_total, splits);
   p.splits = (int)cdiv(p.kb_total, p.kb_per_split);
   p.D = D; p.ldd = ldd; p.bias = bias;
-  p.sk_per_cluster = 0;
+  p.sk_chunk = 0; p.sk_units = 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -384,12 +390,14 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   const int64_t total = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.splits;   // work items per CTA pair
   int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
   if (EPI == 2 && splits > 1) {
-    // stream-K: equal share of the (tile pair, k-block) space per CTA pair, >= 8 k-blocks each
-    const int64_t units = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.kb_total;
+    // stream-K: ~4-5 equal chunks per CTA pair (>= 8 k-blocks each), chunk count = rounds x pairs
+    p.sk_units = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.kb_total;
     clusters = num_sms() / 2;
-    if (clusters > units / 8) clusters = units / 8 > 0 ? units / 8 : 1;
-    p.sk_per_cluster = cdiv(units, clusters);
-    clusters = cdiv(units, p.sk_per_cluster);
+    if (clusters > p.sk_units / 8) clusters = p.sk_units / 8 > 0 ? p.sk_units / 8 : 1;
+    int64_t rounds = cdiv((int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * splits, clusters);
+    if (rounds < 1) rounds = 1;
+    p.sk_chunk = cdiv(p.sk_units, rounds * clusters);
+    if (p.sk_chunk < 8) p.sk_chunk = 8;
   }
   const int grid = (int)(2 * clusters);
   gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, mapD, p);
