@@ -58,48 +58,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 struct GemmParams {
   int64_t I, J, R;          // output rows, output cols, reduction length
   int tiles_i, tiles_j, splits, kb_per_split, kb_total;
-  int64_t sk_chunk, sk_units;   // sk_chunk > 0: stream-K in chunks of that many k-blocks over sk_units in total
   void* D; int64_t ldd;
   const float* bias;
-};
-
-// Work decomposition, identical in all three warp roles.  Tiled mode: item w -> (tile pair,
-// split) with a fixed k-block range.  Stream-K mode (wgrad): the tile-major (tile pair,
-// k-block) space is cut into equal chunks of sk_chunk k-blocks dealt round-robin to the CTA
-// pairs (chunk c, c+P, c+2P, ...), with the chunk count a multiple of the pair count: every
-// pair does the same number of k-blocks whatever the tile count, while pairs running at the
-// same time still work on neighbouring tiles and k-ranges (operand reuse in L2 — a contiguous
-// range per pair measured 2.2 ms vs 1.65 ms because it broke exactly that).  Chunks that
-// straddle a tile boundary are processed as two pieces; partial tiles meet in the red.add
-// epilogue.
-struct WorkIter {
-  int64_t w, wend, wstep;      // tiled: item index; stream-K: chunk index
-  int64_t cur, cend;           // stream-K: cursor inside the current chunk (k-block units)
-  __device__ __forceinline__ bool next(const GemmParams& p, uint32_t rank, int& ti, int& tj, int& kb0, int& kb1) {
-    if (p.sk_chunk > 0) {
-      if (cur >= cend) {                       // fetch the next chunk of this pair
-        if (w >= wend) return false;
-        cur = w * p.sk_chunk;
-        cend = cur + p.sk_chunk < p.sk_units ? cur + p.sk_chunk : p.sk_units;
-        w += wstep;
-      }
-      const int64_t tile = cur / p.kb_total;
-      kb0 = (int)(cur % p.kb_total);
-      const int64_t room = cend - cur;
-      kb1 = (int)((int64_t)p.kb_total - kb0 < room ? (int64_t)p.kb_total : kb0 + room);
-      tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
-      cur += kb1 - kb0;
-      return true;
-    }
-    if (w >= wend) return false;
-    const int split = (int)(w % p.splits);
-    const int64_t tile = w / p.splits;
-    tj = (int)(tile % p.tiles_j); ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
-    kb0 = split * p.kb_per_split;
-    kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-    w += wstep;
-    return true;
-  }
 };
 
 // EPI: 0 = bf16 store (+bias), 1 = fp32 store (+bias), 2 = fp32 atomic accumulate (split-R)
@@ -143,17 +103,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pairs_i = (p.tiles_i + 1) / 2;
   const int64_t total = (int64_t)pairs_i * p.tiles_j * p.splits;
-  WorkIter it0;
-  it0.w = blockIdx.x >> 1; it0.wstep = gridDim.x >> 1; it0.cur = 0; it0.cend = 0;
-  it0.wend = p.sk_chunk > 0 ? (p.sk_units + p.sk_chunk - 1) / p.sk_chunk : total;
+  const int64_t w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      WorkIter it = it0;
-      int ti, tj, kb0, kb1;
-      while (it.next(p, rank, ti, tj, kb0, kb1)) {
+      for (int64_t w = w0; w < total; w += wstep) {
+        const int split = (int)(w % p.splits);
+        const int64_t tile = w / p.splits;
+        const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
@@ -187,9 +148,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                              ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      WorkIter it = it0;
-      int ti, tj, kb0, kb1;
-      while (it.next(p, rank, ti, tj, kb0, kb1)) {
+      for (int64_t w = w0; w < total; w += wstep) {
+        const int split = (int)(w % p.splits);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         mbar_wait(tempty(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TN;
@@ -219,9 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
     float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
-    WorkIter it = it0;
-    int ti, tj, kb0, kb1;
-    while (it.next(p, rank, ti, tj, kb0, kb1)) {
+    for (int64_t w = w0; w < total; w += wstep) {
+      const int64_t tile = w / p.splits;
+      const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
       const int64_t col0 = (int64_t)tj * TN;
       if (EPI != 2 && p.bias != nullptr) {
         // stage this tile's bias once (double-buffered with the accumulator stage)
@@ -380,7 +342,6 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   p.kb_per_split = (int)cdiv(p.kb_total, splits);
   p.splits = (int)cdiv(p.kb_total, p.kb_per_split);
   p.D = D; p.ldd = ldd; p.bias = bias;
-  p.sk_chunk = 0; p.sk_units = 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -388,17 +349,7 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
     attr_set = true;
   }
   const int64_t total = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.splits;   // work items per CTA pair
-  int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
-  if (EPI == 2 && splits > 1) {
-    // stream-K: ~4-5 equal chunks per CTA pair (>= 8 k-blocks each), chunk count = rounds x pairs
-    p.sk_units = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.kb_total;
-    clusters = num_sms() / 2;
-    if (clusters > p.sk_units / 8) clusters = p.sk_units / 8 > 0 ? p.sk_units / 8 : 1;
-    int64_t rounds = cdiv((int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * splits, clusters);
-    if (rounds < 1) rounds = 1;
-    p.sk_chunk = cdiv(p.sk_units, rounds * clusters);
-    if (p.sk_chunk < 8) p.sk_chunk = 8;
-  }
+  const int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
   const int grid = (int)(2 * clusters);
   gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, mapD, p);
   SC_LAUNCH_RET();
@@ -442,9 +393,12 @@ bool tc_gemm_wgrad_ok(int64_t lddy, int64_t lda, int64_t lddw, int64_t M, int64_
 int tc_gemm_wgrad(const void* dY, int64_t lddy, const void* A, int64_t lda, float* dW, int64_t lddw,
                   int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
   // dW[n,k] = sum_m dY[m,n] A[m,k] : both operands MN-major, reduction over m, split across CTAs
-  // Split the M-long reduction into ~4 work items per SM.  More splits would balance the last
-  // wave better but the fp32 red.add epilogue is not free: 12 splits measured 2.05 ms vs 1.65 ms
-  // with 4 at 192000x5120x1024 (scattered 4-byte L2 atomics).
+  // Split the M-long reduction into ~4 work items per SM, tile-major with the split index
+  // fastest, so the CTA pairs running at the same time cover all tj tiles of a few tile rows over
+  // the SAME reduction ranges: each dY / X tile is fetched from HBM once and served from L2 to
+  // its other users.  Measured alternatives at 192000x5120x1024 (this: 1.65 ms): 12 splits
+  // 2.05 ms (scattered 4-byte L2 atomics), stream-K with one contiguous range per pair 2.2 ms and
+  // with round-robin chunks 2.0 ms (perfect balance, but unaligned k-ranges lose the L2 sharing).
   const int64_t tiles = cdiv(N, TM) * cdiv(K, TN);
   const int64_t kb = cdiv(M, TK);
   int64_t splits = cdiv(4 * num_sms(), tiles);
