@@ -20,6 +20,7 @@
 // The epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
+#include <stdlib.h>
 
 namespace sc {
 
@@ -237,6 +238,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tma_store_2d(&mapD, stg, (int)col, ti * TM + q * 32);
             bulk_commit();
           }
+        } else if (EPI == 2) {
+          // split-R partial tile: fp32 TMA reduce-add of [32 rows x 16 cols] boxes (64-byte row
+          // segments reduced in L2) instead of 32 scattered 4-byte atomics per lane per chunk
+          const uint32_t stg = base + STAGES * STAGE_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + v * 16), "r"(r[hh * 16 + v * 4 + 0]),
+                           "r"(r[hh * 16 + v * 4 + 1]), "r"(r[hh * 16 + v * 4 + 2]), "r"(r[hh * 16 + v * 4 + 3]) : "memory");
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && col + hh * 16 < p.J && (int64_t)ti * TM + q * 32 < p.I) {
+              tma_reduce_add_2d(&mapD, stg, (int)col + hh * 16, ti * TM + q * 32);
+              bulk_commit();
+            }
+          }
         } else if (row < p.I && col < p.J) {
           if (EPI != 2 && p.bias != nullptr) {
             const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
@@ -261,11 +281,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
               }
             }
-          } else {
-            float* out = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
-#pragma unroll
-            for (int v = 0; v < 32; ++v)
-              if (col + v < p.J) atomicAdd(out + v, __uint_as_float(r[v]));
           }
         }
       }
@@ -274,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (lane == 0) mbar_arrive(tempty(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (EPI == 0 && lane == 0) bulk_wait0();          // all TMA stores of this warp have completed
+    if (EPI != 1 && lane == 0) bulk_wait0();          // all TMA stores / reductions of this warp have completed
   }
   tc_fence_before();
   __syncthreads();
@@ -314,6 +329,19 @@ static bool make_store_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 output [rows, cols] (row stride ld): [32 x 16] reduce-add boxes, no swizzle
+static bool make_reduce_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool tc_common_ok(const void* a, const void* b, const void* d, int64_t lda, int64_t ldb, int64_t ldd,
                          int64_t I, int64_t J, int64_t R, int d_align_elems) {
   if (I < 1 || J < 8 || R < 8) return false;
@@ -332,6 +360,7 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   ok = ok && (B_MN ? make_map(&mapB, B, R, J, ldb, TK) : make_map(&mapB, B, J, R, ldb, TN / 2));
   CUtensorMap mapD = mapA;                               // only dereferenced by the bf16 epilogue
   if (EPI == 0) ok = ok && make_store_map(&mapD, D, I, J, ldd);
+  if (EPI == 2) ok = ok && make_reduce_map(&mapD, D, I, J, ldd);
   if (!ok) return SC_E_UNSUP;
   GemmParams p;
   p.I = I; p.J = J; p.R = R;
@@ -388,7 +417,7 @@ bool tc_gemm_wgrad_ok(int64_t lddy, int64_t lda, int64_t lddw, int64_t M, int64_
                       const void* dY, const void* A, const void* dW) {
   if (in_dtype != SC_BF16) return false;
   // N (rows of dW) comes from dY's columns via TMA: needs N % 8 for the map's 16-B row stride
-  return (N % 8 == 0) && tc_common_ok(dY, A, dW, lddy, lda, lddw, N, K, M, 1) && M >= 64;
+  return (N % 8 == 0) && tc_common_ok(dY, A, dW, lddy, lda, lddw, N, K, M, 4) && M >= 64;
 }
 int tc_gemm_wgrad(const void* dY, int64_t lddy, const void* A, int64_t lda, float* dW, int64_t lddw,
                   int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
@@ -404,6 +433,7 @@ int tc_gemm_wgrad(const void* dY, int64_t lddy, const void* A, int64_t lda, floa
   int64_t splits = cdiv(4 * num_sms(), tiles);
   if (splits > kb / 8) splits = kb / 8;                   // keep >= 8 k-blocks per item
   if (splits < 1) splits = 1;
+  { const char* e = getenv("SC_WGRAD_SPLITS"); if (e) { splits = atoi(e); if (splits > kb / 8) splits = kb / 8; if (splits < 1) splits = 1; } }
   if (!accumulate)
     zero2d_kernel<<<(unsigned)min((int64_t)2048, cdiv(N * K, 256)), 256, 0, st>>>(dW, lddw, N, K);
   return launch_tc<true, true, 2>(dY, lddy, A, lda, dW, lddw, nullptr, N, K, M, (int)splits, st);
