@@ -111,8 +111,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t w = w0; w < total; w += wstep) {
-        const int split = (int)(w % p.splits);
-        const int64_t tile = w / p.splits;
+        const int64_t ntile = (int64_t)pairs_i * p.tiles_j;
+        const int split = (int)(w / ntile);          // split-major: pairs running together share the reduction range
+        const int64_t tile = w % ntile;
         const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -150,7 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int64_t w = w0; w < total; w += wstep) {
-        const int split = (int)(w % p.splits);
+        const int split = (int)(w / ((int64_t)pairs_i * p.tiles_j));
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         mbar_wait(tempty(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
@@ -183,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t w = w0; w < total; w += wstep) {
-      const int64_t tile = w / p.splits;
+      const int64_t tile = w % ((int64_t)pairs_i * p.tiles_j);
       const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
       const int64_t col0 = (int64_t)tj * TN;
       if (EPI != 2 && p.bias != nullptr) {
@@ -422,17 +423,25 @@ bool tc_gemm_wgrad_ok(int64_t lddy, int64_t lda, int64_t lddw, int64_t M, int64_
 int tc_gemm_wgrad(const void* dY, int64_t lddy, const void* A, int64_t lda, float* dW, int64_t lddw,
                   int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
   // dW[n,k] = sum_m dY[m,n] A[m,k] : both operands MN-major, reduction over m, split across CTAs
-  // Split the M-long reduction into ~4 work items per SM, tile-major with the split index
-  // fastest, so the CTA pairs running at the same time cover all tj tiles of a few tile rows over
-  // the SAME reduction ranges: each dY / X tile is fetched from HBM once and served from L2 to
-  // its other users.  Measured alternatives at 192000x5120x1024 (this: 1.65 ms): 12 splits
-  // 2.05 ms (scattered 4-byte L2 atomics), stream-K with one contiguous range per pair 2.2 ms and
-  // with round-robin chunks 2.0 ms (perfect balance, but unaligned k-ranges lose the L2 sharing).
-  const int64_t tiles = cdiv(N, TM) * cdiv(K, TN);
+  // Split the M-long reduction so the (tile pair x split) items fill the 74 CTA pairs evenly.
+  // Items are ordered split-major: the pairs running at the same time work on (almost) all
+  // tiles over the SAME reduction range, so every dY / X tile is fetched from HBM once and
+  // served to its other users from L2; with that ordering more splits only cost the (TMA
+  // reduce-add) epilogue, so the count is chosen to minimise last-wave waste.
+  const int64_t pairs = cdiv(cdiv(N, TM), 2) * cdiv(K, TN);
   const int64_t kb = cdiv(M, TK);
-  int64_t splits = cdiv(4 * num_sms(), tiles);
-  if (splits > kb / 8) splits = kb / 8;                   // keep >= 8 k-blocks per item
-  if (splits < 1) splits = 1;
+  const int64_t clusters = num_sms() / 2;
+  int64_t max_s = kb / 32;
+  if (max_s < 1) max_s = 1;
+  if (max_s > 32) max_s = 32;
+  int64_t splits = 1;
+  double best = 1e30;
+  for (int64_t sidx = 1; sidx <= max_s; ++sidx) {
+    const int64_t kps = cdiv(kb, sidx);
+    const int64_t items = pairs * cdiv(kb, kps);
+    const double cost = (double)cdiv(items, clusters) * ((double)kps + 8.0);   // rounds x (mainloop + ~8 k-blocks of epilogue)
+    if (cost < best - 1e-9) { best = cost; splits = sidx; }
+  }
   { const char* e = getenv("SC_WGRAD_SPLITS"); if (e) { splits = atoi(e); if (splits > kb / 8) splits = kb / 8; if (splits < 1) splits = 1; } }
   if (!accumulate)
     zero2d_kernel<<<(unsigned)min((int64_t)2048, cdiv(N * K, 256)), 256, 0, st>>>(dW, lddw, N, K);
