@@ -114,28 +114,35 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
       for (int i = 0; i < VEC; ++i) ck[i] = S[i];
     }
     const int t0 = c * TC;
+    T* hp = ho + (int64_t)t0 * ldh;                      // running output pointer (one 64-bit add per step)
+    auto step = [&](int u) {
+      float z[VEC], k[VEC], v[VEC], p[VEC], q[VEC], out[VEC];
+      lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
+      lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
+      lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
+      lds2(st + (SC_GATE_P * TC + u) * CB, tid, p);
+      lds2(st + (SC_GATE_Q * TC + u) * CB, tid, q);
 #pragma unroll
-    for (int u = 0; u < TC; ++u) {
-      if (t0 + u < Tn) {
-        float z[VEC], k[VEC], v[VEC], p[VEC], q[VEC], out[VEC];
-        lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
-        lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
-        lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
-        lds2(st + (SC_GATE_P * TC + u) * CB, tid, p);
-        lds2(st + (SC_GATE_Q * TC + u) * CB, tid, q);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float d = sigmoidf_<PRECISE>(q[i]);
-          const float kv = k[i] * v[i];
-          S[i] = fmaf(d, S[i], kv);
-          const float sp = TRAIN ? fmaf(d, S[i], kv) : S[i];
-          const float cc = tanhf_<PRECISE>(p[i] + sp);
-          const float zh = sigmoidf_<PRECISE>(z[i]);
-          h[i] = fmaf(zh, h[i] - cc, cc);
-          out[i] = h[i];
-        }
-        if (live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
+      for (int i = 0; i < VEC; ++i) {
+        const float d = sigmoidf_<PRECISE>(q[i]);
+        const float kv = k[i] * v[i];
+        S[i] = fmaf(d, S[i], kv);
+        const float sp = TRAIN ? fmaf(d, S[i], kv) : S[i];
+        const float cc = tanhf_<PRECISE>(p[i] + sp);
+        const float zh = sigmoidf_<PRECISE>(z[i]);
+        h[i] = fmaf(zh, h[i] - cc, cc);
+        out[i] = h[i];
       }
+      if (live) stg_vec<T>(hp, out);
+      hp += ldh;
+    };
+    if (t0 + TC <= Tn) {                                 // full interval: no per-step bounds test
+#pragma unroll
+      for (int u = 0; u < TC; ++u) step(u);
+    } else {
+#pragma unroll
+      for (int u = 0; u < TC; ++u)
+        if (t0 + u < Tn) step(u);
     }
   }
   if (live) {
@@ -237,63 +244,73 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
         }
       }
     }
-    // pass 2: reverse time
+    // pass 2: reverse time.  Five running output pointers (one per gate block) step back by one
+    // row per timestep instead of rebuilding 64-bit addresses for every store.
+    T* rz = dg + (int64_t)(t0 + TC - 1) * lddg;
+    T* rk = rz + (int64_t)SC_GATE_K * H;
+    T* rv = rz + (int64_t)SC_GATE_V * H;
+    T* rp = rz + (int64_t)SC_GATE_P * H;
+    T* rq = rz + (int64_t)SC_GATE_Q * H;
+    auto step = [&](int u) {
+      float z[VEC], k[VEC], v[VEC], p[VEC], go[VEC], hp[VEC];
+      lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
+      lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
+      lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
+      lds2(st + (SC_GATE_P * TC + u) * CB, tid, p);
+      lds2(st + (5 * TC + u) * CB, tid, go);
+      lds2(st + (6 * TC + u) * CB, tid, hp);
+      if (t0 + u == 0) {
 #pragma unroll
-    for (int u = TC - 1; u >= 0; --u) {
-      const int t = t0 + u;
-      if (t < Tn) {
-        float z[VEC], k[VEC], v[VEC], p[VEC], go[VEC], hp[VEC];
-        lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
-        lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
-        lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
-        lds2(st + (SC_GATE_P * TC + u) * CB, tid, p);
-        lds2(st + (5 * TC + u) * CB, tid, go);
-        lds2(st + (6 * TC + u) * CB, tid, hp);
-        if (t == 0) {
+        for (int i = 0; i < VEC; ++i) hp[i] = hfirst[i];
+      }
+      float dz[VEC], dk[VEC], dv[VEC], dp[VEC], dq[VEC];
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) hp[i] = hfirst[i];
+      for (int i = 0; i < VEC; ++i) {
+        const float d = dl[u][i];
+        const float kv = k[i] * v[i];
+        const float St = Sl[u][i];
+        const float Sp = (u > 0) ? Sl[u - 1][i] : Sin[i];
+        const float sp = TRAIN ? fmaf(d, St, kv) : St;
+        const float cc = tanhf_<PRECISE>(p[i] + sp);
+        const float zh = sigmoidf_<PRECISE>(z[i]);
+        const float gam = go[i] + gz[i];
+        const float omz = 1.f - zh;
+        const float da = gam * omz * fmaf(-cc, cc, 1.f);
+        dz[i] = gam * (hp[i] - cc) * zh * omz;
+        gz[i] = zh * gam;
+        dp[i] = da;
+        float sig, dkv, dd;
+        if (TRAIN) {
+          sig = fmaf(d, da, ds[i]);
+          dkv = da + sig;
+          dd = fmaf(St, da, Sp * sig);
+        } else {
+          sig = da + ds[i];
+          dkv = sig;
+          dd = Sp * sig;
         }
-        float dz[VEC], dk[VEC], dv[VEC], dp[VEC], dq[VEC];
+        ds[i] = d * sig;
+        dk[i] = dkv * v[i];
+        dv[i] = dkv * k[i];
+        dq[i] = dd * d * (1.f - d);
+        acc[SC_GATE_Z][i] += dz[i]; acc[SC_GATE_K][i] += dk[i]; acc[SC_GATE_V][i] += dv[i];
+        acc[SC_GATE_P][i] += dp[i]; acc[SC_GATE_Q][i] += dq[i];
+      }
+      if (live) {
+        stg_vec<T>(rz, dz); stg_vec<T>(rk, dk); stg_vec<T>(rv, dv); stg_vec<T>(rp, dp); stg_vec<T>(rq, dq);
+      }
+    };
+    if (t0 + TC <= Tn) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float d = dl[u][i];
-          const float kv = k[i] * v[i];
-          const float St = Sl[u][i];
-          const float Sp = (u > 0) ? Sl[u - 1][i] : Sin[i];
-          const float sp = TRAIN ? fmaf(d, St, kv) : St;
-          const float cc = tanhf_<PRECISE>(p[i] + sp);
-          const float zh = sigmoidf_<PRECISE>(z[i]);
-          const float gam = go[i] + gz[i];
-          const float omz = 1.f - zh;
-          const float da = gam * omz * fmaf(-cc, cc, 1.f);
-          dz[i] = gam * (hp[i] - cc) * zh * omz;
-          gz[i] = zh * gam;
-          dp[i] = da;
-          float sig, dkv, dd;
-          if (TRAIN) {
-            sig = fmaf(d, da, ds[i]);
-            dkv = da + sig;
-            dd = fmaf(St, da, Sp * sig);
-          } else {
-            sig = da + ds[i];
-            dkv = sig;
-            dd = Sp * sig;
-          }
-          ds[i] = d * sig;
-          dk[i] = dkv * v[i];
-          dv[i] = dkv * k[i];
-          dq[i] = dd * d * (1.f - d);
-          acc[SC_GATE_Z][i] += dz[i]; acc[SC_GATE_K][i] += dk[i]; acc[SC_GATE_V][i] += dv[i];
-          acc[SC_GATE_P][i] += dp[i]; acc[SC_GATE_Q][i] += dq[i];
-        }
-        if (live) {
-          T* row = dg + (int64_t)t * lddg;
-          stg_vec<T>(row + (int64_t)SC_GATE_Z * H, dz);
-          stg_vec<T>(row + (int64_t)SC_GATE_K * H, dk);
-          stg_vec<T>(row + (int64_t)SC_GATE_V * H, dv);
-          stg_vec<T>(row + (int64_t)SC_GATE_P * H, dp);
-          stg_vec<T>(row + (int64_t)SC_GATE_Q * H, dq);
-        }
+      for (int u = TC - 1; u >= 0; --u) {
+        step(u);
+        rz -= lddg; rk -= lddg; rv -= lddg; rp -= lddg; rq -= lddg;
+      }
+    } else {
+#pragma unroll
+      for (int u = TC - 1; u >= 0; --u) {
+        if (t0 + u < Tn) step(u);
+        rz -= lddg; rk -= lddg; rv -= lddg; rp -= lddg; rq -= lddg;
       }
     }
   }
