@@ -333,7 +333,9 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
       Vec<TI, VWI> raw; raw.raw = __ldg(reinterpret_cast<const uint4*>(x + i));
       unpack(raw, f);
 #pragma unroll
-      for (int j = 0; j < VWI; ++j) r[i + j] = ex2f(fmaf(f[j], LOG2E, -l2));
+      for (int j = 0; j < VWI; ++j) f[j] = ex2f(fmaf(f[j], LOG2E, -l2));
+#pragma unroll
+      for (int j = 0; j < VWI; j += 4) *reinterpret_cast<float4*>(r + i + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     }
   } else {
     for (int i = lane; i < V; i += 32) r[i] = ex2f(fmaf(ld_f(x + i), LOG2E, -l2));
@@ -372,7 +374,10 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
     for (int i = lane * VWO; i < V; i += 32 * VWO) {
       float f[VWO];
 #pragma unroll
-      for (int j = 0; j < VWO; ++j) f[j] = scale * r[i + j];
+      for (int j = 0; j < VWO; j += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(r + i + j);
+        f[j] = scale * q4.x; f[j + 1] = scale * q4.y; f[j + 2] = scale * q4.z; f[j + 3] = scale * q4.w;
+      }
       const Vec<TO, VWO> o = pack(f, (TO*)nullptr);
       *reinterpret_cast<uint4*>(dx + i) = o.raw;
     }
