@@ -180,16 +180,21 @@ int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype
  * int64 (row stride ldl), frame_lens/label_lens [B] int64.
  * Workspaces fp32, 16-byte aligned, SKEWED layout [B, T+U1, U1p] with U1p = U1 rounded up to a
  * multiple of 4 and row d = t+u: eb (blank log-probs), el (label log-probs), alpha, beta.
+ * row_offsets: NULL for the padded layout; else [B] int64 first-row index of each utterance in
+ * the COMPACT packing of model.py:147-200 (log_probs is then [total_rows, V], utterance b
+ * holding T_b x (U_b+1) rows in (t,u) order; T and U1 are still the batch maxima).
  * fwd: fills the workspaces and nll[B] (0 for utterances with no frames).
- * bwd: grad [B,T,U1,V] := d(sum_b grad_w[b]*nll_b)/dlog_probs — fully written (zeros except
- * the blank and label entry of each live node). */
+ * bwd: grad (same layout as log_probs) := d(sum_b grad_w[b]*nll_b)/dlog_probs — fully written
+ * (zeros except the blank and label entry of each live node). */
 int sc_rnnt_fwd(const float* log_probs, const int64_t* labels, int64_t ldl,
                 const int64_t* frame_lens, const int64_t* label_lens,
                 int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank,
+                const int64_t* row_offsets,
                 float* eb, float* el, float* alpha, float* beta, float* nll, void* stream);
 int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* frame_lens,
                 const int64_t* label_lens, int64_t B, int64_t T, int64_t U1, int64_t V,
-                int64_t blank, const float* eb, const float* el, const float* alpha,
+                int64_t blank, const int64_t* row_offsets, int64_t total_rows,
+                const float* eb, const float* el, const float* alpha,
                 const float* beta, const float* nll, const float* grad_w, float* grad,
                 void* stream);
 

@@ -44,8 +44,8 @@ SIGNATURES = {
     "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, I32, P],
     "sc_ctc_bwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, I32,
                    P, I64, I64, I32, P],
-    "sc_rnnt_fwd": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P],
-    "sc_rnnt_bwd": [P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, P],
+    "sc_rnnt_fwd": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P],
+    "sc_rnnt_bwd": [P, I64, P, P, I64, I64, I64, I64, I64, P, I64, P, P, P, P, P, P, P, P],
 }
 _RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64}
 

@@ -30,6 +30,7 @@ __device__ __forceinline__ float lse2n(float a, float b) {
 __global__ void rnnt_gather_kernel(const float* __restrict__ lp, const int64_t* __restrict__ labels, int64_t ldl,
                                    const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
                                    int B, int Tn, int U1, int V, int U1p, int64_t blank,
+                                   const int64_t* __restrict__ row_offsets,
                                    float* __restrict__ eb, float* __restrict__ el) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * Tn * U1) return;
@@ -39,7 +40,10 @@ __global__ void rnnt_gather_kernel(const float* __restrict__ lp, const int64_t* 
   int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
   const int64_t Ub = label_lens[b];
   if (t >= Tb || u > Ub) return;
-  const float* row = lp + i * V;
+  // padded (B,T,U1,V) layout, or the compact packing of model.py:147-200: utterance b starts at
+  // row_offsets[b] and holds T_b x (U_b+1) rows
+  const int64_t r = row_offsets ? row_offsets[b] + (int64_t)t * (Ub + 1) + u : i;
+  const float* row = lp + r * V;
   const int64_t D = Tn + U1;
   const int64_t o = ((int64_t)b * D + (t + u)) * U1p + u;
   eb[o] = __ldg(row + blank);
@@ -177,7 +181,8 @@ __global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __re
                                  const float* __restrict__ nll, const float* __restrict__ grad_w,
                                  const int64_t* __restrict__ labels, int64_t ldl,
                                  const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
-                                 int B, int Tn, int U1, int V, int U1p, int64_t blank, float* __restrict__ grad) {
+                                 int B, int Tn, int U1, int V, int U1p, int64_t blank,
+                                 const int64_t* __restrict__ row_offsets, float* __restrict__ grad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * Tn * U1) return;
   const int u = (int)(i % U1);
@@ -193,7 +198,8 @@ __global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __re
   if (a == NEG_INF) return;
   const float ll = -nll[b];
   const float w = grad_w[b];
-  float* g = grad + i * V;
+  const int64_t r = row_offsets ? row_offsets[b] + (int64_t)t * (Ub + 1) + u : i;
+  float* g = grad + r * V;
   // blank: (t,u) -> (t+1,u); at the final node it terminates the path
   float nb = NEG_INF;
   if (t + 1 < Tb) nb = beta[base + (int64_t)(t + 1 + u) * U1p + u];
@@ -221,6 +227,7 @@ static bool rnnt_args_ok(int64_t B, int64_t T, int64_t U1, int64_t V, int64_t bl
 extern "C" int sc_rnnt_fwd(const float* log_probs, const int64_t* labels, int64_t ldl,
                            const int64_t* frame_lens, const int64_t* label_lens,
                            int64_t B, int64_t T, int64_t U1, int64_t V, int64_t blank,
+                           const int64_t* row_offsets,
                            float* eb, float* el, float* alpha, float* beta, float* nll, void* stream) {
   SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank), SC_E_SHAPE);
   SC_CHECK_ARG(frame_lens && label_lens && nll && (U1 == 1 || labels), SC_E_BADARG);
@@ -230,7 +237,7 @@ extern "C" int sc_rnnt_fwd(const float* log_probs, const int64_t* labels, int64_
   if (T > 0) {
     const int64_t n = B * T * U1;
     rnnt_gather_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(log_probs, labels, ldl, frame_lens, label_lens,
-        (int)B, (int)T, (int)U1, (int)V, U1p, blank, eb, el);
+        (int)B, (int)T, (int)U1, (int)V, U1p, blank, row_offsets, eb, el);
   }
   int threads = ((U1p + 31) / 32) * 32;
   const size_t smem = (2 * (size_t)(U1p + 4) + 4 * (size_t)RNNT_EB * U1p) * sizeof(float);
@@ -245,7 +252,8 @@ extern "C" int sc_rnnt_fwd(const float* log_probs, const int64_t* labels, int64_
 
 extern "C" int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* frame_lens,
                            const int64_t* label_lens, int64_t B, int64_t T, int64_t U1, int64_t V,
-                           int64_t blank, const float* eb, const float* el, const float* alpha,
+                           int64_t blank, const int64_t* row_offsets, int64_t total_rows,
+                           const float* eb, const float* el, const float* alpha,
                            const float* beta, const float* nll, const float* grad_w, float* grad,
                            void* stream) {
   SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank), SC_E_SHAPE);
@@ -253,10 +261,12 @@ extern "C" int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* fr
   SC_CHECK_ARG(frame_lens && label_lens && eb && el && alpha && beta && nll && grad_w && grad, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
   const int U1p = (int)((U1 + 3) & ~(int64_t)3);
-  cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)(B * T * U1 * V), st);
+  const int64_t rows = row_offsets ? total_rows : B * T * U1;
+  SC_CHECK_ARG(rows >= 0, SC_E_BADARG);
+  cudaError_t e = cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)(rows * V), st);
   if (e != cudaSuccess) return (int)e;
   const int64_t n = B * T * U1;
   rnnt_grad_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(eb, el, alpha, beta, nll, grad_w, labels, ldl, frame_lens,
-      label_lens, (int)B, (int)T, (int)U1, (int)V, U1p, blank, grad);
+      label_lens, (int)B, (int)T, (int)U1, (int)V, U1p, blank, row_offsets, grad);
   SC_LAUNCH_RET();
 }

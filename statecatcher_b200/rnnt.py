@@ -23,9 +23,12 @@ from .lucyrnn import _LinearFn, _compute_dtype
 
 
 class _RNNTFn(torch.autograd.Function):
+    """log_probs is (B,T,U1,V) padded, or (rows,V) compact with row offsets (model.py:147-200)."""
+
     @staticmethod
-    def forward(ctx, log_probs, labels, frame_lens, label_lens, blank):
-        B, T, U1, V = log_probs.shape
+    def forward(ctx, log_probs, labels, frame_lens, label_lens, blank, offsets, T, U1):
+        V = log_probs.shape[-1]
+        B = labels.shape[0]
         dev = log_probs.device
         U1p = (U1 + 3) & ~3
         ws = lambda: torch.empty(B, T + U1, U1p, dtype=torch.float32, device=dev)   # noqa: E731
@@ -33,36 +36,24 @@ class _RNNTFn(torch.autograd.Function):
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         ldl = labels.stride(0) if labels.numel() else max(U1 - 1, 1)
         call("sc_rnnt_fwd", ptr(log_probs), ptr(labels), ldl, ptr(frame_lens), ptr(label_lens),
-             B, T, U1, V, blank, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), stream())
-        ctx.save_for_backward(labels, frame_lens, label_lens, eb, el, alpha, beta, nll)
-        ctx.cfg = (B, T, U1, V, blank, ldl)
+             B, T, U1, V, blank, ptr(offsets), ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), stream())
+        ctx.save_for_backward(labels, frame_lens, label_lens, eb, el, alpha, beta, nll, offsets)
+        ctx.cfg = (B, T, U1, V, blank, ldl, tuple(log_probs.shape))
         return nll
 
     @staticmethod
     def backward(ctx, gnll):
-        labels, frame_lens, label_lens, eb, el, alpha, beta, nll = ctx.saved_tensors
-        B, T, U1, V, blank, ldl = ctx.cfg
-        grad = torch.empty(B, T, U1, V, dtype=torch.float32, device=nll.device)
+        labels, frame_lens, label_lens, eb, el, alpha, beta, nll, offsets = ctx.saved_tensors
+        B, T, U1, V, blank, ldl, shape = ctx.cfg
+        grad = torch.empty(shape, dtype=torch.float32, device=nll.device)
         w = gnll.to(torch.float32).contiguous()
+        rows = shape[0] if offsets is not None else 0
         call("sc_rnnt_bwd", ptr(labels), ldl, ptr(frame_lens), ptr(label_lens), B, T, U1, V, blank,
-             ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), ptr(w), ptr(grad), stream())
-        return grad, None, None, None, None
+             ptr(offsets), rows, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), ptr(w), ptr(grad), stream())
+        return grad, None, None, None, None, None, None, None
 
 
-def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
-              reduction: str = "mean") -> torch.Tensor:
-    """log_probs [B,T,U+1,V] normalised (log_softmax of the joint), labels [B,U]."""
-    _lib.require_cuda(log_probs, "rnnt_loss input")
-    if log_probs.dim() != 4:
-        raise ValueError("rnnt_loss expects (B,T,U+1,V) log-probs (compact packing is not implemented)")
-    x = log_probs.float().contiguous()
-    B, T, U1, V = x.shape
-    fl, _ = _lens(frames_lengths, x.device, B, "frames_lengths")
-    ll, _ = _lens(labels_lengths, x.device, B, "labels_lengths")
-    lab = labels.to(device=x.device, dtype=torch.int64).contiguous()
-    if lab.dim() != 2 or lab.size(0) != B or lab.size(1) < U1 - 1:
-        raise ValueError("labels must be (B,U) with U >= log_probs.size(2)-1")
-    nll = _RNNTFn.apply(x, lab, fl, ll, int(blank))
+def _reduce(nll, reduction):
     if reduction == "mean":
         return nll.mean()
     if reduction == "sum":
@@ -72,12 +63,38 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
     raise ValueError(f"unknown reduction {reduction!r}")
 
 
+def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
+              reduction: str = "mean", compact: bool = False) -> torch.Tensor:
+    """log_probs: (B,T,U+1,V) normalised (log_softmax of the joint), or with compact=True the
+    packed (sum_b T_b*(U_b+1), V) layout the compact joiner produces; labels (B,U)."""
+    _lib.require_cuda(log_probs, "rnnt_loss input")
+    x = log_probs.float().contiguous()
+    lab = labels.to(device=x.device, dtype=torch.int64).contiguous()
+    B = lab.size(0)
+    fl, _ = _lens(frames_lengths, x.device, B, "frames_lengths")
+    ll, _ = _lens(labels_lengths, x.device, B, "labels_lengths")
+    if compact:
+        if x.dim() != 2:
+            raise ValueError("compact rnnt_loss expects (rows, V) log-probs")
+        rows = fl * (ll + 1)
+        offsets = (torch.cumsum(rows, 0) - rows).contiguous()
+        T, U1 = int(fl.max().item()), int(ll.max().item()) + 1       # host sync: sizes of the workspaces
+        if int(rows.sum().item()) != x.size(0):
+            raise ValueError("compact log_probs row count does not match sum(T_b*(U_b+1))")
+        return _reduce(_RNNTFn.apply(x, lab, fl, ll, int(blank), offsets, T, U1), reduction)
+    if x.dim() != 4:
+        raise ValueError("rnnt_loss expects (B,T,U+1,V) log-probs")
+    _, T, U1, V = x.shape
+    if lab.dim() != 2 or x.size(0) != B or lab.size(1) < U1 - 1:
+        raise ValueError("labels must be (B,U) with U >= log_probs.size(2)-1")
+    return _reduce(_RNNTFn.apply(x, lab, fl, ll, int(blank), None, T, U1), reduction)
+
+
 def RNNTLoss(log_probs, labels, frames_lengths, labels_lengths, blank_id: int = 0, compact: bool = False,
              gather: bool = True, reduction: str = "mean", **_unused):
     """Callable with the keyword signature model.py:97-105 uses on `warp_rnnt.RNNTLoss`."""
-    if compact:
-        raise NotImplementedError("compact=True (packed (sum T*U, V) layout, model.py:147-200) is not implemented")
-    return rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank=blank_id, reduction=reduction)
+    return rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank=blank_id, reduction=reduction,
+                     compact=compact)
 
 
 class RNNTPredictorJoiner(nn.Module):
@@ -104,3 +121,22 @@ class RNNTPredictorJoiner(nn.Module):
         pred = self._lin(pred_emb, self.pred_proj)               # (B, U+1, J)
         joint = torch.tanh(enc.unsqueeze(2) + pred.unsqueeze(1))  # (B, T, U+1, J)
         return self._lin(joint, self.joiner)                     # (B, T, U+1, V)
+
+
+class RNNTCompactPredictorJoiner(RNNTPredictorJoiner):
+    """model.py:147-200: joint only over the live T_b x (U_b+1) nodes of every utterance, packed
+    as (sum_b T_b*(U_b+1), J) rows -> (rows, V) logits (no padding work, no padded lattice)."""
+
+    def forward(self, enc_out, prefix, in_lens, tgt_lens):
+        B = enc_out.size(0)
+        in_lens = [int(v) for v in (in_lens.tolist() if isinstance(in_lens, torch.Tensor) else in_lens)]
+        tgt_lens = [int(v) for v in (tgt_lens.tolist() if isinstance(tgt_lens, torch.Tensor) else tgt_lens)]
+        enc = self._lin(enc_out, self.enc_proj)                  # (B, T, J)
+        pred = self._lin(self.embedding(prefix), self.pred_proj)  # (B, U+1, J)
+        parts = []
+        for b in range(B):
+            T, U1 = in_lens[b], tgt_lens[b] + 1
+            if T > 0:
+                parts.append(torch.tanh(enc[b, :T].unsqueeze(1) + pred[b, :U1].unsqueeze(0)).reshape(T * U1, -1))
+        joint = torch.cat(parts, 0) if parts else enc.new_zeros(0, enc.size(-1))
+        return self._lin(joint, self.joiner)                     # (rows, V)

@@ -151,3 +151,22 @@ def test_compute_loss_glue_carries_state(cuda_device):
         scale = max(1e-3, np.abs(want).max())
         assert np.abs(p.grad.cpu().numpy() - want).max() <= 2e-4 * scale, k      # grads accumulated over 3 segments
     np.testing.assert_allclose(torch.stack(state[0]).cpu().numpy(), torch.stack(ref_state[0]).detach().numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_empty_and_single_frame_segments(cuda_device):
+    """T=0 (e.g. stack_order trims everything) and T=1 segments: shapes follow the reference
+    (logits [B,0,V] / [B,1,V]); state passes through unchanged for T=0."""
+    import statecatcher_b200 as sb
+    for train in (True, False):
+        cfg = sb.LucyRNNConfig(input_dim=5, hidden_dim=8, num_layers=2, vocab_size=6, fused_ops=True, layer_norm=False,
+                               is_training=train, stack_order=3)
+        m = sb.LucyRNN(cfg).cuda()
+        h = [torch.randn(2, 8).cuda() for _ in range(2)]
+        s = [torch.randn(2, 8).cuda() for _ in range(2)]
+        h_in = [t.clone() for t in h]
+        logits, (h2, s2) = m(torch.randn(2, 2, 5).cuda(), (h, s))      # 2 frames, stack 3 -> 0 frames
+        assert logits.shape == (2, 0, 6)
+        for a, b in zip(h2, h_in):
+            assert torch.equal(a, b)
+        logits, _ = m(torch.randn(2, 3, 5).cuda())                      # exactly one stacked frame
+        assert logits.shape == (2, 1, 6) and torch.isfinite(logits).all()

@@ -58,8 +58,31 @@ def test_rnnt_reference_call_signature_and_zero_frames(cuda_device):
     assert loss.dim() == 0
     loss.backward()
     assert (lp.grad[1] == 0).all() and torch.isfinite(lp.grad).all()
-    with pytest.raises(NotImplementedError):
-        sb.RNNTLoss(log_probs=lp, labels=labels, frames_lengths=[T] * B, labels_lengths=[U] * B, compact=True)
+
+
+def test_rnnt_compact_packing_matches_padded(cuda_device):
+    """compact=True (model.py:147-200 packing): same loss and the same gradients as the padded
+    call, through the compact joiner."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(3)
+    B, T, U, V, J, E = 3, 14, 5, 16, 24, 8
+    fl, ll = [14, 9, 11], [5, 2, 0]
+    joiner = sb.RNNTPredictorJoiner(enc_out_dim=V, pred_emb_dim=E, join_dim=J, vocab_size=V).cuda()
+    cj = sb.RNNTCompactPredictorJoiner(enc_out_dim=V, pred_emb_dim=E, join_dim=J, vocab_size=V).cuda()
+    cj.load_state_dict(joiner.state_dict())
+    enc_out = torch.randn(B, T, V, device="cuda")
+    tokens = torch.randint(1, V, (B, U), device="cuda")
+    prefix = torch.cat([torch.zeros(B, 1, dtype=torch.long, device="cuda"), tokens], 1)
+    lp = joiner(enc_out, prefix).log_softmax(-1)
+    loss_p = sb.RNNTLoss(log_probs=lp, labels=tokens, frames_lengths=fl, labels_lengths=ll, blank_id=0)
+    loss_p.backward()
+    lpc = cj(enc_out, prefix, fl, ll).log_softmax(-1)
+    assert lpc.shape[0] == sum(t * (u + 1) for t, u in zip(fl, ll))
+    loss_c = sb.RNNTLoss(log_probs=lpc, labels=tokens, frames_lengths=fl, labels_lengths=ll, blank_id=0, compact=True)
+    loss_c.backward()
+    np.testing.assert_allclose(loss_c.item(), loss_p.item(), rtol=1e-5)
+    for (n, p), (_, q) in zip(joiner.named_parameters(), cj.named_parameters()):
+        np.testing.assert_allclose(q.grad.cpu().numpy(), p.grad.cpu().numpy(), rtol=2e-4, atol=1e-6, err_msg=n)
 
 
 def test_rnnt_joiner_and_large_lattice(cuda_device):
