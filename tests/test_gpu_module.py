@@ -170,3 +170,37 @@ def test_empty_and_single_frame_segments(cuda_device):
             assert torch.equal(a, b)
         logits, _ = m(torch.randn(2, 3, 5).cuda())                      # exactly one stacked frame
         assert logits.shape == (2, 1, 6) and torch.isfinite(logits).all()
+
+
+@pytest.mark.parametrize("train", [True, False], ids=["training_path", "step_path"])
+def test_long_stream_120_segments_state_carry(cuda_device, train):
+    """configs[4]-style run at small width: one stream set cut into 120 consecutive segments,
+    state detached and carried 119 times.  The final state and the last segment's logits must
+    equal the oracle evaluated the same way (no drift from the handoff); in the step path they
+    must also equal ONE pass over the concatenated 120-segment input, bit for bit."""
+    import statecatcher_b200 as sb
+    cfg = sb.LucyRNNConfig(input_dim=8, hidden_dim=16, num_layers=2, vocab_size=7, fused_ops=True, layer_norm=False,
+                           is_training=train)
+    ocfg = LO.OracleConfig(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    P = LO.random_params(ocfg, 21, dtype=torch.float32)
+    model = sb.LucyRNN(cfg).cuda()
+    model.load_state_dict(P)
+    g = torch.Generator().manual_seed(5)
+    B, T, K = 2, 24, 120
+    x = torch.randn(B, T * K, 8, generator=g) * 0.5
+    state, ostate = None, None
+    Pd = {k: v.double() for k, v in P.items()}
+    with torch.no_grad():
+        for i in range(K):
+            seg = x[:, i * T:(i + 1) * T]
+            if state:
+                state = sb.detach_states(state)
+            logits, state = model(seg.cuda(), state) if state else model(seg.cuda())
+            ologits, ostate = LO.forward_closed(Pd, ocfg, seg.double(), ostate)
+        np.testing.assert_allclose(logits.cpu().numpy(), ologits.numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(torch.stack(state[0]).cpu().numpy(), torch.stack(ostate[0]).numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(torch.stack(state[1]).cpu().numpy(), torch.stack(ostate[1]).numpy(), rtol=2e-4, atol=2e-5)
+        if not train:
+            whole, wstate = model(x.cuda())
+            assert torch.equal(whole[:, -T:], logits)
+            assert all(torch.equal(a, b) for a, b in zip(wstate[0] + wstate[1], state[0] + state[1]))
