@@ -198,6 +198,38 @@ int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* frame_lens,
                 const float* beta, const float* nll, const float* grad_w, float* grad,
                 void* stream);
 
+/* ---------------------------------------------------------------- K4': fused joint head
+ * Chunked joint -> loss path that never materialises the (B,T,U+1,V) logits of
+ * model.py:136-144 as a whole (host logic in rnnt.py RNNTFusedHead).
+ * joint_fwd : out[b,t,u,:] = tanh(enc[b,t,:] + pred[b,u,:])  for a block of Tc frames
+ *             (enc/pred strides in elements: batch, then frame / label position).
+ * joint_bwd : d_pre = dJ*(1-joint^2) (joint recomputed); d_enc[b,t,:] = sum_u d_pre (written),
+ *             d_pred[b,u,:] += sum_t d_pre (fp32 [B,U1,J], accumulated across blocks).
+ * rnnt_lse_gather: logits [B,Tc,U1,V] of frames [t0,t0+Tc) -> lse [B,T,U1] and the skewed
+ *             eb/el entries of those nodes.
+ * rnnt_lattice   : alpha/beta/nll from filled eb/el (same kernel as sc_rnnt_fwd).
+ * rnnt_node_grads: gb/gl [B,T,U1] = d(sum_b grad_w[b]*nll_b)/d(log-prob of blank / label).
+ * rnnt_dlogits   : dlogits[b,tc,u,v] = gb*([v==blank]-p_v) + gl*([v==label]-p_v). */
+int sc_joint_fwd(const void* enc, int64_t enc_sb, int64_t enc_st, const void* pred, int64_t pred_sb,
+                 int64_t pred_su, void* out, int64_t B, int64_t Tc, int64_t U1, int64_t J, int dtype,
+                 void* stream);
+int sc_joint_bwd(const void* dJ, const void* enc, int64_t enc_sb, int64_t enc_st, const void* pred,
+                 int64_t pred_sb, int64_t pred_su, void* d_enc, int64_t denc_sb, int64_t denc_st,
+                 float* d_pred, int64_t B, int64_t Tc, int64_t U1, int64_t J, int dtype, void* stream);
+int sc_rnnt_lse_gather(const void* logits, int dtype, const int64_t* labels, int64_t ldl,
+                       const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T,
+                       int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, float* lse,
+                       float* eb, float* el, void* stream);
+int sc_rnnt_lattice(const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T, int64_t U1,
+                    const float* eb, const float* el, float* alpha, float* beta, float* nll, void* stream);
+int sc_rnnt_node_grads(const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T,
+                       int64_t U1, const float* eb, const float* el, const float* alpha, const float* beta,
+                       const float* nll, const float* grad_w, float* gb, float* gl, void* stream);
+int sc_rnnt_dlogits(const void* logits, int dtype, const float* lse, const float* gb, const float* gl,
+                    const int64_t* labels, int64_t ldl, const int64_t* label_lens, int64_t B, int64_t T,
+                    int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, void* dlogits,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

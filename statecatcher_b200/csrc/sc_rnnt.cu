@@ -215,6 +215,159 @@ __global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __re
   }
 }
 
+
+// ================================================================== fused joint head ==
+// Pieces of the chunked joint -> loss path (rnnt.py: RNNTFusedHead): the (B,T,U+1,V) logits
+// of model.py:136-144 are never materialised as a whole — they are produced for a block of
+// frames, reduced to the two log-probs each lattice node needs, and recomputed per block in
+// the backward.
+
+// joint[b,t,u,:] = tanh(enc[b,t,:] + pred[b,u,:])      (model.py:139-140)
+template <typename T>
+__global__ void joint_fwd_kernel(const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
+                                 const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
+                                 T* __restrict__ out, int B, int Tc, int U1, int J) {
+  const int64_t row = blockIdx.x;                       // (b, t, u)
+  const int u = (int)(row % U1);
+  const int t = (int)((row / U1) % Tc);
+  const int b = (int)(row / ((int64_t)U1 * Tc));
+  const T* e = enc + b * enc_sb + t * enc_st;
+  const T* p = pred + b * pred_sb + u * pred_su;
+  T* o = out + row * J;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) st_f(o + j, tanhf_<true>(ld_f(e + j) + ld_f(p + j)));
+}
+
+// d_pre = dJ * (1 - joint^2), joint recomputed from enc/pred.
+// REDUCE_U: d_enc[b,t,:] = sum_u d_pre        (one block per (b,t), written)
+// else    : d_pred[b,u,:] += sum_t d_pre      (one block per (b,u), fp32 accumulate across chunks)
+template <typename T, bool REDUCE_U>
+__global__ void joint_bwd_kernel(const T* __restrict__ dJ, const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
+                                 const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
+                                 T* __restrict__ d_enc, int64_t denc_sb, int64_t denc_st,
+                                 float* __restrict__ d_pred, int B, int Tc, int U1, int J) {
+  const int b = blockIdx.x / (REDUCE_U ? Tc : U1);
+  const int fixed = blockIdx.x % (REDUCE_U ? Tc : U1);  // t (REDUCE_U) or u
+  const int n = REDUCE_U ? U1 : Tc;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    float acc = 0.f;
+    const float base = REDUCE_U ? ld_f(enc + b * enc_sb + fixed * enc_st + j) : ld_f(pred + b * pred_sb + fixed * pred_su + j);
+    for (int i = 0; i < n; ++i) {
+      const int t = REDUCE_U ? fixed : i, u = REDUCE_U ? i : fixed;
+      const float other = REDUCE_U ? ld_f(pred + b * pred_sb + u * pred_su + j) : ld_f(enc + b * enc_sb + t * enc_st + j);
+      const float jt = tanhf_<true>(base + other);
+      const float g = ld_f(dJ + (((int64_t)b * Tc + t) * U1 + u) * J + j);
+      acc = fmaf(g, 1.f - jt * jt, acc);
+    }
+    if (REDUCE_U) st_f(d_enc + b * denc_sb + fixed * denc_st + j, acc);
+    else d_pred[((int64_t)b * U1 + fixed) * J + j] += acc;
+  }
+}
+
+// rows of joint logits [B, Tc, U1, V] for frames [t0, t0+Tc): lse per node + the two log-probs
+// into the skewed eb/el arrays
+template <typename T>
+__global__ void __launch_bounds__(256)
+rnnt_lse_gather_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, int64_t ldl,
+                       const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
+                       int B, int Tn, int t0, int Tc, int U1, int V, int U1p, int64_t blank,
+                       float* __restrict__ lse, float* __restrict__ eb, float* __restrict__ el) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= (int64_t)B * Tc * U1) return;
+  const int u = (int)(row % U1);
+  const int tc = (int)((row / U1) % Tc);
+  const int b = (int)(row / ((int64_t)U1 * Tc));
+  const int t = t0 + tc;
+  int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
+  const int64_t Ub = label_lens[b];
+  if (t >= Tb || u > Ub) return;
+  const T* x = logits + row * V;
+  float m = NEG_INF, ssum = 0.f;
+  for (int i = lane; i < V; i += 32) {
+    const float f = ld_f(x + i);
+    const float nm = fmaxf(m, f);
+    ssum = ssum * __expf(m - nm) + __expf(f - nm);
+    m = nm;
+  }
+  const float gm = warp_max(m);
+  ssum = (m == NEG_INF) ? 0.f : ssum * __expf(m - gm);
+  const float l = gm + __logf(warp_sum(ssum));
+  if (lane == 0) {
+    const int64_t D = Tn + U1;
+    const int64_t o = ((int64_t)b * D + (t + u)) * U1p + u;
+    lse[((int64_t)b * Tn + t) * U1 + u] = l;
+    eb[o] = ld_f(x + blank) - l;
+    el[o] = (u < Ub) ? ld_f(x + labels[(int64_t)b * ldl + u]) - l : NEG_INF;
+  }
+}
+
+// per-node gradients of sum_b w_b*nll_b w.r.t. the blank / label LOG-PROB of the node
+__global__ void rnnt_node_grad_kernel(const float* __restrict__ eb, const float* __restrict__ el,
+                                      const float* __restrict__ alpha, const float* __restrict__ beta,
+                                      const float* __restrict__ nll, const float* __restrict__ grad_w,
+                                      const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
+                                      int B, int Tn, int U1, int U1p, float* __restrict__ gb, float* __restrict__ gl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Tn * U1) return;
+  const int u = (int)(i % U1);
+  const int t = (int)((i / U1) % Tn);
+  const int b = (int)(i / ((int64_t)U1 * Tn));
+  int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
+  const int64_t Ub = label_lens[b];
+  float vb = 0.f, vl = 0.f;
+  if (t < Tb && u <= Ub) {
+    const int64_t D = Tn + U1;
+    const int64_t base = (int64_t)b * D * U1p;
+    const int64_t o = base + (int64_t)(t + u) * U1p + u;
+    const float a = alpha[o];
+    if (a > NEG_INF) {
+      const float ll = -nll[b], w = grad_w[b];
+      float nb = NEG_INF;
+      if (t + 1 < Tb) nb = beta[base + (int64_t)(t + 1 + u) * U1p + u];
+      else if (u == Ub) nb = 0.f;
+      if (nb > NEG_INF) vb = -w * __expf(a + eb[o] + nb - ll);
+      if (u < Ub) {
+        const float nl = beta[base + (int64_t)(t + u + 1) * U1p + (u + 1)];
+        if (nl > NEG_INF) vl = -w * __expf(a + el[o] + nl - ll);
+      }
+    }
+  }
+  gb[i] = vb;
+  gl[i] = vl;
+}
+
+// dlogits[v] = gb*([v==blank]-p_v) + gl*([v==label]-p_v),  p = softmax(logits) of the node
+template <typename T>
+__global__ void __launch_bounds__(256)
+rnnt_dlogits_kernel(const T* __restrict__ logits, const float* __restrict__ lse, const float* __restrict__ gb,
+                    const float* __restrict__ gl, const int64_t* __restrict__ labels, int64_t ldl,
+                    const int64_t* __restrict__ label_lens, int B, int Tn, int t0, int Tc, int U1, int V,
+                    int64_t blank, T* __restrict__ dlogits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= (int64_t)B * Tc * U1) return;
+  const int u = (int)(row % U1);
+  const int tc = (int)((row / U1) % Tc);
+  const int b = (int)(row / ((int64_t)U1 * Tc));
+  const int64_t node = ((int64_t)b * Tn + t0 + tc) * U1 + u;
+  const float vb = gb[node], vl = gl[node];
+  T* d = dlogits + row * V;
+  if (vb == 0.f && vl == 0.f) {                        // dead node (or zero weight): exact zeros
+    for (int i = lane; i < V; i += 32) st_f(d + i, 0.f);
+    return;
+  }
+  const T* x = logits + row * V;
+  const float l = lse[node];
+  const float tot = vb + vl;
+  const int64_t lab = (u < label_lens[b]) ? labels[(int64_t)b * ldl + u] : -1;
+  for (int i = lane; i < V; i += 32) {
+    float g = -tot * __expf(ld_f(x + i) - l);
+    if (i == blank) g += vb;
+    if (i == lab) g += vl;
+    st_f(d + i, g);
+  }
+}
+
 }  // namespace sc
 
 using namespace sc;
@@ -268,5 +421,100 @@ extern "C" int sc_rnnt_bwd(const int64_t* labels, int64_t ldl, const int64_t* fr
   const int64_t n = B * T * U1;
   rnnt_grad_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(eb, el, alpha, beta, nll, grad_w, labels, ldl, frame_lens,
       label_lens, (int)B, (int)T, (int)U1, (int)V, U1p, blank, row_offsets, grad);
+  SC_LAUNCH_RET();
+}
+
+// ---------------------------------------------------------------- fused joint head ABI
+extern "C" int sc_joint_fwd(const void* enc, int64_t enc_sb, int64_t enc_st, const void* pred, int64_t pred_sb,
+                            int64_t pred_su, void* out, int64_t B, int64_t Tc, int64_t U1, int64_t J, int dtype,
+                            void* stream) {
+  SC_CHECK_ARG(B > 0 && Tc >= 0 && U1 > 0 && J > 0 && B * Tc * U1 < ((int64_t)1 << 31), SC_E_SHAPE);
+  if (Tc == 0) return 0;
+  SC_CHECK_ARG(enc && pred && out, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)(B * Tc * U1);
+  const int threads = J >= 256 ? 256 : 128;
+  if (dtype == SC_BF16) joint_fwd_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)enc, enc_sb, enc_st, (const bf16*)pred, pred_sb, pred_su, (bf16*)out, (int)B, (int)Tc, (int)U1, (int)J);
+  else if (dtype == SC_F32) joint_fwd_kernel<float><<<grid, threads, 0, st>>>((const float*)enc, enc_sb, enc_st, (const float*)pred, pred_sb, pred_su, (float*)out, (int)B, (int)Tc, (int)U1, (int)J);
+  else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_joint_bwd(const void* dJ, const void* enc, int64_t enc_sb, int64_t enc_st, const void* pred,
+                            int64_t pred_sb, int64_t pred_su, void* d_enc, int64_t denc_sb, int64_t denc_st,
+                            float* d_pred, int64_t B, int64_t Tc, int64_t U1, int64_t J, int dtype, void* stream) {
+  SC_CHECK_ARG(B > 0 && Tc >= 0 && U1 > 0 && J > 0, SC_E_SHAPE);
+  if (Tc == 0) return 0;
+  SC_CHECK_ARG(dJ && enc && pred && d_enc && d_pred, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = J >= 256 ? 256 : 128;
+  if (dtype == SC_BF16) {
+    joint_bwd_kernel<bf16, true><<<(unsigned)(B * Tc), threads, 0, st>>>((const bf16*)dJ, (const bf16*)enc, enc_sb, enc_st, (const bf16*)pred, pred_sb, pred_su, (bf16*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
+    joint_bwd_kernel<bf16, false><<<(unsigned)(B * U1), threads, 0, st>>>((const bf16*)dJ, (const bf16*)enc, enc_sb, enc_st, (const bf16*)pred, pred_sb, pred_su, (bf16*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
+  } else if (dtype == SC_F32) {
+    joint_bwd_kernel<float, true><<<(unsigned)(B * Tc), threads, 0, st>>>((const float*)dJ, (const float*)enc, enc_sb, enc_st, (const float*)pred, pred_sb, pred_su, (float*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
+    joint_bwd_kernel<float, false><<<(unsigned)(B * U1), threads, 0, st>>>((const float*)dJ, (const float*)enc, enc_sb, enc_st, (const float*)pred, pred_sb, pred_su, (float*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
+  } else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_rnnt_lse_gather(const void* logits, int dtype, const int64_t* labels, int64_t ldl,
+                                  const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T,
+                                  int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, float* lse,
+                                  float* eb, float* el, void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank) && t0 >= 0 && Tc >= 0 && t0 + Tc <= T, SC_E_SHAPE);
+  if (Tc == 0) return 0;
+  SC_CHECK_ARG(logits && frame_lens && label_lens && lse && eb && el && (U1 == 1 || labels), SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int U1p = (int)((U1 + 3) & ~(int64_t)3);
+  const unsigned grid = (unsigned)cdiv(B * Tc * U1, 8);
+  if (dtype == SC_BF16) rnnt_lse_gather_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)logits, labels, ldl, frame_lens, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, U1p, blank, lse, eb, el);
+  else if (dtype == SC_F32) rnnt_lse_gather_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, labels, ldl, frame_lens, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, U1p, blank, lse, eb, el);
+  else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+// alpha/beta + nll from already-filled eb/el (the second half of sc_rnnt_fwd)
+extern "C" int sc_rnnt_lattice(const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T, int64_t U1,
+                               const float* eb, const float* el, float* alpha, float* beta, float* nll, void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, 1, 0), SC_E_SHAPE);
+  SC_CHECK_ARG(frame_lens && label_lens && nll && (T == 0 || (eb && el && alpha && beta)), SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int U1p = (int)((U1 + 3) & ~(int64_t)3);
+  int threads = ((U1p + 31) / 32) * 32;
+  const size_t smem = (2 * (size_t)(U1p + 4) + 4 * (size_t)RNNT_EB * U1p) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rnnt_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  rnnt_alpha_beta_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(eb, el, frame_lens, label_lens, (int)T, (int)U1,
+      U1p, alpha, beta, nll);
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_rnnt_node_grads(const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T,
+                                  int64_t U1, const float* eb, const float* el, const float* alpha, const float* beta,
+                                  const float* nll, const float* grad_w, float* gb, float* gl, void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, 1, 0), SC_E_SHAPE);
+  if (T == 0) return 0;
+  SC_CHECK_ARG(frame_lens && label_lens && eb && el && alpha && beta && nll && grad_w && gb && gl, SC_E_BADARG);
+  const int U1p = (int)((U1 + 3) & ~(int64_t)3);
+  rnnt_node_grad_kernel<<<(unsigned)cdiv(B * T * U1, 256), 256, 0, (cudaStream_t)stream>>>(eb, el, alpha, beta, nll, grad_w,
+      frame_lens, label_lens, (int)B, (int)T, (int)U1, U1p, gb, gl);
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_rnnt_dlogits(const void* logits, int dtype, const float* lse, const float* gb, const float* gl,
+                               const int64_t* labels, int64_t ldl, const int64_t* label_lens, int64_t B, int64_t T,
+                               int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, void* dlogits,
+                               void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank) && t0 >= 0 && Tc >= 0 && t0 + Tc <= T, SC_E_SHAPE);
+  if (Tc == 0) return 0;
+  SC_CHECK_ARG(logits && lse && gb && gl && label_lens && dlogits && (U1 == 1 || labels), SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)cdiv(B * Tc * U1, 8);
+  if (dtype == SC_BF16) rnnt_dlogits_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)logits, lse, gb, gl, labels, ldl, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (bf16*)dlogits);
+  else if (dtype == SC_F32) rnnt_dlogits_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, lse, gb, gl, labels, ldl, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (float*)dlogits);
+  else return SC_E_DTYPE;
   SC_LAUNCH_RET();
 }

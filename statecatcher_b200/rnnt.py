@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, ops
 from ._lib import call, ptr, stream
 from .ctc import _lens
 from .lucyrnn import _LinearFn, _compute_dtype
@@ -140,3 +140,128 @@ class RNNTCompactPredictorJoiner(RNNTPredictorJoiner):
                 parts.append(torch.tanh(enc[b, :T].unsqueeze(1) + pred[b, :U1].unsqueeze(0)).reshape(T * U1, -1))
         joint = torch.cat(parts, 0) if parts else enc.new_zeros(0, enc.size(-1))
         return self._lin(joint, self.joiner)                     # (rows, V)
+
+
+# ------------------------------------------------------------------ fused joint head ----
+class _RNNTFusedFn(torch.autograd.Function):
+    """joiner (model.py:136-144) + log_softmax + transducer loss without the (B,T,U+1,V) tensor.
+
+    Forward: enc/pred projections once; then per block of ``chunk`` frames: joint = tanh(enc+pred)
+    -> logits (K1 GEMM) -> per-node lse and blank/label log-probs into the skewed lattice arrays;
+    the logits block is dropped.  Lattice recursion (K4) gives nll.  Backward: node gradients,
+    then per block the joint and logits are recomputed, dlogits formed in one pass and pushed
+    back through the joiner GEMMs; d_enc / d_pred reductions of the broadcast add by a custom
+    kernel.  Peak memory is one block, not the whole lattice.
+    """
+
+    @staticmethod
+    def forward(ctx, enc_out, pred_emb, labels, fl, ll, blank, chunk, cd, We, be, Wp, bp, Wo, bo):
+        B, T, De = enc_out.shape
+        U1, J, V = pred_emb.shape[1], We.shape[0], Wo.shape[0]
+        dev = enc_out.device
+        wcast = lambda w: w.detach() if w.dtype == cd else ops.cast(w.detach().contiguous(), cd)   # noqa: E731
+        Wec, Wpc, Woc = wcast(We), wcast(Wp), wcast(Wo)
+        e2 = enc_out.reshape(B * T, De)
+        p2 = pred_emb.reshape(B * U1, -1)
+        if e2.dtype != cd:
+            e2 = ops.cast(e2.contiguous(), cd)
+        if p2.dtype != cd:
+            p2 = ops.cast(p2.contiguous(), cd)
+        encp = ops.gemm_fwd(e2, Wec, be.detach()).view(B, T, J)
+        predp = ops.gemm_fwd(p2, Wpc, bp.detach()).view(B, U1, J)
+        U1p = (U1 + 3) & ~3
+        ws = lambda: torch.empty(B, T + U1, U1p, dtype=torch.float32, device=dev)   # noqa: E731
+        eb, el, alpha, beta = ws(), ws(), ws(), ws()
+        lse = torch.empty(B, max(T, 1), U1, dtype=torch.float32, device=dev)
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        ldl = labels.stride(0) if labels.numel() else max(U1 - 1, 1)
+        dtc = _lib.dt(encp)
+        for t0 in range(0, T, chunk):
+            Tc = min(chunk, T - t0)
+            joint = torch.empty(B * Tc * U1, J, dtype=cd, device=dev)
+            ech = encp[:, t0:t0 + Tc]
+            call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
+                 ptr(joint), B, Tc, U1, J, dtc, stream())
+            logits = ops.gemm_fwd(joint, Woc, bo.detach())
+            call("sc_rnnt_lse_gather", ptr(logits), _lib.dt(logits), ptr(labels), ldl, ptr(fl), ptr(ll), B, T, t0, Tc,
+                 U1, V, blank, ptr(lse), ptr(eb), ptr(el), stream())
+            del joint, logits
+        call("sc_rnnt_lattice", ptr(fl), ptr(ll), B, T, U1, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), stream())
+        ctx.save_for_backward(e2, p2, encp, predp, labels, fl, ll, eb, el, alpha, beta, lse, nll, Wec, Wpc, Woc, bo.detach())
+        ctx.cfg = (B, T, U1, J, V, De, blank, chunk, cd, ldl, tuple(pred_emb.shape))
+        return nll
+
+    @staticmethod
+    def backward(ctx, gnll):
+        (e2, p2, encp, predp, labels, fl, ll, eb, el, alpha, beta, lse, nll, Wec, Wpc, Woc, bo) = ctx.saved_tensors
+        B, T, U1, J, V, De, blank, chunk, cd, ldl, pshape = ctx.cfg
+        dev = nll.device
+        gb = torch.empty(B, max(T, 1), U1, dtype=torch.float32, device=dev)
+        gl = torch.empty_like(gb)
+        w = gnll.to(torch.float32).contiguous()
+        call("sc_rnnt_node_grads", ptr(fl), ptr(ll), B, T, U1, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), ptr(w),
+             ptr(gb), ptr(gl), stream())
+        d_encp = torch.empty(B, T, J, dtype=cd, device=dev)
+        d_predp = torch.zeros(B, U1, J, dtype=torch.float32, device=dev)
+        dWo = torch.zeros(V, J, dtype=torch.float32, device=dev)
+        dbo = torch.zeros(V, dtype=torch.float32, device=dev)
+        dtc = _lib.dt(encp)
+        for t0 in range(0, T, chunk):
+            Tc = min(chunk, T - t0)
+            ech = encp[:, t0:t0 + Tc]
+            joint = torch.empty(B * Tc * U1, J, dtype=cd, device=dev)
+            call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
+                 ptr(joint), B, Tc, U1, J, dtc, stream())
+            logits = ops.gemm_fwd(joint, Woc, bo)
+            dlogits = torch.empty_like(logits)
+            call("sc_rnnt_dlogits", ptr(logits), _lib.dt(logits), ptr(lse), ptr(gb), ptr(gl), ptr(labels), ldl, ptr(ll),
+                 B, T, t0, Tc, U1, V, blank, ptr(dlogits), stream())
+            del logits
+            ops.gemm_wgrad(dlogits, joint, out=dWo, accumulate=True)
+            ops.colsum(dlogits, out=dbo, accumulate=True)
+            dJ = ops.gemm_dgrad(dlogits, Woc)
+            del dlogits, joint
+            dch = d_encp[:, t0:t0 + Tc]
+            call("sc_joint_bwd", ptr(dJ), ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0),
+                 predp.stride(1), ptr(dch), dch.stride(0), dch.stride(1), ptr(d_predp), B, Tc, U1, J, dtc, stream())
+            del dJ
+        de2 = d_encp.view(B * T, J)
+        dp2 = d_predp.view(B * U1, J)
+        if dp2.dtype != cd:
+            dp2 = ops.cast(dp2, cd)
+        dWe, dbe = ops.gemm_wgrad(de2, e2), ops.colsum(de2)
+        dWp, dbp = ops.gemm_wgrad(dp2, p2), ops.colsum(dp2)
+        d_enc = ops.gemm_dgrad(de2, Wec).view(B, T, De) if ctx.needs_input_grad[0] else None
+        d_pred = ops.gemm_dgrad(dp2, Wpc).view(pshape) if ctx.needs_input_grad[1] else None
+        return (d_enc, d_pred, None, None, None, None, None, None, dWe, dbe, dWp, dbp, dWo, dbo)
+
+
+class RNNTFusedHead(nn.Module):
+    """Joiner + transducer loss in one node: same parameters (and state_dict keys) as
+    ``RNNTPredictorJoiner`` (model.py:112-145), same loss as ``RNNTLoss(joiner(...).log_softmax(-1))``,
+    but the (B,T,U+1,V) logits exist only one block of ``chunk_frames`` frames at a time, so
+    configs[3] (J=512, V=1024, T=3000, U<=150) runs at batch 64."""
+
+    def __init__(self, enc_out_dim: int, pred_emb_dim: int, join_dim: int, vocab_size: int,
+                 chunk_frames: int = 64, compute_dtype=None):
+        super().__init__()
+        self.embedding = nn.Embedding(vocab_size, pred_emb_dim)
+        self.enc_proj = nn.Linear(enc_out_dim, join_dim)
+        self.pred_proj = nn.Linear(pred_emb_dim, join_dim)
+        self.joiner = nn.Linear(join_dim, vocab_size)
+        self.chunk_frames = chunk_frames
+        self.compute_dtype = compute_dtype
+
+    def forward(self, enc_out, tokens, frames_lengths, labels_lengths, blank_id: int = 0, reduction: str = "mean"):
+        _lib.require_cuda(enc_out, "RNNTFusedHead input")
+        B = enc_out.size(0)
+        tokens = tokens.to(device=enc_out.device, dtype=torch.int64).contiguous()
+        prefix = torch.cat([torch.full((B, 1), blank_id, dtype=torch.int64, device=enc_out.device), tokens], dim=1)
+        fl, _ = _lens(frames_lengths, enc_out.device, B, "frames_lengths")
+        ll, _ = _lens(labels_lengths, enc_out.device, B, "labels_lengths")
+        cd = _compute_dtype(enc_out, self.compute_dtype)
+        pred_emb = self.embedding(prefix)
+        nll = _RNNTFusedFn.apply(enc_out.contiguous(), pred_emb.contiguous(), tokens, fl, ll, int(blank_id),
+                                 int(self.chunk_frames), cd, self.enc_proj.weight, self.enc_proj.bias,
+                                 self.pred_proj.weight, self.pred_proj.bias, self.joiner.weight, self.joiner.bias)
+        return _reduce(nll, reduction)

@@ -108,3 +108,54 @@ def test_rnnt_joiner_and_large_lattice(cuda_device):
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     ref, _ = rnnt_oracle.rnnt_loss_and_grad(lp[1:2].detach().cpu().numpy(), tokens[1:2].cpu().numpy(), [211], [37])
     np.testing.assert_allclose(nll[1].item(), ref[0], rtol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_rnnt_fused_head_matches_unfused(cuda_device, dtype):
+    """RNNTFusedHead (chunked joint -> loss, logits never materialised) == joiner +
+    log_softmax + RNNTLoss: loss, and gradients of every joiner parameter and of enc_out."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(4)
+    B, T, U, V, J, E, De = 3, 21, 6, 40, 32, 16, 24
+    fl, ll = [21, 13, 17], [6, 3, 0]
+    ref = sb.RNNTPredictorJoiner(enc_out_dim=De, pred_emb_dim=E, join_dim=J, vocab_size=V).cuda()
+    head = sb.RNNTFusedHead(enc_out_dim=De, pred_emb_dim=E, join_dim=J, vocab_size=V, chunk_frames=8,
+                            compute_dtype=dtype).cuda()
+    head.load_state_dict(ref.state_dict())
+    enc_a = torch.randn(B, T, De, device="cuda").requires_grad_(True)
+    enc_b = enc_a.detach().clone().requires_grad_(True)
+    tokens = torch.randint(1, V, (B, U), device="cuda")
+    prefix = torch.cat([torch.zeros(B, 1, dtype=torch.long, device="cuda"), tokens], 1)
+    loss_ref = sb.RNNTLoss(log_probs=ref(enc_a, prefix).float().log_softmax(-1), labels=tokens, frames_lengths=fl,
+                           labels_lengths=ll, blank_id=0)
+    loss_ref.backward()
+    loss = head(enc_b, tokens, fl, ll, blank_id=0)
+    loss.backward()
+    tol = 2e-4 if dtype == torch.float32 else 4e-2
+    assert abs(loss.item() - loss_ref.item()) <= tol * abs(loss_ref.item())
+    rel = lambda a, b: (a - b).norm().item() / max(b.norm().item(), 1e-12)   # noqa: E731
+    assert rel(enc_b.grad, enc_a.grad) <= tol * 2
+    for (n, p), (_, q) in zip(ref.named_parameters(), head.named_parameters()):
+        assert q.grad is not None, n
+        assert rel(q.grad, p.grad) <= tol * 2, (n, rel(q.grad, p.grad))
+
+
+def test_rnnt_fused_head_cfg4_shape(cuda_device):
+    """configs[3] geometry at reduced batch: J=512, V=1024, T=600, U=150, B=8 in bf16 — a lattice
+    whose materialised fp32 logits would be 3 GB; runs block-wise, finite, deterministic."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(0)
+    B, T, U, V, J, E = 8, 600, 150, 1024, 512, 64
+    head = sb.RNNTFusedHead(enc_out_dim=V, pred_emb_dim=E, join_dim=J, vocab_size=V, chunk_frames=64,
+                            compute_dtype=torch.bfloat16).cuda()
+    enc = (torch.randn(B, T, V, device="cuda") * 0.1).requires_grad_(True)
+    tokens = torch.randint(1, V, (B, U), device="cuda")
+    fl = [T] * B
+    ll = [75 + 9 * b for b in range(B)]
+    l1 = head(enc, tokens, fl, ll)
+    l1.backward()
+    l2 = head(enc.detach(), tokens, fl, ll)
+    assert torch.isfinite(l1) and l1.item() == l2.item()
+    assert torch.isfinite(enc.grad).all() and enc.grad.abs().max() > 0
+    for n, p in head.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
