@@ -32,6 +32,8 @@ WORKLOADS = {
     # name: model + data shape
     "cfg2": dict(L=6, H=1024, F=80, V=1024, B=64, T=3000, dtype="bf16", umin=75, umax=150),
     "cfg1": dict(L=2, H=256, F=80, V=1024, B=8, T=1000, dtype="f32", umin=25, umax=50),
+    # configs[3]: same encoder + RNN-T head (joint dim 512, pred emb 64) through RNNTFusedHead
+    "cfg4": dict(L=6, H=1024, F=80, V=1024, B=64, T=3000, dtype="bf16", umin=75, umax=150, rnnt=dict(J=512, E=64)),
 }
 
 
@@ -188,7 +190,8 @@ def reference_arm(args, W):
 
 
 def workload_config(args, W, world):
-    return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + CTC (V={W['V']}), {W['dtype']} training, "
+    headname = f"RNN-T fused head (J={W['rnnt']['J']})" if "rnnt" in W else "CTC"
+    return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + {headname} (V={W['V']}), {W['dtype']} training, "
                         f"batch {W['B']} streams/GPU x {W['T']} frames x {W['F']} fbank, carried state "
                         f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
             "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": True,
@@ -225,6 +228,12 @@ def main():
     enc = sb.LucyRNN(cfg, compute_dtype=cd)
     init_reference_like(enc, 1234)                 # same weights on every rank
     enc = enc.to(dev)
+    head = None
+    if "rnnt" in W:
+        torch.manual_seed(99)
+        head = sb.RNNTFusedHead(enc_out_dim=W["V"], pred_emb_dim=W["rnnt"]["E"], join_dim=W["rnnt"]["J"],
+                                vocab_size=W["V"], chunk_frames=64, compute_dtype=cd).to(dev)
+        full = torch.nn.ModuleDict({"enc": enc, "head": head})
     model = StreamDataParallel(enc) if world > 1 else enc
 
     # a few distinct synthetic segments per rank, cycled (streams of this rank: seed by rank)
@@ -244,7 +253,11 @@ def main():
         st = sb.detach_states(state["s"]) if state["s"] else None
         model.zero_grad(set_to_none=True)
         logits, state["s"] = model(xd[j], st) if st else model(xd[j])
-        loss = sb.ctc_loss_from_logits(logits, tokd[j], inld[j], tgld[j], zero_infinity=True)
+        if head is not None:
+            head.zero_grad(set_to_none=True)
+            loss = head(logits, tokd[j], inld[j], tgld[j], blank_id=0)
+        else:
+            loss = sb.ctc_loss_from_logits(logits, tokd[j], inld[j], tgld[j], zero_infinity=True)
         loss.backward()
         return loss
 
@@ -258,7 +271,11 @@ def main():
         st = sb.detach_states(state["s"]) if state["s"] else None
         model.zero_grad(set_to_none=True)
         logits, state["s"] = model(xbuf, st) if st else model(xbuf)
-        loss = sb.ctc_loss_from_logits(logits, tokbuf[j], hostb[j][2], hostb[j][3], zero_infinity=True)  # list lengths -> H2D
+        if head is not None:
+            head.zero_grad(set_to_none=True)
+            loss = head(logits, tokbuf[j], hostb[j][2], hostb[j][3], blank_id=0)
+        else:
+            loss = sb.ctc_loss_from_logits(logits, tokbuf[j], hostb[j][2], hostb[j][3], zero_infinity=True)  # list lengths -> H2D
         loss.backward()
         return loss.item()                                          # D2H result read
 
