@@ -223,18 +223,39 @@ __global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __re
 // the backward.
 
 // joint[b,t,u,:] = tanh(enc[b,t,:] + pred[b,u,:])      (model.py:139-140)
-template <typename T>
-__global__ void joint_fwd_kernel(const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
-                                 const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
-                                 T* __restrict__ out, int B, int Tc, int U1, int J) {
-  const int64_t row = blockIdx.x;                       // (b, t, u)
-  const int u = (int)(row % U1);
-  const int t = (int)((row / U1) % Tc);
-  const int b = (int)(row / ((int64_t)U1 * Tc));
-  const T* e = enc + b * enc_sb + t * enc_st;
-  const T* p = pred + b * pred_sb + u * pred_su;
-  T* o = out + row * J;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) st_f(o + j, tanhf_<true>(ld_f(e + j) + ld_f(p + j)));
+// One thread per 16-byte vector of the output (8 bf16 / 4 fp32), fully coalesced; enc/pred
+// rows are tiny and stay in L1/L2.  VECOK=false is the scalar path for odd J / alignment.
+template <typename T, bool VECOK>
+__global__ void __launch_bounds__(256)
+joint_fwd_kernel(const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
+                 const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
+                 T* __restrict__ out, int B, int Tc, int U1, int J) {
+  constexpr int VW = VECOK ? 16 / (int)sizeof(T) : 1;
+  const int vec_per_row = J / VW;
+  const int64_t total = (int64_t)B * Tc * U1 * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int jv = (int)(i % vec_per_row);
+    const int64_t row = i / vec_per_row;
+    const int u = (int)(row % U1);
+    const int t = (int)((row / U1) % Tc);
+    const int b = (int)(row / ((int64_t)U1 * Tc));
+    const T* e = enc + b * enc_sb + t * enc_st + jv * VW;
+    const T* p = pred + b * pred_sb + u * pred_su + jv * VW;
+    T* o = out + row * J + jv * VW;
+    if constexpr (VECOK) {
+      float fe[VW], fp[VW];
+      Vec<T, VW> ve, vp;
+      ve.raw = __ldg(reinterpret_cast<const uint4*>(e));
+      vp.raw = __ldg(reinterpret_cast<const uint4*>(p));
+      unpack(ve, fe); unpack(vp, fp);
+#pragma unroll
+      for (int k = 0; k < VW; ++k) fe[k] = tanhf_<false>(fe[k] + fp[k]);
+      const Vec<T, VW> vo = pack(fe, (T*)nullptr);
+      *reinterpret_cast<uint4*>(o) = vo.raw;
+    } else {
+      st_f(o, tanhf_<true>(ld_f(e) + ld_f(p)));
+    }
+  }
 }
 
 // d_pre = dJ * (1 - joint^2), joint recomputed from enc/pred.
@@ -432,11 +453,17 @@ extern "C" int sc_joint_fwd(const void* enc, int64_t enc_sb, int64_t enc_st, con
   if (Tc == 0) return 0;
   SC_CHECK_ARG(enc && pred && out, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)(B * Tc * U1);
-  const int threads = J >= 256 ? 256 : 128;
-  if (dtype == SC_BF16) joint_fwd_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)enc, enc_sb, enc_st, (const bf16*)pred, pred_sb, pred_su, (bf16*)out, (int)B, (int)Tc, (int)U1, (int)J);
-  else if (dtype == SC_F32) joint_fwd_kernel<float><<<grid, threads, 0, st>>>((const float*)enc, enc_sb, enc_st, (const float*)pred, pred_sb, pred_su, (float*)out, (int)B, (int)Tc, (int)U1, (int)J);
+  const bool al = (((uintptr_t)enc | (uintptr_t)pred | (uintptr_t)out) & 15) == 0;
+#define SC_JOINT(TT, VW_) do { \
+    const bool vec = al && (J % (VW_) == 0) && (enc_sb % (VW_) == 0) && (enc_st % (VW_) == 0) && (pred_sb % (VW_) == 0) && (pred_su % (VW_) == 0); \
+    const int64_t n = B * Tc * U1 * (vec ? J / (VW_) : J); \
+    const unsigned grid = (unsigned)min((int64_t)148 * 64, cdiv(n, 256)); \
+    if (vec) joint_fwd_kernel<TT, true><<<grid, 256, 0, st>>>((const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)out, (int)B, (int)Tc, (int)U1, (int)J); \
+    else joint_fwd_kernel<TT, false><<<grid, 256, 0, st>>>((const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)out, (int)B, (int)Tc, (int)U1, (int)J); } while (0)
+  if (dtype == SC_BF16) SC_JOINT(bf16, 8);
+  else if (dtype == SC_F32) SC_JOINT(float, 4);
   else return SC_E_DTYPE;
+#undef SC_JOINT
   SC_LAUNCH_RET();
 }
 
