@@ -176,16 +176,20 @@ class _RNNTFusedFn(torch.autograd.Function):
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         ldl = labels.stride(0) if labels.numel() else max(U1 - 1, 1)
         dtc = _lib.dt(encp)
+        # block buffers are allocated once and reused by every block (views for the tail block)
+        rows_max = B * min(chunk, max(T, 1)) * U1
+        joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
+        logits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
         for t0 in range(0, T, chunk):
             Tc = min(chunk, T - t0)
-            joint = torch.empty(B * Tc * U1, J, dtype=cd, device=dev)
+            joint, logits = joint_buf[:B * Tc * U1], logits_buf[:B * Tc * U1]
             ech = encp[:, t0:t0 + Tc]
             call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
                  ptr(joint), B, Tc, U1, J, dtc, stream())
-            logits = ops.gemm_fwd(joint, Woc, bo.detach())
+            ops.gemm_fwd(joint, Woc, bo.detach(), out=logits)
             call("sc_rnnt_lse_gather", ptr(logits), _lib.dt(logits), ptr(labels), ldl, ptr(fl), ptr(ll), B, T, t0, Tc,
                  U1, V, blank, ptr(lse), ptr(eb), ptr(el), stream())
-            del joint, logits
+        del joint_buf, logits_buf
         call("sc_rnnt_lattice", ptr(fl), ptr(ll), B, T, U1, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), stream())
         ctx.save_for_backward(e2, p2, encp, predp, labels, fl, ll, eb, el, alpha, beta, lse, nll, Wec, Wpc, Woc, bo.detach())
         ctx.cfg = (B, T, U1, J, V, De, blank, chunk, cd, ldl, tuple(pred_emb.shape))
@@ -206,25 +210,28 @@ class _RNNTFusedFn(torch.autograd.Function):
         dWo = torch.zeros(V, J, dtype=torch.float32, device=dev)
         dbo = torch.zeros(V, dtype=torch.float32, device=dev)
         dtc = _lib.dt(encp)
+        rows_max = B * min(chunk, max(T, 1)) * U1
+        joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
+        logits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
+        dlogits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
+        dJ_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
         for t0 in range(0, T, chunk):
             Tc = min(chunk, T - t0)
+            n = B * Tc * U1
+            joint, logits, dlogits, dJ = joint_buf[:n], logits_buf[:n], dlogits_buf[:n], dJ_buf[:n]
             ech = encp[:, t0:t0 + Tc]
-            joint = torch.empty(B * Tc * U1, J, dtype=cd, device=dev)
             call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
                  ptr(joint), B, Tc, U1, J, dtc, stream())
-            logits = ops.gemm_fwd(joint, Woc, bo)
-            dlogits = torch.empty_like(logits)
+            ops.gemm_fwd(joint, Woc, bo, out=logits)
             call("sc_rnnt_dlogits", ptr(logits), _lib.dt(logits), ptr(lse), ptr(gb), ptr(gl), ptr(labels), ldl, ptr(ll),
                  B, T, t0, Tc, U1, V, blank, ptr(dlogits), stream())
-            del logits
             ops.gemm_wgrad(dlogits, joint, out=dWo, accumulate=True)
             ops.colsum(dlogits, out=dbo, accumulate=True)
-            dJ = ops.gemm_dgrad(dlogits, Woc)
-            del dlogits, joint
+            ops.gemm_dgrad(dlogits, Woc, out=dJ)
             dch = d_encp[:, t0:t0 + Tc]
             call("sc_joint_bwd", ptr(dJ), ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0),
                  predp.stride(1), ptr(dch), dch.stride(0), dch.stride(1), ptr(d_predp), B, Tc, U1, J, dtc, stream())
-            del dJ
+        del joint_buf, logits_buf, dlogits_buf, dJ_buf
         de2 = d_encp.view(B * T, J)
         dp2 = d_predp.view(B * U1, J)
         if dp2.dtype != cd:
