@@ -230,6 +230,16 @@ int sc_rnnt_dlogits(const void* logits, int dtype, const float* lse, const float
                     int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, void* dlogits,
                     void* stream);
 
+/* ---------------------------------------------------------------- greedy CTC decode ---
+ * Replaces decoder.py:3-30 (argmax + Python collapse loop with one .item() sync per token).
+ * logits [B,T,V] (strides like sc_ctc_fwd; log-probs or raw logits — argmax is the same),
+ * in_lens [B] int64.  pred [B,T] int32 workspace; out_tokens [B,T] int64 receives each
+ * utterance's collapsed label sequence (blanks and repeats removed) left-aligned, out_lens [B]
+ * its length.  Argmax ties resolve to the lowest index. */
+int sc_ctc_greedy_decode(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                         const int64_t* in_lens, int64_t B, int64_t T, int64_t V, int64_t blank,
+                         int* pred, int64_t* out_tokens, int64_t* out_lens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,8 +7,9 @@ from .lucyrnn_conf import LucyRNNConfig
 from .lucyrnn import LucyRNN, LucyRNNCell, LucyRNNtriton
 from .ctc import CTCLoss, ctc_loss, ctc_loss_from_logits
 from .rnnt import RNNTCompactPredictorJoiner, RNNTFusedHead, RNNTLoss, RNNTPredictorJoiner, rnnt_loss
+from .decoder import ctc_greedy_decoder
 from .glue import LucyASRModel, assert_all_detached, compute_loss, detach_states
 
 __all__ = ["LucyRNNConfig", "LucyRNN", "LucyRNNCell", "LucyRNNtriton", "CTCLoss", "ctc_loss",
            "ctc_loss_from_logits", "LucyASRModel", "compute_loss", "detach_states",
-           "assert_all_detached", "RNNTLoss", "RNNTPredictorJoiner", "RNNTCompactPredictorJoiner", "RNNTFusedHead", "rnnt_loss"]
+           "assert_all_detached", "RNNTLoss", "RNNTPredictorJoiner", "RNNTCompactPredictorJoiner", "RNNTFusedHead", "rnnt_loss", "ctc_greedy_decoder"]
