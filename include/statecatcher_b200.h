@@ -240,6 +240,21 @@ int sc_ctc_greedy_decode(const void* logits, int64_t stride_b, int64_t stride_t,
                          const int64_t* in_lens, int64_t B, int64_t T, int64_t V, int64_t blank,
                          int* pred, int64_t* out_tokens, int64_t* out_lens, void* stream);
 
+/* ---------------------------------------------------------------- fused clip + Adam(W)
+ * Replaces clip_grad_norm_ (train.py:553), the per-parameter .item() grad-norm loop
+ * (train.py:555-560) and optimizer.step() for Adam/AdamW (train.py:112-137, 563-566).
+ * sumsq_accum: *acc (device double, caller zeroes it) += sum(g^2) over one fp32 tensor.
+ * scale_grads: g *= min(1, max_norm/(sqrt(*sumsq)+1e-6))           (standalone clip).
+ * adam_step  : one Adam (decoupled=0, weight decay as L2) / AdamW (decoupled=1) update of a
+ *              contiguous fp32 tensor; step is the 1-based step count (bias correction);
+ *              sumsq may be NULL (no clipping), else the clip coefficient above is applied to
+ *              the gradient on the fly (the gradient buffer itself is left untouched). */
+int sc_sumsq_accum(const float* g, int64_t n, double* acc, void* stream);
+int sc_scale_grads(float* g, int64_t n, const double* sumsq, float max_norm, void* stream);
+int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int64_t step, const double* sumsq,
+                 float max_norm, int decoupled, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,9 @@ SIGNATURES = {
     "sc_rnnt_node_grads": [P, P, I64, I64, I64, P, P, P, P, P, P, P, P, P],
     "sc_rnnt_dlogits": [P, I32, P, P, P, P, I64, P, I64, I64, I64, I64, I64, I64, I64, P, P],
     "sc_ctc_greedy_decode": [P, I64, I64, I32, P, I64, I64, I64, I64, P, P, P, P],
+    "sc_sumsq_accum": [P, I64, P, P],
+    "sc_scale_grads": [P, I64, P, F32, P],
+    "sc_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P, F32, I32, P],
 }
 _RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64}
 
