@@ -37,6 +37,7 @@ class _Bucket:
         self.pending = len(params)
         self.work = None
         self.flat: Optional[torch.Tensor] = None
+        self.avg_in_collective = False
 
 
 class StreamDataParallel(nn.Module):
@@ -102,7 +103,10 @@ class StreamDataParallel(nn.Module):
         if not grads:
             return
         b.flat = torch.cat([g.reshape(-1) for g in grads])
-        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        # NCCL averages inside the collective; gloo (CPU tests) only sums
+        b.avg_in_collective = self.average and dist.get_backend(self.pg) == "nccl"
+        op = dist.ReduceOp.AVG if b.avg_in_collective else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.pg, async_op=True)
         self.n_allreduce += 1
 
     def _finish(self):
@@ -115,14 +119,15 @@ class StreamDataParallel(nn.Module):
             if b.work is None:
                 continue
             b.work.wait()
-            flat = b.flat / self.world if self.average else b.flat
-            off = 0
-            for p in b.params:
-                if p.grad is None:
-                    continue
-                n = p.grad.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            flat = b.flat
+            if self.average and not b.avg_in_collective:
+                flat = flat / self.world
+            grads = [p.grad for p in b.params if p.grad is not None]
+            views, off = [], 0
+            for g in grads:
+                views.append(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            torch._foreach_copy_(grads, views)               # one fused copy-back per bucket
             b.work, b.flat = None, None
         self._armed = False
 
