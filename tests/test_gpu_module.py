@@ -204,3 +204,37 @@ def test_long_stream_120_segments_state_carry(cuda_device, train):
             whole, wstate = model(x.cuda())
             assert torch.equal(whole[:, -T:], logits)
             assert all(torch.equal(a, b) for a, b in zip(wstate[0] + wstate[1], state[0] + state[1]))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_module_vs_fp64_oracle_at_width_256(cuda_device, dtype):
+    """H=256 (cfg1 width), L=2, B=4, T=96: every projection runs on the tcgen05 kernels in bf16
+    (with projection folding) and on the SIMT kernels in fp32; compared with the fp64 oracle
+    (closed form + autograd).  fp32: rtol 1e-4 contract; bf16: the stated rel-L2 bounds."""
+    import statecatcher_b200 as sb
+    cfg = sb.LucyRNNConfig(input_dim=80, hidden_dim=256, num_layers=2, vocab_size=128, fused_ops=True, layer_norm=False)
+    ocfg = LO.OracleConfig(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    P = LO.reference_init_params(ocfg, 7, out_std=0.05)
+    model = sb.LucyRNN(cfg, compute_dtype=dtype).cuda()
+    model.load_state_dict(P)
+    g = torch.Generator().manual_seed(2)
+    B, T = 4, 96
+    x = torch.randn(B, T, 80, generator=g)
+    toks = torch.randint(1, 128, (B, 12), generator=g)
+    inl, tgl = [T, 80, T, 50], [12, 7, 0, 9]
+    Pd = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    ref_losses, ref_logits, ref_state = LO.train_segments(Pd, ocfg, [x.double()], [toks], [inl], [tgl], looped=False)
+    logits, state = model(x.cuda())
+    loss = sb.ctc_loss_from_logits(logits, toks.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)   # noqa: E731
+    lt, gt = (2e-5, 2e-4) if dtype == torch.float32 else (3e-2, 6e-2)
+    assert rel(logits.float().detach().cpu().numpy(), ref_logits[0].numpy()) <= lt
+    assert abs(loss.item() - ref_losses[0].item()) <= max(lt, 1e-4) * abs(ref_losses[0].item())
+    assert rel(torch.stack(state[0]).cpu().numpy(), torch.stack(ref_state[0]).detach().numpy()) <= lt
+    for k, p in model.named_parameters():
+        want = Pd[k].grad.numpy()
+        if np.abs(want).max() == 0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert rel(p.grad.cpu().numpy(), want) <= gt, (k, rel(p.grad.cpu().numpy(), want))
