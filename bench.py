@@ -33,6 +33,9 @@ WORKLOADS = {
     "cfg2": dict(L=6, H=1024, F=80, V=1024, B=64, T=3000, dtype="bf16", umin=75, umax=150),
     "cfg1": dict(L=2, H=256, F=80, V=1024, B=8, T=1000, dtype="f32", umin=25, umax=50),
     # configs[3]: same encoder + RNN-T head (joint dim 512, pred emb 64) through RNNTFusedHead
+    # configs[4], second half: streaming forward-only throughput (step path, state carried, no grad)
+    "cfg5_fwd_b64": dict(L=6, H=1024, F=80, V=1024, B=64, T=3000, dtype="bf16", umin=75, umax=150, forward_only=True),
+    "cfg5_fwd_b1": dict(L=6, H=1024, F=80, V=1024, B=1, T=3000, dtype="bf16", umin=75, umax=150, forward_only=True),
     "cfg4": dict(L=6, H=1024, F=80, V=1024, B=64, T=3000, dtype="bf16", umin=75, umax=150, rnnt=dict(J=512, E=64)),
 }
 
@@ -40,7 +43,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
@@ -194,7 +197,7 @@ def workload_config(args, W, world):
     return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + {headname} (V={W['V']}), {W['dtype']} training, "
                         f"batch {W['B']} streams/GPU x {W['T']} frames x {W['F']} fbank, carried state "
                         f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
-            "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": True,
+            "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": not W.get("forward_only", False),
             "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
             "l2_policy": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2",
             "optimizer": "excluded (SURVEY.md 8d); zero_grad included"}
@@ -223,8 +226,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cd = torch.bfloat16 if W["dtype"] == "bf16" else torch.float32
+    fwd_only = bool(W.get("forward_only"))
     cfg = sb.LucyRNNConfig(input_dim=W["F"], hidden_dim=W["H"], num_layers=W["L"], vocab_size=W["V"],
-                           is_training=True, fused_ops=True, layer_norm=bool(args.layer_norm))
+                           is_training=not fwd_only, fused_ops=True, layer_norm=bool(args.layer_norm))
     enc = sb.LucyRNN(cfg, compute_dtype=cd)
     init_reference_like(enc, 1234)                 # same weights on every rank
     enc = enc.to(dev)
@@ -250,6 +254,10 @@ def main():
 
     def step_resident(i):
         j = i % NSEG
+        if fwd_only:                                            # streaming inference: step path, no autograd
+            with torch.no_grad():
+                logits, state["s"] = model(xd[j], state["s"]) if state["s"] else model(xd[j])
+            return logits
         st = sb.detach_states(state["s"]) if state["s"] else None
         model.zero_grad(set_to_none=True)
         logits, state["s"] = model(xd[j], st) if st else model(xd[j])
@@ -267,6 +275,10 @@ def main():
     def step_e2e(i):
         j = i % NSEG
         xbuf.copy_(xh[j], non_blocking=True)                       # H2D features from pinned host
+        if fwd_only:
+            with torch.no_grad():
+                logits, state["s"] = model(xbuf, state["s"]) if state["s"] else model(xbuf)
+            return logits[:, -1, :8].float().cpu()                  # D2H read of a result slice
         tokbuf[j].copy_(tokh[j], non_blocking=True)                # H2D labels
         st = sb.detach_states(state["s"]) if state["s"] else None
         model.zero_grad(set_to_none=True)
@@ -329,11 +341,13 @@ def main():
 
     # ---- optimizer step, reported beside the metric, not inside it ----
     from statecatcher_b200.optim import FusedAdam
-    params = list(enc.parameters()) + (list(head.parameters()) if head is not None else [])
-    opt = FusedAdam(params, lr=1e-5, weight_decay=0.01, decoupled=True, max_grad_norm=50.0)   # train.py:553 clips at 50
-    for _ in range(2):
-        opt.step()
-    ms_opt = timed(lambda i: opt.step(), 5) / 5.0
+    ms_opt = None
+    if not fwd_only:
+        params = list(enc.parameters()) + (list(head.parameters()) if head is not None else [])
+        opt = FusedAdam(params, lr=1e-5, weight_decay=0.01, decoupled=True, max_grad_norm=50.0)   # train.py:553 clips at 50
+        for _ in range(2):
+            opt.step()
+        ms_opt = timed(lambda i: opt.step(), 5) / 5.0
 
     if rank != 0:
         if world > 1:
@@ -390,12 +404,13 @@ def main():
     roofline = dict(roofs[dominant], kernel=dominant) if dominant else None
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not fwd_only:
         fps, cores, sample, _, _, _ = cpu_reference_run(W, bool(args.layer_norm), 1, 0, args.cpu_seconds)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
 
     line = {
-        "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "metric": "forward_frames_per_sec" if fwd_only else "train_frames_per_sec", "value": value, "unit": "frames/s",
+        "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": W["dtype"], "data": "synthetic",
