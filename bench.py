@@ -194,7 +194,11 @@ def reference_arm(args, W):
 
 def workload_config(args, W, world):
     headname = f"RNN-T fused head (J={W['rnnt']['J']})" if "rnnt" in W else "CTC"
-    return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + {headname} (V={W['V']}), {W['dtype']} training, "
+    if W.get("forward_only"):
+        headname, mode = "output_proj only", "streaming forward-only (is_training=False step path, no autograd)"
+    else:
+        mode = "training"
+    return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + {headname} (V={W['V']}), {W['dtype']} {mode}, "
                         f"batch {W['B']} streams/GPU x {W['T']} frames x {W['F']} fbank, carried state "
                         f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
             "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": not W.get("forward_only", False),
