@@ -424,6 +424,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": host_enqueue_ms,
+        "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "optimizer": {"kind": "FusedAdam (AdamW + fused global-norm clip at 50, no host sync)", "ms_per_step": ms_opt,
                       "included_in_value": False},
         "roofline": roofline,
