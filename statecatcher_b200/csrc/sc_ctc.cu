@@ -364,7 +364,18 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
   zsum = warp_sum(zsum);
   const float inv = (zsum > 0.f) ? 1.f / zsum : 0.f;
   __syncwarp();
-  for (int s = lane; s < S; s += 32) atomicAdd(r + ext_label(tg, s, blank), -vb[s] * inv);
+  // Every other lattice node is the blank: its ~U+1 contributions are summed in registers and
+  // added once (as shared-memory atomics — CAS loops for fp32 — they all hit one address and
+  // were ~1/3 of the kernel's instructions); label nodes scatter with atomics (labels may repeat).
+  float bsum = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const float occ = vb[s] * inv;
+    if (s & 1) atomicAdd(r + tg[s >> 1], -occ);
+    else bsum += occ;
+  }
+  bsum = warp_sum(bsum);
+  __syncwarp();
+  if (lane == 0) r[blank] -= bsum;
   __syncwarp();
   float scale;
   if (reduction == 1) scale = grad_out[0] / ((float)B * fmaxf((float)U, 1.f));
