@@ -195,48 +195,51 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
       issue(0);
       if (nvis > 1) issue(1);
     }
-    int vi = 0, pos = 0, rows = rows_of(blk_of(0));
-    mbar_wait(smem_u32(&ebar[0]), 0);
-    auto emission = [&]() -> float {                           // row `pos` of the current visit, node s
-      const int r = dir == 0 ? pos : rows - 1 - pos;
-      return ebuf[((size_t)(vi & 1) * CTC_EB + r) * Smax + (has ? s : 0)];
-    };
-    // init column (step 0)
-    {
-      float v = NEG_INF;
-      if (has && (dir == 0 ? s < 2 : s >= S - 2)) v = emission();
-      if (has) { bufA[s] = v; out_b[(int64_t)t_first * Smax + s] = v; }
-    }
-    __syncthreads();
+    const int sidx = has ? s : 0;
     const int64_t stride = (int64_t)step * Smax;
-    float* op = out_b + (int64_t)t_first * Smax + (has ? s : 0);
-    int i = 1;
-    while (i < Tb) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {                            // unrolled by 2: static buffer parity
-        if (i < Tb) {
-          const float* src = j ? bufB : bufA;
-          float* dst = j ? bufA : bufB;
-          if (++pos == rows) {                                 // block exhausted (uniform)
-            if (threadIdx.x == 0 && vi + 2 < nvis) issue(vi + 2);   // its buffer is free: all threads passed the barrier
-            ++vi; pos = 0; rows = rows_of(blk_of(vi));
-            mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
-          }
-          const float e = emission();
-          op += stride;
-          float v = NEG_INF;
-          if (has) v = lse3_2(src[s], src[s + nb], skip ? src[s + 2 * nb] : NEG_INF) + e;
-          if ((i % CTC_RENORM) == 0) {
-            const float m = block_max(v);
-            if (m > NEG_INF) { v -= m; csum += (double)m; }
-          }
-          if (has) { dst[s] = v; *op = v; }
-          __syncthreads();
-          ++i;
+    float* op = out_b + (int64_t)t_first * Smax + sidx;
+    float* prev = bufA;
+    float* cur = bufB;
+    // Visit-structured loop: everything that happens once per 16-row emission block (barrier wait,
+    // re-centring, recycling the buffer) sits outside the per-timestep path, which is then just
+    // LDS x4 -> lse3 -> STS/STG -> barrier.
+    for (int vi = 0; vi < nvis; ++vi) {
+      mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+      const int rows = rows_of(blk_of(vi));
+      // emission pointer of this thread's node for the first row visited, and its per-step stride
+      const float* ep = ebuf + ((size_t)(vi & 1) * CTC_EB + (dir == 0 ? 0 : rows - 1)) * Smax + sidx;
+      const int estride = dir == 0 ? Smax : -Smax;
+      int pos = 0;
+      if (vi == 0) {                                             // init column (step 0)
+        float v = NEG_INF;
+        if (has && (dir == 0 ? s < 2 : s >= S - 2)) v = *ep;
+        if (has) { prev[s] = v; *op = v; }
+        __syncthreads();
+        ep += estride;
+        pos = 1;
+      } else {
+        // re-centre the last column once per visit (at most every CTC_EB steps)
+        const float m = block_max(has ? prev[s] : NEG_INF);
+        if (m > NEG_INF) {
+          if (has) { prev[s] -= m; *op = prev[s]; }
+          csum += (double)m;
         }
+        __syncthreads();
       }
+      for (; pos < rows; ++pos) {
+        const float e = *ep;
+        ep += estride;
+        op += stride;
+        float v = NEG_INF;
+        if (has) v = lse3_2(prev[s], prev[s + nb], skip ? prev[s + 2 * nb] : NEG_INF) + e;
+        if (has) { cur[s] = v; *op = v; }
+        __syncthreads();
+        float* tmp = prev; prev = cur; cur = tmp;
+      }
+      // every thread is past the barrier of this visit's last row: its buffer can be refilled
+      if (threadIdx.x == 0 && vi + 2 < nvis) issue(vi + 2);
     }
-    final_buf = ((Tb - 1) & 1) ? bufB : bufA;
+    final_buf = prev;
   } else {
     // ---- general path: several nodes per thread ----
     // init column
