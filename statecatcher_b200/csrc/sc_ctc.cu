@@ -308,7 +308,7 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
                 TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
   extern __shared__ __align__(128) float sm[];       // per warp: V floats (row) + Spad floats (lattice)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * CTC_WARPS + warp;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // warps per block shrink for large V
   if (row >= (int64_t)B * Tn) return;
   const int b = (int)(row / Tn), t = (int)(row % Tn);
   int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
@@ -448,14 +448,18 @@ static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_
                            int64_t blank, const float* lse, const float* alpha, const float* beta,
                            const float* nll, const float* grad_out, int reduction, void* dlogits,
                            int64_t dstride_b, int64_t dstride_t, cudaStream_t st) {
-  const size_t smem = (size_t)CTC_WARPS * (V + ((Smax + 3) & ~3)) * sizeof(float);
+  // one shared-memory row of V + S floats per warp: fewer warps per block when the vocabulary is large
+  const size_t per_warp = (size_t)(V + ((Smax + 3) & ~3)) * sizeof(float);
+  int warps = CTC_WARPS;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  const size_t smem = per_warp * warps;
   if (smem > 200 * 1024) return SC_E_SHAPE;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ctc_grad_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
-  ctc_grad_kernel<TI, TO><<<blocks, CTC_WARPS * 32, smem, st>>>((const TI*)logits, stride_b, stride_t, targets, ldt,
+  const unsigned blocks = (unsigned)cdiv(B * T, warps);
+  ctc_grad_kernel<TI, TO><<<blocks, warps * 32, smem, st>>>((const TI*)logits, stride_b, stride_t, targets, ldt,
       in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction,
       (TO*)dlogits, dstride_b, dstride_t);
   SC_LAUNCH_RET();

@@ -343,3 +343,21 @@ def test_ctc_large_properties(cuda_device):
     assert torch.isfinite(l1) and l1.item() == l2.item()
     assert (x.grad[3, 1700:] == 0).all() and (x.grad[5] == 0).all()
     assert x.grad.sum(-1).abs().max().item() < 1e-5
+
+
+def test_ctc_large_vocab(cuda_device):
+    """V=20000 (shared-memory row per warp no longer fits 8 warps per block)."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(8)
+    B, T, V, U = 2, 30, 20000, 5
+    logits = torch.randn(B, T, V, generator=g)
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl, tgl = [T, 22], [5, 3]
+    xd = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(xd.log_softmax(-1).transpose(0, 1), tokens, inl, tgl, zero_infinity=True)
+    ref.backward()
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=1e-7)
