@@ -95,3 +95,77 @@ def compute_loss(mode: str, criterion, model: nn.Module, feats, masks, tokens, i
     else:
         raise ValueError(f"Unknown mode: {mode}")
     return loss, output_state, enc_out, output_state
+
+
+class SegmentPrefetcher:
+    """Host -> device staging of segment batches, one batch ahead of the compute stream.
+
+    The reference moves each batch with a blocking ``.to(device)`` right before the forward
+    (train.py:505-512); at B200 speed that copy (61 MB of fp32 features for 64 x 3000 frames)
+    is ~3 % of a step.  This feeder issues the copy of batch i+1 on its own CUDA stream while
+    batch i computes, into one of two device buffers, and hands the consumer tensors that are
+    already ordered after the copy on the current stream.  Host tensors should be pinned.
+
+        feeder = SegmentPrefetcher(iter_of_tuples_of_host_tensors, device)
+        for feats, tokens, in_lens, tgt_lens in feeder: ...   # non-tensors pass through
+
+    A buffer is reused two batches later; the copy stream waits for the compute stream's
+    position at the time the *previous* batch was handed out, so a buffer is never overwritten
+    while kernels still read it.
+    """
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.dev = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.released = [None, None]          # compute-stream events guarding buffer reuse
+        self.slot = 0
+        self.pending = None
+        self._stage()
+
+    def _stage(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.pending = None
+            return
+        k = self.slot
+        isT = [torch.is_tensor(h) for h in host]
+        bufs = self.bufs[k]
+        if bufs is None or len(bufs) != len(host) or any(
+                t and (not torch.is_tensor(b) or b.shape != h.shape or b.dtype != h.dtype)
+                for b, h, t in zip(bufs, host, isT)):
+            bufs = [torch.empty(h.shape, dtype=h.dtype, device=self.dev) if t else None
+                    for h, t in zip(host, isT)]
+        with torch.cuda.stream(self.copy_stream):
+            if self.released[k] is not None:
+                self.copy_stream.wait_event(self.released[k])
+            for i, (h, t) in enumerate(zip(host, isT)):
+                if t:
+                    bufs[i].copy_(h, non_blocking=True)
+                else:
+                    bufs[i] = h                       # lengths lists etc. pass through
+            self.ready[k].record(self.copy_stream)
+        self.bufs[k] = bufs
+        self.pending = k
+        self.slot ^= 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.pending is None:
+            raise StopIteration
+        k = self.pending
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ready[k])
+        out = tuple(self.bufs[k])
+        # the other buffer was handed out one batch ago: everything enqueued on the compute
+        # stream up to now has finished with it once this event fires
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.released[k ^ 1] = ev
+        self._stage()
+        return out

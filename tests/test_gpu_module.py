@@ -238,3 +238,25 @@ def test_module_vs_fp64_oracle_at_width_256(cuda_device, dtype):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert rel(p.grad.cpu().numpy(), want) <= gt, (k, rel(p.grad.cpu().numpy(), want))
+
+
+@pytest.mark.gpu
+def test_segment_prefetcher_orders_copies():
+    """Batches come out in order, bit-identical, while a long kernel queue is still reading the
+    previous buffers (double-buffer reuse guarded by events)."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    host = [(torch.randn(64, 257, 80, generator=g).pin_memory(),
+             torch.randint(1, 50, (64, 9), generator=g).pin_memory(), [257] * 64, i) for i in range(7)]
+    feeder = sb.SegmentPrefetcher(iter(host), dev)
+    sums, refs = [], []
+    big = torch.randn(4096, 4096, device=dev)
+    for n, (x, tok, lens, tag) in enumerate(feeder):
+        assert tag == n and lens == [257] * 64 and x.is_cuda and tok.is_cuda
+        for _ in range(6):                                   # keep the compute stream busy
+            big = torch.tanh(big @ big * 1e-3)
+        sums.append((x.double().sum() + tok.sum()).reshape(1))       # reads the buffers late in the queue
+        refs.append(float(host[n][0].double().sum() + host[n][1].sum()))
+    assert len(sums) == 7
+    got = torch.cat(sums).cpu().tolist()
+    assert got == pytest.approx(refs, rel=1e-12)
