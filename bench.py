@@ -203,6 +203,9 @@ def workload_config(args, W, world):
                         f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
             "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": not W.get("forward_only", False),
             "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
+            "dp_allreduce": None if world == 1 else (
+                "bucketed, overlapped with backward" if os.environ.get("SC_DP_OVERLAP", "1") != "0"
+                else "bucketed, launched after backward"),
             "l2_policy": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2",
             "optimizer": "excluded (SURVEY.md 8d); zero_grad included"}
 

@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -42,9 +44,14 @@ class _Bucket:
 
 class StreamDataParallel(nn.Module):
     def __init__(self, module: nn.Module, process_group=None, bucket_mb: float = 32.0,
-                 average: bool = True):
+                 average: bool = True, overlap: Optional[bool] = None):
         super().__init__()
         self.module = module
+        if overlap is None:
+            overlap = os.environ.get("SC_DP_OVERLAP", "1") != "0"
+        # overlap=False: every bucket is launched from the end-of-backward callback instead of
+        # from its hook, so no NCCL kernel shares the SMs with the persistent GEMMs
+        self.overlap = overlap
         self.pg = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -95,7 +102,7 @@ class StreamDataParallel(nn.Module):
             torch.autograd.Variable._execution_engine.queue_callback(self._finish)
         b = self.buckets[self._p2b[p]]
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and self.overlap:
             self._launch(b)
 
     def _launch(self, b: _Bucket):
@@ -113,7 +120,7 @@ class StreamDataParallel(nn.Module):
         # params whose grad never arrived this backward (unused: the dead W_r / layernorm_r of
         # lucyrnn.py:50/56) leave their bucket incomplete on every rank alike: flush it now.
         for b in self.buckets:
-            if b.work is None and b.pending != len(b.params) and b.pending > 0:
+            if b.work is None and b.pending != len(b.params) and (b.pending > 0 or not self.overlap):
                 self._launch(b)
         for b in self.buckets:
             if b.work is None:
