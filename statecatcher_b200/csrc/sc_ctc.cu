@@ -12,9 +12,18 @@
 //   2. ctc_alpha_beta : one CTA per (utterance, direction); lattice node s on thread s; the
 //      previous column lives in a double-buffered shared-memory line, one __syncthreads per
 //      timestep; the emission for step t+1 is prefetched before the barrier of step t.
-//   3. ctc_grad       : one warp per frame: dlogits = gout*scale_b*(softmax - occupancy),
-//      occupancy scattered with shared-memory atomics; exact zeros for t>=T_b and for
-//      infeasible utterances (zero_infinity).
+//   3. ctc_grad       : one warp per frame: occupancy = softmax over the lattice of alpha+beta
+//      (lattice nodes taken as (blank,label) pairs, one float2 load each from alpha and beta,
+//      kept in registers between the max, the sum and the scatter);
+//      dlogits = gout*scale_b*(softmax - occupancy), label occupancies scattered with
+//      shared-memory atomics; exact zeros for t>=T_b and for infeasible utterances.
+// Tried and rejected (r01): (a) a scaled linear-domain recursion, one warp per lattice with
+// the column in registers — 6x shorter serial chain, but with T >> U the forward and backward
+// masses sit at opposite ends of the lattice and their overlap (the occupancy) lies 2^-125
+// and further below either column's maximum, outside fp32's range (measured on random
+// logits, T=300, U=30); (b) log-domain with 2 or 4 nodes per thread in registers and shuffle
+// exchange — 0.77 ms against 0.53 ms for one node per thread: fewer warps leave the
+// MUFU/FMNMX latency chain of each step exposed.
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
@@ -97,8 +106,10 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
 }
 
 // ---- pass 2 ------------------------------------------------------------------------
-// dir 0 = alpha (forward in t), dir 1 = beta (backward in t).  Both include the emission of
-// their own timestep, as in the oracle (ctc_oracle.py) and ATen.  Everything here is in
+// dir 0 = alpha (forward in t), dir 1 = beta (backward in t).  Both carry the emission of
+// their own timestep through the recursion, as in the oracle (ctc_oracle.py) and ATen; alpha is
+// written with it, beta WITHOUT it, so alpha+beta is the log-occupancy up to a per-frame constant
+// and the gradient pass needs no emission gather.  Everything here is in
 // LOG2 units (lplat is written pre-scaled by log2(e)) so the serial chain is
 // LDS -> max -> ex2 -> add -> lg2 -> add -> STS -> barrier with no multiplies and no branches:
 // the first version spent ~1300 cycles per timestep in ~90 dependent SASS instructions
@@ -111,6 +122,8 @@ __device__ __forceinline__ float lse3_2(float a, float b, float c) {
   return m + lg2f(ex2f(a - m) + ex2f(b - m) + ex2f(c - m));
 }
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float CTC_DEAD = -1e30f;          // below CTC_DEAD_TEST a log2-domain value counts as probability zero
+constexpr float CTC_DEAD_TEST = -1e29f;
 constexpr float LN2 = 0.6931471805599453f;
 
 __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
@@ -211,9 +224,9 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
       const int estride = dir == 0 ? Smax : -Smax;
       int pos = 0;
       if (vi == 0) {                                             // init column (step 0)
-        float v = NEG_INF;
-        if (has && (dir == 0 ? s < 2 : s >= S - 2)) v = *ep;
-        if (has) { prev[s] = v; *op = v; }
+        float v = NEG_INF, pre = NEG_INF;
+        if (has && (dir == 0 ? s < 2 : s >= S - 2)) { v = *ep; pre = 0.f; }
+        if (has) { prev[s] = v; *op = dir == 0 ? v : pre; }
         __syncthreads();
         ep += estride;
         pos = 1;
@@ -221,7 +234,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
         // re-centre the last column once per visit (at most every CTC_EB steps)
         const float m = block_max(has ? prev[s] : NEG_INF);
         if (m > NEG_INF) {
-          if (has) { prev[s] -= m; *op = prev[s]; }
+          if (has) prev[s] -= m;                                  // rows already written keep their own offset
           csum += (double)m;
         }
         __syncthreads();
@@ -230,9 +243,10 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
         const float e = *ep;
         ep += estride;
         op += stride;
-        float v = NEG_INF;
-        if (has) v = lse3_2(prev[s], prev[s + nb], skip ? prev[s + 2 * nb] : NEG_INF) + e;
-        if (has) { cur[s] = v; *op = v; }
+        float pre = NEG_INF;
+        if (has) pre = lse3_2(prev[s], prev[s + nb], skip ? prev[s + 2 * nb] : NEG_INF);
+        const float v = pre + e;
+        if (has) { cur[s] = v; *op = dir == 0 ? v : pre; }
         __syncthreads();
         float* tmp = prev; prev = cur; cur = tmp;
       }
@@ -244,19 +258,21 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     // ---- general path: several nodes per thread ----
     // init column
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      float v = NEG_INF;
-      if (dir == 0) { if (s < 2) v = lp_b[(int64_t)t_first * Smax + s]; }
-      else          { if (s >= S - 2) v = lp_b[(int64_t)t_first * Smax + s]; }
+      float v = NEG_INF, pre = NEG_INF;
+      if (dir == 0 ? s < 2 : s >= S - 2) { v = lp_b[(int64_t)t_first * Smax + s]; pre = 0.f; }
       bufA[s] = v;
-      out_b[(int64_t)t_first * Smax + s] = v;
+      out_b[(int64_t)t_first * Smax + s] = dir == 0 ? v : pre;
     }
     __syncthreads();
     float* prev = bufA;
     float* cur = bufB;
     for (int i = 1; i < Tb; ++i) {
       const int t = t_first + i * step;
-      for (int s = threadIdx.x; s < S; s += blockDim.x)
-        cur[s] = lse3_2(prev[s], prev[s + nb], skip_ok(s) ? prev[s + 2 * nb] : NEG_INF) + lp_b[(int64_t)t * Smax + s];
+      for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const float pre = lse3_2(prev[s], prev[s + nb], skip_ok(s) ? prev[s + 2 * nb] : NEG_INF);
+        cur[s] = pre + lp_b[(int64_t)t * Smax + s];
+        if (dir == 1) out_b[(int64_t)t * Smax + s] = pre;       // beta leaves without its frame's emission
+      }
       if ((i % CTC_RENORM) == 0) {
         float m = NEG_INF;
         for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, cur[s]);
@@ -266,7 +282,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
           csum += (double)m;
         }
       }
-      for (int s = threadIdx.x; s < S; s += blockDim.x) out_b[(int64_t)t * Smax + s] = cur[s];
+      if (dir == 0) for (int s = threadIdx.x; s < S; s += blockDim.x) out_b[(int64_t)t * Smax + s] = cur[s];
       __syncthreads();
       float* tmp = prev; prev = cur; cur = tmp;
     }
@@ -296,7 +312,11 @@ __global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* 
 }
 
 // ---- pass 3 ------------------------------------------------------------------------
-template <typename TI, typename TO>
+// Lattice nodes are taken as (blank 2u, label 2u+1) pairs, pair u on lane u%32 (one float2 load
+// from alpha and one from beta per pair).  NP > 0: lattices up to 64*NP nodes, each lane keeps
+// its NP pairs' log-occupancies in registers between the max, the normalising sum and the
+// scatter.  NP == 0: any width, recomputed from (L1-hot) reloads in each sweep.
+template <typename TI, typename TO, int NP>
 __global__ void __launch_bounds__(CTC_WARPS * 32)
 ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_t,
                 const int64_t* __restrict__ targets, int64_t ldt,
@@ -306,11 +326,11 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
                 const float* __restrict__ beta, const float* __restrict__ nll,
                 const float* __restrict__ grad_out, int reduction,
                 TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
-  extern __shared__ __align__(128) float sm[];       // per warp: V floats (row) + Spad floats (lattice)
+  extern __shared__ __align__(128) float sm[];       // per warp: V floats (softmax row, then the gradient row)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // warps per block shrink for large V
-  if (row >= (int64_t)B * Tn) return;
-  const int b = (int)(row / Tn), t = (int)(row % Tn);
+  const unsigned row = blockIdx.x * (blockDim.x >> 5) + warp;   // warps per block shrink for large V
+  if (row >= (unsigned)B * (unsigned)Tn) return;
+  const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
   int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
   TO* dx = dlogits + b * dstride_b + t * dstride_t;
   const float n = nll[b];
@@ -324,9 +344,7 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
     }
     return;
   }
-  const int Spad = (Smax + 3) & ~3;
-  float* r = sm + (int64_t)warp * (V + Spad);
-  float* vb = r + V;
+  float* r = sm + (int64_t)warp * V;
   const TI* x = logits + b * stride_b + t * stride_t;
   const float l2 = lse[row] * LOG2E;
   // softmax row -> shared memory
@@ -344,37 +362,62 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
     for (int i = lane; i < V; i += 32) r[i] = ex2f(fmaf(ld_f(x + i), LOG2E, -l2));
   }
   const int U = (int)tgt_lens[b];
-  const int S = 2 * U + 1;
   const int64_t* tg = targets + (int64_t)b * ldt;
-  const float* al = alpha + row * Smax;
-  const float* be = beta + row * Smax;
-  // occupancy_s = 2^(alpha+beta-lp)_s / sum_s' 2^(alpha+beta-lp)_s'  (log2 units; the sum is
-  // 2^(-nll*log2e) for every frame, normalising per frame keeps it exact under re-centring)
-  float vmax = NEG_INF;
-  for (int s = lane; s < S; s += 32) {
-    const float lp2 = fmaf(ld_f(x + ext_label(tg, s, blank)), LOG2E, -l2);
-    const float v = al[s] + be[s] - lp2;
-    vb[s] = v;
-    vmax = fmaxf(vmax, v);
-  }
-  vmax = warp_max(vmax);
-  float zsum = 0.f;
-  for (int s = lane; s < S; s += 32) {
-    const float pv = ex2f(vb[s] - vmax);            // own slots only: no sync needed
-    vb[s] = pv;
-    zsum += pv;
-  }
-  zsum = warp_sum(zsum);
-  const float inv = (zsum > 0.f) ? 1.f / zsum : 0.f;
-  __syncwarp();
-  // Every other lattice node is the blank: its ~U+1 contributions are summed in registers and
-  // added once (as shared-memory atomics — CAS loops for fp32 — they all hit one address and
-  // were ~1/3 of the kernel's instructions); label nodes scatter with atomics (labels may repeat).
-  float bsum = 0.f;
-  for (int s = lane; s < S; s += 32) {
-    const float occ = vb[s] * inv;
-    if (s & 1) atomicAdd(r + tg[s >> 1], -occ);
-    else bsum += occ;
+  // pair u <= U exists; its label node only for u < U.  occupancy_s = 2^(alpha+beta)_s / sum_s'
+  // (beta carries no emission; per-frame offsets from re-centring cancel in the normalisation)
+  const float2* al2 = reinterpret_cast<const float2*>(alpha + (int64_t)row * Smax);
+  const float2* be2 = reinterpret_cast<const float2*>(beta + (int64_t)row * Smax);
+  float z = 0.f, bsum = 0.f, vmax = CTC_DEAD;
+  if (NP > 0) {
+    float wb[NP > 0 ? NP : 1], wl[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int kk = 0; kk < NP; ++kk) {
+      const int u = lane + 32 * kk;
+      wb[kk] = CTC_DEAD; wl[kk] = CTC_DEAD;
+      if (u <= U) {
+        const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
+        wb[kk] = a.x + c.x;
+        if (u < U) wl[kk] = a.y + c.y;
+      }
+      vmax = fmaxf(vmax, fmaxf(wb[kk], wl[kk]));
+    }
+    vmax = warp_max(vmax);
+#pragma unroll
+    for (int kk = 0; kk < NP; ++kk) {
+      wb[kk] = ex2f(wb[kk] - vmax);
+      wl[kk] = ex2f(wl[kk] - vmax);
+      z += wb[kk] + wl[kk];
+    }
+    z = warp_sum(z);
+    const float inv = (vmax > CTC_DEAD_TEST && z > 0.f) ? 1.f / z : 0.f;
+    __syncwarp();                                     // softmax row complete before the scatter
+    // Every other lattice node is the blank: its contributions are summed in registers and
+    // added once; label nodes scatter with shared-memory atomics (labels may repeat).
+#pragma unroll
+    for (int kk = 0; kk < NP; ++kk) {
+      const int u = lane + 32 * kk;
+      bsum += wb[kk] * inv;
+      if (u < U) atomicAdd(r + tg[u], -wl[kk] * inv);
+    }
+  } else {
+    for (int u = lane; u <= U; u += 32) {
+      const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
+      vmax = fmaxf(vmax, a.x + c.x);
+      if (u < U) vmax = fmaxf(vmax, a.y + c.y);
+    }
+    vmax = warp_max(vmax);
+    for (int u = lane; u <= U; u += 32) {
+      const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
+      z += ex2f(a.x + c.x - vmax) + (u < U ? ex2f(a.y + c.y - vmax) : 0.f);
+    }
+    z = warp_sum(z);
+    const float inv = (vmax > CTC_DEAD_TEST && z > 0.f) ? 1.f / z : 0.f;
+    __syncwarp();
+    for (int u = lane; u <= U; u += 32) {
+      const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
+      bsum += ex2f(a.x + c.x - vmax) * inv;
+      if (u < U) atomicAdd(r + tg[u], -ex2f(a.y + c.y - vmax) * inv);
+    }
   }
   bsum = warp_sum(bsum);
   __syncwarp();
@@ -441,28 +484,36 @@ extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t
   SC_LAUNCH_RET();
 }
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, int NP>
 static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_t,
                            const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                            const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int Smax,
                            int64_t blank, const float* lse, const float* alpha, const float* beta,
                            const float* nll, const float* grad_out, int reduction, void* dlogits,
                            int64_t dstride_b, int64_t dstride_t, cudaStream_t st) {
-  // one shared-memory row of V + S floats per warp: fewer warps per block when the vocabulary is large
-  const size_t per_warp = (size_t)(V + ((Smax + 3) & ~3)) * sizeof(float);
+  // one shared-memory row of V floats per warp: fewer warps per block when the vocabulary is large
+  const size_t per_warp = (size_t)V * sizeof(float);
   int warps = CTC_WARPS;
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
   const size_t smem = per_warp * warps;
   if (smem > 200 * 1024) return SC_E_SHAPE;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ctc_grad_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ctc_grad_kernel<TI, TO, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   const unsigned blocks = (unsigned)cdiv(B * T, warps);
-  ctc_grad_kernel<TI, TO><<<blocks, warps * 32, smem, st>>>((const TI*)logits, stride_b, stride_t, targets, ldt,
+  ctc_grad_kernel<TI, TO, NP><<<blocks, warps * 32, smem, st>>>((const TI*)logits, stride_b, stride_t, targets, ldt,
       in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction,
       (TO*)dlogits, dstride_b, dstride_t);
   SC_LAUNCH_RET();
+}
+
+template <typename TI, typename TO, typename... A>
+static int ctc_grad_by_width(int Smax, A... a) {
+  if (Smax <= 128) return launch_ctc_grad<TI, TO, 2>(a...);
+  if (Smax <= 320) return launch_ctc_grad<TI, TO, 5>(a...);
+  if (Smax <= 640) return launch_ctc_grad<TI, TO, 10>(a...);
+  return launch_ctc_grad<TI, TO, 0>(a...);
 }
 
 extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
@@ -476,9 +527,10 @@ extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t
   if (T == 0) return 0;
   SC_CHECK_ARG(logits && in_lens && tgt_lens && lse && alpha && beta && nll && grad_out && dlogits, SC_E_BADARG);
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2, SC_E_BADARG);
+  SC_CHECK_ARG(B * T < ((int64_t)1 << 31), SC_E_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
-#define SC_CTC_GRAD(TI, TO) launch_ctc_grad<TI, TO>(logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, \
+#define SC_CTC_GRAD(TI, TO) ctc_grad_by_width<TI, TO>(Smax, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, \
     B, T, V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, st)
   if (dtype == SC_F32 && out_dtype == SC_F32) return SC_CTC_GRAD(float, float);
   if (dtype == SC_BF16 && out_dtype == SC_BF16) return SC_CTC_GRAD(bf16, bf16);

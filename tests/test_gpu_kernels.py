@@ -361,3 +361,50 @@ def test_ctc_large_vocab(cuda_device):
     loss.backward()
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
     np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("U,T", [(3, 40), (63, 150), (64, 200), (127, 300), (128, 330), (159, 400), (191, 470),
+                                 (192, 480), (255, 600), (256, 640), (320, 800)])
+def test_ctc_lattice_width_variants(cuda_device, U, T):
+    """1, 2, 3 and 4 warps per lattice (four nodes per thread), the boundaries between them, and
+    the thread-strided kernel beyond 512 nodes; small vocabulary so that repeated labels (no
+    skip transition) are common."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(U)
+    B, V = 3, 6
+    logits = torch.randn(B, T, V, generator=g) * 1.5
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl, tgl = [T, T - 7, T - 16], [U, max(U - 5, 0), max(U // 2, 1)]
+    xd = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(xd.log_softmax(-1).transpose(0, 1), tokens, inl, tgl, zero_infinity=True)
+    ref.backward()
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-7)
+
+
+def test_ctc_mismatched_transcript(cuda_device):
+    """A confident model (40-nat margins) whose frames follow a label sequence unrelated to the
+    transcript: forward and backward masses barely overlap (the case a scaled linear-domain
+    recursion cannot represent).  Loss and gradient must still match torch's fp64 CTC."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(21)
+    B, T, V, U = 4, 300, 40, 30
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    logits = torch.randn(B, T, V, generator=g)
+    for b in (1, 3):
+        wrong = torch.randint(1, V, (T,), generator=g)
+        logits[b] = -20.0
+        logits[b, torch.arange(T), wrong] = 20.0
+    inl, tgl = [T, T, T - 3, T - 40], [U, U, U - 4, U]
+    xd = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(xd.log_softmax(-1).transpose(0, 1), tokens, inl, tgl,
+                                       reduction="sum", zero_infinity=True)
+    ref.backward()
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, reduction="sum", zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-6)
