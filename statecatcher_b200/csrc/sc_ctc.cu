@@ -23,7 +23,9 @@
 // and further below either column's maximum, outside fp32's range (measured on random
 // logits, T=300, U=30); (b) log-domain with 2 or 4 nodes per thread in registers and shuffle
 // exchange — 0.77 ms against 0.53 ms for one node per thread: fewer warps leave the
-// MUFU/FMNMX latency chain of each step exposed.
+// MUFU/FMNMX latency chain of each step exposed; (c) two timesteps per block barrier with a
+// 3-2-1 trapezoid of recomputed neighbour nodes — no change (0.54 ms): the two dependent
+// log-sum-exps, not the barrier, are the chain.
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
