@@ -404,7 +404,13 @@ def main():
     roofs = {
         "scan_fwd": roof(["sc_lucy_scan_fwd"], "hbm"),
         "scan_bwd": roof(["sc_lucy_scan_bwd"], "hbm"),
-        "ctc": roof(["sc_ctc_fwd", "sc_ctc_bwd"], "hbm", ctc_bytes),
+        "ctc": roof(["sc_ctc_emissions", "sc_ctc_lattice", "sc_ctc_bwd"], "hbm", ctc_bytes),
+        # the three CTC passes on their own (bytes each pass must move, per frame: emissions read V*e and
+        # write the 4(2U+1)-byte lattice row; the recursions read it and write alpha and beta; the gradient
+        # pass reads logits, alpha, beta and writes dlogits)
+        "ctc_emissions": roof(["sc_ctc_emissions"], "hbm", (W["V"] * e + 4 * (2 * umean + 1)) * live_frames * args.steps),
+        "ctc_lattice": roof(["sc_ctc_lattice"], "hbm", 12 * (2 * umean + 1) * live_frames * args.steps),
+        "ctc_grad": roof(["sc_ctc_bwd"], "hbm", (2 * W["V"] * e + 8 * (2 * umean + 1)) * live_frames * args.steps),
         "gemm": roof(["sc_gemm_fwd", "sc_gemm_dgrad", "sc_gemm_wgrad"], "tensor"),
     }
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -414,7 +420,10 @@ def main():
             if v and k in tr:
                 v["traffic"] = tr[k]
     roofs = {k: v for k, v in roofs.items() if v}
-    dominant = max(roofs, key=lambda k: roofs[k]["ms_per_step"]) if roofs else None
+    if "ctc_lattice" in roofs:
+        roofs["ctc_lattice"]["note"] = ("alpha/beta recursions: T serial log-sum-exp steps per utterance, "
+                                        "latency-bound by construction (SURVEY.md 8d); GB/s shown for completeness")
+    dominant = max((k for k in roofs if not k.startswith("ctc_")), key=lambda k: roofs[k]["ms_per_step"]) if roofs else None
     roofline = dict(roofs[dominant], kernel=dominant) if dominant else None
 
     cpu = None

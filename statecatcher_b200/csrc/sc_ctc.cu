@@ -449,28 +449,39 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
 
 using namespace sc;
 
-extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
-                          const int64_t* targets, int64_t ldt, const int64_t* in_lens,
-                          const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
-                          int64_t blank, float* lse, float* lplat, float* alpha, float* beta,
-                          float* nll, float* loss, int reduction, void* stream) {
+extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                                const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+                                int64_t blank, float* lse, float* lplat, void* stream) {
   SC_CHECK_ARG(B > 0 && T >= 0 && V > 0 && Umax >= 0 && blank >= 0 && blank < V, SC_E_BADARG);
-  SC_CHECK_ARG(in_lens && tgt_lens && nll && (Umax == 0 || targets), SC_E_BADARG);
-  SC_CHECK_ARG(reduction >= 0 && reduction <= 2 && (reduction == 0 || loss), SC_E_BADARG);
-  SC_CHECK_ARG(T == 0 || (logits && lse && lplat && alpha && beta), SC_E_BADARG);
+  SC_CHECK_ARG(in_lens && tgt_lens && (Umax == 0 || targets), SC_E_BADARG);
+  SC_CHECK_ARG(T == 0 || (logits && lse && lplat), SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && V < (1 << 30) && Umax < (1 << 20), SC_E_SHAPE);
+  SC_CHECK_ARG(dtype == SC_F32 || dtype == SC_BF16, SC_E_DTYPE);
+  if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);      // row width of lplat/alpha/beta (16-B rows)
-  if (T > 0) {
-    const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
-    if (dtype == SC_F32)
-      ctc_lse_gather_kernel<float><<<blocks, CTC_WARPS * 32, 0, st>>>((const float*)logits, stride_b, stride_t,
-          targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat);
-    else if (dtype == SC_BF16)
-      ctc_lse_gather_kernel<bf16><<<blocks, CTC_WARPS * 32, 0, st>>>((const bf16*)logits, stride_b, stride_t,
-          targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat);
-    else return SC_E_DTYPE;
-  }
+  const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
+  if (dtype == SC_F32)
+    ctc_lse_gather_kernel<float><<<blocks, CTC_WARPS * 32, 0, st>>>((const float*)logits, stride_b, stride_t,
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat);
+  else
+    ctc_lse_gather_kernel<bf16><<<blocks, CTC_WARPS * 32, 0, st>>>((const bf16*)logits, stride_b, stride_t,
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat);
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_ctc_lattice(const float* lplat, const int64_t* targets, int64_t ldt,
+                              const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T,
+                              int64_t Umax, int64_t blank, float* alpha, float* beta, float* nll,
+                              float* loss, int reduction, void* stream) {
+  SC_CHECK_ARG(B > 0 && T >= 0 && Umax >= 0 && blank >= 0, SC_E_BADARG);
+  SC_CHECK_ARG(in_lens && tgt_lens && nll && (Umax == 0 || targets), SC_E_BADARG);
+  SC_CHECK_ARG(reduction >= 0 && reduction <= 2 && (reduction == 0 || loss), SC_E_BADARG);
+  SC_CHECK_ARG(T == 0 || (lplat && alpha && beta), SC_E_BADARG);
+  SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && Umax < (1 << 20), SC_E_SHAPE);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
   int threads = ((Smax + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   // two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
@@ -484,6 +495,19 @@ extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t
       (int)T, Smax, blank, alpha, beta, nll);
   if (reduction != 0) ctc_reduce_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, (int)B, reduction, loss);
   SC_LAUNCH_RET();
+}
+
+extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                          const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                          const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+                          int64_t blank, float* lse, float* lplat, float* alpha, float* beta,
+                          float* nll, float* loss, int reduction, void* stream) {
+  SC_CHECK_ARG(blank >= 0 && blank < V, SC_E_BADARG);
+  const int rc = sc_ctc_emissions(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax,
+                                  blank, lse, lplat, stream);
+  if (rc) return rc;
+  return sc_ctc_lattice(lplat, targets, ldt, in_lens, tgt_lens, B, T, Umax, blank, alpha, beta, nll, loss, reduction,
+                        stream);
 }
 
 template <typename TI, typename TO, int NP>

@@ -55,9 +55,10 @@ class _CTCFn(torch.autograd.Function):
         nll = torch.empty(B, **f32)
         loss = torch.zeros((), **f32)
         ldt = targets.stride(0) if targets.numel() else max(Umax, 1)
-        call("sc_ctc_fwd", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
-             ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), ptr(alpha),
-             ptr(beta), ptr(nll), ptr(loss), red, stream())
+        call("sc_ctc_emissions", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
+             ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), stream())
+        call("sc_ctc_lattice", ptr(lplat), ptr(targets), ldt, ptr(in_lens), ptr(tgt_lens), B, T, Umax, blank,
+             ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, stream())
         ctx.save_for_backward(x, targets, in_lens, tgt_lens, lse, alpha, beta, nll)
         ctx.cfg = (blank, red, Umax, ldt)
         if red != 0:

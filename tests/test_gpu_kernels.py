@@ -408,3 +408,32 @@ def test_ctc_mismatched_transcript(cuda_device):
     loss.backward()
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
     np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-6)
+
+
+def test_ctc_combined_entry_matches_split(cuda_device):
+    """sc_ctc_fwd (one call) == sc_ctc_emissions + sc_ctc_lattice (what ctc.py binds), bit for bit."""
+    from statecatcher_b200._lib import call, dt, ptr, stream
+    g = torch.Generator().manual_seed(31)
+    B, T, V, U = 3, 50, 17, 6
+    x = torch.randn(B, T, V, generator=g).cuda()
+    tok = torch.randint(1, V, (B, U), generator=g).cuda()
+    il = torch.tensor([T, T - 5, 30], device="cuda")
+    tl = torch.tensor([U, 4, 0], device="cuda")
+    S = (2 * U + 1 + 3) & ~3
+    outs = []
+    for split in (False, True):
+        f32 = dict(dtype=torch.float32, device="cuda")
+        lse, lplat = torch.zeros(B, T, **f32), torch.zeros(B, T, S, **f32)
+        alpha, beta = torch.zeros(B, T, S, **f32), torch.zeros(B, T, S, **f32)
+        nll, loss = torch.zeros(B, **f32), torch.zeros((), **f32)
+        if split:
+            call("sc_ctc_emissions", ptr(x), x.stride(0), x.stride(1), dt(x), ptr(tok), tok.stride(0), ptr(il), ptr(tl),
+                 B, T, V, U, 0, ptr(lse), ptr(lplat), stream())
+            call("sc_ctc_lattice", ptr(lplat), ptr(tok), tok.stride(0), ptr(il), ptr(tl), B, T, U, 0,
+                 ptr(alpha), ptr(beta), ptr(nll), ptr(loss), 1, stream())
+        else:
+            call("sc_ctc_fwd", ptr(x), x.stride(0), x.stride(1), dt(x), ptr(tok), tok.stride(0), ptr(il), ptr(tl),
+                 B, T, V, U, 0, ptr(lse), ptr(lplat), ptr(alpha), ptr(beta), ptr(nll), ptr(loss), 1, stream())
+        outs.append((lse, lplat, alpha, beta, nll, loss))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
