@@ -244,6 +244,7 @@ def test_module_vs_fp64_oracle_at_width_256(cuda_device, dtype):
 def test_segment_prefetcher_orders_copies():
     """Batches come out in order, bit-identical, while a long kernel queue is still reading the
     previous buffers (double-buffer reuse guarded by events)."""
+    import statecatcher_b200 as sb
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(5)
     host = [(torch.randn(64, 257, 80, generator=g).pin_memory(),
