@@ -28,15 +28,13 @@ constexpr int TM = 128;          // tile rows   (UMMA M)
 constexpr int TN = 256;          // tile cols   (UMMA N)
 constexpr int TK = 64;           // reduction elements per stage = one 128-byte swizzle row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
-constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * TK * 2;              // 16 KB
-constexpr int B_BYTES = TN * TK * 2;              // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int RING_BYTES = 192 * 1024;            // operand ring: 4 stages of 48 KB, or 6 of 32 KB in pair mode
 constexpr int ATOM_BYTES = TK * 128;              // one [TK x 64-element] MN-major box = 8 KB
 constexpr int EPI_WARPS = 8;                     // two warps per TMEM lane quarter, 128 columns each
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 2;      // per epilogue warp: one [32 rows x 32 cols] bf16 box for the TMA store
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * TN * 4 /*bias*/ +
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * TN * 4 /*bias*/ +
                            EPI_WARPS * EPI_STAGE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -64,13 +62,21 @@ struct GemmParams {
 };
 
 // EPI: 0 = bf16 store (+bias), 1 = fp32 store (+bias), 2 = fp32 atomic accumulate (split-R)
-template <bool A_MN, bool B_MN, int EPI>
+// PAIR: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256 across the two
+// SMs, N = 256): each CTA stages its own 128 rows of A and only HALF of the B tile — the tensor
+// cores read the other half from the peer's shared memory — so a stage is 32 KB instead of 48 KB
+// (shared-memory write and operand-read traffic per flop drop by a third, six stages fit).
+// !PAIR: each CTA issues its own M = 128 MMA on a full copy of the B tile (TMA multicast).
+template <bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const GemmParams p) {
+  constexpr int B_BYTES = (PAIR ? TN / 2 : TN) * TK * 2;            // 16 KB / 32 KB
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = RING_BYTES / STAGE_BYTES;                   // 6 / 4
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024-B aligned tiles
-  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  const uint32_t bar0 = base + RING_BYTES;
   // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then tmem ptr
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -78,19 +84,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + RING_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    // empty: released by the MMA commits of BOTH CTAs of the pair (each multicasts half of B into the other)
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 2); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), EPI_WARPS); }
+    // !PAIR: empty is released by the MMA commits of BOTH CTAs (each multicasts half of B into the other).
+    // PAIR: the leader's single commit is multicast to both CTAs; the leader's tempty collects the
+    // epilogue warps of both CTAs (the peer's full/tempty barriers are never waited on).
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), PAIR ? 1 : 2); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                   // peer's barriers are initialised before any multicast
@@ -120,6 +128,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          if (PAIR) {
+            // both CTAs' loads are counted on the leader's barrier; only the leader expects them
+            if (rank == 0) mbar_expect_tx(full(stage), 2 * STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d_pair(sa, &mapA, full(stage), kb * TK, ti * TM);
+            } else {
+#pragma unroll
+              for (int a = 0; a < TM / 64; ++a) tma_load_2d_pair(sa + a * ATOM_BYTES, &mapA, full(stage), ti * TM + a * 64, kb * TK);
+            }
+            // this CTA's half of the B tile (columns rank*128 .. +128 of the 256-wide tile)
+            if (!B_MN) {
+              tma_load_2d_pair(sb, &mapB, full(stage), kb * TK, tj * TN + (int)rank * (TN / 2));
+            } else {
+#pragma unroll
+              for (int b = 0; b < TN / 128; ++b)
+                tma_load_2d_pair(sb + b * ATOM_BYTES, &mapB, full(stage), tj * TN + ((int)rank * (TN / 128) + b) * 64, kb * TK);
+            }
+          } else {
           mbar_expect_tx(full(stage), STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(sa, &mapA, full(stage), kb * TK, ti * TM);
@@ -137,17 +163,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               tma_load_2d_mc(sb + bb * ATOM_BYTES, &mapB, full(stage), tj * TN + bb * 64, kb * TK, 0x3);
             }
           }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && (!PAIR || rank == 0)) {
       // instruction descriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
       // a_major bit15, b_major bit16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+                             ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TM : TM) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int64_t w = w0; w < total; w += wstep) {
@@ -167,12 +194,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                      : make_desc(sa + k * UK * 2, 0, 1024);
             const uint64_t bd = B_MN ? make_desc(sb + k * UK * 128, ATOM_BYTES, 1024)
                                      : make_desc(sb + k * UK * 2, 0, 1024);
-            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_mc(empty(stage), 0x3);            // stage reusable (here AND in the peer) once these MMAs retire
+          // stage reusable (here AND in the peer) once these MMAs retire
+          if (PAIR) umma_commit_pair_mc(empty(stage), 0x3); else umma_commit_mc(empty(stage), 0x3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull(acc));                        // accumulator complete -> epilogue
+        if (PAIR) umma_commit_pair_mc(tfull(acc), 0x3); else umma_commit(tfull(acc));   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -181,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                   // which 128-column half of the tile
     const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
-    float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
+    float* sbias = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t w = w0; w < total; w += wstep) {
       const int64_t tile = w % ((int64_t)pairs_i * p.tiles_j);
@@ -208,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           // to the TMA engine — full 64-byte row segments instead of 32 scattered 16-byte stores
           // per instruction (measured 1.9 TB/s -> the store path was the fwd GEMM's bottleneck);
           // the tensor map clips rows >= I and columns >= J.
-          const uint32_t stg = base + STAGES * STAGE_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+          const uint32_t stg = base + RING_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
           if (p.bias != nullptr) {
             const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
 #pragma unroll
@@ -242,7 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else if (EPI == 2) {
           // split-R partial tile: fp32 TMA reduce-add of [32 rows x 16 cols] boxes (64-byte row
           // segments reduced in L2) instead of 32 scattered 4-byte atomics per lane per chunk
-          const uint32_t stg = base + STAGES * STAGE_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+          const uint32_t stg = base + RING_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (lane == 0) bulk_wait_read0();
@@ -287,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(acc));
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty(acc)); else mbar_arrive(tempty(acc)); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (EPI != 1 && lane == 0) bulk_wait0();          // all TMA stores / reductions of this warp have completed
@@ -297,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   cluster_sync_all();                                   // no CTA leaves while the peer can still signal it
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -372,16 +401,24 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   p.kb_per_split = (int)cdiv(p.kb_total, splits);
   p.splits = (int)cdiv(p.kb_total, p.kb_per_split);
   p.D = D; p.ldd = ldd; p.bias = bias;
+  // CTA-pair MMA by default.  Timed alone at 192000 x 5120 x 1024: fwd 1.445 -> 1.367 ms, dgrad
+  // 1.398 -> 1.328 ms, wgrad 1.392 -> 1.452 ms; inside the power-capped training step all three
+  // gain (GEMM total 26.7 -> 25.3 ms per step: a third less shared-memory traffic per flop is
+  // also less energy per flop).  SC_GEMM_PAIR=0 selects the multicast variant (A/B measurements).
+  static const bool pair = [] { const char* e = getenv("SC_GEMM_PAIR"); return !(e && e[0] == '0'); }();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t total = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.splits;   // work items per CTA pair
   const int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;
   const int grid = (int)(2 * clusters);
-  gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, mapD, p);
+  if (pair) gemm_tc_kernel<A_MN, B_MN, EPI, true><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, mapD, p);
+  else gemm_tc_kernel<A_MN, B_MN, EPI, false><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, mapD, p);
   SC_LAUNCH_RET();
 }
 
