@@ -9,14 +9,18 @@
 // "MN-major" operands are consumed straight from their row-major activation layout through
 // the UMMA descriptor's major bit — no transposed copies of activations are ever made.
 //
-// Structure per CTA (one persistent CTA per SM, 320 threads):
-//   warp 0   : TMA producer — cp.async.bulk.tensor 128B-swizzled tiles into a 4-stage ring
-//   warp 1   : MMA issuer   — one thread issues tcgen05.mma (M=128, N=256, K=16, bf16->fp32)
-//              into one of two 256-column TMEM accumulator stages; tcgen05.commit releases
-//              smem stages / publishes the accumulator through mbarriers
+// Structure (one persistent CTA per SM, 320 threads, clusters of two CTAs = one MMA pair):
+//   warp 0   : TMA producer — cp.async.bulk.tensor 128B-swizzled tiles into the operand ring
+//              (pair mode: 6 stages of [A 128x64 | half of B 128x64]; both CTAs' bytes are counted
+//              on the leader's mbarrier)
+//   warp 1   : MMA issuer   — one thread of the LEADER CTA issues tcgen05.mma.cta_group::2
+//              (M=256 over the two SMs, N=256, K=16, bf16->fp32) into one of two 256-column TMEM
+//              accumulator stages; tcgen05.commit (multicast to both CTAs) releases smem stages /
+//              publishes the accumulator through mbarriers
 //   warps 2-9: epilogue     — tcgen05.ld (32 lanes x 32 columns per instruction), bias add
-//              from a shared-memory copy staged once per tile,
-//              bf16/fp32 conversion, 16-byte global stores (or fp32 red.add for split-R wgrad)
+//              from a shared-memory copy staged once per tile, bf16 boxes through shared memory
+//              to a TMA store (or fp32 TMA reduce-add for split-R wgrad); both CTAs' epilogue
+//              warps release the accumulator on the leader's barrier
 // The epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
