@@ -14,6 +14,9 @@ def t(f, n=10):
     for _ in range(n): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+x0 = torch.randn(M, 80, device='cuda').bfloat16(); w0 = (torch.randn(N, 80, device='cuda') / 9).bfloat16()
+ms = t(lambda: ops.gemm_fwd(x0, w0, b, out=y))
+print(f"fwd K=80 {ms:.3f} ms  output {M * N * 2 / ms / 1e9:.2f} TB/s")
 fl = 2.0 * M * N * K
 for name, f in (("fwd", lambda: ops.gemm_fwd(a, w, b, out=y)), ("dgrad", lambda: ops.gemm_dgrad(dy, w, out=da)),
                 ("wgrad", lambda: ops.gemm_wgrad(dy, a, out=dw))):

@@ -33,7 +33,7 @@ constexpr int TN = 256;          // tile cols   (UMMA N)
 constexpr int TK = 64;           // reduction elements per stage = one 128-byte swizzle row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int A_BYTES = TM * TK * 2;              // 16 KB
-constexpr int RING_BYTES = 192 * 1024;            // operand ring: 4 stages of 48 KB, or 6 of 32 KB in pair mode
+constexpr int RING_BYTES = 192 * 1024;            // operand ring region: 4 stages of 48 KB; pair mode: 5 of 32 KB + 2nd set of store boxes
 constexpr int ATOM_BYTES = TK * 128;              // one [TK x 64-element] MN-major box = 8 KB
 constexpr int EPI_WARPS = 8;                     // two warps per TMEM lane quarter, 128 columns each
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
@@ -77,7 +77,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapD, const GemmParams p) {
   constexpr int B_BYTES = (PAIR ? TN / 2 : TN) * TK * 2;            // 16 KB / 32 KB
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = RING_BYTES / STAGE_BYTES;                   // 6 / 4
+  constexpr int STAGES = PAIR ? 5 : 4;
+  constexpr int EPI_BUFS = PAIR ? 2 : 1;                             // store boxes per epilogue warp (2nd set: tail of the ring region)
+  static_assert(STAGES * STAGE_BYTES + (EPI_BUFS - 1) * EPI_WARPS * EPI_STAGE_BYTES <= RING_BYTES, "ring region");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024-B aligned tiles
   const uint32_t bar0 = base + RING_BYTES;
@@ -216,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
     float* sbias = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256);
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t ebox = 0;                                  // store boxes issued by this warp (selects the staging buffer)
     for (int64_t w = w0; w < total; w += wstep) {
       const int64_t tile = w % ((int64_t)pairs_i * p.tiles_j);
       const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
@@ -241,7 +244,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           // to the TMA engine — full 64-byte row segments instead of 32 scattered 16-byte stores
           // per instruction (measured 1.9 TB/s -> the store path was the fwd GEMM's bottleneck);
           // the tensor map clips rows >= I and columns >= J.
-          const uint32_t stg = base + RING_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+          const uint32_t stg = (EPI_BUFS == 2 && (ebox & 1))
+                                   ? base + STAGES * STAGE_BYTES + (uint32_t)(warp - 2) * EPI_STAGE_BYTES
+                                   : base + RING_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+          ++ebox;
           if (p.bias != nullptr) {
             const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
 #pragma unroll
@@ -253,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               r[v * 4 + 3] = __float_as_uint(__uint_as_float(r[v * 4 + 3]) + b4.w);
             }
           }
-          if (lane == 0) bulk_wait_read0();              // previous box has left shared memory
+          if (lane == 0) { if (EPI_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0(); }   // the box written 1 (2) stores ago has left shared memory
           __syncwarp();
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
