@@ -241,7 +241,7 @@ int sc_rnnt_node_grads(const int64_t* frame_lens, const int64_t* label_lens, int
 int sc_rnnt_dlogits(const void* logits, int dtype, const float* lse, const float* gb, const float* gl,
                     const int64_t* labels, int64_t ldl, const int64_t* label_lens, int64_t B, int64_t T,
                     int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, void* dlogits,
-                    void* stream);
+                    float* dbias /* nullable: [V] fp32, += column sums of dlogits */, void* stream);
 
 /* ---------------------------------------------------------------- greedy CTC decode ---
  * Replaces decoder.py:3-30 (argmax + Python collapse loop with one .item() sync per token).

@@ -53,7 +53,7 @@ SIGNATURES = {
     "sc_rnnt_lse_gather": [P, I32, P, I64, P, P, I64, I64, I64, I64, I64, I64, I64, P, P, P, P],
     "sc_rnnt_lattice": [P, P, I64, I64, I64, P, P, P, P, P, P],
     "sc_rnnt_node_grads": [P, P, I64, I64, I64, P, P, P, P, P, P, P, P, P],
-    "sc_rnnt_dlogits": [P, I32, P, P, P, P, I64, P, I64, I64, I64, I64, I64, I64, I64, P, P],
+    "sc_rnnt_dlogits": [P, I32, P, P, P, P, I64, P, I64, I64, I64, I64, I64, I64, I64, P, P, P],
     "sc_ctc_greedy_decode": [P, I64, I64, I32, P, I64, I64, I64, I64, P, P, P, P],
     "sc_sumsq_accum": [P, I64, P, P],
     "sc_scale_grads": [P, I64, P, F32, P],

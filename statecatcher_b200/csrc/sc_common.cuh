@@ -137,6 +137,76 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// log(sum_i exp(x_i)) of one row, computed by one warp (every lane gets the result).
+// Rows whose 16-byte vectors fit four per lane (V <= 1024 bf16 / 512 fp32) are pulled into
+// registers with all loads in flight at once, then max and exp-sum are two passes over
+// registers — ~5 instructions per element instead of the online form's per-chunk rescaling.
+template <typename T>
+__device__ __forceinline__ float warp_row_lse(const T* __restrict__ x, int V, int lane) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  const float NEGINF = -INFINITY;
+  float m = NEGINF, ssum = 0.f;
+  const bool vec_ok = (V % VW == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec_ok && V <= 4 * 32 * VW) {
+    Vec<T, VW> raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = (k * 32 + lane) * VW;
+      if (i < V) raw[k].raw = __ldg(reinterpret_cast<const uint4*>(x + i));
+    }
+    float f[4][VW];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((k * 32 + lane) * VW < V) {
+        unpack(raw[k], f[k]);
+#pragma unroll
+        for (int j = 0; j < VW; ++j) m = fmaxf(m, f[k][j]);
+      }
+    }
+    m = warp_max(m);
+    const float mc = (m == NEGINF) ? 0.f : m;                 // all -inf row: exp(-inf - 0) = 0, lse = -inf
+    const float mc2 = mc * 1.4426950408889634f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((k * 32 + lane) * VW < V) {
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {                        // exp(f - m) as one FFMA + one MUFU (no range fix-ups: the argument is <= 0)
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(f[k][j], 1.4426950408889634f, -mc2)));
+          ssum += e;
+        }
+      }
+    }
+    return mc + __logf(warp_sum(ssum));
+  }
+  if (vec_ok) {
+    for (int i = lane * VW; i < V; i += 32 * VW) {
+      float f[VW];
+      Vec<T, VW> raw; raw.raw = __ldg(reinterpret_cast<const uint4*>(x + i));
+      unpack(raw, f);
+      float mm = f[0];
+#pragma unroll
+      for (int j = 1; j < VW; ++j) mm = fmaxf(mm, f[j]);
+      const float nm = fmaxf(m, mm);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < VW; ++j) acc += __expf(f[j] - nm);
+      ssum = ssum * __expf(m - nm) + acc;
+      m = nm;
+    }
+  } else {
+    for (int i = lane; i < V; i += 32) {
+      const float f = ld_f(x + i);
+      const float nm = fmaxf(m, f);
+      ssum = ssum * __expf(m - nm) + __expf(f - nm);
+      m = nm;
+    }
+  }
+  const float gm = warp_max(m);
+  ssum = (m == NEGINF) ? 0.f : ssum * __expf(m - gm);
+  return gm + __logf(warp_sum(ssum));
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace sc

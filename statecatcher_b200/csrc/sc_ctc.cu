@@ -62,49 +62,22 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
                       int B, int Tn, int V, int Smax, int64_t blank,
                       float* __restrict__ lse, float* __restrict__ lplat) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * CTC_WARPS + warp;
-  if (row >= (int64_t)B * Tn) return;
-  const int b = (int)(row / Tn), t = (int)(row % Tn);
-  int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
-  if (t >= Tb) return;
-  const T* x = logits + b * stride_b + t * stride_t;
-  // online max/sum, each lane over a strided slice
-  float m = NEG_INF, ssum = 0.f;
-  constexpr int VW = 16 / sizeof(T);
-  const bool vec_ok = (V % VW == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  if (vec_ok) {
-    for (int i = lane * VW; i < V; i += 32 * VW) {
-      float f[VW];
-      Vec<T, VW> raw; raw.raw = __ldg(reinterpret_cast<const uint4*>(x + i));
-      unpack(raw, f);
-      float mm = f[0];
-#pragma unroll
-      for (int j = 1; j < VW; ++j) mm = fmaxf(mm, f[j]);
-      const float nm = fmaxf(m, mm);
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < VW; ++j) acc += __expf(f[j] - nm);
-      ssum = ssum * __expf(m - nm) + acc;
-      m = nm;
-    }
-  } else {
-    for (int i = lane; i < V; i += 32) {
-      const float f = ld_f(x + i);
-      const float nm = fmaxf(m, f);
-      ssum = ssum * __expf(m - nm) + __expf(f - nm);
-      m = nm;
-    }
+  const unsigned nrows = (unsigned)B * (unsigned)Tn;           // B*T < 2^31 (checked by the host)
+  // (grid-stride loop; launched with one warp per row — capping the grid at a few blocks per SM
+  // measured slower: 0.148 -> 0.203 ms)
+  for (unsigned row = blockIdx.x * CTC_WARPS + warp; row < nrows; row += gridDim.x * CTC_WARPS) {
+    const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
+    int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
+    if (t >= Tb) continue;
+    const T* x = logits + b * stride_b + t * stride_t;
+    const float l = warp_row_lse<T>(x, V, lane);
+    if (lane == 0) lse[row] = l;
+    const int S = 2 * (int)tgt_lens[b] + 1;
+    const int64_t* tg = targets + (int64_t)b * ldt;
+    float* out = lplat + (int64_t)row * Smax;
+    // emissions in log2 units (the recursion runs on ex2/lg2 directly)
+    for (int s = lane; s < S; s += 32) out[s] = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
   }
-  const float gm = warp_max(m);
-  ssum = (m == NEG_INF) ? 0.f : ssum * __expf(m - gm);
-  const float gs = warp_sum(ssum);
-  const float l = gm + __logf(gs);
-  if (lane == 0) lse[row] = l;
-  const int S = 2 * (int)tgt_lens[b] + 1;
-  const int64_t* tg = targets + (int64_t)b * ldt;
-  float* out = lplat + row * Smax;
-  // emissions in log2 units (the recursion runs on ex2/lg2 directly)
-  for (int s = lane; s < S; s += 32) out[s] = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
 }
 
 // ---- pass 2 ------------------------------------------------------------------------
@@ -319,19 +292,16 @@ __global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* 
 // its NP pairs' log-occupancies in registers between the max, the normalising sum and the
 // scatter.  NP == 0: any width, recomputed from (L1-hot) reloads in each sweep.
 template <typename TI, typename TO, int NP>
-__global__ void __launch_bounds__(CTC_WARPS * 32)
-ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_t,
-                const int64_t* __restrict__ targets, int64_t ldt,
-                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                int B, int Tn, int V, int Smax, int64_t blank,
-                const float* __restrict__ lse, const float* __restrict__ alpha,
-                const float* __restrict__ beta, const float* __restrict__ nll,
-                const float* __restrict__ grad_out, int reduction,
-                TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
-  extern __shared__ __align__(128) float sm[];       // per warp: V floats (softmax row, then the gradient row)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned row = blockIdx.x * (blockDim.x >> 5) + warp;   // warps per block shrink for large V
-  if (row >= (unsigned)B * (unsigned)Tn) return;
+__device__ __forceinline__ void
+ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const int lane,
+             const TI* __restrict__ logits, int64_t stride_b, int64_t stride_t,
+             const int64_t* __restrict__ targets, int64_t ldt,
+             const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+             int B, int Tn, int V, int Smax, int64_t blank,
+             const float* __restrict__ lse, const float* __restrict__ alpha,
+             const float* __restrict__ beta, const float* __restrict__ nll,
+             const float* __restrict__ grad_out, int reduction,
+             TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
   const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
   int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
   TO* dx = dlogits + b * dstride_b + t * dstride_t;
@@ -442,6 +412,28 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
     }
   } else {
     for (int i = lane; i < V; i += 32) st_f(dx + i, scale * r[i]);
+  }
+}
+
+
+template <typename TI, typename TO, int NP>
+__global__ void __launch_bounds__(CTC_WARPS * 32)
+ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_t,
+                const int64_t* __restrict__ targets, int64_t ldt,
+                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                int B, int Tn, int V, int Smax, int64_t blank,
+                const float* __restrict__ lse, const float* __restrict__ alpha,
+                const float* __restrict__ beta, const float* __restrict__ nll,
+                const float* __restrict__ grad_out, int reduction,
+                TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
+  extern __shared__ __align__(128) float sm[];       // per warp: V floats (softmax row, then the gradient row)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned wpb = blockDim.x >> 5;               // warps per block shrink for large V
+  const unsigned nrows = (unsigned)B * (unsigned)Tn;
+  for (unsigned row = blockIdx.x * wpb + warp; row < nrows; row += gridDim.x * wpb) {   // launched with one warp per row (a capped, persistent grid measured slower)
+    ctc_grad_row<TI, TO, NP>(sm, row, warp, lane, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, B, Tn, V,
+                             Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t);
+    __syncwarp();                                     // the warp's shared-memory row is reused by its next frame
   }
 }
 

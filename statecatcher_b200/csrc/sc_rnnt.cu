@@ -223,44 +223,124 @@ __global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __re
 // the backward.
 
 // joint[b,t,u,:] = tanh(enc[b,t,:] + pred[b,u,:])      (model.py:139-140)
-// One thread per 16-byte vector of the output (8 bf16 / 4 fp32), fully coalesced; enc/pred
-// rows are tiny and stay in L1/L2.  VECOK=false is the scalar path for odd J / alignment.
-template <typename T, bool VECOK>
+// bf16 uses tanh.approx (rel. error 2^-11, below bf16's own rounding), fp32 the precise form.
+template <typename T> struct JointTanh { static __device__ __forceinline__ float f(float x) { return tanhf_<true>(x); } };
+template <> struct JointTanh<bf16> { static __device__ __forceinline__ float f(float x) { return tanhf_<false>(x); } };
+
+// Vector kernel: one block per (b,t); a thread owns one 16-byte vector of the J channels and
+// every (256/vectors-per-row)-th label row u, so enc[b,t,:] is loaded once per thread and the
+// block streams U1 contiguous output rows.  No per-element index arithmetic.
+template <typename T>
+__global__ void __launch_bounds__(256)
+joint_fwd_vec_kernel(const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
+                     const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
+                     T* __restrict__ out, int Tc, int U1, int J) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  const int vpr = J / VW, upb = blockDim.x / vpr;
+  const int jv = threadIdx.x % vpr, uq = threadIdx.x / vpr;
+  if (uq >= upb) return;
+  const int b = blockIdx.x / Tc, t = blockIdx.x - b * Tc;
+  float fe[VW];
+  { Vec<T, VW> ve; ve.raw = __ldg(reinterpret_cast<const uint4*>(enc + b * enc_sb + t * enc_st + jv * VW)); unpack(ve, fe); }
+  const T* p = pred + b * pred_sb + jv * VW;
+  T* o = out + (int64_t)blockIdx.x * U1 * J + jv * VW;
+  for (int u = uq; u < U1; u += upb) {
+    float fp[VW];
+    Vec<T, VW> vp; vp.raw = __ldg(reinterpret_cast<const uint4*>(p + u * pred_su));
+    unpack(vp, fp);
+#pragma unroll
+    for (int k = 0; k < VW; ++k) fp[k] = JointTanh<T>::f(fe[k] + fp[k]);
+    const Vec<T, VW> vo = pack(fp, (T*)nullptr);
+    *reinterpret_cast<uint4*>(o + (int64_t)u * J) = vo.raw;
+  }
+}
+
+// Scalar fallback (odd J / unaligned): one thread per element.
+template <typename T>
 __global__ void __launch_bounds__(256)
 joint_fwd_kernel(const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
                  const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
                  T* __restrict__ out, int B, int Tc, int U1, int J) {
-  constexpr int VW = VECOK ? 16 / (int)sizeof(T) : 1;
-  const int vec_per_row = J / VW;
-  const int64_t total = (int64_t)B * Tc * U1 * vec_per_row;
+  const int64_t total = (int64_t)B * Tc * U1 * J;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int jv = (int)(i % vec_per_row);
-    const int64_t row = i / vec_per_row;
+    const int j = (int)(i % J);
+    const int64_t row = i / J;
     const int u = (int)(row % U1);
     const int t = (int)((row / U1) % Tc);
     const int b = (int)(row / ((int64_t)U1 * Tc));
-    const T* e = enc + b * enc_sb + t * enc_st + jv * VW;
-    const T* p = pred + b * pred_sb + u * pred_su + jv * VW;
-    T* o = out + row * J + jv * VW;
-    if constexpr (VECOK) {
-      float fe[VW], fp[VW];
-      Vec<T, VW> ve, vp;
-      ve.raw = __ldg(reinterpret_cast<const uint4*>(e));
-      vp.raw = __ldg(reinterpret_cast<const uint4*>(p));
-      unpack(ve, fe); unpack(vp, fp);
-#pragma unroll
-      for (int k = 0; k < VW; ++k) fe[k] = tanhf_<false>(fe[k] + fp[k]);
-      const Vec<T, VW> vo = pack(fe, (T*)nullptr);
-      *reinterpret_cast<uint4*>(o) = vo.raw;
-    } else {
-      st_f(o, tanhf_<true>(ld_f(e) + ld_f(p)));
-    }
+    st_f(out + i, JointTanh<T>::f(ld_f(enc + b * enc_sb + t * enc_st + j) + ld_f(pred + b * pred_sb + u * pred_su + j)));
   }
 }
 
 // d_pre = dJ * (1 - joint^2), joint recomputed from enc/pred.
 // REDUCE_U: d_enc[b,t,:] = sum_u d_pre        (one block per (b,t), written)
 // else    : d_pred[b,u,:] += sum_t d_pre      (one block per (b,u), fp32 accumulate across chunks)
+// Vector kernels: thread = (row group q, 16-byte channel vector jv); the block's row groups walk
+// the reduced index in parallel (16-byte loads of dJ, several rows in flight per thread) and
+// are combined through shared memory at the end.
+template <typename T, bool REDUCE_U>
+__global__ void __launch_bounds__(256)
+joint_bwd_vec_kernel(const T* __restrict__ dJ, const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
+                     const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
+                     T* __restrict__ d_enc, int64_t denc_sb, int64_t denc_st,
+                     float* __restrict__ d_pred, int Tc, int U1, int J) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  extern __shared__ __align__(16) float red[];           // [groups][J]
+  const int vpr = J / VW, groups = blockDim.x / vpr;
+  const int jv = threadIdx.x % vpr, q = threadIdx.x / vpr;
+  const int nfix = REDUCE_U ? Tc : U1;
+  const int b = blockIdx.x / nfix, fixed = blockIdx.x - b * nfix;   // t (REDUCE_U) or u
+  const int n = REDUCE_U ? U1 : Tc;
+  float acc[VW];
+#pragma unroll
+  for (int k = 0; k < VW; ++k) acc[k] = 0.f;
+  if (q < groups) {
+    float fb[VW];
+    {
+      const T* bp = REDUCE_U ? enc + b * enc_sb + fixed * enc_st : pred + b * pred_sb + fixed * pred_su;
+      Vec<T, VW> vb; vb.raw = __ldg(reinterpret_cast<const uint4*>(bp + jv * VW)); unpack(vb, fb);
+    }
+    for (int i = q; i < n; i += groups) {
+      const int t = REDUCE_U ? fixed : i, u = REDUCE_U ? i : fixed;
+      const T* op = REDUCE_U ? pred + b * pred_sb + u * pred_su : enc + b * enc_sb + t * enc_st;
+      float fo[VW], fg[VW];
+      Vec<T, VW> vo, vg;
+      vo.raw = __ldg(reinterpret_cast<const uint4*>(op + jv * VW));
+      vg.raw = __ldg(reinterpret_cast<const uint4*>(dJ + (((int64_t)b * Tc + t) * U1 + u) * J + jv * VW));
+      unpack(vo, fo); unpack(vg, fg);
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        const float jt = JointTanh<T>::f(fb[k] + fo[k]);
+        acc[k] = fmaf(fg[k], 1.f - jt * jt, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VW; ++k) red[q * J + jv * VW + k] = acc[k];
+  }
+  __syncthreads();
+  // first group's threads sum the groups' partials for their vector
+  if (q == 0) {
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      float sum = 0.f;
+      for (int g = 0; g < groups; ++g) sum += red[g * J + jv * VW + k];
+      acc[k] = sum;
+    }
+    if (REDUCE_U) {
+      const Vec<T, VW> vo = pack(acc, (T*)nullptr);
+      *reinterpret_cast<uint4*>(d_enc + b * denc_sb + fixed * denc_st + jv * VW) = vo.raw;
+    } else {
+      float* dp = d_pred + ((int64_t)b * U1 + fixed) * J + jv * VW;
+#pragma unroll
+      for (int k = 0; k < VW; k += 4) {
+        float4 c = *reinterpret_cast<float4*>(dp + k);
+        c.x += acc[k]; c.y += acc[k + 1]; c.z += acc[k + 2]; c.w += acc[k + 3];
+        *reinterpret_cast<float4*>(dp + k) = c;
+      }
+    }
+  }
+}
+
 template <typename T, bool REDUCE_U>
 __global__ void joint_bwd_kernel(const T* __restrict__ dJ, const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
                                  const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,
@@ -275,7 +355,7 @@ __global__ void joint_bwd_kernel(const T* __restrict__ dJ, const T* __restrict__
     for (int i = 0; i < n; ++i) {
       const int t = REDUCE_U ? fixed : i, u = REDUCE_U ? i : fixed;
       const float other = REDUCE_U ? ld_f(pred + b * pred_sb + u * pred_su + j) : ld_f(enc + b * enc_sb + t * enc_st + j);
-      const float jt = tanhf_<true>(base + other);
+      const float jt = JointTanh<T>::f(base + other);
       const float g = ld_f(dJ + (((int64_t)b * Tc + t) * U1 + u) * J + j);
       acc = fmaf(g, 1.f - jt * jt, acc);
     }
@@ -293,32 +373,26 @@ rnnt_lse_gather_kernel(const T* __restrict__ logits, const int64_t* __restrict__
                        int B, int Tn, int t0, int Tc, int U1, int V, int U1p, int64_t blank,
                        float* __restrict__ lse, float* __restrict__ eb, float* __restrict__ el) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
-  if (row >= (int64_t)B * Tc * U1) return;
-  const int u = (int)(row % U1);
-  const int tc = (int)((row / U1) % Tc);
-  const int b = (int)(row / ((int64_t)U1 * Tc));
-  const int t = t0 + tc;
-  int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
-  const int64_t Ub = label_lens[b];
-  if (t >= Tb || u > Ub) return;
-  const T* x = logits + row * V;
-  float m = NEG_INF, ssum = 0.f;
-  for (int i = lane; i < V; i += 32) {
-    const float f = ld_f(x + i);
-    const float nm = fmaxf(m, f);
-    ssum = ssum * __expf(m - nm) + __expf(f - nm);
-    m = nm;
-  }
-  const float gm = warp_max(m);
-  ssum = (m == NEG_INF) ? 0.f : ssum * __expf(m - gm);
-  const float l = gm + __logf(warp_sum(ssum));
-  if (lane == 0) {
-    const int64_t D = Tn + U1;
-    const int64_t o = ((int64_t)b * D + (t + u)) * U1p + u;
-    lse[((int64_t)b * Tn + t) * U1 + u] = l;
-    eb[o] = ld_f(x + blank) - l;
-    el[o] = (u < Ub) ? ld_f(x + labels[(int64_t)b * ldl + u]) - l : NEG_INF;
+  const unsigned nrows = (unsigned)B * (unsigned)Tc * (unsigned)U1;   // < 2^31 (checked by the host)
+  // (grid-stride loop, launched with one warp per row: a capped persistent grid measured slower)
+  for (unsigned row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
+    const unsigned bt = row / (unsigned)U1;
+    const int u = (int)(row - bt * (unsigned)U1);
+    const int b = (int)(bt / (unsigned)Tc);
+    const int tc = (int)(bt - (unsigned)b * (unsigned)Tc);
+    const int t = t0 + tc;
+    int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
+    const int64_t Ub = label_lens[b];
+    if (t >= Tb || u > Ub) continue;
+    const T* x = logits + (int64_t)row * V;
+    const float l = warp_row_lse<T>(x, V, lane);
+    if (lane == 0) {
+      const int64_t D = Tn + U1;
+      const int64_t o = ((int64_t)b * D + (t + u)) * U1p + u;
+      lse[((int64_t)b * Tn + t) * U1 + u] = l;
+      eb[o] = ld_f(x + blank) - l;
+      el[o] = (u < Ub) ? ld_f(x + labels[(int64_t)b * ldl + u]) - l : NEG_INF;
+    }
   }
 }
 
@@ -358,6 +432,98 @@ __global__ void rnnt_node_grad_kernel(const float* __restrict__ eb, const float*
 }
 
 // dlogits[v] = gb*([v==blank]-p_v) + gl*([v==label]-p_v),  p = softmax(logits) of the node
+// Vector kernel: persistent warps stride over the node rows; a lane owns the same NV 16-byte
+// column vectors of every row it visits, so the column sums of dlogits (the gradient of the
+// joiner's output bias) accumulate in registers and leave through one shared-memory and one
+// global atomic per column per block — no second pass over the V-wide tensor.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+rnnt_dlogits_vec_kernel(const T* __restrict__ logits, const float* __restrict__ lse, const float* __restrict__ gb,
+                        const float* __restrict__ gl, const int64_t* __restrict__ labels, int64_t ldl,
+                        const int64_t* __restrict__ label_lens, int B, int Tn, int t0, int Tc, int U1, int V,
+                        int64_t blank, T* __restrict__ dlogits, float* __restrict__ dbias) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  extern __shared__ __align__(16) float colacc[];        // [V]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) colacc[i] = 0.f;
+    __syncthreads();
+  }
+  float cs[NV][VW];
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < VW; ++j) cs[k][j] = 0.f;
+  const unsigned nrows = (unsigned)B * (unsigned)Tc * (unsigned)U1;
+  const unsigned wstep = gridDim.x * 8;
+  for (unsigned row = blockIdx.x * 8 + warp; row < nrows; row += wstep) {
+    const unsigned bt = row / (unsigned)U1;
+    const int u = (int)(row - bt * (unsigned)U1);
+    const int b = (int)(bt / (unsigned)Tc);
+    const int tc = (int)(bt - (unsigned)b * (unsigned)Tc);
+    const int64_t node = ((int64_t)b * Tn + t0 + tc) * U1 + u;
+    const float vb = gb[node], vl = gl[node];
+    T* d = dlogits + (int64_t)row * V;
+    if (vb == 0.f && vl == 0.f) {                        // dead node (or zero weight): exact zeros
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = (k * 32 + lane) * VW;
+        if (i < V) *reinterpret_cast<uint4*>(d + i) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const T* x = logits + (int64_t)row * V;
+    const float l2 = lse[node] * 1.4426950408889634f;
+    const float tot = vb + vl;
+    const int lab = (u < label_lens[b]) ? (int)labels[(int64_t)b * ldl + u] : -1;
+    Vec<T, VW> raw[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = (k * 32 + lane) * VW;
+      if (i < V) raw[k].raw = __ldg(reinterpret_cast<const uint4*>(x + i));
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = (k * 32 + lane) * VW;
+      if (i < V) {
+        float g[VW];
+        unpack(raw[k], g);
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {                    // softmax prob = 2^(x*log2e - lse*log2e): one FFMA + one MUFU
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(g[j], 1.4426950408889634f, -l2)));
+          g[j] = -tot * e;
+        }
+        const int ob = (int)blank - i, ol = lab - i;     // the two special columns, if this vector holds them
+        if ((unsigned)ob < (unsigned)VW || (unsigned)ol < (unsigned)VW) {
+#pragma unroll
+          for (int j = 0; j < VW; ++j) {
+            if (j == ob) g[j] += vb;
+            if (j == ol) g[j] += vl;
+          }
+        }
+        const Vec<T, VW> o = pack(g, (T*)nullptr);
+        *reinterpret_cast<uint4*>(d + i) = o.raw;
+#pragma unroll
+        for (int j = 0; j < VW; ++j) cs[k][j] += g[j];
+      }
+    }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = (k * 32 + lane) * VW;
+      if (i < V) {
+#pragma unroll
+        for (int j = 0; j < VW; ++j) atomicAdd(colacc + i + j, cs[k][j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < V; i += blockDim.x) atomicAdd(dbias + i, colacc[i]);
+  }
+}
+
+// Scalar fallback (any V / alignment); the bias gradient is then a separate column-sum pass.
 template <typename T>
 __global__ void __launch_bounds__(256)
 rnnt_dlogits_kernel(const T* __restrict__ logits, const float* __restrict__ lse, const float* __restrict__ gb,
@@ -455,11 +621,10 @@ extern "C" int sc_joint_fwd(const void* enc, int64_t enc_sb, int64_t enc_st, con
   cudaStream_t st = (cudaStream_t)stream;
   const bool al = (((uintptr_t)enc | (uintptr_t)pred | (uintptr_t)out) & 15) == 0;
 #define SC_JOINT(TT, VW_) do { \
-    const bool vec = al && (J % (VW_) == 0) && (enc_sb % (VW_) == 0) && (enc_st % (VW_) == 0) && (pred_sb % (VW_) == 0) && (pred_su % (VW_) == 0); \
-    const int64_t n = B * Tc * U1 * (vec ? J / (VW_) : J); \
-    const unsigned grid = (unsigned)min((int64_t)148 * 64, cdiv(n, 256)); \
-    if (vec) joint_fwd_kernel<TT, true><<<grid, 256, 0, st>>>((const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)out, (int)B, (int)Tc, (int)U1, (int)J); \
-    else joint_fwd_kernel<TT, false><<<grid, 256, 0, st>>>((const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)out, (int)B, (int)Tc, (int)U1, (int)J); } while (0)
+    const bool vec = al && (J % (VW_) == 0) && (J / (VW_) <= 256) && (enc_sb % (VW_) == 0) && (enc_st % (VW_) == 0) && \
+                     (pred_sb % (VW_) == 0) && (pred_su % (VW_) == 0); \
+    if (vec) joint_fwd_vec_kernel<TT><<<(unsigned)(B * Tc), 256, 0, st>>>((const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)out, (int)Tc, (int)U1, (int)J); \
+    else joint_fwd_kernel<TT><<<(unsigned)min((int64_t)148 * 64, cdiv(B * Tc * U1 * J, 256)), 256, 0, st>>>((const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)out, (int)B, (int)Tc, (int)U1, (int)J); } while (0)
   if (dtype == SC_BF16) SC_JOINT(bf16, 8);
   else if (dtype == SC_F32) SC_JOINT(float, 4);
   else return SC_E_DTYPE;
@@ -474,14 +639,24 @@ extern "C" int sc_joint_bwd(const void* dJ, const void* enc, int64_t enc_sb, int
   if (Tc == 0) return 0;
   SC_CHECK_ARG(dJ && enc && pred && d_enc && d_pred, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool al = (((uintptr_t)dJ | (uintptr_t)enc | (uintptr_t)pred | (uintptr_t)d_enc | (uintptr_t)d_pred) & 15) == 0;
   const int threads = J >= 256 ? 256 : 128;
-  if (dtype == SC_BF16) {
-    joint_bwd_kernel<bf16, true><<<(unsigned)(B * Tc), threads, 0, st>>>((const bf16*)dJ, (const bf16*)enc, enc_sb, enc_st, (const bf16*)pred, pred_sb, pred_su, (bf16*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
-    joint_bwd_kernel<bf16, false><<<(unsigned)(B * U1), threads, 0, st>>>((const bf16*)dJ, (const bf16*)enc, enc_sb, enc_st, (const bf16*)pred, pred_sb, pred_su, (bf16*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
-  } else if (dtype == SC_F32) {
-    joint_bwd_kernel<float, true><<<(unsigned)(B * Tc), threads, 0, st>>>((const float*)dJ, (const float*)enc, enc_sb, enc_st, (const float*)pred, pred_sb, pred_su, (float*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
-    joint_bwd_kernel<float, false><<<(unsigned)(B * U1), threads, 0, st>>>((const float*)dJ, (const float*)enc, enc_sb, enc_st, (const float*)pred, pred_sb, pred_su, (float*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J);
-  } else return SC_E_DTYPE;
+#define SC_JBWD(TT, VW_) do { \
+    const bool vec = al && (J % (VW_) == 0) && (J / (VW_) <= 256) && (enc_sb % (VW_) == 0) && (enc_st % (VW_) == 0) && \
+                     (pred_sb % (VW_) == 0) && (pred_su % (VW_) == 0) && (denc_sb % (VW_) == 0) && (denc_st % (VW_) == 0); \
+    if (vec) { \
+      const size_t smem = (size_t)(256 / (J / (VW_))) * J * sizeof(float); \
+      if (smem > 48 * 1024) return SC_E_SHAPE; \
+      joint_bwd_vec_kernel<TT, true><<<(unsigned)(B * Tc), 256, smem, st>>>((const TT*)dJ, (const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)d_enc, denc_sb, denc_st, d_pred, (int)Tc, (int)U1, (int)J); \
+      joint_bwd_vec_kernel<TT, false><<<(unsigned)(B * U1), 256, smem, st>>>((const TT*)dJ, (const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)d_enc, denc_sb, denc_st, d_pred, (int)Tc, (int)U1, (int)J); \
+    } else { \
+      joint_bwd_kernel<TT, true><<<(unsigned)(B * Tc), threads, 0, st>>>((const TT*)dJ, (const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J); \
+      joint_bwd_kernel<TT, false><<<(unsigned)(B * U1), threads, 0, st>>>((const TT*)dJ, (const TT*)enc, enc_sb, enc_st, (const TT*)pred, pred_sb, pred_su, (TT*)d_enc, denc_sb, denc_st, d_pred, (int)B, (int)Tc, (int)U1, (int)J); \
+    } } while (0)
+  if (dtype == SC_BF16) SC_JBWD(bf16, 8);
+  else if (dtype == SC_F32) SC_JBWD(float, 4);
+  else return SC_E_DTYPE;
+#undef SC_JBWD
   SC_LAUNCH_RET();
 }
 
@@ -489,7 +664,7 @@ extern "C" int sc_rnnt_lse_gather(const void* logits, int dtype, const int64_t* 
                                   const int64_t* frame_lens, const int64_t* label_lens, int64_t B, int64_t T,
                                   int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, float* lse,
                                   float* eb, float* el, void* stream) {
-  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank) && t0 >= 0 && Tc >= 0 && t0 + Tc <= T, SC_E_SHAPE);
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank) && t0 >= 0 && Tc >= 0 && t0 + Tc <= T && B * Tc * U1 < ((int64_t)1 << 31), SC_E_SHAPE);
   if (Tc == 0) return 0;
   SC_CHECK_ARG(logits && frame_lens && label_lens && lse && eb && el && (U1 == 1 || labels), SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
@@ -534,14 +709,31 @@ extern "C" int sc_rnnt_node_grads(const int64_t* frame_lens, const int64_t* labe
 extern "C" int sc_rnnt_dlogits(const void* logits, int dtype, const float* lse, const float* gb, const float* gl,
                                const int64_t* labels, int64_t ldl, const int64_t* label_lens, int64_t B, int64_t T,
                                int64_t t0, int64_t Tc, int64_t U1, int64_t V, int64_t blank, void* dlogits,
-                               void* stream) {
-  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank) && t0 >= 0 && Tc >= 0 && t0 + Tc <= T, SC_E_SHAPE);
+                               float* dbias, void* stream) {
+  SC_CHECK_ARG(rnnt_args_ok(B, T, U1, V, blank) && t0 >= 0 && Tc >= 0 && t0 + Tc <= T && B * Tc * U1 < ((int64_t)1 << 31), SC_E_SHAPE);
   if (Tc == 0) return 0;
   SC_CHECK_ARG(logits && lse && gb && gl && label_lens && dlogits && (U1 == 1 || labels), SC_E_BADARG);
+  SC_CHECK_ARG(dtype == SC_BF16 || dtype == SC_F32, SC_E_DTYPE);
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)cdiv(B * Tc * U1, 8);
+  const int64_t rows = B * Tc * U1;
+  const int vw = dtype == SC_BF16 ? 8 : 4;
+  const bool vec = (V % vw == 0) && V <= 1024 && ((((uintptr_t)logits | (uintptr_t)dlogits) & 15) == 0);
+  if (vec) {
+    // persistent: enough warps to fill the machine, few enough blocks that the per-block column
+    // atomics stay negligible
+    const unsigned grid = (unsigned)min(cdiv(rows, 8), (int64_t)num_sms() * 4);
+    const size_t smem = (size_t)V * sizeof(float);
+    if (dtype == SC_BF16)
+      rnnt_dlogits_vec_kernel<bf16, 4><<<grid, 256, smem, st>>>((const bf16*)logits, lse, gb, gl, labels, ldl, label_lens,
+          (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (bf16*)dlogits, dbias);
+    else
+      rnnt_dlogits_vec_kernel<float, 8><<<grid, 256, smem, st>>>((const float*)logits, lse, gb, gl, labels, ldl, label_lens,
+          (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (float*)dlogits, dbias);
+    SC_LAUNCH_RET();
+  }
+  const unsigned grid = (unsigned)cdiv(rows, 8);
   if (dtype == SC_BF16) rnnt_dlogits_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)logits, lse, gb, gl, labels, ldl, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (bf16*)dlogits);
-  else if (dtype == SC_F32) rnnt_dlogits_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, lse, gb, gl, labels, ldl, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (float*)dlogits);
-  else return SC_E_DTYPE;
+  else rnnt_dlogits_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, lse, gb, gl, labels, ldl, label_lens, (int)B, (int)T, (int)t0, (int)Tc, (int)U1, (int)V, blank, (float*)dlogits);
+  if (dbias != nullptr) return sc_colsum(dlogits, V, dtype, dbias, rows, V, 1, stream);
   SC_LAUNCH_RET();
 }

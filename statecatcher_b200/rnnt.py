@@ -224,9 +224,8 @@ class _RNNTFusedFn(torch.autograd.Function):
                  ptr(joint), B, Tc, U1, J, dtc, stream())
             ops.gemm_fwd(joint, Woc, bo, out=logits)
             call("sc_rnnt_dlogits", ptr(logits), _lib.dt(logits), ptr(lse), ptr(gb), ptr(gl), ptr(labels), ldl, ptr(ll),
-                 B, T, t0, Tc, U1, V, blank, ptr(dlogits), stream())
+                 B, T, t0, Tc, U1, V, blank, ptr(dlogits), ptr(dbo), stream())     # dbo += column sums (fused)
             ops.gemm_wgrad(dlogits, joint, out=dWo, accumulate=True)
-            ops.colsum(dlogits, out=dbo, accumulate=True)
             ops.gemm_dgrad(dlogits, Woc, out=dJ)
             dch = d_encp[:, t0:t0 + Tc]
             call("sc_joint_bwd", ptr(dJ), ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0),
