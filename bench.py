@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--layer-norm", action="store_true", help="layer_norm=True variant (general path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rnnt-keep", choices=["auto", "0", "1"], default="auto",
+                    help="cfg4: keep every block's joint/logits in HBM for the backward (1), recompute (0), or decide by free memory")
     ap.add_argument("--detail", action="store_true", help="per-call timing table of the last timed step on stderr")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -243,7 +245,8 @@ def main():
     if "rnnt" in W:
         torch.manual_seed(99)
         head = sb.RNNTFusedHead(enc_out_dim=W["V"], pred_emb_dim=W["rnnt"]["E"], join_dim=W["rnnt"]["J"],
-                                vocab_size=W["V"], chunk_frames=64, compute_dtype=cd).to(dev)
+                                vocab_size=W["V"], chunk_frames=64, compute_dtype=cd,
+                                keep_blocks={"auto": None, "0": False, "1": True}[args.rnnt_keep]).to(dev)
         full = torch.nn.ModuleDict({"enc": enc, "head": head})
     model = StreamDataParallel(enc) if world > 1 else enc
 

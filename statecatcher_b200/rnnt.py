@@ -13,6 +13,8 @@ oracle/rnnt_oracle.py and torchaudio.functional.rnnt_loss.
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn as nn
 
@@ -155,7 +157,7 @@ class _RNNTFusedFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, enc_out, pred_emb, labels, fl, ll, blank, chunk, cd, We, be, Wp, bp, Wo, bo):
+    def forward(ctx, enc_out, pred_emb, labels, fl, ll, blank, chunk, cd, keep_blocks, We, be, Wp, bp, Wo, bo):
         B, T, De = enc_out.shape
         U1, J, V = pred_emb.shape[1], We.shape[0], Wo.shape[0]
         dev = enc_out.device
@@ -176,21 +178,34 @@ class _RNNTFusedFn(torch.autograd.Function):
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         ldl = labels.stride(0) if labels.numel() else max(U1 - 1, 1)
         dtc = _lib.dt(encp)
-        # block buffers are allocated once and reused by every block (views for the tail block)
+        # Block buffers are allocated once and reused by every block (views for the tail block) —
+        # unless the whole joint + logits lattice fits comfortably in free HBM (cfg4: 88 GB of the
+        # B200's 180 GB), in which case every block keeps its own and the backward skips the
+        # recomputation of the joiner (one elementwise pass and one GEMM per block).
         rows_max = B * min(chunk, max(T, 1)) * U1
-        joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
-        logits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
+        esz = torch.empty((), dtype=cd).element_size()
+        need = B * T * U1 * (J + V) * esz
+        keep = keep_blocks if keep_blocks is not None else (T > 0 and need < 0.75 * torch.cuda.mem_get_info(dev)[0])
+        kept = []
+        if not keep:
+            joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
+            logits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
         for t0 in range(0, T, chunk):
             Tc = min(chunk, T - t0)
-            joint, logits = joint_buf[:B * Tc * U1], logits_buf[:B * Tc * U1]
+            if keep:
+                joint = torch.empty(B * Tc * U1, J, dtype=cd, device=dev)
+                logits = torch.empty(B * Tc * U1, V, dtype=cd, device=dev)
+                kept.append((joint, logits))
+            else:
+                joint, logits = joint_buf[:B * Tc * U1], logits_buf[:B * Tc * U1]
             ech = encp[:, t0:t0 + Tc]
             call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
                  ptr(joint), B, Tc, U1, J, dtc, stream())
             ops.gemm_fwd(joint, Woc, bo.detach(), out=logits)
             call("sc_rnnt_lse_gather", ptr(logits), _lib.dt(logits), ptr(labels), ldl, ptr(fl), ptr(ll), B, T, t0, Tc,
                  U1, V, blank, ptr(lse), ptr(eb), ptr(el), stream())
-        del joint_buf, logits_buf
         call("sc_rnnt_lattice", ptr(fl), ptr(ll), B, T, U1, ptr(eb), ptr(el), ptr(alpha), ptr(beta), ptr(nll), stream())
+        ctx.kept = kept                                   # plain attribute: not inputs/outputs of the node
         ctx.save_for_backward(e2, p2, encp, predp, labels, fl, ll, eb, el, alpha, beta, lse, nll, Wec, Wpc, Woc, bo.detach())
         ctx.cfg = (B, T, U1, J, V, De, blank, chunk, cd, ldl, tuple(pred_emb.shape))
         return nll
@@ -211,18 +226,26 @@ class _RNNTFusedFn(torch.autograd.Function):
         dbo = torch.zeros(V, dtype=torch.float32, device=dev)
         dtc = _lib.dt(encp)
         rows_max = B * min(chunk, max(T, 1)) * U1
-        joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
-        logits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
+        kept = ctx.kept
+        joint_buf = logits_buf = None                    # recompute buffers, allocated on first use
         dlogits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
         dJ_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
-        for t0 in range(0, T, chunk):
+        for bi, t0 in enumerate(range(0, T, chunk)):
             Tc = min(chunk, T - t0)
             n = B * Tc * U1
-            joint, logits, dlogits, dJ = joint_buf[:n], logits_buf[:n], dlogits_buf[:n], dJ_buf[:n]
+            dlogits, dJ = dlogits_buf[:n], dJ_buf[:n]
             ech = encp[:, t0:t0 + Tc]
-            call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
-                 ptr(joint), B, Tc, U1, J, dtc, stream())
-            ops.gemm_fwd(joint, Woc, bo, out=logits)
+            if kept and kept[bi] is not None:
+                joint, logits = kept[bi]
+                kept[bi] = None                          # released as the backward passes it (a 2nd backward recomputes)
+            else:
+                if joint_buf is None:
+                    joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
+                    logits_buf = torch.empty(rows_max, V, dtype=cd, device=dev)
+                joint, logits = joint_buf[:n], logits_buf[:n]
+                call("sc_joint_fwd", ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0), predp.stride(1),
+                     ptr(joint), B, Tc, U1, J, dtc, stream())
+                ops.gemm_fwd(joint, Woc, bo, out=logits)
             call("sc_rnnt_dlogits", ptr(logits), _lib.dt(logits), ptr(lse), ptr(gb), ptr(gl), ptr(labels), ldl, ptr(ll),
                  B, T, t0, Tc, U1, V, blank, ptr(dlogits), ptr(dbo), stream())     # dbo += column sums (fused)
             ops.gemm_wgrad(dlogits, joint, out=dWo, accumulate=True)
@@ -230,7 +253,7 @@ class _RNNTFusedFn(torch.autograd.Function):
             dch = d_encp[:, t0:t0 + Tc]
             call("sc_joint_bwd", ptr(dJ), ptr(ech), ech.stride(0), ech.stride(1), ptr(predp), predp.stride(0),
                  predp.stride(1), ptr(dch), dch.stride(0), dch.stride(1), ptr(d_predp), B, Tc, U1, J, dtc, stream())
-        del joint_buf, logits_buf, dlogits_buf, dJ_buf
+        del dlogits_buf, dJ_buf
         de2 = d_encp.view(B * T, J)
         dp2 = d_predp.view(B * U1, J)
         if dp2.dtype != cd:
@@ -239,7 +262,7 @@ class _RNNTFusedFn(torch.autograd.Function):
         dWp, dbp = ops.gemm_wgrad(dp2, p2), ops.colsum(dp2)
         d_enc = ops.gemm_dgrad(de2, Wec).view(B, T, De) if ctx.needs_input_grad[0] else None
         d_pred = ops.gemm_dgrad(dp2, Wpc).view(pshape) if ctx.needs_input_grad[1] else None
-        return (d_enc, d_pred, None, None, None, None, None, None, dWe, dbe, dWp, dbp, dWo, dbo)
+        return (d_enc, d_pred, None, None, None, None, None, None, None, dWe, dbe, dWp, dbp, dWo, dbo)
 
 
 class RNNTFusedHead(nn.Module):
@@ -249,7 +272,7 @@ class RNNTFusedHead(nn.Module):
     configs[3] (J=512, V=1024, T=3000, U<=150) runs at batch 64."""
 
     def __init__(self, enc_out_dim: int, pred_emb_dim: int, join_dim: int, vocab_size: int,
-                 chunk_frames: int = 64, compute_dtype=None):
+                 chunk_frames: int = 64, compute_dtype=None, keep_blocks: Optional[bool] = None):
         super().__init__()
         self.embedding = nn.Embedding(vocab_size, pred_emb_dim)
         self.enc_proj = nn.Linear(enc_out_dim, join_dim)
@@ -257,6 +280,7 @@ class RNNTFusedHead(nn.Module):
         self.joiner = nn.Linear(join_dim, vocab_size)
         self.chunk_frames = chunk_frames
         self.compute_dtype = compute_dtype
+        self.keep_blocks = keep_blocks        # None: keep the blocks' joint/logits when they fit in free HBM, else recompute
 
     def forward(self, enc_out, tokens, frames_lengths, labels_lengths, blank_id: int = 0, reduction: str = "mean"):
         _lib.require_cuda(enc_out, "RNNTFusedHead input")
@@ -268,6 +292,6 @@ class RNNTFusedHead(nn.Module):
         cd = _compute_dtype(enc_out, self.compute_dtype)
         pred_emb = self.embedding(prefix)
         nll = _RNNTFusedFn.apply(enc_out.contiguous(), pred_emb.contiguous(), tokens, fl, ll, int(blank_id),
-                                 int(self.chunk_frames), cd, self.enc_proj.weight, self.enc_proj.bias,
+                                 int(self.chunk_frames), cd, self.keep_blocks, self.enc_proj.weight, self.enc_proj.bias,
                                  self.pred_proj.weight, self.pred_proj.bias, self.joiner.weight, self.joiner.bias)
         return _reduce(nll, reduction)

@@ -159,3 +159,34 @@ def test_rnnt_fused_head_cfg4_shape(cuda_device):
     assert torch.isfinite(enc.grad).all() and enc.grad.abs().max() > 0
     for n, p in head.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_rnnt_fused_head_keep_vs_recompute(cuda_device):
+    """Keeping every block's joint/logits in HBM and recomputing them in the backward are the
+    same computation: identical loss, gradients equal up to atomic summation order; a second backward over kept
+    blocks (already released) falls back to recomputation."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(9)
+    B, T, U, V, J, E, De = 2, 37, 5, 48, 64, 16, 32
+    fl, ll = [37, 30], [5, 2]
+    heads = [sb.RNNTFusedHead(enc_out_dim=De, pred_emb_dim=E, join_dim=J, vocab_size=V, chunk_frames=16,
+                              compute_dtype=torch.bfloat16, keep_blocks=k).cuda() for k in (True, False)]
+    heads[1].load_state_dict(heads[0].state_dict())
+    enc = torch.randn(B, T, De, device="cuda")
+    tokens = torch.randint(1, V, (B, U), device="cuda")
+    outs = []
+    for h in heads:
+        e = enc.clone().requires_grad_(True)
+        loss = h(e, tokens, fl, ll, blank_id=0)
+        loss.backward(retain_graph=True)
+        g1 = [e.grad.clone()] + [p.grad.clone() for p in h.parameters()]
+        e.grad = None
+        h.zero_grad(set_to_none=True)
+        loss.backward()                                  # kept blocks were released: recomputed now
+        g2 = [e.grad.clone()] + [p.grad.clone() for p in h.parameters()]
+        for a, b in zip(g1, g2):                         # split-R weight gradients / bias sums reduce atomically:
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)   # same values, summation order may differ
+        outs.append((loss.detach(), g1))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
