@@ -115,6 +115,16 @@ int sc_lucy_scan_fwd(const void* G, int64_t ldg, const float* h0, const float* s
  * [B,T,5H] (same block order) and ADDS the per-column sums of dG into dbias[5H] (fp32,
  * the caller zeroes or pre-loads it).  No gradient is produced for h0/s0 (the carried
  * state is detached between segments, model.py:60-61). */
+/* Few-streams variant of sc_lucy_scan_fwd (streaming inference with one or a few live streams):
+ * the same outputs computed by a time-parallel chunked scan (both recurrences are affine in their
+ * state, lucyrnn.py:153-166 / 172-184), three launches over (stream, channel block, 64-step
+ * chunk).  sc_lucy_scan_chunked_work_bytes returns the fp32 workspace it needs, or 0 when the
+ * sequential kernel is the better choice for (B, T, H) on this device. */
+int64_t sc_lucy_scan_chunked_work_bytes(int64_t B, int64_t T, int64_t H);
+int sc_lucy_scan_fwd_chunked(const void* G, int64_t ldg, const float* h0, const float* s0,
+                             void* Hout, int64_t ldh, float* hT, float* sT, float* Sckpt,
+                             float* work, int64_t B, int64_t T, int64_t H, int dtype, int train_mode,
+                             void* stream);
 int sc_lucy_scan_bwd(const void* G, int64_t ldg, const void* Hout, int64_t ldh,
                      const float* h0, const float* s0, const float* Sckpt,
                      const void* dHout, int64_t lddh, void* dG, int64_t lddg, float* dbias,

@@ -36,6 +36,8 @@ SIGNATURES = {
     "sc_layernorm_fwd": [P, I64, P, P, P, I64, P, P, I64, I64, I32, P],
     "sc_layernorm_bwd": [P, I64, P, I64, P, P, P, P, I64, P, P, I64, I64, I32, P],
     "sc_lucy_scan_fwd": [P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I32, I32, P],
+    "sc_lucy_scan_chunked_work_bytes": [I64, I64, I64],
+    "sc_lucy_scan_fwd_chunked": [P, I64, P, P, P, I64, P, P, P, P, I64, I64, I64, I32, I32, P],
     "sc_lucy_scan_bwd": [P, I64, P, I64, P, P, P, P, I64, P, I64, P, I64, I64, I64, I32, I32, P],
     "sc_lucy_sscan_fwd": [P, P, P, I64, P, I64, P, P, I64, P, P, I64, I64, I64, I32, I32, I32, F32, P],
     "sc_lucy_sscan_bwd": [P, P, P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I64, I32, I32, I32, F32, P],
@@ -59,7 +61,7 @@ SIGNATURES = {
     "sc_scale_grads": [P, I64, P, F32, P],
     "sc_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P, F32, I32, P],
 }
-_RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64}
+_RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64}
 
 _lib = None
 
@@ -125,7 +127,7 @@ profile = None
 
 KERNELS_PER_CALL = {
     "sc_gemm_fwd": 1, "sc_gemm_dgrad": 1, "sc_gemm_wgrad": 1, "sc_cast": 1, "sc_colsum": 2,
-    "sc_layernorm_fwd": 1, "sc_layernorm_bwd": 1, "sc_lucy_scan_fwd": 1, "sc_lucy_scan_bwd": 1,
+    "sc_layernorm_fwd": 1, "sc_layernorm_bwd": 1, "sc_lucy_scan_fwd": 1, "sc_lucy_scan_fwd_chunked": 3, "sc_lucy_scan_bwd": 1,
     "sc_lucy_sscan_fwd": 1, "sc_lucy_sscan_bwd": 1, "sc_lucy_hscan_fwd": 1, "sc_lucy_hscan_bwd": 1,
     "sc_ctc_fwd": 3, "sc_ctc_emissions": 1, "sc_ctc_lattice": 2, "sc_ctc_bwd": 1, "sc_rnnt_fwd": 2, "sc_rnnt_bwd": 2, "sc_split_bf16": 1, "sc_joint_fwd": 1, "sc_joint_bwd": 2, "sc_rnnt_lse_gather": 1, "sc_rnnt_lattice": 1,
     "sc_rnnt_node_grads": 1, "sc_rnnt_dlogits": 1, "sc_ctc_greedy_decode": 2,

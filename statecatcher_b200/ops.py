@@ -120,8 +120,14 @@ def scan_fwd(G, B, T, H, h0, s0, train_mode: bool):
     hT = torch.empty(B, H, dtype=torch.float32, device=dev)
     sT = None if train_mode else torch.empty(B, H, dtype=torch.float32, device=dev)
     ck = torch.empty(B, max(n_ckpt(T), 1), H, dtype=torch.float32, device=dev)
-    call("sc_lucy_scan_fwd", ptr(G), _ld(G), ptr(h0), ptr(s0), ptr(Hout), H, ptr(hT), ptr(sT), ptr(ck),
-         B, T, H, dt(G), int(train_mode), stream())
+    wb = _lib.load().sc_lucy_scan_chunked_work_bytes(B, T, H) if T > 0 else 0
+    if wb > 0:                       # few live streams: time-parallel chunked scan (same outputs)
+        work = torch.empty(wb // 4, dtype=torch.float32, device=dev)
+        call("sc_lucy_scan_fwd_chunked", ptr(G), _ld(G), ptr(h0), ptr(s0), ptr(Hout), H, ptr(hT), ptr(sT), ptr(ck),
+             ptr(work), B, T, H, dt(G), int(train_mode), stream())
+    else:
+        call("sc_lucy_scan_fwd", ptr(G), _ld(G), ptr(h0), ptr(s0), ptr(Hout), H, ptr(hT), ptr(sT), ptr(ck),
+             B, T, H, dt(G), int(train_mode), stream())
     return Hout, hT, sT, ck
 
 

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.sc_version() == 6
+    assert lib.sc_version() == 7
     assert b"BADARG" in lib.sc_error_string(-1)
     buf = __import__("ctypes").create_string_buffer(128)
     assert lib.sc_build_info(buf, 128) == 0 and b"sm_100a" in buf.value

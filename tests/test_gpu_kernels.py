@@ -437,3 +437,44 @@ def test_ctc_combined_entry_matches_split(cuda_device):
         outs.append((lse, lplat, alpha, beta, nll, loss))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("train_mode", [False, True], ids=["step", "train"])
+@pytest.mark.parametrize("B,T,H", [(1, 256, 64), (2, 300, 200), (1, 1000, 256), (1, 3000, 1024)])
+def test_scan_fwd_chunked_matches_sequential(cuda_device, dtype, train_mode, B, T, H):
+    """The time-parallel chunked forward scan (few live streams) against the sequential kernel on
+    the same gates: outputs, carried states and the backward's checkpoints.  The two differ
+    only by re-association across 64-step chunk boundaries."""
+    from statecatcher_b200._lib import call, dt, ptr, stream, load
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + H)
+    G = (torch.randn(B * T, 5 * H, generator=g, device="cuda") * 1.5).to(dtype)
+    h0 = torch.randn(B, H, generator=g, device="cuda")
+    s0 = torch.randn(B, H, generator=g, device="cuda")
+    nck = (T + 7) // 8
+    outs = []
+    for chunked in (False, True):
+        Hout = torch.empty(B * T, H, dtype=dtype, device="cuda")
+        hT = torch.empty(B, H, device="cuda")
+        sT = torch.zeros(B, H, device="cuda")
+        ck = torch.empty(B, nck, H, device="cuda")
+        if chunked:
+            wb = 4 * B * ((T + 63) // 64) * H * 4
+            work = torch.empty(wb // 4, device="cuda")
+            call("sc_lucy_scan_fwd_chunked", ptr(G), 5 * H, ptr(h0), ptr(s0), ptr(Hout), H, ptr(hT), ptr(sT), ptr(ck),
+                 ptr(work), B, T, H, dt(G), int(train_mode), stream())
+        else:
+            call("sc_lucy_scan_fwd", ptr(G), 5 * H, ptr(h0), ptr(s0), ptr(Hout), H, ptr(hT), ptr(sT), ptr(ck),
+                 B, T, H, dt(G), int(train_mode), stream())
+        outs.append((Hout.float(), hT, sT, ck))
+    tol = dict(rtol=2e-5, atol=2e-6) if dtype == torch.float32 else dict(rtol=1.6e-2, atol=1e-3)
+    torch.testing.assert_close(outs[1][0], outs[0][0], **tol)                 # Hout (bf16: one rounding step apart at most)
+    st = dict(rtol=2e-5, atol=2e-5) if dtype == torch.float32 else dict(rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(outs[1][1], outs[0][1], **st)                  # hT
+    if not train_mode:
+        torch.testing.assert_close(outs[1][2], outs[0][2], **st)              # sT
+    torch.testing.assert_close(outs[1][3], outs[0][3], **st)                  # checkpoints of S
+    lib = load()
+    assert lib.sc_lucy_scan_chunked_work_bytes(1, 3000, 1024) == 4 * 47 * 1024 * 4
+    assert lib.sc_lucy_scan_chunked_work_bytes(64, 3000, 1024) == 0           # enough streams: sequential kernel
+    assert lib.sc_lucy_scan_chunked_work_bytes(1, 100, 1024) == 0             # too short to cut
