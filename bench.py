@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rnnt-keep", choices=["auto", "0", "1"], default="auto",
                     help="cfg4: keep every block's joint/logits in HBM for the backward (1), recompute (0), or decide by free memory")
+    ap.add_argument("--graph", action="store_true",
+                    help="forward-only workloads: replay each segment from a CUDA graph (GraphedStreamingEncoder)")
     ap.add_argument("--detail", action="store_true", help="per-call timing table of the last timed step on stderr")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -205,6 +207,7 @@ def workload_config(args, W, world):
                         f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
             "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": not W.get("forward_only", False),
             "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
+            "cuda_graph": bool(getattr(args, "graph", False)) and bool(W.get("forward_only")),
             "dp_allreduce": None if world == 1 else (
                 "bucketed, overlapped with backward" if os.environ.get("SC_DP_OVERLAP", "1") != "0"
                 else "bucketed, launched after backward"),
@@ -262,8 +265,12 @@ def main():
     frames_step = W["B"] * W["T"]
     state = {"s": None}
 
+    runner = sb.GraphedStreamingEncoder(enc, W["B"], W["T"], W["F"], dev) if (fwd_only and args.graph) else None
+
     def step_resident(i):
         j = i % NSEG
+        if runner is not None:                                  # whole segment replayed from one CUDA graph
+            return runner.step(xd[j])
         if fwd_only:                                            # streaming inference: step path, no autograd
             with torch.no_grad():
                 logits, state["s"] = model(xd[j], state["s"]) if state["s"] else model(xd[j])
@@ -293,6 +300,8 @@ def main():
         if feeder["it"] is None:
             feeder["it"] = sb.SegmentPrefetcher(host_batches(), dev)
         xbuf, tokbuf, inl, tgl = next(feeder["it"])                           # H2D features + labels from pinned host
+        if runner is not None:
+            return runner.step(xbuf)[:, -1, :8].float().cpu()       # D2H read of a result slice
         if fwd_only:
             with torch.no_grad():
                 logits, state["s"] = model(xbuf, state["s"]) if state["s"] else model(xbuf)

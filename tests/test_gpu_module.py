@@ -261,3 +261,31 @@ def test_segment_prefetcher_orders_copies():
     assert len(sums) == 7
     got = torch.cat(sums).cpu().tolist()
     assert got == pytest.approx(refs, rel=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 3])
+def test_graphed_streaming_encoder_matches_eager(B):
+    """Three carried segments replayed from the CUDA graph == the same three eager calls,
+    bit for bit (same kernels, same order), including the carried (h, s) state and reset()."""
+    import statecatcher_b200 as sb
+    torch.manual_seed(3)
+    cfg = sb.LucyRNNConfig(input_dim=24, hidden_dim=128, num_layers=2, vocab_size=40, is_training=False,
+                           fused_ops=True, layer_norm=False)
+    model = sb.LucyRNN(cfg, compute_dtype=torch.bfloat16).cuda()
+    torch.nn.init.normal_(model.output_proj.weight, std=0.05)
+    T = 320                                                  # long enough for the chunked scan at B=1
+    segs = [torch.randn(B, T, 24, device="cuda") for _ in range(3)]
+    with torch.no_grad():
+        state, want = None, []
+        for x in segs:
+            out, state = model(x, state) if state else model(x)
+            want.append(out.clone())
+    runner = sb.GraphedStreamingEncoder(model, B, T, 24)
+    for k in range(2):                                       # second pass after reset(): same stream again
+        runner.reset()
+        for x, w in zip(segs, want):
+            got = runner.step(x)
+            assert torch.equal(got, w)
+    for a, b in zip(runner.state[0] + runner.state[1], state[0] + state[1]):
+        assert torch.equal(a, b.float())
