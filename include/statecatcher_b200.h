@@ -164,7 +164,8 @@ int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn
  * the (T,B,V) transposed view nn.CTCLoss receives are accepted.  Rows need not be
  * normalised (log-softmax is folded in and is idempotent).
  * targets [B,Umax] int64 (row stride ldt), in_lens/tgt_lens [B] int64.
- * Workspaces (caller-allocated, fp32, 16-byte aligned): lse [B,T], lplat/alpha/beta [B,T,S]
+ * Workspaces (caller-allocated, fp32, 16-byte aligned): lse [B,T], cshift [B,T] (per-frame shift
+ * taken out of the lattice emissions: the largest of them, log2 units), lplat/alpha/beta [B,T,S]
  * with S = 2*Umax+1 rounded up to a multiple of 4 (alpha/beta are in log2 units; alpha includes
  * the emission of its frame, beta does not; both carry an arbitrary per-frame offset).  nll [B] = per-utterance negative log-likelihood (+inf if infeasible);
  * loss [1] = reduction of nll: reduction 0 none (loss untouched), 1 mean
@@ -172,17 +173,17 @@ int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn
 int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
-               int64_t blank, float* lse, float* lplat, float* alpha, float* beta,
+               int64_t blank, float* lse, float* lplat, float* cshift, float* alpha, float* beta,
                float* nll, float* loss, int reduction, void* stream);
 /* The two halves of sc_ctc_fwd as separate calls (what statecatcher_b200/ctc.py binds, so that
  * the bandwidth-bound emission pass and the latency-bound lattice recursion are timed apart):
- * sc_ctc_emissions: logits -> lse, lplat (log-softmax + gather of the 2U+1 lattice emissions);
- * sc_ctc_lattice:   lplat -> alpha, beta, nll, loss (the alpha/beta recursions + reduction). */
+ * sc_ctc_emissions: logits -> lse, lplat, cshift (log-softmax + gather of the 2U+1 lattice emissions);
+ * sc_ctc_lattice:   lplat, cshift -> alpha, beta, nll, loss (the alpha/beta recursions + reduction). */
 int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                      const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                      const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
-                     int64_t blank, float* lse, float* lplat, void* stream);
-int sc_ctc_lattice(const float* lplat, const int64_t* targets, int64_t ldt,
+                     int64_t blank, float* lse, float* lplat, float* cshift, void* stream);
+int sc_ctc_lattice(const float* lplat, const float* cshift, const int64_t* targets, int64_t ldt,
                    const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T,
                    int64_t Umax, int64_t blank, float* alpha, float* beta, float* nll,
                    float* loss, int reduction, void* stream);

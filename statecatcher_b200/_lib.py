@@ -43,9 +43,9 @@ SIGNATURES = {
     "sc_lucy_sscan_bwd": [P, P, P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I64, I32, I32, I32, F32, P],
     "sc_lucy_hscan_fwd": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I32, P],
     "sc_lucy_hscan_bwd": [P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I64, I64, I64, I32, P],
-    "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, I32, P],
-    "sc_ctc_emissions": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P],
-    "sc_ctc_lattice": [P, P, I64, P, P, I64, I64, I64, I64, P, P, P, P, I32, P],
+    "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, I32, P],
+    "sc_ctc_emissions": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P],
+    "sc_ctc_lattice": [P, P, P, I64, P, P, I64, I64, I64, I64, P, P, P, P, I32, P],
     "sc_ctc_bwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, I32,
                    P, I64, I64, I32, P],
     "sc_rnnt_fwd": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P],

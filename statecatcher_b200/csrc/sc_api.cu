@@ -21,7 +21,7 @@ int tc_gemm_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, i
 
 using namespace sc;
 
-extern "C" int sc_version(void) { return 7; }
+extern "C" int sc_version(void) { return 8; }
 
 extern "C" const char* sc_error_string(int code) {
   switch (code) {

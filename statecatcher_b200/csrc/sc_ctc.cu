@@ -29,6 +29,7 @@
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
+#include <stdlib.h>
 
 namespace sc {
 
@@ -60,7 +61,7 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
                       const int64_t* __restrict__ targets, int64_t ldt,
                       const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                       int B, int Tn, int V, int Smax, int64_t blank,
-                      float* __restrict__ lse, float* __restrict__ lplat) {
+                      float* __restrict__ lse, float* __restrict__ lplat, float* __restrict__ cshift) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned nrows = (unsigned)B * (unsigned)Tn;           // B*T < 2^31 (checked by the host)
   // (grid-stride loop; launched with one warp per row — capping the grid at a few blocks per SM
@@ -75,8 +76,21 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
     const int S = 2 * (int)tgt_lens[b] + 1;
     const int64_t* tg = targets + (int64_t)b * ldt;
     float* out = lplat + (int64_t)row * Smax;
-    // emissions in log2 units (the recursion runs on ex2/lg2 directly)
-    for (int s = lane; s < S; s += 32) out[s] = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
+    // emissions in log2 units (the recursion runs on ex2/lg2 directly), shifted so that the
+    // frame's largest lattice emission is 0: the recursion's values then drift by the gap between
+    // the paths and the frame-wise best node (~2 per frame on random logits, ~0 on a trained
+    // model) instead of by log2(V) per frame, which lets it re-centre 4x less often at the same
+    // fp32 resolution.  The shift goes to cshift[b,t] and is added back into the likelihood.
+    float c = NEG_INF;
+    for (int s = lane; s < S; s += 32) {
+      const float e = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
+      out[s] = e;
+      c = fmaxf(c, e);
+    }
+    c = warp_max(c);
+    if (!(c > -1e29f)) c = 0.f;                                  // every lattice emission is -inf: leave the row alone
+    for (int s = lane; s < S; s += 32) out[s] = fmaxf(out[s] - c, -1e30f);   // each lane re-reads its own stores; -inf logits become the recursion's finite dead value
+    if (lane == 0) cshift[row] = c;
   }
 }
 
@@ -101,7 +115,22 @@ constexpr float CTC_DEAD = -1e30f;          // below CTC_DEAD_TEST a log2-domain
 constexpr float CTC_DEAD_TEST = -1e29f;
 constexpr float LN2 = 0.6931471805599453f;
 
-__global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
+// sum_t cshift[t], t < n, over the block in double; result valid in every thread.  Contains two
+// block barriers: call it from uniform code.
+__device__ __forceinline__ double block_shift_sum(const float* __restrict__ c, int n, double* dred) {
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) acc += (double)c[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) r += dred[w];
+  __syncthreads();
+  return r;
+}
+
+__global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
                                       const int64_t* __restrict__ targets, int64_t ldt,
                                       const int64_t* __restrict__ in_lens,
                                       const int64_t* __restrict__ tgt_lens,
@@ -110,6 +139,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
                                       float* __restrict__ nll) {
   extern __shared__ __align__(128) float sm[];   // 2 lines of (Smax + 4) floats (2 pad cells either side) + emission blocks
   __shared__ float red[32];
+  __shared__ double dred[32];
   __shared__ __align__(8) uint64_t ebar[2];
   const int b = blockIdx.x, dir = blockIdx.y;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
@@ -122,6 +152,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
     if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
     return;
   }
+  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
   for (int i = threadIdx.x; i < 2 * LINE; i += blockDim.x) sm[i] = NEG_INF;
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&ebar[0]), 1);
@@ -208,7 +239,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
       } else {
         // re-centre the last column once per visit (at most every CTC_EB steps)
         const float m = block_max(has ? prev[s] : NEG_INF);
-        if (m > NEG_INF) {
+        if (m > CTC_DEAD_TEST) {
           if (has) prev[s] -= m;                                  // rows already written keep their own offset
           csum += (double)m;
         }
@@ -252,7 +283,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
         float m = NEG_INF;
         for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, cur[s]);
         m = block_max(m);
-        if (m > NEG_INF) {
+        if (m > CTC_DEAD_TEST) {
           for (int s = threadIdx.x; s < S; s += blockDim.x) cur[s] -= m;
           csum += (double)m;
         }
@@ -265,8 +296,197 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat,
   }
   if (dir == 0 && threadIdx.x == 0) {
     const float ll2 = lse3_2(final_buf[S - 1], S > 1 ? final_buf[S - 2] : NEG_INF, NEG_INF);
-    nll[b] = (ll2 == NEG_INF) ? INFINITY : (float)(-(csum + (double)ll2) * (double)LN2);   // +inf when infeasible
+    nll[b] = (ll2 < CTC_DEAD_TEST) ? INFINITY : (float)(-(csum + shift_sum + (double)ll2) * (double)LN2);   // +inf when infeasible
   }
+}
+
+// ---- pass 2, wavefront variant (lattices up to 1024 nodes) ---------------------------------
+// Same recursion, no block barrier per timestep.  Node values live in REGISTERS (thread i owns
+// node i for alpha, node S-1-i for beta, so both directions only ever look at lower threads);
+// the two neighbours come from __shfl_up, and only lanes 0/1 of a warp need anything from
+// another warp: lanes 30/31 of warp w-1 publish {value, step tag} pairs into a shared-memory
+// slot per timestep and lanes 0/1 of warp w poll that slot for the tag of the previous step.
+// Dependencies only run from warp w-1 to warp w, so the warps settle into a skew of one
+// shared-memory round trip and after that nobody waits: the per-step cost is one warp's own
+// chain (SHFL -> min/max -> 2x ex2 -> lg2) instead of the slowest of 10 warps plus a barrier
+// (measured: see DESIGN.md 3.3).  The block still meets once per emission block of `EB` rows
+// (32-64 timesteps): there the column is re-centred on its maximum, the slots are recycled and
+// the next emission block is requested.  log2(2^a+2^b+2^c) is taken as
+// max + lg2(1 + 2^(mid-max) + 2^(min-max)): 3 MUFU ops instead of 4 — with 3 warps per
+// scheduler the MUFU pipe (8 issue cycles per warp instruction) is what bounds a step.
+// Dead nodes are the FINITE sentinel CTC_DEAD here (not -inf), so max - max never produces a NaN
+// and the log-sum-exp needs no clamp: 4 min/max + 2 ex2 + 1 lg2.
+__device__ __forceinline__ float lse3w(float a, float b, float c) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  const float m = fmaxf(hi, c), mid = fminf(hi, c);
+  return m + lg2f(1.f + ex2f(mid - m) + ex2f(lo - m));
+}
+__device__ __forceinline__ void slot_publish(uint32_t addr, float v, int tag) {
+  asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" :: "r"(addr), "r"(__float_as_uint(v)), "r"(tag));
+}
+// value published by lane 31 of the producing warp, once it carries `tag`.  Straight-line when
+// the slot is already there (the steady state); bounded spin, then trap, when it is not.
+__device__ __forceinline__ float slot_poll(uint32_t addr, int tag) {
+  uint32_t v;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t, n;\n"
+      "ld.volatile.shared.v2.b32 {%0, t}, [%1];\n"
+      "setp.eq.s32 p, t, %2;\n"
+      "@p bra.uni SC_SLOT_DONE;\n"
+      "mov.b32 n, 0;\n"
+      "SC_SLOT_SPIN:\n"
+      "ld.volatile.shared.v2.b32 {%0, t}, [%1];\n"
+      "setp.eq.s32 p, t, %2;\n"
+      "@p bra.uni SC_SLOT_DONE;\n"
+      "add.s32 n, n, 1;\n"
+      "setp.lt.s32 p, n, 0x2000000;\n"
+      "@p bra.uni SC_SLOT_SPIN;\n"
+      "trap;\n"
+      "SC_SLOT_DONE:\n"
+      "}\n"
+      : "=r"(v) : "r"(addr), "r"(tag));
+  return __uint_as_float(v);
+}
+
+template <int dir>
+__device__ __forceinline__ void
+ctc_wave_body(float* __restrict__ sm, const float* __restrict__ lplat, const float* __restrict__ cshift,
+              const int64_t* __restrict__ targets, int64_t ldt,
+              const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+              int Tn, int Smax, int EB, int64_t blank,
+              float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
+  __shared__ float red[2][32];
+  __shared__ double dred[32];
+  __shared__ float fin[2];
+  __shared__ __align__(8) uint64_t ebar[2];
+  const int b = blockIdx.x;
+  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64;
+  const int U = (int)tgt_lens[b];
+  const int S = 2 * U + 1;
+  const int64_t* tg = targets + (int64_t)b * ldt;
+  if (Tb <= 0) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
+    return;
+  }
+  const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
+  const int nwarps = (int)(blockDim.x >> 5);
+  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
+  float* ebuf = sm;
+  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * Smax);   // [nwarps][EB+1] x {value, tag}
+  for (int k = i; k < nwarps * (EB + 1) * 2; k += blockDim.x) slots[k] = -1;
+  if (i == 0) {
+    fin[0] = CTC_DEAD; fin[1] = CTC_DEAD;
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool has = i < S;
+  const int s = dir == 0 ? i : S - 1 - i;                        // this thread's lattice node
+  const int sidx = has ? s : 0;
+  // skip transition (from two nodes away) is a per-node constant; lane 0 of every warp sits on
+  // a blank (even node), so it never takes one and only lane 31's value has to cross warps
+  bool skip = false;
+  if (has && (s & 1)) {
+    if (dir == 0) skip = s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1];
+    else skip = s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1];
+  }
+  const bool producer = lane == 31 && warp + 1 < nwarps;
+  const bool lane0 = lane == 0, lane1 = lane == 1;
+  const uint32_t my_slot = smem_u32(slots) + (uint32_t)(warp * (EB + 1) * 8);
+  const uint32_t in_slot = smem_u32(slots) + (uint32_t)((warp > 0 ? warp - 1 : 0) * (EB + 1) * 8);
+  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
+  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
+  const int nvis = (Tb + EB - 1) / EB;
+  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
+  auto rows_of = [&](int blk) { const int r = Tb - blk * EB; return r < EB ? r : EB; };
+  auto issue = [&](int vi) {
+    const int blk = blk_of(vi);
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
+    const uint32_t bar = smem_u32(&ebar[vi & 1]);
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * Smax), lp_b + (int64_t)blk * EB * Smax, bytes, bar);
+  };
+  if (i == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  const int t_first = dir == 0 ? 0 : Tb - 1;
+  const int64_t stride = dir == 0 ? (int64_t)Smax : -(int64_t)Smax;
+  const int estride = dir == 0 ? Smax : -Smax;
+  float* op = out_b + (int64_t)t_first * Smax + sidx;
+  double csum = 0.0;
+  float p0 = CTC_DEAD;                                           // this node's value after the last step
+  int g = 0;                                                     // steps done so far (= tag of the next step)
+  for (int vi = 0; vi < nvis; ++vi) {
+    int pos = 0;
+    if (vi > 0) {
+      // block meeting: re-centre the column, recycle slots and the emission buffer of visit vi-1
+      float m = warp_max(has ? p0 : CTC_DEAD);
+      if (lane == 0) red[vi & 1][warp] = m;
+      __syncthreads();
+      m = CTC_DEAD;
+      for (int w = 0; w < nwarps; ++w) m = fmaxf(m, red[vi & 1][w]);
+      if (m > CTC_DEAD_TEST) { p0 = fmaxf(p0 - m, CTC_DEAD); csum += (double)m; }   // rows already written keep their own offset
+      if (i == 0 && vi + 1 < nvis) issue(vi + 1);
+      if (producer) slot_publish(my_slot, p0, g - 1);            // carry-in of this visit, re-centred
+    }
+    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+    const int rows = rows_of(blk_of(vi));
+    const float* ep = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * Smax + sidx;
+    if (vi == 0) {                                               // first column
+      float v = CTC_DEAD, pre = CTC_DEAD;
+      if (has && i < 2) { v = *ep; pre = 0.f; }
+      if (has) *op = dir == 0 ? v : pre;
+      p0 = v;
+      if (producer) slot_publish(my_slot + 8, v, 0);
+      ep += estride;
+      pos = 1;
+      g = 1;
+    }
+    uint32_t rd = in_slot + (uint32_t)(pos * 8);                 // slot with the neighbour warp's previous step
+    uint32_t wr = my_slot + (uint32_t)((pos + 1) * 8);
+#pragma unroll 2
+    for (; pos < rows; ++pos) {
+      const float e = *ep;                                       // consumed last in the step: its latency hides behind the chain
+      ep += estride;
+      op += stride;
+      float a1 = __shfl_up_sync(0xffffffffu, p0, 1);
+      float a2 = __shfl_up_sync(0xffffffffu, p0, 2);
+      float x = CTC_DEAD;
+      if (warp > 0) x = slot_poll(rd, g - 1);
+      a1 = lane0 ? x : a1;
+      a2 = lane1 ? x : a2;
+      const float pre = lse3w(p0, a1, skip ? a2 : CTC_DEAD);
+      const float v = pre + e;
+      if (has) *op = dir == 0 ? v : pre;                         // beta leaves without its frame's emission
+      p0 = v;
+      if (producer) slot_publish(wr, v, g);
+      ++g; rd += 8; wr += 8;
+    }
+  }
+  if (dir == 0) {
+    if (has && i >= S - 2) fin[S - 1 - i] = p0;
+    __syncthreads();
+    if (i == 0) {
+      const float ll2 = lse3w(fin[0], fin[1], CTC_DEAD);
+      nll[b] = (ll2 < CTC_DEAD_TEST) ? INFINITY : (float)(-(csum + shift_sum + (double)ll2) * (double)LN2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+ctc_alpha_beta_wave_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
+                           const int64_t* __restrict__ targets, int64_t ldt,
+                           const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                           int Tn, int Smax, int EB, int64_t blank,
+                           float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
+  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB x Smax floats, then nwarps x (EB+1) 8-byte slots
+  if (blockIdx.y == 0) ctc_wave_body<0>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
+  else ctc_wave_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
 }
 
 // loss = reduction over utterances with zero_infinity
@@ -444,10 +664,10 @@ using namespace sc;
 extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                                 const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                                 const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
-                                int64_t blank, float* lse, float* lplat, void* stream) {
+                                int64_t blank, float* lse, float* lplat, float* cshift, void* stream) {
   SC_CHECK_ARG(B > 0 && T >= 0 && V > 0 && Umax >= 0 && blank >= 0 && blank < V, SC_E_BADARG);
   SC_CHECK_ARG(in_lens && tgt_lens && (Umax == 0 || targets), SC_E_BADARG);
-  SC_CHECK_ARG(T == 0 || (logits && lse && lplat), SC_E_BADARG);
+  SC_CHECK_ARG(T == 0 || (logits && lse && lplat && cshift), SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && V < (1 << 30) && Umax < (1 << 20), SC_E_SHAPE);
   SC_CHECK_ARG(dtype == SC_F32 || dtype == SC_BF16, SC_E_DTYPE);
   if (T == 0) return 0;
@@ -456,35 +676,70 @@ extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t st
   const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
   if (dtype == SC_F32)
     ctc_lse_gather_kernel<float><<<blocks, CTC_WARPS * 32, 0, st>>>((const float*)logits, stride_b, stride_t,
-        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat);
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat, cshift);
   else
     ctc_lse_gather_kernel<bf16><<<blocks, CTC_WARPS * 32, 0, st>>>((const bf16*)logits, stride_b, stride_t,
-        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat);
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat, cshift);
   SC_LAUNCH_RET();
 }
 
-extern "C" int sc_ctc_lattice(const float* lplat, const int64_t* targets, int64_t ldt,
+// Rows of emissions per block meeting of the wavefront kernel: as many as fit next to the
+// other CTAs that have to share an SM (2B CTAs over the device), at most 64.
+static int ctc_wave_rows(int Smax, int64_t B, int nwarps, size_t* smem_out) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int per_sm = (int)((2 * B + sms - 1) / sms);
+  if (per_sm > 8) per_sm = 8;
+  const size_t budget = (size_t)220 * 1024 / (size_t)per_sm - 2048;
+  int forced = 0;
+  if (const char* ev = getenv("SC_CTC_EB")) forced = atoi(ev);
+  for (int eb = 64; eb >= 4; eb >>= 1) {
+    if (forced > 0 && eb != forced) continue;
+    const size_t need = 2 * (size_t)eb * Smax * sizeof(float) + (size_t)nwarps * (eb + 1) * 8 + 16;
+    if (need <= budget || eb == 4 || forced > 0) { *smem_out = need; return eb; }
+  }
+  return 0;
+}
+
+extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int64_t* targets, int64_t ldt,
                               const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T,
                               int64_t Umax, int64_t blank, float* alpha, float* beta, float* nll,
                               float* loss, int reduction, void* stream) {
   SC_CHECK_ARG(B > 0 && T >= 0 && Umax >= 0 && blank >= 0, SC_E_BADARG);
   SC_CHECK_ARG(in_lens && tgt_lens && nll && (Umax == 0 || targets), SC_E_BADARG);
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2 && (reduction == 0 || loss), SC_E_BADARG);
-  SC_CHECK_ARG(T == 0 || (lplat && alpha && beta), SC_E_BADARG);
+  SC_CHECK_ARG(T == 0 || (lplat && cshift && alpha && beta), SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && Umax < (1 << 20), SC_E_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
   int threads = ((Smax + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  // two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
-  const size_t smem = (2 * (size_t)(Smax + 4) + (Smax <= 1024 ? 2 * (size_t)CTC_EB * Smax : 0)) * sizeof(float);
-  SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  bool wave = Smax <= 1024;                                      // SC_CTC_WAVE=0: the block-barrier kernel (A/B measurements)
+  if (const char* ev = getenv("SC_CTC_WAVE")) wave = wave && atoi(ev) != 0;
+  if (wave) {
+    size_t smem = 0;
+    const int eb = ctc_wave_rows(Smax, B, threads / 32, &smem);
+    SC_CHECK_ARG(eb > 0 && smem <= 220 * 1024, SC_E_SHAPE);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ctc_alpha_beta_wave_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
+        (int)T, Smax, eb, blank, alpha, beta, nll);
+  } else {
+    // two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
+    const size_t smem = (2 * (size_t)(Smax + 4) + (Smax <= 1024 ? 2 * (size_t)CTC_EB * Smax : 0)) * sizeof(float);
+    SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ctc_alpha_beta_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
+        (int)T, Smax, blank, alpha, beta, nll);
   }
-  ctc_alpha_beta_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, targets, ldt, in_lens, tgt_lens,
-      (int)T, Smax, blank, alpha, beta, nll);
   if (reduction != 0) ctc_reduce_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, (int)B, reduction, loss);
   SC_LAUNCH_RET();
 }
@@ -492,13 +747,13 @@ extern "C" int sc_ctc_lattice(const float* lplat, const int64_t* targets, int64_
 extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                           const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                           const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
-                          int64_t blank, float* lse, float* lplat, float* alpha, float* beta,
+                          int64_t blank, float* lse, float* lplat, float* cshift, float* alpha, float* beta,
                           float* nll, float* loss, int reduction, void* stream) {
   SC_CHECK_ARG(blank >= 0 && blank < V, SC_E_BADARG);
   const int rc = sc_ctc_emissions(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax,
-                                  blank, lse, lplat, stream);
+                                  blank, lse, lplat, cshift, stream);
   if (rc) return rc;
-  return sc_ctc_lattice(lplat, targets, ldt, in_lens, tgt_lens, B, T, Umax, blank, alpha, beta, nll, loss, reduction,
+  return sc_ctc_lattice(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, blank, alpha, beta, nll, loss, reduction,
                         stream);
 }
 

@@ -50,14 +50,15 @@ class _CTCFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         lse = torch.empty(B, max(T, 1), **f32)
         lplat = torch.empty(B, max(T, 1), S, **f32)
+        cshift = torch.empty(B, max(T, 1), **f32)
         alpha = torch.empty(B, max(T, 1), S, **f32)
         beta = torch.empty(B, max(T, 1), S, **f32)
         nll = torch.empty(B, **f32)
         loss = torch.zeros((), **f32)
         ldt = targets.stride(0) if targets.numel() else max(Umax, 1)
         call("sc_ctc_emissions", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
-             ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), stream())
-        call("sc_ctc_lattice", ptr(lplat), ptr(targets), ldt, ptr(in_lens), ptr(tgt_lens), B, T, Umax, blank,
+             ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), ptr(cshift), stream())
+        call("sc_ctc_lattice", ptr(lplat), ptr(cshift), ptr(targets), ldt, ptr(in_lens), ptr(tgt_lens), B, T, Umax, blank,
              ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, stream())
         ctx.save_for_backward(x, targets, in_lens, tgt_lens, lse, alpha, beta, nll)
         ctx.cfg = (blank, red, Umax, ldt)

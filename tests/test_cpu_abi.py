@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.sc_version() == 7
+    assert lib.sc_version() == 8
     assert b"BADARG" in lib.sc_error_string(-1)
     buf = __import__("ctypes").create_string_buffer(128)
     assert lib.sc_build_info(buf, 128) == 0 and b"sm_100a" in buf.value
@@ -39,7 +39,7 @@ def test_argument_errors_are_return_codes_not_crashes():
     lib = _lib.load()
     assert lib.sc_lucy_scan_fwd(None, 0, None, None, None, 0, None, None, None, 1, 1, 8, 0, 1, None) == -1
     assert lib.sc_gemm_fwd(None, 0, None, 0, None, None, 0, -1, 1, 1, 0, 0, 0, None) == -1
-    assert lib.sc_ctc_fwd(None, 0, 0, 0, None, 0, None, None, 0, 1, 1, 0, 0, None, None, None, None, None, None, 1, None) == -1
+    assert lib.sc_ctc_fwd(None, 0, 0, 0, None, 0, None, None, 0, 1, 1, 0, 0, None, None, None, None, None, None, None, 1, None) == -1
     assert lib.sc_cast(None, 0, 7, None, 0, 0, 0, 0, None) == 0          # empty problem is a no-op
 
 

@@ -423,18 +423,18 @@ def test_ctc_combined_entry_matches_split(cuda_device):
     outs = []
     for split in (False, True):
         f32 = dict(dtype=torch.float32, device="cuda")
-        lse, lplat = torch.zeros(B, T, **f32), torch.zeros(B, T, S, **f32)
+        lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, S, **f32), torch.zeros(B, T, **f32)
         alpha, beta = torch.zeros(B, T, S, **f32), torch.zeros(B, T, S, **f32)
         nll, loss = torch.zeros(B, **f32), torch.zeros((), **f32)
         if split:
             call("sc_ctc_emissions", ptr(x), x.stride(0), x.stride(1), dt(x), ptr(tok), tok.stride(0), ptr(il), ptr(tl),
-                 B, T, V, U, 0, ptr(lse), ptr(lplat), stream())
-            call("sc_ctc_lattice", ptr(lplat), ptr(tok), tok.stride(0), ptr(il), ptr(tl), B, T, U, 0,
+                 B, T, V, U, 0, ptr(lse), ptr(lplat), ptr(csh), stream())
+            call("sc_ctc_lattice", ptr(lplat), ptr(csh), ptr(tok), tok.stride(0), ptr(il), ptr(tl), B, T, U, 0,
                  ptr(alpha), ptr(beta), ptr(nll), ptr(loss), 1, stream())
         else:
             call("sc_ctc_fwd", ptr(x), x.stride(0), x.stride(1), dt(x), ptr(tok), tok.stride(0), ptr(il), ptr(tl),
-                 B, T, V, U, 0, ptr(lse), ptr(lplat), ptr(alpha), ptr(beta), ptr(nll), ptr(loss), 1, stream())
-        outs.append((lse, lplat, alpha, beta, nll, loss))
+                 B, T, V, U, 0, ptr(lse), ptr(lplat), ptr(csh), ptr(alpha), ptr(beta), ptr(nll), ptr(loss), 1, stream())
+        outs.append((lse, lplat, csh, alpha, beta, nll, loss))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
 
