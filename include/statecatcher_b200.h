@@ -279,6 +279,27 @@ int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
                  float beta2, float eps, float weight_decay, int64_t step, const double* sumsq,
                  float max_norm, int decoupled, void* stream);
 
+/* ---------------------------------------------------------------- frontend ------------
+ * Replaces make_frontend (model.py:250-279): torchaudio MFCC(n_mfcc=80, dct_type=2, norm='ortho',
+ * log_mels=True) / MelSpectrogram + AmplitudeToDB(top_db=80) with n_fft = win_length = 400,
+ * hop_length = 160, n_mels = 80, center=False, power=2, mel_scale='htk', followed by
+ * train.py:475's transpose: wav [B,S] fp32 (row stride ldw) -> out [B,T,80] fp32 (stream stride
+ * out_stride_b >= T*80), T = 1 + (S-400)/160 (nothing is written when S < 400).
+ * sc_frontend_tables fills a HOST buffer of sc_frontend_tables_len() floats (window, folded DFT
+ * bases, sparse mel bands, DCT; pure C, no CUDA call) which the caller uploads once and passes as
+ * `tables` (device).  mode 0 = mfcc; mode 1 = mel dB, gmax = device word receiving the batch
+ * maximum, top_db < 0 skips AmplitudeToDB's floor. */
+int64_t sc_frontend_tables_len(void);
+int sc_frontend_tables(float* host_out, int64_t n, int sample_rate);
+int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, const float* tables, int mode,
+                float top_db, float* out, int64_t out_stride_b, unsigned int* gmax, void* stream);
+/* compute_frame_mask (train.py:296-306) + the in_lens line (train.py:490), bit-exact:
+ * sample_mask [B,S] bytes (row stride ldm); frame_mask[b,t] = any(sample_mask[b, t*sub:(t+1)*sub])
+ * for t < T; in_lens[b] = (int64) min(float(sum_s sample_mask[b,s]) / subsample, nfeat) with the
+ * division in fp32.  Requires T*sub <= S (the caller enforces the reference's S_trim == T*sub). */
+int sc_frame_mask(const uint8_t* sample_mask, int64_t ldm, int64_t B, int64_t S, int64_t T, int64_t sub,
+                  float subsample, int64_t nfeat, uint8_t* frame_mask, int64_t* in_lens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,8 +60,13 @@ SIGNATURES = {
     "sc_sumsq_accum": [P, I64, P, P],
     "sc_scale_grads": [P, I64, P, F32, P],
     "sc_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P, F32, I32, P],
+    "sc_frontend_tables_len": [],
+    "sc_frontend_tables": [P, I64, I32],
+    "sc_frontend": [P, I64, I64, I64, P, I32, F32, P, I64, P, P],
+    "sc_frame_mask": [P, I64, I64, I64, I64, I64, F32, I64, P, P, P],
 }
-_RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64}
+_RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64,
+             "sc_frontend_tables_len": I64}
 
 _lib = None
 
@@ -130,7 +135,7 @@ KERNELS_PER_CALL = {
     "sc_layernorm_fwd": 1, "sc_layernorm_bwd": 1, "sc_lucy_scan_fwd": 1, "sc_lucy_scan_fwd_chunked": 3, "sc_lucy_scan_bwd": 1,
     "sc_lucy_sscan_fwd": 1, "sc_lucy_sscan_bwd": 1, "sc_lucy_hscan_fwd": 1, "sc_lucy_hscan_bwd": 1,
     "sc_ctc_fwd": 3, "sc_ctc_emissions": 1, "sc_ctc_lattice": 2, "sc_ctc_bwd": 1, "sc_rnnt_fwd": 2, "sc_rnnt_bwd": 2, "sc_split_bf16": 1, "sc_joint_fwd": 1, "sc_joint_bwd": 2, "sc_rnnt_lse_gather": 1, "sc_rnnt_lattice": 1,
-    "sc_rnnt_node_grads": 1, "sc_rnnt_dlogits": 1, "sc_ctc_greedy_decode": 2,
+    "sc_rnnt_node_grads": 1, "sc_rnnt_dlogits": 1, "sc_ctc_greedy_decode": 2, "sc_frontend": 1, "sc_frame_mask": 1,
 }
 _ESZ = {SC_F32: 4, SC_BF16: 2}
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libstatecatcher_b200.so")
 SOURCES = ["sc_api.cu", "sc_scan.cu", "sc_scan_tma.cu", "sc_scan_chunked.cu", "sc_ctc.cu", "sc_gemm_simt.cu", "sc_gemm_tcgen05.cu",
-           "sc_rowops.cu", "sc_rnnt.cu", "sc_decode.cu", "sc_optim.cu"]
+           "sc_rowops.cu", "sc_rnnt.cu", "sc_decode.cu", "sc_optim.cu", "sc_frontend.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

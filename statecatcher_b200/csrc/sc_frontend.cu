@@ -1,0 +1,332 @@
+// Frontend: the step in front of the hot path.
+//
+// Replaces make_frontend (model.py:250-279) — torchaudio MFCC(n_mfcc=80, dct ortho, log_mels) or
+// MelSpectrogram + AmplitudeToDB(top_db=80) with n_fft = win = 400, hop = 160, 80 htk mel bands,
+// center=False, power 2 — together with train.py:473-475's transpose to (B, T, 80), and
+// compute_frame_mask + the in_lens line (train.py:296-306, 486-490).
+//
+// One fused kernel per segment batch, one CTA per 32 consecutive frames of a stream:
+//   samples -> shared memory (each sample is read from HBM once although frames overlap 2.5x)
+//   -> Hann window and TWO radix-2 folds of the real 400-point DFT (x[n] with x[400-n], then
+//      n with 200-n): four dense ~100x100 real transforms instead of a 400x402 one, 40.6 k MAC
+//      per frame instead of 160.8 k, fp32 FMA with 16 frames x 4 bins of accumulators per thread
+//   -> |X|^2 -> 80 triangular mel bands (sparse: a band touches <= 32 bins) -> log
+//   -> 80x80 DCT-II (mfcc) or 10 log10 + batch maximum (mel) -> (B, T, 80) fp32.
+// The spectrogram, the mel spectrogram and the (B, 80, T) tensor torchaudio materialises never
+// reach HBM: algorithmic bytes per frame = 160 samples x 4 B in + 80 x 4 B out = 960 B.
+// Tensor cores are deliberately not used: the power spectrum of speech spans > 60 dB inside one
+// frame and bf16/tf32 operands would put the weak bins' error at 1e-2 of their value.
+#include "sc_common.cuh"
+
+#include <math.h>
+
+namespace sc {
+
+constexpr int FE_NFFT = 400, FE_HOP = 160, FE_NMEL = 80, FE_NMFCC = 80, FE_NFREQ = 201;
+constexpr int FE_FT = 32;              // frames per CTA
+constexpr int FE_NB = 104;             // padded size of one folded transform (101 rounded up to a multiple of 8)
+constexpr int FE_MAXW = 32;            // bins per mel band (at most)
+constexpr int FE_PW = 208;             // row pitch of the power spectrum in shared memory
+// table layout (floats)
+constexpr int FE_OFF_WIN = 0;
+constexpr int FE_OFF_BAS = 400;                                  // [4][104][104]
+constexpr int FE_OFF_MELW = FE_OFF_BAS + 4 * FE_NB * FE_NB;      // [80][32]
+constexpr int FE_OFF_MELLO = FE_OFF_MELW + FE_NMEL * FE_MAXW;    // [80] int: first bin
+constexpr int FE_OFF_MELCNT = FE_OFF_MELLO + FE_NMEL;            // [80] int: number of bins
+constexpr int FE_OFF_DCT = FE_OFF_MELCNT + FE_NMEL;              // [80][80]
+constexpr int FE_TABLE_LEN = FE_OFF_DCT + FE_NMEL * FE_NMFCC;
+constexpr int FE_XS = (FE_FT - 1) * FE_HOP + FE_NFFT;            // samples one CTA needs
+
+__device__ __forceinline__ unsigned enc_ordered(float f) {      // monotone float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// mode 0: mfcc; mode 1: mel dB before the top_db floor (batch maximum -> gmax, ordered encoding)
+__global__ void __launch_bounds__(256, 2)
+frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
+                const float* __restrict__ tab, int mode,
+                float* __restrict__ out, int64_t out_stride_b, unsigned* __restrict__ gmax) {
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;                                   // [FE_XS] samples, later the log-mel rows [32][80]
+  float* V = sm + ((FE_XS + 3) & ~3);               // [4][104][32] folded inputs, later the power spectrum [32][208]
+  const int b = blockIdx.y, t0 = blockIdx.x * FE_FT, tid = threadIdx.x;
+  const int nf = min(FE_FT, T - t0);                // live frames of this tile
+  const float* w_b = wav + (int64_t)b * ldw;
+  const int s0 = t0 * FE_HOP;
+  for (int i = tid; i < FE_XS; i += 256) xs[i] = (s0 + i < S) ? __ldg(w_b + s0 + i) : 0.f;
+  __syncthreads();
+  // ---- window + two folds ------------------------------------------------------------
+  const float* win = tab + FE_OFF_WIN;
+  for (int idx = tid; idx < FE_FT * FE_NB; idx += 256) {
+    const int f = idx & (FE_FT - 1), n = idx >> 5;  // f fastest: conflict-free stores
+    const float* x = xs + f * FE_HOP;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    if (n == 0) {
+      const float a0 = x[0] * __ldg(win), a2 = x[200] * __ldg(win + 200);
+      v0 = a0 + a2; v1 = a0 - a2;
+    } else if (n < 100) {
+      const float a = x[n] * __ldg(win + n), ar = x[400 - n] * __ldg(win + 400 - n);
+      const float c = x[200 - n] * __ldg(win + 200 - n), cr = x[200 + n] * __ldg(win + 200 + n);
+      const float e1 = a + ar, e2 = c + cr, o1 = a - ar, o2 = c - cr;
+      v0 = e1 + e2; v1 = e1 - e2; v2 = o1 - o2; v3 = o1 + o2;
+    } else if (n == 100) {
+      const float a = x[100] * __ldg(win + 100), ar = x[300] * __ldg(win + 300);
+      v0 = a + ar; v3 = a - ar;
+    }
+    V[(0 * FE_NB + n) * FE_FT + f] = v0;
+    V[(1 * FE_NB + n) * FE_FT + f] = v1;
+    V[(2 * FE_NB + n) * FE_FT + f] = v2;
+    V[(3 * FE_NB + n) * FE_FT + f] = v3;
+  }
+  __syncthreads();
+  // ---- four 104x104 transforms: warp pair q, thread = 4 bins x 16 frames ---------------
+  const int q = tid >> 6, r = tid & 63;
+  const int kg = r % 26, fg = r / 26;               // r < 52 active
+  const bool active = r < 52;
+  float acc[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  if (active) {
+    const float4* bas = reinterpret_cast<const float4*>(tab + FE_OFF_BAS + (size_t)q * FE_NB * FE_NB) + kg;
+    const float4* vq = reinterpret_cast<const float4*>(V + (size_t)q * FE_NB * FE_FT + fg * 16);
+#pragma unroll 2
+    for (int n = 0; n < FE_NB; ++n) {
+      const float4 bv = __ldg(bas + n * (FE_NB / 4));
+      float xv[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t4 = vq[n * (FE_FT / 4) + j];
+        xv[4 * j] = t4.x; xv[4 * j + 1] = t4.y; xv[4 * j + 2] = t4.z; xv[4 * j + 3] = t4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        acc[i][0] = fmaf(xv[i], bv.x, acc[i][0]);
+        acc[i][1] = fmaf(xv[i], bv.y, acc[i][1]);
+        acc[i][2] = fmaf(xv[i], bv.z, acc[i][2]);
+        acc[i][3] = fmaf(xv[i], bv.w, acc[i][3]);
+      }
+    }
+  }
+  __syncthreads();                                  // V is dead: its space becomes the power spectrum
+  float* P = V;
+  if (active && q < 2) {                            // real parts: q0 -> even bins, q1 -> odd bins
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = 2 * (4 * kg + c) + q;
+      if (k < FE_NFREQ) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[(fg * 16 + i) * FE_PW + k] = acc[i][c];
+      }
+    }
+  }
+  __syncthreads();
+  if (active && q >= 2) {                           // imaginary parts complete |X|^2
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = 2 * (4 * kg + c) + (q - 2);
+      if (k < FE_NFREQ) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float* p = P + (fg * 16 + i) * FE_PW + k;
+          const float re = *p;
+          *p = fmaf(re, re, acc[i][c] * acc[i][c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- mel bands + log ---------------------------------------------------------------
+  float* L = xs;                                    // [32][80]
+  const float* melw = tab + FE_OFF_MELW;
+  const int* mello = reinterpret_cast<const int*>(tab + FE_OFF_MELLO);
+  const int* melcnt = reinterpret_cast<const int*>(tab + FE_OFF_MELCNT);
+  float lmax = -INFINITY;
+  for (int idx = tid; idx < FE_FT * FE_NMEL; idx += 256) {
+    const int f = idx / FE_NMEL, m = idx - f * FE_NMEL;
+    const int lo = __ldg(mello + m), cnt = __ldg(melcnt + m);
+    const float* p = P + f * FE_PW + lo;
+    float acc_m = 0.f;
+    for (int i = 0; i < cnt; ++i) acc_m = fmaf(p[i], __ldg(melw + m * FE_MAXW + i), acc_m);
+    float v;
+    if (mode == 0) v = logf(acc_m + 1e-6f);
+    else { v = 10.f * log10f(fmaxf(acc_m, 1e-10f)); if (f < nf) lmax = fmaxf(lmax, v); }
+    L[idx] = v;
+  }
+  __syncthreads();
+  float* o_b = out + (int64_t)b * out_stride_b + (int64_t)t0 * FE_NMFCC;
+  if (mode == 0) {
+    // ---- DCT-II: thread = coefficient c, frames fgroup, fgroup+3, ... ------------------
+    const int c = tid % FE_NMFCC, f0 = tid / FE_NMFCC;           // 240 threads busy
+    if (f0 < 3) {
+      const float* dct = tab + FE_OFF_DCT + c;
+      float a[11];
+#pragma unroll
+      for (int j = 0; j < 11; ++j) a[j] = 0.f;
+      for (int m = 0; m < FE_NMEL; ++m) {
+        const float d = __ldg(dct + m * FE_NMFCC);
+#pragma unroll
+        for (int j = 0; j < 11; ++j) {
+          const int f = f0 + 3 * j;
+          a[j] = fmaf(L[(f < FE_FT ? f : 0) * FE_NMEL + m], d, a[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const int f = f0 + 3 * j;
+        if (f < nf) o_b[f * FE_NMFCC + c] = a[j];
+      }
+    }
+  } else {
+    for (int idx = tid; idx < nf * FE_NMEL; idx += 256) o_b[idx] = L[idx];
+    lmax = warp_max(lmax);
+    if ((tid & 31) == 0 && lmax > -INFINITY) atomicMax(gmax, enc_ordered(lmax));
+  }
+}
+
+// AmplitudeToDB's top_db: x = max(x, batch_max - top_db)
+__global__ void db_floor_kernel(float* __restrict__ x, int64_t n, const unsigned* __restrict__ gmax, float top_db) {
+  const float floor_v = dec_ordered(*gmax) - top_db;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = fmaxf(x[i], floor_v);
+}
+
+// compute_frame_mask + in_lens: one block per stream, one warp per frame in turn
+__global__ void __launch_bounds__(1024)
+frame_mask_kernel(const uint8_t* __restrict__ mask, int64_t ldm, int S, int T, int sub, float subsample, int nfeat,
+                  uint8_t* __restrict__ frame_mask, int64_t* __restrict__ in_lens) {
+  __shared__ int total;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const uint8_t* m = mask + (int64_t)b * ldm;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int t = warp; t < T; t += nw) {
+    int c = 0;
+    for (int i = lane; i < sub; i += 32) c += m[(int64_t)t * sub + i] != 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) { frame_mask[(int64_t)b * T + t] = c > 0; cnt += c; }
+  }
+  // samples past T*sub count for in_lens but belong to no frame
+  for (int64_t i = (int64_t)T * sub + threadIdx.x; i < S; i += blockDim.x) cnt += m[i] != 0;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0 && cnt) atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // (mask.sum(1) / subsample).clamp(max=nfeat).long() with the division in fp32 as torch does
+    const float qv = fminf(__fdiv_rn((float)total, subsample), (float)nfeat);
+    in_lens[b] = (int64_t)qv;
+  }
+}
+
+}  // namespace sc
+
+using namespace sc;
+
+extern "C" int64_t sc_frontend_tables_len(void) { return FE_TABLE_LEN; }
+
+// Host-side (no CUDA): window, folded DFT bases, sparse mel bands and the DCT matrix, computed in
+// double and rounded to fp32.  The caller uploads the buffer once and passes it to sc_frontend.
+extern "C" int sc_frontend_tables(float* out, int64_t n, int sample_rate) {
+  SC_CHECK_ARG(out && n >= FE_TABLE_LEN && sample_rate >= 2, SC_E_BADARG);
+  const double PI = 3.14159265358979323846;
+  for (int64_t i = 0; i < FE_TABLE_LEN; ++i) out[i] = 0.f;
+  for (int i = 0; i < FE_NFFT; ++i) out[FE_OFF_WIN + i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / FE_NFFT));
+  // bases: angle 2*pi*k*n/400 reduced exactly in integers before the trig call
+  auto ang = [&](int k, int nn) { return 2.0 * PI * (double)((k * nn) % FE_NFFT) / FE_NFFT; };
+  for (int nn = 0; nn <= 100; ++nn) {
+    for (int j = 0; j <= 100; ++j) {
+      float* b0 = out + FE_OFF_BAS + (0 * FE_NB + nn) * FE_NB + j;
+      float* b1 = out + FE_OFF_BAS + (1 * FE_NB + nn) * FE_NB + j;
+      float* b2 = out + FE_OFF_BAS + (2 * FE_NB + nn) * FE_NB + j;
+      float* b3 = out + FE_OFF_BAS + (3 * FE_NB + nn) * FE_NB + j;
+      *b0 = (float)cos(ang(2 * j, nn));                                   // Re, even bins k = 2j, n = 0..100
+      if (nn < 100 && j < 100) *b1 = (float)cos(ang(2 * j + 1, nn));      // Re, odd bins, n = 0..99
+      if (nn >= 1 && nn < 100 && j >= 1 && j < 100) *b2 = (float)(-sin(ang(2 * j, nn)));   // Im, even bins, n = 1..99
+      if (nn >= 1 && j < 100) *b3 = (float)(-sin(ang(2 * j + 1, nn)));    // Im, odd bins, n = 1..100
+    }
+  }
+  // htk mel bands (torchaudio.functional.melscale_fbanks, norm=None), kept sparse
+  const double f_max = (double)(sample_rate / 2);
+  const double m_max = 2595.0 * log10(1.0 + f_max / 700.0);
+  double f_pts[FE_NMEL + 2];
+  for (int i = 0; i < FE_NMEL + 2; ++i) f_pts[i] = 700.0 * (pow(10.0, (m_max * i / (FE_NMEL + 1)) / 2595.0) - 1.0);
+  int* lo_t = reinterpret_cast<int*>(out + FE_OFF_MELLO);
+  int* cnt_t = reinterpret_cast<int*>(out + FE_OFF_MELCNT);
+  for (int m = 0; m < FE_NMEL; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < FE_NFREQ; ++k) {
+      const double fr = (double)(sample_rate / 2) * k / (FE_NFREQ - 1);
+      const double down = (fr - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+      const double up = (f_pts[m + 2] - fr) / (f_pts[m + 2] - f_pts[m + 1]);
+      const double wv = fmax(0.0, fmin(down, up));
+      if (wv > 0.0) {
+        if (lo < 0) lo = k;
+        hi = k;
+      }
+    }
+    const int cnt = lo < 0 ? 0 : hi - lo + 1;
+    if (cnt > FE_MAXW) return SC_E_SHAPE;
+    lo_t[m] = lo < 0 ? 0 : lo;
+    cnt_t[m] = cnt;
+    for (int i = 0; i < cnt; ++i) {
+      const double fr = (double)(sample_rate / 2) * (lo + i) / (FE_NFREQ - 1);
+      const double down = (fr - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+      const double up = (f_pts[m + 2] - fr) / (f_pts[m + 2] - f_pts[m + 1]);
+      out[FE_OFF_MELW + m * FE_MAXW + i] = (float)fmax(0.0, fmin(down, up));
+    }
+  }
+  // DCT-II, ortho (torchaudio.functional.create_dct): D[m][c]
+  for (int m = 0; m < FE_NMEL; ++m)
+    for (int c = 0; c < FE_NMFCC; ++c) {
+      double d = cos(PI / FE_NMEL * (m + 0.5) * c) * sqrt(2.0 / FE_NMEL);
+      if (c == 0) d *= 1.0 / sqrt(2.0);
+      out[FE_OFF_DCT + m * FE_NMFCC + c] = (float)d;
+    }
+  return 0;
+}
+
+extern "C" int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, const float* tables, int mode,
+                           float top_db, float* out, int64_t out_stride_b, unsigned int* gmax, void* stream) {
+  SC_CHECK_ARG(B > 0 && S >= 0 && (mode == 0 || mode == 1), SC_E_BADARG);
+  SC_CHECK_ARG(S < ((int64_t)1 << 31) && B < 65536, SC_E_SHAPE);
+  if (S < FE_NFFT) return 0;                                     // no frame fits
+  SC_CHECK_ARG(wav && tables && out && (mode == 0 || gmax), SC_E_BADARG);
+  const int T = 1 + (int)((S - FE_NFFT) / FE_HOP);
+  SC_CHECK_ARG(out_stride_b >= (int64_t)T * FE_NMFCC && ldw >= S, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (((FE_XS + 3) & ~3) + 4 * FE_NB * FE_FT) * sizeof(float);
+  static_assert(4 * FE_NB * FE_FT >= FE_FT * FE_PW, "power spectrum must fit in the folded-input space");
+  static_assert(FE_XS >= FE_FT * FE_NMEL, "log-mel rows must fit in the sample space");
+  cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if (mode == 1) {
+    e = cudaMemsetAsync(gmax, 0, sizeof(unsigned), st);           // ordered encoding: 0 is below every float
+    if (e != cudaSuccess) return (int)e;
+  }
+  frontend_kernel<<<dim3((unsigned)cdiv(T, FE_FT), (unsigned)B), 256, smem, st>>>(wav, ldw, (int)S, T, tables, mode, out,
+                                                                                   out_stride_b, gmax);
+  if (mode == 1 && top_db >= 0.f) {
+    // out rows are dense per stream only when out_stride_b == T*80; floor stream by stream otherwise
+    if (out_stride_b == (int64_t)T * FE_NMFCC) {
+      db_floor_kernel<<<592, 256, 0, st>>>(out, B * (int64_t)T * FE_NMFCC, gmax, top_db);
+    } else {
+      for (int64_t b = 0; b < B; ++b)
+        db_floor_kernel<<<32, 256, 0, st>>>(out + b * out_stride_b, (int64_t)T * FE_NMFCC, gmax, top_db);
+    }
+  }
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_frame_mask(const uint8_t* sample_mask, int64_t ldm, int64_t B, int64_t S, int64_t T, int64_t sub,
+                             float subsample, int64_t nfeat, uint8_t* frame_mask, int64_t* in_lens, void* stream) {
+  SC_CHECK_ARG(B > 0 && S > 0 && T > 0 && sub > 0 && nfeat >= 0 && subsample > 0.f, SC_E_BADARG);
+  SC_CHECK_ARG(sample_mask && frame_mask && in_lens && ldm >= S, SC_E_BADARG);
+  SC_CHECK_ARG(S < ((int64_t)1 << 31) && T * sub <= S, SC_E_SHAPE);
+  frame_mask_kernel<<<(unsigned)B, 1024, 0, (cudaStream_t)stream>>>(sample_mask, ldm, (int)S, (int)T, (int)sub, subsample,
+                                                                    (int)nfeat, frame_mask, in_lens);
+  SC_LAUNCH_RET();
+}
