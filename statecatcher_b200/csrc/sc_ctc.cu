@@ -489,6 +489,157 @@ ctc_alpha_beta_wave_kernel(const float* __restrict__ lplat, const float* __restr
   else ctc_wave_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
 }
 
+// ---- pass 2, wavefront variant with a (blank, label) PAIR per thread --------------------------
+// Thread i owns blank node 2i and label node 2i+1 (alpha; mirrored node numbering for beta).
+// The label looks at its own blank (same thread), so ONE shuffle per step — the previous thread's
+// label — feeds both nodes; the two log-sum-exps are independent and interleave in the pipeline,
+// and a 301-node lattice is 5 warps instead of 10: half the instructions per node and at most two
+// warps per scheduler.
+__device__ __forceinline__ float lse2w(float a, float b) {
+  const float m = fmaxf(a, b), lo = fminf(a, b);
+  return m + lg2f(1.f + ex2f(lo - m));
+}
+
+template <int dir>
+__device__ __forceinline__ void
+ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const float* __restrict__ cshift,
+               const int64_t* __restrict__ targets, int64_t ldt,
+               const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+               int Tn, int Smax, int EB, int64_t blank,
+               float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
+  __shared__ float red[2][32];
+  __shared__ double dred[32];
+  __shared__ float fin[2];
+  __shared__ __align__(8) uint64_t ebar[2];
+  const int b = blockIdx.x;
+  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64;
+  const int U = (int)tgt_lens[b];
+  const int64_t* tg = targets + (int64_t)b * ldt;
+  if (Tb <= 0) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
+    return;
+  }
+  const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
+  const int nwarps = (int)(blockDim.x >> 5);
+  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
+  float* ebuf = sm;
+  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * Smax);   // [nwarps][EB+1] x {value, tag}
+  for (int k = i; k < nwarps * (EB + 1) * 2; k += blockDim.x) slots[k] = -1;
+  if (i == 0) {
+    fin[0] = CTC_DEAD; fin[1] = CTC_DEAD;
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool hasb = i <= U, hasl = i < U;
+  // memory positions of this thread's blank and label node
+  const int sb = hasb ? (dir == 0 ? 2 * i : 2 * U - 2 * i) : 0;
+  const int sl = hasl ? (dir == 0 ? 2 * i + 1 : 2 * U - 2 * i - 1) : 0;
+  bool skip = false;                                             // label may also come from the previous thread's label
+  if (hasl) {
+    if (dir == 0) skip = i >= 1 && tg[i] != tg[i - 1];
+    else { const int u = U - 1 - i; skip = u + 1 < U && tg[u] != tg[u + 1]; }
+  }
+  const bool producer = lane == 31 && warp + 1 < nwarps;
+  const bool lane0 = lane == 0;
+  const uint32_t my_slot = smem_u32(slots) + (uint32_t)(warp * (EB + 1) * 8);
+  const uint32_t in_slot = smem_u32(slots) + (uint32_t)((warp > 0 ? warp - 1 : 0) * (EB + 1) * 8);
+  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
+  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
+  const int nvis = (Tb + EB - 1) / EB;
+  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
+  auto rows_of = [&](int blk) { const int r = Tb - blk * EB; return r < EB ? r : EB; };
+  auto issue = [&](int vi) {
+    const int blk = blk_of(vi);
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
+    const uint32_t bar = smem_u32(&ebar[vi & 1]);
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * Smax), lp_b + (int64_t)blk * EB * Smax, bytes, bar);
+  };
+  if (i == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  const int t_first = dir == 0 ? 0 : Tb - 1;
+  const int64_t stride = dir == 0 ? (int64_t)Smax : -(int64_t)Smax;
+  const int estride = dir == 0 ? Smax : -Smax;
+  float* opb = out_b + (int64_t)t_first * Smax + sb;
+  float* opl = out_b + (int64_t)t_first * Smax + sl;
+  double csum = 0.0;
+  float pb = CTC_DEAD, pl = CTC_DEAD;                            // the pair's values after the last step
+  int g = 0;
+  for (int vi = 0; vi < nvis; ++vi) {
+    int pos = 0;
+    if (vi > 0) {
+      float m = warp_max(hasb ? fmaxf(pb, pl) : CTC_DEAD);
+      if (lane == 0) red[vi & 1][warp] = m;
+      __syncthreads();
+      m = CTC_DEAD;
+      for (int w = 0; w < nwarps; ++w) m = fmaxf(m, red[vi & 1][w]);
+      if (m > CTC_DEAD_TEST) { pb = fmaxf(pb - m, CTC_DEAD); pl = fmaxf(pl - m, CTC_DEAD); csum += (double)m; }
+      if (i == 0 && vi + 1 < nvis) issue(vi + 1);
+      if (producer) slot_publish(my_slot, pl, g - 1);
+    }
+    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+    const int rows = rows_of(blk_of(vi));
+    const float* erow = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * Smax;
+    const float* epb = erow + sb;
+    const float* epl = erow + sl;
+    if (vi == 0) {                                               // first column: nodes 0 and 1 of the scan order
+      if (i == 0) { pb = *epb; pl = hasl ? *epl : CTC_DEAD; }
+      if (hasb) *opb = dir == 0 ? pb : (i == 0 ? 0.f : CTC_DEAD);
+      if (hasl) *opl = dir == 0 ? pl : (i == 0 ? 0.f : CTC_DEAD);
+      if (producer) slot_publish(my_slot + 8, pl, 0);
+      epb += estride; epl += estride;
+      pos = 1;
+      g = 1;
+    }
+    uint32_t rd = in_slot + (uint32_t)(pos * 8);
+    uint32_t wr = my_slot + (uint32_t)((pos + 1) * 8);
+#pragma unroll 2
+    for (; pos < rows; ++pos) {
+      const float eb = *epb;
+      const float el = hasl ? *epl : CTC_DEAD;                   // a missing label node stays dead
+      epb += estride; epl += estride;
+      opb += stride; opl += stride;
+      float xl = __shfl_up_sync(0xffffffffu, pl, 1);
+      float x = CTC_DEAD;
+      if (warp > 0) x = slot_poll(rd, g - 1);
+      xl = lane0 ? x : xl;
+      const float preb = lse2w(pb, xl);
+      const float prel = lse3w(pl, pb, skip ? xl : CTC_DEAD);
+      pb = preb + eb;
+      pl = prel + el;
+      if (hasb) *opb = dir == 0 ? pb : preb;                     // beta leaves without its frame's emission
+      if (hasl) *opl = dir == 0 ? pl : prel;
+      if (producer) slot_publish(wr, pl, g);
+      ++g; rd += 8; wr += 8;
+    }
+  }
+  if (dir == 0) {
+    if (i == U) fin[0] = pb;
+    if (i == U - 1) fin[1] = pl;
+    __syncthreads();
+    if (i == 0) {
+      const float ll2 = lse2w(fin[0], fin[1]);
+      nll[b] = (ll2 < CTC_DEAD_TEST) ? INFINITY : (float)(-(csum + shift_sum + (double)ll2) * (double)LN2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512, 1)
+ctc_alpha_beta_wave2_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
+                            const int64_t* __restrict__ targets, int64_t ldt,
+                            const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                            int Tn, int Smax, int EB, int64_t blank,
+                            float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
+  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB x Smax floats, then nwarps x (EB+1) 8-byte slots
+  if (blockIdx.y == 0) ctc_wave2_body<0>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
+  else ctc_wave2_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
+}
+
 // loss = reduction over utterances with zero_infinity
 __global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* __restrict__ tgt_lens,
                                   int B, int reduction, float* __restrict__ loss) {
@@ -717,17 +868,19 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
   int threads = ((Smax + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  bool wave = Smax <= 1024;                                      // SC_CTC_WAVE=0: the block-barrier kernel (A/B measurements)
-  if (const char* ev = getenv("SC_CTC_WAVE")) wave = wave && atoi(ev) != 0;
+  int wave = Smax <= 1024 ? 2 : 0;                               // SC_CTC_WAVE: 0 block-barrier kernel, 1 node per thread, 2 pair per thread
+  if (const char* ev = getenv("SC_CTC_WAVE")) { const int w = atoi(ev); if (w >= 0 && w < wave) wave = w; }
   if (wave) {
+    const int wthreads = wave == 2 ? (((int)Umax + 1 + 31) / 32) * 32 : threads;
     size_t smem = 0;
-    const int eb = ctc_wave_rows(Smax, B, threads / 32, &smem);
+    const int eb = ctc_wave_rows(Smax, B, wthreads / 32, &smem);
     SC_CHECK_ARG(eb > 0 && smem <= 220 * 1024, SC_E_SHAPE);
+    auto kern = wave == 2 ? ctc_alpha_beta_wave2_kernel : ctc_alpha_beta_wave_kernel;
     if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    ctc_alpha_beta_wave_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
+    kern<<<dim3((unsigned)B, 2), wthreads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
         (int)T, Smax, eb, blank, alpha, beta, nll);
   } else {
     // two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
