@@ -351,11 +351,17 @@ def main():
     _lib.kernels = 0
     _lib.profile = []
     ms = timed(step_resident, args.steps)
-    host_enqueue_ms = host["ms"]
     prof, _lib.profile = _lib.profile, None
     launches = _lib.kernels
     clocks = sampler.stop() if rank == 0 else None
     value = frames_step * world * args.steps / (ms * 1e-3)
+    # host cost of ENQUEUEING one step, measured on an empty launch queue (inside the timed loop the
+    # host runs ahead until the queue is full and then advances at the GPU's pace, which says nothing)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_resident(0)
+    host_enqueue_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
 
     # ---- end-to-end through the public API with host buffers ----
     for i in range(2):
