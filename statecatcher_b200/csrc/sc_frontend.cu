@@ -17,6 +17,7 @@
 // Tensor cores are deliberately not used: the power spectrum of speech spans > 60 dB inside one
 // frame and bf16/tf32 operands would put the weak bins' error at 1e-2 of their value.
 #include "sc_common.cuh"
+#include "sc_tma.cuh"
 
 #include <math.h>
 
@@ -24,12 +25,14 @@ namespace sc {
 
 constexpr int FE_NFFT = 400, FE_HOP = 160, FE_NMEL = 80, FE_NMFCC = 80, FE_NFREQ = 201;
 constexpr int FE_FT = 32;              // frames per CTA
+constexpr int FE_THREADS = 224;        // 7 warps: 4 transforms x 52 threads do the DFT stage, all 224 the rest
 constexpr int FE_NB = 104;             // padded size of one folded transform (101 rounded up to a multiple of 8)
 constexpr int FE_MAXW = 32;            // bins per mel band (at most)
-constexpr int FE_PW = 208;             // row pitch of the power spectrum in shared memory
+constexpr int FE_VP = 36;              // row pitch (frames) of the folded inputs / power spectrum: 16-byte rows, 4-way instead of 32-way conflicts on the fold's stores
+constexpr int FE_STAGE = 4 * 8 * FE_NB; // floats per basis stage: 8 rows of each of the 4 transforms
 // table layout (floats)
 constexpr int FE_OFF_WIN = 0;
-constexpr int FE_OFF_BAS = 400;                                  // [4][104][104]
+constexpr int FE_OFF_BAS = 400;                                  // [13 stages][4 transforms][8 rows][104 bins]
 constexpr int FE_OFF_MELW = FE_OFF_BAS + 4 * FE_NB * FE_NB;      // [80][32]
 constexpr int FE_OFF_MELLO = FE_OFF_MELW + FE_NMEL * FE_MAXW;    // [80] int: first bin
 constexpr int FE_OFF_MELCNT = FE_OFF_MELLO + FE_NMEL;            // [80] int: number of bins
@@ -46,23 +49,41 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 }
 
 // mode 0: mfcc; mode 1: mel dB before the top_db floor (batch maximum -> gmax, ordered encoding)
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(FE_THREADS, 2)
 frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
                 const float* __restrict__ tab, int mode,
                 float* __restrict__ out, int64_t out_stride_b, unsigned* __restrict__ gmax) {
-  extern __shared__ __align__(16) float sm[];
-  float* xs = sm;                                   // [FE_XS] samples, later the log-mel rows [32][80]
-  float* V = sm + ((FE_XS + 3) & ~3);               // [4][104][32] folded inputs, later the power spectrum [32][208]
-  const int b = blockIdx.y, t0 = blockIdx.x * FE_FT, tid = threadIdx.x;
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) uint64_t bbar[2];
+  float* xs = sm;                                   // [FE_XS] samples; later the log-mel rows L[80][32]
+  float* V = sm + FE_XS;                            // [4][104][36] folded inputs; later the power spectrum P[2][104][36]
+  float* BS = V + 4 * FE_NB * FE_VP;                // 2 stages x [4][8][104] basis rows
+  const int b = blockIdx.y, t0 = blockIdx.x * FE_FT, tid = threadIdx.x, lane = tid & 31;
   const int nf = min(FE_FT, T - t0);                // live frames of this tile
+  // the folded DFT bases (173 KB) stream through shared memory in 13 stages of 8 rows x 4
+  // transforms (one 13 KB bulk copy each, double-buffered): read from L2 once per CTA with the
+  // latency off the multiply-add loop
+  auto issue = [&](int st) {
+    const uint32_t bar = smem_u32(&bbar[st & 1]);
+    mbar_expect_tx(bar, FE_STAGE * 4u);
+    bulk_load_1d(smem_u32(BS + (st & 1) * FE_STAGE), tab + FE_OFF_BAS + (size_t)st * FE_STAGE, FE_STAGE * 4u, bar);
+  };
+  if (tid == 0) {
+    mbar_init(smem_u32(&bbar[0]), 1);
+    mbar_init(smem_u32(&bbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue(0);
+    issue(1);
+  }
   const float* w_b = wav + (int64_t)b * ldw;
   const int s0 = t0 * FE_HOP;
-  for (int i = tid; i < FE_XS; i += 256) xs[i] = (s0 + i < S) ? __ldg(w_b + s0 + i) : 0.f;
+  for (int i = tid; i < FE_XS; i += FE_THREADS) xs[i] = (s0 + i < S) ? __ldg(w_b + s0 + i) : 0.f;
   __syncthreads();
-  // ---- window + two folds ------------------------------------------------------------
+  // ---- window + two folds.  A warp takes 32 consecutive n of one frame: frames start 160
+  // floats apart (a multiple of the 32 banks), so lanes must differ in n, not in the frame --------
   const float* win = tab + FE_OFF_WIN;
-  for (int idx = tid; idx < FE_FT * FE_NB; idx += 256) {
-    const int f = idx & (FE_FT - 1), n = idx >> 5;  // f fastest: conflict-free stores
+  for (int idx = tid; idx < FE_FT * FE_NB; idx += FE_THREADS) {
+    const int f = idx / FE_NB, n = idx - f * FE_NB;
     const float* x = xs + f * FE_HOP;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
     if (n == 0) {
@@ -77,80 +98,89 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
       const float a = x[100] * __ldg(win + 100), ar = x[300] * __ldg(win + 300);
       v0 = a + ar; v3 = a - ar;
     }
-    V[(0 * FE_NB + n) * FE_FT + f] = v0;
-    V[(1 * FE_NB + n) * FE_FT + f] = v1;
-    V[(2 * FE_NB + n) * FE_FT + f] = v2;
-    V[(3 * FE_NB + n) * FE_FT + f] = v3;
+    V[(0 * FE_NB + n) * FE_VP + f] = v0;
+    V[(1 * FE_NB + n) * FE_VP + f] = v1;
+    V[(2 * FE_NB + n) * FE_VP + f] = v2;
+    V[(3 * FE_NB + n) * FE_VP + f] = v3;
   }
   __syncthreads();
-  // ---- four 104x104 transforms: warp pair q, thread = 4 bins x 16 frames ---------------
-  const int q = tid >> 6, r = tid & 63;
-  const int kg = r % 26, fg = r / 26;               // r < 52 active
-  const bool active = r < 52;
-  float acc[16][4];
+  // ---- four 104x104 transforms: 52 threads each, thread = 4 bins x 16 frames.  Accumulators are
+  // frame PAIRS so that every multiply-add is one packed FFMA2 (fma.rn.f32x2, sm_100): half the
+  // FMA-pipe issue slots of scalar FFMA ----------------------------------------------------------
+  const int q = tid / 52, r = tid - q * 52;         // tid < 208 active
+  const int kg = r % 26, fg = r / 26;
+  const bool active = tid < 208;
+  float2 acc[8][4];                                 // [frame pair][bin]
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-  if (active) {
-    const float4* bas = reinterpret_cast<const float4*>(tab + FE_OFF_BAS + (size_t)q * FE_NB * FE_NB) + kg;
-    const float4* vq = reinterpret_cast<const float4*>(V + (size_t)q * FE_NB * FE_FT + fg * 16);
+  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = make_float2(0.f, 0.f); }
+  for (int st = 0; st < FE_NB / 8; ++st) {
+    if (tid == 0 && st >= 1 && st + 1 < FE_NB / 8) issue(st + 1);   // its buffer was released by the barrier ending stage st-1
+    mbar_wait(smem_u32(&bbar[st & 1]), (uint32_t)((st >> 1) & 1));
+    if (active) {
+      const float4* bs = reinterpret_cast<const float4*>(BS + (st & 1) * FE_STAGE + q * (8 * FE_NB)) + kg;
+      const float4* vq = reinterpret_cast<const float4*>(V + ((size_t)q * FE_NB + st * 8) * FE_VP + fg * 16);
 #pragma unroll 2
-    for (int n = 0; n < FE_NB; ++n) {
-      const float4 bv = __ldg(bas + n * (FE_NB / 4));
-      float xv[16];
+      for (int rr = 0; rr < 8; ++rr) {
+        const float4 bv = bs[rr * (FE_NB / 4)];
+        const float2 b0 = make_float2(bv.x, bv.x), b1 = make_float2(bv.y, bv.y);
+        const float2 b2 = make_float2(bv.z, bv.z), b3 = make_float2(bv.w, bv.w);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 t4 = vq[n * (FE_FT / 4) + j];
-        xv[4 * j] = t4.x; xv[4 * j + 1] = t4.y; xv[4 * j + 2] = t4.z; xv[4 * j + 3] = t4.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        acc[i][0] = fmaf(xv[i], bv.x, acc[i][0]);
-        acc[i][1] = fmaf(xv[i], bv.y, acc[i][1]);
-        acc[i][2] = fmaf(xv[i], bv.z, acc[i][2]);
-        acc[i][3] = fmaf(xv[i], bv.w, acc[i][3]);
+        for (int j = 0; j < 4; ++j) {
+          const float4 t4 = vq[rr * (FE_VP / 4) + j];
+          const float2 x0 = make_float2(t4.x, t4.y), x1 = make_float2(t4.z, t4.w);
+          acc[2 * j][0] = __ffma2_rn(x0, b0, acc[2 * j][0]);
+          acc[2 * j][1] = __ffma2_rn(x0, b1, acc[2 * j][1]);
+          acc[2 * j][2] = __ffma2_rn(x0, b2, acc[2 * j][2]);
+          acc[2 * j][3] = __ffma2_rn(x0, b3, acc[2 * j][3]);
+          acc[2 * j + 1][0] = __ffma2_rn(x1, b0, acc[2 * j + 1][0]);
+          acc[2 * j + 1][1] = __ffma2_rn(x1, b1, acc[2 * j + 1][1]);
+          acc[2 * j + 1][2] = __ffma2_rn(x1, b2, acc[2 * j + 1][2]);
+          acc[2 * j + 1][3] = __ffma2_rn(x1, b3, acc[2 * j + 1][3]);
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();                                  // V is dead: its space becomes the power spectrum
+  // V is dead (every thread is past the last stage's barrier): its space becomes the power
+  // spectrum, row = parity*104 + k/2, 16 frames of a thread stored as four float4
   float* P = V;
   if (active && q < 2) {                            // real parts: q0 -> even bins, q1 -> odd bins
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int k = 2 * (4 * kg + c) + q;
-      if (k < FE_NFREQ) {
+      float4* p4 = reinterpret_cast<float4*>(P + (q * FE_NB + 4 * kg + c) * FE_VP + fg * 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) P[(fg * 16 + i) * FE_PW + k] = acc[i][c];
-      }
+      for (int j = 0; j < 4; ++j) p4[j] = make_float4(acc[2 * j][c].x, acc[2 * j][c].y, acc[2 * j + 1][c].x, acc[2 * j + 1][c].y);
     }
   }
   __syncthreads();
   if (active && q >= 2) {                           // imaginary parts complete |X|^2
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int k = 2 * (4 * kg + c) + (q - 2);
-      if (k < FE_NFREQ) {
+      float4* p4 = reinterpret_cast<float4*>(P + ((q - 2) * FE_NB + 4 * kg + c) * FE_VP + fg * 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float* p = P + (fg * 16 + i) * FE_PW + k;
-          const float re = *p;
-          *p = fmaf(re, re, acc[i][c] * acc[i][c]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float4 re = p4[j];
+        const float2 i0 = acc[2 * j][c], i1 = acc[2 * j + 1][c];
+        p4[j] = make_float4(fmaf(re.x, re.x, i0.x * i0.x), fmaf(re.y, re.y, i0.y * i0.y),
+                            fmaf(re.z, re.z, i1.x * i1.x), fmaf(re.w, re.w, i1.y * i1.y));
       }
     }
   }
   __syncthreads();
-  // ---- mel bands + log ---------------------------------------------------------------
-  float* L = xs;                                    // [32][80]
+  // ---- mel bands + log: lane = frame (conflict-free), L[m][f] ---------------------------
+  float* L = xs;                                    // [80][32]
   const float* melw = tab + FE_OFF_MELW;
   const int* mello = reinterpret_cast<const int*>(tab + FE_OFF_MELLO);
   const int* melcnt = reinterpret_cast<const int*>(tab + FE_OFF_MELCNT);
   float lmax = -INFINITY;
-  for (int idx = tid; idx < FE_FT * FE_NMEL; idx += 256) {
-    const int f = idx / FE_NMEL, m = idx - f * FE_NMEL;
+  for (int idx = tid; idx < FE_FT * FE_NMEL; idx += FE_THREADS) {
+    const int m = idx >> 5, f = idx & (FE_FT - 1);
     const int lo = __ldg(mello + m), cnt = __ldg(melcnt + m);
-    const float* p = P + f * FE_PW + lo;
     float acc_m = 0.f;
-    for (int i = 0; i < cnt; ++i) acc_m = fmaf(p[i], __ldg(melw + m * FE_MAXW + i), acc_m);
+    for (int i = 0; i < cnt; ++i) {
+      const int k = lo + i;
+      acc_m = fmaf(P[((k & 1) * FE_NB + (k >> 1)) * FE_VP + f], __ldg(melw + m * FE_MAXW + i), acc_m);
+    }
     float v;
     if (mode == 0) v = logf(acc_m + 1e-6f);
     else { v = 10.f * log10f(fmaxf(acc_m, 1e-10f)); if (f < nf) lmax = fmaxf(lmax, v); }
@@ -159,31 +189,38 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
   __syncthreads();
   float* o_b = out + (int64_t)b * out_stride_b + (int64_t)t0 * FE_NMFCC;
   if (mode == 0) {
-    // ---- DCT-II: thread = coefficient c, frames fgroup, fgroup+3, ... ------------------
-    const int c = tid % FE_NMFCC, f0 = tid / FE_NMFCC;           // 240 threads busy
-    if (f0 < 3) {
+    // ---- DCT-II: thread = coefficient c and 16 frames (8 frame pairs, packed FMAs) -----
+    const int c = tid % FE_NMFCC, f0 = (tid / FE_NMFCC) * 16;     // 160 threads busy
+    if (tid < 2 * FE_NMFCC) {
       const float* dct = tab + FE_OFF_DCT + c;
-      float a[11];
+      float2 a[8];
 #pragma unroll
-      for (int j = 0; j < 11; ++j) a[j] = 0.f;
+      for (int j = 0; j < 8; ++j) a[j] = make_float2(0.f, 0.f);
+#pragma unroll 2
       for (int m = 0; m < FE_NMEL; ++m) {
         const float d = __ldg(dct + m * FE_NMFCC);
+        const float2 d2 = make_float2(d, d);
+        const float4* l4 = reinterpret_cast<const float4*>(L + m * FE_FT + f0);
 #pragma unroll
-        for (int j = 0; j < 11; ++j) {
-          const int f = f0 + 3 * j;
-          a[j] = fmaf(L[(f < FE_FT ? f : 0) * FE_NMEL + m], d, a[j]);
+        for (int j = 0; j < 4; ++j) {
+          const float4 t4 = l4[j];
+          a[2 * j] = __ffma2_rn(make_float2(t4.x, t4.y), d2, a[2 * j]);
+          a[2 * j + 1] = __ffma2_rn(make_float2(t4.z, t4.w), d2, a[2 * j + 1]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        const int f = f0 + 3 * j;
-        if (f < nf) o_b[f * FE_NMFCC + c] = a[j];
+      for (int j = 0; j < 8; ++j) {
+        if (f0 + 2 * j < nf) o_b[(f0 + 2 * j) * FE_NMFCC + c] = a[j].x;
+        if (f0 + 2 * j + 1 < nf) o_b[(f0 + 2 * j + 1) * FE_NMFCC + c] = a[j].y;
       }
     }
   } else {
-    for (int idx = tid; idx < nf * FE_NMEL; idx += 256) o_b[idx] = L[idx];
+    for (int idx = tid; idx < nf * FE_NMEL; idx += FE_THREADS) {
+      const int f = idx / FE_NMEL, m = idx - f * FE_NMEL;
+      o_b[idx] = L[m * FE_FT + f];
+    }
     lmax = warp_max(lmax);
-    if ((tid & 31) == 0 && lmax > -INFINITY) atomicMax(gmax, enc_ordered(lmax));
+    if (lane == 0 && lmax > -INFINITY) atomicMax(gmax, enc_ordered(lmax));
   }
 }
 
@@ -239,10 +276,8 @@ extern "C" int sc_frontend_tables(float* out, int64_t n, int sample_rate) {
   auto ang = [&](int k, int nn) { return 2.0 * PI * (double)((k * nn) % FE_NFFT) / FE_NFFT; };
   for (int nn = 0; nn <= 100; ++nn) {
     for (int j = 0; j <= 100; ++j) {
-      float* b0 = out + FE_OFF_BAS + (0 * FE_NB + nn) * FE_NB + j;
-      float* b1 = out + FE_OFF_BAS + (1 * FE_NB + nn) * FE_NB + j;
-      float* b2 = out + FE_OFF_BAS + (2 * FE_NB + nn) * FE_NB + j;
-      float* b3 = out + FE_OFF_BAS + (3 * FE_NB + nn) * FE_NB + j;
+      auto at = [&](int qq) { return out + FE_OFF_BAS + (((nn / 8) * 4 + qq) * 8 + (nn % 8)) * FE_NB + j; };
+      float *b0 = at(0), *b1 = at(1), *b2 = at(2), *b3 = at(3);
       *b0 = (float)cos(ang(2 * j, nn));                                   // Re, even bins k = 2j, n = 0..100
       if (nn < 100 && j < 100) *b1 = (float)cos(ang(2 * j + 1, nn));      // Re, odd bins, n = 0..99
       if (nn >= 1 && nn < 100 && j >= 1 && j < 100) *b2 = (float)(-sin(ang(2 * j, nn)));   // Im, even bins, n = 1..99
@@ -298,8 +333,8 @@ extern "C" int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, 
   const int T = 1 + (int)((S - FE_NFFT) / FE_HOP);
   SC_CHECK_ARG(out_stride_b >= (int64_t)T * FE_NMFCC && ldw >= S, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (((FE_XS + 3) & ~3) + 4 * FE_NB * FE_FT) * sizeof(float);
-  static_assert(4 * FE_NB * FE_FT >= FE_FT * FE_PW, "power spectrum must fit in the folded-input space");
+  const size_t smem = (FE_XS + 4 * FE_NB * FE_VP + 2 * FE_STAGE) * sizeof(float);
+  static_assert(FE_XS % 4 == 0 && FE_NB % 8 == 0 && FE_VP % 4 == 0, "16-byte alignment of the shared-memory regions");
   static_assert(FE_XS >= FE_FT * FE_NMEL, "log-mel rows must fit in the sample space");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -307,7 +342,7 @@ extern "C" int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, 
     e = cudaMemsetAsync(gmax, 0, sizeof(unsigned), st);           // ordered encoding: 0 is below every float
     if (e != cudaSuccess) return (int)e;
   }
-  frontend_kernel<<<dim3((unsigned)cdiv(T, FE_FT), (unsigned)B), 256, smem, st>>>(wav, ldw, (int)S, T, tables, mode, out,
+  frontend_kernel<<<dim3((unsigned)cdiv(T, FE_FT), (unsigned)B), FE_THREADS, smem, st>>>(wav, ldw, (int)S, T, tables, mode, out,
                                                                                    out_stride_b, gmax);
   if (mode == 1 && top_db >= 0.f) {
     // out rows are dense per stream only when out_stride_b == T*80; floor stream by stream otherwise

@@ -47,7 +47,8 @@ def test_oracle_frame_mask_rejects_what_the_reference_rejects():
 def _unpack(tab):
     NB = 104
     o = 400 + 4 * NB * NB
-    t = dict(win=tab[:400], bas=tab[400:o].reshape(4, NB, NB))
+    # bases are stored [13 stages][4 transforms][8 rows][104 bins] (one bulk copy per stage)
+    t = dict(win=tab[:400], bas=tab[400:o].reshape(13, 4, 8, NB).transpose(1, 0, 2, 3).reshape(4, NB, NB))
     t["melw"] = tab[o:o + 80 * 32].reshape(80, 32); o += 80 * 32
     t["lo"] = tab[o:o + 80].view(np.int32); o += 80
     t["cnt"] = tab[o:o + 80].view(np.int32); o += 80

@@ -478,3 +478,97 @@ def test_scan_fwd_chunked_matches_sequential(cuda_device, dtype, train_mode, B, 
     assert lib.sc_lucy_scan_chunked_work_bytes(1, 3000, 1024) == 4 * 47 * 1024 * 4
     assert lib.sc_lucy_scan_chunked_work_bytes(64, 3000, 1024) == 0           # enough streams: sequential kernel
     assert lib.sc_lucy_scan_chunked_work_bytes(1, 100, 1024) == 0             # too short to cut
+
+
+@pytest.mark.parametrize("T", [63, 64, 65, 127, 128, 129, 193])
+def test_ctc_wavefront_block_meetings(cuda_device, T):
+    """Sequence lengths around the 64-row emission blocks at which the wavefront alpha/beta kernel
+    holds its block meeting (re-centring, slot recycling), with a lattice that spans three warps
+    in the node-per-thread kernel and two in the pair-per-thread kernel."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(1000 + T)
+    B, V, U = 3, 12, 40
+    logits = torch.randn(B, T, V, generator=g) * 2
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl = [T, T - 1, max(1, T - 20)]
+    tgl = [min(U, T // 2), 17, 1]
+    loss_ref, _, grad_ref = ctc_oracle.ctc_loss_and_grad(logits.numpy(), tokens.numpy(), inl, tgl)
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), grad_ref, rtol=2e-4, atol=2e-6)
+
+
+def test_ctc_three_lattice_kernels_agree(cuda_device, monkeypatch):
+    """SC_CTC_WAVE = 0 (block barrier per step), 1 (wavefront, node per thread), 2 (wavefront,
+    pair per thread; the default): same loss and gradient on a cfg2-like lattice, and the
+    emission-block size does not matter."""
+    from statecatcher_b200 import ctc_loss_from_logits
+    g = torch.Generator().manual_seed(77)
+    B, T, V, U = 5, 700, 64, 150
+    logits = torch.randn(B, T, V, generator=g) * 2
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl, tgl = [T, T, 650, 333, 1], [150, 75, 149, 0, 1]
+    xd = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(xd.log_softmax(-1).transpose(0, 1), tokens, inl, tgl, zero_infinity=True)
+    ref.backward()
+    outs = []
+    for wave, eb in [("0", None), ("1", None), ("2", None), ("2", "8"), ("1", "16")]:
+        monkeypatch.setenv("SC_CTC_WAVE", wave)
+        if eb:
+            monkeypatch.setenv("SC_CTC_EB", eb)
+        else:
+            monkeypatch.delenv("SC_CTC_EB", raising=False)
+        x = logits.cuda().requires_grad_(True)
+        loss = ctc_loss_from_logits(x, tokens.cuda(), inl, tgl, zero_infinity=True)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-7)
+        outs.append(x.grad)
+    for o in outs[1:]:
+        assert (o - outs[0]).abs().max().item() < 2e-6
+
+
+def test_ctc_more_lattices_than_sms(cuda_device):
+    """100 utterances = 200 (utterance, direction) CTAs on 148 SMs: the wavefront kernel sizes
+    its emission blocks so that two CTAs share an SM."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(9)
+    B, T, V, U = 100, 150, 20, 30
+    logits = torch.randn(B, T, V, generator=g)
+    tokens = torch.randint(1, V, (B, U), generator=g)
+    inl = [T - (b % 7) for b in range(B)]
+    tgl = [U - (b % 11) for b in range(B)]
+    loss_ref, _, grad_ref = ctc_oracle.ctc_loss_and_grad(logits.numpy(), tokens.numpy(), inl, tgl)
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref, rtol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), grad_ref, rtol=2e-4, atol=2e-6)
+
+
+def test_ctc_masked_vocabulary_entries(cuda_device):
+    """-inf logits: harmless off the lattice; on a needed label they make the utterance
+    infeasible (loss 0, gradient row 0 with zero_infinity) without poisoning its batch mates."""
+    from statecatcher_b200 import ctc_loss
+    g = torch.Generator().manual_seed(10)
+    B, T, V, U = 3, 90, 10, 5
+    logits = torch.randn(B, T, V, generator=g)
+    tokens = torch.randint(1, 8, (B, U), generator=g)
+    logits[:, :, 9] = float("-inf")                         # never a target
+    logits[1, :, int(tokens[1, 2])] = float("-inf")         # utterance 1 cannot emit one of its labels
+    inl, tgl = [T, T, T - 3], [U, U, U]
+    # torch's own gradient is NaN here (log_softmax backward of a -inf input); the loss is not, and the
+    # numpy oracle gives the finite gradient (0 at the masked entries)
+    ref = torch.nn.functional.ctc_loss(logits.double().log_softmax(-1).transpose(0, 1), tokens, inl, tgl, zero_infinity=True)
+    with np.errstate(all="ignore"):
+        loss_ref, nll_ref, want = ctc_oracle.ctc_loss_and_grad(logits.numpy(), tokens.numpy(), inl, tgl)
+    assert nll_ref[1] == 0 and abs(loss_ref - ref.item()) < 1e-9
+    x = logits.cuda().requires_grad_(True)
+    loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, zero_infinity=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+    got = x.grad.cpu().numpy()
+    assert np.isfinite(got).all() and (got[1] == 0).all() and (got[:, :, 9] == 0).all()
+    np.testing.assert_allclose(got[[0, 2]], want[[0, 2]], rtol=2e-3, atol=2e-7)
