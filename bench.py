@@ -405,7 +405,11 @@ def main():
         torch.cuda.synchronize()
         ms_fe = ev0.elapsed_time(ev1) / 5.0
         fe_info = {"kind": "MFCC 400/160/80 (model.py:250-279) fused kernel, waveform -> (B,T,80)", "ms_per_step": ms_fe,
-                   "gb_per_s_algorithmic": W["B"] * W["T"] * 960 / (ms_fe * 1e-3) / 1e9, "included_in_value": False}
+                   "gb_per_s_algorithmic": W["B"] * W["T"] * 960 / (ms_fe * 1e-3) / 1e9,
+                   # 4 folded 104x104 transforms + 80x80 DCT per frame, 2 flops per multiply-add; the kernel is
+                   # fp32-FMA-bound (148 SMs x 128 lanes x 2 x clock ~ 72 TFLOP/s at 1.9 GHz), not HBM-bound
+                   "bound": "fp32 fma", "tflops_fp32": W["B"] * W["T"] * 2 * (4 * 104 * 104 + 6400) / (ms_fe * 1e-3) / 1e12,
+                   "included_in_value": False}
         del wav
 
     # ---- roofline per kernel family from the events recorded inside the timed region ----

@@ -77,31 +77,51 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
   }
   const float* w_b = wav + (int64_t)b * ldw;
   const int s0 = t0 * FE_HOP;
-  for (int i = tid; i < FE_XS; i += FE_THREADS) xs[i] = (s0 + i < S) ? __ldg(w_b + s0 + i) : 0.f;
+  {
+    constexpr int NL = (FE_XS + FE_THREADS - 1) / FE_THREADS;     // 24 loads per thread, all in flight at once
+    float tmp[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = tid + j * FE_THREADS;
+      tmp[j] = (i < FE_XS && s0 + i < S) ? __ldg(w_b + s0 + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = tid + j * FE_THREADS;
+      if (i < FE_XS) xs[i] = tmp[j];
+    }
+  }
   __syncthreads();
   // ---- window + two folds.  A warp takes 32 consecutive n of one frame: frames start 160
   // floats apart (a multiple of the 32 banks), so lanes must differ in n, not in the frame --------
   const float* win = tab + FE_OFF_WIN;
-  for (int idx = tid; idx < FE_FT * FE_NB; idx += FE_THREADS) {
-    const int f = idx / FE_NB, n = idx - f * FE_NB;
-    const float* x = xs + f * FE_HOP;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-    if (n == 0) {
-      const float a0 = x[0] * __ldg(win), a2 = x[200] * __ldg(win + 200);
-      v0 = a0 + a2; v1 = a0 - a2;
-    } else if (n < 100) {
-      const float a = x[n] * __ldg(win + n), ar = x[400 - n] * __ldg(win + 400 - n);
-      const float c = x[200 - n] * __ldg(win + 200 - n), cr = x[200 + n] * __ldg(win + 200 + n);
-      const float e1 = a + ar, e2 = c + cr, o1 = a - ar, o2 = c - cr;
-      v0 = e1 + e2; v1 = e1 - e2; v2 = o1 - o2; v3 = o1 + o2;
-    } else if (n == 100) {
-      const float a = x[100] * __ldg(win + 100), ar = x[300] * __ldg(win + 300);
-      v0 = a + ar; v3 = a - ar;
+  if (tid < 2 * FE_NB) {
+    const int n = tid % FE_NB, fh = tid / FE_NB;    // thread = one n, 16 frames; its 4 window values stay in registers
+    // v0..v3 = c0*a(n) + c1*a(400-n) + c2*a(200-n) + c3*a(200+n) patterns; n = 0 and n >= 100 are the edge rows
+    const bool mid = n >= 1 && n < 100;
+    const int i0 = n <= 100 ? n : 0, i1 = mid ? 400 - n : (n == 100 ? 300 : 200), i2 = mid ? 200 - n : 0, i3 = mid ? 200 + n : 0;
+    const float w0 = n <= 100 ? __ldg(win + i0) : 0.f;
+    const float w1 = n <= 100 ? __ldg(win + i1) : 0.f;
+    const float w2 = mid ? __ldg(win + i2) : 0.f, w3 = mid ? __ldg(win + i3) : 0.f;
+    float* vp = V + n * FE_VP + fh * 16;
+#pragma unroll 4
+    for (int ff = 0; ff < 16; ++ff) {
+      const float* x = xs + (fh * 16 + ff) * FE_HOP;
+      const float a = x[i0] * w0, ar = x[i1] * w1, c = x[i2] * w2, cr = x[i3] * w3;
+      float v0, v1, v2, v3;
+      if (mid) {
+        const float e1 = a + ar, e2 = c + cr, o1 = a - ar, o2 = c - cr;
+        v0 = e1 + e2; v1 = e1 - e2; v2 = o1 - o2; v3 = o1 + o2;
+      } else if (n == 0) {                          // a = a(0), ar = a(200)
+        v0 = a + ar; v1 = a - ar; v2 = 0.f; v3 = 0.f;
+      } else {                                      // n = 100: a(100), a(300); rows 101..103 are zero (w = 0)
+        v0 = a + ar; v1 = 0.f; v2 = 0.f; v3 = a - ar;
+      }
+      vp[0 * FE_NB * FE_VP + ff] = v0;
+      vp[1 * FE_NB * FE_VP + ff] = v1;
+      vp[2 * FE_NB * FE_VP + ff] = v2;
+      vp[3 * FE_NB * FE_VP + ff] = v3;
     }
-    V[(0 * FE_NB + n) * FE_VP + f] = v0;
-    V[(1 * FE_NB + n) * FE_VP + f] = v1;
-    V[(2 * FE_NB + n) * FE_VP + f] = v2;
-    V[(3 * FE_NB + n) * FE_VP + f] = v3;
   }
   __syncthreads();
   // ---- four 104x104 transforms: 52 threads each, thread = 4 bins x 16 frames.  Accumulators are
@@ -141,6 +161,12 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
     }
     __syncthreads();
   }
+  // the basis ring is free: fetch the 80x80 DCT matrix into it while the power spectrum and the mel bands are formed
+  if (tid == 0 && mode == 0) {
+    const uint32_t bar = smem_u32(&bbar[1]);        // its 7th use: 13 stages -> slot 1 completed phases 0..5
+    mbar_expect_tx(bar, FE_NMEL * FE_NMFCC * 4u);
+    bulk_load_1d(smem_u32(BS), tab + FE_OFF_DCT, FE_NMEL * FE_NMFCC * 4u, bar);
+  }
   // V is dead (every thread is past the last stage's barrier): its space becomes the power
   // spectrum, row = parity*104 + k/2, 16 frames of a thread stored as four float4
   float* P = V;
@@ -177,9 +203,13 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
     const int m = idx >> 5, f = idx & (FE_FT - 1);
     const int lo = __ldg(mello + m), cnt = __ldg(melcnt + m);
     float acc_m = 0.f;
-    for (int i = 0; i < cnt; ++i) {
-      const int k = lo + i;
-      acc_m = fmaf(P[((k & 1) * FE_NB + (k >> 1)) * FE_VP + f], __ldg(melw + m * FE_MAXW + i), acc_m);
+    const float* wm = melw + m * FE_MAXW;
+    {                                               // bins of the band's first parity, then the other: consecutive rows each
+      const float* pe = P + ((lo & 1) * FE_NB + (lo >> 1)) * FE_VP + f;
+      for (int i = 0; i < cnt; i += 2, pe += FE_VP) acc_m = fmaf(*pe, __ldg(wm + i), acc_m);
+      const int k1 = lo + 1;
+      const float* po = P + ((k1 & 1) * FE_NB + (k1 >> 1)) * FE_VP + f;
+      for (int i = 1; i < cnt; i += 2, po += FE_VP) acc_m = fmaf(*po, __ldg(wm + i), acc_m);
     }
     float v;
     if (mode == 0) v = logf(acc_m + 1e-6f);
@@ -192,13 +222,14 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
     // ---- DCT-II: thread = coefficient c and 16 frames (8 frame pairs, packed FMAs) -----
     const int c = tid % FE_NMFCC, f0 = (tid / FE_NMFCC) * 16;     // 160 threads busy
     if (tid < 2 * FE_NMFCC) {
-      const float* dct = tab + FE_OFF_DCT + c;
+      mbar_wait(smem_u32(&bbar[1]), 0u);            // slot 1: stages 1,3,..,11 were phases 0..5 -> this copy is phase 6 (parity 0)
+      const float* dct = BS + c;
       float2 a[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] = make_float2(0.f, 0.f);
-#pragma unroll 2
+#pragma unroll 4
       for (int m = 0; m < FE_NMEL; ++m) {
-        const float d = __ldg(dct + m * FE_NMFCC);
+        const float d = dct[m * FE_NMFCC];
         const float2 d2 = make_float2(d, d);
         const float4* l4 = reinterpret_cast<const float4*>(L + m * FE_FT + f0);
 #pragma unroll
@@ -336,6 +367,7 @@ extern "C" int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, 
   const size_t smem = (FE_XS + 4 * FE_NB * FE_VP + 2 * FE_STAGE) * sizeof(float);
   static_assert(FE_XS % 4 == 0 && FE_NB % 8 == 0 && FE_VP % 4 == 0, "16-byte alignment of the shared-memory regions");
   static_assert(FE_XS >= FE_FT * FE_NMEL, "log-mel rows must fit in the sample space");
+  static_assert(2 * FE_STAGE >= FE_NMEL * FE_NMFCC && ((FE_NB / 8) % 2) == 1, "DCT matrix reuses the basis ring; slot 1 must have completed an even number of phases");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   if (mode == 1) {
