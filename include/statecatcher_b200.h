@@ -292,11 +292,16 @@ int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
 int64_t sc_frontend_tables_len(void);
 int sc_frontend_tables(float* host_out, int64_t n, int sample_rate);
 int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, const float* tables, int mode,
-                float top_db, float* out, int64_t out_stride_b, unsigned int* gmax, void* stream);
+                float top_db, const uint8_t* frame_mask /* nullable, mode 0 only: [B,T] bytes, row stride ldmask;
+                frames with 0 are written as zeros = model.py:377 folded in */, int64_t ldmask,
+                float* out, int64_t out_stride_b, unsigned int* gmax, void* stream);
 /* compute_frame_mask (train.py:296-306) + the in_lens line (train.py:490), bit-exact:
  * sample_mask [B,S] bytes (row stride ldm); frame_mask[b,t] = any(sample_mask[b, t*sub:(t+1)*sub])
  * for t < T; in_lens[b] = (int64) min(float(sum_s sample_mask[b,s]) / subsample, nfeat) with the
  * division in fp32.  Requires T*sub <= S (the caller enforces the reference's S_trim == T*sub). */
+/* dst[r,:] = src[r,:] * float(mask[r]) — `feats * mask.unsqueeze(-1).float()` (model.py:377). */
+int sc_mask_rows(const void* src, int64_t lds, int dtype, const uint8_t* mask, void* dst, int64_t ldd,
+                 int64_t rows, int64_t cols, void* stream);
 int sc_frame_mask(const uint8_t* sample_mask, int64_t ldm, int64_t B, int64_t S, int64_t T, int64_t sub,
                   float subsample, int64_t nfeat, uint8_t* frame_mask, int64_t* in_lens, void* stream);
 

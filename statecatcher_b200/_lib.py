@@ -62,7 +62,8 @@ SIGNATURES = {
     "sc_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P, F32, I32, P],
     "sc_frontend_tables_len": [],
     "sc_frontend_tables": [P, I64, I32],
-    "sc_frontend": [P, I64, I64, I64, P, I32, F32, P, I64, P, P],
+    "sc_frontend": [P, I64, I64, I64, P, I32, F32, P, I64, P, I64, P, P],
+    "sc_mask_rows": [P, I64, I32, P, P, I64, I64, I64, P],
     "sc_frame_mask": [P, I64, I64, I64, I64, I64, F32, I64, P, P, P],
 }
 _RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64,

@@ -51,7 +51,7 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 // mode 0: mfcc; mode 1: mel dB before the top_db floor (batch maximum -> gmax, ordered encoding)
 __global__ void __launch_bounds__(FE_THREADS, 2)
 frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
-                const float* __restrict__ tab, int mode,
+                const float* __restrict__ tab, int mode, const uint8_t* __restrict__ row_mask, int64_t ldmask,
                 float* __restrict__ out, int64_t out_stride_b, unsigned* __restrict__ gmax) {
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t bbar[2];
@@ -218,6 +218,8 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
   }
   __syncthreads();
   float* o_b = out + (int64_t)b * out_stride_b + (int64_t)t0 * FE_NMFCC;
+  // optional frame mask (model.py:377 `feats * mask` folded in): masked frames are written as zeros
+  const uint8_t* mk = row_mask ? row_mask + (int64_t)b * ldmask + t0 : nullptr;
   if (mode == 0) {
     // ---- DCT-II: thread = coefficient c and 16 frames (8 frame pairs, packed FMAs) -----
     const int c = tid % FE_NMFCC, f0 = (tid / FE_NMFCC) * 16;     // 160 threads busy
@@ -241,8 +243,8 @@ frontend_kernel(const float* __restrict__ wav, int64_t ldw, int S, int T,
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (f0 + 2 * j < nf) o_b[(f0 + 2 * j) * FE_NMFCC + c] = a[j].x;
-        if (f0 + 2 * j + 1 < nf) o_b[(f0 + 2 * j + 1) * FE_NMFCC + c] = a[j].y;
+        if (f0 + 2 * j < nf) o_b[(f0 + 2 * j) * FE_NMFCC + c] = (mk && !mk[f0 + 2 * j]) ? 0.f : a[j].x;
+        if (f0 + 2 * j + 1 < nf) o_b[(f0 + 2 * j + 1) * FE_NMFCC + c] = (mk && !mk[f0 + 2 * j + 1]) ? 0.f : a[j].y;
       }
     }
   } else {
@@ -356,13 +358,15 @@ extern "C" int sc_frontend_tables(float* out, int64_t n, int sample_rate) {
 }
 
 extern "C" int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, const float* tables, int mode,
-                           float top_db, float* out, int64_t out_stride_b, unsigned int* gmax, void* stream) {
+                           float top_db, const uint8_t* frame_mask, int64_t ldmask,
+                           float* out, int64_t out_stride_b, unsigned int* gmax, void* stream) {
   SC_CHECK_ARG(B > 0 && S >= 0 && (mode == 0 || mode == 1), SC_E_BADARG);
   SC_CHECK_ARG(S < ((int64_t)1 << 31) && B < 65536, SC_E_SHAPE);
   if (S < FE_NFFT) return 0;                                     // no frame fits
   SC_CHECK_ARG(wav && tables && out && (mode == 0 || gmax), SC_E_BADARG);
   const int T = 1 + (int)((S - FE_NFFT) / FE_HOP);
   SC_CHECK_ARG(out_stride_b >= (int64_t)T * FE_NMFCC && ldw >= S, SC_E_BADARG);
+  SC_CHECK_ARG(!frame_mask || (mode == 0 && ldmask >= T), SC_E_BADARG);   // the dB floor of the mel path must see unmasked values
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (FE_XS + 4 * FE_NB * FE_VP + 2 * FE_STAGE) * sizeof(float);
   static_assert(FE_XS % 4 == 0 && FE_NB % 8 == 0 && FE_VP % 4 == 0, "16-byte alignment of the shared-memory regions");
@@ -374,8 +378,8 @@ extern "C" int sc_frontend(const float* wav, int64_t ldw, int64_t B, int64_t S, 
     e = cudaMemsetAsync(gmax, 0, sizeof(unsigned), st);           // ordered encoding: 0 is below every float
     if (e != cudaSuccess) return (int)e;
   }
-  frontend_kernel<<<dim3((unsigned)cdiv(T, FE_FT), (unsigned)B), FE_THREADS, smem, st>>>(wav, ldw, (int)S, T, tables, mode, out,
-                                                                                   out_stride_b, gmax);
+  frontend_kernel<<<dim3((unsigned)cdiv(T, FE_FT), (unsigned)B), FE_THREADS, smem, st>>>(wav, ldw, (int)S, T, tables, mode, frame_mask, ldmask,
+                                                                                          out, out_stride_b, gmax);
   if (mode == 1 && top_db >= 0.f) {
     // out rows are dense per stream only when out_stride_b == T*80; floor stream by stream otherwise
     if (out_stride_b == (int64_t)T * FE_NMFCC) {

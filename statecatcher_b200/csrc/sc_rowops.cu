@@ -15,6 +15,18 @@ __global__ void cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __restr
   }
 }
 
+// dst[r, :] = src[r, :] * float(mask[r])  —  model.py:377 `feats * mask.unsqueeze(-1).float()`
+// (a true multiply, so -0.0 / NaN behave as upstream)
+template <typename T>
+__global__ void mask_rows_kernel(const T* __restrict__ src, int64_t lds, const uint8_t* __restrict__ mask,
+                                 T* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    st_f(dst + r * ldd + c, ld_f(src + r * lds + c) * (mask[r] ? 1.f : 0.f));
+  }
+}
+
 // hi = bf16(x), lo = bf16(x - hi): a two-term bf16 expansion (16 mantissa bits) of an fp32
 // matrix, written side by side as [rows, 2*cols] so one bf16 tensor-core GEMM over the
 // doubled reduction dimension reproduces the fp32 product to ~1e-5.
@@ -331,6 +343,19 @@ extern "C" int sc_cast(const void* src, int64_t lds, int src_dtype, void* dst, i
     cast_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols);
   else if (src_dtype == SC_BF16 && dst_dtype == SC_BF16)
     cast_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols);
+  else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_mask_rows(const void* src, int64_t lds, int dtype, const uint8_t* mask, void* dst, int64_t ldd,
+                            int64_t rows, int64_t cols, void* stream) {
+  SC_CHECK_ARG(rows >= 0 && cols >= 0, SC_E_BADARG);
+  if (rows * cols == 0) return 0;
+  SC_CHECK_ARG(src && dst && mask, SC_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)min((int64_t)148 * 16, cdiv(rows * cols, 256));
+  if (dtype == SC_F32) mask_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, lds, mask, (float*)dst, ldd, rows, cols);
+  else if (dtype == SC_BF16) mask_rows_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)src, lds, mask, (bf16*)dst, ldd, rows, cols);
   else return SC_E_DTYPE;
   SC_LAUNCH_RET();
 }

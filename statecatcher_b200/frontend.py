@@ -44,8 +44,10 @@ class _Frontend(nn.Module):
     def num_frames(n_samples: int) -> int:
         return 0 if n_samples < N_FFT else 1 + (n_samples - N_FFT) // HOP
 
-    def features(self, waveform: torch.Tensor) -> torch.Tensor:
-        """(..., S) -> (..., T, 80) contiguous fp32 (the layout the encoder consumes)."""
+    def features(self, waveform: torch.Tensor, frame_mask: torch.Tensor = None) -> torch.Tensor:
+        """(..., S) -> (..., T, 80) contiguous fp32 (the layout the encoder consumes).  With
+        ``frame_mask`` (B, T) bool (MFCC only) masked frames come out as zeros: model.py:377's
+        ``feats * mask.unsqueeze(-1).float()`` without another pass over the features."""
         _lib.require_cuda(waveform, "frontend input")
         if self.tables.device != waveform.device:
             raise RuntimeError("frontend tables and waveform are on different devices: move the module with .to(device)")
@@ -58,8 +60,15 @@ class _Frontend(nn.Module):
         out = torch.empty(B, T, N_MELS, dtype=torch.float32, device=w.device)
         if B and T:
             gmax = torch.empty(1, dtype=torch.int32, device=w.device) if self.mode == 1 else None
+            fm, ldm = None, 0
+            if frame_mask is not None:
+                fm = frame_mask.to(torch.bool).reshape(B, -1)
+                if fm.shape[1] != T or self.mode != 0:
+                    raise ValueError(f"frame_mask must be ({B}, {T}) and the frontend 'mfcc'")
+                fm = fm if fm.stride(-1) == 1 else fm.contiguous()
+                ldm = fm.stride(0)
             call("sc_frontend", ptr(w), w.stride(0), B, S, ptr(self.tables), self.mode, float(self.top_db),
-                 ptr(out), out.stride(0), ptr(gmax), stream())
+                 ptr(fm), ldm, ptr(out), out.stride(0), ptr(gmax), stream())
         return out.reshape(*lead, T, N_MELS)
 
     @torch.no_grad()
@@ -116,6 +125,17 @@ def frame_mask_and_lens(sample_mask: torch.Tensor, n_feat_frames: int, stack_ord
     call("sc_frame_mask", ptr(m), m.stride(0), B, S, T, sub, float(subsample), int(n_feat_frames), ptr(fm), ptr(lens),
          stream())
     return fm, lens.tolist()
+
+
+def featurize(frontend: _Frontend, waveform: torch.Tensor, sample_mask: torch.Tensor
+              ) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
+    """train.py:473-490 + model.py:377 in two launches: (B, S) waveform and sample mask ->
+    (feats (B, T, 80) with masked frames zeroed, frame_mask (B, T) bool, in_lens list[int])."""
+    T = frontend.num_frames(waveform.shape[-1])
+    fm, lens = frame_mask_and_lens(sample_mask, T)
+    if fm.shape[1] != T:                 # upstream asserts this (train.py:492)
+        raise AssertionError(f"Mismatch: feats={T} vs mask={fm.shape[1]}")
+    return frontend.features(waveform, fm if frontend.mode == 0 else None), fm, lens
 
 
 def compute_frame_mask(sample_mask: torch.Tensor, subsample: float) -> torch.Tensor:

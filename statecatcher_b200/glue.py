@@ -15,6 +15,7 @@ from typing import Any, Optional
 import torch
 import torch.nn as nn
 
+from . import ops
 from .ctc import CTCLoss, ctc_loss_from_logits
 from .lucyrnn import LucyRNN
 from .lucyrnn_conf import LucyRNNConfig
@@ -60,7 +61,10 @@ class LucyASRModel(nn.Module):
         if hasattr(self, "proj"):
             feats = self.proj(feats)
         if mask is not None:
-            feats = feats * mask.unsqueeze(-1).float()
+            if feats.requires_grad or feats.dtype not in (torch.float32, torch.bfloat16):
+                feats = feats * mask.unsqueeze(-1).float()       # keeps autograd through an input projection
+            else:
+                feats = ops.mask_rows(feats, mask)               # model.py:377, our kernel
         if states is not None:
             return self.encoder(feats, states)
         return self.encoder(feats)

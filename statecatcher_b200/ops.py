@@ -69,6 +69,19 @@ def cast(src: torch.Tensor, dtype, out: Optional[torch.Tensor] = None) -> torch.
     return out.view(src.shape) if out.dim() != src.dim() else out
 
 
+def mask_rows(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """x [..., C] * mask[...].float() (model.py:377), one pass, x's dtype."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    m = mask.to(torch.bool).reshape(-1).contiguous()
+    if m.numel() != x2.shape[0]:
+        raise ValueError(f"mask has {m.numel()} rows, features {x2.shape[0]}")
+    out = torch.empty(x2.shape, dtype=x.dtype, device=x.device)
+    call("sc_mask_rows", ptr(x2), _ld(x2), dt(x2), ptr(m), ptr(out), _ld(out), x2.shape[0], x2.shape[1], stream())
+    return out.view(x.shape)
+
+
 def split_bf16(src: torch.Tensor) -> torch.Tensor:
     """fp32 [R,C] -> bf16 [R,2C] = [hi | lo] two-term expansion."""
     R, C = src.shape

@@ -76,7 +76,7 @@ def test_table_builder_argument_errors():
     buf = torch.empty(16)
     assert lib.sc_frontend_tables(buf.data_ptr(), 16, 16000) == -1      # buffer too small
     assert lib.sc_frontend_tables(None, 1 << 20, 16000) == -1
-    assert lib.sc_frontend(None, 0, 0, 0, None, 0, 0.0, None, 0, None, None) == -1
+    assert lib.sc_frontend(None, 0, 0, 0, None, 0, 0.0, None, 0, None, 0, None, None) == -1
     assert lib.sc_frame_mask(None, 0, 1, 1, 1, 1, 1.0, 1, None, None, None) == -1
 
 

@@ -114,3 +114,46 @@ def test_frame_mask_random_patterns_and_stack_order(cuda_device):
         assert np.array_equal(fm.cpu().numpy(), ofm) and lens == olens
     with pytest.raises(RuntimeError):
         sb.frame_mask_and_lens(torch.ones(1, 1000, dtype=torch.bool, device="cuda"), 7, 3)
+
+
+def test_featurize_folds_the_frame_mask(cuda_device, G):
+    """featurize = frontend + compute_frame_mask + in_lens + model.py:377's feats*mask: masked
+    frames are zeros, live frames equal the unmasked features, lens as the reference computes."""
+    import statecatcher_b200 as sb
+    g = torch.Generator().manual_seed(11)
+    B, S = 3, 16000
+    wav = torch.randn(B, S, generator=g) * 0.1
+    valid = [16000, 9000, 0]
+    m = torch.zeros(B, S, dtype=torch.bool)
+    for b, v in enumerate(valid):
+        m[b, :v] = True
+    fe = sb.MFCC(16000).cuda()
+    feats, fm, lens = sb.featurize(fe, wav.cuda(), m.cuda())
+    plain = fe.features(wav.cuda())
+    ofm, olens = FO.frame_mask_and_lens(m.numpy(), plain.shape[1])
+    assert np.array_equal(fm.cpu().numpy(), ofm) and lens == olens
+    want = plain * fm.unsqueeze(-1).float()
+    assert torch.equal(feats, want)
+    assert (feats[2] == 0).all() and (feats[1, lens[1] + 1:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_mask_rows_is_the_reference_multiply(cuda_device, dtype):
+    """sc_mask_rows == feats * mask.unsqueeze(-1).float() bit for bit (incl. -0.0), and
+    LucyASRModel.forward routes through it."""
+    import statecatcher_b200 as sb
+    from statecatcher_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(4, 37, 80, generator=g).to(dtype).cuda()
+    mask = (torch.rand(4, 37, generator=g) > 0.4).cuda()
+    got = ops.mask_rows(x, mask)
+    want = (x * mask.unsqueeze(-1).float()).to(dtype)
+    assert got.dtype == dtype and torch.equal(got.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                                              want.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
+    cfg = sb.LucyRNNConfig(input_dim=80, hidden_dim=32, num_layers=1, vocab_size=11, fused_ops=True, layer_norm=False)
+    model = sb.LucyASRModel(cfg).cuda()
+    torch.nn.init.normal_(model.encoder.output_proj.weight, std=0.1)
+    xf = x.float()
+    a, _ = model(xf, mask)
+    b_, _ = model.encoder(xf * mask.unsqueeze(-1).float())
+    assert torch.equal(a, b_)
