@@ -38,8 +38,9 @@ constexpr int ATOM_BYTES = TK * 128;              // one [TK x 64-element] MN-ma
 constexpr int EPI_WARPS = 8;                     // two warps per TMEM lane quarter, 128 columns each
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 2;      // per epilogue warp: one [32 rows x 32 cols] bf16 box for the TMA store
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * TN * 4 /*bias*/ +
-                           EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int EPI_OFF = RING_BYTES + 256 /*barriers*/ + 2 * TN * 4 /*bias*/ + 256 /*pad: store boxes 512-B aligned for SWIZZLE_64B*/;
+static_assert(EPI_OFF % 512 == 0, "store boxes must be 512-byte aligned (64-byte swizzle pattern)");
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
@@ -246,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           // the tensor map clips rows >= I and columns >= J.
           const uint32_t stg = (EPI_BUFS == 2 && (ebox & 1))
                                    ? base + STAGES * STAGE_BYTES + (uint32_t)(warp - 2) * EPI_STAGE_BYTES
-                                   : base + RING_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+                                   : base + EPI_OFF + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
           ++ebox;
           if (p.bias != nullptr) {
             const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
@@ -269,7 +270,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
               pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + v * 16), "r"(pk[0]), "r"(pk[1]),
+            // 64-byte rows, SWIZZLE_64B (16-byte chunk ^= (row >> 1) & 3): the 8 lanes of a store phase land in 8
+            // different bank groups; unswizzled, rows 64 B apart gave a 4-way conflict on every store
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((v ^ ((lane >> 1) & 3)) * 16)), "r"(pk[0]), "r"(pk[1]),
                          "r"(pk[2]), "r"(pk[3]) : "memory");
           }
           fence_async_smem();
@@ -281,14 +284,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else if (EPI == 2) {
           // split-R partial tile: fp32 TMA reduce-add of [32 rows x 16 cols] boxes (64-byte row
           // segments reduced in L2) instead of 32 scattered 4-byte atomics per lane per chunk
-          const uint32_t stg = base + RING_BYTES + 256 + 2 * TN * 4 + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+          const uint32_t stg = base + EPI_OFF + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
 #pragma unroll
             for (int v = 0; v < 4; ++v)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + v * 16), "r"(r[hh * 16 + v * 4 + 0]),
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((v ^ ((lane >> 1) & 3)) * 16)), "r"(r[hh * 16 + v * 4 + 0]),
                            "r"(r[hh * 16 + v * 4 + 1]), "r"(r[hh * 16 + v * 4 + 2]), "r"(r[hh * 16 + v * 4 + 3]) : "memory");
             fence_async_smem();
             __syncwarp();
@@ -356,7 +359,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   return r == CUDA_SUCCESS;
 }
 
-// bf16 output [rows, cols] (row stride ld): [32 x 32] store boxes, no swizzle
+// bf16 output [rows, cols] (row stride ld): [32 x 32] store boxes (64-byte rows), 64-byte swizzle
 static bool make_store_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
@@ -365,11 +368,11 @@ static bool make_store_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// fp32 output [rows, cols] (row stride ld): [32 x 16] reduce-add boxes, no swizzle
+// fp32 output [rows, cols] (row stride ld): [32 x 16] reduce-add boxes (64-byte rows), 64-byte swizzle
 static bool make_reduce_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
@@ -378,7 +381,7 @@ static bool make_reduce_map(CUtensorMap* m, const void* ptr, int64_t rows, int64
   cuuint32_t box[2] = {16, 32};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
