@@ -289,3 +289,40 @@ def test_graphed_streaming_encoder_matches_eager(B):
             assert torch.equal(got, w)
     for a, b in zip(runner.state[0] + runner.state[1], state[0] + state[1]):
         assert torch.equal(a, b.float())
+
+
+@pytest.mark.gpu
+def test_configs0_full_size_four_carried_segments(cuda_device):
+    """BASELINE.json configs[0] in full: LucyRNN 2-layer h=256 + CTC (V=1024), batch 8, 10 s
+    segments (1000 frames x 80), state carried over 4 segments, fp32 — logits, losses, final
+    state and the weight gradients accumulated over the 4 segments against the fp64 oracle
+    (closed form + autograd; ~20 s of CPU)."""
+    import statecatcher_b200 as sb
+    cfg = sb.LucyRNNConfig(input_dim=80, hidden_dim=256, num_layers=2, vocab_size=1024, fused_ops=True,
+                           layer_norm=False, is_training=True)
+    ocfg = LO.OracleConfig(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    P = LO.reference_init_params(ocfg, 7, out_std=0.02)
+    Pd = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    g = torch.Generator().manual_seed(1)
+    B, T, NS = 8, 1000, 4
+    xs = [torch.randn(B, T, 80, generator=g) for _ in range(NS)]
+    toks = [torch.randint(1, 1024, (B, 50), generator=g) for _ in range(NS)]
+    inl = [[T] * 7 + [600]] * NS
+    tgl = [[25 + 3 * b for b in range(B)]] * NS
+    ref_losses, ref_logits, ref_state = LO.train_segments(Pd, ocfg, [x.double() for x in xs], toks, inl, tgl, looped=False)
+    model = sb.LucyRNN(cfg).cuda()
+    model.load_state_dict(P)
+    crit = sb.CTCLoss(blank=0, zero_infinity=True)
+    state = None
+    for i in range(NS):
+        if state:
+            state = sb.detach_states(state)
+        logits, state = model(xs[i].cuda(), state) if state else model(xs[i].cuda())
+        loss = crit(logits.log_softmax(-1).transpose(0, 1), toks[i].cuda(), inl[i], tgl[i])     # the reference's own call shape
+        loss.backward()
+        np.testing.assert_allclose(logits.detach().cpu().numpy(), ref_logits[i].numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(loss.item(), ref_losses[i].item(), rtol=1e-4)
+    np.testing.assert_allclose(torch.stack(state[0]).cpu().numpy(), torch.stack(ref_state[0]).detach().numpy(), rtol=1e-4, atol=1e-5)
+    for k, p in model.named_parameters():
+        want = Pd[k].grad.numpy()
+        assert np.abs(p.grad.cpu().numpy() - want).max() <= 2e-4 * max(1e-3, np.abs(want).max()), k
