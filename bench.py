@@ -196,6 +196,17 @@ def reference_arm(args, W):
     print(json.dumps(line), flush=True)
 
 
+def _config_label(args, W, world):
+    """Which BASELINE.json config the workload is."""
+    if "rnnt" in W:
+        return "configs[3]"
+    if W.get("forward_only"):
+        return "configs[4], streaming half"
+    if args.workload == "cfg1":
+        return "configs[0]"
+    return "configs[1]" if world == 1 else f"configs[2], {W['B'] * world} streams"
+
+
 def workload_config(args, W, world):
     headname = f"RNN-T fused head (J={W['rnnt']['J']})" if "rnnt" in W else "CTC"
     if W.get("forward_only"):
@@ -204,7 +215,7 @@ def workload_config(args, W, world):
         mode = "training"
     return {"workload": f"LucyRNN {W['L']}-layer h={W['H']} + {headname} (V={W['V']}), {W['dtype']} {mode}, "
                         f"batch {W['B']} streams/GPU x {W['T']} frames x {W['F']} fbank, carried state "
-                        f"({'configs[1]' if world == 1 else 'configs[2], ' + str(W['B'] * world) + ' streams'})",
+                        f"({_config_label(args, W, world)})",
             "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": not W.get("forward_only", False),
             "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
             "cuda_graph": bool(getattr(args, "graph", False)) and bool(W.get("forward_only")),

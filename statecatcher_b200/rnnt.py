@@ -185,7 +185,13 @@ class _RNNTFusedFn(torch.autograd.Function):
         rows_max = B * min(chunk, max(T, 1)) * U1
         esz = torch.empty((), dtype=cd).element_size()
         need = B * T * U1 * (J + V) * esz
-        keep = keep_blocks if keep_blocks is not None else (T > 0 and need < 0.75 * torch.cuda.mem_get_info(dev)[0])
+        if keep_blocks is not None:
+            keep = keep_blocks
+        else:
+            # free = what the driver still has + what torch's caching allocator holds but is not using (after the
+            # first step the previous step's blocks sit there: cudaMemGetInfo alone would say "no room")
+            free = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            keep = T > 0 and need < 0.75 * free
         kept = []
         if not keep:
             joint_buf = torch.empty(rows_max, J, dtype=cd, device=dev)
