@@ -154,13 +154,15 @@ __device__ __forceinline__ float warp_row_lse(const T* __restrict__ x, int V, in
       const int i = (k * 32 + lane) * VW;
       if (i < V) raw[k].raw = __ldg(reinterpret_cast<const uint4*>(x + i));
     }
-    float f[4][VW];
+    // only the RAW 16-byte words stay live across the two passes (16 registers instead of 16 + 32 unpacked
+    // floats): these kernels are bound by bytes in flight per SM, i.e. by how many warps fit
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if ((k * 32 + lane) * VW < V) {
-        unpack(raw[k], f[k]);
+        float f[VW];
+        unpack(raw[k], f);
 #pragma unroll
-        for (int j = 0; j < VW; ++j) m = fmaxf(m, f[k][j]);
+        for (int j = 0; j < VW; ++j) m = fmaxf(m, f[j]);
       }
     }
     m = warp_max(m);
@@ -169,10 +171,12 @@ __device__ __forceinline__ float warp_row_lse(const T* __restrict__ x, int V, in
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if ((k * 32 + lane) * VW < V) {
+        float f[VW];
+        unpack(raw[k], f);
 #pragma unroll
         for (int j = 0; j < VW; ++j) {                        // exp(f - m) as one FFMA + one MUFU (no range fix-ups: the argument is <= 0)
           float e;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(f[k][j], 1.4426950408889634f, -mc2)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(f[j], 1.4426950408889634f, -mc2)));
           ssum += e;
         }
       }

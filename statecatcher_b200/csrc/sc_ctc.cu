@@ -56,7 +56,7 @@ constexpr int CTC_EB = 16;       // rows of emissions per bulk-copied shared-mem
 
 // ---- pass 1 ------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(CTC_WARPS * 32)
+__global__ void __launch_bounds__(CTC_WARPS * 32, 5)
 ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t stride_t,
                       const int64_t* __restrict__ targets, int64_t ldt,
                       const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,

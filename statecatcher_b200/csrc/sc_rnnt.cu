@@ -367,7 +367,7 @@ __global__ void joint_bwd_kernel(const T* __restrict__ dJ, const T* __restrict__
 // rows of joint logits [B, Tc, U1, V] for frames [t0, t0+Tc): lse per node + the two log-probs
 // into the skewed eb/el arrays
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 rnnt_lse_gather_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, int64_t ldl,
                        const int64_t* __restrict__ frame_lens, const int64_t* __restrict__ label_lens,
                        int B, int Tn, int t0, int Tc, int U1, int V, int U1p, int64_t blank,
