@@ -26,6 +26,10 @@
 // MUFU/FMNMX latency chain of each step exposed; (c) two timesteps per block barrier with a
 // 3-2-1 trapezoid of recomputed neighbour nodes — no change (0.54 ms): the two dependent
 // log-sum-exps, not the barrier, are the chain.
+// (d) pass 1 with the logits rows streamed through a shared-memory ring by bulk async copies
+// (8 consumer warps + a producer warp per CTA, 96 KB in flight per CTA, labels prefetched while the
+// row is awaited, emissions kept in registers): 0.192 ms against 0.185 ms for the register-staged
+// kernel at 40 warps per SM — bytes in flight are not what holds pass 1 at ~2.9 TB/s; not kept.
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
