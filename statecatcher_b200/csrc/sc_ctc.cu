@@ -86,14 +86,33 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
     // model) instead of by log2(V) per frame, which lets it re-centre 4x less often at the same
     // fp32 resolution.  The shift goes to cshift[b,t] and is added back into the likelihood.
     float c = NEG_INF;
-    for (int s = lane; s < S; s += 32) {
-      const float e = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
-      out[s] = e;
-      c = fmaxf(c, e);
+    constexpr int NL = 10;                                       // lattice nodes per lane kept in registers (S <= 320)
+    if (S <= 32 * NL) {
+      // straight-line: the lane's emissions stay in registers between the max and the single store
+      // (the two-pass loop below cost more instructions per frame than the V-wide log-sum-exp itself)
+      float e[NL];
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        const int s = lane + 32 * k;
+        const int lab = (s < S) ? ((s & 1) ? (int)tg[s >> 1] : (int)blank) : (int)blank;
+        e[k] = (ld_f(x + lab) - l) * 1.4426950408889634f;
+        if (s < S) c = fmaxf(c, e[k]);
+      }
+      c = warp_max(c);
+      if (!(c > -1e29f)) c = 0.f;                                // every lattice emission is -inf: leave the row alone
+#pragma unroll
+      for (int k = 0; k < NL; ++k)
+        if (lane + 32 * k < S) out[lane + 32 * k] = fmaxf(e[k] - c, -1e30f);   // -inf logits become the recursion's finite dead value
+    } else {
+      for (int s = lane; s < S; s += 32) {
+        const float e = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
+        out[s] = e;
+        c = fmaxf(c, e);
+      }
+      c = warp_max(c);
+      if (!(c > -1e29f)) c = 0.f;
+      for (int s = lane; s < S; s += 32) out[s] = fmaxf(out[s] - c, -1e30f);   // each lane re-reads its own stores
     }
-    c = warp_max(c);
-    if (!(c > -1e29f)) c = 0.f;                                  // every lattice emission is -inf: leave the row alone
-    for (int s = lane; s < S; s += 32) out[s] = fmaxf(out[s] - c, -1e30f);   // each lane re-reads its own stores; -inf logits become the recursion's finite dead value
     if (lane == 0) cshift[row] = c;
   }
 }
