@@ -572,3 +572,21 @@ def test_ctc_masked_vocabulary_entries(cuda_device):
     got = x.grad.cpu().numpy()
     assert np.isfinite(got).all() and (got[1] == 0).all() and (got[:, :, 9] == 0).all()
     np.testing.assert_allclose(got[[0, 2]], want[[0, 2]], rtol=2e-3, atol=2e-7)
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 80), (33, 1024), (5, 30), (1, 4), (129, 5124)])
+def test_cast_vectorised_and_scalar_paths_bit_exact(cuda_device, rows, cols):
+    """sc_cast both ways == torch's conversion bit for bit, on the 4-wide path (cols % 4 == 0,
+    aligned) and the scalar one, contiguous and with a row stride."""
+    from statecatcher_b200 import ops
+    g = torch.Generator().manual_seed(rows * 131 + cols)
+    x = (torch.randn(rows, cols, generator=g) * 3).cuda()
+    got = ops.cast(x, torch.bfloat16)
+    assert torch.equal(got.view(torch.int16), x.to(torch.bfloat16).view(torch.int16))
+    back = ops.cast(got, torch.float32)
+    assert torch.equal(back, got.float())
+    wide = (torch.randn(rows, cols + 8, generator=g)).cuda()
+    view = wide[:, 4:4 + cols]                               # row stride cols+8, 16-byte aligned start
+    assert torch.equal(ops.cast(view, torch.bfloat16).view(torch.int16), view.to(torch.bfloat16).view(torch.int16))
+    odd = wide[:, 1:1 + cols]                                # misaligned start: scalar path
+    assert torch.equal(ops.cast(odd, torch.bfloat16).view(torch.int16), odd.to(torch.bfloat16).view(torch.int16))
