@@ -17,4 +17,13 @@ Parity status
   not in requirements.txt, and its call site model.py:97-105 matches no
   published API).  Restates the Graves-2012 transducer DP and is cross-checked
   against ``torchaudio.functional.rnnt_loss``.
+* Glue around the encoder: ``lucy_oracle.detach_states`` + the CTC composition, the RNN-T
+  predictor/joiner (joiner_oracle.py, with a hand backward) and the greedy decoder
+  (decoder_oracle.py) are PINNED on tests/golden/glue_cases.npz, produced by running the
+  reference's own ``model.compute_loss`` / ``ASRModel`` / ``RNNTPredictorJoiner`` /
+  ``RNNTCompactPredictorJoiner`` / ``decoder.ctc_greedy_decoder`` (tests/golden/make_glue_golden.py;
+  ``xlstm`` stubbed, the Triton encoder replaced by the reference's native ``LucyRNN``).  The
+  transducer loss VALUE under the joiner stays the torchaudio substitute pin.
+* Frontend (frontend_oracle.py): PINNED on golden vectors from the reference's own torchaudio
+  objects (tests/golden/make_frontend_golden.py).
 """

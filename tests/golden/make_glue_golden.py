@@ -116,9 +116,9 @@ class WarpRNNTStandIn:
         return nll.mean()
 
 
-def joiner_cases(out, seed):
+def joiner_cases(out, tag, dims, seed):
     g = torch.Generator().manual_seed(seed)
-    B, T, U, De, E, J, V = 3, 6, 4, 10, 5, 8, 10
+    B, T, U, De, E, J, V = dims
     pad = ref_model.RNNTPredictorJoiner(De, E, J, V, debug=False)
     sd = {k: 0.5 * torch.randn(v.shape, generator=g) for k, v in pad.state_dict().items()}
     pad.load_state_dict(sd)
@@ -127,14 +127,14 @@ def joiner_cases(out, seed):
     assert list(cj.state_dict()) == list(sd)
     enc_out = torch.randn(B, T, De, generator=g)
     tokens = torch.randint(1, V, (B, U), generator=g)
-    in_lens, tgt_lens = torch.tensor([T, 4, 1]), torch.tensor([U, 2, 0])
+    in_lens, tgt_lens = torch.tensor([T, T - 2, 1]), torch.tensor([U, 2, 0])
     prefix = torch.cat([torch.zeros(B, 1, dtype=tokens.dtype), tokens], 1)
     for k, v in sd.items():
-        out["joiner/param/" + k] = v.numpy()
-    out["joiner/enc_out"], out["joiner/tokens"], out["joiner/prefix"] = enc_out.numpy(), tokens.numpy(), prefix.numpy()
-    out["joiner/in_lens"], out["joiner/tgt_lens"] = in_lens.numpy(), tgt_lens.numpy()
-    out["joiner/logits_padded"] = pad(enc_out, prefix).detach().numpy()
-    out["joiner/logits_compact"] = cj(enc_out, prefix, in_lens, tgt_lens).detach().numpy()
+        out[tag + "/param/" + k] = v.numpy()
+    out[tag + "/enc_out"], out[tag + "/tokens"], out[tag + "/prefix"] = enc_out.numpy(), tokens.numpy(), prefix.numpy()
+    out[tag + "/in_lens"], out[tag + "/tgt_lens"] = in_lens.numpy(), tgt_lens.numpy()
+    out[tag + "/logits_padded"] = pad(enc_out, prefix).detach().numpy()
+    out[tag + "/logits_compact"] = cj(enc_out, prefix, in_lens, tgt_lens).detach().numpy()
 
     # compute_loss(mode="rnnt") around the padded joiner: the "model" is anything returning (enc_out, state)
     class Enc(nn.Module):
@@ -147,10 +147,10 @@ def joiner_cases(out, seed):
                                              blank_id=0, use_rnnt_joiner=pad, input_state=None, args=args)
     pad.zero_grad()
     loss.backward()
-    out["joiner/rnnt_loss"] = loss.detach().numpy()
-    out["joiner/rnnt_grad_enc_out"] = e.grad.numpy()
+    out[tag + "/rnnt_loss"] = loss.detach().numpy()
+    out[tag + "/rnnt_grad_enc_out"] = e.grad.numpy()
     for k, q in pad.named_parameters():
-        out["joiner/rnnt_grad/" + k] = q.grad.numpy()
+        out[tag + "/rnnt_grad/" + k] = q.grad.numpy()
 
 
 def decoder_cases(out, seed):
@@ -171,7 +171,8 @@ def main():
     out = {}
     ctc_pipeline(out, "ctc_plain", proj_dim=-1, seed=401)
     ctc_pipeline(out, "ctc_proj", proj_dim=6, seed=402)
-    joiner_cases(out, 403)
+    joiner_cases(out, "joiner", (3, 6, 4, 10, 5, 8, 10), 403)          # odd sizes: scalar kernel paths
+    joiner_cases(out, "joiner16", (3, 11, 4, 24, 8, 16, 16), 405)      # 16-byte-aligned rows: vector kernel paths
     decoder_cases(out, 404)
     path = os.path.join(HERE, "glue_cases.npz")
     np.savez_compressed(path, **out)

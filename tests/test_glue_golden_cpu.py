@@ -71,8 +71,9 @@ def test_golden_masked_frames_do_not_reach_the_loss(G):
     assert (d[1, cut:] == 0).all() and np.abs(d[1, :cut]).max() > 0
 
 
-def test_joiner_oracle_matches_reference_classes(G):
-    J = _sub(G, "joiner/")
+@pytest.mark.parametrize("case", ["joiner", "joiner16"])
+def test_joiner_oracle_matches_reference_classes(G, case):
+    J = _sub(G, case + "/")
     P = _sub(J, "param/")
     assert list(P) == ["embedding.weight", "enc_proj.weight", "enc_proj.bias", "pred_proj.weight", "pred_proj.bias",
                        "joiner.weight", "joiner.bias"]                               # state_dict order, model.py:115-127
@@ -87,10 +88,11 @@ def test_joiner_oracle_matches_reference_classes(G):
     np.testing.assert_allclose(np.concatenate(rows), comp, rtol=0, atol=1e-12)
 
 
-def test_rnnt_compute_loss_oracle_matches_reference_composition(G):
+@pytest.mark.parametrize("case", ["joiner", "joiner16"])
+def test_rnnt_compute_loss_oracle_matches_reference_composition(G, case):
     """compute_loss(mode='rnnt') of the reference around its padded joiner (criterion: torchaudio
     behind warp_rnnt's keyword signature): loss, d enc_out, every joiner gradient."""
-    J = _sub(G, "joiner/")
+    J = _sub(G, case + "/")
     loss, d_enc, g = JO.rnnt_head_loss_and_grads(_sub(J, "param/"), J["enc_out"], J["tokens"], J["in_lens"], J["tgt_lens"])
     np.testing.assert_allclose(loss, J["rnnt_loss"], rtol=1e-5)
     np.testing.assert_allclose(d_enc, J["rnnt_grad_enc_out"], rtol=1e-4, atol=1e-6)
