@@ -124,3 +124,46 @@ def test_rnnt_oracle_matches_torchaudio_golden(case):
                                                     G[case + "/frame_lens"], G[case + "/label_lens"])
     np.testing.assert_allclose(nll, G[case + "/nll"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(dx, G[case + "/grad"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_ctc_oracle_matches_live_torch_on_random_ragged_batches(seed, reduction):
+    """Beyond the fixed edge cases: seeded ragged batches (repeated labels, short inputs, empty and
+    infeasible utterances mixed in) against the installed torch's CPU ctc_loss in fp64 — the very
+    call the reference makes (train.py:142, model.py:70-71)."""
+    rng = np.random.default_rng(1000 + seed)
+    B, T, V = int(rng.integers(1, 6)), int(rng.integers(1, 40)), int(rng.integers(2, 12))
+    Umax = max(1, int(rng.integers(1, 12)))
+    logits = rng.normal(size=(B, T, V)) * 2.0
+    in_lens = [int(rng.integers(0, T + 1)) for _ in range(B)]
+    in_lens[0] = T
+    tgt_lens = [int(rng.integers(0, Umax + 1)) for _ in range(B)]
+    tokens = rng.integers(1, V, size=(B, Umax))
+    if seed % 3 == 0:                                            # runs of one label: needs blanks between repeats
+        tokens[:] = tokens[:, :1]
+    x = torch.tensor(logits, requires_grad=True)
+    want = torch.nn.functional.ctc_loss(x.log_softmax(-1).transpose(0, 1), torch.tensor(tokens), in_lens, tgt_lens,
+                                        blank=0, reduction=reduction, zero_infinity=True)
+    want.backward()
+    loss, nll, grad = ctc_oracle.ctc_loss_and_grad(logits, tokens, in_lens, tgt_lens, reduction=reduction)
+    np.testing.assert_allclose(loss, want.item(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(grad, x.grad.numpy(), rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_rnnt_oracle_matches_live_torchaudio_on_random_ragged_batches(seed):
+    TAF = pytest.importorskip("torchaudio.functional")
+    rng = np.random.default_rng(2000 + seed)
+    B, T, U, V = int(rng.integers(1, 5)), int(rng.integers(1, 14)), int(rng.integers(0, 7)), int(rng.integers(2, 9))
+    logits = rng.normal(size=(B, T, U + 1, V)).astype(np.float32)
+    fl = [T] + [int(rng.integers(1, T + 1)) for _ in range(B - 1)]
+    ll = [U] + [int(rng.integers(0, U + 1)) for _ in range(B - 1)]
+    labels = rng.integers(1, V, size=(B, max(U, 1)))[:, :U] if U else np.zeros((B, 0), np.int64)
+    x = torch.tensor(logits, requires_grad=True)
+    want = TAF.rnnt_loss(x, torch.tensor(labels).int(), torch.tensor(fl).int(), torch.tensor(ll).int(), blank=0,
+                         reduction="none")
+    want.sum().backward()
+    nll, dx = rnnt_oracle.rnnt_loss_and_grad_logits(logits, labels, fl, ll)
+    np.testing.assert_allclose(nll, want.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dx, x.grad.numpy(), rtol=1e-4, atol=1e-6)
