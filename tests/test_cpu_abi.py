@@ -33,6 +33,38 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.sc_build_info(buf, 128) == 0 and b"sm_100a" in buf.value
 
 
+def test_ctypes_signatures_agree_with_the_header_argument_by_argument():
+    """Every prototype in include/statecatcher_b200.h against the ctypes argtypes/restype in
+    _lib.SIGNATURES: argument count and class (pointer / int64_t / int / float).  A drifted
+    binding would pass garbage to a kernel instead of failing."""
+    import ctypes
+    from statecatcher_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "statecatcher_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    protos = re.findall(r"([A-Za-z_][\w\s\*]*?)\b(sc_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt)
+    assert {n for _, n, _ in protos} == set(_lib.SIGNATURES)
+
+    def klass(decl):
+        decl = decl.strip()
+        if decl in ("", "void"):
+            return None
+        if "*" in decl:
+            return "P"
+        t = re.sub(r"\b[A-Za-z_]\w*$", "", decl).replace("const", "").strip()      # drop the parameter name
+        return {"int64_t": "I64", "int": "I32", "float": "F32"}[t]
+
+    names = {ctypes.c_void_p: "P", ctypes.c_char_p: "P", ctypes.c_int64: "I64", ctypes.c_int: "I32", ctypes.c_float: "F32"}
+    for ret, name, args in protos:
+        declared = [k for k in (klass(a) for a in args.split(",")) if k]
+        bound = [names[t] for t in _lib.SIGNATURES[name]]
+        assert declared == bound, (name, declared, bound)
+        ret = ret.strip().splitlines()[-1].replace("extern", "").replace("SC_API", "").strip()   # text before it: macros
+        want_ret = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "const char*": ctypes.c_char_p,
+                    "const char *": ctypes.c_char_p}[ret]
+        assert _lib._RESTYPES.get(name, ctypes.c_int) is want_ret, (name, ret)
+
+
 def test_argument_errors_are_return_codes_not_crashes():
     """Bad arguments come back as negative SC_E_* codes before any launch (safe without a GPU)."""
     from statecatcher_b200 import _lib
