@@ -11,7 +11,8 @@ backward pass finishes them: output_proj first, layer 0 last), launches one asyn
 NCCL all-reduce per bucket from a post-accumulate-grad hook the moment the bucket's last
 gradient lands (so communication over NVLink overlaps the rest of the backward), and joins
 all buckets in an end-of-backward callback.  Averaging by world size reproduces
-``reduction='mean'`` over the GLOBAL batch when shards are equal (mean of rank means).
+``reduction='mean'`` over the GLOBAL batch when shards are equal (mean of rank means); for
+unequal shards multiply the local loss by ``shard_loss_scale`` first.
 """
 from __future__ import annotations
 
@@ -31,6 +32,16 @@ def partition_streams(n_streams: int, world_size: int, rank: int) -> range:
     base, rem = divmod(n_streams, world_size)
     start = rank * base + min(rank, rem)
     return range(start, start + base + (1 if rank < rem else 0))
+
+
+def shard_loss_scale(n_local: int, n_global: int, world_size: int) -> float:
+    """Factor for a rank's ``reduction='mean'`` loss when shards are NOT equal (n_streams not a
+    multiple of the world size, or a rank's streams ran out): the wrapper averages rank
+    gradients, i.e. computes ``(1/W) * sum_r mean_r``; scaling rank r's loss by
+    ``n_local * W / n_global`` turns that into the mean over the global batch.  1.0 for equal shards."""
+    if n_global <= 0 or world_size <= 0 or not (0 <= n_local <= n_global):
+        raise ValueError("shard_loss_scale: need 0 <= n_local <= n_global, n_global > 0, world_size > 0")
+    return n_local * world_size / n_global
 
 
 class _Bucket:

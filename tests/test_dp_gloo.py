@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 import torch.nn as nn
 
 from oracle import lucy_oracle as LO
-from statecatcher_b200.dp import StreamDataParallel, partition_streams
+from statecatcher_b200.dp import StreamDataParallel, partition_streams, shard_loss_scale
 
 
 def test_partition_streams():
@@ -117,3 +117,50 @@ def test_stream_data_parallel_matches_single_process(tmp_path):
         torch.testing.assert_close(a, b[:2].detach(), rtol=1e-9, atol=1e-12)
     # no_sync grad differs from the synchronised one (it is the local shard's only)
     assert not torch.allclose(got["local_only"], got["grads"][net.names[0]])
+
+
+# ---- unequal shards: 5 streams over 2 ranks (3 + 2), local losses weighted by shard_loss_scale ----
+def _uneven_problem():
+    cfg = LO.OracleConfig(input_dim=6, hidden_dim=8, num_layers=1, vocab_size=7, fused_ops=True, layer_norm=False)
+    g = torch.Generator().manual_seed(23)
+    B, T = 5, 8
+    x = torch.randn(B, T, 6, generator=g, dtype=torch.float64)
+    toks = torch.randint(1, 7, (B, 3), generator=g)
+    return cfg, B, T, x, toks, [T, T, T - 3, T, T - 1], [3, 1, 2, 3, 2]
+
+
+def _uneven_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        cfg, B, T, x, toks, inl, tgl = _uneven_problem()
+        net = _OracleNet(cfg, 9)
+        ddp = StreamDataParallel(net)
+        mine = partition_streams(B, world, rank)
+        sl = slice(mine.start, mine.stop)
+        logits, _ = ddp(x[sl])
+        loss = nn.CTCLoss(blank=0, zero_infinity=True)(logits.log_softmax(-1).transpose(0, 1), toks[sl], inl[sl], tgl[sl])
+        (loss * shard_loss_scale(len(mine), B, world)).backward()
+        if rank == 1:
+            torch.save({k: (p.grad.clone() if p.grad is not None else None) for k, p in zip(net.names, net.params)}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unequal_shards_reproduce_the_global_mean(tmp_path):
+    assert shard_loss_scale(64, 512, 8) == 1.0 and shard_loss_scale(3, 5, 2) == 1.2 and shard_loss_scale(0, 5, 2) == 0.0
+    with pytest.raises(ValueError):
+        shard_loss_scale(6, 5, 2)
+    out = str(tmp_path / "rank1.pt")
+    mp.spawn(_uneven_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    cfg, B, T, x, toks, inl, tgl = _uneven_problem()
+    net = _OracleNet(cfg, 9)
+    logits, _ = net(x)
+    nn.CTCLoss(blank=0, zero_infinity=True)(logits.log_softmax(-1).transpose(0, 1), toks, inl, tgl).backward()
+    for k, p in zip(net.names, net.params):
+        if p.grad is None:
+            assert got[k] is None, k
+            continue
+        torch.testing.assert_close(got[k], p.grad, rtol=1e-9, atol=1e-12, msg=k)
