@@ -278,6 +278,11 @@ int sc_scale_grads(float* g, int64_t n, const double* sumsq, float max_norm, voi
 int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int64_t step, const double* sumsq,
                  float max_norm, int decoupled, void* stream);
+/* lion_step  : one Lion update (train.py:125-131 constructs `lion_pytorch.Lion`, absent upstream and
+ *              unpinned; the published rule): p *= 1 - lr*wd; p -= lr*sign(beta1*m + (1-beta1)*g);
+ *              m = beta2*m + (1-beta2)*g.  sumsq / max_norm as in adam_step. */
+int sc_lion_step(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
+                 float weight_decay, const double* sumsq, float max_norm, void* stream);
 
 /* ---------------------------------------------------------------- frontend ------------
  * Replaces make_frontend (model.py:250-279): torchaudio MFCC(n_mfcc=80, dct_type=2, norm='ortho',

@@ -62,6 +62,24 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// Lion (Chen et al. 2023, "Symbolic Discovery of Optimization Algorithms", Algorithm 2; the rule the
+// absent `lion_pytorch.Lion` of train.py:125-131 implements): decoupled decay, the SIGN of the
+// beta1-interpolated momentum as the update, momentum tracked with beta2.  One state tensor.
+__global__ void __launch_bounds__(256)
+lion_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, int64_t n, float lr,
+                 float b1, float b2, float wd, const double* __restrict__ sumsq, float max_norm) {
+  const float c = clip_coef(sumsq, max_norm);
+  const float keep = 1.f - lr * wd;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * c;
+    const float mi = m[i];
+    const float u = fmaf(b1, mi, (1.f - b1) * gi);
+    const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
+    p[i] = fmaf(-lr, sgn, p[i] * keep);
+    m[i] = fmaf(b2, mi, (1.f - b2) * gi);
+  }
+}
+
 }  // namespace sc
 
 using namespace sc;
@@ -94,5 +112,15 @@ extern "C" int sc_adam_step(float* p, const float* g, float* m, float* v, int64_
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adam_step_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
       bc2s, sumsq, max_norm, decoupled);
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_lion_step(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
+                            float weight_decay, const double* sumsq, float max_norm, void* stream) {
+  SC_CHECK_ARG(n >= 0, SC_E_BADARG);
+  if (n == 0) return 0;
+  SC_CHECK_ARG(p && g && m, SC_E_BADARG);
+  lion_step_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, sumsq,
+      max_norm);
   SC_LAUNCH_RET();
 }

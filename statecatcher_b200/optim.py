@@ -1,4 +1,4 @@
-"""Fused gradient clipping + Adam/AdamW for the parameters of the path.
+"""Fused gradient clipping + Adam/AdamW/Lion for the parameters of the path.
 
 The reference clips with ``torch.nn.utils.clip_grad_norm_(model.parameters(), 50)``
 (train.py:553), optionally logs the norm with one ``.item()`` sync per parameter
@@ -6,7 +6,10 @@ The reference clips with ``torch.nn.utils.clip_grad_norm_(model.parameters(), 50
 ``FusedAdam`` does all three with two kernels per tensor and no host synchronisation: the
 global norm stays on the device (``.grad_norm`` is a 0-dim device tensor) and the update kernel
 applies the clip coefficient on the fly.  ``clip_grad_norm_`` is the standalone clip with the
-signature and return value of torch's.
+signature and return value of torch's.  ``Lion`` is the third choice of train.py's
+``--optimizer`` (train.py:125-131 builds ``lion_pytorch.Lion(params, lr=, weight_decay=)``; that
+package is absent and unpinned upstream, so the published update rule is what is implemented,
+with the package's constructor signature and defaults).
 """
 from __future__ import annotations
 
@@ -86,4 +89,48 @@ class FusedAdam(torch.optim.Optimizer):
                 call("sc_adam_step", ptr(p), ptr(p.grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
                      float(grp["lr"]), float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]),
                      int(st["step"]), ptr(acc), float(self.max_grad_norm or 0.0), int(bool(grp["decoupled"])), stream())
+        return loss
+
+
+class Lion(torch.optim.Optimizer):
+    """``lion_pytorch.Lion(params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0)`` (the call of
+    train.py:125-131) as one kernel per tensor: decoupled decay, ``p -= lr * sign(b1*m + (1-b1)*g)``,
+    ``m = b2*m + (1-b2)*g``; ``max_grad_norm`` fuses the global-norm clip like ``FusedAdam``."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0, max_grad_norm=None):
+        if lr <= 0.0:
+            raise ValueError("lr must be positive")
+        if not all(0.0 <= b <= 1.0 for b in betas):
+            raise ValueError("betas must lie in [0, 1]")
+        super().__init__(params, dict(lr=lr, betas=betas, weight_decay=weight_decay))
+        self.max_grad_norm = max_grad_norm
+        self.grad_norm = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        allp = [p for grp in self.param_groups for p in grp["params"]]
+        pgs = _grads(allp)
+        if not pgs:
+            return loss
+        acc = None
+        if self.max_grad_norm is not None:
+            acc = _global_sumsq(pgs, pgs[0][1].device)
+            self.grad_norm = acc.sqrt().float()
+        for grp in self.param_groups:
+            b1, b2 = grp["betas"]
+            for p in grp["params"]:
+                if p.grad is None:
+                    continue
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError("fused optimizer expects contiguous fp32 parameters")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p)
+                call("sc_lion_step", ptr(p), ptr(p.grad), ptr(st["exp_avg"]), p.numel(), float(grp["lr"]),
+                     float(b1), float(b2), float(grp["weight_decay"]), ptr(acc), float(self.max_grad_norm or 0.0),
+                     stream())
         return loss

@@ -1,0 +1,71 @@
+"""GPU: fused Lion step (sc_lion_step, optim.Lion) vs oracle/optim_oracle.py over several steps.
+lion_pytorch (train.py:125-131) is absent upstream: parity unpinned, the published rule is the oracle.
+The sign of an interpolation that fp32 cannot resolve from 0 is excluded element-wise."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.1])
+@pytest.mark.parametrize("max_norm", [None, 0.5, 1e9])
+def test_lion_matches_oracle(cuda_device, wd, max_norm):
+    from statecatcher_b200.optim import Lion
+    from oracle.optim_oracle import lion_step, clip_coef
+    rng = np.random.default_rng(7)
+    shapes = [(33, 17), (5,), (257, 64), (1,)]
+    lr, betas = 3e-3, (0.9, 0.99)
+    ref_p = [rng.standard_normal(s).astype(np.float32).astype(np.float64) for s in shapes]
+    ref_m = [np.zeros(s) for s in shapes]
+    my_p = [torch.from_numpy(p.astype(np.float32)).cuda().requires_grad_(True) for p in ref_p]
+    opt = Lion(my_p, lr=lr, betas=betas, weight_decay=wd, max_grad_norm=max_norm)
+    ok = [np.ones(s, bool) for s in shapes]
+    for it in range(4):
+        grads = [(rng.standard_normal(s) * (3.0 if it == 1 else 0.3)).astype(np.float32) for s in shapes]
+        for q, gr in zip(my_p, grads):
+            q.grad = torch.from_numpy(gr).cuda()
+        coef = 1.0
+        if max_norm is not None:
+            total, coef = clip_coef(grads, max_norm)
+        opt.step()
+        if max_norm is not None:
+            np.testing.assert_allclose(opt.grad_norm.item(), total, rtol=1e-5)
+        for i, gr in enumerate(grads):
+            ref_p[i], ref_m[i], u = lion_step(ref_p[i], gr.astype(np.float64) * coef, ref_m[i], lr, betas, wd)
+            ok[i] &= np.abs(u) > 1e-6 * (np.abs(ref_m[i]) + np.abs(gr) + 1e-30)
+        for i, q in enumerate(my_p):
+            got = q.detach().cpu().numpy().astype(np.float64)
+            assert ok[i].mean() > 0.99
+            np.testing.assert_allclose(got[ok[i]], ref_p[i][ok[i]], rtol=2e-6, atol=2e-6)
+            np.testing.assert_allclose(opt.state[q]["exp_avg"].cpu().numpy(), ref_m[i], rtol=2e-5, atol=1e-6)
+
+
+def test_lion_first_step_moves_by_lr_exactly(cuda_device):
+    """Zero momentum: every element with a non-zero gradient moves by exactly lr (fp32), zeros stay."""
+    from statecatcher_b200.optim import Lion
+    p = torch.zeros(1000, device="cuda", requires_grad=True)
+    g = torch.randn(1000, generator=torch.Generator().manual_seed(0))
+    g[::10] = 0.0
+    p.grad = g.cuda()
+    Lion([p], lr=0.25).step()
+    assert torch.equal(p.detach().cpu(), -0.25 * torch.sign(g))
+
+
+def test_lion_shim_and_errors(cuda_device):
+    import os, sys, importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "shims"))
+    try:
+        sys.modules.pop("lion_pytorch", None)
+        from statecatcher_b200.optim import Lion
+        assert importlib.import_module("lion_pytorch").Lion is Lion
+    finally:
+        sys.path.remove(os.path.join(root, "shims"))
+        sys.modules.pop("lion_pytorch", None)
+    with pytest.raises(ValueError):
+        Lion([torch.zeros(2, device="cuda", requires_grad=True)], lr=0.0)
+    h = torch.zeros(4, device="cuda", dtype=torch.float16, requires_grad=True)
+    h.grad = torch.zeros_like(h)
+    with pytest.raises(TypeError):
+        Lion([h]).step()

@@ -167,3 +167,20 @@ def test_rnnt_oracle_matches_live_torchaudio_on_random_ragged_batches(seed):
     nll, dx = rnnt_oracle.rnnt_loss_and_grad_logits(logits, labels, fl, ll)
     np.testing.assert_allclose(nll, want.detach().numpy(), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(dx, x.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_lion_oracle_known_answers():
+    """Hand-worked Lion steps (published rule; lion_pytorch itself is absent: parity unpinned)."""
+    from oracle.optim_oracle import lion_step, clip_coef
+    p = np.array([1.0, -2.0, 0.5, 3.0]); g = np.array([0.2, -0.1, 0.0, -4.0]); m = np.array([0.0, 1.0, 0.0, 1.0])
+    # u = .9m + .1g = [.02, .89, 0, .5]; sign = [1, 1, 0, 1]
+    p1, m1, u = lion_step(p, g, m, lr=0.1, betas=(0.9, 0.99), weight_decay=0.5)
+    np.testing.assert_allclose(u, [0.02, 0.89, 0.0, 0.5], atol=1e-15)
+    np.testing.assert_allclose(p1, [0.95 - 0.1, -1.9 - 0.1, 0.475, 2.85 - 0.1], atol=1e-15)
+    np.testing.assert_allclose(m1, [0.002, 0.989, 0.0, 0.95], atol=1e-15)
+    # first step from zero momentum moves every element with a non-zero gradient by exactly lr
+    p2, _, _ = lion_step(p, g, np.zeros(4), lr=1e-4)
+    np.testing.assert_allclose(p2 - p, -1e-4 * np.sign(g), atol=1e-18)
+    total, coef = clip_coef([np.array([3.0, 0.0]), np.array([4.0])], 1.0)
+    assert total == 5.0 and abs(coef - 1.0 / (5.0 + 1e-6)) < 1e-15
+    assert clip_coef([np.array([0.3])], 1.0)[1] == 1.0
