@@ -7,17 +7,19 @@
 
 namespace sc {
 
+// head = elements in front of the first 16-byte boundary (0 for torch allocations; a view may start anywhere)
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ acc) {
+sumsq_kernel(const float* __restrict__ g, int64_t n, int64_t head, double* __restrict__ acc) {
   float s = 0.f;
-  const int64_t n4 = n / 4;
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = (n - head) / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g + head);
+  for (int64_t i = tid; i < n4; i += nth) {
     const float4 v = g4[i];
     s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
   }
-  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    s = fmaf(g[i], g[i], s);
+  for (int64_t i = tid; i < head; i += nth) s = fmaf(g[i], g[i], s);
+  for (int64_t i = head + n4 * 4 + tid; i < n; i += nth) s = fmaf(g[i], g[i], s);
   __shared__ float red[8];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -45,52 +47,97 @@ scale_grads_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ 
 }
 
 // decoupled = 1: AdamW (p *= 1 - lr*wd);  decoupled = 0: Adam with L2 (g += wd*p)
+struct AdamArgs { float lr, b1, b2, eps, wd, step, bc2_sqrt, c; int decoupled; };
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  float pi = p;
+  float gi = g * a.c;
+  if (a.decoupled) pi *= 1.f - a.lr * a.wd; else gi = fmaf(a.wd, pi, gi);
+  const float mi = fmaf(a.b1, m, (1.f - a.b1) * gi);
+  const float vi = fmaf(a.b2, v, (1.f - a.b2) * gi * gi);
+  m = mi; v = vi;
+  p = pi - a.step * mi / (sqrtf(vi) / a.bc2_sqrt + a.eps);
+}
+
+// VEC = 1: all four arrays are 16-byte aligned, the body moves float4 words (seven 128-bit accesses per
+// four elements) and the scalar loop only sees the n % 4 tail; VEC = 0: scalar throughout.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                  const double* __restrict__ sumsq, float max_norm, int decoupled) {
-  const float c = clip_coef(sumsq, max_norm);
-  const float step = lr / bc1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float pi = p[i];
-    float gi = g[i] * c;
-    if (decoupled) pi *= 1.f - lr * wd; else gi = fmaf(wd, pi, gi);
-    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-    m[i] = mi; v[i] = vi;
-    p[i] = pi - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  const AdamArgs a{lr, b1, b2, eps, wd, lr / bc1, bc2_sqrt, clip_coef(sumsq, max_norm), decoupled};
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (VEC) {
+    const int64_t n4 = n / 4;
+    float4* p4 = reinterpret_cast<float4*>(p); const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
+    for (int64_t i = tid; i < n4; i += nth) {
+      float4 pp = p4[i], mm = m4[i], vv = v4[i];
+      const float4 gg = g4[i];
+      adam_elem(pp.x, gg.x, mm.x, vv.x, a); adam_elem(pp.y, gg.y, mm.y, vv.y, a);
+      adam_elem(pp.z, gg.z, mm.z, vv.z, a); adam_elem(pp.w, gg.w, mm.w, vv.w, a);
+      p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    }
+    done = n4 * 4;
   }
+  for (int64_t i = done + tid; i < n; i += nth) adam_elem(p[i], g[i], m[i], v[i], a);
 }
 
 // Lion (Chen et al. 2023, "Symbolic Discovery of Optimization Algorithms", Algorithm 2; the rule the
 // absent `lion_pytorch.Lion` of train.py:125-131 implements): decoupled decay, the SIGN of the
 // beta1-interpolated momentum as the update, momentum tracked with beta2.  One state tensor.
+struct LionArgs { float lr, b1, b2, keep, c; };
+
+__device__ __forceinline__ void lion_elem(float& p, float g, float& m, const LionArgs& a) {
+  const float gi = g * a.c;
+  const float mi = m;
+  const float u = fmaf(a.b1, mi, (1.f - a.b1) * gi);
+  const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
+  p = fmaf(-a.lr, sgn, p * a.keep);
+  m = fmaf(a.b2, mi, (1.f - a.b2) * gi);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
 lion_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, int64_t n, float lr,
                  float b1, float b2, float wd, const double* __restrict__ sumsq, float max_norm) {
-  const float c = clip_coef(sumsq, max_norm);
-  const float keep = 1.f - lr * wd;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * c;
-    const float mi = m[i];
-    const float u = fmaf(b1, mi, (1.f - b1) * gi);
-    const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
-    p[i] = fmaf(-lr, sgn, p[i] * keep);
-    m[i] = fmaf(b2, mi, (1.f - b2) * gi);
+  const LionArgs a{lr, b1, b2, 1.f - lr * wd, clip_coef(sumsq, max_norm)};
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (VEC) {
+    const int64_t n4 = n / 4;
+    float4* p4 = reinterpret_cast<float4*>(p); const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    for (int64_t i = tid; i < n4; i += nth) {
+      float4 pp = p4[i], mm = m4[i];
+      const float4 gg = g4[i];
+      lion_elem(pp.x, gg.x, mm.x, a); lion_elem(pp.y, gg.y, mm.y, a);
+      lion_elem(pp.z, gg.z, mm.z, a); lion_elem(pp.w, gg.w, mm.w, a);
+      p4[i] = pp; m4[i] = mm;
+    }
+    done = n4 * 4;
   }
+  for (int64_t i = done + tid; i < n; i += nth) lion_elem(p[i], g[i], m[i], a);
 }
 
 }  // namespace sc
 
 using namespace sc;
 
+static bool aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
 static unsigned opt_grid(int64_t n) { return (unsigned)min((int64_t)148 * 8, cdiv(n, 1024) > 0 ? cdiv(n, 1024) : 1); }
 
 extern "C" int sc_sumsq_accum(const float* g, int64_t n, double* acc, void* stream) {
   SC_CHECK_ARG(n >= 0 && acc, SC_E_BADARG);
   if (n == 0) return 0;
-  SC_CHECK_ARG(g && ((uintptr_t)g & 15) == 0, SC_E_ALIGN);
-  sumsq_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(g, n, acc);
+  SC_CHECK_ARG(g && ((uintptr_t)g & 3) == 0, SC_E_ALIGN);
+  int64_t head = (int64_t)((16 - ((uintptr_t)g & 15)) & 15) / 4;
+  if (head > n) head = n;
+  sumsq_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(g, n, head, acc);
   SC_LAUNCH_RET();
 }
 
@@ -110,8 +157,12 @@ extern "C" int sc_adam_step(float* p, const float* g, float* m, float* v, int64_
   SC_CHECK_ARG(p && g && m && v, SC_E_BADARG);
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  adam_step_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
-      bc2s, sumsq, max_norm, decoupled);
+  if (aligned16(p, g, m, v))
+    adam_step_kernel<1><<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+        bc1, bc2s, sumsq, max_norm, decoupled);
+  else
+    adam_step_kernel<0><<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+        bc1, bc2s, sumsq, max_norm, decoupled);
   SC_LAUNCH_RET();
 }
 
@@ -120,7 +171,11 @@ extern "C" int sc_lion_step(float* p, const float* g, float* m, int64_t n, float
   SC_CHECK_ARG(n >= 0, SC_E_BADARG);
   if (n == 0) return 0;
   SC_CHECK_ARG(p && g && m, SC_E_BADARG);
-  lion_step_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, sumsq,
-      max_norm);
+  if (aligned16(p, g, m, m))
+    lion_step_kernel<1><<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, sumsq,
+        max_norm);
+  else
+    lion_step_kernel<0><<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, sumsq,
+        max_norm);
   SC_LAUNCH_RET();
 }

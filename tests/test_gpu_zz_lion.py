@@ -69,3 +69,51 @@ def test_lion_shim_and_errors(cuda_device):
     h.grad = torch.zeros_like(h)
     with pytest.raises(TypeError):
         Lion([h]).step()
+
+
+@pytest.mark.parametrize("kind", ["adam", "lion"])
+def test_vector_and_scalar_bodies_agree_bitwise(cuda_device, kind):
+    """16-byte aligned tensors take the float4 body, a view that starts 4 bytes into an allocation
+    takes the scalar one: same arithmetic per element, so three steps must agree bit for bit."""
+    from statecatcher_b200.optim import FusedAdam, Lion
+    n = 4099
+    g = torch.Generator().manual_seed(11)
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) for _ in range(3)]
+
+    def run(offset):
+        base = torch.zeros(n + 8, device="cuda")
+        p = base[offset:offset + n]
+        p.copy_(p0.cuda())
+        p.requires_grad_(True)
+        assert p.data_ptr() % 16 == (4 * offset) % 16
+        opt = (FusedAdam([p], lr=1e-2, weight_decay=0.01) if kind == "adam"
+               else Lion([p], lr=1e-2, weight_decay=0.01))
+        for gr in grads:
+            gb = torch.zeros(n + 8, device="cuda")
+            p.grad = gb[offset:offset + n]
+            p.grad.copy_(gr.cuda())
+            opt.step()
+        return p.detach().cpu().clone()
+
+    assert torch.equal(run(0), run(1))
+
+
+@pytest.mark.parametrize("offset", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 4099])
+def test_clip_norm_of_unaligned_views(cuda_device, offset, n):
+    """sc_sumsq_accum takes a gradient that starts anywhere on a 4-byte boundary (scalar head, float4
+    body, scalar tail): the norm matches fp64 and the clip scales the whole view."""
+    from statecatcher_b200.optim import clip_grad_norm_
+    gr = torch.randn(n, generator=torch.Generator().manual_seed(n + offset))
+    buf = torch.zeros(n + 8, device="cuda")
+    p = buf[offset:offset + n].requires_grad_(True)
+    gb = torch.zeros(n + 8, device="cuda")
+    p.grad = gb[offset:offset + n]
+    p.grad.copy_(gr.cuda())
+    total = gr.double().norm().item()
+    norm = clip_grad_norm_([p], 0.5 * total)
+    np.testing.assert_allclose(norm.item(), total, rtol=1e-5)
+    coef = min(1.0, 0.5 * total / (total + 1e-6))
+    np.testing.assert_allclose(p.grad.cpu().numpy(), (gr * coef).numpy(), rtol=1e-5, atol=1e-8)
+    assert gb[:offset].abs().sum().item() == 0 and gb[offset + n:].abs().sum().item() == 0
