@@ -283,6 +283,21 @@ int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
  *              m = beta2*m + (1-beta2)*g.  sumsq / max_norm as in adam_step. */
 int sc_lion_step(float* p, const float* g, float* m, int64_t n, float lr, float beta1, float beta2,
                  float weight_decay, const double* sumsq, float max_norm, void* stream);
+/* Multi-tensor forms of the three calls above: ONE launch per 32 tensors instead of one per tensor
+ * (the 26 parameter tensors of the 6-layer model: 3 launches per optimizer step instead of 52).
+ * p / g / m / v / n are HOST arrays of `count` DEVICE pointers / element counts (the only host-array
+ * arguments of this ABI: the table is passed in the kernel parameters, so it follows gradients that
+ * zero_grad(set_to_none=True) re-allocates every step); tensors with n == 0 are skipped; all tensors
+ * of a call share the hyper-parameters and the step count.  Same arithmetic per element as the
+ * single-tensor calls (bit-identical parameter updates). */
+int sc_sumsq_accum_multi(const float* const* g, const int64_t* n, int64_t count, double* acc, void* stream);
+int sc_adam_step_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
+                       const int64_t* n, int64_t count, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int64_t step, const double* sumsq, float max_norm, int decoupled,
+                       void* stream);
+int sc_lion_step_multi(float* const* p, const float* const* g, float* const* m, const int64_t* n,
+                       int64_t count, float lr, float beta1, float beta2, float weight_decay,
+                       const double* sumsq, float max_norm, void* stream);
 
 /* ---------------------------------------------------------------- frontend ------------
  * Replaces make_frontend (model.py:250-279): torchaudio MFCC(n_mfcc=80, dct_type=2, norm='ortho',

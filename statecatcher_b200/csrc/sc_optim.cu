@@ -4,6 +4,7 @@
 // 563-566).  Two kernels per parameter tensor and no host synchronisation: the global norm stays
 // on the device and the update kernel derives the clip coefficient from it.
 #include "sc_common.cuh"
+#include <string.h>
 
 namespace sc {
 
@@ -62,12 +63,8 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 // VEC = 1: all four arrays are 16-byte aligned, the body moves float4 words (seven 128-bit accesses per
 // four elements) and the scalar loop only sees the n % 4 tail; VEC = 0: scalar throughout.
 template <int VEC>
-__global__ void __launch_bounds__(256)
-adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                 const double* __restrict__ sumsq, float max_norm, int decoupled) {
-  const AdamArgs a{lr, b1, b2, eps, wd, lr / bc1, bc2_sqrt, clip_coef(sumsq, max_norm), decoupled};
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void adam_range(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                           float* __restrict__ v, int64_t n, const AdamArgs& a, int64_t tid, int64_t nth) {
   int64_t done = 0;
   if (VEC) {
     const int64_t n4 = n / 4;
@@ -85,6 +82,15 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   for (int64_t i = done + tid; i < n; i += nth) adam_elem(p[i], g[i], m[i], v[i], a);
 }
 
+template <int VEC>
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                 const double* __restrict__ sumsq, float max_norm, int decoupled) {
+  const AdamArgs a{lr, b1, b2, eps, wd, lr / bc1, bc2_sqrt, clip_coef(sumsq, max_norm), decoupled};
+  adam_range<VEC>(p, g, m, v, n, a, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
 // Lion (Chen et al. 2023, "Symbolic Discovery of Optimization Algorithms", Algorithm 2; the rule the
 // absent `lion_pytorch.Lion` of train.py:125-131 implements): decoupled decay, the SIGN of the
 // beta1-interpolated momentum as the update, momentum tracked with beta2.  One state tensor.
@@ -100,11 +106,8 @@ __device__ __forceinline__ void lion_elem(float& p, float g, float& m, const Lio
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
-lion_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, int64_t n, float lr,
-                 float b1, float b2, float wd, const double* __restrict__ sumsq, float max_norm) {
-  const LionArgs a{lr, b1, b2, 1.f - lr * wd, clip_coef(sumsq, max_norm)};
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void lion_range(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                           int64_t n, const LionArgs& a, int64_t tid, int64_t nth) {
   int64_t done = 0;
   if (VEC) {
     const int64_t n4 = n / 4;
@@ -120,6 +123,74 @@ lion_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     done = n4 * 4;
   }
   for (int64_t i = done + tid; i < n; i += nth) lion_elem(p[i], g[i], m[i], a);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+lion_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, int64_t n, float lr,
+                 float b1, float b2, float wd, const double* __restrict__ sumsq, float max_norm) {
+  const LionArgs a{lr, b1, b2, 1.f - lr * wd, clip_coef(sumsq, max_norm)};
+  lion_range<VEC>(p, g, m, n, a, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// ---- multi-tensor variants: up to SC_MT tensors per launch, the table travels in the kernel parameters
+// (no device-side table to keep in step with gradients that zero_grad(set_to_none=True) re-allocates);
+// blockIdx.y = tensor, blockIdx.x strides over its elements with the bodies above.
+constexpr int SC_MT = 32;
+struct MultiDesc { float* p[SC_MT]; const float* g[SC_MT]; float* m[SC_MT]; float* v[SC_MT]; int64_t n[SC_MT]; };
+
+__device__ __forceinline__ bool dev_aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_multi_kernel(const __grid_constant__ MultiDesc d, double* __restrict__ acc) {
+  const int t = blockIdx.y;
+  const float* __restrict__ g = d.g[t];
+  const int64_t n = d.n[t];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if ((int64_t)blockIdx.x * blockDim.x * 4 >= n + 12) return;       // whole block has nothing: uniform exit
+  int64_t head = (int64_t)((16 - ((uintptr_t)g & 15)) & 15) / 4;
+  if (head > n) head = n;
+  const int64_t n4 = (n - head) / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g + head);
+  float s = 0.f;
+  for (int64_t i = tid; i < n4; i += nth) {
+    const float4 v = g4[i];
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+  for (int64_t i = tid; i < head; i += nth) s = fmaf(g[i], g[i], s);
+  for (int64_t i = head + n4 * 4 + tid; i < n; i += nth) s = fmaf(g[i], g[i], s);
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float r = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffu, r, o);
+    if (threadIdx.x == 0 && r != 0.f) atomicAdd(acc, (double)r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ MultiDesc d, float lr, float b1, float b2, float eps, float wd, float bc1,
+                  float bc2_sqrt, const double* __restrict__ sumsq, float max_norm, int decoupled) {
+  const int t = blockIdx.y;
+  const AdamArgs a{lr, b1, b2, eps, wd, lr / bc1, bc2_sqrt, clip_coef(sumsq, max_norm), decoupled};
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (dev_aligned16(d.p[t], d.g[t], d.m[t], d.v[t])) adam_range<1>(d.p[t], d.g[t], d.m[t], d.v[t], d.n[t], a, tid, nth);
+  else adam_range<0>(d.p[t], d.g[t], d.m[t], d.v[t], d.n[t], a, tid, nth);
+}
+
+__global__ void __launch_bounds__(256)
+lion_multi_kernel(const __grid_constant__ MultiDesc d, float lr, float b1, float b2, float wd,
+                  const double* __restrict__ sumsq, float max_norm) {
+  const int t = blockIdx.y;
+  const LionArgs a{lr, b1, b2, 1.f - lr * wd, clip_coef(sumsq, max_norm)};
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (dev_aligned16(d.p[t], d.g[t], d.m[t], d.m[t])) lion_range<1>(d.p[t], d.g[t], d.m[t], d.n[t], a, tid, nth);
+  else lion_range<0>(d.p[t], d.g[t], d.m[t], d.n[t], a, tid, nth);
 }
 
 }  // namespace sc
@@ -178,4 +249,66 @@ extern "C" int sc_lion_step(float* p, const float* g, float* m, int64_t n, float
     lion_step_kernel<0><<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, n, lr, beta1, beta2, weight_decay, sumsq,
         max_norm);
   SC_LAUNCH_RET();
+}
+
+// ---- multi-tensor entry points.  p/g/m/v/n are HOST arrays (of device pointers / element counts).
+static unsigned multi_gx(const int64_t* n, int cnt) {
+  int64_t mx = 1;
+  for (int i = 0; i < cnt; ++i) mx = n[i] > mx ? n[i] : mx;
+  const int64_t cap = (int64_t)148 * 8 / cnt > 8 ? (int64_t)148 * 8 / cnt : 8;   // ~8 CTAs of 256 threads per SM in all
+  const int64_t want = cdiv(mx, (int64_t)4096);
+  return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+template <class Launch>
+static int multi_chunks(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* n,
+                        int64_t count, Launch&& launch) {
+  for (int64_t base = 0; base < count;) {
+    MultiDesc d;
+    memset(&d, 0, sizeof(d));
+    int k = 0;
+    for (; base < count && k < SC_MT; ++base) {
+      if (n[base] < 0) return SC_E_BADARG;
+      if (n[base] == 0) continue;
+      if (!g[base] || (p && !p[base]) || (m && !m[base]) || (v && !v[base])) return SC_E_BADARG;
+      if (((uintptr_t)g[base] & 3) || (p && ((uintptr_t)p[base] & 3))) return SC_E_ALIGN;
+      d.g[k] = g[base]; d.n[k] = n[base];
+      d.p[k] = p ? p[base] : nullptr; d.m[k] = m ? m[base] : nullptr; d.v[k] = v ? v[base] : nullptr;
+      ++k;
+    }
+    if (k == 0) continue;
+    launch(d, dim3(multi_gx(d.n, k), (unsigned)k));
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+extern "C" int sc_sumsq_accum_multi(const float* const* g, const int64_t* n, int64_t count, double* acc, void* stream) {
+  SC_CHECK_ARG(count >= 0 && acc && (count == 0 || (g && n)), SC_E_BADARG);
+  return multi_chunks(nullptr, g, nullptr, nullptr, n, count, [&](const MultiDesc& d, dim3 grid) {
+    sumsq_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, acc);
+  });
+}
+
+extern "C" int sc_adam_step_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
+                                  const int64_t* n, int64_t count, float lr, float beta1, float beta2, float eps,
+                                  float weight_decay, int64_t step, const double* sumsq, float max_norm, int decoupled,
+                                  void* stream) {
+  SC_CHECK_ARG(count >= 0 && step >= 1 && (count == 0 || (p && g && m && v && n)), SC_E_BADARG);
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  return multi_chunks(p, g, m, v, n, count, [&](const MultiDesc& d, dim3 grid) {
+    adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, sumsq,
+        max_norm, decoupled);
+  });
+}
+
+extern "C" int sc_lion_step_multi(float* const* p, const float* const* g, float* const* m, const int64_t* n,
+                                  int64_t count, float lr, float beta1, float beta2, float weight_decay,
+                                  const double* sumsq, float max_norm, void* stream) {
+  SC_CHECK_ARG(count >= 0 && (count == 0 || (p && g && m && n)), SC_E_BADARG);
+  return multi_chunks(p, g, m, nullptr, n, count, [&](const MultiDesc& d, dim3 grid) {
+    lion_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, lr, beta1, beta2, weight_decay, sumsq, max_norm);
+  });
 }

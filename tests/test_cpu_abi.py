@@ -73,6 +73,20 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert lib.sc_gemm_fwd(None, 0, None, 0, None, None, 0, -1, 1, 1, 0, 0, 0, None) == -1
     assert lib.sc_ctc_fwd(None, 0, 0, 0, None, 0, None, None, 0, 1, 1, 0, 0, None, None, None, None, None, None, None, 1, None) == -1
     assert lib.sc_cast(None, 0, 7, None, 0, 0, 0, 0, None) == 0          # empty problem is a no-op
+    # multi-tensor optimizer calls: HOST pointer tables are validated before anything is launched
+    import ctypes
+    ptrs = (ctypes.c_void_p * 2)(None, None)
+    ns = (ctypes.c_int64 * 2)(0, 0)
+    assert lib.sc_sumsq_accum_multi(ptrs, ns, 2, 16, None) == 0           # every tensor empty: no-op
+    assert lib.sc_sumsq_accum_multi(ptrs, ns, -1, 16, None) == -1
+    assert lib.sc_sumsq_accum_multi(None, None, 1, 16, None) == -1
+    assert lib.sc_sumsq_accum_multi(ptrs, (ctypes.c_int64 * 2)(0, -5), 2, 16, None) == -1
+    assert lib.sc_sumsq_accum_multi(ptrs, (ctypes.c_int64 * 2)(0, 5), 2, 16, None) == -1      # null gradient with n > 0
+    assert lib.sc_sumsq_accum_multi((ctypes.c_void_p * 1)(18), (ctypes.c_int64 * 1)(5), 1, 16, None) == -2   # not 4-byte aligned
+    assert lib.sc_adam_step_multi(ptrs, ptrs, ptrs, ptrs, ns, 2, 1e-3, .9, .99, 1e-8, 0., 0, None, 0., 1, None) == -1   # step < 1
+    assert lib.sc_adam_step_multi(ptrs, ptrs, ptrs, ptrs, ns, 2, 1e-3, .9, .99, 1e-8, 0., 1, None, 0., 1, None) == 0
+    assert lib.sc_lion_step_multi(ptrs, ptrs, None, ns, 2, 1e-4, .9, .99, 0., None, 0., None) == -1
+    assert lib.sc_lion_step_multi(ptrs, ptrs, ptrs, ns, 2, 1e-4, .9, .99, 0., None, 0., None) == 0
 
 
 def test_config_contract_matches_reference_dataclass():

@@ -117,3 +117,69 @@ def test_clip_norm_of_unaligned_views(cuda_device, offset, n):
     coef = min(1.0, 0.5 * total / (total + 1e-6))
     np.testing.assert_allclose(p.grad.cpu().numpy(), (gr * coef).numpy(), rtol=1e-5, atol=1e-8)
     assert gb[:offset].abs().sum().item() == 0 and gb[offset + n:].abs().sum().item() == 0
+
+
+def _assorted_params(seed, count=70):
+    """`count` tensors of assorted sizes: an empty one, scalars, n % 4 tails, one off a 16-byte boundary,
+    one large enough for several grid strides; more than one 32-tensor chunk."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = [0, 1, 2, 3, 5, 1024, 4099, 300_001] + [int(torch.randint(1, 3000, (1,), generator=g)) for _ in range(count - 8)]
+    vals = [torch.randn(n, generator=g) for n in sizes]
+    grads = [[torch.randn(n, generator=g) for n in sizes] for _ in range(3)]
+    return sizes, vals, grads
+
+
+@pytest.mark.parametrize("kind", ["adam", "adamw", "lion"])
+@pytest.mark.parametrize("max_norm", [None, 5.0])
+def test_multi_tensor_step_equals_per_tensor_step(cuda_device, kind, max_norm):
+    """sc_*_multi (one launch per 32 tensors) against the per-tensor calls over three steps: bit-identical
+    without clipping (same arithmetic per element); with clipping the two sum the squares in a different
+    order, so the shared coefficient may differ in its last bit."""
+    from statecatcher_b200.optim import FusedAdam, Lion
+    sizes, vals, grads = _assorted_params(5)
+
+    def run(multi):
+        ps = []
+        for i, v in enumerate(vals):
+            if i == 6:                                   # a view that starts 4 bytes into its allocation
+                base = torch.zeros(v.numel() + 4, device="cuda")
+                p = base[1:1 + v.numel()]
+                p.copy_(v.cuda())
+            else:
+                p = v.cuda()
+            ps.append(p.requires_grad_(True))
+        if kind == "lion":
+            opt = Lion(ps, lr=1e-2, weight_decay=0.01, max_grad_norm=max_norm, multi_tensor=multi)
+        else:
+            opt = FusedAdam(ps, lr=1e-2, weight_decay=0.01, decoupled=(kind == "adamw"), max_grad_norm=max_norm,
+                            multi_tensor=multi)
+        norms = []
+        for gs in grads:
+            for p, gr in zip(ps, gs):
+                p.grad = gr.cuda()
+            opt.step()
+            if max_norm is not None:
+                norms.append(opt.grad_norm.item())
+        return [p.detach().cpu() for p in ps], norms
+
+    one, n1 = run(False)
+    many, n2 = run(True)
+    for a, b in zip(one, many):
+        if max_norm is None:
+            assert torch.equal(a, b)
+        else:
+            # Lion moves by lr*sign: a flipped sign of a near-zero interpolation shows as 2*lr on one element
+            if kind == "lion":
+                assert (a - b).abs().gt(1e-6).float().mean().item() < 1e-3 if a.numel() else True
+            else:
+                np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(n2, n1, rtol=1e-6)
+
+
+def test_multi_tensor_norm_matches_fp64(cuda_device):
+    from statecatcher_b200.optim import _global_sumsq
+    sizes, vals, _ = _assorted_params(9)
+    gs = [v.cuda() for v in vals]
+    acc = _global_sumsq([(None, g) for g in gs], gs[0].device, multi_tensor=True)
+    want = sum(float((v.double() ** 2).sum()) for v in vals)
+    np.testing.assert_allclose(acc.item(), want, rtol=1e-6)
