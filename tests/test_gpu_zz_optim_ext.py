@@ -173,7 +173,7 @@ def test_multi_tensor_step_equals_per_tensor_step(cuda_device, kind, max_norm):
                 assert (a - b).abs().gt(1e-6).float().mean().item() < 1e-3 if a.numel() else True
             else:
                 np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(n2, n1, rtol=1e-6)
+    np.testing.assert_allclose(n2, n1, rtol=1e-5)
 
 
 def test_multi_tensor_norm_matches_fp64(cuda_device):
@@ -182,4 +182,4 @@ def test_multi_tensor_norm_matches_fp64(cuda_device):
     gs = [v.cuda() for v in vals]
     acc = _global_sumsq([(None, g) for g in gs], gs[0].device, multi_tensor=True)
     want = sum(float((v.double() ** 2).sum()) for v in vals)
-    np.testing.assert_allclose(acc.item(), want, rtol=1e-6)
+    np.testing.assert_allclose(acc.item(), want, rtol=1e-5)
