@@ -113,3 +113,27 @@ def test_rejects_what_the_kernels_do_not_take(recorder):
         Lion([q]).step()
     with pytest.raises(ValueError):
         Lion([q], betas=(0.9, 1.5))
+
+
+@pytest.mark.parametrize("cls", ["adam", "lion"])
+def test_gradscaler_drives_the_fused_optimizers(recorder, cls):
+    """train.py:513-566 under --use-scaler: scale -> backward -> unscale_ -> clip -> scaler.step(optimizer).
+    The scaler steps the optimizer when no gradient overflowed and skips it otherwise."""
+    from statecatcher_b200.optim import FusedAdam, Lion
+    p = torch.ones(6, requires_grad=True)
+    opt = FusedAdam([p], max_grad_norm=50.0) if cls == "adam" else Lion([p], max_grad_norm=50.0)
+    scaler = torch.amp.GradScaler("cpu", init_scale=1024.0)
+    scaler.scale((p * 2).sum()).backward()
+    assert torch.equal(p.grad, torch.full((6,), 2048.0))
+    scaler.unscale_(opt)
+    assert torch.equal(p.grad, torch.full((6,), 2.0))
+    scaler.step(opt)
+    scaler.update()
+    assert [c[0] for c in recorder][-1] == ("sc_adam_step" if cls == "adam" else "sc_lion_step")
+    recorder.clear()
+    opt.zero_grad()
+    scaler.scale((p * float("inf")).sum()).backward()
+    scaler.unscale_(opt)
+    scaler.step(opt)                                         # overflow: the step is skipped
+    scaler.update()
+    assert not recorder and scaler.get_scale() < 1024.0
