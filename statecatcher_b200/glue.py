@@ -234,3 +234,95 @@ class GraphedStreamingEncoder:
     @property
     def state(self):
         return self.h, self.s
+
+
+class GraphedTrainStep:
+    """One training step of a LucyRNN — carried state in, forward, fused CTC loss, backward, carried state out —
+    replayed from ONE CUDA graph.
+
+    For small models (BASELINE configs[0]: 2 x 256, 8 streams x 1000 frames) a step is a chain of ~300 launches
+    of a few microseconds each and the GPU waits for Python; captured once, the chain replays without the launch
+    path.  Features, labels, lengths, the carried ``(h, s)`` and the loss live in static buffers; the parameter
+    gradients are the graph's own tensors, OVERWRITTEN by every replay (clear them with
+    ``zero_grad(set_to_none=False)`` or not at all — ``set_to_none=True`` would detach the optimizer from them).
+    The state of segment k seeds segment k+1 inside the graph, detached at the boundary exactly as
+    ``compute_loss`` does it (model.py:60-63); ``reset()`` starts new streams.
+
+        runner = GraphedTrainStep(model, batch=8, frames=1000, feat_dim=80, max_labels=50)
+        for feats, tokens, in_lens, tgt_lens in segments:
+            loss = runner.step(feats, tokens, in_lens, tgt_lens)      # gradients are in p.grad
+            optimizer.step()
+
+    Single GPU (the hooks of ``StreamDataParallel`` cannot run inside a capture).  Written after round 1's GPU
+    budget was spent: compiled into the package and covered by tests/test_gpu_zz_graph_train.py, not yet timed.
+    """
+
+    def __init__(self, model: LucyRNN, batch: int, frames: int, feat_dim: int, max_labels: int, blank: int = 0,
+                 reduction: str = "mean", zero_infinity: bool = True, device=None,
+                 in_dtype: torch.dtype = torch.float32, warmup: int = 3):
+        cfg = model.config
+        if not cfg.is_training:
+            raise ValueError("GraphedTrainStep needs a model built with is_training=True (segment path)")
+        if not cfg.return_last_states:
+            raise ValueError("GraphedTrainStep needs return_last_states=True")
+        self.model = model
+        self.head = (int(blank), reduction, bool(zero_infinity))
+        dev = torch.device(device) if device is not None else next(model.parameters()).device
+        H, L = cfg.hidden_dim, cfg.num_layers
+        self.x = torch.zeros(batch, frames, feat_dim, device=dev, dtype=in_dtype)
+        self.tokens = torch.zeros(batch, max(max_labels, 1), device=dev, dtype=torch.int64)
+        self.in_lens = torch.full((batch,), frames // max(cfg.stack_order, 1), device=dev, dtype=torch.int64)
+        self.tgt_lens = torch.zeros(batch, device=dev, dtype=torch.int64)
+        self.h = [torch.zeros(batch, H, device=dev) for _ in range(L)]
+        self.s = [torch.zeros(batch, H, device=dev) for _ in range(L)]
+        self.loss = None
+        params = [p for p in model.parameters() if p.requires_grad]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):                    # lazy one-time setup outside the capture
+                for p in params:
+                    p.grad = None
+                self._step()
+            for p in params:
+                p.grad = None                                  # the capture allocates the static gradients
+            self.reset()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self):
+        blank, reduction, zero_infinity = self.head
+        logits, (h2, s2) = self.model(self.x, (list(self.h), list(self.s)))
+        loss = ctc_loss_from_logits(logits, self.tokens, self.in_lens, self.tgt_lens, blank, reduction, zero_infinity)
+        loss.backward()
+        with torch.no_grad():
+            for dst, src in zip(self.h + self.s, list(h2) + list(s2)):
+                if src is not dst:                             # training path hands the caller's s back untouched
+                    dst.copy_(src.detach())
+        return loss.detach()
+
+    def reset(self):
+        """Start new streams: zero the carried state."""
+        for t in self.h + self.s:
+            t.zero_()
+
+    def step(self, feats: torch.Tensor, tokens: torch.Tensor, in_lens, tgt_lens) -> torch.Tensor:
+        if tokens.dim() != 2 or tokens.size(0) != self.tokens.size(0) or tokens.size(1) > self.tokens.size(1):
+            raise ValueError("tokens must be (batch, U) with U <= max_labels")
+        self.x.copy_(feats, non_blocking=True)
+        self.tokens.zero_()
+        self.tokens[:, :tokens.size(1)].copy_(tokens, non_blocking=True)
+        for dst, src, name in ((self.in_lens, in_lens, "in_lens"), (self.tgt_lens, tgt_lens, "tgt_lens")):
+            t = src if torch.is_tensor(src) else torch.tensor([int(v) for v in src], dtype=torch.int64)
+            if t.numel() != dst.numel():
+                raise ValueError(f"{name} must have {dst.numel()} entries")
+            dst.copy_(t.to(torch.int64), non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    @property
+    def state(self):
+        return self.h, self.s
