@@ -135,9 +135,23 @@ lion_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 // ---- multi-tensor variants: up to SC_MT tensors per launch, the table travels in the kernel parameters
 // (no device-side table to keep in step with gradients that zero_grad(set_to_none=True) re-allocates);
-// blockIdx.y = tensor, blockIdx.x strides over its elements with the bodies above.
+// every tensor gets blocks in proportion to its size (one per SC_MT_CHUNK elements, at least one): blk0 is the
+// running block count, a block finds its tensor by walking it (<= 32 compares on kernel parameters) and then
+// strides over that tensor with the bodies above, as one of the tensor's own blocks.
 constexpr int SC_MT = 32;
-struct MultiDesc { float* p[SC_MT]; const float* g[SC_MT]; float* m[SC_MT]; float* v[SC_MT]; int64_t n[SC_MT]; };
+constexpr int64_t SC_MT_CHUNK = 16384;
+struct MultiDesc {
+  float* p[SC_MT]; const float* g[SC_MT]; float* m[SC_MT]; float* v[SC_MT]; int64_t n[SC_MT];
+  unsigned blk0[SC_MT + 1]; int count;
+};
+
+struct MultiSlot { int t; int64_t tid, nth; };
+__device__ __forceinline__ MultiSlot multi_slot(const MultiDesc& d) {
+  int t = 0;
+  while (t + 1 < d.count && blockIdx.x >= d.blk0[t + 1]) ++t;
+  const int64_t lb = blockIdx.x - d.blk0[t], nb = d.blk0[t + 1] - d.blk0[t];
+  return MultiSlot{t, lb * blockDim.x + threadIdx.x, nb * blockDim.x};
+}
 
 __device__ __forceinline__ bool dev_aligned16(const void* a, const void* b, const void* c, const void* d) {
   return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
@@ -145,11 +159,11 @@ __device__ __forceinline__ bool dev_aligned16(const void* a, const void* b, cons
 
 __global__ void __launch_bounds__(256)
 sumsq_multi_kernel(const __grid_constant__ MultiDesc d, double* __restrict__ acc) {
-  const int t = blockIdx.y;
+  const MultiSlot sl = multi_slot(d);
+  const int t = sl.t;
   const float* __restrict__ g = d.g[t];
   const int64_t n = d.n[t];
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  if ((int64_t)blockIdx.x * blockDim.x * 4 >= n + 12) return;       // whole block has nothing: uniform exit
+  const int64_t tid = sl.tid, nth = sl.nth;
   int64_t head = (int64_t)((16 - ((uintptr_t)g & 15)) & 15) / 4;
   if (head > n) head = n;
   const int64_t n4 = (n - head) / 4;
@@ -176,9 +190,10 @@ sumsq_multi_kernel(const __grid_constant__ MultiDesc d, double* __restrict__ acc
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ MultiDesc d, float lr, float b1, float b2, float eps, float wd, float bc1,
                   float bc2_sqrt, const double* __restrict__ sumsq, float max_norm, int decoupled) {
-  const int t = blockIdx.y;
+  const MultiSlot sl = multi_slot(d);
+  const int t = sl.t;
   const AdamArgs a{lr, b1, b2, eps, wd, lr / bc1, bc2_sqrt, clip_coef(sumsq, max_norm), decoupled};
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = sl.tid, nth = sl.nth;
   if (dev_aligned16(d.p[t], d.g[t], d.m[t], d.v[t])) adam_range<1>(d.p[t], d.g[t], d.m[t], d.v[t], d.n[t], a, tid, nth);
   else adam_range<0>(d.p[t], d.g[t], d.m[t], d.v[t], d.n[t], a, tid, nth);
 }
@@ -186,9 +201,10 @@ adam_multi_kernel(const __grid_constant__ MultiDesc d, float lr, float b1, float
 __global__ void __launch_bounds__(256)
 lion_multi_kernel(const __grid_constant__ MultiDesc d, float lr, float b1, float b2, float wd,
                   const double* __restrict__ sumsq, float max_norm) {
-  const int t = blockIdx.y;
+  const MultiSlot sl = multi_slot(d);
+  const int t = sl.t;
   const LionArgs a{lr, b1, b2, 1.f - lr * wd, clip_coef(sumsq, max_norm)};
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = sl.tid, nth = sl.nth;
   if (dev_aligned16(d.p[t], d.g[t], d.m[t], d.m[t])) lion_range<1>(d.p[t], d.g[t], d.m[t], d.n[t], a, tid, nth);
   else lion_range<0>(d.p[t], d.g[t], d.m[t], d.n[t], a, tid, nth);
 }
@@ -252,14 +268,6 @@ extern "C" int sc_lion_step(float* p, const float* g, float* m, int64_t n, float
 }
 
 // ---- multi-tensor entry points.  p/g/m/v/n are HOST arrays (of device pointers / element counts).
-static unsigned multi_gx(const int64_t* n, int cnt) {
-  int64_t mx = 1;
-  for (int i = 0; i < cnt; ++i) mx = n[i] > mx ? n[i] : mx;
-  const int64_t cap = (int64_t)148 * 8 / cnt > 8 ? (int64_t)148 * 8 / cnt : 8;   // ~8 CTAs of 256 threads per SM in all
-  const int64_t want = cdiv(mx, (int64_t)4096);
-  return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-}
-
 template <class Launch>
 static int multi_chunks(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* n,
                         int64_t count, Launch&& launch) {
@@ -277,7 +285,10 @@ static int multi_chunks(float* const* p, const float* const* g, float* const* m,
       ++k;
     }
     if (k == 0) continue;
-    launch(d, dim3(multi_gx(d.n, k), (unsigned)k));
+    d.count = k;
+    d.blk0[0] = 0;
+    for (int i = 0; i < k; ++i) d.blk0[i + 1] = d.blk0[i] + (unsigned)cdiv(d.n[i], SC_MT_CHUNK);
+    launch(d, dim3(d.blk0[k]));
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
