@@ -61,8 +61,12 @@ def parse():
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+        try:
+            d = json.load(open(p))
+            return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                        tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+        except (ValueError, KeyError, TypeError):
+            pass                                   # unreadable or incomplete driver file: stated fallback below
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
