@@ -8,19 +8,26 @@
 
 namespace sc {
 
-// head = elements in front of the first 16-byte boundary (0 for torch allocations; a view may start anywhere)
-__global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, int64_t n, int64_t head, double* __restrict__ acc) {
-  float s = 0.f;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+// Sum of squares of g[tid::nth] over [0, n).  A gradient may start anywhere on a 4-byte boundary (a view into a
+// bucket): the elements in front of the first 16-byte boundary and the n % 4 tail go through scalar loads, the
+// body through float4.
+__device__ __forceinline__ float sumsq_range(const float* __restrict__ g, int64_t n, int64_t tid, int64_t nth) {
+  int64_t head = (int64_t)((16 - ((uintptr_t)g & 15)) & 15) / 4;
+  if (head > n) head = n;
   const int64_t n4 = (n - head) / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g + head);
+  float s = 0.f;
   for (int64_t i = tid; i < n4; i += nth) {
     const float4 v = g4[i];
     s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
   }
   for (int64_t i = tid; i < head; i += nth) s = fmaf(g[i], g[i], s);
   for (int64_t i = head + n4 * 4 + tid; i < n; i += nth) s = fmaf(g[i], g[i], s);
+  return s;
+}
+
+// block of 256 threads: one double atomic per block
+__device__ __forceinline__ void block_add_to(double* __restrict__ acc, float s) {
   __shared__ float red[8];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -31,6 +38,11 @@ sumsq_kernel(const float* __restrict__ g, int64_t n, int64_t head, double* __res
     for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
     if (threadIdx.x == 0) atomicAdd(acc, (double)t);
   }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ acc) {
+  block_add_to(acc, sumsq_range(g, n, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x));
 }
 
 // clip_coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))   (torch.nn.utils.clip_grad_norm_)
@@ -160,31 +172,7 @@ __device__ __forceinline__ bool dev_aligned16(const void* a, const void* b, cons
 __global__ void __launch_bounds__(256)
 sumsq_multi_kernel(const __grid_constant__ MultiDesc d, double* __restrict__ acc) {
   const MultiSlot sl = multi_slot(d);
-  const int t = sl.t;
-  const float* __restrict__ g = d.g[t];
-  const int64_t n = d.n[t];
-  const int64_t tid = sl.tid, nth = sl.nth;
-  int64_t head = (int64_t)((16 - ((uintptr_t)g & 15)) & 15) / 4;
-  if (head > n) head = n;
-  const int64_t n4 = (n - head) / 4;
-  const float4* g4 = reinterpret_cast<const float4*>(g + head);
-  float s = 0.f;
-  for (int64_t i = tid; i < n4; i += nth) {
-    const float4 v = g4[i];
-    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
-  }
-  for (int64_t i = tid; i < head; i += nth) s = fmaf(g[i], g[i], s);
-  for (int64_t i = head + n4 * 4 + tid; i < n; i += nth) s = fmaf(g[i], g[i], s);
-  __shared__ float red[8];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    float r = red[threadIdx.x];
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffu, r, o);
-    if (threadIdx.x == 0 && r != 0.f) atomicAdd(acc, (double)r);
-  }
+  block_add_to(acc, sumsq_range(d.g[sl.t], d.n[sl.t], sl.tid, sl.nth));
 }
 
 __global__ void __launch_bounds__(256)
@@ -222,9 +210,7 @@ extern "C" int sc_sumsq_accum(const float* g, int64_t n, double* acc, void* stre
   SC_CHECK_ARG(n >= 0 && acc, SC_E_BADARG);
   if (n == 0) return 0;
   SC_CHECK_ARG(g && ((uintptr_t)g & 3) == 0, SC_E_ALIGN);
-  int64_t head = (int64_t)((16 - ((uintptr_t)g & 15)) & 15) / 4;
-  if (head > n) head = n;
-  sumsq_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(g, n, head, acc);
+  sumsq_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(g, n, acc);
   SC_LAUNCH_RET();
 }
 
