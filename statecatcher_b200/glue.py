@@ -254,7 +254,7 @@ class GraphedTrainStep:
             optimizer.step()
 
     Single GPU (the hooks of ``StreamDataParallel`` cannot run inside a capture).  Written after round 1's GPU
-    budget was spent: compiled into the package and covered by tests/test_gpu_zz_graph_train.py, not yet timed.
+    budget was spent: compiled into the package and covered by tests/test_gpu_zzz_graph_train.py, not yet timed.
     """
 
     def __init__(self, model: LucyRNN, batch: int, frames: int, feat_dim: int, max_labels: int, blank: int = 0,
