@@ -323,6 +323,169 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat, const flo
   }
 }
 
+// ---- pass 2, LINEAR-domain variant with a per-node exponent (SC_CTC_WAVE=3; EXPERIMENTAL, opt-in) -------
+// alpha[s] = m * 2^e with an fp32 mantissa m in [0.5, 1) and an int exponent e per node.  The step is
+//   emax = max(e_a, e_b, e_c);  sum = m_a 2^(e_a-emax) + m_b 2^(e_b-emax) + m_c 2^(e_c-emax);  v = sum * p
+// followed by an exponent extraction on the bits of v: integer ops, two FADD and one FMUL where the log-domain
+// step has min/max -> ex2 x2 -> lg2 (three MUFU round trips).  lg2 is taken only for the values that are
+// STORED (same alpha / beta format as the other kernels, each row relative to an exponent the block agrees on
+// once per emission block), never for what the next step reads.  A column scaled by one common factor loses the
+// nodes 2^-125 below its maximum (rejected earlier, see below); the per-node exponent keeps them.  Accuracy was
+// settled on the CPU before this was written (profiles/ctc_linear_exp_study.py: occupancies within 4e-6 /
+// 1.3e-5 of fp64 at T=3000, U=150 with the mantissa renormalised every step, as here).  Same block structure
+// as ctc_alpha_beta_kernel's fast path (one node per thread, previous column in shared memory, one barrier per
+// step).  Written after round 1's GPU budget was spent: compiles, has never run.
+constexpr int CTC_E_DEAD = -(1 << 28);
+// m * 2^d for d <= 0 (the exponent field is built directly; below 2^-60 the term cannot reach the sum's last bit)
+__device__ __forceinline__ float scale_pow2(float m, int d) {
+  return d < -60 ? 0.f : m * __int_as_float((127 + d) << 23);
+}
+
+__global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
+                                          const int64_t* __restrict__ targets, int64_t ldt,
+                                          const int64_t* __restrict__ in_lens,
+                                          const int64_t* __restrict__ tgt_lens,
+                                          int Tn, int Smax, int64_t blank,
+                                          float* __restrict__ alpha, float* __restrict__ beta,
+                                          float* __restrict__ nll) {
+  extern __shared__ __align__(128) float sm[];   // 2 mantissa lines + 2 exponent lines of (Smax + 4) cells, then 2 emission blocks
+  __shared__ int ired[32];
+  __shared__ double dred[32];
+  __shared__ __align__(8) uint64_t ebar[2];
+  const int b = blockIdx.x, dir = blockIdx.y;
+  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64;
+  const int U = (int)tgt_lens[b];
+  const int S = 2 * U + 1;
+  const int64_t* tg = targets + (int64_t)b * ldt;
+  const int LINE = Smax + 4;
+  if (Tb <= 0) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
+    return;
+  }
+  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
+  int* ism = reinterpret_cast<int*>(sm + 2 * LINE);
+  for (int i = threadIdx.x; i < 2 * LINE; i += blockDim.x) { sm[i] = 0.f; ism[i] = CTC_E_DEAD; }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float* pm = sm + 2;            float* cm = sm + LINE + 2;            // previous / current mantissas
+  int* pe = ism + 2;             int* ce = ism + LINE + 2;             // previous / current exponents
+  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
+  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
+  const int t_first = dir == 0 ? 0 : Tb - 1;
+  const int step = dir == 0 ? 1 : -1;
+  const int nb = dir == 0 ? -1 : 1;
+  const int s = threadIdx.x;
+  const bool has = s < S;
+  bool skip = false;
+  if (has && (s & 1)) skip = dir == 0 ? (s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1]) : (s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1]);
+  auto block_max_i = [&](int m) -> int {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = m;
+    __syncthreads();
+    int r = CTC_E_DEAD;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) r = max(r, ired[w]);
+    return r;
+  };
+  // emission in log2 units (<= 0 after the per-frame shift) -> integer part for the exponent, 2^fraction in [1, 2)
+  auto split_emission = [](float e, float& pf, int& ei) {
+    if (!(e > -1.0e6f)) { pf = 0.f; ei = 0; return; }           // masked vocabulary entry: probability zero
+    const float fl = floorf(e);
+    pf = ex2f(e - fl);
+    ei = (int)fl;
+  };
+  // v > 0 normal -> mantissa in [0.5, 1) and the exponent that goes with it; v == 0 -> dead node
+  auto renorm = [](float v, int ebase, float& m, int& e) {
+    if (v > 0.f) {
+      const int bits = __float_as_int(v);
+      m = __int_as_float((bits & 0x007fffff) | (126 << 23));
+      e = ebase + ((bits >> 23) & 0xff) - 126;
+    } else { m = 0.f; e = CTC_E_DEAD; }
+  };
+  float* ebuf = reinterpret_cast<float*>(ism + 2 * LINE);      // 2 buffers of CTC_EB rows x Smax
+  const int nvis = (Tb + CTC_EB - 1) / CTC_EB;
+  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
+  auto rows_of = [&](int blk) { const int r = Tb - blk * CTC_EB; return r < CTC_EB ? r : CTC_EB; };
+  auto issue = [&](int vi) {
+    const int blk = blk_of(vi);
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
+    const uint32_t bar = smem_u32(&ebar[vi & 1]);
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * CTC_EB * Smax), lp_b + (int64_t)blk * CTC_EB * Smax, bytes, bar);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  const int sidx = has ? s : 0;
+  const int64_t stride = (int64_t)step * Smax;
+  float* op = out_b + (int64_t)t_first * Smax + sidx;
+  int eref = 0;                                                  // exponent the stored rows of this visit are relative to
+  for (int vi = 0; vi < nvis; ++vi) {
+    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+    const int rows = rows_of(blk_of(vi));
+    const float* ep = ebuf + ((size_t)(vi & 1) * CTC_EB + (dir == 0 ? 0 : rows - 1)) * Smax + sidx;
+    const int estride = dir == 0 ? Smax : -Smax;
+    int pos = 0;
+    if (vi == 0) {                                               // init column (step 0)
+      float m0 = 0.f; int e0 = CTC_E_DEAD; bool live = false;
+      if (has && (dir == 0 ? s < 2 : s >= S - 2)) {
+        float pf; int ei;
+        split_emission(*ep, pf, ei);
+        renorm(pf, ei, m0, e0);
+        live = true;
+      }
+      if (has) {
+        pm[s] = m0; pe[s] = e0;
+        *op = dir == 0 ? (m0 > 0.f ? lg2f(m0) + (float)e0 : NEG_INF) : (live ? 0.f : NEG_INF);
+      }
+      __syncthreads();
+      ep += estride;
+      pos = 1;
+    } else {
+      // stored rows are relative to the largest live exponent at the start of their emission block
+      const int m = block_max_i(has ? pe[s] : CTC_E_DEAD);
+      if (m > CTC_E_DEAD) eref = m;
+      __syncthreads();
+    }
+    for (; pos < rows; ++pos) {
+      float pf; int ei;
+      split_emission(*ep, pf, ei);
+      ep += estride;
+      op += stride;
+      if (has) {
+        const float ma = pm[s], mb = pm[s + nb];
+        const int ea = pe[s], eb2 = pe[s + nb];
+        float mc = 0.f; int ec = CTC_E_DEAD;
+        if (skip) { mc = pm[s + 2 * nb]; ec = pe[s + 2 * nb]; }
+        const int emax = max(ea, max(eb2, ec));
+        const float sum = scale_pow2(ma, ea - emax) + scale_pow2(mb, eb2 - emax) + scale_pow2(mc, ec - emax);
+        float mn; int en;
+        renorm(sum * pf, emax + ei, mn, en);
+        cm[s] = mn; ce[s] = en;
+        if (dir == 0) *op = mn > 0.f ? lg2f(mn) + (float)(en - eref) : NEG_INF;
+        else          *op = sum > 0.f ? lg2f(sum) + (float)(emax - eref) : NEG_INF;   // beta leaves without its frame's emission
+      }
+      __syncthreads();
+      float* tm = pm; pm = cm; cm = tm;
+      int* te = pe; pe = ce; ce = te;
+    }
+    if (threadIdx.x == 0 && vi + 2 < nvis) issue(vi + 2);
+  }
+  if (dir == 0 && threadIdx.x == 0) {
+    const float m1 = pm[S - 1], m2 = S > 1 ? pm[S - 2] : 0.f;
+    const int e1 = pe[S - 1], e2 = S > 1 ? pe[S - 2] : CTC_E_DEAD;
+    const int emax = max(e1, e2);
+    const float v = scale_pow2(m1, e1 - emax) + scale_pow2(m2, e2 - emax);
+    nll[b] = (v > 0.f) ? (float)(-(shift_sum + (double)emax + log2((double)v)) * (double)LN2) : INFINITY;
+  }
+}
+
 // ---- pass 2, wavefront variant (lattices up to 1024 nodes) ---------------------------------
 // Same recursion, no block barrier per timestep.  Node values live in REGISTERS (thread i owns
 // node i for alpha, node S-1-i for beta, so both directions only ever look at lower threads);
@@ -892,8 +1055,21 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
   int threads = ((Smax + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   int wave = Smax <= 1024 ? 2 : 0;                               // SC_CTC_WAVE: 0 block-barrier kernel, 1 node per thread, 2 pair per thread
-  if (const char* ev = getenv("SC_CTC_WAVE")) { const int w = atoi(ev); if (w >= 0 && w < wave) wave = w; }
-  if (wave) {
+  if (const char* ev = getenv("SC_CTC_WAVE")) {
+    const int w = atoi(ev);
+    if (w >= 0 && w < wave) wave = w;
+    if (w == 3 && Smax <= 1024) wave = 3;                        // experimental linear-domain recursion (opt-in)
+  }
+  if (wave == 3) {
+    const size_t smem = (4 * (size_t)(Smax + 4) + 2 * (size_t)CTC_EB * Smax) * sizeof(float);
+    SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ctc_alpha_beta_lin_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
+        (int)T, Smax, blank, alpha, beta, nll);
+  } else if (wave) {
     const int wthreads = wave == 2 ? (((int)Umax + 1 + 31) / 32) * 32 : threads;
     size_t smem = 0;
     const int eb = ctc_wave_rows(Smax, B, wthreads / 32, &smem);
