@@ -93,6 +93,50 @@ def linear_exp_domain(p, ext, renorm_every=1):
     return out
 
 
+def kernel_rows(p, lp2_frac_int, ext, with_emission, EB=16):
+    """What ctc_alpha_beta_lin_kernel STORES: fp32 rows lg2(m) + float(e - eref), eref = largest live exponent of
+    the previous column at the start of each EB-row emission block; mantissa/exponent handling as in the kernel
+    (emission split into integer part -> exponent and 2^fraction in [1,2), terms below 2^-60 dropped)."""
+    pf, ei = lp2_frac_int
+    T, S = pf.shape
+    skip = np.zeros(S, bool)
+    skip[2:] = (ext[2:] != 0) & (ext[2:] != ext[:-2])
+    DEAD = np.int64(-(1 << 28))
+    m = np.zeros(S, f32)
+    e = np.full(S, DEAD)
+    rows = np.full((T, S), -np.inf, dtype=f32)
+
+    def renorm(v, ebase):
+        mm, de = np.frexp(v)
+        live = v > 0
+        return np.where(live, mm, 0).astype(f32), np.where(live, ebase + de, DEAD)
+
+    def sc(mm, d):
+        return np.where(d < -60, f32(0), mm * np.exp2(np.maximum(d, -60)).astype(f32)).astype(f32)
+
+    m[:2], e[:2] = renorm(pf[0, :2], ei[0, :2])
+    with np.errstate(divide="ignore"):
+        rows[0, :2] = (np.log2(m[:2]).astype(f32) + e[:2].astype(f32)) if with_emission else f32(0)
+    eref = 0
+    for t in range(1, T):
+        if t % EB == 0 and (e > DEAD).any():
+            eref = e[e > DEAD].max()
+        mb = np.concatenate([[f32(0)], m[:-1]]); eb = np.concatenate([[DEAD], e[:-1]])
+        mc = np.where(skip, np.concatenate([[f32(0), f32(0)], m[:-2]]), f32(0))
+        ec = np.where(skip, np.concatenate([[DEAD, DEAD], e[:-2]]), DEAD)
+        emax = np.maximum(np.maximum(e, eb), ec)
+        s = ((sc(m, e - emax) + sc(mb, eb - emax)).astype(f32) + sc(mc, ec - emax)).astype(f32)
+        v = (s * pf[t]).astype(f32)
+        m, e_new = renorm(v, emax + ei[t])
+        with np.errstate(divide="ignore"):
+            if with_emission:
+                rows[t] = np.where(m > 0, np.log2(m).astype(f32) + (e_new - eref).astype(f32), -np.inf)
+            else:
+                rows[t] = np.where(s > 0, np.log2(s).astype(f32) + (emax - eref).astype(f32), -np.inf)
+        e = e_new
+    return rows
+
+
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
     U = int(sys.argv[2]) if len(sys.argv) > 2 else 150
@@ -132,6 +176,22 @@ def main():
         print(f"  occupancy: max abs err {err.max():.3e} (values up to {g_ref.max():.3f}), "
               f"max rel err where gamma > 1e-3: {(err / np.maximum(g_ref, 1e-30))[g_ref > 1e-3].max():.3e}, "
               f"row-sum err {np.abs(g.sum(1) - 1).max():.3e}, nodes lost (0 vs > 1e-6): {dead_wrong}")
+        if K == 1:
+            # the kernel's own storage format, then the gradient pass's per-frame normalisation in fp32
+            lp2s = ((lp - shift) / np.log(2.0)).astype(f32)
+            fl = np.floor(lp2s)
+            split = (np.exp2((lp2s - fl).astype(f32)).astype(f32), fl.astype(np.int64))
+            ra = kernel_rows(p, split, ext, True)
+            rb = kernel_rows(p[::-1, ::-1], (split[0][::-1, ::-1], split[1][::-1, ::-1]), ext[::-1], False)[::-1, ::-1]
+            ab = (ra + rb).astype(f32)                       # beta rows carry no emission: alpha + beta is the log-occupancy
+            ab = np.where(np.isfinite(ab), ab, -np.inf)
+            gk = np.exp2((ab - ab.max(1, keepdims=True)).astype(f32)).astype(f32)
+            gk = gk / gk.sum(1, keepdims=True)
+            errk = np.abs(gk - g_ref)
+            print(f"  kernel storage format (fp32 rows relative to a per-16-row exponent, per-frame normalisation): "
+                  f"max abs err {errk.max():.3e}, max rel err where gamma > 1e-3: "
+                  f"{(errk / np.maximum(g_ref, 1e-30))[g_ref > 1e-3].max():.3e}, largest |stored value| "
+                  f"{np.abs(ra[np.isfinite(ra)]).max():.1f} / {np.abs(rb[np.isfinite(rb)]).max():.1f}")
 
 
 if __name__ == "__main__":
