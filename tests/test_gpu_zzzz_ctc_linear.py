@@ -1,11 +1,17 @@
 """GPU: the EXPERIMENTAL linear-domain CTC lattice kernel (SC_CTC_WAVE=3, opt-in) against the default kernel and
 torch's fp64 ctc_loss.  The kernel was written after round 1's GPU budget was spent and has never run, so this
-file sorts after every other GPU test: whatever it does cannot mask or disturb them."""
+file sorts after every other GPU test AND only runs when SC_RUN_EXPERIMENTAL=1 is set: a kernel that has never
+run must not be able to hang or poison the default `pytest -m gpu` run.
+    SC_RUN_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zzzz_ctc_linear.py -q"""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SC_RUN_EXPERIMENTAL") != "1",
+                                 reason="experimental kernel (never run on a GPU yet): set SC_RUN_EXPERIMENTAL=1")]
 
 
 @pytest.mark.parametrize("shape", [(5, 700, 64, 150), (3, 50, 11, 6), (2, 3000, 1024, 150)], ids=["cfg2like", "small", "cfg2row"])
