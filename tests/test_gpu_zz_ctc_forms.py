@@ -2,13 +2,18 @@
 drop-in accepts — concatenated 1-D targets, tensor lengths, unbatched (T,V) input — give the loss and
 gradient of the padded form bit for bit, and agree with the fp64 oracle.  (Written after round 1's GPU
 budget was spent; sorted last so that a failure cannot mask the measured tests under -x.)"""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import ctc_oracle
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SC_RUN_EXPERIMENTAL") != "1",
+                                 reason="written after round 1's GPU budget was spent, not yet run on a B200: "
+                                        "set SC_RUN_EXPERIMENTAL=1")]
 
 
 def _case(seed=0, B=5, T=40, V=11, U=7):

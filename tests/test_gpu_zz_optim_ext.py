@@ -1,11 +1,16 @@
 """GPU: fused Lion step (sc_lion_step, optim.Lion) vs oracle/optim_oracle.py over several steps.
 lion_pytorch (train.py:125-131) is absent upstream: parity unpinned, the published rule is the oracle.
 The sign of an interpolation that fp32 cannot resolve from 0 is excluded element-wise."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SC_RUN_EXPERIMENTAL") != "1",
+                                 reason="written after round 1's GPU budget was spent, not yet run on a B200: "
+                                        "set SC_RUN_EXPERIMENTAL=1")]
 
 
 @pytest.mark.parametrize("wd", [0.0, 0.1])
