@@ -27,7 +27,7 @@ def needs_rebuild():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(HERE, "..", "include", "statecatcher_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

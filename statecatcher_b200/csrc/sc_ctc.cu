@@ -32,6 +32,7 @@
 // kernel at 40 warps per SM — bytes in flight are not what holds pass 1 at ~2.9 TB/s; not kept.
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
+#include "sc_ctc_lin_math.h"
 #include "sc_tma.cuh"
 #include <stdlib.h>
 
@@ -335,12 +336,6 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat, const flo
 // 1.3e-5 of fp64 at T=3000, U=150 with the mantissa renormalised every step, as here).  Same block structure
 // as ctc_alpha_beta_kernel's fast path (one node per thread, previous column in shared memory, one barrier per
 // step).  Written after round 1's GPU budget was spent: compiles, has never run.
-constexpr int CTC_E_DEAD = -(1 << 28);
-// m * 2^d for d <= 0 (the exponent field is built directly; below 2^-60 the term cannot reach the sum's last bit)
-__device__ __forceinline__ float scale_pow2(float m, int d) {
-  return d < -60 ? 0.f : m * __int_as_float((127 + d) << 23);
-}
-
 __global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
                                           const int64_t* __restrict__ targets, int64_t ldt,
                                           const int64_t* __restrict__ in_lens,
@@ -399,14 +394,6 @@ __global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const
     pf = ex2f(e - fl);
     ei = (int)fl;
   };
-  // v > 0 normal -> mantissa in [0.5, 1) and the exponent that goes with it; v == 0 -> dead node
-  auto renorm = [](float v, int ebase, float& m, int& e) {
-    if (v > 0.f) {
-      const int bits = __float_as_int(v);
-      m = __int_as_float((bits & 0x007fffff) | (126 << 23));
-      e = ebase + ((bits >> 23) & 0xff) - 126;
-    } else { m = 0.f; e = CTC_E_DEAD; }
-  };
   float* ebuf = reinterpret_cast<float*>(ism + 2 * LINE);      // 2 buffers of CTC_EB rows x Smax
   const int nvis = (Tb + CTC_EB - 1) / CTC_EB;
   auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
@@ -437,7 +424,7 @@ __global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const
       if (has && (dir == 0 ? s < 2 : s >= S - 2)) {
         float pf; int ei;
         split_emission(*ep, pf, ei);
-        renorm(pf, ei, m0, e0);
+        ctc_lin_renorm(pf, ei, m0, e0);
         live = true;
       }
       if (has) {
@@ -463,10 +450,8 @@ __global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const
         const int ea = pe[s], eb2 = pe[s + nb];
         float mc = 0.f; int ec = CTC_E_DEAD;
         if (skip) { mc = pm[s + 2 * nb]; ec = pe[s + 2 * nb]; }
-        const int emax = max(ea, max(eb2, ec));
-        const float sum = scale_pow2(ma, ea - emax) + scale_pow2(mb, eb2 - emax) + scale_pow2(mc, ec - emax);
-        float mn; int en;
-        renorm(sum * pf, emax + ei, mn, en);
+        float mn, sum; int en, emax;
+        ctc_lin_step(ma, ea, mb, eb2, mc, ec, pf, ei, mn, en, sum, emax);
         cm[s] = mn; ce[s] = en;
         if (dir == 0) *op = mn > 0.f ? lg2f(mn) + (float)(en - eref) : NEG_INF;
         else          *op = sum > 0.f ? lg2f(sum) + (float)(emax - eref) : NEG_INF;   // beta leaves without its frame's emission
@@ -481,7 +466,7 @@ __global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const
     const float m1 = pm[S - 1], m2 = S > 1 ? pm[S - 2] : 0.f;
     const int e1 = pe[S - 1], e2 = S > 1 ? pe[S - 2] : CTC_E_DEAD;
     const int emax = max(e1, e2);
-    const float v = scale_pow2(m1, e1 - emax) + scale_pow2(m2, e2 - emax);
+    const float v = ctc_lin_scale_pow2(m1, e1 - emax) + ctc_lin_scale_pow2(m2, e2 - emax);
     nll[b] = (v > 0.f) ? (float)(-(shift_sum + (double)emax + log2((double)v)) * (double)LN2) : INFINITY;
   }
 }

@@ -71,3 +71,44 @@ def test_sparser_renormalisation_fails_on_peaky_input():
     big = g_ref > 1e-3
     lost = ((g == 0) & (g_ref > 1e-6)).any()
     assert lost or not np.isfinite(ll) or (np.abs(g - g_ref)[big] / g_ref[big]).max() > 1e-3
+
+
+def test_the_kernels_own_arithmetic_header_on_the_host(tmp_path):
+    """statecatcher_b200/csrc/sc_ctc_lin_math.h — the exponent-field arithmetic the experimental kernel compiles —
+    built as plain C++ (tests/ctc_lin_host.cpp) and run over whole utterances: log2(alpha) of every node against
+    the fp64 recursion, including masked emissions (probability zero) and a lattice that dies completely."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of this image"
+    exe = tmp_path / "ctc_lin_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "ctc_lin_host.cpp")], check=True)
+
+    def run(lp2, ext):
+        T, S = lp2.shape
+        skip = np.zeros(S, np.uint8)
+        skip[2:] = (ext[2:] != 0) & (ext[2:] != ext[:-2])
+        src, dst = tmp_path / "in.bin", tmp_path / "out.bin"
+        with open(src, "wb") as f:
+            f.write(np.array([T, S], np.int32).tobytes() + skip.tobytes() + np.ascontiguousarray(lp2, np.float32).tobytes())
+        subprocess.run([str(exe), str(src), str(dst)], check=True)
+        return np.fromfile(dst, np.float64).reshape(T, S)
+
+    for scale, T, U, V in ((2.0, 600, 40, 64), (6.0, 600, 40, 64), (2.0, 50, 24, 9)):
+        logits, y, ext, lp = _case(T, U, V, scale, 3)
+        shift = lp.max(1, keepdims=True)
+        lp2 = ((lp - shift) / np.log(2.0)).astype(np.float32)
+        got = run(lp2, ext) + (np.cumsum(shift[:, 0]) / np.log(2.0))[:, None]
+        # reference on the SAME fp32 emissions, so that only the recursion's arithmetic is compared
+        ref = (study.fp64_log_domain(lp2.astype(np.float64) * np.log(2.0), ext) / np.log(2.0)
+               + (np.cumsum(shift[:, 0]) / np.log(2.0))[:, None])
+        live = np.isfinite(ref)
+        assert (np.isfinite(got) == live).all()                  # same nodes reachable, none lost
+        # values are log2 of probabilities thousands of binades apart: compare the probabilities' ratio
+        assert np.abs(got[live] - ref[live]).max() < 3e-4, (scale, np.abs(got[live] - ref[live]).max())
+    # masked emissions: label 1 can never be emitted -> every node from the first label on is dead for good
+    lp2 = np.zeros((6, 5), np.float32)
+    lp2[:, 1] = -np.inf
+    got = run(lp2, np.array([0, 1, 0, 2, 0]))
+    assert np.isfinite(got[:, 0]).all() and not np.isfinite(got[:, 1:]).any()
+    np.testing.assert_allclose(got[:, 0], 0.0, atol=1e-6)
