@@ -800,6 +800,202 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   }
 }
 
+// ---- pass 2, pair-per-thread wavefront with the LINEAR-domain step (SC_CTC_WAVE=4; EXPERIMENTAL, opt-in) ----
+// ctc_wave2_body with the node value as (mantissa, exponent) (sc_ctc_lin_math.h) instead of a log2 number: same
+// thread/node assignment, same neighbour-only handoff, slots widened to 16 bytes {mantissa, exponent, step tag, -}.
+// Nothing is re-centred at the block meetings (exponents are exact integers); the meeting only agrees on the
+// exponent the stored rows of the next emission block are relative to.  Written after round 1's GPU budget was
+// spent: compiles, has never run.
+__device__ __forceinline__ void slot_publish4(uint32_t addr, float m, int e, int tag) {
+  asm volatile("st.volatile.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+               :: "r"(addr), "r"(__float_as_uint(m)), "r"(e), "r"(tag), "r"(0));
+}
+__device__ __forceinline__ void slot_poll4(uint32_t addr, int tag, float& m, int& e) {
+  uint32_t vm; int ve;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t, n, z;\n"
+      "ld.volatile.shared.v4.b32 {%0, %1, t, z}, [%2];\n"
+      "setp.eq.s32 p, t, %3;\n"
+      "@p bra.uni SC_SLOT4_DONE;\n"
+      "mov.b32 n, 0;\n"
+      "SC_SLOT4_SPIN:\n"
+      "ld.volatile.shared.v4.b32 {%0, %1, t, z}, [%2];\n"
+      "setp.eq.s32 p, t, %3;\n"
+      "@p bra.uni SC_SLOT4_DONE;\n"
+      "add.s32 n, n, 1;\n"
+      "setp.lt.s32 p, n, 0x2000000;\n"
+      "@p bra.uni SC_SLOT4_SPIN;\n"
+      "trap;\n"
+      "SC_SLOT4_DONE:\n"
+      "}\n"
+      : "=r"(vm), "=r"(ve) : "r"(addr), "r"(tag));
+  m = __uint_as_float(vm);
+  e = ve;
+}
+// emission in log2 units (<= 0 after the per-frame shift) -> integer part for the exponent, 2^fraction in [1, 2);
+// anything below -1e6 (masked vocabulary entry, missing node) is probability zero
+__device__ __forceinline__ void ctc_lin_split(float e, float& pf, int& ei) {
+  if (!(e > -1.0e6f)) { pf = 0.f; ei = 0; return; }
+  const float fl = floorf(e);
+  pf = ex2f(e - fl);
+  ei = (int)fl;
+}
+
+template <int dir>
+__device__ __forceinline__ void
+ctc_wave2_lin_body(float* __restrict__ sm, const float* __restrict__ lplat, const float* __restrict__ cshift,
+                   const int64_t* __restrict__ targets, int64_t ldt,
+                   const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                   int Tn, int Smax, int EB, int64_t blank,
+                   float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
+  __shared__ int ired[2][32];
+  __shared__ double dred[32];
+  __shared__ float finm[2];
+  __shared__ int fine[2];
+  __shared__ __align__(8) uint64_t ebar[2];
+  const int b = blockIdx.x;
+  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64;
+  const int U = (int)tgt_lens[b];
+  const int64_t* tg = targets + (int64_t)b * ldt;
+  if (Tb <= 0) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
+    return;
+  }
+  const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
+  const int nwarps = (int)(blockDim.x >> 5);
+  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
+  float* ebuf = sm;
+  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * Smax);   // [nwarps][EB+1] x {mantissa, exponent, tag, -}
+  for (int k = i; k < nwarps * (EB + 1) * 4; k += blockDim.x) slots[k] = -1;
+  if (i == 0) {
+    finm[0] = 0.f; finm[1] = 0.f; fine[0] = CTC_E_DEAD; fine[1] = CTC_E_DEAD;
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool hasb = i <= U, hasl = i < U;
+  const int sb = hasb ? (dir == 0 ? 2 * i : 2 * U - 2 * i) : 0;
+  const int sl = hasl ? (dir == 0 ? 2 * i + 1 : 2 * U - 2 * i - 1) : 0;
+  bool skip = false;
+  if (hasl) {
+    if (dir == 0) skip = i >= 1 && tg[i] != tg[i - 1];
+    else { const int u = U - 1 - i; skip = u + 1 < U && tg[u] != tg[u + 1]; }
+  }
+  const bool producer = lane == 31 && warp + 1 < nwarps;
+  const bool lane0 = lane == 0;
+  const uint32_t my_slot = smem_u32(slots) + (uint32_t)(warp * (EB + 1) * 16);
+  const uint32_t in_slot = smem_u32(slots) + (uint32_t)((warp > 0 ? warp - 1 : 0) * (EB + 1) * 16);
+  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
+  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
+  const int nvis = (Tb + EB - 1) / EB;
+  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
+  auto rows_of = [&](int blk) { const int r = Tb - blk * EB; return r < EB ? r : EB; };
+  auto issue = [&](int vi) {
+    const int blk = blk_of(vi);
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
+    const uint32_t bar = smem_u32(&ebar[vi & 1]);
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * Smax), lp_b + (int64_t)blk * EB * Smax, bytes, bar);
+  };
+  if (i == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  const int t_first = dir == 0 ? 0 : Tb - 1;
+  const int64_t stride = dir == 0 ? (int64_t)Smax : -(int64_t)Smax;
+  const int estride = dir == 0 ? Smax : -Smax;
+  float* opb = out_b + (int64_t)t_first * Smax + sb;
+  float* opl = out_b + (int64_t)t_first * Smax + sl;
+  float mb = 0.f, ml = 0.f;                                      // the pair after the last step: mantissas ...
+  int eb_ = CTC_E_DEAD, el_ = CTC_E_DEAD;                        // ... and exponents
+  int eref = 0;                                                  // what the stored rows of this visit are relative to
+  int g = 0;
+  for (int vi = 0; vi < nvis; ++vi) {
+    int pos = 0;
+    if (vi > 0) {
+      int m = hasb ? max(eb_, el_) : CTC_E_DEAD;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) ired[vi & 1][warp] = m;
+      __syncthreads();
+      m = CTC_E_DEAD;
+      for (int w = 0; w < nwarps; ++w) m = max(m, ired[vi & 1][w]);
+      if (m > CTC_E_DEAD) eref = m;
+      if (i == 0 && vi + 1 < nvis) issue(vi + 1);
+      if (producer) slot_publish4(my_slot, ml, el_, g - 1);      // carry-in of this visit
+    }
+    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+    const int rows = rows_of(blk_of(vi));
+    const float* erow = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * Smax;
+    const float* epb = erow + sb;
+    const float* epl = erow + sl;
+    if (vi == 0) {                                               // first column: nodes 0 and 1 of the scan order
+      if (i == 0) {
+        float pf; int ei;
+        ctc_lin_split(*epb, pf, ei);
+        ctc_lin_renorm(pf, ei, mb, eb_);
+        if (hasl) { ctc_lin_split(*epl, pf, ei); ctc_lin_renorm(pf, ei, ml, el_); }
+      }
+      if (hasb) *opb = dir == 0 ? (mb > 0.f ? lg2f(mb) + (float)eb_ : CTC_DEAD) : (i == 0 ? 0.f : CTC_DEAD);
+      if (hasl) *opl = dir == 0 ? (ml > 0.f ? lg2f(ml) + (float)el_ : CTC_DEAD) : (i == 0 ? 0.f : CTC_DEAD);
+      if (producer) slot_publish4(my_slot + 16, ml, el_, 0);
+      epb += estride; epl += estride;
+      pos = 1;
+      g = 1;
+    }
+    uint32_t rd = in_slot + (uint32_t)(pos * 16);
+    uint32_t wr = my_slot + (uint32_t)((pos + 1) * 16);
+#pragma unroll 2
+    for (; pos < rows; ++pos) {
+      float pfb, pfl; int eib, eil;
+      ctc_lin_split(*epb, pfb, eib);
+      ctc_lin_split(hasl ? *epl : NEG_INF, pfl, eil);            // a missing label node stays dead
+      epb += estride; epl += estride;
+      opb += stride; opl += stride;
+      float xm = __shfl_up_sync(0xffffffffu, ml, 1);
+      int xe = __shfl_up_sync(0xffffffffu, el_, 1);
+      float qm = 0.f; int qe = CTC_E_DEAD;
+      if (warp > 0) slot_poll4(rd, g - 1, qm, qe);
+      if (lane0) { xm = qm; xe = qe; }
+      float nmb, nml, sumb, suml; int neb, nel, emaxb, emaxl;
+      ctc_lin_step(mb, eb_, xm, xe, 0.f, CTC_E_DEAD, pfb, eib, nmb, neb, sumb, emaxb);
+      ctc_lin_step(ml, el_, mb, eb_, skip ? xm : 0.f, skip ? xe : CTC_E_DEAD, pfl, eil, nml, nel, suml, emaxl);
+      mb = nmb; eb_ = neb; ml = nml; el_ = nel;
+      if (hasb) *opb = dir == 0 ? (mb > 0.f ? lg2f(mb) + (float)(eb_ - eref) : CTC_DEAD)
+                                : (sumb > 0.f ? lg2f(sumb) + (float)(emaxb - eref) : CTC_DEAD);
+      if (hasl) *opl = dir == 0 ? (ml > 0.f ? lg2f(ml) + (float)(el_ - eref) : CTC_DEAD)
+                                : (suml > 0.f ? lg2f(suml) + (float)(emaxl - eref) : CTC_DEAD);
+      if (producer) slot_publish4(wr, ml, el_, g);
+      ++g; rd += 16; wr += 16;
+    }
+  }
+  if (dir == 0) {
+    if (i == U) { finm[0] = mb; fine[0] = eb_; }
+    if (i == U - 1) { finm[1] = ml; fine[1] = el_; }
+    __syncthreads();
+    if (i == 0) {
+      const int emax = max(fine[0], fine[1]);
+      const float v = ctc_lin_scale_pow2(finm[0], fine[0] - emax) + ctc_lin_scale_pow2(finm[1], fine[1] - emax);
+      nll[b] = (v > 0.f) ? (float)(-(shift_sum + (double)emax + log2((double)v)) * (double)LN2) : INFINITY;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512, 1)
+ctc_alpha_beta_wave2_lin_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
+                                const int64_t* __restrict__ targets, int64_t ldt,
+                                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                                int Tn, int Smax, int EB, int64_t blank,
+                                float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
+  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB x Smax floats, then nwarps x (EB+1) 16-byte slots
+  if (blockIdx.y == 0) ctc_wave2_lin_body<0>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
+  else ctc_wave2_lin_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
+}
+
 __global__ void __launch_bounds__(512, 1)
 ctc_alpha_beta_wave2_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
                             const int64_t* __restrict__ targets, int64_t ldt,
@@ -1043,8 +1239,21 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
   if (const char* ev = getenv("SC_CTC_WAVE")) {
     const int w = atoi(ev);
     if (w >= 0 && w < wave) wave = w;
-    if (w == 3 && Smax <= 1024) wave = 3;                        // experimental linear-domain recursion (opt-in)
+    if ((w == 3 || w == 4) && Smax <= 1024) wave = w;            // experimental linear-domain recursions (opt-in)
   }
+  if (wave == 4) {
+    const int wthreads = (((int)Umax + 1 + 31) / 32) * 32;
+    size_t smem = 0;
+    const int eb = ctc_wave_rows(Smax, B, wthreads / 32, &smem);
+    smem += (size_t)(wthreads / 32) * (eb + 1) * 8;              // 16-byte slots instead of 8
+    SC_CHECK_ARG(eb > 0 && smem <= 220 * 1024, SC_E_SHAPE);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_wave2_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ctc_alpha_beta_wave2_lin_kernel<<<dim3((unsigned)B, 2), wthreads, smem, st>>>(lplat, cshift, targets, ldt, in_lens,
+        tgt_lens, (int)T, Smax, eb, blank, alpha, beta, nll);
+  } else
   if (wave == 3) {
     const size_t smem = (4 * (size_t)(Smax + 4) + 2 * (size_t)CTC_EB * Smax) * sizeof(float);
     SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);

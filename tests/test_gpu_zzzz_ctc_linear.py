@@ -16,7 +16,7 @@ pytestmark = [pytest.mark.gpu,
 
 @pytest.mark.parametrize("shape", [(5, 700, 64, 150), (3, 50, 11, 6), (2, 3000, 1024, 150)], ids=["cfg2like", "small", "cfg2row"])
 def test_linear_domain_lattice_kernel_agrees(cuda_device, monkeypatch, shape):
-    """SC_CTC_WAVE=3 (EXPERIMENTAL: linear-domain recursion with a per-node exponent, opt-in) against the default
+    """SC_CTC_WAVE=3 and 4 (EXPERIMENTAL: linear-domain recursion with a per-node exponent, opt-in) against the default
     kernel and torch's fp64 ctc_loss: loss, gradient, ragged lengths, an empty transcript, a one-frame
     utterance, an infeasible one, repeated labels, and peaky logits (the input that breaks a column-scaled
     linear recursion)."""
@@ -40,13 +40,14 @@ def test_linear_domain_lattice_kernel_agrees(cuda_device, monkeypatch, shape):
         ref = torch.nn.functional.ctc_loss(xd.log_softmax(-1).transpose(0, 1), tokens, inl, tgl, zero_infinity=True)
         ref.backward()
         out = {}
-        for wave in ("2", "3"):
+        for wave in ("2", "3", "4"):
             monkeypatch.setenv("SC_CTC_WAVE", wave)
             x = logits.cuda().requires_grad_(True)
             loss = ctc_loss_from_logits(x, tokens.cuda(), inl, tgl, zero_infinity=True)
             loss.backward()
             out[wave] = (loss.item(), x.grad.cpu())
         monkeypatch.delenv("SC_CTC_WAVE")
-        np.testing.assert_allclose(out["3"][0], ref.item(), rtol=1e-4)
-        np.testing.assert_allclose(out["3"][1].numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-7)
-        assert (out["3"][1] - out["2"][1]).abs().max().item() < 5e-6
+        for wave in ("3", "4"):                               # 3: block-barrier structure, 4: pair-per-thread wavefront
+            np.testing.assert_allclose(out[wave][0], ref.item(), rtol=1e-4, err_msg=wave)
+            np.testing.assert_allclose(out[wave][1].numpy(), xd.grad.numpy(), rtol=2e-3, atol=2e-7, err_msg=wave)
+            assert (out[wave][1] - out["2"][1]).abs().max().item() < 5e-6, wave
