@@ -962,7 +962,7 @@ ctc_wave2_lin_body(float* __restrict__ sm, const float* __restrict__ lplat, cons
       if (warp > 0) slot_poll4(rd, g - 1, qm, qe);
       if (lane0) { xm = qm; xe = qe; }
       float nmb, nml, sumb, suml; int neb, nel, emaxb, emaxl;
-      ctc_lin_step(mb, eb_, xm, xe, 0.f, CTC_E_DEAD, pfb, eib, nmb, neb, sumb, emaxb);
+      ctc_lin_step2(mb, eb_, xm, xe, pfb, eib, nmb, neb, sumb, emaxb);
       ctc_lin_step(ml, el_, mb, eb_, skip ? xm : 0.f, skip ? xe : CTC_E_DEAD, pfl, eil, nml, nel, suml, emaxl);
       mb = nmb; eb_ = neb; ml = nml; el_ = nel;
       if (hasb) *opb = dir == 0 ? (mb > 0.f ? lg2f(mb) + (float)(eb_ - eref) : CTC_DEAD)

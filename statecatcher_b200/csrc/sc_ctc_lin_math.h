@@ -57,3 +57,11 @@ SC_LIN_HD void ctc_lin_step(float ma, int ea, float mb, int eb, float mc, int ec
   sum = ctc_lin_scale_pow2(ma, ea - emax) + ctc_lin_scale_pow2(mb, eb - emax) + ctc_lin_scale_pow2(mc, ec - emax);
   ctc_lin_renorm(sum * pf, emax + ei, mn, en);
 }
+
+// Two predecessors only (a blank node: itself and the node before it).
+SC_LIN_HD void ctc_lin_step2(float ma, int ea, float mb, int eb, float pf, int ei,
+                             float& mn, int& en, float& sum, int& emax) {
+  emax = ea > eb ? ea : eb;
+  sum = ctc_lin_scale_pow2(ma, ea - emax) + ctc_lin_scale_pow2(mb, eb - emax);
+  ctc_lin_renorm(sum * pf, emax + ei, mn, en);
+}

@@ -43,7 +43,8 @@ int main(int argc, char** argv) {
       float mc = 0.f; int ec = CTC_E_DEAD;
       if (skip[s]) { mc = pm[s]; ec = pe[s]; }
       float mn, sum; int en, emax;
-      ctc_lin_step(pm[s + 2], pe[s + 2], pm[s + 1], pe[s + 1], mc, ec, pf, ei, mn, en, sum, emax);
+      if (s & 1) ctc_lin_step(pm[s + 2], pe[s + 2], pm[s + 1], pe[s + 1], mc, ec, pf, ei, mn, en, sum, emax);
+      else       ctc_lin_step2(pm[s + 2], pe[s + 2], pm[s + 1], pe[s + 1], pf, ei, mn, en, sum, emax);   // blank: two predecessors
       cm[s + 2] = mn; ce[s + 2] = en;
       out[(size_t)t * S + s] = mn > 0.f ? log2((double)mn) + en : -INFINITY;
     }
