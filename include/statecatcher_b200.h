@@ -12,7 +12,13 @@
  *
  * Conventions
  *   - all pointers are raw DEVICE pointers unless a parameter says "host";
- *   - nothing is allocated, no static mutable state, every call is re-entrant;
+ *   - nothing is allocated and every call is re-entrant (forward thread and autograd's backward
+ *     thread may call concurrently, for one or several devices of a process).  The only state the
+ *     library keeps is a set of one-time, per-DEVICE caches published through atomics (SM count,
+ *     'max dynamic shared memory already raised for this kernel') and environment switches
+ *     (SC_*) latched once, immutable afterwards;
+ *   - kernels are launched on the CUDA runtime's CURRENT device: the caller selects the device
+ *     that owns the pointers first (the Python layer does: `torch.cuda.device_of(tensor)`);
  *   - every call takes the cudaStream_t to launch on (as void*), and only enqueues work;
  *   - sizes/strides are int64_t counted in ELEMENTS, not bytes;
  *   - dtype codes: SC_F32 = 0, SC_BF16 = 1 (storage type of activations; all arithmetic

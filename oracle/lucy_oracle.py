@@ -252,9 +252,14 @@ def _linear_scan(a, b, x0):
     """y_t = a_t*y_{t-1} + b_t over dim 1, y_{-1}=x0.  Returns all y."""
     y = x0
     out = []
-    for t in range(a.shape[1]):
-        y = a[:, t] * y + b[:, t]
+    # unbind, not a[:, t]: the backward of T separate selects zero-fills a full [B,T,H] tensor per
+    # step (O(T^2) traffic — the very cost SURVEY.md 0.10 measures in the reference); unbind's
+    # backward is one stack.  Same values either way.
+    for a_t, b_t in zip(a.unbind(1), b.unbind(1)):
+        y = a_t * y + b_t
         out.append(y)
+    if not out:
+        return a.new_zeros(a.shape)
     return torch.stack(out, dim=1)
 
 

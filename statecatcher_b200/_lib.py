@@ -120,6 +120,34 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def device_ctx(t):
+    """Context manager that makes ``t``'s CUDA device current (nothing for non-CUDA tensors)."""
+    import contextlib
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        return torch.cuda.device(t.device)
+    return contextlib.nullcontext()
+
+
+def on_tensor_device(fn):
+    """Decorator for the public entry points: run ``fn`` with the CUDA runtime's current device set
+    to the device of its first CUDA tensor argument.  The C-ABI launches on the CURRENT device and
+    ``stream()`` returns the current device's stream, so a model on cuda:1 called while cuda:0 is
+    current would otherwise launch on the wrong device with foreign pointers (autograd's backward
+    thread already switches to the tensors' device by itself)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+    return wrapper
+
+
 def require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise RuntimeError(
@@ -171,6 +199,8 @@ def call(name: str, *args):
     global launches, kernels
     launches += 1
     kernels += KERNELS_PER_CALL.get(name, 1)
+    if name == "sc_gemm_wgrad" and args[9] == SC_BF16 and not args[10]:
+        kernels += 1                 # the tcgen05 split-R wgrad zero-fills dW first (zero2d_kernel) when not accumulating
     fn = getattr(load(), name)
     if profile is None:
         check(fn(*args), name)

@@ -1204,11 +1204,7 @@ extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t st
 // Rows of emissions per block meeting of the wavefront kernel: as many as fit next to the
 // other CTAs that have to share an SM (2B CTAs over the device), at most 64.
 static int ctc_wave_rows(int Smax, int64_t B, int nwarps, size_t* smem_out) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = num_sms();
   int per_sm = (int)((2 * B + sms - 1) / sms);
   if (per_sm > 8) per_sm = 8;
   const size_t budget = (size_t)220 * 1024 / (size_t)per_sm - 2048;

@@ -419,13 +419,11 @@ static int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   // gain (GEMM total 26.7 -> 25.3 ms per step: a third less shared-memory traffic per flop is
   // also less energy per flop).  SC_GEMM_PAIR=0 selects the multicast variant (A/B measurements).
   static const bool pair = [] { const char* e = getenv("SC_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  static std::atomic<uint64_t> attr_done{0};                      // per (instantiation, device); see ensure_dyn_smem
+  {
+    cudaError_t e = ensure_dyn_smem(pair ? gemm_tc_kernel<A_MN, B_MN, EPI, true> : gemm_tc_kernel<A_MN, B_MN, EPI, false>,
+                                    SMEM_BYTES, attr_done);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int64_t total = (int64_t)((p.tiles_i + 1) / 2) * p.tiles_j * p.splits;   // work items per CTA pair
   const int64_t clusters = total < num_sms() / 2 ? total : num_sms() / 2;

@@ -449,9 +449,8 @@ using namespace sc;
 
 // SC_SCAN_GENERIC=1 in the environment forces the register-prefetch kernels (A/B measurements)
 static bool scan_force_generic() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SC_SCAN_GENERIC"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+  static const bool v = [] { const char* e = getenv("SC_SCAN_GENERIC"); return e && e[0] == '1'; }();
+  return v;
 }
 
 static bool scan_args_ok(int64_t B, int64_t T, int64_t H) {

@@ -656,8 +656,7 @@ static bool tma_ok(const void* G, int64_t ldg, const void* a, int64_t lda, const
 
 // SC_SCAN_VEC=1|2 in the environment overrides the channels-per-thread choice (A/B measurements)
 static int scan_vec_choice() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SC_SCAN_VEC"); v = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0; }
+  static const int v = [] { const char* e = getenv("SC_SCAN_VEC"); return (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0; }();
   return v;
 }
 
@@ -673,12 +672,10 @@ static int scan_fwd_tma(const void* G, int64_t ldg, const float* h0, const float
   const unsigned grid = (unsigned)(B * cblocks);
   auto kt = lucy_scan_fwd_tma_kernel<T, VEC, NST, true, PRECISE>;
   auto ks = lucy_scan_fwd_tma_kernel<T, VEC, NST, false, PRECISE>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static std::atomic<uint64_t> attr_t{0}, attr_s{0};             // per (instantiation, device)
+  {
+    const cudaError_t e = train ? ensure_dyn_smem(kt, smem, attr_t) : ensure_dyn_smem(ks, smem, attr_s);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   if (train) kt<<<grid, CB / VEC, smem, st>>>(mapG, h0, s0, (T*)Hout, ldh, hT, sT, Sckpt, (int)Tn, (int)H, cblocks);
   else       ks<<<grid, CB / VEC, smem, st>>>(mapG, h0, s0, (T*)Hout, ldh, hT, sT, Sckpt, (int)Tn, (int)H, cblocks);
@@ -699,12 +696,10 @@ static int scan_bwd_tma(const void* G, int64_t ldg, const void* Hout, int64_t ld
   const unsigned grid = (unsigned)(B * cblocks);
   auto kt = lucy_scan_bwd_tma_kernel<T, VEC, NST, true, PRECISE>;
   auto ks = lucy_scan_bwd_tma_kernel<T, VEC, NST, false, PRECISE>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static std::atomic<uint64_t> attr_t{0}, attr_s{0};             // per (instantiation, device)
+  {
+    const cudaError_t e = train ? ensure_dyn_smem(kt, smem, attr_t) : ensure_dyn_smem(ks, smem, attr_s);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   if (train) kt<<<grid, CB / VEC, smem, st>>>(mapG, mapH, mapDH, h0, Sckpt, (T*)dG, lddg, dbias, (int)Tn, (int)H, cblocks);
   else       ks<<<grid, CB / VEC, smem, st>>>(mapG, mapH, mapDH, h0, Sckpt, (T*)dG, lddg, dbias, (int)Tn, (int)H, cblocks);

@@ -1,6 +1,7 @@
 // mbarrier / TMA / tcgen05 PTX wrappers and the host-side tensor-map encoder shared by the
 // tcgen05 GEMM (sc_gemm_tcgen05.cu) and the TMA-staged scans (sc_scan_tma.cu).
 #pragma once
+#include <atomic>
 #include "sc_common.cuh"
 #include <cuda.h>
 
@@ -158,29 +159,51 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // C++11 magic static: initialised once, thread-safe, immutable afterwards
+  static const EncodeTiledFn fn = [] {
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
+      return (EncodeTiledFn)ptr;
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
 
+// Per-device one-time caches.  The exports are called from the forward thread and from autograd's
+// backward thread, possibly for several devices of one process: everything cached below is keyed by
+// the CURRENT device and published through atomics (a lost race only repeats an idempotent query).
+constexpr int SC_MAX_DEVICES = 64;
+
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev;
+}
+
 inline int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[SC_MAX_DEVICES];                   // zero-initialised
+  const int dev = current_device();
+  std::atomic<int>& slot = cache[dev % SC_MAX_DEVICES];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device).  `done` is a
+// function-local `static std::atomic<uint64_t>` of the call site (one per template instantiation).
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, int bytes, std::atomic<uint64_t>& done) {
+  const uint64_t bit = 1ull << (current_device() % SC_MAX_DEVICES);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 }  // namespace sc

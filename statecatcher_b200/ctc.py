@@ -81,6 +81,7 @@ class _CTCFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+@_lib.on_tensor_device
 def ctc_loss(log_probs: torch.Tensor, targets: torch.Tensor, input_lengths: LenT,
              target_lengths: LenT, blank: int = 0, reduction: str = "mean",
              zero_infinity: bool = False) -> torch.Tensor:

@@ -16,6 +16,7 @@ from ._lib import call, dt, ptr, stream
 from .ctc import _lens
 
 
+@_lib.on_tensor_device
 def ctc_greedy_decoder(log_probs: torch.Tensor, input_lengths, blank: int = 0) -> List[List[int]]:
     _lib.require_cuda(log_probs, "ctc_greedy_decoder input")
     x = log_probs

@@ -44,6 +44,7 @@ class _Frontend(nn.Module):
     def num_frames(n_samples: int) -> int:
         return 0 if n_samples < N_FFT else 1 + (n_samples - N_FFT) // HOP
 
+    @_lib.on_tensor_device
     def features(self, waveform: torch.Tensor, frame_mask: torch.Tensor = None) -> torch.Tensor:
         """(..., S) -> (..., T, 80) contiguous fp32 (the layout the encoder consumes).  With
         ``frame_mask`` (B, T) bool (MFCC only) masked frames come out as zeros: model.py:377's
@@ -108,6 +109,7 @@ def _mask_geometry(S: int, subsample: float) -> Tuple[int, int]:
     return T, sub
 
 
+@_lib.on_tensor_device
 def frame_mask_and_lens(sample_mask: torch.Tensor, n_feat_frames: int, stack_order: int = 1
                         ) -> Tuple[torch.Tensor, List[int]]:
     """train.py:486-490 in one kernel: ``sample_mask`` (B, S) bool -> (frame_mask (B, T) bool,

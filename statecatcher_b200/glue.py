@@ -127,6 +127,9 @@ class SegmentPrefetcher:
         self.released = [None, None]          # compute-stream events guarding buffer reuse
         self.slot = 0
         self.pending = None
+        # the staging buffers come from the caching allocator of the CURRENT stream: a recycled block may
+        # still be read by compute work already in flight, so the copy stream starts behind it
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
         self._stage()
 
     def _stage(self):
@@ -243,8 +246,8 @@ class GraphedTrainStep:
     For small models (BASELINE configs[0]: 2 x 256, 8 streams x 1000 frames) a step is a chain of ~300 launches
     of a few microseconds each and the GPU waits for Python; captured once, the chain replays without the launch
     path.  Features, labels, lengths, the carried ``(h, s)`` and the loss live in static buffers; the parameter
-    gradients are the graph's own tensors, OVERWRITTEN by every replay (clear them with
-    ``zero_grad(set_to_none=False)`` or not at all — ``set_to_none=True`` would detach the optimizer from them).
+    gradients are the graph's own tensors, OVERWRITTEN by every replay (no need to clear them; ``step``
+    re-attaches them to ``p.grad`` when ``zero_grad(set_to_none=True)`` has dropped them).
     The state of segment k seeds segment k+1 inside the graph, detached at the boundary exactly as
     ``compute_loss`` does it (model.py:60-63); ``reset()`` starts new streams.
 
@@ -292,6 +295,9 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._step()
+        # the captured gradient tensors are the only link between a replay and the optimizer
+        self._params = params
+        self._grads = [p.grad for p in params]
 
     def _step(self):
         blank, reduction, zero_infinity = self.head
@@ -320,6 +326,12 @@ class GraphedTrainStep:
             if t.numel() != dst.numel():
                 raise ValueError(f"{name} must have {dst.numel()} entries")
             dst.copy_(t.to(torch.int64), non_blocking=True)
+        # optimizer.zero_grad() (set_to_none=True is torch's default) or a user assignment may have
+        # detached p.grad from the graph's own gradient tensor: replay would still write the captured
+        # buffer while the optimizer saw nothing and silently stopped updating.  Re-attach.
+        for p, g in zip(self._params, self._grads):
+            if p.grad is not g:
+                p.grad = g
         self.graph.replay()
         return self.loss
 

@@ -74,6 +74,7 @@ class LucyRNNCell(nn.Module):
                 nn.init.constant_(ln.bias, 0)
                 nn.init.constant_(ln.weight, 1.0)
 
+    @_lib.on_tensor_device
     def forward(self, x, h_prev, s_prev, mask=None):
         if mask is not None:
             raise NotImplementedError("LucyRNNCell: mask must be None (dead argument upstream)")
@@ -392,6 +393,7 @@ class LucyRNN(nn.Module):
         nn.init.zeros_(self.output_proj.weight)
         nn.init.zeros_(self.output_proj.bias)
 
+    @_lib.on_tensor_device
     def forward(self, x, hidden_states=None, masks=None):
         cfg = self.config
         if masks is not None:
@@ -413,6 +415,19 @@ class LucyRNN(nn.Module):
             s = [torch.zeros(batch_size, H, device=x.device) for _ in range(cfg.num_layers)]
         else:
             h, s = hidden_states                                    # caller's lists, updated in place
+            # the reference fails with a broadcast error when a carried state does not match the
+            # batch (e.g. a last partial batch, lucyrnn.py:64); here the scan would read h0/s0 out
+            # of bounds, so check before anything is enqueued
+            for nm, lst in (("h", h), ("s", s)):
+                if len(lst) != cfg.num_layers:
+                    raise RuntimeError(f"LucyRNN.forward: hidden_states {nm} has {len(lst)} entries, "
+                                       f"the model has {cfg.num_layers} layers")
+                for l, t in enumerate(lst):
+                    if tuple(t.shape) != (batch_size, H):
+                        raise RuntimeError(f"LucyRNN.forward: carried state {nm}[{l}] has shape {tuple(t.shape)}, "
+                                           f"expected ({batch_size}, {H}) for this batch")
+                    if t.device != x.device:
+                        raise RuntimeError(f"LucyRNN.forward: carried state {nm}[{l}] is on {t.device}, input on {x.device}")
         cd = _compute_dtype(x, self.compute_dtype)
         inp = x.contiguous()
         if inp.dtype != cd:

@@ -66,10 +66,11 @@ def clip_grad_norm_(parameters, max_norm: float) -> torch.Tensor:
     pgs = _grads(list(parameters))
     if not pgs:
         return torch.zeros(())
-    acc = _global_sumsq(pgs, pgs[0][1].device)
-    for _, g in pgs:
-        call("sc_scale_grads", ptr(g), g.numel(), ptr(acc), float(max_norm), stream())
-    return acc.sqrt().float()
+    with _lib.device_ctx(pgs[0][1]):
+        acc = _global_sumsq(pgs, pgs[0][1].device)
+        for _, g in pgs:
+            call("sc_scale_grads", ptr(g), g.numel(), ptr(acc), float(max_norm), stream())
+        return acc.sqrt().float()
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -87,11 +88,18 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        loss = closure() if closure is not None else None
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():                      # a standard closure calls loss.backward()
+                loss = closure()
         allp = [p for grp in self.param_groups for p in grp["params"]]
         pgs = _grads(allp)
         if not pgs:
             return loss
+        with _lib.device_ctx(pgs[0][1]):          # the C-ABI launches on the current device
+            return self._step(pgs, loss)
+
+    def _step(self, pgs, loss):
         acc = None
         if self.max_grad_norm is not None:
             acc = _global_sumsq(pgs, pgs[0][1].device, self.multi_tensor)
@@ -149,6 +157,10 @@ class Lion(torch.optim.Optimizer):
         pgs = _grads(allp)
         if not pgs:
             return loss
+        with _lib.device_ctx(pgs[0][1]):
+            return self._step(pgs, loss)
+
+    def _step(self, pgs, loss):
         acc = None
         if self.max_grad_norm is not None:
             acc = _global_sumsq(pgs, pgs[0][1].device, self.multi_tensor)

@@ -65,6 +65,7 @@ def _reduce(nll, reduction):
     raise ValueError(f"unknown reduction {reduction!r}")
 
 
+@_lib.on_tensor_device
 def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
               reduction: str = "mean", compact: bool = False) -> torch.Tensor:
     """log_probs: (B,T,U+1,V) normalised (log_softmax of the joint), or with compact=True the
@@ -117,6 +118,7 @@ class RNNTPredictorJoiner(nn.Module):
             x = x.to(cd)
         return _LinearFn.apply(x.contiguous(), layer.weight, layer.bias, cd)
 
+    @_lib.on_tensor_device
     def forward(self, enc_out: torch.Tensor, prefix: torch.Tensor):
         pred_emb = self.embedding(prefix)                        # (B, U+1, E)
         enc = self._lin(enc_out, self.enc_proj)                  # (B, T, J)
@@ -129,6 +131,7 @@ class RNNTCompactPredictorJoiner(RNNTPredictorJoiner):
     """model.py:147-200: joint only over the live T_b x (U_b+1) nodes of every utterance, packed
     as (sum_b T_b*(U_b+1), J) rows -> (rows, V) logits (no padding work, no padded lattice)."""
 
+    @_lib.on_tensor_device
     def forward(self, enc_out, prefix, in_lens, tgt_lens):
         B = enc_out.size(0)
         in_lens = [int(v) for v in (in_lens.tolist() if isinstance(in_lens, torch.Tensor) else in_lens)]
@@ -288,6 +291,7 @@ class RNNTFusedHead(nn.Module):
         self.compute_dtype = compute_dtype
         self.keep_blocks = keep_blocks        # None: keep the blocks' joint/logits when they fit in free HBM, else recompute
 
+    @_lib.on_tensor_device
     def forward(self, enc_out, tokens, frames_lengths, labels_lengths, blank_id: int = 0, reduction: str = "mean"):
         _lib.require_cuda(enc_out, "RNNTFusedHead input")
         B = enc_out.size(0)
