@@ -54,7 +54,6 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="forward-only workloads: replay each segment from a CUDA graph (GraphedStreamingEncoder)")
     ap.add_argument("--detail", action="store_true", help="per-call timing table of the last timed step on stderr")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
 
@@ -137,63 +136,119 @@ def init_reference_like(model, seed, out_std=0.02):
 
 
 # --------------------------------------------------------------------------------------
-def cpu_reference_run(W, layer_norm, steps, warmup, target_seconds, B=None, T=None):
-    """The reference's CPU algorithm (oracle.lucy_oracle.forward_looped: per-timestep cell loop
-    with re-projection, lucyrnn.py:109-170) + nn.CTCLoss + backward, fp32, all host threads,
-    on a bounded sample of the workload.  Returns frames/s and a description."""
+# Fixed CPU samples — identical for every N and every run:
+#   configs[0] in full:           2 x 256, B=8, T=1000, 4 carried segments, U in [25, 50]
+#   configs[1..4] (6 x 1024):     the stated reduced shape B=8, T=300 (SURVEY.md 8d label lengths U in [T/40, T/20]),
+#                                 because 192 000 frames per step is >20 min of CPU per step
+CPU_SAMPLES = {
+    "cfg1": dict(B=8, T=1000, umin=25, umax=50, segments=4),
+    "default": dict(B=8, T=300, umin=7, umax=15, segments=1),
+}
+REFERENCE_DIR = "/root/reference"
+
+
+def _cpu_sample_batch(W, S, seed):
+    """Same recipe as synth_batch at the sample's shape: one shortened and one finished stream."""
+    return synth_batch(dict(W, B=S["B"], T=S["T"], umin=S["umin"], umax=S["umax"]), seed)
+
+
+def _reference_module(W, layer_norm):
+    """The UNMODIFIED reference (lucyrnn.py:72-191, kernel_impl="native"), when its tree is mounted (the
+    authoring container; it cannot travel to the GPU box).  Returns (step_fn, 'reference') or None."""
+    if not os.path.isfile(os.path.join(REFERENCE_DIR, "lucyrnn.py")):
+        return None
+    saved = {k: sys.modules.pop(k) for k in ("lucyrnn", "lucyrnn_conf", "lucyrnn_triton") if k in sys.modules}
+    sys.path.insert(0, REFERENCE_DIR)
+    try:
+        import lucyrnn as ref_lucyrnn                              # noqa: E402  (needs triton importable: lucyrnn.py:4)
+        from lucyrnn_conf import LucyRNNConfig as RefConfig
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(REFERENCE_DIR)
+        for k in ("lucyrnn", "lucyrnn_conf", "lucyrnn_triton"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+    cfg = RefConfig(input_dim=W["F"], hidden_dim=W["H"], num_layers=W["L"], vocab_size=W["V"], kernel_impl="native",
+                    is_training=True, fused_ops=True, layer_norm=layer_norm)
+    model = ref_lucyrnn.LucyRNN(cfg)
+    init_reference_like(model, 1234)
+
+    def detach(st):                                                 # model.py:11-25 on the (h, s) tuple of lists
+        return tuple([t.detach() for t in lst] for lst in st)
+
+    def step(x, state):
+        model.zero_grad(set_to_none=True)
+        logits, state = model(x, detach(state)) if state else model(x)
+        return logits, state
+    return step
+
+
+def _port_module(W, layer_norm):
     from oracle import lucy_oracle as LO
-    torch.set_num_threads(os.cpu_count() or 1)
-    cores = torch.get_num_threads()
     cfg = LO.OracleConfig(input_dim=W["F"], hidden_dim=W["H"], num_layers=W["L"], vocab_size=W["V"],
                           is_training=True, fused_ops=True, layer_norm=layer_norm)
     P = LO.reference_init_params(cfg, 1234)
     for p in P.values():
         p.requires_grad_(True)
-    B = B or min(W["B"], 8)
+
+    def step(x, state):
+        for p in P.values():
+            p.grad = None
+        return LO.forward_looped_as_timed(P, cfg, x, LO.detach_states(state) if state else None)
+    return step
+
+
+def cpu_reference_run(W, workload, layer_norm, steps, warmup):
+    """The reference's CPU path on the box's host cores, fp32, all host threads: the unmodified reference
+    module when /root/reference is mounted (kind "reference"), else the oracle's restatement of the same
+    per-timestep algorithm including its slice-assign memory behaviour (kind "port"); + nn.CTCLoss + backward,
+    state detached and carried between steps (model.py:60-63, train.py:580).  One step = one segment of the
+    FIXED sample shape (CPU_SAMPLES).  Returns frames/s, cores, kind, description, ms per step."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    S = CPU_SAMPLES.get(workload, CPU_SAMPLES["default"])
+    stepfn = _reference_module(W, layer_norm)
+    kind = "reference" if stepfn is not None else "port"
+    if stepfn is None:
+        stepfn = _port_module(W, layer_norm)
     crit = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+    batches = [_cpu_sample_batch(W, S, 1234 + i) for i in range(2)]
 
-    def run(Tn, nsteps):
-        g = torch.Generator().manual_seed(7)
-        state, t0 = None, time.perf_counter()
-        for _ in range(nsteps):
-            x = torch.randn(B, Tn, W["F"], generator=g)
-            U = max(1, Tn // 25)
-            tok = torch.randint(1, W["V"], (B, U), generator=g)
-            for p in P.values():
-                p.grad = None
-            if state:
-                state = LO.detach_states(state)
-            logits, state = LO.forward_looped(P, cfg, x, state)
-            loss = crit(logits.log_softmax(-1).transpose(0, 1), tok, [Tn] * B, [U] * B)
+    def run(nsteps, state):
+        t0 = time.perf_counter()
+        for i in range(nsteps):
+            x, tok, inl, tgl = batches[i % 2]
+            logits, state = stepfn(x, state)
+            loss = crit(logits.log_softmax(-1).transpose(0, 1), tok, inl, tgl)     # model.py:70-71
             loss.backward()
-        return time.perf_counter() - t0
+        return time.perf_counter() - t0, state
 
-    if T is None:
-        probe_T = 8
-        dt = run(probe_T, 1)                       # calibrate (also warms the thread pool)
-        per_frame_step = dt / probe_T
-        T = int(max(8, min(W["T"], target_seconds / max(per_frame_step, 1e-6) / max(steps + warmup, 1))))
+    state = None
     if warmup:
-        run(T, warmup)
-    dt = run(T, steps)
-    fps = B * T * steps / dt
-    sample = (f"{W['L']}x{W['H']} V={W['V']} fp32 fused_ops=True layer_norm={layer_norm}, B={B}, T={T} frames, "
-              f"{steps} carried segment(s); reference loop structure (lucyrnn.py:109-170) restated in oracle/lucy_oracle.py")
-    return fps, cores, sample, dt / steps * 1e3, B, T
+        _, state = run(warmup, state)
+    dt, _ = run(steps, state)
+    fps = S["B"] * S["T"] * steps / dt
+    src = ("unmodified /root/reference/lucyrnn.py LucyRNN(kernel_impl='native')" if kind == "reference" else
+           "oracle/lucy_oracle.forward_looped_as_timed (reference loop + slice-assign structure, lucyrnn.py:109-170; "
+           "the reference tree is not mounted on this box)")
+    sample = (f"{W['L']}x{W['H']} V={W['V']} fp32 fused_ops=True layer_norm={layer_norm}, fixed shape B={S['B']} T={S['T']} "
+              f"U in [{S['umin']},{S['umax']}], {steps} timed step(s) with carried state after {warmup} warm-up; "
+              f"os.cpu_count()={os.cpu_count()} torch threads={cores}; {src} + nn.CTCLoss + backward")
+    return fps, cores, kind, sample, dt / steps * 1e3
 
 
 def reference_arm(args, W):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fps, cores, sample, ms, B, T = cpu_reference_run(W, args.layer_norm, args.steps, args.warmup,
-                                                     target_seconds=max(20.0, 8.0 * args.steps))
+    fps, cores, kind, sample, ms = cpu_reference_run(W, args.workload, args.layer_norm, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, W, max(1, args.gpus)),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -487,8 +542,10 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not fwd_only:
-        fps, cores, sample, _, _, _ = cpu_reference_run(W, bool(args.layer_norm), 1, 0, args.cpu_seconds)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        # bounded sample: cfg1 = its 4 carried segments in full (~30 s); 6x1024 = 2 steps of the reduced shape
+        nst = CPU_SAMPLES[args.workload]["segments"] if args.workload in CPU_SAMPLES else 2
+        fps, cores, kind, sample, _ = cpu_reference_run(W, args.workload, bool(args.layer_norm), nst, 0)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
 
     line = {
         "metric": "forward_frames_per_sec" if fwd_only else "train_frames_per_sec", "value": value, "unit": "frames/s",

@@ -170,21 +170,32 @@ int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn
  * the (T,B,V) transposed view nn.CTCLoss receives are accepted.  Rows need not be
  * normalised (log-softmax is folded in and is idempotent).
  * targets [B,Umax] int64 (row stride ldt), in_lens/tgt_lens [B] int64.
- * Workspaces (caller-allocated, fp32, 16-byte aligned): lse [B,T], cshift [B,T] (per-frame shift
- * taken out of the lattice emissions: the largest of them, log2 units), lplat/alpha/beta [B,T,S]
- * with S = 2*Umax+1 rounded up to a multiple of 4 (alpha/beta are in log2 units; alpha includes
- * the emission of its frame, beta does not; both carry an arbitrary per-frame offset).  nll [B] = per-utterance negative log-likelihood (+inf if infeasible);
+ * Lengths are validated on the device (they may be device tensors the host never sees): T_b is clamped
+ * to T; an utterance with U_b < 0 or U_b > Umax, or with a label outside [0, V), is reported infeasible
+ * (nll = +inf, zero gradient row) instead of reading out of bounds.
+ * Workspaces (caller-allocated, 16-byte aligned): lse [B,T] fp32, cshift [B,T] fp32 (per-frame shift
+ * taken out of the lattice emissions: the largest of them, log2 units), lplat/alpha/beta [B,T,S] 4-byte
+ * cells with S = 2*Umax+1 rounded up to a multiple of 4, and the opaque `ws` of
+ * sc_ctc_workspace_bytes(B, T, Umax) bytes (per-utterance format flags, per-direction likelihoods and range
+ * records).  The CONTENT of lplat/alpha/beta is private to the three passes and depends on Umax:
+ *   Umax <= 255: fp64 linear-domain recursion (csrc/sc_ctc_lin64.cuh) — lplat rows hold U+1 emission
+ *     probabilities, alpha/beta rows the high words of fp64 node values; utterances whose dynamic range fp64
+ *     cannot hold are detected, flagged in ws and recomputed by the log-domain kernel;
+ *   larger lattices: log-domain recursion, fp32 log2 values (alpha with its frame's emission, beta without).
+ * The same lse / alpha / beta / nll / ws must be handed to sc_ctc_bwd.
+ * nll [B] = per-utterance negative log-likelihood (+inf if infeasible);
  * loss [1] = reduction of nll: reduction 0 none (loss untouched), 1 mean
  * = mean_b(nll_b/max(U_b,1)), 2 sum; infeasible utterances contribute 0 (zero_infinity). */
+int64_t sc_ctc_workspace_bytes(int64_t B, int64_t T, int64_t Umax);
 int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
                int64_t blank, float* lse, float* lplat, float* cshift, float* alpha, float* beta,
-               float* nll, float* loss, int reduction, void* stream);
+               float* nll, float* loss, int reduction, void* ws, void* stream);
 /* The two halves of sc_ctc_fwd as separate calls (what statecatcher_b200/ctc.py binds, so that
  * the bandwidth-bound emission pass and the latency-bound lattice recursion are timed apart):
- * sc_ctc_emissions: logits -> lse, lplat, cshift (log-softmax + gather of the 2U+1 lattice emissions);
- * sc_ctc_lattice:   lplat, cshift -> alpha, beta, nll, loss (the alpha/beta recursions + reduction). */
+ * sc_ctc_emissions: logits -> lse, lplat, cshift (log-softmax + gather of the lattice emissions);
+ * sc_ctc_lattice:   lplat, cshift -> alpha, beta, nll, loss, ws (the alpha/beta recursions + reduction). */
 int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                      const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                      const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
@@ -192,7 +203,7 @@ int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int
 int sc_ctc_lattice(const float* lplat, const float* cshift, const int64_t* targets, int64_t ldt,
                    const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T,
                    int64_t Umax, int64_t blank, float* alpha, float* beta, float* nll,
-                   float* loss, int reduction, void* stream);
+                   float* loss, int reduction, void* ws, void* stream);
 /* dlogits[b,t,:] = gout * scale_b * (softmax - occupancy) for t < T_b, exactly 0 for
  * t >= T_b and for infeasible utterances.  grad_out: device fp32, [1] for mean/sum, [B]
  * for reduction none.  dlogits strides like logits. */
@@ -201,7 +212,8 @@ int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype
                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
                int64_t blank, const float* lse, const float* alpha, const float* beta,
                const float* nll, const float* grad_out, int reduction,
-               void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype, void* stream);
+               void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
+               const void* ws, void* stream);
 
 /* ---------------------------------------------------------------- K4: RNN-T ----------
  * Replaces warp_rnnt.RNNTLoss as called at model.py:97-105 (gather=True): transducer

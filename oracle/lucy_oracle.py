@@ -245,6 +245,55 @@ def forward_looped(P, cfg, x, state=None):
     return logits, (h, s)
 
 
+def _cell_as_timed(P, pre, cfg, x_t, h_prev, s_prev):
+    """_cell with the reference's operation GRANULARITY as well (lucyrnn.py:44-70): one 6H-wide
+    fused projection per call and the dead r gate (with its LayerNorm) evaluated, as the reference
+    does.  Same values as _cell; used where the oracle stands in for the reference's CPU COST."""
+    u = _ln(_lin(x_t, P, pre + "input_proj"), P, pre + "layernorm_in", cfg)
+    if not cfg.fused_ops:
+        torch.sigmoid(_ln(_lin(u, P, pre + "W_r"), P, pre + "layernorm_r", cfg))      # dead gate, lucyrnn.py:56
+        return _cell(P, pre, cfg, x_t, h_prev, s_prev)
+    r, z, k, v, h_pre, dl = _lin(u, P, pre + "W_fused").chunk(6, dim=-1)
+    torch.sigmoid(_ln(r, P, pre + "layernorm_r", cfg))                                  # dead gate, lucyrnn.py:50
+    z = torch.sigmoid(_ln(z, P, pre + "layernorm_z", cfg))
+    s = torch.sigmoid(dl) * s_prev + k * v
+    c = torch.tanh(_ln(h_pre + s, P, pre + "layernorm_h", cfg))
+    return (1 - z) * c + z * h_prev, s
+
+
+def forward_looped_as_timed(P, cfg, x, state=None):
+    """forward_looped with the reference's memory behaviour too: per-step selects ``t[:, i, :]`` and
+    the in-place ``layer_output[:, t, :] = h`` of lucyrnn.py:153-166, whose backward zero-fills a full
+    (B,T,H) tensor per timestep.  This is the strategy bench.py times as the CPU
+    baseline when the reference tree itself is not mounted (kind "port")."""
+    if cfg.decay_mode != "learned" or not cfg.is_training:
+        return forward_looped(P, cfg, x, state)
+    x = _stack_frames(x, cfg)
+    B, T, _ = x.shape
+    h, s = _init_state(cfg, B, x.dtype, state)
+    inp = x.clone()                                                  # lucyrnn.py:110
+    for l in range(cfg.num_layers):
+        pre = f"layers.{l}."
+        u = _ln(_lin(inp, P, pre + "input_proj"), P, pre + "layernorm_in", cfg)
+        if cfg.fused_ops:
+            _, _, k, v, _, dl = _lin(u, P, pre + "W_fused").chunk(6, dim=-1)
+        else:
+            k, v, dl = _lin(u, P, pre + "W_k"), _lin(u, P, pre + "W_v"), _lin(u, P, pre + "W_decay")
+        kv, d = k * v, torch.sigmoid(dl)
+        run = torch.zeros(B, cfg.hidden_dim, dtype=x.dtype)
+        steps = []
+        for t in range(T):                                           # lucyrnn.py:153-158
+            run = d[:, t, :] * run + kv[:, t, :]
+            steps.append(run.unsqueeze(1))
+        S_all = torch.cat(steps, dim=1)
+        out = torch.zeros(B, T, cfg.hidden_dim, dtype=x.dtype)
+        for t in range(T):                                           # lucyrnn.py:160-166
+            h[l], _ = _cell_as_timed(P, pre, cfg, inp[:, t, :], h[l], S_all[:, t, :])
+            out[:, t, :] = h[l]
+        inp = out
+    return _lin(inp, P, "output_proj"), (h, s)
+
+
 # --------------------------------------------------------------------------- #
 # strategy 2: closed form (Appendix A) — the spec of the CUDA path
 # --------------------------------------------------------------------------- #

@@ -43,11 +43,12 @@ SIGNATURES = {
     "sc_lucy_sscan_bwd": [P, P, P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I64, I32, I32, I32, F32, P],
     "sc_lucy_hscan_fwd": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I32, P],
     "sc_lucy_hscan_bwd": [P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I64, I64, I64, I32, P],
-    "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, I32, P],
+    "sc_ctc_workspace_bytes": [I64, I64, I64],
+    "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, I32, P, P],
     "sc_ctc_emissions": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P],
-    "sc_ctc_lattice": [P, P, P, I64, P, P, I64, I64, I64, I64, P, P, P, P, I32, P],
+    "sc_ctc_lattice": [P, P, P, I64, P, P, I64, I64, I64, I64, P, P, P, P, I32, P, P],
     "sc_ctc_bwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, I32,
-                   P, I64, I64, I32, P],
+                   P, I64, I64, I32, P, P],
     "sc_rnnt_fwd": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P],
     "sc_rnnt_bwd": [P, I64, P, P, I64, I64, I64, I64, I64, P, I64, P, P, P, P, P, P, P, P],
     "sc_joint_fwd": [P, I64, I64, P, I64, I64, P, I64, I64, I64, I64, I32, P],
@@ -71,6 +72,7 @@ SIGNATURES = {
     "sc_frame_mask": [P, I64, I64, I64, I64, I64, F32, I64, P, P, P],
 }
 _RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64,
+             "sc_ctc_workspace_bytes": I64,
              "sc_frontend_tables_len": I64}
 
 _lib = None
@@ -167,7 +169,7 @@ KERNELS_PER_CALL = {
     "sc_gemm_fwd": 1, "sc_gemm_dgrad": 1, "sc_gemm_wgrad": 1, "sc_cast": 1, "sc_colsum": 2,
     "sc_layernorm_fwd": 1, "sc_layernorm_bwd": 1, "sc_lucy_scan_fwd": 1, "sc_lucy_scan_fwd_chunked": 3, "sc_lucy_scan_bwd": 1,
     "sc_lucy_sscan_fwd": 1, "sc_lucy_sscan_bwd": 1, "sc_lucy_hscan_fwd": 1, "sc_lucy_hscan_bwd": 1,
-    "sc_ctc_fwd": 3, "sc_ctc_emissions": 1, "sc_ctc_lattice": 2, "sc_ctc_bwd": 1, "sc_rnnt_fwd": 2, "sc_rnnt_bwd": 2, "sc_split_bf16": 1, "sc_joint_fwd": 1, "sc_joint_bwd": 2, "sc_rnnt_lse_gather": 1, "sc_rnnt_lattice": 1,
+    "sc_ctc_fwd": 5, "sc_ctc_emissions": 1, "sc_ctc_lattice": 4, "sc_ctc_bwd": 1, "sc_rnnt_fwd": 2, "sc_rnnt_bwd": 2, "sc_split_bf16": 1, "sc_joint_fwd": 1, "sc_joint_bwd": 2, "sc_rnnt_lse_gather": 1, "sc_rnnt_lattice": 1,
     "sc_rnnt_node_grads": 1, "sc_rnnt_dlogits": 1, "sc_ctc_greedy_decode": 2, "sc_frontend": 1, "sc_frame_mask": 1,
 }
 _ESZ = {SC_F32: 4, SC_BF16: 2}

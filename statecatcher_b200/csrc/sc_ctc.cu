@@ -32,7 +32,6 @@
 // kernel at 40 warps per SM — bytes in flight are not what holds pass 1 at ~2.9 TB/s; not kept.
 // Algorithmic HBM bytes per frame: 3*V*e + 8*(2U+1)  (SURVEY.md 8d).
 #include "sc_common.cuh"
-#include "sc_ctc_lin_math.h"
 #include "sc_tma.cuh"
 #include <stdlib.h>
 
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32, 5)
 ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t stride_t,
                       const int64_t* __restrict__ targets, int64_t ldt,
                       const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                      int B, int Tn, int V, int Smax, int64_t blank,
+                      int B, int Tn, int V, int Umax, int Smax, int64_t blank,
                       float* __restrict__ lse, float* __restrict__ lplat, float* __restrict__ cshift) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned nrows = (unsigned)B * (unsigned)Tn;           // B*T < 2^31 (checked by the host)
@@ -75,12 +74,16 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
     const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
     int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
     if (t >= Tb) continue;
+    const int64_t U64 = tgt_lens[b];
+    if (U64 < 0 || U64 > Umax) continue;                         // invalid length (torch raises on the host; lengths here may be device tensors): the lattice pass reports the utterance infeasible
     const T* x = logits + b * stride_b + t * stride_t;
     const float l = warp_row_lse<T>(x, V, lane);
     if (lane == 0) lse[row] = l;
-    const int S = 2 * (int)tgt_lens[b] + 1;
+    const int S = 2 * (int)U64 + 1;
     const int64_t* tg = targets + (int64_t)b * ldt;
     float* out = lplat + (int64_t)row * Smax;
+    // a label outside [0, V) is probability zero (-inf emission): the utterance comes out infeasible
+    auto emis = [&](int64_t lab) -> float { return (lab >= 0 && lab < V) ? (ld_f(x + lab) - l) * 1.4426950408889634f : NEG_INF; };
     // emissions in log2 units (the recursion runs on ex2/lg2 directly), shifted so that the
     // frame's largest lattice emission is 0: the recursion's values then drift by the gap between
     // the paths and the frame-wise best node (~2 per frame on random logits, ~0 on a trained
@@ -95,8 +98,8 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
 #pragma unroll
       for (int k = 0; k < NL; ++k) {
         const int s = lane + 32 * k;
-        const int lab = (s < S) ? ((s & 1) ? (int)tg[s >> 1] : (int)blank) : (int)blank;
-        e[k] = (ld_f(x + lab) - l) * 1.4426950408889634f;
+        const int64_t lab = (s < S && (s & 1)) ? tg[s >> 1] : blank;
+        e[k] = emis(lab);
         if (s < S) c = fmaxf(c, e[k]);
       }
       c = warp_max(c);
@@ -106,7 +109,7 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t st
         if (lane + 32 * k < S) out[lane + 32 * k] = fmaxf(e[k] - c, -1e30f);   // -inf logits become the recursion's finite dead value
     } else {
       for (int s = lane; s < S; s += 32) {
-        const float e = (ld_f(x + ext_label(tg, s, blank)) - l) * 1.4426950408889634f;
+        const float e = emis(ext_label(tg, s, blank));
         out[s] = e;
         c = fmaxf(c, e);
       }
@@ -158,7 +161,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat, const flo
                                       const int64_t* __restrict__ targets, int64_t ldt,
                                       const int64_t* __restrict__ in_lens,
                                       const int64_t* __restrict__ tgt_lens,
-                                      int Tn, int Smax, int64_t blank,
+                                      int Tn, int Umax, int Smax, int64_t blank,
                                       float* __restrict__ alpha, float* __restrict__ beta,
                                       float* __restrict__ nll) {
   extern __shared__ __align__(128) float sm[];   // 2 lines of (Smax + 4) floats (2 pad cells either side) + emission blocks
@@ -168,12 +171,14 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat, const flo
   const int b = blockIdx.x, dir = blockIdx.y;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
-  const int U = (int)tgt_lens[b];
+  const int64_t U64 = tgt_lens[b];
+  const bool bad_len = U64 < 0 || U64 > Umax;
+  const int U = bad_len ? 0 : (int)U64;
   const int S = 2 * U + 1;
   const int64_t* tg = targets + (int64_t)b * ldt;
   const int LINE = Smax + 4;
-  if (Tb <= 0) {
-    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
+  if (Tb <= 0 || bad_len) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0 && !bad_len) ? 0.f : INFINITY;
     return;
   }
   const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
@@ -324,152 +329,9 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ lplat, const flo
   }
 }
 
-// ---- pass 2, LINEAR-domain variant with a per-node exponent (SC_CTC_WAVE=3; EXPERIMENTAL, opt-in) -------
-// alpha[s] = m * 2^e with an fp32 mantissa m in [0.5, 1) and an int exponent e per node.  The step is
-//   emax = max(e_a, e_b, e_c);  sum = m_a 2^(e_a-emax) + m_b 2^(e_b-emax) + m_c 2^(e_c-emax);  v = sum * p
-// followed by an exponent extraction on the bits of v: integer ops, two FADD and one FMUL where the log-domain
-// step has min/max -> ex2 x2 -> lg2 (three MUFU round trips).  lg2 is taken only for the values that are
-// STORED (same alpha / beta format as the other kernels, each row relative to an exponent the block agrees on
-// once per emission block), never for what the next step reads.  A column scaled by one common factor loses the
-// nodes 2^-125 below its maximum (rejected earlier, see below); the per-node exponent keeps them.  Accuracy was
-// settled on the CPU before this was written (profiles/ctc_linear_exp_study.py: occupancies within 4e-6 /
-// 1.3e-5 of fp64 at T=3000, U=150 with the mantissa renormalised every step, as here).  Same block structure
-// as ctc_alpha_beta_kernel's fast path (one node per thread, previous column in shared memory, one barrier per
-// step).  Written after round 1's GPU budget was spent: compiles, has never run.
-__global__ void ctc_alpha_beta_lin_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
-                                          const int64_t* __restrict__ targets, int64_t ldt,
-                                          const int64_t* __restrict__ in_lens,
-                                          const int64_t* __restrict__ tgt_lens,
-                                          int Tn, int Smax, int64_t blank,
-                                          float* __restrict__ alpha, float* __restrict__ beta,
-                                          float* __restrict__ nll) {
-  extern __shared__ __align__(128) float sm[];   // 2 mantissa lines + 2 exponent lines of (Smax + 4) cells, then 2 emission blocks
-  __shared__ int ired[32];
-  __shared__ double dred[32];
-  __shared__ __align__(8) uint64_t ebar[2];
-  const int b = blockIdx.x, dir = blockIdx.y;
-  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
-  const int Tb = (int)Tb64;
-  const int U = (int)tgt_lens[b];
-  const int S = 2 * U + 1;
-  const int64_t* tg = targets + (int64_t)b * ldt;
-  const int LINE = Smax + 4;
-  if (Tb <= 0) {
-    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
-    return;
-  }
-  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
-  int* ism = reinterpret_cast<int*>(sm + 2 * LINE);
-  for (int i = threadIdx.x; i < 2 * LINE; i += blockDim.x) { sm[i] = 0.f; ism[i] = CTC_E_DEAD; }
-  if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&ebar[0]), 1);
-    mbar_init(smem_u32(&ebar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  float* pm = sm + 2;            float* cm = sm + LINE + 2;            // previous / current mantissas
-  int* pe = ism + 2;             int* ce = ism + LINE + 2;             // previous / current exponents
-  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
-  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
-  const int t_first = dir == 0 ? 0 : Tb - 1;
-  const int step = dir == 0 ? 1 : -1;
-  const int nb = dir == 0 ? -1 : 1;
-  const int s = threadIdx.x;
-  const bool has = s < S;
-  bool skip = false;
-  if (has && (s & 1)) skip = dir == 0 ? (s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1]) : (s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1]);
-  auto block_max_i = [&](int m) -> int {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = m;
-    __syncthreads();
-    int r = CTC_E_DEAD;
-    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) r = max(r, ired[w]);
-    return r;
-  };
-  // emission in log2 units (<= 0 after the per-frame shift) -> integer part for the exponent, 2^fraction in [1, 2)
-  auto split_emission = [](float e, float& pf, int& ei) {
-    if (!(e > -1.0e6f)) { pf = 0.f; ei = 0; return; }           // masked vocabulary entry: probability zero
-    const float fl = floorf(e);
-    pf = ex2f(e - fl);
-    ei = (int)fl;
-  };
-  float* ebuf = reinterpret_cast<float*>(ism + 2 * LINE);      // 2 buffers of CTC_EB rows x Smax
-  const int nvis = (Tb + CTC_EB - 1) / CTC_EB;
-  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
-  auto rows_of = [&](int blk) { const int r = Tb - blk * CTC_EB; return r < CTC_EB ? r : CTC_EB; };
-  auto issue = [&](int vi) {
-    const int blk = blk_of(vi);
-    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
-    const uint32_t bar = smem_u32(&ebar[vi & 1]);
-    mbar_expect_tx(bar, bytes);
-    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * CTC_EB * Smax), lp_b + (int64_t)blk * CTC_EB * Smax, bytes, bar);
-  };
-  if (threadIdx.x == 0) {
-    issue(0);
-    if (nvis > 1) issue(1);
-  }
-  const int sidx = has ? s : 0;
-  const int64_t stride = (int64_t)step * Smax;
-  float* op = out_b + (int64_t)t_first * Smax + sidx;
-  int eref = 0;                                                  // exponent the stored rows of this visit are relative to
-  for (int vi = 0; vi < nvis; ++vi) {
-    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
-    const int rows = rows_of(blk_of(vi));
-    const float* ep = ebuf + ((size_t)(vi & 1) * CTC_EB + (dir == 0 ? 0 : rows - 1)) * Smax + sidx;
-    const int estride = dir == 0 ? Smax : -Smax;
-    int pos = 0;
-    if (vi == 0) {                                               // init column (step 0)
-      float m0 = 0.f; int e0 = CTC_E_DEAD; bool live = false;
-      if (has && (dir == 0 ? s < 2 : s >= S - 2)) {
-        float pf; int ei;
-        split_emission(*ep, pf, ei);
-        ctc_lin_renorm(pf, ei, m0, e0);
-        live = true;
-      }
-      if (has) {
-        pm[s] = m0; pe[s] = e0;
-        *op = dir == 0 ? (m0 > 0.f ? lg2f(m0) + (float)e0 : NEG_INF) : (live ? 0.f : NEG_INF);
-      }
-      __syncthreads();
-      ep += estride;
-      pos = 1;
-    } else {
-      // stored rows are relative to the largest live exponent at the start of their emission block
-      const int m = block_max_i(has ? pe[s] : CTC_E_DEAD);
-      if (m > CTC_E_DEAD) eref = m;
-      __syncthreads();
-    }
-    for (; pos < rows; ++pos) {
-      float pf; int ei;
-      split_emission(*ep, pf, ei);
-      ep += estride;
-      op += stride;
-      if (has) {
-        const float ma = pm[s], mb = pm[s + nb];
-        const int ea = pe[s], eb2 = pe[s + nb];
-        float mc = 0.f; int ec = CTC_E_DEAD;
-        if (skip) { mc = pm[s + 2 * nb]; ec = pe[s + 2 * nb]; }
-        float mn, sum; int en, emax;
-        ctc_lin_step(ma, ea, mb, eb2, mc, ec, pf, ei, mn, en, sum, emax);
-        cm[s] = mn; ce[s] = en;
-        if (dir == 0) *op = mn > 0.f ? lg2f(mn) + (float)(en - eref) : NEG_INF;
-        else          *op = sum > 0.f ? lg2f(sum) + (float)(emax - eref) : NEG_INF;   // beta leaves without its frame's emission
-      }
-      __syncthreads();
-      float* tm = pm; pm = cm; cm = tm;
-      int* te = pe; pe = ce; ce = te;
-    }
-    if (threadIdx.x == 0 && vi + 2 < nvis) issue(vi + 2);
-  }
-  if (dir == 0 && threadIdx.x == 0) {
-    const float m1 = pm[S - 1], m2 = S > 1 ? pm[S - 2] : 0.f;
-    const int e1 = pe[S - 1], e2 = S > 1 ? pe[S - 2] : CTC_E_DEAD;
-    const int emax = max(e1, e2);
-    const float v = ctc_lin_scale_pow2(m1, e1 - emax) + ctc_lin_scale_pow2(m2, e2 - emax);
-    nll[b] = (v > 0.f) ? (float)(-(shift_sum + (double)emax + log2((double)v)) * (double)LN2) : INFINITY;
-  }
-}
+}  // namespace sc
+#include "sc_ctc_lin64.cuh"
+namespace sc {
 
 // ---- pass 2, wavefront variant (lattices up to 1024 nodes) ---------------------------------
 // Same recursion, no block barrier per timestep.  Node values live in REGISTERS (thread i owns
@@ -521,145 +383,6 @@ __device__ __forceinline__ float slot_poll(uint32_t addr, int tag) {
   return __uint_as_float(v);
 }
 
-template <int dir>
-__device__ __forceinline__ void
-ctc_wave_body(float* __restrict__ sm, const float* __restrict__ lplat, const float* __restrict__ cshift,
-              const int64_t* __restrict__ targets, int64_t ldt,
-              const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-              int Tn, int Smax, int EB, int64_t blank,
-              float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
-  __shared__ float red[2][32];
-  __shared__ double dred[32];
-  __shared__ float fin[2];
-  __shared__ __align__(8) uint64_t ebar[2];
-  const int b = blockIdx.x;
-  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
-  const int Tb = (int)Tb64;
-  const int U = (int)tgt_lens[b];
-  const int S = 2 * U + 1;
-  const int64_t* tg = targets + (int64_t)b * ldt;
-  if (Tb <= 0) {
-    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
-    return;
-  }
-  const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
-  const int nwarps = (int)(blockDim.x >> 5);
-  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
-  float* ebuf = sm;
-  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * Smax);   // [nwarps][EB+1] x {value, tag}
-  for (int k = i; k < nwarps * (EB + 1) * 2; k += blockDim.x) slots[k] = -1;
-  if (i == 0) {
-    fin[0] = CTC_DEAD; fin[1] = CTC_DEAD;
-    mbar_init(smem_u32(&ebar[0]), 1);
-    mbar_init(smem_u32(&ebar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const bool has = i < S;
-  const int s = dir == 0 ? i : S - 1 - i;                        // this thread's lattice node
-  const int sidx = has ? s : 0;
-  // skip transition (from two nodes away) is a per-node constant; lane 0 of every warp sits on
-  // a blank (even node), so it never takes one and only lane 31's value has to cross warps
-  bool skip = false;
-  if (has && (s & 1)) {
-    if (dir == 0) skip = s >= 2 && tg[s >> 1] != tg[(s >> 1) - 1];
-    else skip = s + 2 < S && tg[s >> 1] != tg[(s >> 1) + 1];
-  }
-  const bool producer = lane == 31 && warp + 1 < nwarps;
-  const bool lane0 = lane == 0, lane1 = lane == 1;
-  const uint32_t my_slot = smem_u32(slots) + (uint32_t)(warp * (EB + 1) * 8);
-  const uint32_t in_slot = smem_u32(slots) + (uint32_t)((warp > 0 ? warp - 1 : 0) * (EB + 1) * 8);
-  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
-  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
-  const int nvis = (Tb + EB - 1) / EB;
-  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
-  auto rows_of = [&](int blk) { const int r = Tb - blk * EB; return r < EB ? r : EB; };
-  auto issue = [&](int vi) {
-    const int blk = blk_of(vi);
-    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
-    const uint32_t bar = smem_u32(&ebar[vi & 1]);
-    mbar_expect_tx(bar, bytes);
-    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * Smax), lp_b + (int64_t)blk * EB * Smax, bytes, bar);
-  };
-  if (i == 0) {
-    issue(0);
-    if (nvis > 1) issue(1);
-  }
-  const int t_first = dir == 0 ? 0 : Tb - 1;
-  const int64_t stride = dir == 0 ? (int64_t)Smax : -(int64_t)Smax;
-  const int estride = dir == 0 ? Smax : -Smax;
-  float* op = out_b + (int64_t)t_first * Smax + sidx;
-  double csum = 0.0;
-  float p0 = CTC_DEAD;                                           // this node's value after the last step
-  int g = 0;                                                     // steps done so far (= tag of the next step)
-  for (int vi = 0; vi < nvis; ++vi) {
-    int pos = 0;
-    if (vi > 0) {
-      // block meeting: re-centre the column, recycle slots and the emission buffer of visit vi-1
-      float m = warp_max(has ? p0 : CTC_DEAD);
-      if (lane == 0) red[vi & 1][warp] = m;
-      __syncthreads();
-      m = CTC_DEAD;
-      for (int w = 0; w < nwarps; ++w) m = fmaxf(m, red[vi & 1][w]);
-      if (m > CTC_DEAD_TEST) { p0 = fmaxf(p0 - m, CTC_DEAD); csum += (double)m; }   // rows already written keep their own offset
-      if (i == 0 && vi + 1 < nvis) issue(vi + 1);
-      if (producer) slot_publish(my_slot, p0, g - 1);            // carry-in of this visit, re-centred
-    }
-    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
-    const int rows = rows_of(blk_of(vi));
-    const float* ep = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * Smax + sidx;
-    if (vi == 0) {                                               // first column
-      float v = CTC_DEAD, pre = CTC_DEAD;
-      if (has && i < 2) { v = *ep; pre = 0.f; }
-      if (has) *op = dir == 0 ? v : pre;
-      p0 = v;
-      if (producer) slot_publish(my_slot + 8, v, 0);
-      ep += estride;
-      pos = 1;
-      g = 1;
-    }
-    uint32_t rd = in_slot + (uint32_t)(pos * 8);                 // slot with the neighbour warp's previous step
-    uint32_t wr = my_slot + (uint32_t)((pos + 1) * 8);
-#pragma unroll 2
-    for (; pos < rows; ++pos) {
-      const float e = *ep;                                       // consumed last in the step: its latency hides behind the chain
-      ep += estride;
-      op += stride;
-      float a1 = __shfl_up_sync(0xffffffffu, p0, 1);
-      float a2 = __shfl_up_sync(0xffffffffu, p0, 2);
-      float x = CTC_DEAD;
-      if (warp > 0) x = slot_poll(rd, g - 1);
-      a1 = lane0 ? x : a1;
-      a2 = lane1 ? x : a2;
-      const float pre = lse3w(p0, a1, skip ? a2 : CTC_DEAD);
-      const float v = pre + e;
-      if (has) *op = dir == 0 ? v : pre;                         // beta leaves without its frame's emission
-      p0 = v;
-      if (producer) slot_publish(wr, v, g);
-      ++g; rd += 8; wr += 8;
-    }
-  }
-  if (dir == 0) {
-    if (has && i >= S - 2) fin[S - 1 - i] = p0;
-    __syncthreads();
-    if (i == 0) {
-      const float ll2 = lse3w(fin[0], fin[1], CTC_DEAD);
-      nll[b] = (ll2 < CTC_DEAD_TEST) ? INFINITY : (float)(-(csum + shift_sum + (double)ll2) * (double)LN2);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(1024, 1)
-ctc_alpha_beta_wave_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
-                           const int64_t* __restrict__ targets, int64_t ldt,
-                           const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                           int Tn, int Smax, int EB, int64_t blank,
-                           float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
-  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB x Smax floats, then nwarps x (EB+1) 8-byte slots
-  if (blockIdx.y == 0) ctc_wave_body<0>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
-  else ctc_wave_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
-}
-
 // ---- pass 2, wavefront variant with a (blank, label) PAIR per thread --------------------------
 // Thread i owns blank node 2i and label node 2i+1 (alpha; mirrored node numbering for beta).
 // The label looks at its own blank (same thread), so ONE shuffle per step — the previous thread's
@@ -671,12 +394,15 @@ __device__ __forceinline__ float lse2w(float a, float b) {
   return m + lg2f(1.f + ex2f(lo - m));
 }
 
-template <int dir>
+// FMT 0: emission rows of 2U+1 log2 values (pitch = Smax); FMT 1: the linear-domain words of sc_ctc_lin64.cuh
+// (pitch LP; [0] blank, [1+u] label u) — in that format the kernel only recomputes the utterances the fp64
+// recursion flagged (lossy[b] != 0) and leaves at once for the others.
+template <int dir, int FMT>
 __device__ __forceinline__ void
 ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const float* __restrict__ cshift,
                const int64_t* __restrict__ targets, int64_t ldt,
                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-               int Tn, int Smax, int EB, int64_t blank,
+               int Tn, int Umax, int Smax, int LP, int EB, const int* __restrict__ lossy,
                float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
   __shared__ float red[2][32];
   __shared__ double dred[32];
@@ -685,17 +411,21 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   const int b = blockIdx.x;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
-  const int U = (int)tgt_lens[b];
+  if (FMT == 1 && !lossy[b]) return;                             // the fp64 recursion's result stands
+  const int64_t U64 = tgt_lens[b];
+  const bool bad_len = U64 < 0 || U64 > Umax;
+  const int U = bad_len ? 0 : (int)U64;
   const int64_t* tg = targets + (int64_t)b * ldt;
-  if (Tb <= 0) {
-    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
+  if (Tb <= 0 || bad_len) {
+    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0 && !bad_len) ? 0.f : INFINITY;
     return;
   }
   const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
   const int nwarps = (int)(blockDim.x >> 5);
   const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
   float* ebuf = sm;
-  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * Smax);   // [nwarps][EB+1] x {value, tag}
+  const int EP = FMT == 1 ? LP : Smax;                           // pitch of an emission row
+  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * EP);     // [nwarps][EB+1] x {value, tag}
   for (int k = i; k < nwarps * (EB + 1) * 2; k += blockDim.x) slots[k] = -1;
   if (i == 0) {
     fin[0] = CTC_DEAD; fin[1] = CTC_DEAD;
@@ -717,17 +447,21 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   const bool lane0 = lane == 0;
   const uint32_t my_slot = smem_u32(slots) + (uint32_t)(warp * (EB + 1) * 8);
   const uint32_t in_slot = smem_u32(slots) + (uint32_t)((warp > 0 ? warp - 1 : 0) * (EB + 1) * 8);
-  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
+  // where the pair's emissions sit in a row, and how a stored word becomes a log2 value
+  const int eb_pos = FMT == 1 ? 0 : sb;
+  const int el_pos = FMT == 1 ? (hasl ? (dir == 0 ? 1 + i : U - i) : 0) : sl;
+  auto ld_e = [](const float* q) -> float { return FMT == 1 ? lin_word_to_log2(__float_as_uint(*q)) : *q; };
+  const float* lp_b = lplat + (int64_t)b * Tn * EP;
   float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
   const int nvis = (Tb + EB - 1) / EB;
   auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
   auto rows_of = [&](int blk) { const int r = Tb - blk * EB; return r < EB ? r : EB; };
   auto issue = [&](int vi) {
     const int blk = blk_of(vi);
-    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)EP * 4u;
     const uint32_t bar = smem_u32(&ebar[vi & 1]);
     mbar_expect_tx(bar, bytes);
-    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * Smax), lp_b + (int64_t)blk * EB * Smax, bytes, bar);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * EP), lp_b + (int64_t)blk * EB * EP, bytes, bar);
   };
   if (i == 0) {
     issue(0);
@@ -735,7 +469,7 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   }
   const int t_first = dir == 0 ? 0 : Tb - 1;
   const int64_t stride = dir == 0 ? (int64_t)Smax : -(int64_t)Smax;
-  const int estride = dir == 0 ? Smax : -Smax;
+  const int estride = dir == 0 ? EP : -EP;
   float* opb = out_b + (int64_t)t_first * Smax + sb;
   float* opl = out_b + (int64_t)t_first * Smax + sl;
   double csum = 0.0;
@@ -755,11 +489,11 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
     }
     mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
     const int rows = rows_of(blk_of(vi));
-    const float* erow = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * Smax;
-    const float* epb = erow + sb;
-    const float* epl = erow + sl;
+    const float* erow = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * EP;
+    const float* epb = erow + eb_pos;
+    const float* epl = erow + el_pos;
     if (vi == 0) {                                               // first column: nodes 0 and 1 of the scan order
-      if (i == 0) { pb = *epb; pl = hasl ? *epl : CTC_DEAD; }
+      if (i == 0) { pb = ld_e(epb); pl = hasl ? ld_e(epl) : CTC_DEAD; }
       if (hasb) *opb = dir == 0 ? pb : (i == 0 ? 0.f : CTC_DEAD);
       if (hasl) *opl = dir == 0 ? pl : (i == 0 ? 0.f : CTC_DEAD);
       if (producer) slot_publish(my_slot + 8, pl, 0);
@@ -771,8 +505,8 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
     uint32_t wr = my_slot + (uint32_t)((pos + 1) * 8);
 #pragma unroll 2
     for (; pos < rows; ++pos) {
-      const float eb = *epb;
-      const float el = hasl ? *epl : CTC_DEAD;                   // a missing label node stays dead
+      const float eb = ld_e(epb);
+      const float el = hasl ? ld_e(epl) : CTC_DEAD;              // a missing label node stays dead
       epb += estride; epl += estride;
       opb += stride; opl += stride;
       float xl = __shfl_up_sync(0xffffffffu, pl, 1);
@@ -800,211 +534,16 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   }
 }
 
-// ---- pass 2, pair-per-thread wavefront with the LINEAR-domain step (SC_CTC_WAVE=4; EXPERIMENTAL, opt-in) ----
-// ctc_wave2_body with the node value as (mantissa, exponent) (sc_ctc_lin_math.h) instead of a log2 number: same
-// thread/node assignment, same neighbour-only handoff, slots widened to 16 bytes {mantissa, exponent, step tag, -}.
-// Nothing is re-centred at the block meetings (exponents are exact integers); the meeting only agrees on the
-// exponent the stored rows of the next emission block are relative to.  Written after round 1's GPU budget was
-// spent: compiles, has never run.
-__device__ __forceinline__ void slot_publish4(uint32_t addr, float m, int e, int tag) {
-  asm volatile("st.volatile.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-               :: "r"(addr), "r"(__float_as_uint(m)), "r"(e), "r"(tag), "r"(0));
-}
-__device__ __forceinline__ void slot_poll4(uint32_t addr, int tag, float& m, int& e) {
-  uint32_t vm; int ve;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b32 t, n, z;\n"
-      "ld.volatile.shared.v4.b32 {%0, %1, t, z}, [%2];\n"
-      "setp.eq.s32 p, t, %3;\n"
-      "@p bra.uni SC_SLOT4_DONE;\n"
-      "mov.b32 n, 0;\n"
-      "SC_SLOT4_SPIN:\n"
-      "ld.volatile.shared.v4.b32 {%0, %1, t, z}, [%2];\n"
-      "setp.eq.s32 p, t, %3;\n"
-      "@p bra.uni SC_SLOT4_DONE;\n"
-      "add.s32 n, n, 1;\n"
-      "setp.lt.s32 p, n, 0x2000000;\n"
-      "@p bra.uni SC_SLOT4_SPIN;\n"
-      "trap;\n"
-      "SC_SLOT4_DONE:\n"
-      "}\n"
-      : "=r"(vm), "=r"(ve) : "r"(addr), "r"(tag));
-  m = __uint_as_float(vm);
-  e = ve;
-}
-// emission in log2 units (<= 0 after the per-frame shift) -> integer part for the exponent, 2^fraction in [1, 2);
-// anything below -1e6 (masked vocabulary entry, missing node) is probability zero
-__device__ __forceinline__ void ctc_lin_split(float e, float& pf, int& ei) {
-  if (!(e > -1.0e6f)) { pf = 0.f; ei = 0; return; }
-  const float fl = floorf(e);
-  pf = ex2f(e - fl);
-  ei = (int)fl;
-}
-
-template <int dir>
-__device__ __forceinline__ void
-ctc_wave2_lin_body(float* __restrict__ sm, const float* __restrict__ lplat, const float* __restrict__ cshift,
-                   const int64_t* __restrict__ targets, int64_t ldt,
-                   const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                   int Tn, int Smax, int EB, int64_t blank,
-                   float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
-  __shared__ int ired[2][32];
-  __shared__ double dred[32];
-  __shared__ float finm[2];
-  __shared__ int fine[2];
-  __shared__ __align__(8) uint64_t ebar[2];
-  const int b = blockIdx.x;
-  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
-  const int Tb = (int)Tb64;
-  const int U = (int)tgt_lens[b];
-  const int64_t* tg = targets + (int64_t)b * ldt;
-  if (Tb <= 0) {
-    if (dir == 0 && threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
-    return;
-  }
-  const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
-  const int nwarps = (int)(blockDim.x >> 5);
-  const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
-  float* ebuf = sm;
-  int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * Smax);   // [nwarps][EB+1] x {mantissa, exponent, tag, -}
-  for (int k = i; k < nwarps * (EB + 1) * 4; k += blockDim.x) slots[k] = -1;
-  if (i == 0) {
-    finm[0] = 0.f; finm[1] = 0.f; fine[0] = CTC_E_DEAD; fine[1] = CTC_E_DEAD;
-    mbar_init(smem_u32(&ebar[0]), 1);
-    mbar_init(smem_u32(&ebar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const bool hasb = i <= U, hasl = i < U;
-  const int sb = hasb ? (dir == 0 ? 2 * i : 2 * U - 2 * i) : 0;
-  const int sl = hasl ? (dir == 0 ? 2 * i + 1 : 2 * U - 2 * i - 1) : 0;
-  bool skip = false;
-  if (hasl) {
-    if (dir == 0) skip = i >= 1 && tg[i] != tg[i - 1];
-    else { const int u = U - 1 - i; skip = u + 1 < U && tg[u] != tg[u + 1]; }
-  }
-  const bool producer = lane == 31 && warp + 1 < nwarps;
-  const bool lane0 = lane == 0;
-  const uint32_t my_slot = smem_u32(slots) + (uint32_t)(warp * (EB + 1) * 16);
-  const uint32_t in_slot = smem_u32(slots) + (uint32_t)((warp > 0 ? warp - 1 : 0) * (EB + 1) * 16);
-  const float* lp_b = lplat + (int64_t)b * Tn * Smax;
-  float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
-  const int nvis = (Tb + EB - 1) / EB;
-  auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
-  auto rows_of = [&](int blk) { const int r = Tb - blk * EB; return r < EB ? r : EB; };
-  auto issue = [&](int vi) {
-    const int blk = blk_of(vi);
-    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)Smax * 4u;
-    const uint32_t bar = smem_u32(&ebar[vi & 1]);
-    mbar_expect_tx(bar, bytes);
-    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * EB * Smax), lp_b + (int64_t)blk * EB * Smax, bytes, bar);
-  };
-  if (i == 0) {
-    issue(0);
-    if (nvis > 1) issue(1);
-  }
-  const int t_first = dir == 0 ? 0 : Tb - 1;
-  const int64_t stride = dir == 0 ? (int64_t)Smax : -(int64_t)Smax;
-  const int estride = dir == 0 ? Smax : -Smax;
-  float* opb = out_b + (int64_t)t_first * Smax + sb;
-  float* opl = out_b + (int64_t)t_first * Smax + sl;
-  float mb = 0.f, ml = 0.f;                                      // the pair after the last step: mantissas ...
-  int eb_ = CTC_E_DEAD, el_ = CTC_E_DEAD;                        // ... and exponents
-  int eref = 0;                                                  // what the stored rows of this visit are relative to
-  int g = 0;
-  for (int vi = 0; vi < nvis; ++vi) {
-    int pos = 0;
-    if (vi > 0) {
-      int m = hasb ? max(eb_, el_) : CTC_E_DEAD;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) ired[vi & 1][warp] = m;
-      __syncthreads();
-      m = CTC_E_DEAD;
-      for (int w = 0; w < nwarps; ++w) m = max(m, ired[vi & 1][w]);
-      if (m > CTC_E_DEAD) eref = m;
-      if (i == 0 && vi + 1 < nvis) issue(vi + 1);
-      if (producer) slot_publish4(my_slot, ml, el_, g - 1);      // carry-in of this visit
-    }
-    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
-    const int rows = rows_of(blk_of(vi));
-    const float* erow = ebuf + ((size_t)(vi & 1) * EB + (dir == 0 ? 0 : rows - 1)) * Smax;
-    const float* epb = erow + sb;
-    const float* epl = erow + sl;
-    if (vi == 0) {                                               // first column: nodes 0 and 1 of the scan order
-      if (i == 0) {
-        float pf; int ei;
-        ctc_lin_split(*epb, pf, ei);
-        ctc_lin_renorm(pf, ei, mb, eb_);
-        if (hasl) { ctc_lin_split(*epl, pf, ei); ctc_lin_renorm(pf, ei, ml, el_); }
-      }
-      if (hasb) *opb = dir == 0 ? (mb > 0.f ? lg2f(mb) + (float)eb_ : CTC_DEAD) : (i == 0 ? 0.f : CTC_DEAD);
-      if (hasl) *opl = dir == 0 ? (ml > 0.f ? lg2f(ml) + (float)el_ : CTC_DEAD) : (i == 0 ? 0.f : CTC_DEAD);
-      if (producer) slot_publish4(my_slot + 16, ml, el_, 0);
-      epb += estride; epl += estride;
-      pos = 1;
-      g = 1;
-    }
-    uint32_t rd = in_slot + (uint32_t)(pos * 16);
-    uint32_t wr = my_slot + (uint32_t)((pos + 1) * 16);
-#pragma unroll 2
-    for (; pos < rows; ++pos) {
-      float pfb, pfl; int eib, eil;
-      ctc_lin_split(*epb, pfb, eib);
-      ctc_lin_split(hasl ? *epl : NEG_INF, pfl, eil);            // a missing label node stays dead
-      epb += estride; epl += estride;
-      opb += stride; opl += stride;
-      float xm = __shfl_up_sync(0xffffffffu, ml, 1);
-      int xe = __shfl_up_sync(0xffffffffu, el_, 1);
-      float qm = 0.f; int qe = CTC_E_DEAD;
-      if (warp > 0) slot_poll4(rd, g - 1, qm, qe);
-      if (lane0) { xm = qm; xe = qe; }
-      float nmb, nml, sumb, suml; int neb, nel, emaxb, emaxl;
-      ctc_lin_step2(mb, eb_, xm, xe, pfb, eib, nmb, neb, sumb, emaxb);
-      ctc_lin_step(ml, el_, mb, eb_, skip ? xm : 0.f, skip ? xe : CTC_E_DEAD, pfl, eil, nml, nel, suml, emaxl);
-      mb = nmb; eb_ = neb; ml = nml; el_ = nel;
-      if (hasb) *opb = dir == 0 ? (mb > 0.f ? lg2f(mb) + (float)(eb_ - eref) : CTC_DEAD)
-                                : (sumb > 0.f ? lg2f(sumb) + (float)(emaxb - eref) : CTC_DEAD);
-      if (hasl) *opl = dir == 0 ? (ml > 0.f ? lg2f(ml) + (float)(el_ - eref) : CTC_DEAD)
-                                : (suml > 0.f ? lg2f(suml) + (float)(emaxl - eref) : CTC_DEAD);
-      if (producer) slot_publish4(wr, ml, el_, g);
-      ++g; rd += 16; wr += 16;
-    }
-  }
-  if (dir == 0) {
-    if (i == U) { finm[0] = mb; fine[0] = eb_; }
-    if (i == U - 1) { finm[1] = ml; fine[1] = el_; }
-    __syncthreads();
-    if (i == 0) {
-      const int emax = max(fine[0], fine[1]);
-      const float v = ctc_lin_scale_pow2(finm[0], fine[0] - emax) + ctc_lin_scale_pow2(finm[1], fine[1] - emax);
-      nll[b] = (v > 0.f) ? (float)(-(shift_sum + (double)emax + log2((double)v)) * (double)LN2) : INFINITY;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(512, 1)
-ctc_alpha_beta_wave2_lin_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
-                                const int64_t* __restrict__ targets, int64_t ldt,
-                                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                                int Tn, int Smax, int EB, int64_t blank,
-                                float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
-  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB x Smax floats, then nwarps x (EB+1) 16-byte slots
-  if (blockIdx.y == 0) ctc_wave2_lin_body<0>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
-  else ctc_wave2_lin_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
-}
-
+template <int FMT>
 __global__ void __launch_bounds__(512, 1)
 ctc_alpha_beta_wave2_kernel(const float* __restrict__ lplat, const float* __restrict__ cshift,
                             const int64_t* __restrict__ targets, int64_t ldt,
                             const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                            int Tn, int Smax, int EB, int64_t blank,
+                            int Tn, int Umax, int Smax, int LP, int EB, const int* __restrict__ lossy,
                             float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll) {
-  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB x Smax floats, then nwarps x (EB+1) 8-byte slots
-  if (blockIdx.y == 0) ctc_wave2_body<0>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
-  else ctc_wave2_body<1>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Smax, EB, blank, alpha, beta, nll);
+  extern __shared__ __align__(128) float sm[];   // 2 emission blocks of EB rows, then nwarps x (EB+1) 8-byte slots
+  if (blockIdx.y == 0) ctc_wave2_body<0, FMT>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Umax, Smax, LP, EB, lossy, alpha, beta, nll);
+  else ctc_wave2_body<1, FMT>(sm, lplat, cshift, targets, ldt, in_lens, tgt_lens, Tn, Umax, Smax, LP, EB, lossy, alpha, beta, nll);
 }
 
 // loss = reduction over utterances with zero_infinity
@@ -1039,7 +578,7 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
              const float* __restrict__ lse, const float* __restrict__ alpha,
              const float* __restrict__ beta, const float* __restrict__ nll,
              const float* __restrict__ grad_out, int reduction,
-             TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
+             TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t, const int* __restrict__ lossy) {
   const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
   int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
   TO* dx = dlogits + b * dstride_b + t * dstride_t;
@@ -1071,8 +610,9 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
   } else {
     for (int i = lane; i < V; i += 32) r[i] = ex2f(fmaf(ld_f(x + i), LOG2E, -l2));
   }
-  const int U = (int)tgt_lens[b];
+  const int U = (int)tgt_lens[b];                     // valid here: an invalid length left nll = inf above
   const int64_t* tg = targets + (int64_t)b * ldt;
+  const bool lin = lossy != nullptr && !lossy[b];     // rows in the linear-domain format (lossy == nullptr: log-domain launch)
   // pair u <= U exists; its label node only for u < U.  occupancy_s = 2^(alpha+beta)_s / sum_s'
   // (beta carries no emission; per-frame offsets from re-centring cancel in the normalisation)
   const float2* al2 = reinterpret_cast<const float2*>(alpha + (int64_t)row * Smax);
@@ -1080,26 +620,63 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
   float z = 0.f, bsum = 0.f, vmax = CTC_DEAD;
   if (NP > 0) {
     float wb[NP > 0 ? NP : 1], wl[NP > 0 ? NP : 1];
+    bool live;
+    if (lin) {
+      // linear-domain rows (sc_ctc_lin64.cuh): each node is the high word of an fp64 value, alpha at its node
+      // index, beta at the mirrored one.  occupancy ~ alpha*beta: exponent fields add, 20-bit mantissas multiply;
+      // the frame's largest exponent sum is the common scale (per-column scale factors cancel with it).
+      const uint2* aw = reinterpret_cast<const uint2*>(alpha + (int64_t)row * Smax);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(beta + (int64_t)row * Smax);
+      int eb_[NP > 0 ? NP : 1], el_[NP > 0 ? NP : 1];
+      int emax = -1;
+      auto mant = [](uint32_t w) -> float { return __uint_as_float(0x3f800000u | ((w & 0xfffffu) << 3)); };
 #pragma unroll
-    for (int kk = 0; kk < NP; ++kk) {
-      const int u = lane + 32 * kk;
-      wb[kk] = CTC_DEAD; wl[kk] = CTC_DEAD;
-      if (u <= U) {
-        const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
-        wb[kk] = a.x + c.x;
-        if (u < U) wl[kk] = a.y + c.y;
+      for (int kk = 0; kk < NP; ++kk) {
+        const int u = lane + 32 * kk;
+        eb_[kk] = -1; el_[kk] = -1; wb[kk] = 0.f; wl[kk] = 0.f;
+        if (u <= U) {
+          const uint2 a = __ldg(aw + u);
+          const uint32_t cb = __ldg(bw + 2 * (U - u));
+          if (a.x != 0u && cb != 0u) { eb_[kk] = (int)(a.x >> 20) + (int)(cb >> 20); wb[kk] = mant(a.x) * mant(cb); }
+          if (u < U) {
+            const uint32_t cl = __ldg(bw + 2 * (U - u) - 1);
+            if (a.y != 0u && cl != 0u) { el_[kk] = (int)(a.y >> 20) + (int)(cl >> 20); wl[kk] = mant(a.y) * mant(cl); }
+          }
+        }
+        emax = max(emax, max(eb_[kk], el_[kk]));
       }
-      vmax = fmaxf(vmax, fmaxf(wb[kk], wl[kk]));
-    }
-    vmax = warp_max(vmax);
+      emax = __reduce_max_sync(0xffffffffu, emax);
+      auto pow2 = [](int d) -> float { return d < -126 ? 0.f : __uint_as_float((uint32_t)(d + 127) << 23); };   // d <= 0
 #pragma unroll
-    for (int kk = 0; kk < NP; ++kk) {
-      wb[kk] = ex2f(wb[kk] - vmax);
-      wl[kk] = ex2f(wl[kk] - vmax);
-      z += wb[kk] + wl[kk];
+      for (int kk = 0; kk < NP; ++kk) {
+        wb[kk] = eb_[kk] >= 0 ? wb[kk] * pow2(eb_[kk] - emax) : 0.f;
+        wl[kk] = el_[kk] >= 0 ? wl[kk] * pow2(el_[kk] - emax) : 0.f;
+        z += wb[kk] + wl[kk];
+      }
+      live = emax >= 0;
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < NP; ++kk) {
+        const int u = lane + 32 * kk;
+        wb[kk] = CTC_DEAD; wl[kk] = CTC_DEAD;
+        if (u <= U) {
+          const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
+          wb[kk] = a.x + c.x;
+          if (u < U) wl[kk] = a.y + c.y;
+        }
+        vmax = fmaxf(vmax, fmaxf(wb[kk], wl[kk]));
+      }
+      vmax = warp_max(vmax);
+#pragma unroll
+      for (int kk = 0; kk < NP; ++kk) {
+        wb[kk] = ex2f(wb[kk] - vmax);
+        wl[kk] = ex2f(wl[kk] - vmax);
+        z += wb[kk] + wl[kk];
+      }
+      live = vmax > CTC_DEAD_TEST;
     }
     z = warp_sum(z);
-    const float inv = (vmax > CTC_DEAD_TEST && z > 0.f) ? 1.f / z : 0.f;
+    const float inv = (live && z > 0.f) ? 1.f / z : 0.f;
     __syncwarp();                                     // softmax row complete before the scatter
     // Every other lattice node is the blank: its contributions are summed in registers and
     // added once; label nodes scatter with shared-memory atomics (labels may repeat).
@@ -1163,14 +740,14 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
                 const float* __restrict__ lse, const float* __restrict__ alpha,
                 const float* __restrict__ beta, const float* __restrict__ nll,
                 const float* __restrict__ grad_out, int reduction,
-                TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t) {
+                TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t, const int* __restrict__ lossy) {
   extern __shared__ __align__(128) float sm[];       // per warp: V floats (softmax row, then the gradient row)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned wpb = blockDim.x >> 5;               // warps per block shrink for large V
   const unsigned nrows = (unsigned)B * (unsigned)Tn;
   for (unsigned row = blockIdx.x * wpb + warp; row < nrows; row += gridDim.x * wpb) {   // launched with one warp per row (a capped, persistent grid measured slower)
     ctc_grad_row<TI, TO, NP>(sm, row, warp, lane, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, B, Tn, V,
-                             Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t);
+                             Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, lossy);
     __syncwarp();                                     // the warp's shared-memory row is reused by its next frame
   }
 }
@@ -1178,6 +755,21 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
 }  // namespace sc
 
 using namespace sc;
+
+// Which lattice representation a call uses — decided from Umax alone, so the three entry points agree without
+// sharing state: lattices of up to 32*LIN_MAXK - 1 labels run the fp64 linear-domain recursion (sc_ctc_lin64.cuh),
+// larger ones the log-domain kernels.  SC_CTC_LIN=0 in the environment forces the log-domain path (A/B runs).
+static bool ctc_use_lin(int64_t Umax) {
+  static const bool off = [] { const char* e = getenv("SC_CTC_LIN"); return e && e[0] == '0'; }();
+  return !off && Umax + 1 <= 32 * LIN_MAXK;
+}
+static int ctc_lin_pitch(int64_t Umax) { return (int)((Umax + 1 + 3) & ~(int64_t)3); }
+
+extern "C" int64_t sc_ctc_workspace_bytes(int64_t B, int64_t T, int64_t Umax) {
+  (void)Umax;
+  if (B <= 0 || T < 0) return 16;
+  return ctc_ws_bytes(B, T);
+}
 
 extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                                 const int64_t* targets, int64_t ldt, const int64_t* in_lens,
@@ -1192,18 +784,27 @@ extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t st
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);      // row width of lplat/alpha/beta (16-B rows)
   const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
+  if (ctc_use_lin(Umax)) {
+    const int LP = ctc_lin_pitch(Umax);
+#define SC_CTC_E(TT, NL) ctc_lse_gather_lin_kernel<TT, NL><<<blocks, CTC_WARPS * 32, 0, st>>>((const TT*)logits, stride_b, stride_t, \
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, (int)Umax, LP, blank, lse, (uint32_t*)lplat, cshift)
+    if (dtype == SC_F32) { if (Umax + 1 <= 160) SC_CTC_E(float, 5); else SC_CTC_E(float, 8); }
+    else { if (Umax + 1 <= 160) SC_CTC_E(bf16, 5); else SC_CTC_E(bf16, 8); }
+#undef SC_CTC_E
+    SC_LAUNCH_RET();
+  }
   if (dtype == SC_F32)
     ctc_lse_gather_kernel<float><<<blocks, CTC_WARPS * 32, 0, st>>>((const float*)logits, stride_b, stride_t,
-        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat, cshift);
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, (int)Umax, Smax, blank, lse, lplat, cshift);
   else
     ctc_lse_gather_kernel<bf16><<<blocks, CTC_WARPS * 32, 0, st>>>((const bf16*)logits, stride_b, stride_t,
-        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, lplat, cshift);
+        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, (int)Umax, Smax, blank, lse, lplat, cshift);
   SC_LAUNCH_RET();
 }
 
 // Rows of emissions per block meeting of the wavefront kernel: as many as fit next to the
 // other CTAs that have to share an SM (2B CTAs over the device), at most 64.
-static int ctc_wave_rows(int Smax, int64_t B, int nwarps, size_t* smem_out) {
+static int ctc_wave_rows(int pitch, int64_t B, int nwarps, size_t* smem_out) {
   const int sms = num_sms();
   int per_sm = (int)((2 * B + sms - 1) / sms);
   if (per_sm > 8) per_sm = 8;
@@ -1212,67 +813,75 @@ static int ctc_wave_rows(int Smax, int64_t B, int nwarps, size_t* smem_out) {
   if (const char* ev = getenv("SC_CTC_EB")) forced = atoi(ev);
   for (int eb = 64; eb >= 4; eb >>= 1) {
     if (forced > 0 && eb != forced) continue;
-    const size_t need = 2 * (size_t)eb * Smax * sizeof(float) + (size_t)nwarps * (eb + 1) * 8 + 16;
+    const size_t need = 2 * (size_t)eb * pitch * sizeof(float) + (size_t)nwarps * (eb + 1) * 8 + 16;
     if (need <= budget || eb == 4 || forced > 0) { *smem_out = need; return eb; }
   }
+  return 0;
+}
+
+template <int FMT>
+static int launch_wave2(const float* lplat, const float* cshift, const int64_t* targets, int64_t ldt,
+                        const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T, int64_t Umax,
+                        int Smax, int LP, const int* lossy, float* alpha, float* beta, float* nll, cudaStream_t st) {
+  const int wthreads = (((int)Umax + 1 + 31) / 32) * 32;
+  size_t smem = 0;
+  const int eb = ctc_wave_rows(FMT == 1 ? LP : Smax, B, wthreads / 32, &smem);
+  SC_CHECK_ARG(eb > 0 && smem <= 220 * 1024, SC_E_SHAPE);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_wave2_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  ctc_alpha_beta_wave2_kernel<FMT><<<dim3((unsigned)B, 2), wthreads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
+      (int)T, (int)Umax, Smax, LP, eb, lossy, alpha, beta, nll);
+  return 0;
+}
+
+static int launch_lin64(const float* lplat, const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                        const int64_t* tgt_lens, int64_t B, int64_t T, int64_t Umax, int Smax, int LP,
+                        float* alpha, float* beta, float* nll, const CtcWs& w, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)LIN_EB * LP * sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ctc_lin64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  ctc_lin64_kernel<<<dim3((unsigned)B, 2), 32, smem, st>>>((const uint32_t*)lplat, targets, ldt, in_lens, tgt_lens,
+      (int)T, (int)Umax, LP, Smax, alpha, beta, nll, w);
   return 0;
 }
 
 extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int64_t* targets, int64_t ldt,
                               const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T,
                               int64_t Umax, int64_t blank, float* alpha, float* beta, float* nll,
-                              float* loss, int reduction, void* stream) {
+                              float* loss, int reduction, void* ws, void* stream) {
   SC_CHECK_ARG(B > 0 && T >= 0 && Umax >= 0 && blank >= 0, SC_E_BADARG);
-  SC_CHECK_ARG(in_lens && tgt_lens && nll && (Umax == 0 || targets), SC_E_BADARG);
+  SC_CHECK_ARG(in_lens && tgt_lens && nll && ws && (Umax == 0 || targets), SC_E_BADARG);
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2 && (reduction == 0 || loss), SC_E_BADARG);
   SC_CHECK_ARG(T == 0 || (lplat && cshift && alpha && beta), SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && Umax < (1 << 20), SC_E_SHAPE);
+  SC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 7) == 0, SC_E_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
-  int threads = ((Smax + 31) / 32) * 32;
-  if (threads > 1024) threads = 1024;
-  int wave = Smax <= 1024 ? 2 : 0;                               // SC_CTC_WAVE: 0 block-barrier kernel, 1 node per thread, 2 pair per thread
-  if (const char* ev = getenv("SC_CTC_WAVE")) {
-    const int w = atoi(ev);
-    if (w >= 0 && w < wave) wave = w;
-    if ((w == 3 || w == 4) && Smax <= 1024) wave = w;            // experimental linear-domain recursions (opt-in)
-  }
-  if (wave == 4) {
-    const int wthreads = (((int)Umax + 1 + 31) / 32) * 32;
-    size_t smem = 0;
-    const int eb = ctc_wave_rows(Smax, B, wthreads / 32, &smem);
-    smem += (size_t)(wthreads / 32) * (eb + 1) * 8;              // 16-byte slots instead of 8
-    SC_CHECK_ARG(eb > 0 && smem <= 220 * 1024, SC_E_SHAPE);
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_wave2_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+  int rc = 0;
+  if (ctc_use_lin(Umax)) {
+    // fp64 linear-domain recursion -> range check -> log-domain recomputation of the utterances it flags
+    const CtcWs w = ctc_ws_carve(ws, B, T);
+    const int LP = ctc_lin_pitch(Umax);
+    rc = launch_lin64(lplat, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, alpha, beta, nll, w, st);
+    if (rc) return rc;
+    int force = 0;
+    if (const char* ev = getenv("SC_CTC_FORCE_LOSSY")) force = ev[0] == '1';     // tests: send every utterance down the recomputation path
+    ctc_lin64_check_kernel<<<(unsigned)B, LIN_CHECK_THREADS, 0, st>>>(cshift, in_lens, tgt_lens, (int)T, (int)Umax, Smax, force, alpha, beta, nll, w);
+    if (T > 0) {
+      rc = launch_wave2<1>(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, w.lossy, alpha, beta, nll, st);
+      if (rc) return rc;
     }
-    ctc_alpha_beta_wave2_lin_kernel<<<dim3((unsigned)B, 2), wthreads, smem, st>>>(lplat, cshift, targets, ldt, in_lens,
-        tgt_lens, (int)T, Smax, eb, blank, alpha, beta, nll);
-  } else
-  if (wave == 3) {
-    const size_t smem = (4 * (size_t)(Smax + 4) + 2 * (size_t)CTC_EB * Smax) * sizeof(float);
-    SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-    }
-    ctc_alpha_beta_lin_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
-        (int)T, Smax, blank, alpha, beta, nll);
-  } else if (wave) {
-    const int wthreads = wave == 2 ? (((int)Umax + 1 + 31) / 32) * 32 : threads;
-    size_t smem = 0;
-    const int eb = ctc_wave_rows(Smax, B, wthreads / 32, &smem);
-    SC_CHECK_ARG(eb > 0 && smem <= 220 * 1024, SC_E_SHAPE);
-    auto kern = wave == 2 ? ctc_alpha_beta_wave2_kernel : ctc_alpha_beta_wave_kernel;
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-    }
-    kern<<<dim3((unsigned)B, 2), wthreads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
-        (int)T, Smax, eb, blank, alpha, beta, nll);
+  } else if (Smax <= 1024 && !(getenv("SC_CTC_WAVE") && getenv("SC_CTC_WAVE")[0] == '0')) {
+    rc = launch_wave2<0>(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, 0, nullptr, alpha, beta, nll, st);
+    if (rc) return rc;
   } else {
-    // two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
+    // block-barrier kernel, any lattice width: two recursion lines + (fast path, S <= 1024) two blocks of CTC_EB emission rows
+    int threads = ((Smax + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
     const size_t smem = (2 * (size_t)(Smax + 4) + (Smax <= 1024 ? 2 * (size_t)CTC_EB * Smax : 0)) * sizeof(float);
     SC_CHECK_ARG(smem <= 200 * 1024, SC_E_SHAPE);
     if (smem > 48 * 1024) {
@@ -1280,7 +889,7 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
       if (e != cudaSuccess) return (int)e;
     }
     ctc_alpha_beta_kernel<<<dim3((unsigned)B, 2), threads, smem, st>>>(lplat, cshift, targets, ldt, in_lens, tgt_lens,
-        (int)T, Smax, blank, alpha, beta, nll);
+        (int)T, (int)Umax, Smax, blank, alpha, beta, nll);
   }
   if (reduction != 0) ctc_reduce_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, (int)B, reduction, loss);
   SC_LAUNCH_RET();
@@ -1290,13 +899,13 @@ extern "C" int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t
                           const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                           const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
                           int64_t blank, float* lse, float* lplat, float* cshift, float* alpha, float* beta,
-                          float* nll, float* loss, int reduction, void* stream) {
+                          float* nll, float* loss, int reduction, void* ws, void* stream) {
   SC_CHECK_ARG(blank >= 0 && blank < V, SC_E_BADARG);
   const int rc = sc_ctc_emissions(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax,
                                   blank, lse, lplat, cshift, stream);
   if (rc) return rc;
   return sc_ctc_lattice(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, blank, alpha, beta, nll, loss, reduction,
-                        stream);
+                        ws, stream);
 }
 
 template <typename TI, typename TO, int NP>
@@ -1305,7 +914,7 @@ static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_
                            const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int Smax,
                            int64_t blank, const float* lse, const float* alpha, const float* beta,
                            const float* nll, const float* grad_out, int reduction, void* dlogits,
-                           int64_t dstride_b, int64_t dstride_t, cudaStream_t st) {
+                           int64_t dstride_b, int64_t dstride_t, const int* lossy, cudaStream_t st) {
   // one shared-memory row of V floats per warp: fewer warps per block when the vocabulary is large
   const size_t per_warp = (size_t)V * sizeof(float);
   int warps = CTC_WARPS;
@@ -1319,7 +928,7 @@ static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_
   const unsigned blocks = (unsigned)cdiv(B * T, warps);
   ctc_grad_kernel<TI, TO, NP><<<blocks, warps * 32, smem, st>>>((const TI*)logits, stride_b, stride_t, targets, ldt,
       in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction,
-      (TO*)dlogits, dstride_b, dstride_t);
+      (TO*)dlogits, dstride_b, dstride_t, lossy);
   SC_LAUNCH_RET();
 }
 
@@ -1337,16 +946,18 @@ extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t
                           int64_t blank, const float* lse, const float* alpha, const float* beta,
                           const float* nll, const float* grad_out, int reduction,
                           void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
-                          void* stream) {
+                          const void* ws, void* stream) {
   SC_CHECK_ARG(B > 0 && T >= 0 && V > 0 && Umax >= 0 && blank >= 0 && blank < V, SC_E_BADARG);
   if (T == 0) return 0;
-  SC_CHECK_ARG(logits && in_lens && tgt_lens && lse && alpha && beta && nll && grad_out && dlogits, SC_E_BADARG);
+  SC_CHECK_ARG(logits && in_lens && tgt_lens && lse && alpha && beta && nll && grad_out && dlogits && ws, SC_E_BADARG);
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2, SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31), SC_E_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
+  // rows are in the linear-domain format except for the utterances flagged in the workspace (same rule as the forward)
+  const int* lossy = ctc_use_lin(Umax) ? ctc_ws_carve(const_cast<void*>(ws), B, T).lossy : nullptr;
 #define SC_CTC_GRAD(TI, TO) ctc_grad_by_width<TI, TO>(Smax, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, \
-    B, T, V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, st)
+    B, T, V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, lossy, st)
   if (dtype == SC_F32 && out_dtype == SC_F32) return SC_CTC_GRAD(float, float);
   if (dtype == SC_BF16 && out_dtype == SC_BF16) return SC_CTC_GRAD(bf16, bf16);
   if (dtype == SC_F32 && out_dtype == SC_BF16) return SC_CTC_GRAD(float, bf16);

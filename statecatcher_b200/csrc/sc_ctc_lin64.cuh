@@ -1,0 +1,390 @@
+// K3, pass 2 for lattices of up to 255 labels: the alpha/beta recursions in the LINEAR domain on fp64.
+// Included by sc_ctc.cu (uses its helpers); replaces model.py:70-71's ctc_loss_gpu recursions.
+//
+// Why: the log-domain step is a dependent chain max -> ex2 -> add -> lg2 -> add per node; measured on a B200
+// (profiles/micro/lat_bench.cu) that chain is 87 cycles for ONE two-term node with nothing else in the warp, and
+// 285 cycles per timestep in the shipped pair-per-thread kernel once the cross-warp handoff, stores and address
+// arithmetic share the in-order issue slot.  In the linear domain a step is alpha'(s) = (alpha(s) + alpha(s-1) +
+// skip*alpha(s-2)) * p_t(s): DADD/DFMA/DMUL at 8.4 cycles each, no MUFU at all.  fp32 cannot hold it (with T >> U
+// the forward and backward masses sit at opposite ends of the lattice; the nodes that carry the occupancy lie
+// 2^-125 and further below a column's maximum — r01), a per-node software exponent costs more integer work than
+// it saves (SC_CTC_WAVE=3/4 of r01, measured 0.73 / 1.00 ms against 0.46 ms: deleted), but fp64 IS a hardware
+// (mantissa, 11-bit exponent) pair: a column kept with its maximum near 2^400 has 1400 binary orders below it.
+//
+// Shape: ONE WARP per (utterance, direction), no barrier and no polling anywhere.  Lane i owns the (blank, label)
+// pairs c = 32 j + i, j < K, of the scan order (alpha: pair c = nodes 2c, 2c+1; beta: the mirrored lattice), so for
+// a fixed j the warp's pairs are adjacent in memory and every row leaves through K coalesced 8-byte stores.  A label
+// needs the previous pair's label: one lane rotation per j (lane 0 takes lane 31's value of j-1).  All K chains of
+// a step are independent, so the in-order warp always has DP work to issue while a shuffle is in flight.
+//
+// Formats (4 bytes per node, as before):
+//  * emissions  lplat[b,t,:] (pitch LP words): [0] = p(blank), [1+u] = p(label u), each the HIGH WORD of the fp64
+//    value p = 2^(e - c_t) (c_t = the frame's largest lattice emission, so p <= 1; cshift[b,t] = c_t is added back
+//    into the likelihood).  (hi, lo=0) is a valid double: no conversion instruction in the recursion.  20 mantissa
+//    bits = a 4.8e-7 relative perturbation of each emission, the size of fp32 rounding of the logit itself; both
+//    directions read the same words, so alpha, beta and the likelihood stay mutually consistent.  All blank nodes
+//    share one emission: U+1 words per frame instead of 2U+1.
+//  * alpha / beta rows: the high word of each node's fp64 value (alpha WITH its frame's emission, beta without), at
+//    its SCAN-ORDER position (beta row reversed: node s sits at 2U - s).  The gradient pass adds exponents and
+//    multiplies the 20-bit mantissas; per-column scale factors cancel in its per-frame normalisation.
+//
+// Range: every 8 steps the warp takes the column maximum (integer max of high words, one REDUX) and, when it has
+// drifted by more than 2^48 from 2^900, rescales by an exact power of two (integer add on the exponent fields,
+// the shift accumulated as an integer).  A column then has ~1700 binary orders below its maximum; measured need at
+// T=3000, U=150, V=1024 on N(0, s^2) logits (the most occupied node against the column maximum): 741 (s=1),
+// 944 (s=2), 1355 (s=3).  What fp64 cannot hold is detected, never silently accepted — ctc_lin64_check_kernel:
+//  (a) the column maximum falling by more than 2^200 within 8 steps -> `danger` (the guaranteed range is gone);
+//  (b) the two directions' likelihoods disagreeing (mass lost to underflow in one direction shows up here);
+//  (c) at every 32nd frame, sum_s alpha_t(s) beta_t(s) — formed from the stored rows exactly the way the gradient
+//      pass forms occupancies — must reproduce that likelihood to 1e-4 (log2): a flushed node that carried more
+//      than that share of any sampled frame's mass fails it.
+// Any of them sets lossy[b] = 1 and the log-domain pair-per-thread kernel recomputes exactly those utterances (it
+// exits at once for the others); the gradient pass reads lossy[b] to know which row format it is looking at.
+#pragma once
+
+namespace sc {
+
+constexpr int LIN_EB = 64;                 // emission rows per bulk-copied shared-memory block
+constexpr int LIN_CHECK = 8;               // steps between range checks
+constexpr int LIN_TGT = 1023 + 900;        // exponent field the column maximum is kept near (growth is < 2^13 per 8 steps: no overflow)
+constexpr int LIN_HYST = 48;               // rescale when the maximum is further than 2^48 from the target
+constexpr int LIN_DANGER = LIN_TGT - LIN_HYST - 200;   // column maximum this low at a check: it fell by > 2^200 within 8 steps
+constexpr int LIN_MAXK = 8;                // pairs per lane: lattices of up to 32*8 - 1 labels
+constexpr int LIN_SAMPLE = 32;             // check (c) looks at frames t = 15 mod 32
+
+// layout of the opaque workspace `ws` (sc_ctc_workspace_bytes)
+struct CtcWs {
+  int* lossy;        // [B]      1: rows of this utterance are in the log-domain format (recomputed)
+  int* danger;       // [B][2]   per direction: range event (a) above
+  double* zl2;       // [B][2]   per direction: log2 of the shift-free likelihood (-inf when zero)
+  int* accs;         // [B][2][NT] log2 of the scale taken out of the rows of frames [8k, 8k+7], per direction
+  int NT;
+};
+__host__ __device__ inline int ctc_ws_nt(int64_t T) { return (int)(T / LIN_CHECK) + 2; }
+__host__ __device__ inline CtcWs ctc_ws_carve(void* ws, int64_t B, int64_t T) {
+  CtcWs w;
+  char* p = reinterpret_cast<char*>(ws);
+  w.NT = ctc_ws_nt(T);
+  w.zl2 = reinterpret_cast<double*>(p);                          p += (size_t)B * 2 * sizeof(double);
+  w.lossy = reinterpret_cast<int*>(p);                           p += (((size_t)B * 4 + 15) & ~(size_t)15);
+  w.danger = reinterpret_cast<int*>(p);                          p += (((size_t)B * 8 + 15) & ~(size_t)15);
+  w.accs = reinterpret_cast<int*>(p);
+  return w;
+}
+inline int64_t ctc_ws_bytes(int64_t B, int64_t T) {
+  return (int64_t)(B * 16 + ((B * 4 + 15) & ~(int64_t)15) + ((B * 8 + 15) & ~(int64_t)15) + B * 2 * ctc_ws_nt(T) * 4 + 16);
+}
+
+// high word of 2^d (d <= 0, log2 units), mantissa rounded to 20 bits; 0 = probability zero
+__device__ __forceinline__ uint32_t lin_word_of_log2(float d) {
+  if (!(d > -1000.f)) return 0u;
+  const float fl = floorf(d);
+  const uint32_t mb = __float_as_uint(ex2f(d - fl));             // 2^frac in [1, 2]: exponent field 127 (128 when it rounds to 2)
+  return (uint32_t)((896 + (int)fl) << 20) + ((mb + 4u) >> 3);   // (1023 - 127 + fl) << 20, + the float's own exponent/mantissa >> 3
+}
+// the reverse, for the log-domain kernels reading the same emission words
+__device__ __forceinline__ float lin_word_to_log2(uint32_t w) {
+  if (w == 0u) return -1e30f;
+  return (float)((int)(w >> 20) - 1023) + lg2f(__uint_as_float(0x3f800000u | ((w & 0xfffffu) << 3)));
+}
+__device__ __forceinline__ double lin_hi2d(uint32_t w) { return __hiloint2double((int)w, 0); }
+__device__ __forceinline__ int lin_hi(double v) { return __double2hiint(v); }
+__device__ __forceinline__ double lin_rot(double v, int src) {
+  return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+// ---- pass 1, linear emission format -------------------------------------------------------------------------
+template <typename T, int NL>
+__global__ void __launch_bounds__(CTC_WARPS * 32, 5)
+ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_t stride_t,
+                          const int64_t* __restrict__ targets, int64_t ldt,
+                          const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                          int B, int Tn, int V, int Umax, int LP, int64_t blank,
+                          float* __restrict__ lse, uint32_t* __restrict__ lplat, float* __restrict__ cshift) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned nrows = (unsigned)B * (unsigned)Tn;
+  for (unsigned row = blockIdx.x * CTC_WARPS + warp; row < nrows; row += gridDim.x * CTC_WARPS) {
+    const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
+    int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
+    if (t >= Tb) continue;
+    const int64_t U64 = tgt_lens[b];
+    if (U64 < 0 || U64 > Umax) continue;                         // invalid length: the lattice pass reports the utterance infeasible
+    const int U = (int)U64;
+    const T* x = logits + b * stride_b + t * stride_t;
+    const float l = warp_row_lse<T>(x, V, lane);
+    if (lane == 0) lse[row] = l;
+    const int64_t* tg = targets + (int64_t)b * ldt;
+    uint32_t* out = lplat + (int64_t)row * LP;
+    float e[NL];
+    float c = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int idx = lane + 32 * k;                             // 0 = blank, 1 + u = label u
+      e[k] = -INFINITY;
+      if (idx <= U) {
+        const int64_t lab = idx == 0 ? blank : tg[idx - 1];
+        if (lab >= 0 && lab < V) e[k] = (ld_f(x + lab) - l) * 1.4426950408889634f;   // a label outside the vocabulary is probability zero
+        c = fmaxf(c, e[k]);
+      }
+    }
+    c = warp_max(c);
+    if (!(c > -1e29f)) c = 0.f;                                  // every lattice emission is -inf: leave the row dead
+#pragma unroll
+    for (int k = 0; k < NL; ++k)
+      if (lane + 32 * k <= U) out[lane + 32 * k] = lin_word_of_log2(e[k] - c);
+    if (lane == 0) cshift[row] = c;
+  }
+}
+
+// ---- pass 2, linear domain ----------------------------------------------------------------------------------
+// K = pairs per lane for THIS utterance (ceil((U+1)/32), chosen at run time by the kernel below): slots j < K-1 are
+// complete for every lane, only the last slot has lanes without a label (c >= U) or without a pair (c > U), so two
+// predicates cover the whole step and a short transcript costs proportionally fewer DP instructions.
+template <int K, int DIR>
+__device__ __forceinline__ void
+ctc_lin64_run(uint32_t* __restrict__ ebuf, uint64_t* ebar, const uint32_t* __restrict__ lp_b,
+              const int64_t* __restrict__ tg, int Tb, int U, int LP, int Smax, float* __restrict__ out_b,
+              int* __restrict__ accrec, double* __restrict__ zl2_out, int* __restrict__ danger_out) {
+  const int lane = threadIdx.x;
+  const int cl = 32 * (K - 1) + lane;                            // this lane's pair in the last slot
+  const bool vl_last = cl < U, vb_last = cl <= U;
+  const uint32_t lmask = vl_last ? 0xffffffffu : 0u;             // a missing label's emission word is ANDed to zero
+  int lidx[K];                                                   // the label's word in an emission row
+  double skipf[K];                                               // 1.0 when the label may also be entered from the previous pair's label
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int c = 32 * j + lane;
+    const bool vl = c < U;
+    const int u = DIR == 0 ? c : U - 1 - c;                      // label index in the transcript
+    lidx[j] = vl ? 1 + u : 0;
+    bool sk = false;
+    if (vl && c >= 1) sk = tg[u] != tg[DIR == 0 ? u - 1 : u + 1];
+    skipf[j] = sk ? 1.0 : 0.0;
+  }
+  const int nvis = (Tb + LIN_EB - 1) / LIN_EB;
+  auto blk_of = [&](int vi) { return DIR == 0 ? vi : nvis - 1 - vi; };
+  auto rows_of = [&](int blk) { const int r = Tb - blk * LIN_EB; return r < LIN_EB ? r : LIN_EB; };
+  auto issue = [&](int vi) {
+    const int blk = blk_of(vi);
+    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)LP * 4u;
+    const uint32_t bar = smem_u32(&ebar[vi & 1]);
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * LIN_EB * LP), lp_b + (int64_t)blk * LIN_EB * LP, bytes, bar);
+  };
+  if (lane == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  double bv[K], lv[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { bv[j] = 0.0; lv[j] = 0.0; }
+  if (lane == 0) bv[0] = __hiloint2double(LIN_TGT << 20, 0);     // virtual column before the first frame: all mass in front of node 0, at the target scale
+  int acc = 1023 - LIN_TGT;                                      // log2 of the scale taken out of the column so far
+  int danger = 0;
+  int t = DIR == 0 ? 0 : Tb - 1;
+  if (lane == 0) accrec[t >> 3] = acc;                           // scale of the rows up to the first check
+  const int src = (lane + 31) & 31;
+  const bool lane0 = lane == 0;
+  for (int vi = 0; vi < nvis; ++vi) {
+    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
+    const int rows = rows_of(blk_of(vi));
+    const uint32_t* erow = ebuf + ((size_t)(vi & 1) * LIN_EB + (DIR == 0 ? 0 : rows - 1)) * LP;
+    uint2* orow = reinterpret_cast<uint2*>(out_b + (int64_t)t * Smax) + lane;
+    for (int pos = 0; pos < rows; ++pos) {
+      const double pb = lin_hi2d(erow[0]);
+      double pl[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) pl[j] = lin_hi2d(j == K - 1 ? (erow[lidx[j]] & lmask) : erow[lidx[j]]);
+      double prev[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) prev[j] = lin_rot(lv[j], src);
+#pragma unroll
+      for (int j = K - 1; j > 0; --j) prev[j] = lane0 ? prev[j - 1] : prev[j];
+      prev[0] = lane0 ? 0.0 : prev[0];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const double sb = bv[j] + prev[j];
+        const double sl = fma(skipf[j], prev[j], lv[j] + bv[j]);
+        bv[j] = sb * pb;
+        lv[j] = sl * pl[j];
+        uint2 w;
+        w.x = (uint32_t)lin_hi(DIR == 0 ? bv[j] : sb);           // beta leaves without its frame's emission
+        w.y = (uint32_t)lin_hi(DIR == 0 ? lv[j] : sl);
+        if (j < K - 1) orow[32 * j] = w;
+        else if (vb_last) { w.y &= lmask; orow[32 * j] = w; }
+      }
+      erow += DIR == 0 ? LP : -LP;
+      orow += DIR == 0 ? (Smax >> 1) : -(Smax >> 1);
+      const bool check = DIR == 0 ? ((t & (LIN_CHECK - 1)) == LIN_CHECK - 1) : ((t & (LIN_CHECK - 1)) == 0);
+      if (check) {
+        int m = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) m = max(m, max(lin_hi(bv[j]), lin_hi(lv[j])));
+        m = __reduce_max_sync(0xffffffffu, m);
+        const int e = m >> 20;
+        if (e > 0) {
+          if (e < LIN_DANGER) danger = 1;
+          const int d = e - LIN_TGT;
+          if (d > LIN_HYST || d < -LIN_HYST) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+              const int hb = lin_hi(bv[j]), hl = lin_hi(lv[j]);
+              bv[j] = ((hb >> 20) > 0 && (hb >> 20) - d > 0) ? __hiloint2double(hb - (d << 20), __double2loint(bv[j])) : 0.0;
+              lv[j] = ((hl >> 20) > 0 && (hl >> 20) - d > 0) ? __hiloint2double(hl - (d << 20), __double2loint(lv[j])) : 0.0;
+            }
+            acc += d;
+          }
+        }
+        // rows of the next 8 frames in scan order carry this scale (alpha: frames t+1..t+8, beta: t-8..t-1)
+        if (lane0) { const int k = DIR == 0 ? (t >> 3) + 1 : (t >> 3) - 1; if (k >= 0) accrec[k] = acc; }
+      }
+      t += DIR == 0 ? 1 : -1;
+    }
+    __syncwarp();                                               // every lane is done with this visit's emission block
+    if (lane0 && vi + 2 < nvis) issue(vi + 2);
+  }
+  // likelihood from this direction: the last pair's blank and the label before it (both after their emission)
+  double z = 0.0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int c = 32 * j + lane;
+    if (c == U) z += bv[j];
+    if (c == U - 1) z += lv[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) z += lin_rot(z, lane ^ o);
+  if (lane0) {
+    *zl2_out = z > 0.0 ? log2(z) + (double)acc : -INFINITY;
+    *danger_out = danger;
+  }
+}
+
+template <int DIR>
+__device__ __forceinline__ void
+ctc_lin64_body(uint32_t* __restrict__ ebuf, uint64_t* ebar, const uint32_t* __restrict__ lplat,
+               const int64_t* __restrict__ targets, int64_t ldt,
+               const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+               int Tn, int Umax, int LP, int Smax, float* __restrict__ alpha, float* __restrict__ beta,
+               float* __restrict__ nll, CtcWs ws) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64;
+  const int64_t U64 = tgt_lens[b];
+  const bool bad_len = U64 < 0 || U64 > Umax;
+  const int U = bad_len ? 0 : (int)U64;
+  if (lane == 0) { ws.danger[2 * b + DIR] = 0; if (DIR == 0) ws.lossy[b] = 0; }
+  if (Tb <= 0 || bad_len) {
+    if (lane == 0) {
+      const bool ok = !bad_len && U == 0;                        // no frames, no labels: probability one
+      ws.zl2[2 * b + DIR] = ok ? 0.0 : -INFINITY;
+      if (DIR == 0) nll[b] = ok ? 0.f : INFINITY;
+    }
+    return;
+  }
+  if (lane == 0) {
+    mbar_init(smem_u32(&ebar[0]), 1);
+    mbar_init(smem_u32(&ebar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t* tg = targets + (int64_t)b * ldt;
+  const uint32_t* lp_b = lplat + (int64_t)b * Tn * LP;
+  float* out_b = (DIR == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
+  int* accrec = ws.accs + (size_t)(2 * b + DIR) * ws.NT;
+  double* zo = ws.zl2 + 2 * b + DIR;
+  int* dg = ws.danger + 2 * b + DIR;
+#define SC_LIN_RUN(KK) ctc_lin64_run<KK, DIR>(ebuf, ebar, lp_b, tg, Tb, U, LP, Smax, out_b, accrec, zo, dg)
+  switch ((U + 32) >> 5) {                                       // pairs per lane for this transcript
+    case 1: SC_LIN_RUN(1); break;
+    case 2: SC_LIN_RUN(2); break;
+    case 3: SC_LIN_RUN(3); break;
+    case 4: SC_LIN_RUN(4); break;
+    case 5: SC_LIN_RUN(5); break;
+    case 6: SC_LIN_RUN(6); break;
+    case 7: SC_LIN_RUN(7); break;
+    default: SC_LIN_RUN(8); break;
+  }
+#undef SC_LIN_RUN
+}
+
+__global__ void __launch_bounds__(32, 1)
+ctc_lin64_kernel(const uint32_t* __restrict__ lplat, const int64_t* __restrict__ targets, int64_t ldt,
+                 const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+                 int Tn, int Umax, int LP, int Smax, float* __restrict__ alpha, float* __restrict__ beta,
+                 float* __restrict__ nll, CtcWs ws) {
+  extern __shared__ __align__(128) uint32_t lin_sm[];            // 2 emission blocks of LIN_EB x LP words
+  __shared__ __align__(8) uint64_t ebar[2];
+  if (blockIdx.y == 0) ctc_lin64_body<0>(lin_sm, ebar, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
+  else ctc_lin64_body<1>(lin_sm, ebar, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
+}
+
+// one block per utterance: likelihood, and whether fp64 held everything (see the header of this file)
+constexpr int LIN_CHECK_THREADS = 128;
+__global__ void __launch_bounds__(LIN_CHECK_THREADS)
+ctc_lin64_check_kernel(const float* __restrict__ cshift, const int64_t* __restrict__ in_lens,
+                       const int64_t* __restrict__ tgt_lens, int Tn, int Umax, int Smax, int force_lossy,
+                       const float* __restrict__ alpha, const float* __restrict__ beta,
+                       float* __restrict__ nll, CtcWs ws) {
+  __shared__ double dred[LIN_CHECK_THREADS / 32];
+  __shared__ int bad[LIN_CHECK_THREADS / 32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
+  const int Tb = (int)Tb64;
+  const int64_t U64 = tgt_lens[b];
+  if (Tb <= 0 || U64 < 0 || U64 > Umax) return;                  // nll already final, lossy[b] = 0
+  const int U = (int)U64;
+  const double za = ws.zl2[2 * b], zb = ws.zl2[2 * b + 1];
+  double ssum = 0.0;
+  const float* cs = cshift + (int64_t)b * Tn;
+  for (int t = threadIdx.x; t < Tb; t += LIN_CHECK_THREADS) ssum += (double)cs[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ssum += lin_rot(ssum, lane ^ o);
+  int lossy = (ws.danger[2 * b] | ws.danger[2 * b + 1] | force_lossy) ? 1 : 0;
+  const bool fa = za > -INFINITY, fb = zb > -INFINITY;
+  if (fa != fb) lossy = 1;
+  if (fa && fb) {
+    if (fabs(za - zb) > 1e-6) lossy = 1;                         // (b) both directions must see the same likelihood
+    // (c) sum_s alpha_t(s) beta_t(s) at sampled frames, from the stored words
+    const int* aa = ws.accs + (size_t)(2 * b) * ws.NT;
+    const int* ab = ws.accs + (size_t)(2 * b + 1) * ws.NT;
+    for (int t = LIN_SAMPLE / 2 - 1 + LIN_SAMPLE * warp; t < Tb; t += LIN_SAMPLE * (LIN_CHECK_THREADS / 32)) {
+      const uint2* aw = reinterpret_cast<const uint2*>(alpha + ((int64_t)b * Tn + t) * Smax);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(beta + ((int64_t)b * Tn + t) * Smax);
+      int emax = -1;
+      for (int u = lane; u <= U; u += 32) {
+        const uint2 a = aw[u];
+        const uint32_t cb = bw[2 * (U - u)];
+        if (a.x != 0u && cb != 0u) emax = max(emax, (int)(a.x >> 20) + (int)(cb >> 20));
+        if (u < U) { const uint32_t cl = bw[2 * (U - u) - 1]; if (a.y != 0u && cl != 0u) emax = max(emax, (int)(a.y >> 20) + (int)(cl >> 20)); }
+      }
+      emax = __reduce_max_sync(0xffffffffu, emax);
+      double acc = 0.0;
+      auto term = [&](uint32_t x, uint32_t y) -> double {
+        if (x == 0u || y == 0u) return 0.0;
+        const int d = (int)(x >> 20) + (int)(y >> 20) - emax;
+        if (d < -60) return 0.0;
+        return __hiloint2double((int)(0x3ff00000u | (x & 0xfffffu)), 0) * __hiloint2double((int)(0x3ff00000u | (y & 0xfffffu)), 0) *
+               __hiloint2double((1023 + d) << 20, 0);
+      };
+      for (int u = lane; u <= U; u += 32) {
+        const uint2 a = aw[u];
+        acc += term(a.x, bw[2 * (U - u)]);
+        if (u < U) acc += term(a.y, bw[2 * (U - u) - 1]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += lin_rot(acc, lane ^ o);
+      const double zt = emax >= 0 ? log2(acc) + (double)(emax - 2046) + (double)aa[t >> 3] + (double)ab[t >> 3] : -INFINITY;
+      if (!(fabs(zt - za) <= 1e-4)) lossy = 1;
+    }
+  }
+  if (lane == 0) { dred[warp] = ssum; bad[warp] = lossy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < LIN_CHECK_THREADS / 32; ++w) { tot += dred[w]; lossy |= bad[w]; }
+    ws.lossy[b] = lossy;
+    if (!lossy) nll[b] = fa ? (float)(-(za + tot) * 0.6931471805599453) : INFINITY;
+  }
+}
+
+}  // namespace sc

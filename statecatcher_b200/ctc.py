@@ -55,12 +55,14 @@ class _CTCFn(torch.autograd.Function):
         beta = torch.empty(B, max(T, 1), S, **f32)
         nll = torch.empty(B, **f32)
         loss = torch.zeros((), **f32)
+        # opaque per-call workspace of the lattice pass (format flags, per-direction likelihoods, range records)
+        ws = torch.empty(_lib.load().sc_ctc_workspace_bytes(B, T, Umax) // 8 + 1, dtype=torch.float64, device=dev)
         ldt = targets.stride(0) if targets.numel() else max(Umax, 1)
         call("sc_ctc_emissions", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
              ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), ptr(cshift), stream())
         call("sc_ctc_lattice", ptr(lplat), ptr(cshift), ptr(targets), ldt, ptr(in_lens), ptr(tgt_lens), B, T, Umax, blank,
-             ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, stream())
-        ctx.save_for_backward(x, targets, in_lens, tgt_lens, lse, alpha, beta, nll)
+             ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, ptr(ws), stream())
+        ctx.save_for_backward(x, targets, in_lens, tgt_lens, lse, alpha, beta, nll, ws)
         ctx.cfg = (blank, red, Umax, ldt)
         if red != 0:
             ctx.mark_non_differentiable(nll)     # per-utterance nll is a by-product here
@@ -68,7 +70,7 @@ class _CTCFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout, _gnll):
-        x, targets, in_lens, tgt_lens, lse, alpha, beta, nll = ctx.saved_tensors
+        x, targets, in_lens, tgt_lens, lse, alpha, beta, nll, ws = ctx.saved_tensors
         blank, red, Umax, ldt = ctx.cfg
         T, B, V = x.shape
         g = (_gnll if red == 0 else gout).to(torch.float32).contiguous()
@@ -77,7 +79,7 @@ class _CTCFn(torch.autograd.Function):
             else torch.empty_like(x, memory_format=torch.contiguous_format)
         call("sc_ctc_bwd", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
              ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(alpha), ptr(beta),
-             ptr(nll), ptr(g), red, ptr(dx), dx.stride(1), dx.stride(0), dt(dx), stream())
+             ptr(nll), ptr(g), red, ptr(dx), dx.stride(1), dx.stride(0), dt(dx), ptr(ws), stream())
         return dx, None, None, None, None, None, None
 
 

@@ -71,7 +71,8 @@ def test_argument_errors_are_return_codes_not_crashes():
     lib = _lib.load()
     assert lib.sc_lucy_scan_fwd(None, 0, None, None, None, 0, None, None, None, 1, 1, 8, 0, 1, None) == -1
     assert lib.sc_gemm_fwd(None, 0, None, 0, None, None, 0, -1, 1, 1, 0, 0, 0, None) == -1
-    assert lib.sc_ctc_fwd(None, 0, 0, 0, None, 0, None, None, 0, 1, 1, 0, 0, None, None, None, None, None, None, None, 1, None) == -1
+    assert lib.sc_ctc_fwd(None, 0, 0, 0, None, 0, None, None, 0, 1, 1, 0, 0, None, None, None, None, None, None, None, 1, None, None) == -1
+    assert lib.sc_ctc_workspace_bytes(64, 3000, 150) >= 64 * (16 + 4 + 8 + 2 * 4 * (3000 // 8))
     assert lib.sc_cast(None, 0, 7, None, 0, 0, 0, 0, None) == 0          # empty problem is a no-op
     # multi-tensor optimizer calls: HOST pointer tables are validated before anything is launched
     import ctypes
@@ -191,6 +192,9 @@ def test_shims_resolve_to_the_package():
         assert m.config.kernel_impl == "triton"
     finally:
         sys.path.remove(os.path.join(ROOT, "shims"))
+        route = sys.modules.pop("_sc_route", None)
+        if route is not None:
+            route.uninstall()                                  # the shims route nn.CTCLoss; undo for the other tests
         for k in ("lucyrnn", "lucyrnn_conf", "lucyrnn_triton"):
             sys.modules.pop(k, None)
         sys.modules.update(saved)

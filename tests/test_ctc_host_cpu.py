@@ -37,7 +37,7 @@ def test_padded_targets_and_list_lengths(rec):
     assert e["in_lens"].dtype == torch.int64 and e["in_lens"].tolist() == [20, 20, 11, 20]
     assert e["tgt_lens"].tolist() == [3, 1, 2, 0]
     assert [c[0] for c in rec] == ["sc_ctc_emissions", "sc_ctc_lattice"]
-    assert rec[1][1][-2] == 1                                   # reduction code: mean
+    assert rec[1][1][-3] == 1                                   # reduction code: mean (then ws, stream)
 
 
 def test_concatenated_targets_are_padded_with_blank(rec):
@@ -48,7 +48,7 @@ def test_concatenated_targets_are_padded_with_blank(rec):
     e = _em(rec)
     assert e["targets"].tolist() == [[3, 4, 0, 0], [0, 0, 0, 0], [1, 2, 2, 4]]
     assert e["Umax"] == 4 and e["ldt"] == 4
-    assert rec[1][1][-2] == 2
+    assert rec[1][1][-3] == 2
 
 
 def test_unbatched_input(rec):
@@ -85,4 +85,4 @@ def test_argument_errors(rec):
     assert not rec
     crit = CTCLoss(blank=3, reduction="none", zero_infinity=True)
     out = crit(x, torch.tensor([[1], [2]]), [5, 5], [1, 1])
-    assert out.shape == (2,) and _em(rec)["blank"] == 3 and rec[1][1][-2] == 0
+    assert out.shape == (2,) and _em(rec)["blank"] == 3 and rec[1][1][-3] == 0
