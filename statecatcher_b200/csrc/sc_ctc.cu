@@ -763,7 +763,7 @@ static bool ctc_use_lin(int64_t Umax) {
   static const bool off = [] { const char* e = getenv("SC_CTC_LIN"); return e && e[0] == '0'; }();
   return !off && Umax + 1 <= 32 * LIN_MAXK;
 }
-static int ctc_lin_pitch(int64_t Umax) { return (int)((Umax + 1 + 3) & ~(int64_t)3); }
+static int ctc_lin_pitch(int64_t Umax) { return (int)((Umax + 1 + 4) & ~(int64_t)3); }   // U+1 emissions + at least one zero word (the last)
 
 extern "C" int64_t sc_ctc_workspace_bytes(int64_t B, int64_t T, int64_t Umax) {
   (void)Umax;
@@ -839,12 +839,13 @@ static int launch_wave2(const float* lplat, const float* cshift, const int64_t* 
 static int launch_lin64(const float* lplat, const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                         const int64_t* tgt_lens, int64_t B, int64_t T, int64_t Umax, int Smax, int LP,
                         float* alpha, float* beta, float* nll, const CtcWs& w, cudaStream_t st) {
-  const size_t smem = 2 * (size_t)LIN_EB * LP * sizeof(uint32_t);
+  const int Kmax = (int)((Umax + 32) >> 5);
+  const size_t smem = (2 * (size_t)LIN_EB * (32 * Kmax + 4) + 2 * (size_t)LIN_ROWS * 64 * Kmax) * sizeof(uint32_t);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ctc_lin64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  ctc_lin64_kernel<<<dim3((unsigned)B, 2), 32, smem, st>>>((const uint32_t*)lplat, targets, ldt, in_lens, tgt_lens,
+  ctc_lin64_kernel<<<dim3((unsigned)B, 2), LIN_THREADS, smem, st>>>((const uint32_t*)lplat, targets, ldt, in_lens, tgt_lens,
       (int)T, (int)Umax, LP, Smax, alpha, beta, nll, w);
   return 0;
 }
@@ -870,7 +871,8 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
     if (rc) return rc;
     int force = 0;
     if (const char* ev = getenv("SC_CTC_FORCE_LOSSY")) force = ev[0] == '1';     // tests: send every utterance down the recomputation path
-    ctc_lin64_check_kernel<<<(unsigned)B, LIN_CHECK_THREADS, 0, st>>>(cshift, in_lens, tgt_lens, (int)T, (int)Umax, Smax, force, alpha, beta, nll, w);
+    const unsigned nsb = 1 + (unsigned)cdiv(cdiv(T, LIN_SAMPLE), LIN_CHECK_THREADS / 32);
+    ctc_lin64_check_kernel<<<dim3((unsigned)B, nsb), LIN_CHECK_THREADS, 0, st>>>(cshift, in_lens, tgt_lens, (int)T, (int)Umax, Smax, force, alpha, beta, nll, w);
     if (T > 0) {
       rc = launch_wave2<1>(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, w.lossy, alpha, beta, nll, st);
       if (rc) return rc;

@@ -132,169 +132,297 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
 #pragma unroll
     for (int k = 0; k < NL; ++k)
       if (lane + 32 * k <= U) out[lane + 32 * k] = lin_word_of_log2(e[k] - c);
-    if (lane == 0) cshift[row] = c;
+    if (lane == 0) { cshift[row] = c; out[U + 1] = 0u; }        // the row's zero word: what a missing label reads
   }
 }
 
 // ---- pass 2, linear domain ----------------------------------------------------------------------------------
-// K = pairs per lane for THIS utterance (ceil((U+1)/32), chosen at run time by the kernel below): slots j < K-1 are
-// complete for every lane, only the last slot has lanes without a label (c >= U) or without a pair (c > U), so two
-// predicates cover the whole step and a short transcript costs proportionally fewer DP instructions.
+// K = pairs per lane for THIS utterance (ceil((U+1)/32), chosen at run time by the kernel below).  Lane i owns the
+// K CONSECUTIVE pairs c = K i + j of the scan order: a pair's label needs the previous pair's label of the
+// PREVIOUS column, which for j > 0 is the lane's own register — one lane rotation per step (the previous lane's last
+// label) feeds the whole lane, every other operand is already there.
+// One warp alone on its scheduler pays every latency it exposes (measured: ~3 cycles per instruction however the
+// step is arranged, a taken branch ~20), so the recursion warp issues nothing but the recursion: LIN_ROWS steps are
+// unrolled into one branch-free group; the lane's LAST pair is computed first and its label rotated at once (the
+// shuffle for the next step is in flight under the other pairs' DP work); emission words come from a shared-memory
+// block with a COMPILE-TIME pitch (immediate offsets, no address arithmetic) and are turned into doubles one step
+// ahead; the row goes to a staging buffer as plain 4-byte shared-memory stores of the registers that already hold
+// the high words.  Everything else is a SECOND warp's job (warp specialisation, mbarrier hand-offs): it lands the
+// emission rows (bulk async copies, row by row into the compile-time pitch) and copies finished staging batches to
+// global memory with coalesced 16-byte stores.
+// Per step and recursion lane: 5K DP instructions, K+1 LDS, K+1 moves, 2K STS, 2 shuffles, 2 selects.
+constexpr int LIN_ROWS = 8;                // steps per group = rows per staging batch (two batches)
+constexpr int LIN_THREADS = 64;            // warp 0: recursion, warp 1: I/O
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+
+struct LinBars {                            // shared-memory mbarriers of one CTA
+  uint64_t efull[2], eempty[2];             // emission block landed / consumed
+  uint64_t sfull[2], sempty[2];             // staging batch written / copied out
+  int meta[2][2];                           // per staging batch: rows, first frame
+};
+
+template <int K, int DIR>
+struct Lin64 {
+  static constexpr int SP = 64 * K;        // staging row pitch in words (>= 2*32*K)
+  static constexpr int EPW = 32 * K + 4;   // emission row pitch in shared memory, words (>= U+2 rounded up to 4)
+  double bv[K], lv[K];
+  double nbv;                              // previous lane's last label of the previous column (0 for lane 0)
+  double skipf[K];
+  int lane;
+  int src;
+
+  // emission doubles of the row at shared address `ea` (+ the lane's label offsets, already folded into eb[])
+  __device__ __forceinline__ void load_em(const uint32_t (&eb)[K + 1], int rowoff, double (&p)[K + 1]) const {
+#pragma unroll
+    for (int j = 0; j <= K; ++j) p[j] = lin_hi2d(lds32(eb[j] + (uint32_t)rowoff));
+  }
+  // one column: consumes the emission doubles p (p[K] = blank), writes the lane's 2K row words at shared address sa
+  __device__ __forceinline__ void step(const double (&p)[K + 1], uint32_t sa) {
+    double nb_next = 0.0;
+#pragma unroll
+    for (int j = K - 1; j >= 0; --j) {                           // downwards: lv[j-1] is still the previous column's
+      const double prev = j > 0 ? lv[j - 1] : nbv;
+      const double sb = bv[j] + prev;
+      const double sl = fma(skipf[j], prev, lv[j] + bv[j]);
+      bv[j] = sb * p[K];
+      lv[j] = sl * p[j];
+      if (j == K - 1) nb_next = lin_rot(lv[K - 1], src);         // in flight under the remaining pairs
+      sts32(sa + 8 * j, (uint32_t)lin_hi(DIR == 0 ? bv[j] : sb));       // beta leaves without its frame's emission
+      sts32(sa + 8 * j + 4, (uint32_t)lin_hi(DIR == 0 ? lv[j] : sl));
+    }
+    nbv = lane == 0 ? 0.0 : nb_next;
+  }
+};
+
+// group boundaries of the scan (both warps walk the same sequence): groups end where the range check sits — alpha
+// after frames 7 mod 8, beta after frames 0 mod 8 — and never cross an emission block.
+template <int DIR>
+__device__ __forceinline__ int lin_group_len(int t, int rows) {
+  int n = DIR == 0 ? LIN_ROWS - (t & (LIN_ROWS - 1)) : (t & (LIN_ROWS - 1)) + 1;
+  return n < rows ? n : rows;
+}
+
 template <int K, int DIR>
 __device__ __forceinline__ void
-ctc_lin64_run(uint32_t* __restrict__ ebuf, uint64_t* ebar, const uint32_t* __restrict__ lp_b,
-              const int64_t* __restrict__ tg, int Tb, int U, int LP, int Smax, float* __restrict__ out_b,
-              int* __restrict__ accrec, double* __restrict__ zl2_out, int* __restrict__ danger_out) {
+ctc_lin64_recursion(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars* bars,
+                    const int64_t* __restrict__ tg, int Tb, int U,
+                    int* __restrict__ accrec, double* __restrict__ zl2_out, int* __restrict__ danger_out) {
+  constexpr int SP = Lin64<K, DIR>::SP, EPW = Lin64<K, DIR>::EPW;
+  Lin64<K, DIR> L;
   const int lane = threadIdx.x;
-  const int cl = 32 * (K - 1) + lane;                            // this lane's pair in the last slot
-  const bool vl_last = cl < U, vb_last = cl <= U;
-  const uint32_t lmask = vl_last ? 0xffffffffu : 0u;             // a missing label's emission word is ANDed to zero
-  int lidx[K];                                                   // the label's word in an emission row
-  double skipf[K];                                               // 1.0 when the label may also be entered from the previous pair's label
+  L.lane = lane;
+  L.src = (lane + 31) & 31;
+  uint32_t eoff[K + 1];                                          // byte offset of the lane's emission words inside a row
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const int c = 32 * j + lane;
+    const int c = K * lane + j;
     const bool vl = c < U;
     const int u = DIR == 0 ? c : U - 1 - c;                      // label index in the transcript
-    lidx[j] = vl ? 1 + u : 0;
+    eoff[j] = 4u * (uint32_t)(vl ? 1 + u : U + 1);               // U+1: the row's zero word
     bool sk = false;
     if (vl && c >= 1) sk = tg[u] != tg[DIR == 0 ? u - 1 : u + 1];
-    skipf[j] = sk ? 1.0 : 0.0;
+    L.skipf[j] = sk ? 1.0 : 0.0;                                 // 1.0 when the label may also be entered from the previous pair's label
+    L.bv[j] = 0.0; L.lv[j] = 0.0;
   }
-  const int nvis = (Tb + LIN_EB - 1) / LIN_EB;
-  auto blk_of = [&](int vi) { return DIR == 0 ? vi : nvis - 1 - vi; };
-  auto rows_of = [&](int blk) { const int r = Tb - blk * LIN_EB; return r < LIN_EB ? r : LIN_EB; };
-  auto issue = [&](int vi) {
-    const int blk = blk_of(vi);
-    const uint32_t bytes = (uint32_t)rows_of(blk) * (uint32_t)LP * 4u;
-    const uint32_t bar = smem_u32(&ebar[vi & 1]);
-    mbar_expect_tx(bar, bytes);
-    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * LIN_EB * LP), lp_b + (int64_t)blk * LIN_EB * LP, bytes, bar);
-  };
-  if (lane == 0) {
-    issue(0);
-    if (nvis > 1) issue(1);
-  }
-  double bv[K], lv[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) { bv[j] = 0.0; lv[j] = 0.0; }
-  if (lane == 0) bv[0] = __hiloint2double(LIN_TGT << 20, 0);     // virtual column before the first frame: all mass in front of node 0, at the target scale
+  eoff[K] = 0u;                                                  // the blank's word
+  L.nbv = 0.0;
+  if (lane == 0) L.bv[0] = __hiloint2double(LIN_TGT << 20, 0);   // virtual column before the first frame: all mass in front of node 0, at the target scale
   int acc = 1023 - LIN_TGT;                                      // log2 of the scale taken out of the column so far
   int danger = 0;
+  const int nvis = (Tb + LIN_EB - 1) / LIN_EB;
   int t = DIR == 0 ? 0 : Tb - 1;
   if (lane == 0) accrec[t >> 3] = acc;                           // scale of the rows up to the first check
-  const int src = (lane + 31) & 31;
-  const bool lane0 = lane == 0;
+  const uint32_t ebuf_a = smem_u32(ebuf), stage_a = smem_u32(stage);
+  int g = 0;                                                     // groups done
   for (int vi = 0; vi < nvis; ++vi) {
-    mbar_wait(smem_u32(&ebar[vi & 1]), (uint32_t)((vi >> 1) & 1));
-    const int rows = rows_of(blk_of(vi));
-    const uint32_t* erow = ebuf + ((size_t)(vi & 1) * LIN_EB + (DIR == 0 ? 0 : rows - 1)) * LP;
-    uint2* orow = reinterpret_cast<uint2*>(out_b + (int64_t)t * Smax) + lane;
-    for (int pos = 0; pos < rows; ++pos) {
-      const double pb = lin_hi2d(erow[0]);
-      double pl[K];
+    mbar_wait(smem_u32(&bars->efull[vi & 1]), (uint32_t)((vi >> 1) & 1));
+    const int blk = DIR == 0 ? vi : nvis - 1 - vi;
+    int rows = Tb - blk * LIN_EB; if (rows > LIN_EB) rows = LIN_EB;
+    int row = DIR == 0 ? 0 : rows - 1;                           // row of the block the next step reads
+    while (rows > 0) {
+      const int n = lin_group_len<DIR>(t, rows);
+      const bool aligned = DIR == 0 ? ((t + n - 1) & 7) == 7 : ((t - n + 1) & 7) == 0;
+      const int batch = g & 1;
+      if (g >= 2) mbar_wait(smem_u32(&bars->sempty[batch]), (uint32_t)(((g >> 1) - 1) & 1));   // the I/O warp has copied this buffer out
+      uint32_t eb[K + 1];
+      const uint32_t rowbase = ebuf_a + 4u * (uint32_t)(((vi & 1) * LIN_EB + row) * EPW);
 #pragma unroll
-      for (int j = 0; j < K; ++j) pl[j] = lin_hi2d(j == K - 1 ? (erow[lidx[j]] & lmask) : erow[lidx[j]]);
-      double prev[K];
+      for (int j = 0; j <= K; ++j) eb[j] = rowbase + eoff[j];
+      const uint32_t sa = stage_a + 4u * (uint32_t)(batch * LIN_ROWS * SP + 2 * K * lane);
+      constexpr int ESTEP = (DIR == 0 ? 4 : -4) * EPW;
+      double p[K + 1], pn[K + 1];
+      L.load_em(eb, 0, p);
+      if (n == LIN_ROWS) {
 #pragma unroll
-      for (int j = 0; j < K; ++j) prev[j] = lin_rot(lv[j], src);
+        for (int s2 = 0; s2 < LIN_ROWS; ++s2) {
+          if (s2 + 1 < LIN_ROWS) L.load_em(eb, (s2 + 1) * ESTEP, pn);    // one step ahead
+          L.step(p, sa + 4u * (uint32_t)(s2 * SP));
 #pragma unroll
-      for (int j = K - 1; j > 0; --j) prev[j] = lane0 ? prev[j - 1] : prev[j];
-      prev[0] = lane0 ? 0.0 : prev[0];
+          for (int j = 0; j <= K; ++j) p[j] = pn[j];
+        }
+      } else {
+        for (int s2 = 0; s2 < n; ++s2) {
+          if (s2 + 1 < n) L.load_em(eb, (s2 + 1) * ESTEP, pn);
+          L.step(p, sa + 4u * (uint32_t)(s2 * SP));
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const double sb = bv[j] + prev[j];
-        const double sl = fma(skipf[j], prev[j], lv[j] + bv[j]);
-        bv[j] = sb * pb;
-        lv[j] = sl * pl[j];
-        uint2 w;
-        w.x = (uint32_t)lin_hi(DIR == 0 ? bv[j] : sb);           // beta leaves without its frame's emission
-        w.y = (uint32_t)lin_hi(DIR == 0 ? lv[j] : sl);
-        if (j < K - 1) orow[32 * j] = w;
-        else if (vb_last) { w.y &= lmask; orow[32 * j] = w; }
+          for (int j = 0; j <= K; ++j) p[j] = pn[j];
+        }
       }
-      erow += DIR == 0 ? LP : -LP;
-      orow += DIR == 0 ? (Smax >> 1) : -(Smax >> 1);
-      const bool check = DIR == 0 ? ((t & (LIN_CHECK - 1)) == LIN_CHECK - 1) : ((t & (LIN_CHECK - 1)) == 0);
-      if (check) {
+      __syncwarp();
+      if (lane == 0) {
+        bars->meta[batch][0] = n; bars->meta[batch][1] = t;
+        mbar_arrive(smem_u32(&bars->sfull[batch]));              // release: the batch and its meta are visible to the I/O warp
+      }
+      if (aligned) {
         int m = 0;
 #pragma unroll
-        for (int j = 0; j < K; ++j) m = max(m, max(lin_hi(bv[j]), lin_hi(lv[j])));
+        for (int j = 0; j < K; ++j) m = max(m, max(lin_hi(L.bv[j]), lin_hi(L.lv[j])));
         m = __reduce_max_sync(0xffffffffu, m);
         const int e = m >> 20;
         if (e > 0) {
           if (e < LIN_DANGER) danger = 1;
           const int d = e - LIN_TGT;
           if (d > LIN_HYST || d < -LIN_HYST) {
+            auto rescale = [&](double v) -> double {
+              const int h = lin_hi(v);
+              return ((h >> 20) > 0 && (h >> 20) - d > 0) ? __hiloint2double(h - (d << 20), __double2loint(v)) : 0.0;
+            };
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-              const int hb = lin_hi(bv[j]), hl = lin_hi(lv[j]);
-              bv[j] = ((hb >> 20) > 0 && (hb >> 20) - d > 0) ? __hiloint2double(hb - (d << 20), __double2loint(bv[j])) : 0.0;
-              lv[j] = ((hl >> 20) > 0 && (hl >> 20) - d > 0) ? __hiloint2double(hl - (d << 20), __double2loint(lv[j])) : 0.0;
-            }
+            for (int j = 0; j < K; ++j) { L.bv[j] = rescale(L.bv[j]); L.lv[j] = rescale(L.lv[j]); }
+            L.nbv = rescale(L.nbv);
             acc += d;
           }
         }
         // rows of the next 8 frames in scan order carry this scale (alpha: frames t+1..t+8, beta: t-8..t-1)
-        if (lane0) { const int k = DIR == 0 ? (t >> 3) + 1 : (t >> 3) - 1; if (k >= 0) accrec[k] = acc; }
+        const int tl = DIR == 0 ? t + n - 1 : t - n + 1;
+        if (lane == 0) { const int k = DIR == 0 ? (tl >> 3) + 1 : (tl >> 3) - 1; if (k >= 0) accrec[k] = acc; }
       }
-      t += DIR == 0 ? 1 : -1;
+      row += DIR == 0 ? n : -n;
+      t += DIR == 0 ? n : -n;
+      rows -= n;
+      ++g;
     }
     __syncwarp();                                               // every lane is done with this visit's emission block
-    if (lane0 && vi + 2 < nvis) issue(vi + 2);
+    if (lane == 0) mbar_arrive(smem_u32(&bars->eempty[vi & 1]));
   }
   // likelihood from this direction: the last pair's blank and the label before it (both after their emission)
   double z = 0.0;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const int c = 32 * j + lane;
-    if (c == U) z += bv[j];
-    if (c == U - 1) z += lv[j];
+    const int c = K * lane + j;
+    if (c == U) z += L.bv[j];
+    if (c == U - 1) z += L.lv[j];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) z += lin_rot(z, lane ^ o);
-  if (lane0) {
+  if (lane == 0) {
     *zl2_out = z > 0.0 ? log2(z) + (double)acc : -INFINITY;
     *danger_out = danger;
   }
 }
 
+// the I/O warp: emission rows in (bulk async copies into the compile-time pitch), finished staging batches out
 template <int DIR>
 __device__ __forceinline__ void
-ctc_lin64_body(uint32_t* __restrict__ ebuf, uint64_t* ebar, const uint32_t* __restrict__ lplat,
+ctc_lin64_io(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars* bars, const uint32_t* __restrict__ lp_b,
+             int Tb, int U, int K, int LP, int Smax, float* __restrict__ out_b) {
+  const int lane = threadIdx.x & 31;
+  const int EPW = 32 * K + 4, SP = 64 * K;
+  const int nvis = (Tb + LIN_EB - 1) / LIN_EB;
+  const uint32_t erow_bytes = (uint32_t)((U + 2 + 3) & ~3) * 4u;       // blank, U labels, the zero word
+  const int rowchunks = (2 * U + 2 + 3) >> 2;                          // 16-byte chunks of an output row (nodes 0..2U, + the empty label slot)
+  auto issue = [&](int vi) {                                           // lane 0 only
+    const int blk = DIR == 0 ? vi : nvis - 1 - vi;
+    int rows = Tb - blk * LIN_EB; if (rows > LIN_EB) rows = LIN_EB;
+    const uint32_t bar = smem_u32(&bars->efull[vi & 1]);
+    mbar_expect_tx(bar, erow_bytes * (uint32_t)rows);
+    const uint32_t* src = lp_b + (int64_t)blk * LIN_EB * LP;
+    const uint32_t dst = smem_u32(ebuf + (size_t)(vi & 1) * LIN_EB * EPW);
+    for (int r = 0; r < rows; ++r) bulk_load_1d(dst + 4u * (uint32_t)(r * EPW), src + (int64_t)r * LP, erow_bytes, bar);
+  };
+  if (lane == 0) {
+    issue(0);
+    if (nvis > 1) issue(1);
+  }
+  int t = DIR == 0 ? 0 : Tb - 1;
+  int g = 0;
+  for (int vi = 0; vi < nvis; ++vi) {
+    const int blk = DIR == 0 ? vi : nvis - 1 - vi;
+    int rows = Tb - blk * LIN_EB; if (rows > LIN_EB) rows = LIN_EB;
+    while (rows > 0) {
+      const int n = lin_group_len<DIR>(t, rows);
+      const int batch = g & 1;
+      mbar_wait(smem_u32(&bars->sfull[batch]), (uint32_t)((g >> 1) & 1));
+      if (lane == 0) {
+        // the generic-proxy stores of the recursion warp -> the async proxy that reads them
+        fence_async_smem();
+        for (int r = 0; r < n; ++r)
+          bulk_store_1d(out_b + (int64_t)(DIR == 0 ? t + r : t - r) * Smax,
+                        smem_u32(stage + ((size_t)batch * LIN_ROWS + r) * SP), (uint32_t)rowchunks * 16u);
+        bulk_commit();
+        bulk_wait_read0();                                       // the copy engine has read the rows: the buffer is free
+        mbar_arrive(smem_u32(&bars->sempty[batch]));
+      }
+      t += DIR == 0 ? n : -n;
+      rows -= n;
+      ++g;
+    }
+    if (vi + 2 < nvis) {
+      mbar_wait(smem_u32(&bars->eempty[vi & 1]), (uint32_t)((vi >> 1) & 1));   // the recursion warp has left this emission block
+      if (lane == 0) issue(vi + 2);
+    }
+  }
+  if (lane == 0) bulk_wait0();                                   // every row is written before the CTA retires
+}
+
+template <int DIR>
+__device__ __forceinline__ void
+ctc_lin64_body(uint32_t* __restrict__ lin_sm, LinBars* bars, const uint32_t* __restrict__ lplat,
                const int64_t* __restrict__ targets, int64_t ldt,
                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                int Tn, int Umax, int LP, int Smax, float* __restrict__ alpha, float* __restrict__ beta,
                float* __restrict__ nll, CtcWs ws) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
   const int64_t U64 = tgt_lens[b];
   const bool bad_len = U64 < 0 || U64 > Umax;
   const int U = bad_len ? 0 : (int)U64;
-  if (lane == 0) { ws.danger[2 * b + DIR] = 0; if (DIR == 0) ws.lossy[b] = 0; }
+  if (tid == 0) { ws.danger[2 * b + DIR] = 0; if (DIR == 0) ws.lossy[b] = 0; }
   if (Tb <= 0 || bad_len) {
-    if (lane == 0) {
+    if (tid == 0) {
       const bool ok = !bad_len && U == 0;                        // no frames, no labels: probability one
       ws.zl2[2 * b + DIR] = ok ? 0.0 : -INFINITY;
       if (DIR == 0) nll[b] = ok ? 0.f : INFINITY;
     }
     return;
   }
-  if (lane == 0) {
-    mbar_init(smem_u32(&ebar[0]), 1);
-    mbar_init(smem_u32(&ebar[1]), 1);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->efull[i]), 1); mbar_init(smem_u32(&bars->eempty[i]), 1);
+      mbar_init(smem_u32(&bars->sfull[i]), 1); mbar_init(smem_u32(&bars->sempty[i]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
-  const int64_t* tg = targets + (int64_t)b * ldt;
+  __syncthreads();
+  const int K = (U + 32) >> 5;                                   // pairs per lane for this transcript
+  const int Kmax = (Umax + 32) >> 5;
+  uint32_t* ebuf = lin_sm;                                       // 2 emission blocks of LIN_EB rows, pitch 32K+4 words
+  uint32_t* stage = lin_sm + 2 * (size_t)LIN_EB * (32 * Kmax + 4);   // 2 staging batches of LIN_ROWS rows, pitch 64K words
   const uint32_t* lp_b = lplat + (int64_t)b * Tn * LP;
   float* out_b = (DIR == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
+  if (tid >= 32) {
+    ctc_lin64_io<DIR>(ebuf, stage, bars, lp_b, Tb, U, K, LP, Smax, out_b);
+    return;
+  }
+  const int64_t* tg = targets + (int64_t)b * ldt;
   int* accrec = ws.accs + (size_t)(2 * b + DIR) * ws.NT;
   double* zo = ws.zl2 + 2 * b + DIR;
   int* dg = ws.danger + 2 * b + DIR;
-#define SC_LIN_RUN(KK) ctc_lin64_run<KK, DIR>(ebuf, ebar, lp_b, tg, Tb, U, LP, Smax, out_b, accrec, zo, dg)
-  switch ((U + 32) >> 5) {                                       // pairs per lane for this transcript
+#define SC_LIN_RUN(KK) ctc_lin64_recursion<KK, DIR>(ebuf, stage, bars, tg, Tb, U, accrec, zo, dg)
+  switch (K) {
     case 1: SC_LIN_RUN(1); break;
     case 2: SC_LIN_RUN(2); break;
     case 3: SC_LIN_RUN(3); break;
@@ -307,18 +435,20 @@ ctc_lin64_body(uint32_t* __restrict__ ebuf, uint64_t* ebar, const uint32_t* __re
 #undef SC_LIN_RUN
 }
 
-__global__ void __launch_bounds__(32, 1)
+__global__ void __launch_bounds__(LIN_THREADS, 1)
 ctc_lin64_kernel(const uint32_t* __restrict__ lplat, const int64_t* __restrict__ targets, int64_t ldt,
                  const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                  int Tn, int Umax, int LP, int Smax, float* __restrict__ alpha, float* __restrict__ beta,
                  float* __restrict__ nll, CtcWs ws) {
-  extern __shared__ __align__(128) uint32_t lin_sm[];            // 2 emission blocks of LIN_EB x LP words
-  __shared__ __align__(8) uint64_t ebar[2];
-  if (blockIdx.y == 0) ctc_lin64_body<0>(lin_sm, ebar, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
-  else ctc_lin64_body<1>(lin_sm, ebar, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
+  extern __shared__ __align__(128) uint32_t lin_sm[];
+  __shared__ __align__(8) LinBars bars;
+  if (blockIdx.y == 0) ctc_lin64_body<0>(lin_sm, &bars, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
+  else ctc_lin64_body<1>(lin_sm, &bars, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
 }
 
-// one block per utterance: likelihood, and whether fp64 held everything (see the header of this file)
+// likelihood, and whether fp64 held everything (see the header of this file).  grid (B, 1 + samples/4): block
+// (b, 0) does the per-utterance part (a), (b) and writes nll[b]; the warps of the other blocks take one sampled
+// frame each for (c).  lossy[b] was zeroed by the lattice kernel; problems are OR-ed in.
 constexpr int LIN_CHECK_THREADS = 128;
 __global__ void __launch_bounds__(LIN_CHECK_THREADS)
 ctc_lin64_check_kernel(const float* __restrict__ cshift, const int64_t* __restrict__ in_lens,
@@ -326,7 +456,6 @@ ctc_lin64_check_kernel(const float* __restrict__ cshift, const int64_t* __restri
                        const float* __restrict__ alpha, const float* __restrict__ beta,
                        float* __restrict__ nll, CtcWs ws) {
   __shared__ double dred[LIN_CHECK_THREADS / 32];
-  __shared__ int bad[LIN_CHECK_THREADS / 32];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
@@ -334,57 +463,64 @@ ctc_lin64_check_kernel(const float* __restrict__ cshift, const int64_t* __restri
   if (Tb <= 0 || U64 < 0 || U64 > Umax) return;                  // nll already final, lossy[b] = 0
   const int U = (int)U64;
   const double za = ws.zl2[2 * b], zb = ws.zl2[2 * b + 1];
-  double ssum = 0.0;
-  const float* cs = cshift + (int64_t)b * Tn;
-  for (int t = threadIdx.x; t < Tb; t += LIN_CHECK_THREADS) ssum += (double)cs[t];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ssum += lin_rot(ssum, lane ^ o);
-  int lossy = (ws.danger[2 * b] | ws.danger[2 * b + 1] | force_lossy) ? 1 : 0;
   const bool fa = za > -INFINITY, fb = zb > -INFINITY;
-  if (fa != fb) lossy = 1;
-  if (fa && fb) {
-    if (fabs(za - zb) > 1e-6) lossy = 1;                         // (b) both directions must see the same likelihood
-    // (c) sum_s alpha_t(s) beta_t(s) at sampled frames, from the stored words
-    const int* aa = ws.accs + (size_t)(2 * b) * ws.NT;
-    const int* ab = ws.accs + (size_t)(2 * b + 1) * ws.NT;
-    for (int t = LIN_SAMPLE / 2 - 1 + LIN_SAMPLE * warp; t < Tb; t += LIN_SAMPLE * (LIN_CHECK_THREADS / 32)) {
-      const uint2* aw = reinterpret_cast<const uint2*>(alpha + ((int64_t)b * Tn + t) * Smax);
-      const uint32_t* bw = reinterpret_cast<const uint32_t*>(beta + ((int64_t)b * Tn + t) * Smax);
-      int emax = -1;
-      for (int u = lane; u <= U; u += 32) {
-        const uint2 a = aw[u];
-        const uint32_t cb = bw[2 * (U - u)];
-        if (a.x != 0u && cb != 0u) emax = max(emax, (int)(a.x >> 20) + (int)(cb >> 20));
-        if (u < U) { const uint32_t cl = bw[2 * (U - u) - 1]; if (a.y != 0u && cl != 0u) emax = max(emax, (int)(a.y >> 20) + (int)(cl >> 20)); }
-      }
-      emax = __reduce_max_sync(0xffffffffu, emax);
-      double acc = 0.0;
-      auto term = [&](uint32_t x, uint32_t y) -> double {
-        if (x == 0u || y == 0u) return 0.0;
-        const int d = (int)(x >> 20) + (int)(y >> 20) - emax;
-        if (d < -60) return 0.0;
-        return __hiloint2double((int)(0x3ff00000u | (x & 0xfffffu)), 0) * __hiloint2double((int)(0x3ff00000u | (y & 0xfffffu)), 0) *
-               __hiloint2double((1023 + d) << 20, 0);
-      };
-      for (int u = lane; u <= U; u += 32) {
-        const uint2 a = aw[u];
-        acc += term(a.x, bw[2 * (U - u)]);
-        if (u < U) acc += term(a.y, bw[2 * (U - u) - 1]);
-      }
+  if (blockIdx.y == 0) {
+    double ssum = 0.0;
+    const float* cs = cshift + (int64_t)b * Tn;
+    for (int t = threadIdx.x; t < Tb; t += LIN_CHECK_THREADS) ssum += (double)cs[t];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += lin_rot(acc, lane ^ o);
-      const double zt = emax >= 0 ? log2(acc) + (double)(emax - 2046) + (double)aa[t >> 3] + (double)ab[t >> 3] : -INFINITY;
-      if (!(fabs(zt - za) <= 1e-4)) lossy = 1;
+    for (int o = 16; o > 0; o >>= 1) ssum += lin_rot(ssum, lane ^ o);
+    if (lane == 0) dred[warp] = ssum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < LIN_CHECK_THREADS / 32; ++w) tot += dred[w];
+      int lossy = (ws.danger[2 * b] | ws.danger[2 * b + 1] | force_lossy) ? 1 : 0;       // (a)
+      if (fa != fb || (fa && fabs(za - zb) > 1e-6)) lossy = 1;                            // (b) both directions must see the same likelihood
+      if (lossy) atomicOr(ws.lossy + b, 1);
+      nll[b] = fa ? (float)(-(za + tot) * 0.6931471805599453) : INFINITY;                 // recomputed later if the utterance ends up flagged
+    }
+    return;
+  }
+  // (c) sum_s alpha_t(s) beta_t(s) at a sampled frame, from the stored words
+  if (!(fa && fb)) return;
+  const int t = LIN_SAMPLE / 2 - 1 + LIN_SAMPLE * ((blockIdx.y - 1) * (LIN_CHECK_THREADS / 32) + warp);
+  if (t >= Tb) return;
+  const uint2* aw = reinterpret_cast<const uint2*>(alpha + ((int64_t)b * Tn + t) * Smax);
+  const uint32_t* bw = reinterpret_cast<const uint32_t*>(beta + ((int64_t)b * Tn + t) * Smax);
+  constexpr int NPC = LIN_MAXK;                                  // pairs per lane (U <= 32*LIN_MAXK - 1)
+  uint32_t wa[NPC], wl[NPC], xb[NPC], xl[NPC];
+  int emax = -1;
+#pragma unroll
+  for (int k = 0; k < NPC; ++k) {
+    const int u = lane + 32 * k;
+    wa[k] = 0u; wl[k] = 0u; xb[k] = 0u; xl[k] = 0u;
+    if (u <= U) {
+      const uint2 a = aw[u];
+      wa[k] = a.x; wl[k] = a.y;
+      xb[k] = bw[2 * (U - u)];
+      if (u < U) xl[k] = bw[2 * (U - u) - 1];
+      if (wa[k] != 0u && xb[k] != 0u) emax = max(emax, (int)(wa[k] >> 20) + (int)(xb[k] >> 20));
+      if (wl[k] != 0u && xl[k] != 0u) emax = max(emax, (int)(wl[k] >> 20) + (int)(xl[k] >> 20));
     }
   }
-  if (lane == 0) { dred[warp] = ssum; bad[warp] = lossy; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int w = 0; w < LIN_CHECK_THREADS / 32; ++w) { tot += dred[w]; lossy |= bad[w]; }
-    ws.lossy[b] = lossy;
-    if (!lossy) nll[b] = fa ? (float)(-(za + tot) * 0.6931471805599453) : INFINITY;
-  }
+  emax = __reduce_max_sync(0xffffffffu, emax);
+  auto term = [&](uint32_t x, uint32_t y) -> double {
+    if (x == 0u || y == 0u) return 0.0;
+    const int d = (int)(x >> 20) + (int)(y >> 20) - emax;
+    if (d < -60) return 0.0;
+    return __hiloint2double((int)(0x3ff00000u | (x & 0xfffffu)), 0) * __hiloint2double((int)(0x3ff00000u | (y & 0xfffffu)), 0) *
+           __hiloint2double((1023 + d) << 20, 0);
+  };
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < NPC; ++k) acc += term(wa[k], xb[k]) + term(wl[k], xl[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += lin_rot(acc, lane ^ o);
+  const int* aa = ws.accs + (size_t)(2 * b) * ws.NT;
+  const int* ab = ws.accs + (size_t)(2 * b + 1) * ws.NT;
+  const double zt = emax >= 0 ? log2(acc) + (double)(emax - 2046) + (double)aa[t >> 3] + (double)ab[t >> 3] : -INFINITY;
+  if (lane == 0 && !(fabs(zt - za) <= 1e-4)) atomicOr(ws.lossy + b, 1);
 }
 
 }  // namespace sc

