@@ -229,12 +229,10 @@ def cpu_reference_run(W, workload, layer_norm, steps, warmup):
         _, state = run(warmup, state)
     dt, _ = run(steps, state)
     fps = S["B"] * S["T"] * steps / dt
-    src = ("unmodified /root/reference/lucyrnn.py LucyRNN(kernel_impl='native')" if kind == "reference" else
-           "oracle/lucy_oracle.forward_looped_as_timed (reference loop + slice-assign structure, lucyrnn.py:109-170; "
-           "the reference tree is not mounted on this box)")
-    sample = (f"{W['L']}x{W['H']} V={W['V']} fp32 fused_ops=True layer_norm={layer_norm}, fixed shape B={S['B']} T={S['T']} "
-              f"U in [{S['umin']},{S['umax']}], {steps} timed step(s) with carried state after {warmup} warm-up; "
-              f"os.cpu_count()={os.cpu_count()} torch threads={cores}; {src} + nn.CTCLoss + backward")
+    src = ("unmodified /root/reference/lucyrnn.py LucyRNN(native)" if kind == "reference" else
+           "oracle.forward_looped_as_timed (reference loop + slice-assign structure, lucyrnn.py:109-170; reference tree not mounted here)")
+    sample = (f"{W['L']}x{W['H']} V={W['V']} fp32 LN={layer_norm}, fixed B={S['B']} T={S['T']} U in [{S['umin']},{S['umax']}], "
+              f"{steps} step(s) carried state, {warmup} warm-up; cpu_count={os.cpu_count()} threads={cores}; {src} + nn.CTCLoss + backward")
     return fps, cores, kind, sample, dt / steps * 1e3
 
 
@@ -279,8 +277,9 @@ def workload_config(args, W, world):
             "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
             "cuda_graph": bool(getattr(args, "graph", False)) and bool(W.get("forward_only")),
             "dp_allreduce": None if world == 1 else (
-                "bucketed, overlapped with backward" if os.environ.get("SC_DP_OVERLAP", "1") != "0"
-                else "bucketed, launched after backward"),
+                ("bucketed, overlapped with backward" if os.environ.get("SC_DP_OVERLAP", "0") == "1"
+                 else "one flat buffer, after backward") +
+                (", bf16 payload" if W["dtype"] == "bf16" and os.environ.get("SC_DP_GRAD", "bf16").lower() == "bf16" else ", fp32 payload")),
             "l2_policy": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2",
             "optimizer": "excluded (SURVEY.md 8d); zero_grad included"}
 
@@ -321,7 +320,10 @@ def main():
                                 vocab_size=W["V"], chunk_frames=64, compute_dtype=cd,
                                 keep_blocks={"auto": None, "0": False, "1": True}[args.rnnt_keep]).to(dev)
         full = torch.nn.ModuleDict({"enc": enc, "head": head})
-    model = StreamDataParallel(enc) if world > 1 else enc
+    # gradient exchange: one flat buffer, after the backward; bf16 payload for the bf16 workloads (fp32 master gradients),
+    # SC_DP_GRAD=f32 / SC_DP_OVERLAP=1 select the other variants for A/B runs
+    dp_bf16 = cd == torch.bfloat16 and os.environ.get("SC_DP_GRAD", "bf16").lower() == "bf16"
+    model = StreamDataParallel(enc, grad_dtype=torch.bfloat16 if dp_bf16 else None) if world > 1 else enc
 
     # a few distinct synthetic segments per rank, cycled (streams of this rank: seed by rank)
     NSEG = 2
@@ -534,9 +536,6 @@ def main():
             if v and k in tr:
                 v["traffic"] = tr[k]
     roofs = {k: v for k, v in roofs.items() if v}
-    if "ctc_lattice" in roofs:
-        roofs["ctc_lattice"]["note"] = ("alpha/beta recursions: T serial log-sum-exp steps per utterance, "
-                                        "latency-bound by construction (SURVEY.md 8d); GB/s shown for completeness")
     dominant = max((k for k in roofs if not k.startswith("ctc_")), key=lambda k: roofs[k]["ms_per_step"]) if roofs else None
     roofline = dict(roofs[dominant], kernel=dominant) if dominant else None
 
@@ -547,6 +546,12 @@ def main():
         fps, cores, kind, sample, _ = cpu_reference_run(W, args.workload, bool(args.layer_norm), nst, 0)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
 
+    # compact per-kernel table (the driver keeps only the last ~1500 characters of the line: the roofline numbers and the
+    # CPU baseline go LAST; long descriptions go first)
+    def compact(v):
+        return {"bound": v["bound"], "achieved": round(v["achieved"], 1), "peak": v["peak"], "unit": v["unit"],
+                "frac": round(v["frac"], 4), "ms_per_step": round(v["ms_per_step"], 4),
+                "launches_per_step": v["launches_per_step"], "traffic": v.get("traffic")}
     line = {
         "metric": "forward_frames_per_sec" if fwd_only else "train_frames_per_sec", "value": value, "unit": "frames/s",
         "n_gpus": world,
@@ -554,18 +559,18 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": W["dtype"], "data": "synthetic",
         "config": workload_config(args, W, world),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
-        "host_enqueue_ms_per_step": host_enqueue_ms,
-        "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
-        "optimizer": {"kind": "FusedAdam (AdamW + fused global-norm clip at 50, no host sync)", "ms_per_step": ms_opt,
+        "optimizer": {"kind": "FusedAdam multi-tensor (AdamW + fused global-norm clip at 50, no host sync)", "ms_per_step": ms_opt,
                       "included_in_value": False},
         "frontend": fe_info,
-        "roofline": roofline,
-        "roofline_by_kernel": roofs,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
+        "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
         "cpu_baseline": cpu,
+        "roofline": roofline,
+        "roofline_by_kernel": {k: compact(v) for k, v in roofs.items()},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

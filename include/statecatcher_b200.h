@@ -316,6 +316,16 @@ int sc_adam_step_multi(float* const* p, const float* const* g, float* const* m, 
 int sc_lion_step_multi(float* const* p, const float* const* g, float* const* m, const int64_t* n,
                        int64_t count, float lr, float beta1, float beta2, float weight_decay,
                        const double* sumsq, float max_norm, void* stream);
+/* Data-parallel gradient exchange (reference: none — train.py is single-process): pack the fp32
+ * gradients of a bucket into their slices of ONE flat communication buffer (flat_dtype SC_F32, or SC_BF16 = half
+ * the NVLink payload of the all-reduce) and, after the collective, the reverse with the averaging factor
+ * (g = scale * slice).  g, flat_slices and n are HOST arrays of device pointers / element counts (one launch per
+ * 32 tensors, like the optimizer's multi-tensor calls); a slice must be aligned to its element size. */
+int sc_grads_pack_multi(const float* const* g, void* const* flat_slices, const int64_t* n, int64_t count,
+                        int flat_dtype, void* stream);
+int sc_grads_unpack_multi(float* const* g, const void* const* flat_slices, const int64_t* n, int64_t count,
+                          int flat_dtype, float scale, void* stream);
+
 
 /* ---------------------------------------------------------------- frontend ------------
  * Replaces make_frontend (model.py:250-279): torchaudio MFCC(n_mfcc=80, dct_type=2, norm='ortho',

@@ -65,6 +65,8 @@ SIGNATURES = {
     "sc_sumsq_accum_multi": [P, P, I64, P, P],
     "sc_adam_step_multi": [P, P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P, F32, I32, P],
     "sc_lion_step_multi": [P, P, P, P, I64, F32, F32, F32, F32, P, F32, P],
+    "sc_grads_pack_multi": [P, P, P, I64, I32, P],
+    "sc_grads_unpack_multi": [P, P, P, I64, I32, F32, P],
     "sc_frontend_tables_len": [],
     "sc_frontend_tables": [P, I64, I32],
     "sc_frontend": [P, I64, I64, I64, P, I32, F32, P, I64, P, I64, P, P],

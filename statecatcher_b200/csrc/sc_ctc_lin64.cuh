@@ -111,19 +111,23 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
     if (U64 < 0 || U64 > Umax) continue;                         // invalid length: the lattice pass reports the utterance infeasible
     const int U = (int)U64;
     const T* x = logits + b * stride_b + t * stride_t;
+    const int64_t* tg = targets + (int64_t)b * ldt;
+    int64_t lab[NL];                                             // requested before the V-wide pass: their latency hides under it
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int idx = lane + 32 * k;                             // 0 = blank, 1 + u = label u
+      lab[k] = (idx >= 1 && idx <= U) ? tg[idx - 1] : blank;
+    }
     const float l = warp_row_lse<T>(x, V, lane);
     if (lane == 0) lse[row] = l;
-    const int64_t* tg = targets + (int64_t)b * ldt;
     uint32_t* out = lplat + (int64_t)row * LP;
     float e[NL];
     float c = -INFINITY;
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
-      const int idx = lane + 32 * k;                             // 0 = blank, 1 + u = label u
       e[k] = -INFINITY;
-      if (idx <= U) {
-        const int64_t lab = idx == 0 ? blank : tg[idx - 1];
-        if (lab >= 0 && lab < V) e[k] = (ld_f(x + lab) - l) * 1.4426950408889634f;   // a label outside the vocabulary is probability zero
+      if (lane + 32 * k <= U) {
+        if (lab[k] >= 0 && lab[k] < V) e[k] = (ld_f(x + lab[k]) - l) * 1.4426950408889634f;   // a label outside the vocabulary is probability zero
         c = fmaxf(c, e[k]);
       }
     }

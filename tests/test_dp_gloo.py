@@ -49,15 +49,19 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
         cfg = LO.OracleConfig(input_dim=6, hidden_dim=8, num_layers=2, vocab_size=7, fused_ops=False, layer_norm=True)
         net = _OracleNet(cfg, 5)
-        ddp = StreamDataParallel(net, bucket_mb=0.0005)            # tiny buckets -> several all-reduces
-        assert len(ddp.buckets) > 3
+        if overlap:
+            ddp = StreamDataParallel(net, bucket_mb=0.0005, overlap=True)   # tiny buckets -> several all-reduces, launched from hooks
+            assert len(ddp.buckets) > 3
+        else:
+            ddp = StreamDataParallel(net)                          # default: one flat buffer, exchanged after the backward
+            assert len(ddp.buckets) == 1 and not ddp.overlap
         g = torch.Generator().manual_seed(11)
         B, T = 4, 9                                                # global batch: 4 streams, 2 per rank
         xs = [torch.randn(B, T, 6, generator=g, dtype=torch.float64) for _ in range(2)]
@@ -73,7 +77,7 @@ def _worker(rank, world, port, out):
             logits, state = ddp(xs[i][sl], state)
             loss = crit(logits.log_softmax(-1).transpose(0, 1), toks[i][sl], inl[sl], tgl[sl])
             loss.backward()                                        # grads accumulate over segments
-        assert ddp.n_allreduce >= 3
+        assert ddp.n_allreduce >= 3 if overlap else ddp.n_allreduce == 1
         grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in zip(net.names, net.params)}
         # no_sync: local accumulation only
         for p in net.params:
@@ -88,9 +92,10 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_stream_data_parallel_matches_single_process(tmp_path):
+@pytest.mark.parametrize("overlap", [False, True], ids=["after-backward", "hook-overlapped"])
+def test_stream_data_parallel_matches_single_process(tmp_path, overlap):
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, overlap), nprocs=2, join=True)
     got = torch.load(out)
     # single process over the concatenated batch (reduction='mean' over the GLOBAL batch)
     cfg = LO.OracleConfig(input_dim=6, hidden_dim=8, num_layers=2, vocab_size=7, fused_ops=False, layer_norm=True)

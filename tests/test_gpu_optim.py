@@ -47,3 +47,27 @@ def test_standalone_clip(cuda_device):
     before = ps[1].grad.clone()
     clip_grad_norm_(ps, 1e9)                               # no-op branch: bit-exact
     assert torch.equal(ps[1].grad, before)
+
+
+@pytest.mark.parametrize("flat_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_grads_pack_unpack_multi(cuda_device, flat_dtype):
+    """sc_grads_pack_multi / sc_grads_unpack_multi (the flat communication buffer of dp.StreamDataParallel): 40 tensors
+    (two launches of <= 32), odd sizes, slices on 16-byte boundaries; pack == torch cast, unpack == scale * slice."""
+    import ctypes
+    from statecatcher_b200 import _lib
+    from statecatcher_b200.dp import _aligned_offsets
+    from statecatcher_b200.optim import _counts, _table
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 8, 9, 1000, 4097] * 6 + [33, 65537, 12, 5]
+    grads = [torch.randn(n, generator=g).cuda() for n in sizes]
+    offs, total = _aligned_offsets(grads)
+    flat = torch.full((total,), 7.0, dtype=flat_dtype, device="cuda")
+    esz = flat.element_size()
+    slices = (ctypes.c_void_p * len(grads))(*[flat.data_ptr() + o * esz for o in offs])
+    _lib.call("sc_grads_pack_multi", _table(grads), slices, _counts(grads), len(grads), _lib.dt(flat), _lib.stream())
+    for gr, o in zip(grads, offs):
+        assert torch.equal(flat[o:o + gr.numel()], gr.to(flat_dtype))
+    out = [torch.zeros_like(gr) for gr in grads]
+    _lib.call("sc_grads_unpack_multi", _table(out), slices, _counts(out), len(out), _lib.dt(flat), 0.125, _lib.stream())
+    for gr, o2 in zip(grads, out):
+        assert torch.equal(o2, gr.to(flat_dtype).float() * 0.125)

@@ -7,10 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SC_RUN_EXPERIMENTAL") != "1",
-                                 reason="written after round 1's GPU budget was spent, not yet run on a B200: "
-                                        "set SC_RUN_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("wd", [0.0, 0.1])

@@ -1,16 +1,12 @@
 """GPU: GraphedTrainStep (whole training step replayed from one CUDA graph) against the eager step over
-carried segments: loss, every parameter gradient and the carried state.  (Written after round 1's GPU budget
-was spent; sorted last so that a failure cannot mask the measured tests under -x.)"""
+carried segments: loss, every parameter gradient and the carried state.  (Green on a B200 since r02.)"""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SC_RUN_EXPERIMENTAL") != "1",
-                                 reason="written after round 1's GPU budget was spent, not yet run on a B200: "
-                                        "set SC_RUN_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _segments(n, B, T, F, V, U, seed=0):

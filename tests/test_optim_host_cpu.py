@@ -33,7 +33,8 @@ def test_per_tensor_calls(recorder, cls):
     from statecatcher_b200.optim import FusedAdam, Lion
     ps = _params()
     ps[3].grad = None                                      # a parameter without gradient is skipped
-    opt = FusedAdam(ps, max_grad_norm=50.0) if cls == "adam" else Lion(ps, max_grad_norm=50.0)
+    opt = (FusedAdam(ps, max_grad_norm=50.0, multi_tensor=False) if cls == "adam"
+           else Lion(ps, max_grad_norm=50.0, multi_tensor=False))
     opt.step()
     names = [c[0] for c in recorder]
     assert names == ["sc_sumsq_accum"] * 4 + ["sc_adam_step" if cls == "adam" else "sc_lion_step"] * 4
@@ -129,7 +130,7 @@ def test_gradscaler_drives_the_fused_optimizers(recorder, cls):
     assert torch.equal(p.grad, torch.full((6,), 2.0))
     scaler.step(opt)
     scaler.update()
-    assert [c[0] for c in recorder][-1] == ("sc_adam_step" if cls == "adam" else "sc_lion_step")
+    assert [c[0] for c in recorder][-1] == ("sc_adam_step_multi" if cls == "adam" else "sc_lion_step_multi")   # multi-tensor is the default
     recorder.clear()
     opt.zero_grad()
     scaler.scale((p * float("inf")).sum()).backward()
