@@ -602,32 +602,6 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
   // (beta carries no emission; per-frame offsets from re-centring cancel in the normalisation)
   const float2* al2 = reinterpret_cast<const float2*>(alpha + (int64_t)row * Smax);
   const float2* be2 = reinterpret_cast<const float2*>(beta + (int64_t)row * Smax);
-  // The lattice words of the frame and the labels they scatter to are requested BEFORE the V-wide softmax pass, so
-  // their latency hides under it (the kernel is bound by exposed load latency, not by bandwidth: ncu r02,
-  // long-scoreboard stalls 14 per issue at 46 % of DRAM peak).  Raw 32-bit words: alpha (blank, label), beta (blank, label).
-  uint32_t qa[NP > 0 ? NP : 1], ql[NP > 0 ? NP : 1], qb[NP > 0 ? NP : 1], qc[NP > 0 ? NP : 1];
-  int labs[NP > 0 ? NP : 1];
-  if (NP > 0) {
-    const uint2* aw = reinterpret_cast<const uint2*>(al2);
-    const uint32_t* bw = reinterpret_cast<const uint32_t*>(be2);
-#pragma unroll
-    for (int kk = 0; kk < NP; ++kk) {
-      const int u = lane + 32 * kk;
-      qa[kk] = 0u; ql[kk] = 0u; qb[kk] = 0u; qc[kk] = 0u; labs[kk] = 0;
-      if (u <= U) {
-        const uint2 a = __ldg(aw + u);
-        qa[kk] = a.x; ql[kk] = a.y;
-        if (lin) {                                    // beta row mirrored: node s at 2U - s
-          qb[kk] = __ldg(bw + 2 * (U - u));
-          if (u < U) qc[kk] = __ldg(bw + 2 * (U - u) - 1);
-        } else {
-          const uint2 c = __ldg(reinterpret_cast<const uint2*>(be2) + u);
-          qb[kk] = c.x; qc[kk] = c.y;
-        }
-        if (u < U) labs[kk] = (int)tg[u];
-      }
-    }
-  }
   const float l2 = lse[row] * LOG2E;
   // softmax row -> shared memory
   if ((V % VWI == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
@@ -651,6 +625,8 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
       // linear-domain rows (sc_ctc_lin64.cuh): each node is the high word of an fp64 value, alpha at its node
       // index, beta at the mirrored one.  occupancy ~ alpha*beta: exponent fields add, 20-bit mantissas multiply;
       // the frame's largest exponent sum is the common scale (per-column scale factors cancel with it).
+      const uint2* aw = reinterpret_cast<const uint2*>(al2);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(be2);
       int eb_[NP > 0 ? NP : 1], el_[NP > 0 ? NP : 1];
       int emax = -1;
       auto mant = [](uint32_t w) -> float { return __uint_as_float(0x3f800000u | ((w & 0xfffffu) << 3)); };
@@ -659,8 +635,13 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
         const int u = lane + 32 * kk;
         eb_[kk] = -1; el_[kk] = -1; wb[kk] = 0.f; wl[kk] = 0.f;
         if (u <= U) {
-          if (qa[kk] != 0u && qb[kk] != 0u) { eb_[kk] = (int)(qa[kk] >> 20) + (int)(qb[kk] >> 20); wb[kk] = mant(qa[kk]) * mant(qb[kk]); }
-          if (u < U && ql[kk] != 0u && qc[kk] != 0u) { el_[kk] = (int)(ql[kk] >> 20) + (int)(qc[kk] >> 20); wl[kk] = mant(ql[kk]) * mant(qc[kk]); }
+          const uint2 a = __ldg(aw + u);
+          const uint32_t cb = __ldg(bw + 2 * (U - u));           // beta row mirrored: node s at 2U - s
+          if (a.x != 0u && cb != 0u) { eb_[kk] = (int)(a.x >> 20) + (int)(cb >> 20); wb[kk] = mant(a.x) * mant(cb); }
+          if (u < U) {
+            const uint32_t cl = __ldg(bw + 2 * (U - u) - 1);
+            if (a.y != 0u && cl != 0u) { el_[kk] = (int)(a.y >> 20) + (int)(cl >> 20); wl[kk] = mant(a.y) * mant(cl); }
+          }
         }
         emax = max(emax, max(eb_[kk], el_[kk]));
       }
@@ -679,8 +660,9 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
         const int u = lane + 32 * kk;
         wb[kk] = CTC_DEAD; wl[kk] = CTC_DEAD;
         if (u <= U) {
-          wb[kk] = __uint_as_float(qa[kk]) + __uint_as_float(qb[kk]);
-          if (u < U) wl[kk] = __uint_as_float(ql[kk]) + __uint_as_float(qc[kk]);
+          const float2 a = __ldg(al2 + u), c = __ldg(be2 + u);
+          wb[kk] = a.x + c.x;
+          if (u < U) wl[kk] = a.y + c.y;
         }
         vmax = fmaxf(vmax, fmaxf(wb[kk], wl[kk]));
       }
@@ -702,7 +684,7 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
     for (int kk = 0; kk < NP; ++kk) {
       const int u = lane + 32 * kk;
       bsum += wb[kk] * inv;
-      if (u < U) atomicAdd(r + labs[kk], -wl[kk] * inv);
+      if (u < U) atomicAdd(r + tg[u], -wl[kk] * inv);
     }
   } else {
     for (int u = lane; u <= U; u += 32) {
