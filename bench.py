@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--rnnt-keep", choices=["auto", "0", "1"], default="auto",
                     help="cfg4: keep every block's joint/logits in HBM for the backward (1), recompute (0), or decide by free memory")
     ap.add_argument("--graph", action="store_true",
-                    help="forward-only workloads: replay each segment from a CUDA graph (GraphedStreamingEncoder)")
+                    help="replay each step from a CUDA graph: GraphedStreamingEncoder (forward-only workloads) / "
+                         "GraphedTrainStep (CTC training workloads, single GPU)")
     ap.add_argument("--detail", action="store_true", help="per-call timing table of the last timed step on stderr")
     return ap.parse_args()
 
@@ -275,7 +276,7 @@ def workload_config(args, W, world):
                         f"({_config_label(args, W, world)})",
             "fused_ops": True, "layer_norm": bool(args.layer_norm), "is_training": not W.get("forward_only", False),
             "streams_per_gpu": W["B"], "frames_per_segment": W["T"], "parallelism": f"dp{world} by stream",
-            "cuda_graph": bool(getattr(args, "graph", False)) and bool(W.get("forward_only")),
+            "cuda_graph": bool(getattr(args, "graph", False)) and (bool(W.get("forward_only")) or ("rnnt" not in W and world == 1)),
             "dp_allreduce": None if world == 1 else (
                 ("bucketed, overlapped with backward" if os.environ.get("SC_DP_OVERLAP", "0") == "1"
                  else "one flat buffer, after backward") +
@@ -338,9 +339,19 @@ def main():
     state = {"s": None}
 
     runner = sb.GraphedStreamingEncoder(enc, W["B"], W["T"], W["F"], dev) if (fwd_only and args.graph) else None
+    # --graph on a CTC training workload (single GPU): the whole step — carried state in, forward, fused CTC, backward,
+    # carried state out — replayed from ONE CUDA graph (glue.GraphedTrainStep); what configs[0] needs, where a step is a
+    # chain of a few hundred launches of a few microseconds each
+    trainer = None
+    if args.graph and not fwd_only and head is None and world == 1:
+        k0 = _lib.kernels
+        trainer = sb.GraphedTrainStep(enc, W["B"], W["T"], W["F"], max_labels=W["umax"])
+        kernels_per_replay = (_lib.kernels - k0) // 4          # 3 warm-up steps + the captured one
 
     def step_resident(i):
         j = i % NSEG
+        if trainer is not None:
+            return trainer.step(xd[j], tokd[j], inld[j], tgld[j])
         if runner is not None:                                  # whole segment replayed from one CUDA graph
             return runner.step(xd[j])
         if fwd_only:                                            # streaming inference: step path, no autograd
@@ -372,6 +383,8 @@ def main():
         if feeder["it"] is None:
             feeder["it"] = sb.SegmentPrefetcher(host_batches(), dev)
         xbuf, tokbuf, inl, tgl = next(feeder["it"])                           # H2D features + labels from pinned host
+        if trainer is not None:
+            return trainer.step(xbuf, tokbuf, inl, tgl).item()      # list lengths -> H2D inside step(); D2H loss read
         if runner is not None:
             return runner.step(xbuf)[:, -1, :8].float().cpu()       # D2H read of a result slice
         if fwd_only:
@@ -424,7 +437,7 @@ def main():
     _lib.profile = []
     ms = timed(step_resident, args.steps)
     prof, _lib.profile = _lib.profile, None
-    launches = _lib.kernels
+    launches = _lib.kernels if trainer is None else kernels_per_replay * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = frames_step * world * args.steps / (ms * 1e-3)
     # host cost of ENQUEUEING one step, measured on an empty launch queue (inside the timed loop the

@@ -91,6 +91,15 @@ int sc_cast(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd,
  * the bf16 tensor-core GEMM without losing the low mantissa bits (projection folding). */
 int sc_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols,
                   void* stream);
+/* fp32 [rows, cols] -> six bf16 blocks out of {hi, mid, lo} (x = hi + mid + lo to 2^-25 |x|) for the tensor-core
+ * evaluation of an fp32 product — a.w = a_hi w_hi + a_hi w_mid + a_mid w_hi + a_hi w_lo + a_mid w_mid + a_lo w_hi as ONE
+ * bf16 GEMM with fp32 accumulation over a six-fold reduction dimension; what replaces the fp32 cuBLAS GEMMs of nn.Linear
+ * (lucyrnn.py:113-116, 186) on the fp32 path.  pattern 0 = [lo hi mid mid hi hi] (left operand), 1 = [hi lo mid hi mid hi]
+ * (right operand; products in ascending magnitude, the tensor core truncates when it accumulates).  block_stride = element offset between consecutive blocks in dst: `cols` for blocks side by side
+ * (ldd >= 6*cols), `rows*ldd` for blocks stacked vertically. */
+int sc_split6_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols,
+                   int pattern, int64_t block_stride, void* stream);
+
 int sc_colsum(const void* X, int64_t ldx, int dtype, float* out, int64_t M, int64_t N,
               int accumulate, void* stream);
 int sc_layernorm_fwd(const void* X, int64_t ldx, const float* w, const float* b,

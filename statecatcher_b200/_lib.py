@@ -32,6 +32,7 @@ SIGNATURES = {
     "sc_gemm_workspace_bytes": [I64, I64, I64],
     "sc_cast": [P, I64, I32, P, I64, I32, I64, I64, P],
     "sc_split_bf16": [P, I64, P, I64, I64, I64, P],
+    "sc_split6_bf16": [P, I64, P, I64, I64, I64, I32, I64, P],
     "sc_colsum": [P, I64, I32, P, I64, I64, I32, P],
     "sc_layernorm_fwd": [P, I64, P, P, P, I64, P, P, I64, I64, I32, P],
     "sc_layernorm_bwd": [P, I64, P, I64, P, P, P, P, I64, P, P, I64, I64, I32, P],

@@ -9,10 +9,10 @@ int simt_gemm_dgrad(const void*, int64_t, const void*, int64_t, void*, int64_t, 
 int simt_gemm_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 // tcgen05/TMA path (sc_gemm_tcgen05.cu).  *_ok say whether the shape/alignment is tiled by it.
 bool tc_gemm_fwd_ok(int64_t lda, int64_t ldw, int64_t ldy, int64_t M, int64_t N, int64_t K, int in_dtype, int out_dtype,
-                    const void* A, const void* W, const void* Y);
+                    const void* A, const void* W, const void* Y, bool forced);
 int tc_gemm_fwd(const void*, int64_t, const void*, int64_t, const float*, void*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
 bool tc_gemm_dgrad_ok(int64_t lddy, int64_t ldw, int64_t ldda, int64_t M, int64_t N, int64_t K, int in_dtype, int out_dtype,
-                      const void* dY, const void* W, const void* dA);
+                      const void* dY, const void* W, const void* dA, bool forced);
 int tc_gemm_dgrad(const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
 bool tc_gemm_wgrad_ok(int64_t lddy, int64_t lda, int64_t lddw, int64_t M, int64_t N, int64_t K, int in_dtype,
                       const void* dY, const void* A, const void* dW);
@@ -55,7 +55,7 @@ extern "C" int sc_gemm_fwd(const void* A, int64_t lda, const void* W, int64_t ld
   if (M == 0 || N == 0) return 0;
   SC_CHECK_ARG(Y && (K == 0 || (A && W)), SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc = impl != 1 && tc_gemm_fwd_ok(lda, ldw, ldy, M, N, K, in_dtype, out_dtype, A, W, Y);
+  const bool tc = impl != 1 && tc_gemm_fwd_ok(lda, ldw, ldy, M, N, K, in_dtype, out_dtype, A, W, Y, impl == 2);
   if (impl == 2 && !tc) return SC_E_UNSUP;
   if (tc) return tc_gemm_fwd(A, lda, W, ldw, bias, Y, ldy, M, N, K, out_dtype, st);
   return simt_gemm_fwd(A, lda, W, ldw, bias, Y, ldy, M, N, K, in_dtype, out_dtype, st);
@@ -68,7 +68,7 @@ extern "C" int sc_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_
   if (M == 0 || K == 0) return 0;
   SC_CHECK_ARG(dA && (N == 0 || (dY && W)), SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc = impl != 1 && tc_gemm_dgrad_ok(lddy, ldw, ldda, M, N, K, in_dtype, out_dtype, dY, W, dA);
+  const bool tc = impl != 1 && tc_gemm_dgrad_ok(lddy, ldw, ldda, M, N, K, in_dtype, out_dtype, dY, W, dA, impl == 2);
   if (impl == 2 && !tc) return SC_E_UNSUP;
   if (tc) return tc_gemm_dgrad(dY, lddy, W, ldw, dA, ldda, M, N, K, out_dtype, st);
   return simt_gemm_dgrad(dY, lddy, W, ldw, dA, ldda, M, N, K, in_dtype, out_dtype, st);

@@ -386,13 +386,14 @@ static bool make_reduce_map(CUtensorMap* m, const void* ptr, int64_t rows, int64
 }
 
 static bool tc_common_ok(const void* a, const void* b, const void* d, int64_t lda, int64_t ldb, int64_t ldd,
-                         int64_t I, int64_t J, int64_t R, int d_align_elems) {
+                         int64_t I, int64_t J, int64_t R, int d_align_elems, bool forced = false) {
   if (I < 1 || J < 8 || R < 8) return false;
   if ((lda % 8) || (ldb % 8) || (ldd % d_align_elems) || (J % 8)) return false;
   if (!aligned16(a) || !aligned16(b) || !aligned16(d)) return false;
   if (I >= ((int64_t)1 << 31) || J >= ((int64_t)1 << 31) || R >= ((int64_t)1 << 31)) return false;
-  // worth the fixed cost only when a tile is reasonably filled
-  return I * J >= 64 * 64 && get_encode() != nullptr;
+  // worth the fixed cost only when a tile is reasonably filled — unless the caller insists (impl = 2: the fp32 six-block
+  // path must take the SAME kernel for every M, or a segment cut differently would not reproduce the same bits)
+  return (forced || I * J >= 64 * 64) && get_encode() != nullptr;
 }
 
 template <bool A_MN, bool B_MN, int EPI>
@@ -440,9 +441,9 @@ __global__ void zero2d_kernel(float* __restrict__ p, int64_t ld, int64_t rows, i
 }
 
 bool tc_gemm_fwd_ok(int64_t lda, int64_t ldw, int64_t ldy, int64_t M, int64_t N, int64_t K, int in_dtype,
-                    int out_dtype, const void* A, const void* W, const void* Y) {
+                    int out_dtype, const void* A, const void* W, const void* Y, bool forced) {
   if (in_dtype != SC_BF16) return false;
-  return tc_common_ok(A, W, Y, lda, ldw, ldy, M, N, K, out_dtype == SC_BF16 ? 8 : 4);
+  return tc_common_ok(A, W, Y, lda, ldw, ldy, M, N, K, out_dtype == SC_BF16 ? 8 : 4, forced);
 }
 int tc_gemm_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* Y, int64_t ldy,
                 int64_t M, int64_t N, int64_t K, int out_dtype, cudaStream_t st) {
@@ -451,9 +452,9 @@ int tc_gemm_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const fl
 }
 
 bool tc_gemm_dgrad_ok(int64_t lddy, int64_t ldw, int64_t ldda, int64_t M, int64_t N, int64_t K, int in_dtype,
-                      int out_dtype, const void* dY, const void* W, const void* dA) {
+                      int out_dtype, const void* dY, const void* W, const void* dA, bool forced) {
   if (in_dtype != SC_BF16) return false;
-  return tc_common_ok(dY, W, dA, lddy, ldw, ldda, M, K, N, out_dtype == SC_BF16 ? 8 : 4);
+  return tc_common_ok(dY, W, dA, lddy, ldw, ldda, M, K, N, out_dtype == SC_BF16 ? 8 : 4, forced);
 }
 int tc_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dA, int64_t ldda,
                   int64_t M, int64_t N, int64_t K, int out_dtype, cudaStream_t st) {

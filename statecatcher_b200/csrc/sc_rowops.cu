@@ -57,6 +57,37 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t lds, bf
   }
 }
 
+// fp32 matrix -> SIX bf16 blocks for the tensor-core evaluation of an fp32 product.  x = hi + mid + lo to 2^-25 |x|
+// (three bf16 terms = 24 mantissa bits), and
+//   a.w = a_hi w_hi + a_hi w_mid + a_mid w_hi + a_hi w_lo + a_mid w_mid + a_lo w_hi   (+ terms below 2^-24 of the product)
+// which ONE bf16 GEMM (fp32 accumulation in TMEM) over a six-fold reduction dimension computes when the blocks of the
+// two operands are laid out in matching order: pattern 0 = [lo hi mid mid hi hi] (left operand),
+// pattern 1 = [hi lo mid hi mid hi] (right operand).  (Two terms per operand — three products — were measured first:
+// 1e-5 relative, five of the fp32 parity tests outside their rtol 1e-4 bounds; r02.)
+// block_stride: element offset between consecutive blocks in dst (cols for blocks side by side in a row of width
+// >= 6*cols; rows*ldd for blocks stacked vertically).
+__global__ void split6_bf16_kernel(const float* __restrict__ src, int64_t lds, bf16* __restrict__ dst, int64_t ldd,
+                                   int64_t rows, int64_t cols, int pattern, int64_t block_stride) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    const float x = src[r * lds + c];
+    const bf16 hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    const bf16 mid = __float2bfloat16_rn(r1);
+    const bf16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    bf16* d = dst + r * ldd + c;
+    // ascending magnitude: lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi — the tensor core TRUNCATES when it adds an MMA's
+    // products into the fp32 accumulator (loss 2^-24 |acc| per add, one-sided): with the small terms first, only the last
+    // K/16 adds happen at full magnitude (measured r02, K = 1024: 2e-5 relative with hi.hi first)
+    if (pattern == 0) {
+      d[0] = lo; d[block_stride] = hi; d[2 * block_stride] = mid; d[3 * block_stride] = mid; d[4 * block_stride] = hi; d[5 * block_stride] = hi;
+    } else {
+      d[0] = hi; d[block_stride] = lo; d[2 * block_stride] = mid; d[3 * block_stride] = hi; d[4 * block_stride] = mid; d[5 * block_stride] = hi;
+    }
+  }
+}
+
 __global__ void zero_kernel(float* __restrict__ p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
@@ -447,5 +478,15 @@ extern "C" int sc_split_bf16(const float* src, int64_t lds, void* dst, int64_t l
   SC_CHECK_ARG(src && dst && ldd >= 2 * cols, SC_E_BADARG);
   const unsigned blocks = (unsigned)min((int64_t)148 * 16, cdiv(rows * cols, 256));
   split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, rows, cols);
+  SC_LAUNCH_RET();
+}
+
+extern "C" int sc_split6_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols,
+                              int pattern, int64_t block_stride, void* stream) {
+  SC_CHECK_ARG(rows >= 0 && cols >= 0 && (pattern == 0 || pattern == 1) && block_stride > 0, SC_E_BADARG);
+  if (rows * cols == 0) return 0;
+  SC_CHECK_ARG(src && dst && ldd >= cols, SC_E_BADARG);
+  const unsigned blocks = (unsigned)min((int64_t)148 * 16, cdiv(rows * cols, 256));
+  split6_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, rows, cols, pattern, block_stride);
   SC_LAUNCH_RET();
 }

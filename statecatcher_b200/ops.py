@@ -12,7 +12,32 @@ import torch
 from . import _lib
 from ._lib import call, dt, ptr, stream
 
+import os
+
 GEMM_IMPL = 0  # 0 auto (tcgen05 when the shape tiles, else SIMT), 1 SIMT, 2 tcgen05
+# fp32 projections: "bf16x6" = the fp32 product evaluated on the tcgen05 tensor cores as ONE bf16 GEMM (fp32 accumulation
+# in TMEM) over a six-fold reduction dimension: operands split into three bf16 terms (24 mantissa bits), the six
+# products above 2^-24 kept (sc_split6_bf16) — ~1e-6 relative, inside the rtol 1e-4 contract with margin (the two-term /
+# three-product form, 1e-5, put five fp32 parity tests outside their bounds); "simt" = the fp32-FMA kernels (~1e-7).
+F32_GEMM = os.environ.get("SC_F32_GEMM", "bf16x6")
+_NT = 6                                  # blocks per operand
+
+
+def _split3(x: torch.Tensor, pattern: int, vertical: bool) -> torch.Tensor:
+    """fp32 [R,C] -> bf16 [R,6C] (blocks side by side) or [6R,C] (stacked); see sc_split6_bf16."""
+    R, C = x.shape
+    if vertical:
+        out = torch.empty(_NT * R, C, dtype=torch.bfloat16, device=x.device)
+        call("sc_split6_bf16", ptr(x), _ld(x), ptr(out), C, R, C, pattern, R * C, stream())
+    else:
+        out = torch.empty(R, _NT * C, dtype=torch.bfloat16, device=x.device)
+        call("sc_split6_bf16", ptr(x), _ld(x), ptr(out), _NT * C, R, C, pattern, C, stream())
+    return out
+
+
+def _x3_ok(*dims) -> bool:
+    """Shapes the tcgen05 kernel tiles after tripling (every operand dimension a multiple of 8, a filled tile)."""
+    return F32_GEMM == "bf16x6" and GEMM_IMPL != 1 and all(d % 8 == 0 and d >= 8 for d in dims)
 
 
 def _ld(t: torch.Tensor) -> int:
@@ -29,6 +54,13 @@ def gemm_fwd(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out
     assert w.shape[1] == K and a.dtype == w.dtype
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype or a.dtype, device=a.device)
+    if a.dtype == torch.float32 and out.dtype == torch.float32 and _x3_ok(N, K) and M >= 1 and _ld(out) % 4 == 0:
+        # the SAME kernel for every M (impl 2 = tcgen05, no size heuristic): a row's bits do not depend on how a stream is
+        # cut into segments (step-path property, tests/test_gpu_module.py::test_long_stream_120_segments_state_carry)
+        a3, w3 = _split3(a, 0, False), _split3(w, 1, False)         # [M,6K] x [N,6K]^T
+        call("sc_gemm_fwd", ptr(a3), _NT * K, ptr(w3), _NT * K, ptr(bias), ptr(out), _ld(out), M, N, _NT * K,
+             _lib.SC_BF16, _lib.SC_F32, 2, stream())
+        return out
     call("sc_gemm_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(out), _ld(out), M, N, K,
          dt(a), dt(out), GEMM_IMPL, stream())
     return out
@@ -41,6 +73,11 @@ def gemm_dgrad(dy: torch.Tensor, w: torch.Tensor, out_dtype=None, out=None) -> t
     assert w.shape[0] == N and dy.dtype == w.dtype
     if out is None:
         out = torch.empty(M, K, dtype=out_dtype or dy.dtype, device=dy.device)
+    if dy.dtype == torch.float32 and out.dtype == torch.float32 and _x3_ok(N, K) and M >= 1 and _ld(out) % 4 == 0:
+        d3, w3 = _split3(dy, 0, False), _split3(w, 1, True)         # [M,6N] x [6N,K]
+        call("sc_gemm_dgrad", ptr(d3), _NT * N, ptr(w3), K, ptr(out), _ld(out), M, _NT * N, K,
+             _lib.SC_BF16, _lib.SC_F32, 2, stream())
+        return out
     call("sc_gemm_dgrad", ptr(dy), _ld(dy), ptr(w), _ld(w), ptr(out), _ld(out), M, N, K,
          dt(dy), dt(out), GEMM_IMPL, stream())
     return out
@@ -55,6 +92,11 @@ def gemm_wgrad(dy: torch.Tensor, a: torch.Tensor, out: Optional[torch.Tensor] = 
     if out is None:
         out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
         accumulate = False
+    if dy.dtype == torch.float32 and _x3_ok(N, K) and M >= 64 and N * K >= 64 * 64 and _ld(out) % 4 == 0:
+        d3, a3 = _split3(dy, 0, True), _split3(a, 1, True)          # [6M,N]^T x [6M,K]
+        call("sc_gemm_wgrad", ptr(d3), N, ptr(a3), K, ptr(out), _ld(out), _NT * M, N, K,
+             _lib.SC_BF16, int(accumulate), GEMM_IMPL, stream())
+        return out
     call("sc_gemm_wgrad", ptr(dy), _ld(dy), ptr(a), _ld(a), ptr(out), _ld(out), M, N, K,
          dt(dy), int(accumulate), GEMM_IMPL, stream())
     return out
