@@ -35,9 +35,12 @@ def test_fp32_training_path_launch_sequence(rec):
     B, T, H, V = 3, 10, 64, 33
     logits, (h, s) = m(torch.randn(B, T, 80))
     assert logits.shape == (B, T, V) and logits.dtype == torch.float32
-    assert [c[0] for c in rec] == ["sc_gemm_fwd", "sc_gemm_fwd", "sc_lucy_scan_fwd"] * 2 + ["sc_gemm_fwd"]
+    # every fp32 projection = two operand splits (sc_split6_bf16) + ONE tensor-core GEMM over a six-fold reduction
+    # (V = 33 is not a multiple of 8: the output projection stays on the fp32-FMA kernel)
+    gemm6 = ["sc_split6_bf16", "sc_split6_bf16", "sc_gemm_fwd"]
+    assert [c[0] for c in rec] == (gemm6 * 2 + ["sc_lucy_scan_fwd"]) * 2 + ["sc_gemm_fwd"]
     # (M, N, K): input projection, gate projection with the dead r gate left out (5H, not 6H), output projection
-    assert _gemm_shapes(rec) == [(B * T, H, 80), (B * T, 5 * H, H), (B * T, H, H), (B * T, 5 * H, H), (B * T, V, H)]
+    assert _gemm_shapes(rec) == [(B * T, H, 6 * 80), (B * T, 5 * H, 6 * H), (B * T, H, 6 * H), (B * T, 5 * H, 6 * H), (B * T, V, H)]
     n = len(rec)
     logits.sum().backward()
     cnt = collections.Counter(c[0] for c in rec[n:])
@@ -77,7 +80,7 @@ def test_return_last_states_false_and_stacking(rec):
     m, _ = _model(return_last_states=False, stack_order=3)   # layer 0 takes 80 * 3 features
     out = m(torch.randn(2, 11, 80))
     assert torch.is_tensor(out) and out.shape == (2, 3, 33)  # 11 // 3 frames, remainder trimmed (lucyrnn.py:92-99)
-    assert _gemm_shapes(rec)[0] == (2 * 3, 64, 240)
+    assert _gemm_shapes(rec)[0] == (2 * 3, 64, 6 * 240)       # six bf16 blocks per fp32 operand (ops.F32_GEMM)
 
 
 @pytest.mark.parametrize("kw,kernels", [
