@@ -326,3 +326,33 @@ def test_configs0_full_size_four_carried_segments(cuda_device):
     for k, p in model.named_parameters():
         want = Pd[k].grad.numpy()
         assert np.abs(p.grad.cpu().numpy() - want).max() <= 2e-4 * max(1e-3, np.abs(want).max()), k
+
+
+@pytest.mark.gpu
+def test_module_on_a_non_current_device():
+    """A model and its inputs on cuda:1 while cuda:0 is the current device: the public entry points
+    switch to the tensors' device for their launches (the C-ABI launches on the CURRENT device), forward and the
+    autograd thread's backward agree, and the result equals the same computation done with cuda:1 current."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import statecatcher_b200 as sb
+    torch.cuda.set_device(0)
+    cfg = sb.LucyRNNConfig(input_dim=80, hidden_dim=64, num_layers=2, vocab_size=40, fused_ops=True, layer_norm=False)
+    torch.manual_seed(0)
+    model = sb.LucyRNN(cfg)
+    torch.nn.init.normal_(model.output_proj.weight, std=0.05)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 40, 80, generator=g)
+    tok = torch.randint(1, 40, (3, 5), generator=g)
+    outs = []
+    for current in (0, 1):
+        torch.cuda.set_device(current)
+        m = sb.LucyRNN(cfg).to("cuda:1")
+        m.load_state_dict(model.state_dict())
+        logits, state = m(x.to("cuda:1"))
+        loss = sb.ctc_loss_from_logits(logits, tok.to("cuda:1"), [40, 33, 40], [5, 3, 0], zero_infinity=True)
+        loss.backward()
+        assert logits.device == torch.device("cuda:1") and state[0][0].device == torch.device("cuda:1")
+        outs.append((logits.detach().cpu(), loss.item(), m.layers[0].W_fused.weight.grad.cpu()))
+    torch.cuda.set_device(0)
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
