@@ -731,6 +731,13 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
 }
 
 
+// Measured and dropped (r02, cfg2 shape, 0.30 ms = 3.8 TB/s of actual traffic as it stands; ncu: 46 % of DRAM peak,
+// long-scoreboard stalls dominate, 45 % issue-active): (a) requesting the frame's lattice words and labels before the
+// V-wide softmax pass (64 instead of 40 registers: 0.30 ms alone, 0.35 -> 0.40 ms inside the step); (b) a persistent grid
+// whose warps keep the NEXT frame's logits / alpha / beta rows in flight as cp.async copies into a double-buffered
+// per-warp stage (bit-identical, 13 KB of shared memory per warp -> 16 warps per SM): 0.39 ms.  A frame is ~800
+// dependent-ish instructions for its warp; what hides that is the 43 resident warps per SM of this form, not a deeper
+// load queue.
 template <typename TI, typename TO, int NP>
 __global__ void __launch_bounds__(CTC_WARPS * 32)
 ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_t,
