@@ -533,7 +533,7 @@ def main():
     roofs = {
         "scan_fwd": roof(["sc_lucy_scan_fwd"], "hbm"),
         "scan_bwd": roof(["sc_lucy_scan_bwd"], "hbm"),
-        "ctc": roof(["sc_ctc_emissions", "sc_ctc_lattice", "sc_ctc_bwd"], "hbm", ctc_bytes),
+        "ctc": roof(["sc_ctc_emissions", "sc_ctc_lattice", "sc_ctc_bwd", "sc_ctc_head", "sc_ctc_scale_grad"], "hbm", ctc_bytes),
         # the three CTC passes on their own (bytes each pass must move, per frame: emissions read V*e and
         # write the 4(2U+1)-byte lattice row; the recursions read it and write alpha and beta; the gradient
         # pass reads logits, alpha, beta and writes dlogits)

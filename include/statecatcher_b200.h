@@ -224,6 +224,29 @@ int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype
                void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
                const void* ws, void* stream);
 
+/* The whole head in one call — loss AND the gradient for a unit upstream gradient, with the two V-wide passes
+ * running UNDER the latency-bound recursions (model.py:70-71 + the backward autograd would run later).
+ * The segment is cut into sc_ctc_head_phases(T, Umax, phases) chunks of whole 64-frame emission blocks; the
+ * recursions run as that many launches over frame ranges on `stream_l` (the column travels through `ws` in fp64:
+ * rows are bit-identical to sc_ctc_lattice), the emission pass feeds them chunk by chunk from `stream_e` (both
+ * ends inwards) and the gradient pass follows on `stream_g` (the middle outwards); ordering is by events, the side
+ * streams fork from and join `stream` (safe inside a stream capture).  stream_l should have a higher priority
+ * than stream_e / stream_g (the recursion blocks must find room on SMs the V-wide kernels fill); null: `stream`.  dlogits = scale_b * (softmax - occupancy)
+ * as sc_ctc_bwd with grad_out = 1; the caller multiplies by the upstream gradient when autograd delivers it
+ * (sc_ctc_scale_grad).  reduction 1 (mean) or 2 (sum) only.  phases <= 0: the library chooses.  stream_e /
+ * stream_g null or equal to `stream`, or a single phase: the same passes one after the other on `stream`.
+ * Workspaces and outputs as sc_ctc_fwd / sc_ctc_bwd. */
+int64_t sc_ctc_head_phases(int64_t T, int64_t Umax, int64_t phases);
+int sc_ctc_head(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+                int64_t blank, float* lse, float* lplat, float* cshift, float* alpha, float* beta,
+                float* nll, float* loss, int reduction, void* ws,
+                void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
+                int64_t phases, void* stream, void* stream_l, void* stream_e, void* stream_g);
+/* x[0..n) *= *scale (device fp32 scalar); returns without touching x when *scale == 1. */
+int sc_ctc_scale_grad(void* x, int dtype, int64_t n, const float* scale, void* stream);
+
 /* ---------------------------------------------------------------- K4: RNN-T ----------
  * Replaces warp_rnnt.RNNTLoss as called at model.py:97-105 (gather=True): transducer
  * alpha/beta over the T x (U+1) lattice swept by anti-diagonals.

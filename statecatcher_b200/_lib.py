@@ -58,6 +58,10 @@ SIGNATURES = {
     "sc_rnnt_lattice": [P, P, I64, I64, I64, P, P, P, P, P, P],
     "sc_rnnt_node_grads": [P, P, I64, I64, I64, P, P, P, P, P, P, P, P, P],
     "sc_rnnt_dlogits": [P, I32, P, P, P, P, I64, P, I64, I64, I64, I64, I64, I64, I64, P, P, P],
+    "sc_ctc_head_phases": [I64, I64, I64],
+    "sc_ctc_head": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, I32, P,
+                    P, I64, I64, I32, I64, P, P, P, P],
+    "sc_ctc_scale_grad": [P, I32, I64, P, P],
     "sc_ctc_greedy_decode": [P, I64, I64, I32, P, I64, I64, I64, I64, P, P, P, P],
     "sc_sumsq_accum": [P, I64, P, P],
     "sc_scale_grads": [P, I64, P, F32, P],
@@ -75,7 +79,7 @@ SIGNATURES = {
     "sc_frame_mask": [P, I64, I64, I64, I64, I64, F32, I64, P, P, P],
 }
 _RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64,
-             "sc_ctc_workspace_bytes": I64,
+             "sc_ctc_workspace_bytes": I64, "sc_ctc_head_phases": I64,
              "sc_frontend_tables_len": I64}
 
 _lib = None
@@ -172,7 +176,7 @@ KERNELS_PER_CALL = {
     "sc_gemm_fwd": 1, "sc_gemm_dgrad": 1, "sc_gemm_wgrad": 1, "sc_cast": 1, "sc_colsum": 2,
     "sc_layernorm_fwd": 1, "sc_layernorm_bwd": 1, "sc_lucy_scan_fwd": 1, "sc_lucy_scan_fwd_chunked": 3, "sc_lucy_scan_bwd": 1,
     "sc_lucy_sscan_fwd": 1, "sc_lucy_sscan_bwd": 1, "sc_lucy_hscan_fwd": 1, "sc_lucy_hscan_bwd": 1,
-    "sc_ctc_fwd": 5, "sc_ctc_emissions": 1, "sc_ctc_lattice": 4, "sc_ctc_bwd": 1, "sc_rnnt_fwd": 2, "sc_rnnt_bwd": 2, "sc_split_bf16": 1, "sc_joint_fwd": 1, "sc_joint_bwd": 2, "sc_rnnt_lse_gather": 1, "sc_rnnt_lattice": 1,
+    "sc_ctc_fwd": 5, "sc_ctc_emissions": 1, "sc_ctc_lattice": 4, "sc_ctc_bwd": 1, "sc_ctc_scale_grad": 1, "sc_rnnt_fwd": 2, "sc_rnnt_bwd": 2, "sc_split_bf16": 1, "sc_joint_fwd": 1, "sc_joint_bwd": 2, "sc_rnnt_lse_gather": 1, "sc_rnnt_lattice": 1,
     "sc_rnnt_node_grads": 1, "sc_rnnt_dlogits": 1, "sc_ctc_greedy_decode": 2, "sc_frontend": 1, "sc_frame_mask": 1,
 }
 _ESZ = {SC_F32: 4, SC_BF16: 2}
@@ -204,6 +208,9 @@ def call(name: str, *args):
     global launches, kernels
     launches += 1
     kernels += KERNELS_PER_CALL.get(name, 1)
+    if name == "sc_ctc_head":        # emission, recursion and gradient launch per phase + check, recomputation, reduction, fix-up
+        ph = load().sc_ctc_head_phases(args[9], args[11], args[26]) if args[29] and args[30] else 1
+        kernels += 3 * ph + 4 - 1 if ph >= 2 else 6 - 1
     if name == "sc_gemm_wgrad" and args[9] == SC_BF16 and not args[10]:
         kernels += 1                 # the tcgen05 split-R wgrad zero-fills dW first (zero2d_kernel) when not accumulating
     fn = getattr(load(), name)

@@ -13,7 +13,7 @@ LIB = os.path.join(CSRC, "libstatecatcher_b200.so")
 SOURCES = ["sc_api.cu", "sc_scan.cu", "sc_scan_tma.cu", "sc_scan_chunked.cu", "sc_ctc.cu", "sc_gemm_simt.cu", "sc_gemm_tcgen05.cu",
            "sc_rowops.cu", "sc_rnnt.cu", "sc_decode.cu", "sc_optim.cu", "sc_frontend.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -39,7 +39,7 @@ def build_library(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + \
+        cmd = [_nvcc()] + NVCC_FLAGS + \
               (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

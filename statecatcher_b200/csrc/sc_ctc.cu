@@ -34,6 +34,7 @@
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
 #include <stdlib.h>
+#include <vector>
 
 namespace sc {
 
@@ -140,6 +141,7 @@ __device__ __forceinline__ float lse3_2(float a, float b, float c) {
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float CTC_DEAD = -1e30f;          // below CTC_DEAD_TEST a log2-domain value counts as probability zero
 constexpr float CTC_DEAD_TEST = -1e29f;
+constexpr int CTC_GRAD_ALL = 0, CTC_GRAD_SPEC = 1, CTC_GRAD_FIX = 2;   // modes of the gradient pass (sc_ctc_head)
 constexpr float LN2 = 0.6931471805599453f;
 
 // sum_t cshift[t], t < n, over the block in double; result valid in every thread.  Contains two
@@ -578,14 +580,18 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
              const float* __restrict__ lse, const float* __restrict__ alpha,
              const float* __restrict__ beta, const float* __restrict__ nll,
              const float* __restrict__ grad_out, int reduction,
-             TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t, const int* __restrict__ lossy) {
+             TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t, const int* __restrict__ lossy, int mode) {
+  // mode CTC_GRAD_SPEC: the likelihood is not known yet (the recursions are still under way in other frames): the
+  // length is validated here and the row is formed as if the utterance were feasible; CTC_GRAD_FIX puts that right
   const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
   int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
   TO* dx = dlogits + b * dstride_b + t * dstride_t;
-  const float n = nll[b];
+  bool dead;
+  if (mode == CTC_GRAD_SPEC) { const int64_t U64 = tgt_lens[b]; dead = U64 < 0 || 2 * U64 + 1 > Smax; }
+  else dead = !isfinite(nll[b]);
   constexpr int VWI = 16 / sizeof(TI), VWO = 16 / sizeof(TO);
   const bool vec_out = (V % VWO == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
-  if (t >= Tb || !isfinite(n)) {                      // exact zeros (App. B)
+  if (t >= Tb || dead) {                              // exact zeros (App. B)
     if (vec_out) {
       for (int i = lane * VWO; i < V; i += 32 * VWO) *reinterpret_cast<uint4*>(dx + i) = make_uint4(0, 0, 0, 0);
     } else {
@@ -595,7 +601,7 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
   }
   float* r = sm + (int64_t)warp * V;
   const TI* x = logits + b * stride_b + t * stride_t;
-  const int U = (int)tgt_lens[b];                     // valid here: an invalid length left nll = inf above
+  const int U = (int)tgt_lens[b];                     // valid here: an invalid length left nll = inf above / was tested above
   const int64_t* tg = targets + (int64_t)b * ldt;
   const bool lin = lossy != nullptr && !lossy[b];     // rows in the linear-domain format (lossy == nullptr: log-domain launch)
   // pair u <= U exists; its label node only for u < U.  occupancy_s = 2^(alpha+beta)_s / sum_s'
@@ -684,7 +690,7 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
     for (int kk = 0; kk < NP; ++kk) {
       const int u = lane + 32 * kk;
       bsum += wb[kk] * inv;
-      if (u < U) atomicAdd(r + tg[u], -wl[kk] * inv);
+      if (u < U && wl[kk] != 0.f) atomicAdd(r + tg[u], -wl[kk] * inv);   // a label outside the vocabulary has occupancy 0
     }
   } else {
     for (int u = lane; u <= U; u += 32) {
@@ -711,9 +717,10 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
   if (lane == 0) r[blank] -= bsum;
   __syncwarp();
   float scale;
-  if (reduction == 1) scale = grad_out[0] / ((float)B * fmaxf((float)U, 1.f));
-  else if (reduction == 2) scale = grad_out[0];
-  else scale = grad_out[b];
+  // grad_out == nullptr: unit upstream gradient (sc_ctc_head forms the gradient before autograd has one)
+  if (reduction == 1) scale = (grad_out ? grad_out[0] : 1.f) / ((float)B * fmaxf((float)U, 1.f));
+  else if (reduction == 2) scale = grad_out ? grad_out[0] : 1.f;
+  else scale = grad_out ? grad_out[b] : 1.f;
   if (vec_out) {
     for (int i = lane * VWO; i < V; i += 32 * VWO) {
       float f[VWO];
@@ -747,14 +754,21 @@ ctc_grad_kernel(const TI* __restrict__ logits, int64_t stride_b, int64_t stride_
                 const float* __restrict__ lse, const float* __restrict__ alpha,
                 const float* __restrict__ beta, const float* __restrict__ nll,
                 const float* __restrict__ grad_out, int reduction,
-                TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t, const int* __restrict__ lossy) {
+                TO* __restrict__ dlogits, int64_t dstride_b, int64_t dstride_t, const int* __restrict__ lossy,
+                int t0, int t1, int mode) {
+  // frames [t0, t1) of every utterance (the whole segment: 0, Tn).  CTC_GRAD_FIX: just the utterances flagged in
+  // `lossy` or found infeasible (the rows of the others were written by earlier CTC_GRAD_SPEC launches and stand)
   extern __shared__ __align__(128) float sm[];       // per warp: V floats (softmax row, then the gradient row)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned wpb = blockDim.x >> 5;               // warps per block shrink for large V
-  const unsigned nrows = (unsigned)B * (unsigned)Tn;
-  for (unsigned row = blockIdx.x * wpb + warp; row < nrows; row += gridDim.x * wpb) {   // launched with one warp per row (a capped, persistent grid measured slower)
+  const unsigned span = (unsigned)(t1 - t0);
+  const unsigned nidx = (unsigned)B * span;
+  for (unsigned idx = blockIdx.x * wpb + warp; idx < nidx; idx += gridDim.x * wpb) {   // launched with one warp per row (a capped, persistent grid measured slower)
+    const unsigned bb = idx / span;
+    if (mode == CTC_GRAD_FIX && !((lossy != nullptr && lossy[bb]) || !isfinite(nll[bb]))) continue;
+    const unsigned row = bb * (unsigned)Tn + (unsigned)t0 + (idx - bb * span);
     ctc_grad_row<TI, TO, NP>(sm, row, warp, lane, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, B, Tn, V,
-                             Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, lossy);
+                             Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, lossy, mode);
     __syncwarp();                                     // the warp's shared-memory row is reused by its next frame
   }
 }
@@ -778,6 +792,22 @@ extern "C" int64_t sc_ctc_workspace_bytes(int64_t B, int64_t T, int64_t Umax) {
   return ctc_ws_bytes(B, T);
 }
 
+// pass 1 in the linear emission format over frames [t0, t1) of every utterance
+static int launch_emissions_lin(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                                const int64_t* targets, int64_t ldt, const int64_t* in_lens, const int64_t* tgt_lens,
+                                int64_t B, int64_t T, int64_t V, int64_t Umax, int64_t blank, float* lse, float* lplat,
+                                float* cshift, int t0, int t1, cudaStream_t st) {
+  if (t1 <= t0) return 0;
+  const int LP = ctc_lin_pitch(Umax);
+  const unsigned blocks = (unsigned)cdiv(B * (int64_t)(t1 - t0), CTC_WARPS);
+#define SC_CTC_E(TT, NL) ctc_lse_gather_lin_kernel<TT, NL><<<blocks, CTC_WARPS * 32, 0, st>>>((const TT*)logits, stride_b, stride_t, \
+      targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, (int)Umax, LP, blank, lse, (uint32_t*)lplat, cshift, t0, t1)
+  if (dtype == SC_F32) { if (Umax + 1 <= 160) SC_CTC_E(float, 5); else SC_CTC_E(float, 8); }
+  else { if (Umax + 1 <= 160) SC_CTC_E(bf16, 5); else SC_CTC_E(bf16, 8); }
+#undef SC_CTC_E
+  SC_LAUNCH_RET();
+}
+
 extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                                 const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                                 const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
@@ -790,16 +820,10 @@ extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t st
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);      // row width of lplat/alpha/beta (16-B rows)
+  if (ctc_use_lin(Umax))
+    return launch_emissions_lin(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank,
+                                lse, lplat, cshift, 0, (int)T, st);
   const unsigned blocks = (unsigned)cdiv(B * T, CTC_WARPS);
-  if (ctc_use_lin(Umax)) {
-    const int LP = ctc_lin_pitch(Umax);
-#define SC_CTC_E(TT, NL) ctc_lse_gather_lin_kernel<TT, NL><<<blocks, CTC_WARPS * 32, 0, st>>>((const TT*)logits, stride_b, stride_t, \
-        targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, (int)Umax, LP, blank, lse, (uint32_t*)lplat, cshift)
-    if (dtype == SC_F32) { if (Umax + 1 <= 160) SC_CTC_E(float, 5); else SC_CTC_E(float, 8); }
-    else { if (Umax + 1 <= 160) SC_CTC_E(bf16, 5); else SC_CTC_E(bf16, 8); }
-#undef SC_CTC_E
-    SC_LAUNCH_RET();
-  }
   if (dtype == SC_F32)
     ctc_lse_gather_kernel<float><<<blocks, CTC_WARPS * 32, 0, st>>>((const float*)logits, stride_b, stride_t,
         targets, ldt, in_lens, tgt_lens, (int)B, (int)T, (int)V, (int)Umax, Smax, blank, lse, lplat, cshift);
@@ -845,15 +869,32 @@ static int launch_wave2(const float* lplat, const float* cshift, const int64_t* 
 
 static int launch_lin64(const float* lplat, const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                         const int64_t* tgt_lens, int64_t B, int64_t T, int64_t Umax, int Smax, int LP,
-                        float* alpha, float* beta, float* nll, const CtcWs& w, cudaStream_t st) {
+                        float* alpha, float* beta, float* nll, const CtcWs& w, int a0, int a1, int b0, int b1,
+                        cudaStream_t st) {
+  // alpha over frames [a0, a1), beta over [b0, b1) (a0, b0 multiples of LIN_EB); the whole segment: 0, T, 0, T
   const int Kmax = (int)((Umax + 32) >> 5);
-  const size_t smem = (2 * (size_t)LIN_EB * (32 * Kmax + 4) + 2 * (size_t)LIN_ROWS * 64 * Kmax) * sizeof(uint32_t);
+  auto need = [&](int nb) { return (2 * (size_t)LIN_EB * (32 * Kmax + 4) + (size_t)nb * LIN_ROWS * 64 * Kmax) * sizeof(uint32_t); };
+  const bool deep = need(LIN_NB) <= 200 * 1024;                  // the widest lattices (7 or 8 pairs per lane) get the shorter ring
+  const size_t smem = need(deep ? LIN_NB : LIN_NB_WIDE);
+  auto kern = deep ? ctc_lin64_kernel<LIN_NB> : ctc_lin64_kernel<LIN_NB_WIDE>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ctc_lin64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  ctc_lin64_kernel<<<dim3((unsigned)B, 2), LIN_THREADS, smem, st>>>((const uint32_t*)lplat, targets, ldt, in_lens, tgt_lens,
-      (int)T, (int)Umax, LP, Smax, alpha, beta, nll, w);
+  kern<<<dim3((unsigned)B, 2), LIN_THREADS, smem, st>>>((const uint32_t*)lplat, targets, ldt, in_lens, tgt_lens,
+      (int)T, (int)Umax, LP, Smax, alpha, beta, nll, w, a0, a1, b0, b1);
+  return 0;
+}
+
+// after the fp64 recursions: likelihood + range check, then the log-domain recomputation of the utterances it flags
+static int ctc_lin_tail(const float* lplat, const float* cshift, const int64_t* targets, int64_t ldt,
+                        const int64_t* in_lens, const int64_t* tgt_lens, int64_t B, int64_t T, int64_t Umax,
+                        int Smax, int LP, float* alpha, float* beta, float* nll, const CtcWs& w, cudaStream_t st) {
+  int force = 0;
+  if (const char* ev = getenv("SC_CTC_FORCE_LOSSY")) force = ev[0] == '1';     // tests: send every utterance down the recomputation path
+  const unsigned nsb = 1 + (unsigned)cdiv(cdiv(T, LIN_SAMPLE), LIN_CHECK_THREADS / 32);
+  ctc_lin64_check_kernel<<<dim3((unsigned)B, nsb), LIN_CHECK_THREADS, 0, st>>>(cshift, in_lens, tgt_lens, (int)T, (int)Umax, Smax, force, alpha, beta, nll, w);
+  if (T > 0) return launch_wave2<1>(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, w.lossy, alpha, beta, nll, st);
   return 0;
 }
 
@@ -874,16 +915,10 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
     // fp64 linear-domain recursion -> range check -> log-domain recomputation of the utterances it flags
     const CtcWs w = ctc_ws_carve(ws, B, T);
     const int LP = ctc_lin_pitch(Umax);
-    rc = launch_lin64(lplat, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, alpha, beta, nll, w, st);
+    rc = launch_lin64(lplat, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, alpha, beta, nll, w, 0, (int)T, 0, (int)T, st);
     if (rc) return rc;
-    int force = 0;
-    if (const char* ev = getenv("SC_CTC_FORCE_LOSSY")) force = ev[0] == '1';     // tests: send every utterance down the recomputation path
-    const unsigned nsb = 1 + (unsigned)cdiv(cdiv(T, LIN_SAMPLE), LIN_CHECK_THREADS / 32);
-    ctc_lin64_check_kernel<<<dim3((unsigned)B, nsb), LIN_CHECK_THREADS, 0, st>>>(cshift, in_lens, tgt_lens, (int)T, (int)Umax, Smax, force, alpha, beta, nll, w);
-    if (T > 0) {
-      rc = launch_wave2<1>(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, w.lossy, alpha, beta, nll, st);
-      if (rc) return rc;
-    }
+    rc = ctc_lin_tail(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, alpha, beta, nll, w, st);
+    if (rc) return rc;
   } else if (Smax <= 1024 && !(getenv("SC_CTC_WAVE") && getenv("SC_CTC_WAVE")[0] == '0')) {
     rc = launch_wave2<0>(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, 0, nullptr, alpha, beta, nll, st);
     if (rc) return rc;
@@ -923,7 +958,8 @@ static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_
                            const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int Smax,
                            int64_t blank, const float* lse, const float* alpha, const float* beta,
                            const float* nll, const float* grad_out, int reduction, void* dlogits,
-                           int64_t dstride_b, int64_t dstride_t, const int* lossy, cudaStream_t st) {
+                           int64_t dstride_b, int64_t dstride_t, const int* lossy, int t0, int t1, int mode,
+                           cudaStream_t st) {
   // one shared-memory row of V floats per warp: fewer warps per block when the vocabulary is large
   const size_t per_warp = (size_t)V * sizeof(float);
   int warps = CTC_WARPS;
@@ -934,10 +970,11 @@ static int launch_ctc_grad(const void* logits, int64_t stride_b, int64_t stride_
     cudaError_t e = cudaFuncSetAttribute(ctc_grad_kernel<TI, TO, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  const unsigned blocks = (unsigned)cdiv(B * T, warps);
+  unsigned blocks = (unsigned)cdiv(B * (int64_t)(t1 - t0), warps);
+  if (mode == CTC_GRAD_FIX && blocks > (unsigned)num_sms() * 4u) blocks = (unsigned)num_sms() * 4u;   // normally nothing to do: a small grid that strides
   ctc_grad_kernel<TI, TO, NP><<<blocks, warps * 32, smem, st>>>((const TI*)logits, stride_b, stride_t, targets, ldt,
       in_lens, tgt_lens, (int)B, (int)T, (int)V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction,
-      (TO*)dlogits, dstride_b, dstride_t, lossy);
+      (TO*)dlogits, dstride_b, dstride_t, lossy, t0, t1, mode);
   SC_LAUNCH_RET();
 }
 
@@ -949,16 +986,17 @@ static int ctc_grad_by_width(int Smax, A... a) {
   return launch_ctc_grad<TI, TO, 0>(a...);
 }
 
-extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
-                          const int64_t* targets, int64_t ldt, const int64_t* in_lens,
-                          const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
-                          int64_t blank, const float* lse, const float* alpha, const float* beta,
-                          const float* nll, const float* grad_out, int reduction,
-                          void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
-                          const void* ws, void* stream) {
+static int ctc_bwd_range(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                                const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+                                int64_t blank, const float* lse, const float* alpha, const float* beta,
+                                const float* nll, const float* grad_out, int reduction,
+                                void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
+                                const void* ws, int64_t t0, int64_t t1, int mode, void* stream) {
   SC_CHECK_ARG(B > 0 && T >= 0 && V > 0 && Umax >= 0 && blank >= 0 && blank < V, SC_E_BADARG);
-  if (T == 0) return 0;
-  SC_CHECK_ARG(logits && in_lens && tgt_lens && lse && alpha && beta && nll && grad_out && dlogits && ws, SC_E_BADARG);
+  SC_CHECK_ARG(t0 >= 0 && t1 <= T && t0 <= t1, SC_E_BADARG);
+  if (t0 == t1) return 0;
+  SC_CHECK_ARG(logits && in_lens && tgt_lens && lse && alpha && beta && nll && dlogits && ws, SC_E_BADARG);
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2, SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31), SC_E_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
@@ -966,11 +1004,190 @@ extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t
   // rows are in the linear-domain format except for the utterances flagged in the workspace (same rule as the forward)
   const int* lossy = ctc_use_lin(Umax) ? ctc_ws_carve(const_cast<void*>(ws), B, T).lossy : nullptr;
 #define SC_CTC_GRAD(TI, TO) ctc_grad_by_width<TI, TO>(Smax, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, \
-    B, T, V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, lossy, st)
+    B, T, V, Smax, blank, lse, alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, lossy, \
+    (int)t0, (int)t1, mode, st)
   if (dtype == SC_F32 && out_dtype == SC_F32) return SC_CTC_GRAD(float, float);
   if (dtype == SC_BF16 && out_dtype == SC_BF16) return SC_CTC_GRAD(bf16, bf16);
   if (dtype == SC_F32 && out_dtype == SC_BF16) return SC_CTC_GRAD(float, bf16);
   if (dtype == SC_BF16 && out_dtype == SC_F32) return SC_CTC_GRAD(bf16, float);
 #undef SC_CTC_GRAD
   return SC_E_DTYPE;
+}
+
+extern "C" int sc_ctc_bwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                          const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                          const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+                          int64_t blank, const float* lse, const float* alpha, const float* beta,
+                          const float* nll, const float* grad_out, int reduction,
+                          void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
+                          const void* ws, void* stream) {
+  SC_CHECK_ARG(T >= 0, SC_E_BADARG);
+  if (T == 0) return 0;
+  SC_CHECK_ARG(grad_out, SC_E_BADARG);
+  return ctc_bwd_range(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank, lse,
+                          alpha, beta, nll, grad_out, reduction, dlogits, dstride_b, dstride_t, out_dtype, ws, 0, T, 0, stream);
+}
+
+// ---- the head in one call: loss AND gradient, the V-wide passes under the recursions ------------------------------
+// The recursions are a chain of T dependent steps on 2B warps: while they run the device is otherwise idle.  alpha
+// needs emissions from frame 0 upwards and beta from the last frame downwards, and a frame's gradient row can be formed
+// as soon as both have passed it (its normaliser is the frame's own sum over the lattice, not the final likelihood).
+// So the segment is cut into P chunks of whole emission blocks and the recursions run as P launches over frame ranges
+// (the column travels through the workspace in fp64: the rows are bit-identical to one launch): phase p takes alpha
+// through chunk p and beta through chunk P-1-p.  On a second stream the emission pass produces the chunks in the
+// order the phases need them (both ends inwards); on a third the gradient pass takes the chunks both directions
+// have crossed (the middle outwards) for a unit upstream gradient.  The recursion launches need 11 K registers and
+// ~100 KB of shared memory on an SM the V-wide kernels would otherwise fill: they go to `stream_l`, which the caller
+// creates with a HIGHER priority than the side streams, so that their blocks are placed first as the others'
+// retire (measured on a B200 without it: no overlap at all, 0.79 ms against 0.82 ms one after the other).
+// Ordering is by events only — no kernel waits on
+// another — so it is safe under serialising tools and inside a stream capture (both side streams fork from and join
+// `stream`).  What stays exposed: the first two chunks' emissions, the last two chunks' gradient rows, the range
+// check.  Utterances the check flags (and infeasible ones, whose rows must be zero) are redone by a last gradient
+// launch.  stream_l null: the recursions stay on `stream`.  stream_e / stream_g null, phases == 1 or a lattice the fp64 kernel does not take: the same passes, one
+// after the other, on `stream`.
+static cudaEvent_t ctc_head_event(int i) {
+  thread_local std::vector<std::vector<cudaEvent_t>> pools;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if ((int)pools.size() <= dev) pools.resize(dev + 1);
+  auto& pool = pools[dev];
+  while ((int)pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    pool.push_back(e);
+  }
+  return pool[i];
+}
+#define SC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// number of recursion launches sc_ctc_head cuts a segment of T frames into (1: nothing to overlap).  phases <= 0: the
+// library's choice (SC_CTC_PHASES in the environment overrides it)
+extern "C" int64_t sc_ctc_head_phases(int64_t T, int64_t Umax, int64_t phases) {
+  if (T <= 0 || Umax < 0 || !ctc_use_lin(Umax)) return 1;
+  const int64_t nblk = cdiv(T, LIN_EB);
+  int64_t P = phases;
+  if (P <= 0) {
+    if (const char* ev = getenv("SC_CTC_PHASES")) P = atoi(ev);
+    if (P <= 0) P = nblk / 6;                                    // >= 6 emission blocks (384 frames) per launch
+    if (P > 8) P = 8;
+  }
+  if (P > nblk) P = nblk;
+  if (P < 2) return 1;
+  const int64_t C = cdiv(nblk, P) * LIN_EB;                      // whole emission blocks per chunk
+  return cdiv(T, C);
+}
+
+extern "C" int sc_ctc_head(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
+                           const int64_t* targets, int64_t ldt, const int64_t* in_lens,
+                           const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,
+                           int64_t blank, float* lse, float* lplat, float* cshift, float* alpha, float* beta,
+                           float* nll, float* loss, int reduction, void* ws,
+                           void* dlogits, int64_t dstride_b, int64_t dstride_t, int out_dtype,
+                           int64_t phases, void* stream, void* stream_l, void* stream_e, void* stream_g) {
+  SC_CHECK_ARG(B > 0 && T >= 0 && V > 0 && Umax >= 0 && blank >= 0 && blank < V, SC_E_BADARG);
+  SC_CHECK_ARG(reduction >= 1 && reduction <= 2 && loss && ws && nll && in_lens && tgt_lens, SC_E_BADARG);
+  SC_CHECK_ARG(T == 0 || (logits && lse && lplat && cshift && alpha && beta && dlogits), SC_E_BADARG);
+  SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && V < (1 << 30) && Umax < (1 << 20), SC_E_SHAPE);
+  SC_CHECK_ARG((dtype == SC_F32 || dtype == SC_BF16) && (out_dtype == SC_F32 || out_dtype == SC_BF16), SC_E_DTYPE);
+  SC_CHECK_ARG(!(dtype == SC_BF16 && out_dtype == SC_F32), SC_E_DTYPE);
+  cudaStream_t st = (cudaStream_t)stream, se = (cudaStream_t)stream_e, sg = (cudaStream_t)stream_g;
+  cudaStream_t sl = stream_l ? (cudaStream_t)stream_l : st;      // the recursions' stream (a high-priority one: see above)
+  const int64_t P = sc_ctc_head_phases(T, Umax, phases);
+  const bool overlap = P >= 2 && se && sg && se != st && sg != st;
+  if (!overlap) {
+    int rc = sc_ctc_fwd(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank, lse,
+                        lplat, cshift, alpha, beta, nll, loss, reduction, ws, stream);
+    if (rc || T == 0) return rc;
+    return ctc_bwd_range(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank, lse,
+                         alpha, beta, nll, nullptr, reduction, dlogits, dstride_b, dstride_t, out_dtype, ws, 0, T,
+                         CTC_GRAD_ALL, stream);
+  }
+  SC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 7) == 0, SC_E_ALIGN);
+  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
+  const int LP = ctc_lin_pitch(Umax);
+  const CtcWs w = ctc_ws_carve(ws, B, T);
+  const int64_t C = cdiv(T, P * LIN_EB) * LIN_EB;                // frames per chunk: whole emission blocks (every chunk non-empty: sc_ctc_head_phases)
+  auto edge = [&](int64_t k) -> int { return (int)(k * C < T ? k * C : T); };   // chunk k = frames [edge(k), edge(k+1))
+  const int nE = (int)((P + 1) / 2);
+  int nev = 0;
+  cudaEvent_t ev0 = ctc_head_event(nev++);
+  SC_CHECK_ARG(ev0, SC_E_BADARG);
+  SC_CU(cudaEventRecord(ev0, st));                               // the logits are ready
+  SC_CU(cudaStreamWaitEvent(se, ev0, 0));
+  if (sl != st) SC_CU(cudaStreamWaitEvent(sl, ev0, 0));
+  std::vector<cudaEvent_t> evE(nE);
+  int rc = 0;
+  for (int p = 0; p < nE; ++p) {                                 // both ends inwards
+    const int q = (int)P - 1 - p;
+    rc = launch_emissions_lin(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank,
+                              lse, lplat, cshift, edge(p), edge(p + 1), se);
+    if (rc) return rc;
+    if (q != p) {
+      rc = launch_emissions_lin(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank,
+                                lse, lplat, cshift, edge(q), edge(q + 1), se);
+      if (rc) return rc;
+    }
+    evE[p] = ctc_head_event(nev++);
+    SC_CHECK_ARG(evE[p], SC_E_BADARG);
+    SC_CU(cudaEventRecord(evE[p], se));
+  }
+  for (int p = 0; p < (int)P; ++p) {
+    const int q = (int)P - 1 - p;
+    if (p < nE) SC_CU(cudaStreamWaitEvent(sl, evE[p], 0));
+    rc = launch_lin64(lplat, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, alpha, beta, nll, w,
+                      edge(p), edge(p + 1), edge(q), edge(q + 1), sl);
+    if (rc) return rc;
+    if (p >= q) {                                                // both directions have crossed chunks p and q
+      cudaEvent_t evL = ctc_head_event(nev++);
+      SC_CHECK_ARG(evL, SC_E_BADARG);
+      SC_CU(cudaEventRecord(evL, sl));
+      SC_CU(cudaStreamWaitEvent(sg, evL, 0));
+      rc = ctc_bwd_range(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank, lse,
+                         alpha, beta, nll, nullptr, reduction, dlogits, dstride_b, dstride_t, out_dtype, ws,
+                         edge(q), edge(q + 1), CTC_GRAD_SPEC, sg);
+      if (rc) return rc;
+      if (q != p) {
+        rc = ctc_bwd_range(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank, lse,
+                           alpha, beta, nll, nullptr, reduction, dlogits, dstride_b, dstride_t, out_dtype, ws,
+                           edge(p), edge(p + 1), CTC_GRAD_SPEC, sg);
+        if (rc) return rc;
+      }
+    }
+  }
+  rc = ctc_lin_tail(lplat, cshift, targets, ldt, in_lens, tgt_lens, B, T, Umax, Smax, LP, alpha, beta, nll, w, sl);
+  if (rc) return rc;
+  ctc_reduce_kernel<<<1, 32, 0, sl>>>(nll, tgt_lens, (int)B, reduction, loss);
+  if (sl != st) {
+    cudaEvent_t evT = ctc_head_event(nev++);
+    SC_CHECK_ARG(evT, SC_E_BADARG);
+    SC_CU(cudaEventRecord(evT, sl));
+    SC_CU(cudaStreamWaitEvent(st, evT, 0));
+  }
+  cudaEvent_t evG = ctc_head_event(nev++);
+  SC_CHECK_ARG(evG, SC_E_BADARG);
+  SC_CU(cudaEventRecord(evG, sg));
+  SC_CU(cudaStreamWaitEvent(st, evG, 0));
+  return ctc_bwd_range(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank, lse,
+                       alpha, beta, nll, nullptr, reduction, dlogits, dstride_b, dstride_t, out_dtype, ws, 0, T,
+                       CTC_GRAD_FIX, stream);
+}
+
+// x *= *scale (device scalar), skipped entirely when *scale == 1: the gradient the overlapped head formed during the
+// forward for a unit upstream gradient, brought to the upstream gradient autograd hands to the backward
+template <typename T>
+__global__ void ctc_scale_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ scale) {
+  const float sc = *scale;
+  if (sc == 1.f) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    st_f(x + i, ld_f(x + i) * sc);
+}
+extern "C" int sc_ctc_scale_grad(void* x, int dtype, int64_t n, const float* scale, void* stream) {
+  SC_CHECK_ARG(n >= 0 && (n == 0 || (x && scale)), SC_E_BADARG);
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)min((int64_t)148 * 16, cdiv(n, 256));
+  if (dtype == SC_F32) ctc_scale_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, n, scale);
+  else if (dtype == SC_BF16) ctc_scale_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)x, n, scale);
+  else return SC_E_DTYPE;
+  SC_LAUNCH_RET();
 }

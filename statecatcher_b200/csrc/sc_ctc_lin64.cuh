@@ -59,6 +59,8 @@ struct CtcWs {
   double* zl2;       // [B][2]   per direction: log2 of the shift-free likelihood (-inf when zero)
   int* accs;         // [B][2][NT] log2 of the scale taken out of the rows of frames [8k, 8k+7], per direction
   int NT;
+  double* state;     // [B][2][2*LIN_MAXK+1][32] column of a direction between two launches over frame ranges
+  int* istate;       // [B][2][2]  {acc, danger} of the same
 };
 __host__ __device__ inline int ctc_ws_nt(int64_t T) { return (int)(T / LIN_CHECK) + 2; }
 __host__ __device__ inline CtcWs ctc_ws_carve(void* ws, int64_t B, int64_t T) {
@@ -68,11 +70,14 @@ __host__ __device__ inline CtcWs ctc_ws_carve(void* ws, int64_t B, int64_t T) {
   w.zl2 = reinterpret_cast<double*>(p);                          p += (size_t)B * 2 * sizeof(double);
   w.lossy = reinterpret_cast<int*>(p);                           p += (((size_t)B * 4 + 15) & ~(size_t)15);
   w.danger = reinterpret_cast<int*>(p);                          p += (((size_t)B * 8 + 15) & ~(size_t)15);
-  w.accs = reinterpret_cast<int*>(p);
+  w.accs = reinterpret_cast<int*>(p);                            p += (((size_t)B * 2 * w.NT * 4 + 15) & ~(size_t)15);
+  w.state = reinterpret_cast<double*>(p);                        p += (size_t)B * 2 * (2 * 8 + 1) * 32 * sizeof(double);
+  w.istate = reinterpret_cast<int*>(p);
   return w;
 }
 inline int64_t ctc_ws_bytes(int64_t B, int64_t T) {
-  return (int64_t)(B * 16 + ((B * 4 + 15) & ~(int64_t)15) + ((B * 8 + 15) & ~(int64_t)15) + B * 2 * ctc_ws_nt(T) * 4 + 16);
+  return (int64_t)(B * 16 + ((B * 4 + 15) & ~(int64_t)15) + ((B * 8 + 15) & ~(int64_t)15) +
+                   ((B * 2 * ctc_ws_nt(T) * 4 + 15) & ~(int64_t)15) + B * 2 * (2 * 8 + 1) * 32 * 8 + B * 2 * 2 * 4 + 32);
 }
 
 // high word of 2^d (d <= 0, log2 units), mantissa rounded to 20 bits; 0 = probability zero
@@ -100,11 +105,14 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
                           const int64_t* __restrict__ targets, int64_t ldt,
                           const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                           int B, int Tn, int V, int Umax, int LP, int64_t blank,
-                          float* __restrict__ lse, uint32_t* __restrict__ lplat, float* __restrict__ cshift) {
+                          float* __restrict__ lse, uint32_t* __restrict__ lplat, float* __restrict__ cshift,
+                          int t0, int t1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned nrows = (unsigned)B * (unsigned)Tn;
-  for (unsigned row = blockIdx.x * CTC_WARPS + warp; row < nrows; row += gridDim.x * CTC_WARPS) {
-    const int b = (int)(row / (unsigned)Tn), t = (int)(row - (unsigned)b * (unsigned)Tn);
+  const unsigned span = (unsigned)(t1 - t0);                     // frames [t0, t1) of every utterance
+  const unsigned nidx = (unsigned)B * span;
+  for (unsigned idx = blockIdx.x * CTC_WARPS + warp; idx < nidx; idx += gridDim.x * CTC_WARPS) {
+    const int b = (int)(idx / span), t = t0 + (int)(idx - (unsigned)b * span);
+    const unsigned row = (unsigned)b * (unsigned)Tn + (unsigned)t;
     int64_t Tb = in_lens[b]; if (Tb > Tn) Tb = Tn;
     if (t >= Tb) continue;
     const int64_t U64 = tgt_lens[b];
@@ -161,16 +169,22 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
 // scheduler, 1-2 pairs per lane, last label handed from warp to warp through a polled shared-memory mailbox, column
 // scale kept common without a barrier by acting on maxima posted one check point earlier) — bit-identical results,
 // 620-800 us: the per-step mailbox round trip costs more than the 3/4 of the DP work it takes off a warp.
-constexpr int LIN_ROWS = 8;                // steps per group = rows per staging batch (two batches)
+constexpr int LIN_ROWS = 8;                // steps per group = rows per staging batch
+constexpr int LIN_NB = 8;                  // staging batches in the ring (power of two; LIN_NB_WIDE for the widest lattices, whose rows are larger).  Two were enough alone (0.39 ms) but a batch
+                                           // is ~1 us of recursion: next to a kernel that loads the memory system the bulk stores take
+                                           // longer than that to read their rows and the recursion waited for its buffer (measured, cfg2:
+                                           // 0.58 ms beside a device copy, 0.56 beside the emission pass, 0.40 beside an issue-bound
+                                           // kernel on an L2-resident tensor — profiles/r02_ctc_interference.txt)
 constexpr int LIN_THREADS = 64;            // warp 0: recursion, warp 1: I/O
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 
+constexpr int LIN_NB_WIDE = 4;
 struct LinBars {                            // shared-memory mbarriers of one CTA
   uint64_t efull[2], eempty[2];             // emission block landed / consumed
-  uint64_t sfull[2], sempty[2];             // staging batch written / copied out
-  int meta[2][2];                           // per staging batch: rows, first frame
+  uint64_t sfull[LIN_NB], sempty[LIN_NB];   // staging batch written / copied out
+  int meta[LIN_NB][2];                      // per staging batch: rows, first frame
 };
 
 template <int K, int DIR>
@@ -214,11 +228,16 @@ __device__ __forceinline__ int lin_group_len(int t, int rows) {
   return n < rows ? n : rows;
 }
 
-template <int K, int DIR>
+template <int K, int DIR, int NB>
 __device__ __forceinline__ void
 ctc_lin64_recursion(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars* bars,
-                    const int64_t* __restrict__ tg, int Tb, int U,
-                    int* __restrict__ accrec, double* __restrict__ zl2_out, int* __restrict__ danger_out) {
+                    const int64_t* __restrict__ tg, int Tb, int U, int lo, int hi,
+                    int* __restrict__ accrec, double* __restrict__ zl2_out, int* __restrict__ danger_out,
+                    double* __restrict__ state, int* __restrict__ istate) {
+  // this launch walks frames [lo, hi) of the direction (lo a multiple of LIN_EB); the column is taken from / left in
+  // `state` when the range does not start / end at the direction's first / last frame
+  const bool first = DIR == 0 ? lo == 0 : hi == Tb;
+  const bool last = DIR == 0 ? hi == Tb : lo == 0;
   constexpr int SP = Lin64<K, DIR>::SP, EPW = Lin64<K, DIR>::EPW;
   Lin64<K, DIR> L;
   const int lane = threadIdx.x;
@@ -238,24 +257,33 @@ ctc_lin64_recursion(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, L
   }
   eoff[K] = 0u;                                                  // the blank's word
   L.nbv = 0.0;
-  if (lane == 0) L.bv[0] = __hiloint2double(LIN_TGT << 20, 0);   // virtual column before the first frame: all mass in front of node 0, at the target scale
   int acc = 1023 - LIN_TGT;                                      // log2 of the scale taken out of the column so far
   int danger = 0;
-  const int nvis = (Tb + LIN_EB - 1) / LIN_EB;
-  int t = DIR == 0 ? 0 : Tb - 1;
-  if (lane == 0) accrec[t >> 3] = acc;                           // scale of the rows up to the first check
+  if (first) {
+    if (lane == 0) L.bv[0] = __hiloint2double(LIN_TGT << 20, 0); // virtual column before the first frame: all mass in front of node 0, at the target scale
+  } else {
+#pragma unroll
+    for (int j = 0; j < K; ++j) { L.bv[j] = state[(2 * j) * 32 + lane]; L.lv[j] = state[(2 * j + 1) * 32 + lane]; }
+    L.nbv = state[(2 * K) * 32 + lane];
+    acc = istate[0]; danger = istate[1];
+  }
+  const int blk_lo = lo / LIN_EB, blk_hi = (hi - 1) / LIN_EB;
+  const int nvis = blk_hi - blk_lo + 1;
+  int t = DIR == 0 ? lo : hi - 1;
+  if (first && lane == 0) accrec[t >> 3] = acc;                  // scale of the rows up to the first check
   const uint32_t ebuf_a = smem_u32(ebuf), stage_a = smem_u32(stage);
   int g = 0;                                                     // groups done
   for (int vi = 0; vi < nvis; ++vi) {
     mbar_wait(smem_u32(&bars->efull[vi & 1]), (uint32_t)((vi >> 1) & 1));
-    const int blk = DIR == 0 ? vi : nvis - 1 - vi;
-    int rows = Tb - blk * LIN_EB; if (rows > LIN_EB) rows = LIN_EB;
-    int row = DIR == 0 ? 0 : rows - 1;                           // row of the block the next step reads
+    const int blk = DIR == 0 ? blk_lo + vi : blk_hi - vi;
+    const int r0 = max(lo, blk * LIN_EB) - blk * LIN_EB, r1 = min(hi, blk * LIN_EB + LIN_EB) - blk * LIN_EB;
+    int rows = r1 - r0;
+    int row = DIR == 0 ? r0 : r1 - 1;                            // row of the block the next step reads
     while (rows > 0) {
       const int n = lin_group_len<DIR>(t, rows);
       const bool aligned = DIR == 0 ? ((t + n - 1) & 7) == 7 : ((t - n + 1) & 7) == 0;
-      const int batch = g & 1;
-      if (g >= 2) mbar_wait(smem_u32(&bars->sempty[batch]), (uint32_t)(((g >> 1) - 1) & 1));   // the I/O warp has copied this buffer out
+      const int batch = g & (NB - 1);
+      if (g >= NB) mbar_wait(smem_u32(&bars->sempty[batch]), (uint32_t)(((g / NB) - 1) & 1));   // the copy engine has read this buffer's previous rows
       uint32_t eb[K + 1];
       const uint32_t rowbase = ebuf_a + 4u * (uint32_t)(((vi & 1) * LIN_EB + row) * EPW);
 #pragma unroll
@@ -317,6 +345,13 @@ ctc_lin64_recursion(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, L
     __syncwarp();                                               // every lane is done with this visit's emission block
     if (lane == 0) mbar_arrive(smem_u32(&bars->eempty[vi & 1]));
   }
+  if (!last) {                                                   // leave the column for the next launch
+#pragma unroll
+    for (int j = 0; j < K; ++j) { state[(2 * j) * 32 + lane] = L.bv[j]; state[(2 * j + 1) * 32 + lane] = L.lv[j]; }
+    state[(2 * K) * 32 + lane] = L.nbv;
+    if (lane == 0) { istate[0] = acc; istate[1] = danger; }
+    return;
+  }
   // likelihood from this direction: the last pair's blank and the label before it (both after their emission)
   double z = 0.0;
 #pragma unroll
@@ -334,37 +369,38 @@ ctc_lin64_recursion(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, L
 }
 
 // the I/O warp: emission rows in (bulk async copies into the compile-time pitch), finished staging batches out
-template <int DIR>
+template <int DIR, int NB>
 __device__ __forceinline__ void
 ctc_lin64_io(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars* bars, const uint32_t* __restrict__ lp_b,
-             int Tb, int U, int K, int LP, int Smax, float* __restrict__ out_b) {
+             int U, int lo, int hi, int K, int LP, int Smax, float* __restrict__ out_b) {
   const int lane = threadIdx.x & 31;
   const int EPW = 32 * K + 4, SP = 64 * K;
-  const int nvis = (Tb + LIN_EB - 1) / LIN_EB;
+  const int blk_lo = lo / LIN_EB, blk_hi = (hi - 1) / LIN_EB;
+  const int nvis = blk_hi - blk_lo + 1;
   const uint32_t erow_bytes = (uint32_t)((U + 2 + 3) & ~3) * 4u;       // blank, U labels, the zero word
   const int rowchunks = (2 * U + 2 + 3) >> 2;                          // 16-byte chunks of an output row (nodes 0..2U, + the empty label slot)
   auto issue = [&](int vi) {                                           // lane 0 only
-    const int blk = DIR == 0 ? vi : nvis - 1 - vi;
-    int rows = Tb - blk * LIN_EB; if (rows > LIN_EB) rows = LIN_EB;
+    const int blk = DIR == 0 ? blk_lo + vi : blk_hi - vi;
+    const int r0 = max(lo, blk * LIN_EB) - blk * LIN_EB, r1 = min(hi, blk * LIN_EB + LIN_EB) - blk * LIN_EB;
     const uint32_t bar = smem_u32(&bars->efull[vi & 1]);
-    mbar_expect_tx(bar, erow_bytes * (uint32_t)rows);
+    mbar_expect_tx(bar, erow_bytes * (uint32_t)(r1 - r0));
     const uint32_t* src = lp_b + (int64_t)blk * LIN_EB * LP;
     const uint32_t dst = smem_u32(ebuf + (size_t)(vi & 1) * LIN_EB * EPW);
-    for (int r = 0; r < rows; ++r) bulk_load_1d(dst + 4u * (uint32_t)(r * EPW), src + (int64_t)r * LP, erow_bytes, bar);
+    for (int r = r0; r < r1; ++r) bulk_load_1d(dst + 4u * (uint32_t)(r * EPW), src + (int64_t)r * LP, erow_bytes, bar);
   };
   if (lane == 0) {
     issue(0);
     if (nvis > 1) issue(1);
   }
-  int t = DIR == 0 ? 0 : Tb - 1;
+  int t = DIR == 0 ? lo : hi - 1;
   int g = 0;
   for (int vi = 0; vi < nvis; ++vi) {
-    const int blk = DIR == 0 ? vi : nvis - 1 - vi;
-    int rows = Tb - blk * LIN_EB; if (rows > LIN_EB) rows = LIN_EB;
+    const int blk = DIR == 0 ? blk_lo + vi : blk_hi - vi;
+    int rows = min(hi, blk * LIN_EB + LIN_EB) - max(lo, blk * LIN_EB);
     while (rows > 0) {
       const int n = lin_group_len<DIR>(t, rows);
-      const int batch = g & 1;
-      mbar_wait(smem_u32(&bars->sfull[batch]), (uint32_t)((g >> 1) & 1));
+      const int batch = g & (NB - 1);
+      mbar_wait(smem_u32(&bars->sfull[batch]), (uint32_t)((g / NB) & 1));
       if (lane == 0) {
         // the generic-proxy stores of the recursion warp -> the async proxy that reads them
         fence_async_smem();
@@ -372,8 +408,10 @@ ctc_lin64_io(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars*
           bulk_store_1d(out_b + (int64_t)(DIR == 0 ? t + r : t - r) * Smax,
                         smem_u32(stage + ((size_t)batch * LIN_ROWS + r) * SP), (uint32_t)rowchunks * 16u);
         bulk_commit();
-        bulk_wait_read0();                                       // the copy engine has read the rows: the buffer is free
-        mbar_arrive(smem_u32(&bars->sempty[batch]));
+        if (g >= NB - 2) {                                       // all but the NB-2 youngest batches have been read: free the oldest
+          bulk_wait_read<NB - 2>();
+          mbar_arrive(smem_u32(&bars->sempty[(g - (NB - 2)) & (NB - 1)]));
+        }
       }
       t += DIR == 0 ? n : -n;
       rows -= n;
@@ -387,51 +425,55 @@ ctc_lin64_io(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars*
   if (lane == 0) bulk_wait0();                                   // every row is written before the CTA retires
 }
 
-template <int DIR>
+template <int DIR, int NB>
 __device__ __forceinline__ void
 ctc_lin64_body(uint32_t* __restrict__ lin_sm, LinBars* bars, const uint32_t* __restrict__ lplat,
                const int64_t* __restrict__ targets, int64_t ldt,
                const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                int Tn, int Umax, int LP, int Smax, float* __restrict__ alpha, float* __restrict__ beta,
-               float* __restrict__ nll, CtcWs ws) {
+               float* __restrict__ nll, CtcWs ws, int f0, int f1) {
+  // f0, f1: the frames [f0, f1) this launch covers in this direction (whole segment: 0, Tn)
   const int b = blockIdx.x, tid = threadIdx.x;
   int64_t Tb64 = in_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
   const int Tb = (int)Tb64;
   const int64_t U64 = tgt_lens[b];
   const bool bad_len = U64 < 0 || U64 > Umax;
   const int U = bad_len ? 0 : (int)U64;
-  if (tid == 0) { ws.danger[2 * b + DIR] = 0; if (DIR == 0) ws.lossy[b] = 0; }
   if (Tb <= 0 || bad_len) {
-    if (tid == 0) {
+    if (tid == 0 && (DIR == 0 ? f0 == 0 : f1 >= Tn)) {           // once, in the launch that holds the direction's first frame
       const bool ok = !bad_len && U == 0;                        // no frames, no labels: probability one
+      ws.danger[2 * b + DIR] = 0;
       ws.zl2[2 * b + DIR] = ok ? 0.0 : -INFINITY;
-      if (DIR == 0) nll[b] = ok ? 0.f : INFINITY;
+      if (DIR == 0) { ws.lossy[b] = 0; nll[b] = ok ? 0.f : INFINITY; }
     }
     return;
   }
+  const int lo = f0 < 0 ? 0 : f0, hi = f1 < Tb ? f1 : Tb;
+  if (lo >= hi) return;                                          // none of this utterance's frames in the range
+  if (tid == 0 && (DIR == 0 ? lo == 0 : hi == Tb)) { ws.danger[2 * b + DIR] = 0; if (DIR == 0) ws.lossy[b] = 0; }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->efull[i]), 1); mbar_init(smem_u32(&bars->eempty[i]), 1);
-      mbar_init(smem_u32(&bars->sfull[i]), 1); mbar_init(smem_u32(&bars->sempty[i]), 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->efull[i]), 1); mbar_init(smem_u32(&bars->eempty[i]), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&bars->sfull[i]), 1); mbar_init(smem_u32(&bars->sempty[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int K = (U + 32) >> 5;                                   // pairs per lane for this transcript
   const int Kmax = (Umax + 32) >> 5;
   uint32_t* ebuf = lin_sm;                                       // 2 emission blocks of LIN_EB rows, pitch 32K+4 words
-  uint32_t* stage = lin_sm + 2 * (size_t)LIN_EB * (32 * Kmax + 4);   // 2 staging batches of LIN_ROWS rows, pitch 64K words
+  uint32_t* stage = lin_sm + 2 * (size_t)LIN_EB * (32 * Kmax + 4);   // LIN_NB staging batches of LIN_ROWS rows, pitch 64K words
   const uint32_t* lp_b = lplat + (int64_t)b * Tn * LP;
   float* out_b = (DIR == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
   if (tid >= 32) {
-    ctc_lin64_io<DIR>(ebuf, stage, bars, lp_b, Tb, U, K, LP, Smax, out_b);
+    ctc_lin64_io<DIR, NB>(ebuf, stage, bars, lp_b, U, lo, hi, K, LP, Smax, out_b);
     return;
   }
   const int64_t* tg = targets + (int64_t)b * ldt;
   int* accrec = ws.accs + (size_t)(2 * b + DIR) * ws.NT;
   double* zo = ws.zl2 + 2 * b + DIR;
   int* dg = ws.danger + 2 * b + DIR;
-#define SC_LIN_RUN(KK) ctc_lin64_recursion<KK, DIR>(ebuf, stage, bars, tg, Tb, U, accrec, zo, dg)
+  double* state = ws.state + (size_t)(2 * b + DIR) * (2 * LIN_MAXK + 1) * 32;
+  int* istate = ws.istate + (size_t)(2 * b + DIR) * 2;
+#define SC_LIN_RUN(KK) ctc_lin64_recursion<KK, DIR, NB>(ebuf, stage, bars, tg, Tb, U, lo, hi, accrec, zo, dg, state, istate)
   switch (K) {
     case 1: SC_LIN_RUN(1); break;
     case 2: SC_LIN_RUN(2); break;
@@ -445,15 +487,17 @@ ctc_lin64_body(uint32_t* __restrict__ lin_sm, LinBars* bars, const uint32_t* __r
 #undef SC_LIN_RUN
 }
 
+template <int NB>
 __global__ void __launch_bounds__(LIN_THREADS, 1)
 ctc_lin64_kernel(const uint32_t* __restrict__ lplat, const int64_t* __restrict__ targets, int64_t ldt,
                  const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                  int Tn, int Umax, int LP, int Smax, float* __restrict__ alpha, float* __restrict__ beta,
-                 float* __restrict__ nll, CtcWs ws) {
+                 float* __restrict__ nll, CtcWs ws, int a0, int a1, int b0, int b1) {
+  // alpha walks frames [a0, a1) upwards, beta frames [b0, b1) downwards (a0, b0 multiples of LIN_EB; the whole segment: 0, Tn)
   extern __shared__ __align__(128) uint32_t lin_sm[];
   __shared__ __align__(8) LinBars bars;
-  if (blockIdx.y == 0) ctc_lin64_body<0>(lin_sm, &bars, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
-  else ctc_lin64_body<1>(lin_sm, &bars, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws);
+  if (blockIdx.y == 0) ctc_lin64_body<0, NB>(lin_sm, &bars, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws, a0, a1);
+  else ctc_lin64_body<1, NB>(lin_sm, &bars, lplat, targets, ldt, in_lens, tgt_lens, Tn, Umax, LP, Smax, alpha, beta, nll, ws, b0, b1);
 }
 
 // likelihood, and whether fp64 held everything (see the header of this file).  grid (B, 1 + samples/4): block

@@ -14,6 +14,7 @@ for frames t >= T_b.
 """
 from __future__ import annotations
 
+import os
 from typing import Sequence, Union
 
 import torch
@@ -24,6 +25,31 @@ from ._lib import call, dt, ptr, stream
 
 _RED = {"none": 0, "mean": 1, "sum": 2}
 LenT = Union[Sequence[int], torch.Tensor]
+
+# The overlapped head (sc_ctc_head), opt-in with SC_CTC_OVERLAP=1: when the loss is a scalar and its input wants a
+# gradient, the forward forms loss AND gradient in one call, the two V-wide passes running on side streams under the
+# latency-bound recursions; the backward then only multiplies by the upstream gradient (a no-op when that is 1, the
+# `loss.backward()` of train.py:549).  Bit-identical to the three passes (tests/test_gpu_ctc_head.py), but measured
+# on a B200 at the cfg2 shape it does not pay yet (profiles/r02_ctc_head_exp.txt: 0.79-0.89 ms against 0.81 ms alone,
+# 1.12 against 1.04 ms inside the step): a frame's gradient row needs both directions, so the gradient pass can only
+# start at the half-way point, and next to a recursion block (164 KB of shared memory) only one of its blocks fits on
+# an SM.  Default: the three passes one after the other, gradient in the backward.
+_OVERLAP = os.environ.get("SC_CTC_OVERLAP", "0") == "1"
+_side_streams = {}
+
+
+def _head_streams(device):
+    """Handles of the three side streams of ``device`` (created once): a high-priority one for the recursion
+    launches, two of default priority for the emission and the gradient pass.  (0, 0, 0) — which sc_ctc_head takes
+    as "one pass after the other" — for a tensor that is not on a CUDA device (only the host-logic tests get here:
+    ``require_cuda`` has already refused such a tensor)."""
+    if device.type != "cuda":
+        return 0, 0, 0
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(device=key, priority=-1), torch.cuda.Stream(device=key),
+                              torch.cuda.Stream(device=key))
+    return tuple(s.cuda_stream for s in _side_streams[key])
 
 
 def _lens(v: LenT, device, B: int, name: str):
@@ -58,10 +84,20 @@ class _CTCFn(torch.autograd.Function):
         # opaque per-call workspace of the lattice pass (format flags, per-direction likelihoods, range records)
         ws = torch.empty(_lib.load().sc_ctc_workspace_bytes(B, T, Umax) // 8 + 1, dtype=torch.float64, device=dev)
         ldt = targets.stride(0) if targets.numel() else max(Umax, 1)
-        call("sc_ctc_emissions", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
-             ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), ptr(cshift), stream())
-        call("sc_ctc_lattice", ptr(lplat), ptr(cshift), ptr(targets), ldt, ptr(in_lens), ptr(tgt_lens), B, T, Umax, blank,
-             ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, ptr(ws), stream())
+        ctx.dx = None
+        if _OVERLAP and red != 0 and T > 0 and ctx.needs_input_grad[0]:
+            dx = _CTCFn._grad_like(x)
+            sl, se, sg = _head_streams(dev)
+            call("sc_ctc_head", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
+                 ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), ptr(cshift),
+                 ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, ptr(ws),
+                 ptr(dx), dx.stride(1), dx.stride(0), dt(dx), 0, stream(), sl, se, sg)
+            ctx.dx = dx                      # for a unit upstream gradient; the backward scales it
+        else:
+            call("sc_ctc_emissions", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
+                 ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(lplat), ptr(cshift), stream())
+            call("sc_ctc_lattice", ptr(lplat), ptr(cshift), ptr(targets), ldt, ptr(in_lens), ptr(tgt_lens), B, T, Umax, blank,
+                 ptr(alpha), ptr(beta), ptr(nll), ptr(loss), red, ptr(ws), stream())
         ctx.save_for_backward(x, targets, in_lens, tgt_lens, lse, alpha, beta, nll, ws)
         ctx.cfg = (blank, red, Umax, ldt)
         if red != 0:
@@ -69,14 +105,22 @@ class _CTCFn(torch.autograd.Function):
         return loss, nll
 
     @staticmethod
+    def _grad_like(x):
+        dense = x.is_contiguous() or x.transpose(0, 1).is_contiguous()
+        return torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if dense \
+            else torch.empty_like(x, memory_format=torch.contiguous_format)
+
+    @staticmethod
     def backward(ctx, gout, _gnll):
         x, targets, in_lens, tgt_lens, lse, alpha, beta, nll, ws = ctx.saved_tensors
         blank, red, Umax, ldt = ctx.cfg
         T, B, V = x.shape
         g = (_gnll if red == 0 else gout).to(torch.float32).contiguous()
-        dense = x.is_contiguous() or x.transpose(0, 1).is_contiguous()
-        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if dense \
-            else torch.empty_like(x, memory_format=torch.contiguous_format)
+        if ctx.dx is not None:               # formed during the forward; a second backward over a retained graph recomputes
+            dx, ctx.dx = ctx.dx, None
+            call("sc_ctc_scale_grad", ptr(dx), dt(dx), dx.numel(), ptr(g), stream())
+            return dx, None, None, None, None, None, None
+        dx = _CTCFn._grad_like(x)
         call("sc_ctc_bwd", ptr(x), x.stride(1), x.stride(0), dt(x), ptr(targets), ldt,
              ptr(in_lens), ptr(tgt_lens), B, T, V, Umax, blank, ptr(lse), ptr(alpha), ptr(beta),
              ptr(nll), ptr(g), red, ptr(dx), dx.stride(1), dx.stride(0), dt(dx), ptr(ws), stream())
