@@ -142,8 +142,57 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
       hp += ldh;
     };
     if (t0 + TC <= Tn) {                                 // full interval: no per-step bounds test
+      {
+        // The same operations per element in the same order (bit-identical), arranged by what depends on what: only
+        // S_t = d S_{t-1} + kv and h_t = zh (h_{t-1} - c) + c are carried from step to step; the gates' activations
+        // and the candidate c_t = tanh(p + S') are not.  Written step by step (`step` above) a warp — there are only
+        // ~7 per SM, one or two per scheduler — serialises ~46 instructions with their LDS / MUFU latencies: measured
+        // 234 cycles per step, fast enough for HBM only at the full clock (alone 0.99 of the copy peak, inside the
+        // power-capped step 0.75).  Here all 8 steps' loads and activations go first (40 LDS and 32 MUFU in flight
+        // together), then the S chain, the 16 tanh, the h chain and the stores: 47 registers instead of 32, inside
+        // the step 2.87 -> 2.35 ms per 6 layers = 0.75 -> 0.92 of the copy peak (r02, alternating same-box runs).
+        // (left to itself ptxas sinks every activation back to its use to save registers and arrives at the same
+        // step-by-step schedule; the warp-level barrier below is a scheduling fence it does not move code across)
+        float d[TC][VEC], kv[TC][VEC], zh[TC][VEC], pa[TC][VEC];
 #pragma unroll
-      for (int u = 0; u < TC; ++u) step(u);
+        for (int u = 0; u < TC; ++u) {
+          float z[VEC], k[VEC], v[VEC], q[VEC];
+          lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
+          lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
+          lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
+          lds2(st + (SC_GATE_P * TC + u) * CB, tid, pa[u]);
+          lds2(st + (SC_GATE_Q * TC + u) * CB, tid, q);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            d[u][i] = sigmoidf_<PRECISE>(q[i]);
+            kv[u][i] = k[i] * v[i];
+            zh[u][i] = sigmoidf_<PRECISE>(z[i]);
+          }
+        }
+        __syncwarp();                                    // the scheduling fence
+#pragma unroll
+        for (int u = 0; u < TC; ++u)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            S[i] = fmaf(d[u][i], S[i], kv[u][i]);
+            pa[u][i] += TRAIN ? fmaf(d[u][i], S[i], kv[u][i]) : S[i];
+          }
+#pragma unroll
+        for (int u = 0; u < TC; ++u)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) pa[u][i] = tanhf_<PRECISE>(pa[u][i]);
+#pragma unroll
+        for (int u = 0; u < TC; ++u) {
+          float out[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            h[i] = fmaf(zh[u][i], h[i] - pa[u][i], pa[u][i]);
+            out[i] = h[i];
+          }
+          if (live) stg_vec<T>(hp, out);
+          hp += ldh;
+        }
+      }
     } else {
 #pragma unroll
       for (int u = 0; u < TC; ++u)
@@ -305,6 +354,9 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
         stg_vec<T>(rz, dz); stg_vec<T>(rk, dk); stg_vec<T>(rv, dv); stg_vec<T>(rp, dp); stg_vec<T>(rq, dq);
       }
     };
+    // (r02: arranging pass 2 like the forward kernel — every step's activations and products first, behind a scheduling
+    // fence, then the carried chain — was measured inside the step at 5.17 ms against 4.97 ms as it stands: 168 registers
+    // instead of 80, and this kernel already sits at 0.87 of the copy peak.  Not kept.)
     if (t0 + TC <= Tn) {
 #pragma unroll
       for (int u = TC - 1; u >= 0; --u) {
