@@ -105,9 +105,11 @@ int sc_colsum(const void* X, int64_t ldx, int dtype, float* out, int64_t M, int6
 int sc_layernorm_fwd(const void* X, int64_t ldx, const float* w, const float* b,
                      void* Y, int64_t ldy, float* mean, float* rstd,
                      int64_t M, int64_t H, int dtype, void* stream);
+/* dxsum (may be null): [H] fp32, the column sums of dX are ADDED to it — the bias gradient of the projection that
+ * produced X, formed while dX is in registers instead of by a second pass over it (sc_colsum). */
 int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* w,
                      const float* mean, const float* rstd, void* dX, int64_t lddx,
-                     float* dw, float* db, int64_t M, int64_t H, int dtype, void* stream);
+                     float* dw, float* db, float* dxsum, int64_t M, int64_t H, int dtype, void* stream);
 
 /* ---------------------------------------------------------------- K2: fused scan -----
  * The whole recurrent part of one layer for fused_ops=True, layer_norm=False (the
@@ -152,7 +154,8 @@ int sc_lucy_scan_bwd(const void* G, int64_t ldg, const void* Hout, int64_t ldh,
  *        'h_pre' chunk (fused, lucyrnn.py:54) or u (unfused, lucyrnn.py:62).
  *        decay_mode 0 = learned sigmoid(q) (lucyrnn.py:124), 1 = prefix_sum with
  *        lambda_decay (lucyrnn.py:126-142; training path only).  S_all [B,T,H] fp32 saved.
- * hscan: c=tanh(An); zh=sigmoid(Zn); h_t=(1-zh)c+zh*h_{t-1}. */
+ * hscan: c=tanh(An); zh=sigmoid(Zn); h_t=(1-zh)c+zh*h_{t-1}.
+ * sscan_bwd's dsum (may be null): [3][H] fp32, the column sums of dk, dv, dq are ADDED to it (bias gradients). */
 int sc_lucy_sscan_fwd(const void* k, const void* v, const void* q, int64_t ldg,
                       const void* addend, int64_t ldadd, const float* s0,
                       void* A, int64_t lda, float* S_all, float* sT,
@@ -160,7 +163,7 @@ int sc_lucy_sscan_fwd(const void* k, const void* v, const void* q, int64_t ldg,
                       int decay_mode, float lambda_decay, void* stream);
 int sc_lucy_sscan_bwd(const void* k, const void* v, const void* q, int64_t ldg,
                       const float* S_all, const float* s0, const void* dA, int64_t ldda,
-                      void* dk, void* dv, void* dq, int64_t lddg,
+                      void* dk, void* dv, void* dq, int64_t lddg, float* dsum,
                       int64_t B, int64_t T, int64_t H, int dtype, int train_mode,
                       int decay_mode, float lambda_decay, void* stream);
 int sc_lucy_hscan_fwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn,

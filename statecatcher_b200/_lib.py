@@ -35,13 +35,13 @@ SIGNATURES = {
     "sc_split6_bf16": [P, I64, P, I64, I64, I64, I32, I64, P],
     "sc_colsum": [P, I64, I32, P, I64, I64, I32, P],
     "sc_layernorm_fwd": [P, I64, P, P, P, I64, P, P, I64, I64, I32, P],
-    "sc_layernorm_bwd": [P, I64, P, I64, P, P, P, P, I64, P, P, I64, I64, I32, P],
+    "sc_layernorm_bwd": [P, I64, P, I64, P, P, P, P, I64, P, P, P, I64, I64, I32, P],
     "sc_lucy_scan_fwd": [P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I32, I32, P],
     "sc_lucy_scan_chunked_work_bytes": [I64, I64, I64],
     "sc_lucy_scan_fwd_chunked": [P, I64, P, P, P, I64, P, P, P, P, I64, I64, I64, I32, I32, P],
     "sc_lucy_scan_bwd": [P, I64, P, I64, P, P, P, P, I64, P, I64, P, I64, I64, I64, I32, I32, P],
     "sc_lucy_sscan_fwd": [P, P, P, I64, P, I64, P, P, I64, P, P, I64, I64, I64, I32, I32, I32, F32, P],
-    "sc_lucy_sscan_bwd": [P, P, P, I64, P, P, P, I64, P, P, P, I64, I64, I64, I64, I32, I32, I32, F32, P],
+    "sc_lucy_sscan_bwd": [P, P, P, I64, P, P, P, I64, P, P, P, I64, P, I64, I64, I64, I32, I32, I32, F32, P],
     "sc_lucy_hscan_fwd": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I32, P],
     "sc_lucy_hscan_bwd": [P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I64, I64, I64, I32, P],
     "sc_ctc_workspace_bytes": [I64, I64, I64],

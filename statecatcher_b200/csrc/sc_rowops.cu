@@ -145,15 +145,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_reg_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
                          const float* __restrict__ w, const float* __restrict__ mean,
                          const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
-                         float* __restrict__ dw, float* __restrict__ db, int64_t M, int H,
+                         float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dxs, int64_t M, int H,
                          int64_t rows_per_block) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
-  float aw[NJ], ab[NJ], wv[NJ];
+  float aw[NJ], ab[NJ], ax[NJ], wv[NJ];             // ax: column sums of dX (the bias gradient of the projection that produced X)
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    aw[j] = 0.f; ab[j] = 0.f;
+    aw[j] = 0.f; ab[j] = 0.f; ax[j] = 0.f;
     const int i = lane + 32 * j;
     wv[j] = (i < H) ? w[i] : 0.f;
   }
@@ -177,7 +177,8 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int i = lane + 32 * j;
-      if (i < H) st_f(dx + i, rs * (dyv[j] * wv[j] - s1 - xh[j] * s2));
+      const float o = rs * (dyv[j] * wv[j] - s1 - xh[j] * s2);
+      if (i < H) { st_f(dx + i, o); ax[j] += o; }
       aw[j] = fmaf(dyv[j], xh[j], aw[j]);
       ab[j] += dyv[j];
     }
@@ -186,17 +187,19 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
   extern __shared__ float sm[];
   float* sdw = sm;
   float* sdb = sm + H;
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  float* sdx = sm + 2 * H;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int i = lane + 32 * j;
-    if (i < H) { atomicAdd(sdw + i, aw[j]); atomicAdd(sdb + i, ab[j]); }
+    if (i < H) { atomicAdd(sdw + i, aw[j]); atomicAdd(sdb + i, ab[j]); if (dxs) atomicAdd(sdx + i, ax[j]); }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     atomicAdd(dw + i, sdw[i]);
     atomicAdd(db + i, sdb[i]);
+    if (dxs) atomicAdd(dxs + i, sdx[i]);
   }
 }
 
@@ -220,22 +223,62 @@ template <> __device__ __forceinline__ void st8<float>(float* p, const float (&f
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// Vectorised forward for H % 256 == 0, H <= 1024 (same lane/column map as the backward below): the row is read once
+// with 16-byte loads and stays in registers for the mean, the variance and the output (the kernel above reads it
+// three times with 2-byte loads: 0.24 ms per [192000 x 1024] bf16 call against 0.12 ms of traffic).
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_vec_kernel(const T* __restrict__ X, int64_t ldx, const float* __restrict__ w,
+                         const float* __restrict__ b, T* __restrict__ Y, int64_t ldy,
+                         float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T* x = X + row * ldx;
+  float xv[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) ld8<T>(x + (lane + 32 * j) * 8, xv[j]);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += xv[j][e];
+  const float mu = warp_sum(s) / (float)H;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { xv[j][e] -= mu; v = fmaf(xv[j][e], xv[j][e], v); }
+  const float rs = rsqrtf(warp_sum(v) / (float)H + LN_EPS);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  T* y = Y + row * ldy;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float wv[8], bv[8], o[8];
+    ld8<float>(w + (lane + 32 * j) * 8, wv);
+    ld8<float>(b + (lane + 32 * j) * 8, bv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = xv[j][e] * rs * wv[e] + bv[e];
+    st8<T>(y + (lane + 32 * j) * 8, o);
+  }
+}
+
 template <typename T, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_vec_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
                          const float* __restrict__ w, const float* __restrict__ mean,
                          const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
-                         float* __restrict__ dw, float* __restrict__ db, int64_t M, int H,
+                         float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dxs, int64_t M, int H,
                          int64_t rows_per_block) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
-  float aw[NV][8], ab[NV][8], wv[NV][8];
+  float aw[NV][8], ab[NV][8], ax[NV][8], wv[NV][8];
 #pragma unroll
   for (int j = 0; j < NV; ++j)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      aw[j][e] = 0.f; ab[j][e] = 0.f;
+      aw[j][e] = 0.f; ab[j][e] = 0.f; ax[j][e] = 0.f;
       wv[j][e] = w[(lane + 32 * j) * 8 + e];
     }
   for (int64_t row = m0 + warp; row < m1; row += LN_WARPS) {
@@ -268,6 +311,7 @@ layernorm_bwd_vec_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
         o[e] = rs * (dyv[j][e] * wv[j][e] - s1 - xh[j][e] * s2);
         aw[j][e] = fmaf(dyv[j][e], xh[j][e], aw[j][e]);
         ab[j][e] += dyv[j][e];
+        ax[j][e] += o[e];
       }
       st8<T>(dx + (lane + 32 * j) * 8, o);
     }
@@ -275,7 +319,8 @@ layernorm_bwd_vec_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
   extern __shared__ float sm[];
   float* sdw = sm;
   float* sdb = sm + H;
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  float* sdx = sm + 2 * H;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < NV; ++j)
@@ -283,11 +328,13 @@ layernorm_bwd_vec_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
     for (int e = 0; e < 8; ++e) {
       atomicAdd(sdw + (lane + 32 * j) * 8 + e, aw[j][e]);
       atomicAdd(sdb + (lane + 32 * j) * 8 + e, ab[j][e]);
+      if (dxs) atomicAdd(sdx + (lane + 32 * j) * 8 + e, ax[j][e]);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     atomicAdd(dw + i, sdw[i]);
     atomicAdd(db + i, sdb[i]);
+    if (dxs) atomicAdd(dxs + i, sdx[i]);
   }
 }
 
@@ -296,12 +343,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
                      const float* __restrict__ w, const float* __restrict__ mean,
                      const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
-                     float* __restrict__ dw, float* __restrict__ db, int64_t M, int H,
+                     float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dxs, int64_t M, int H,
                      int64_t rows_per_block) {
-  extern __shared__ float sm[];        // dw[H], db[H] block partials
+  extern __shared__ float sm[];        // dw[H], db[H], dxsum[H] block partials
   float* sdw = sm;
   float* sdb = sm + H;
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  float* sdx = sm + 2 * H;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
@@ -322,32 +370,35 @@ layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict
     for (int i = lane; i < H; i += 32) {
       const float dyi = ld_f(dy + i);
       const float xh = (ld_f(x + i) - mu) * rs;
-      st_f(dx + i, rs * (dyi * w[i] - s1 - xh * s2));
+      const float o = rs * (dyi * w[i] - s1 - xh * s2);
+      st_f(dx + i, o);
       atomicAdd(sdw + i, dyi * xh);
       atomicAdd(sdb + i, dyi);
+      if (dxs) atomicAdd(sdx + i, o);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     atomicAdd(dw + i, sdw[i]);
     atomicAdd(db + i, sdb[i]);
+    if (dxs) atomicAdd(dxs + i, sdx[i]);
   }
 }
 
 template <typename T>
 static void launch_ln_bwd(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* w, const float* mean,
-                          const float* rstd, void* dX, int64_t lddx, float* dw, float* db, int64_t M, int H,
+                          const float* rstd, void* dX, int64_t lddx, float* dw, float* db, float* dxs, int64_t M, int H,
                           int64_t blocks, int64_t rpb, size_t smem, cudaStream_t st) {
 #define SC_LN_BWD(NJ) do { \
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_reg_kernel<T, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     layernorm_bwd_reg_kernel<T, NJ><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
-        (T*)dX, lddx, dw, db, M, H, rpb); } while (0)
+        (T*)dX, lddx, dw, db, dxs, M, H, rpb); } while (0)
   const bool vec_ok = (H % 256 == 0) && H <= 1024 && (lddy % 8 == 0) && (ldx % 8 == 0) && (lddx % 8 == 0) &&
                       aligned16(dY) && aligned16(X) && aligned16(dX);
 #define SC_LN_BWD_V(NV) do { \
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_vec_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     layernorm_bwd_vec_kernel<T, NV><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
-        (T*)dX, lddx, dw, db, M, H, rpb); } while (0)
+        (T*)dX, lddx, dw, db, dxs, M, H, rpb); } while (0)
   if (vec_ok) {
     switch (H / 256) {
       case 1: SC_LN_BWD_V(1); return;
@@ -365,7 +416,7 @@ static void launch_ln_bwd(const void* dY, int64_t lddy, const void* X, int64_t l
   else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     layernorm_bwd_kernel<T><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd,
-        (T*)dX, lddx, dw, db, M, H, rpb);
+        (T*)dX, lddx, dw, db, dxs, M, H, rpb);
   }
 #undef SC_LN_BWD
 }
@@ -445,17 +496,22 @@ extern "C" int sc_layernorm_fwd(const void* X, int64_t ldx, const float* w, cons
   SC_CHECK_ARG(X && w && b && Y && mean && rstd, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)cdiv(M, LN_WARPS);
-  if (dtype == SC_F32)
-    layernorm_fwd_kernel<float><<<blocks, LN_WARPS * 32, 0, st>>>((const float*)X, ldx, w, b, (float*)Y, ldy, mean, rstd, M, (int)H);
-  else if (dtype == SC_BF16)
-    layernorm_fwd_kernel<bf16><<<blocks, LN_WARPS * 32, 0, st>>>((const bf16*)X, ldx, w, b, (bf16*)Y, ldy, mean, rstd, M, (int)H);
-  else return SC_E_DTYPE;
+  SC_CHECK_ARG(dtype == SC_F32 || dtype == SC_BF16, SC_E_DTYPE);
+  const bool vec_ok = (H % 256 == 0) && H <= 1024 && (ldx % 8 == 0) && (ldy % 8 == 0) && aligned16(X) && aligned16(Y) &&
+                      aligned16(w) && aligned16(b);
+#define SC_LN_FWD_V(TT, NV) layernorm_fwd_vec_kernel<TT, NV><<<blocks, LN_WARPS * 32, 0, st>>>((const TT*)X, ldx, w, b, (TT*)Y, ldy, mean, rstd, M, (int)H)
+#define SC_LN_FWD_T(TT) do { \
+    if (!vec_ok) layernorm_fwd_kernel<TT><<<blocks, LN_WARPS * 32, 0, st>>>((const TT*)X, ldx, w, b, (TT*)Y, ldy, mean, rstd, M, (int)H); \
+    else if (H == 256) SC_LN_FWD_V(TT, 1); else if (H == 512) SC_LN_FWD_V(TT, 2); else if (H == 768) SC_LN_FWD_V(TT, 3); else SC_LN_FWD_V(TT, 4); } while (0)
+  if (dtype == SC_F32) SC_LN_FWD_T(float); else SC_LN_FWD_T(bf16);
+#undef SC_LN_FWD_T
+#undef SC_LN_FWD_V
   SC_LAUNCH_RET();
 }
 
 extern "C" int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* w,
                                 const float* mean, const float* rstd, void* dX, int64_t lddx,
-                                float* dw, float* db, int64_t M, int64_t H, int dtype, void* stream) {
+                                float* dw, float* db, float* dxsum, int64_t M, int64_t H, int dtype, void* stream) {
   SC_CHECK_ARG(M >= 0 && H > 0 && H <= 24 * 1024, SC_E_BADARG);
   if (M == 0) return 0;
   SC_CHECK_ARG(dY && X && w && mean && rstd && dX && dw && db, SC_E_BADARG);
@@ -464,9 +520,9 @@ extern "C" int sc_layernorm_bwd(const void* dY, int64_t lddy, const void* X, int
   if (blocks > cdiv(M, LN_WARPS)) blocks = cdiv(M, LN_WARPS);
   const int64_t rpb = cdiv(M, blocks);
   blocks = cdiv(M, rpb);
-  const size_t smem = 2 * (size_t)H * sizeof(float);
-  if (dtype == SC_F32) launch_ln_bwd<float>(dY, lddy, X, ldx, w, mean, rstd, dX, lddx, dw, db, M, (int)H, blocks, rpb, smem, st);
-  else if (dtype == SC_BF16) launch_ln_bwd<bf16>(dY, lddy, X, ldx, w, mean, rstd, dX, lddx, dw, db, M, (int)H, blocks, rpb, smem, st);
+  const size_t smem = 3 * (size_t)H * sizeof(float);
+  if (dtype == SC_F32) launch_ln_bwd<float>(dY, lddy, X, ldx, w, mean, rstd, dX, lddx, dw, db, dxsum, M, (int)H, blocks, rpb, smem, st);
+  else if (dtype == SC_BF16) launch_ln_bwd<bf16>(dY, lddy, X, ldx, w, mean, rstd, dX, lddx, dw, db, dxsum, M, (int)H, blocks, rpb, smem, st);
   else return SC_E_DTYPE;
   SC_LAUNCH_RET();
 }

@@ -283,12 +283,13 @@ __global__ void __launch_bounds__(128)
 sscan_bwd_kernel(const T* __restrict__ kk, const T* __restrict__ vv, const T* __restrict__ qq, int64_t ldg,
                  const float* __restrict__ S_all, const float* __restrict__ s0,
                  const T* __restrict__ dA, int64_t ldda, T* __restrict__ dk, T* __restrict__ dv,
-                 T* __restrict__ dq, int64_t lddg, int B, int Tn, int H, int train, int decay_mode,
-                 float lam) {
+                 T* __restrict__ dq, int64_t lddg, float* __restrict__ dsum, int B, int Tn, int H, int train,
+                 int decay_mode, float lam) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)B * H) return;
   const int b = (int)(gid / H), ch = (int)(gid % H);
   const int64_t r0 = (int64_t)b * Tn;
+  float ak = 0.f, av = 0.f, aq = 0.f;   // column sums (dsum: [3][H], may be null)
   float ds = 0.f;      // d_{t+1} * sigma_{t+1}
   for (int t = Tn - 1; t >= 0; --t) {
     const int64_t r = r0 + t;
@@ -310,10 +311,13 @@ sscan_bwd_kernel(const T* __restrict__ kk, const T* __restrict__ vv, const T* __
       dd = Sp * sig;
       ds = d * sig;
     }
-    st_f(dk + r * lddg + ch, dkv * v);
-    st_f(dv + r * lddg + ch, dkv * k);
-    st_f(dq + r * lddg + ch, dd * d * (1.f - d));
+    const float o1 = dkv * v, o2 = dkv * k, o3 = dd * d * (1.f - d);
+    st_f(dk + r * lddg + ch, o1);
+    st_f(dv + r * lddg + ch, o2);
+    st_f(dq + r * lddg + ch, o3);
+    ak += o1; av += o2; aq += o3;
   }
+  if (dsum != nullptr) { atomicAdd(dsum + ch, ak); atomicAdd(dsum + H + ch, av); atomicAdd(dsum + 2 * (int64_t)H + ch, aq); }
 }
 
 // prefix_sum backward: w_t depends only on t, so a first forward pass rebuilds logw_t into
@@ -324,11 +328,12 @@ __global__ void __launch_bounds__(128)
 sscan_bwd_prefix_kernel(const T* __restrict__ kk, const T* __restrict__ vv, const T* __restrict__ qq,
                         int64_t ldg, const float* __restrict__ S_all, const T* __restrict__ dA,
                         int64_t ldda, T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dq,
-                        int64_t lddg, int B, int Tn, int H, float lam) {
+                        int64_t lddg, float* __restrict__ dsum, int B, int Tn, int H, float lam) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)B * H) return;
   const int b = (int)(gid / H), ch = (int)(gid % H);
   const int64_t r0 = (int64_t)b * Tn;
+  float ak = 0.f, av = 0.f, aq = 0.f;
   float logw = 0.f;
   for (int t = 0; t < Tn; ++t) logw += logf(expf(-lam * (float)t) + 1e-7f);
   float racc = 0.f;
@@ -342,11 +347,14 @@ sscan_bwd_prefix_kernel(const T* __restrict__ kk, const T* __restrict__ vv, cons
     racc += d * da / (w + 1e-7f);              // dL/dnum_t accumulated over tau >= t
     const float dkv = da + w * racc;
     const float dd = St * da;
-    st_f(dk + r * lddg + ch, dkv * v);
-    st_f(dv + r * lddg + ch, dkv * k);
-    st_f(dq + r * lddg + ch, dd * d * (1.f - d));
+    const float o1 = dkv * v, o2 = dkv * k, o3 = dd * d * (1.f - d);
+    st_f(dk + r * lddg + ch, o1);
+    st_f(dv + r * lddg + ch, o2);
+    st_f(dq + r * lddg + ch, o3);
+    ak += o1; av += o2; aq += o3;
     logw -= logf(expf(-lam * (float)t) + 1e-7f);
   }
+  if (dsum != nullptr) { atomicAdd(dsum + ch, ak); atomicAdd(dsum + H + ch, av); atomicAdd(dsum + 2 * (int64_t)H + ch, aq); }
 }
 
 template <typename T, bool PRECISE>
@@ -439,7 +447,7 @@ int scan_bwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const floa
 int sscan_fwd_tma_dispatch(const void*, const void*, const void*, int64_t, const void*, int64_t, const float*, void*, int64_t,
                            float*, float*, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 int sscan_bwd_tma_dispatch(const void*, const void*, const void*, int64_t, const float*, const float*, const void*, int64_t,
-                           void*, void*, void*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+                           void*, void*, void*, int64_t, float*, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 int hscan_fwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const float*, void*, int64_t, float*, int64_t, int64_t,
                            int64_t, int, cudaStream_t);
 int hscan_bwd_tma_dispatch(const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*, const void*, int64_t,
@@ -534,7 +542,7 @@ extern "C" int sc_lucy_sscan_fwd(const void* k, const void* v, const void* q, in
 
 extern "C" int sc_lucy_sscan_bwd(const void* k, const void* v, const void* q, int64_t ldg,
                                  const float* S_all, const float* s0, const void* dA, int64_t ldda,
-                                 void* dk, void* dv, void* dq, int64_t lddg,
+                                 void* dk, void* dv, void* dq, int64_t lddg, float* dsum,
                                  int64_t B, int64_t T, int64_t H, int dtype, int train_mode,
                                  int decay_mode, float lambda_decay, void* stream) {
   SC_CHECK_ARG(scan_args_ok(B, T, H), SC_E_SHAPE);
@@ -544,24 +552,24 @@ extern "C" int sc_lucy_sscan_bwd(const void* k, const void* v, const void* q, in
   SC_CHECK_ARG(k && v && q && S_all && dA && dk && dv && dq, SC_E_BADARG);
   cudaStream_t st = (cudaStream_t)stream;
   if (!scan_force_generic() && decay_mode == 0) {
-    const int rc = sscan_bwd_tma_dispatch(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, B, T, H, dtype, train_mode, st);
+    const int rc = sscan_bwd_tma_dispatch(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, dsum, B, T, H, dtype, train_mode, st);
     if (rc != SC_E_UNSUP) return rc;
   }
   const unsigned blocks = (unsigned)cdiv(B * H, 128);
   if (dtype == SC_BF16) {
     if (decay_mode == 1)
       sscan_bwd_prefix_kernel<bf16, false><<<blocks, 128, 0, st>>>((const bf16*)k, (const bf16*)v, (const bf16*)q, ldg, S_all,
-          (const bf16*)dA, ldda, (bf16*)dk, (bf16*)dv, (bf16*)dq, lddg, (int)B, (int)T, (int)H, lambda_decay);
+          (const bf16*)dA, ldda, (bf16*)dk, (bf16*)dv, (bf16*)dq, lddg, dsum, (int)B, (int)T, (int)H, lambda_decay);
     else
       sscan_bwd_kernel<bf16, false><<<blocks, 128, 0, st>>>((const bf16*)k, (const bf16*)v, (const bf16*)q, ldg, S_all, s0,
-          (const bf16*)dA, ldda, (bf16*)dk, (bf16*)dv, (bf16*)dq, lddg, (int)B, (int)T, (int)H, train_mode, 0, lambda_decay);
+          (const bf16*)dA, ldda, (bf16*)dk, (bf16*)dv, (bf16*)dq, lddg, dsum, (int)B, (int)T, (int)H, train_mode, 0, lambda_decay);
   } else if (dtype == SC_F32) {
     if (decay_mode == 1)
       sscan_bwd_prefix_kernel<float, true><<<blocks, 128, 0, st>>>((const float*)k, (const float*)v, (const float*)q, ldg, S_all,
-          (const float*)dA, ldda, (float*)dk, (float*)dv, (float*)dq, lddg, (int)B, (int)T, (int)H, lambda_decay);
+          (const float*)dA, ldda, (float*)dk, (float*)dv, (float*)dq, lddg, dsum, (int)B, (int)T, (int)H, lambda_decay);
     else
       sscan_bwd_kernel<float, true><<<blocks, 128, 0, st>>>((const float*)k, (const float*)v, (const float*)q, ldg, S_all, s0,
-          (const float*)dA, ldda, (float*)dk, (float*)dv, (float*)dq, lddg, (int)B, (int)T, (int)H, train_mode, 0, lambda_decay);
+          (const float*)dA, ldda, (float*)dk, (float*)dv, (float*)dq, lddg, dsum, (int)B, (int)T, (int)H, train_mode, 0, lambda_decay);
   } else return SC_E_DTYPE;
   SC_LAUNCH_RET();
 }

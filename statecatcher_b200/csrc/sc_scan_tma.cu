@@ -448,6 +448,35 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
     const int t0 = c * TC;
+    if (t0 + TC <= Tn) {
+      // full interval: loads, decay activations and k*v of all steps first (scheduling fence), then the S chain
+      float d[TC][SV], kv[TC][SV], ad[TC][SV];
+#pragma unroll
+      for (int u = 0; u < TC; ++u) {
+        float kk[SV], vv[SV], qq[SV];
+        lds2(st + (0 * TC + u) * CB, k.tid, kk);
+        lds2(st + (1 * TC + u) * CB, k.tid, vv);
+        lds2(st + (2 * TC + u) * CB, k.tid, qq);
+        lds2(st + (3 * TC + u) * CB, k.tid, ad[u]);
+#pragma unroll
+        for (int i = 0; i < SV; ++i) { d[u][i] = sigmoidf_<PRECISE>(qq[i]); kv[u][i] = kk[i] * vv[i]; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < TC; ++u) {
+        float out[SV];
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          S[i] = fmaf(d[u][i], S[i], kv[u][i]);
+          out[i] = ad[u][i] + (TRAIN ? fmaf(d[u][i], S[i], kv[u][i]) : S[i]);
+        }
+        if (k.live) {
+          stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
+          *reinterpret_cast<float2*>(so + (int64_t)(t0 + u) * H) = make_float2(S[0], S[1]);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int u = 0; u < TC; ++u) {
       if (t0 + u < Tn) {
@@ -484,7 +513,9 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
                      const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapDA,
                      const __grid_constant__ CUtensorMap mapS, const float* __restrict__ s0,
                      T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dq, int64_t lddg,
-                     int Tn, int H, int cblocks) {
+                     float* __restrict__ dsum, int Tn, int H, int cblocks) {
+  // dsum (may be null): [3][H] column sums of dk, dv, dq over all rows, added atomically — the bias gradients of the
+  // gate projection, which otherwise cost a pass over the whole gradient tensor (sc_colsum)
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int BOX = TC * CB * (int)sizeof(T);
   constexpr int SBOX = (TC + 1) * CB * 4;
@@ -507,10 +538,11 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
   };
   if (k.tid == 0)
     for (int it = 0; it < NST - 1 && it < k.nchunk; ++it) issue(it);
-  float ds[SV], sfirst[SV];
+  float ds[SV], sfirst[SV], acc[3][SV];
 #pragma unroll
   for (int i = 0; i < SV; ++i) {
     ds[i] = 0.f;
+    acc[0][i] = 0.f; acc[1][i] = 0.f; acc[2][i] = 0.f;
     sfirst[i] = (TRAIN || !k.live) ? 0.f : s0[(int64_t)k.b * H + k.ch + i];
   }
   const int64_t obase = (int64_t)k.b * Tn * lddg + k.ch;
@@ -555,6 +587,7 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
           ok[i] = dkv * vv[i];
           ov[i] = dkv * kk[i];
           oq[i] = dd * d * (1.f - d);
+          acc[0][i] += ok[i]; acc[1][i] += ov[i]; acc[2][i] += oq[i];
         }
         if (k.live) {
           const int64_t o = obase + (int64_t)t * lddg;
@@ -564,6 +597,12 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
         }
       }
     }
+  }
+  if (k.live && dsum != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < SV; ++i) atomicAdd(dsum + (int64_t)g * H + k.ch + i, acc[g][i]);
   }
 }
 
@@ -599,20 +638,42 @@ hscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
     const int t0 = c * TC;
+    if (t0 + TC <= Tn) {
+      // full interval: every step's loads and activations first, behind a scheduling fence, then the carried chain
+      // (same operations in the same order per element; see lucy_scan_fwd_tma_kernel)
+      float cc[TC][SV], zh[TC][SV];
 #pragma unroll
-    for (int u = 0; u < TC; ++u) {
-      if (t0 + u < Tn) {
-        float an[SV], zn[SV], out[SV];
+      for (int u = 0; u < TC; ++u) {
+        float an[SV], zn[SV];
         lds2(st + u * CB, k.tid, an);
         lds2(st + (TC + u) * CB, k.tid, zn);
 #pragma unroll
-        for (int i = 0; i < SV; ++i) {
-          const float cc = tanhf_<PRECISE>(an[i]);
-          const float zh = sigmoidf_<PRECISE>(zn[i]);
-          h[i] = fmaf(zh, h[i] - cc, cc);
-          out[i] = h[i];
-        }
+        for (int i = 0; i < SV; ++i) { cc[u][i] = tanhf_<PRECISE>(an[i]); zh[u][i] = sigmoidf_<PRECISE>(zn[i]); }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < TC; ++u) {
+        float out[SV];
+#pragma unroll
+        for (int i = 0; i < SV; ++i) { h[i] = fmaf(zh[u][i], h[i] - cc[u][i], cc[u][i]); out[i] = h[i]; }
         if (k.live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < TC; ++u) {
+        if (t0 + u < Tn) {
+          float an[SV], zn[SV], out[SV];
+          lds2(st + u * CB, k.tid, an);
+          lds2(st + (TC + u) * CB, k.tid, zn);
+#pragma unroll
+          for (int i = 0; i < SV; ++i) {
+            const float cc = tanhf_<PRECISE>(an[i]);
+            const float zh = sigmoidf_<PRECISE>(zn[i]);
+            h[i] = fmaf(zh, h[i] - cc, cc);
+            out[i] = h[i];
+          }
+          if (k.live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
+        }
       }
     }
   }
@@ -664,6 +725,44 @@ hscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
     const int t0 = chunk * TC;
+    if (t0 + TC <= Tn && t0 > 0) {
+      // full interval that does not hold frame 0: activations and their products of all steps first (scheduling
+      // fence), then the carried chain gz -> gam; same operations in the same order per element
+      float zh[TC][SV], t1[TC][SV], hmc[TC][SV], go[TC][SV];
+#pragma unroll
+      for (int u = TC - 1; u >= 0; --u) {
+        float an[SV], zn[SV], hp[SV];
+        lds2(st + u * CB, k.tid, an);
+        lds2(st + (TC + u) * CB, k.tid, zn);
+        lds2(st + (2 * TC + u) * CB, k.tid, go[u]);
+        lds2(st + (3 * TC + u) * CB, k.tid, hp);
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const float cc = tanhf_<PRECISE>(an[i]);
+          zh[u][i] = sigmoidf_<PRECISE>(zn[i]);
+          t1[u][i] = fmaf(-cc, cc, 1.f);
+          hmc[u][i] = hp[i] - cc;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = TC - 1; u >= 0; --u) {
+        float da[SV], dz[SV];
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const float gam = go[u][i] + gz[i];
+          gz[i] = zh[u][i] * gam;
+          const float omz = 1.f - zh[u][i];
+          da[i] = gam * omz * t1[u][i];
+          dz[i] = gam * hmc[u][i] * zh[u][i] * omz;
+        }
+        if (k.live) {
+          stg_vec<T>(oa + (int64_t)(t0 + u) * lddan, da);
+          stg_vec<T>(oz + (int64_t)(t0 + u) * lddzn, dz);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int u = TC - 1; u >= 0; --u) {
       const int t = t0 + u;
@@ -838,7 +937,7 @@ int sscan_fwd_tma_dispatch(const void* k, const void* v, const void* q, int64_t 
 
 template <typename T, bool PRECISE>
 static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t ldg, const float* S_all, const float* s0,
-                           const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, int64_t B,
+                           const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, float* dsum, int64_t B,
                            int64_t Tn, int64_t H, int train, cudaStream_t st) {
   if (!split_ok<T>({k, v, q, dA, S_all}, {ldg, ldda}, H, B, Tn) || (lddg % 2) ||
       (((uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dq) & (2 * sizeof(T) - 1)))
@@ -856,15 +955,15 @@ static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t 
   auto ks = sscan_bwd_tma_kernel<T, NST, false, PRECISE>;
   int e = set_smem(kt, smem); if (e) return e;
   e = set_smem(ks, smem); if (e) return e;
-  if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, (int)Tn, (int)H, cblocks);
-  else       ks<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, (int)Tn, (int)H, cblocks);
+  if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
+  else       ks<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
   SC_LAUNCH_RET();
 }
 int sscan_bwd_tma_dispatch(const void* k, const void* v, const void* q, int64_t ldg, const float* S_all, const float* s0,
-                           const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, int64_t B,
+                           const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, float* dsum, int64_t B,
                            int64_t T, int64_t H, int dtype, int train, cudaStream_t st) {
-  if (dtype == SC_BF16) return sscan_bwd_tma_t<bf16, false>(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, B, T, H, train, st);
-  if (dtype == SC_F32) return sscan_bwd_tma_t<float, true>(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, B, T, H, train, st);
+  if (dtype == SC_BF16) return sscan_bwd_tma_t<bf16, false>(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, dsum, B, T, H, train, st);
+  if (dtype == SC_F32) return sscan_bwd_tma_t<float, true>(k, v, q, ldg, S_all, s0, dA, ldda, dk, dv, dq, lddg, dsum, B, T, H, train, st);
   return SC_E_DTYPE;
 }
 

@@ -299,13 +299,22 @@ class _LucyLayerFn(torch.autograd.Function):
                 dAn = dA_final if meta.fused else torch.empty(M, H, dtype=cd, device=dev)
                 dZn = dblk(0)
             ops.hscan_bwd(An, Zn, Hout, h0, g2, dAn, dZn, B, T, H)
+            # bias gradients of the gate projection = column sums of dG: formed by the kernels that write dG's blocks
+            # (LayerNorm backward for z and, when fused, p; the S-scan backward for k, v, q) instead of by a pass
+            # over the whole tensor; blocks nobody sums (no LayerNorm: z, p) fall back to sc_colsum below
+            dbg = torch.zeros(nblk * H, dtype=torch.float32, device=dev)
+            summed = [False] * nblk
             if meta.ln:
                 w_in, w_z, w_h = ctx.lnp
                 dA2_buf = dA_final if meta.fused else torch.empty(M, H, dtype=cd, device=dev)
-                dA2, dw, db = ops.layernorm_bwd(dAn, A2, w_h, sv["mu_h"], sv["rs_h"], dx=dA2_buf)
+                dA2, dw, db = ops.layernorm_bwd(dAn, A2, w_h, sv["mu_h"], sv["rs_h"], dx=dA2_buf,
+                                                dxsum=dbg[3 * H:4 * H] if meta.fused else None)
                 grads[gi["layernorm_h.weight"]], grads[gi["layernorm_h.bias"]] = dw, db
-                _, dw, db = ops.layernorm_bwd(dZn, blk(0), w_z, sv["mu_z"], sv["rs_z"], dx=dblk(0))
+                _, dw, db = ops.layernorm_bwd(dZn, blk(0), w_z, sv["mu_z"], sv["rs_z"], dx=dblk(0), dxsum=dbg[:H])
                 grads[gi["layernorm_z.weight"]], grads[gi["layernorm_z.bias"]] = dw, db
+                summed[0] = True
+                if meta.fused:
+                    summed[3] = True
             else:
                 dA2 = dAn
             if meta.fused:
@@ -316,9 +325,20 @@ class _LucyLayerFn(torch.autograd.Function):
                 grads[gi["W_h.bias"]] = ops.colsum(dA2)
                 dA = ops.gemm_dgrad(dA2, W_h, out=dA_final)
                 du_extra = dA                                       # addend was u (lucyrnn.py:62)
-            ops.sscan_bwd(blk(1), blk(2), blk(qi), S_all, s0, dA, dblk(1), dblk(2), dblk(qi),
-                          B, T, H, meta.train_mode, meta.decay_mode, meta.lam)
-            dbg = ops.colsum(dG)
+            if qi == 3:                                             # k, v, q adjacent: blocks 1..3
+                ksum = dbg[H:4 * H]
+                ops.sscan_bwd(blk(1), blk(2), blk(qi), S_all, s0, dA, dblk(1), dblk(2), dblk(qi),
+                              B, T, H, meta.train_mode, meta.decay_mode, meta.lam, dsum=ksum)
+            else:                                                   # fused: k, v in blocks 1, 2 and q in block 4
+                ksum = torch.zeros(3 * H, dtype=torch.float32, device=dev)
+                ops.sscan_bwd(blk(1), blk(2), blk(qi), S_all, s0, dA, dblk(1), dblk(2), dblk(qi),
+                              B, T, H, meta.train_mode, meta.decay_mode, meta.lam, dsum=ksum)
+                dbg[H:3 * H].copy_(ksum[:2 * H])
+                dbg[4 * H:].copy_(ksum[2 * H:])
+            summed[1] = summed[2] = summed[qi] = True
+            for i, done in enumerate(summed):
+                if not done:
+                    ops.colsum(dblk(i), out=dbg[i * H:(i + 1) * H])
         # gate projection backward
         if meta.fused:
             dWf = torch.empty(6 * H, H, dtype=torch.float32, device=dev)
@@ -336,12 +356,14 @@ class _LucyLayerFn(torch.autograd.Function):
         if du_extra is not None:
             du.add_(du_extra)
         if meta.ln:
-            dpre, dw, db = ops.layernorm_bwd(du, pre, ctx.lnp[0], sv["mu_in"], sv["rs_in"])
+            db_in = torch.zeros(H, dtype=torch.float32, device=dev)
+            dpre, dw, db = ops.layernorm_bwd(du, pre, ctx.lnp[0], sv["mu_in"], sv["rs_in"], dxsum=db_in)
             grads[gi["layernorm_in.weight"]], grads[gi["layernorm_in.bias"]] = dw, db
         else:
             dpre = du
+            db_in = ops.colsum(dpre)
         grads[gi["input_proj.weight"]] = ops.gemm_wgrad(dpre, x2)
-        grads[gi["input_proj.bias"]] = ops.colsum(dpre)
+        grads[gi["input_proj.bias"]] = db_in
         dx = None
         if ctx.needs_input_grad[1]:
             dx = ops.gemm_dgrad(dpre, W_in).view(B, T, Fin)

@@ -152,15 +152,15 @@ def layernorm_fwd(x, w, b, out=None):
     return out, mean, rstd
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dx=None):
-    """Returns dx, dw, db (dw/db fresh fp32)."""
+def layernorm_bwd(dy, x, w, mean, rstd, dx=None, dxsum=None):
+    """Returns dx, dw, db (dw/db fresh fp32).  dxsum (optional): fp32 [H], receives += the column sums of dx."""
     M, H = x.shape
     if dx is None:
         dx = torch.empty(M, H, dtype=x.dtype, device=x.device)
     dw = torch.zeros(H, dtype=torch.float32, device=x.device)
     db = torch.zeros(H, dtype=torch.float32, device=x.device)
     call("sc_layernorm_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(w), ptr(mean), ptr(rstd),
-         ptr(dx), _ld(dx), ptr(dw), ptr(db), M, H, dt(x), stream())
+         ptr(dx), _ld(dx), ptr(dw), ptr(db), ptr(dxsum), M, H, dt(x), stream())
     return dx, dw, db
 
 
@@ -207,10 +207,11 @@ def sscan_fwd(k, v, q, addend, s0, B, T, H, train_mode, decay_mode, lam):
     return A, S_all, sT
 
 
-def sscan_bwd(k, v, q, S_all, s0, dA, dk, dv, dq, B, T, H, train_mode, decay_mode, lam):
+def sscan_bwd(k, v, q, S_all, s0, dA, dk, dv, dq, B, T, H, train_mode, decay_mode, lam, dsum=None):
+    """dsum (optional): fp32 [3*H], receives += the column sums of dk, dv, dq."""
     assert _ld(k) == _ld(v) == _ld(q) and _ld(dk) == _ld(dv) == _ld(dq)
     call("sc_lucy_sscan_bwd", ptr(k), ptr(v), ptr(q), _ld(k), ptr(S_all), ptr(s0), ptr(dA), _ld(dA),
-         ptr(dk), ptr(dv), ptr(dq), _ld(dk), B, T, H, dt(k), int(train_mode), int(decay_mode), float(lam), stream())
+         ptr(dk), ptr(dv), ptr(dq), _ld(dk), ptr(dsum), B, T, H, dt(k), int(train_mode), int(decay_mode), float(lam), stream())
 
 
 def hscan_fwd(An, Zn, h0, B, T, H):

@@ -87,8 +87,8 @@ def test_module_errors(cuda_device):
 
 @pytest.mark.parametrize("name", ["medium_train_fused_noln", "medium_train_fused_ln", "step_fused_noln"])
 def test_module_bf16_within_stated_bound(cuda_device, name):
-    """bf16 compute path vs the fp32 golden: stated bound rel-L2 <= 3e-2 on logits and
-    <= 6e-2 on weight grads (the reference's own fp32->bf16 autocast drift is 1e-2/1.5e-2)."""
+    """bf16 compute path vs the fp32 golden: stated bound rel-L2 <= 2e-2 on logits and
+    <= 3e-2 on weight grads = 2x the reference's own fp32->bf16 autocast drift (1e-2 / 1.5e-2)."""
     G = load_golden("lucy_" + name)
     sb, cfg, model = _build(G, compute_dtype=torch.bfloat16)
     crit = sb.CTCLoss(blank=0, zero_infinity=True)
@@ -96,17 +96,17 @@ def test_module_bf16_within_stated_bound(cuda_device, name):
     logits, state = model(x)
     rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)   # noqa: E731
     assert logits.dtype == torch.bfloat16
-    assert rel(logits.float().detach().cpu().numpy(), G["seg0/logits"]) <= 3e-2
+    assert rel(logits.float().detach().cpu().numpy(), G["seg0/logits"]) <= 2e-2
     assert state[0][0].dtype == torch.float32
     loss = crit(logits.transpose(0, 1), torch.tensor(G["seg0/tokens"]).cuda(),
                 G["seg0/in_lens"].tolist(), G["seg0/tgt_lens"].tolist())
-    assert abs(loss.item() - G["seg0/loss"]) <= 3e-2 * abs(G["seg0/loss"])
+    assert abs(loss.item() - G["seg0/loss"]) <= 2e-2 * abs(G["seg0/loss"])
     loss.backward()
     for k, p in model.named_parameters():
         want = G["seg0/grad/" + k]
         if np.abs(want).max() == 0:
             continue
-        assert rel(p.grad.cpu().numpy(), want) <= 6e-2, (k, rel(p.grad.cpu().numpy(), want))
+        assert rel(p.grad.cpu().numpy(), want) <= 3e-2, (k, rel(p.grad.cpu().numpy(), want))
 
 
 def test_autocast_selects_bf16_path(cuda_device):
@@ -228,7 +228,7 @@ def test_module_vs_fp64_oracle_at_width_256(cuda_device, dtype):
     loss = sb.ctc_loss_from_logits(logits, toks.cuda(), inl, tgl, zero_infinity=True)
     loss.backward()
     rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)   # noqa: E731
-    lt, gt = (2e-5, 2e-4) if dtype == torch.float32 else (3e-2, 6e-2)
+    lt, gt = (2e-5, 2e-4) if dtype == torch.float32 else (2e-2, 3e-2)
     assert rel(logits.float().detach().cpu().numpy(), ref_logits[0].numpy()) <= lt
     assert abs(loss.item() - ref_losses[0].item()) <= max(lt, 1e-4) * abs(ref_losses[0].item())
     assert rel(torch.stack(state[0]).cpu().numpy(), torch.stack(ref_state[0]).detach().numpy()) <= lt
