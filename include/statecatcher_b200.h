@@ -16,7 +16,8 @@
  *     thread may call concurrently, for one or several devices of a process).  The only state the
  *     library keeps is a set of one-time, per-DEVICE caches published through atomics (SM count,
  *     'max dynamic shared memory already raised for this kernel') and environment switches
- *     (SC_*) latched once, immutable afterwards;
+ *     (SC_*) latched once, immutable afterwards; sc_ctc_head additionally keeps a per-thread, per-device pool of
+ *     timing-disabled CUDA events (created on first use) for its cross-stream ordering;
  *   - kernels are launched on the CUDA runtime's CURRENT device: the caller selects the device
  *     that owns the pointers first (the Python layer does: `torch.cuda.device_of(tensor)`);
  *   - every call takes the cudaStream_t to launch on (as void*), and only enqueues work;
