@@ -71,10 +71,11 @@ def _same(a, b, what):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("V", [96, 256], ids=["V96", "V256"])
 @pytest.mark.parametrize("T,phases", [(700, 2), (700, 3), (1000, 5), (1000, 8), (450, 0), (3000, 0), (130, 2), (64, 4)])
-def test_head_equals_the_three_passes(cuda_device, dtype, T, phases):
+def test_head_equals_the_three_passes(cuda_device, dtype, T, phases, V):
     from statecatcher_b200._lib import load
-    B, V, U = 7, 96, 40
+    B, U = 7, 40
     x, tok, il, tl = _case(B, T, V, U, 100 + T + phases, dtype)
     P = load().sc_ctc_head_phases(T, U, phases)
     assert P >= 2 or T <= 64 or (phases == 0 and T < 768)
@@ -181,3 +182,29 @@ def test_head_inside_a_stream_capture(cuda_device, monkeypatch):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(xs.grad, want_g) and torch.equal(l.detach(), want_l)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("V,U", [(256, 60), (1024, 150), (2048, 300), (128, 20)])
+def test_gradient_with_repeated_labels(cuda_device, dtype, V, U):
+    """Transcripts drawn from 5 symbols, so every label repeats many times and the scatter of the label occupancies
+    sums into the same vocabulary entries; one transcript holds the blank index itself; all three lattice widths of
+    the gradient kernel; against torch's fp64 CTC on the same (rounded) logits."""
+    import statecatcher_b200 as sb
+    g = torch.Generator().manual_seed(V + U)
+    B, T = 4, 2 * U + 40
+    x0 = (torch.randn(B, T, V, generator=g) * 1.5).to(dtype).cuda()
+    tok = torch.randint(1, 6, (B, U), generator=g).cuda()
+    tok[2, 3] = 0                                                            # the blank as a label (torch tolerates it)
+    il = torch.tensor([T, T - 7, T, T // 2 + U], device="cuda")
+    tl = torch.tensor([U, U // 2, U - 1, U // 3], device="cuda")
+    x = x0.clone().requires_grad_(True)
+    loss = sb.ctc_loss_from_logits(x, tok, il, tl, reduction="sum", zero_infinity=True)
+    loss.backward()
+    xr = x0.double().requires_grad_(True)
+    want = torch.nn.functional.ctc_loss(xr.log_softmax(-1).transpose(0, 1), tok, il, tl, blank=0, reduction="sum",
+                                        zero_infinity=True)
+    want.backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-5)
+    tol = dict(rtol=1e-4, atol=2e-6) if dtype == torch.float32 else dict(rtol=8e-3, atol=2e-3)
+    np.testing.assert_allclose(x.grad.float().cpu().numpy(), xr.grad.cpu().numpy(), **tol)
