@@ -19,6 +19,13 @@
 
 namespace sc {
 
+// label count of utterance b, held inside the lattice the caller allocated (a length the host never saw — lengths may be
+// device tensors — must not index past U1-1 columns; torch / warp_rnnt raise on the host for such input)
+__device__ __forceinline__ int64_t rnnt_label_len(const int64_t* __restrict__ label_lens, int b, int U1) {
+  const int64_t u = label_lens[b];
+  return u < 0 ? 0 : (u > U1 - 1 ? U1 - 1 : u);
+}
+
 #define NEG_INF (-INFINITY)
 constexpr int RNNT_EB = 16;
 
@@ -38,7 +45,7 @@ __global__ void rnnt_gather_kernel(const float* __restrict__ lp, const int64_t* 
   const int t = (int)((i / U1) % Tn);
   const int b = (int)(i / ((int64_t)U1 * Tn));
   int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
-  const int64_t Ub = label_lens[b];
+  const int64_t Ub = rnnt_label_len(label_lens, b, U1);
   if (t >= Tb || u > Ub) return;
   // padded (B,T,U1,V) layout, or the compact packing of model.py:147-200: utterance b starts at
   // row_offsets[b] and holds T_b x (U_b+1) rows
@@ -60,7 +67,7 @@ __global__ void rnnt_alpha_beta_kernel(const float* __restrict__ eb, const float
   __shared__ __align__(8) uint64_t ebar[2];
   const int b = blockIdx.x, dir = blockIdx.y;
   int64_t Tb64 = frame_lens[b]; if (Tb64 > Tn) Tb64 = Tn;
-  const int Tb = (int)Tb64, Ub = (int)label_lens[b];
+  const int Tb = (int)Tb64, Ub = (int)rnnt_label_len(label_lens, b, U1);
   if (Tb <= 0) {
     if (dir == 0 && threadIdx.x == 0) nll[b] = 0.f;        // no frames: zero loss, zero gradient
     return;
@@ -189,7 +196,7 @@ __global__ void rnnt_grad_kernel(const float* __restrict__ eb, const float* __re
   const int t = (int)((i / U1) % Tn);
   const int b = (int)(i / ((int64_t)U1 * Tn));
   int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
-  const int64_t Ub = label_lens[b];
+  const int64_t Ub = rnnt_label_len(label_lens, b, U1);
   if (t >= Tb || u > Ub) return;
   const int64_t D = Tn + U1;
   const int64_t base = (int64_t)b * D * U1p;
@@ -382,7 +389,7 @@ rnnt_lse_gather_kernel(const T* __restrict__ logits, const int64_t* __restrict__
     const int tc = (int)(bt - (unsigned)b * (unsigned)Tc);
     const int t = t0 + tc;
     int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
-    const int64_t Ub = label_lens[b];
+    const int64_t Ub = rnnt_label_len(label_lens, b, U1);
     if (t >= Tb || u > Ub) continue;
     const T* x = logits + (int64_t)row * V;
     const float l = warp_row_lse<T>(x, V, lane);
@@ -408,7 +415,7 @@ __global__ void rnnt_node_grad_kernel(const float* __restrict__ eb, const float*
   const int t = (int)((i / U1) % Tn);
   const int b = (int)(i / ((int64_t)U1 * Tn));
   int64_t Tb = frame_lens[b]; if (Tb > Tn) Tb = Tn;
-  const int64_t Ub = label_lens[b];
+  const int64_t Ub = rnnt_label_len(label_lens, b, U1);
   float vb = 0.f, vl = 0.f;
   if (t < Tb && u <= Ub) {
     const int64_t D = Tn + U1;
@@ -475,7 +482,7 @@ rnnt_dlogits_vec_kernel(const T* __restrict__ logits, const float* __restrict__ 
     const T* x = logits + (int64_t)row * V;
     const float l2 = lse[node] * 1.4426950408889634f;
     const float tot = vb + vl;
-    const int lab = (u < label_lens[b]) ? (int)labels[(int64_t)b * ldl + u] : -1;
+    const int lab = (u < rnnt_label_len(label_lens, b, U1)) ? (int)labels[(int64_t)b * ldl + u] : -1;
     Vec<T, VW> raw[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -546,7 +553,7 @@ rnnt_dlogits_kernel(const T* __restrict__ logits, const float* __restrict__ lse,
   const T* x = logits + row * V;
   const float l = lse[node];
   const float tot = vb + vl;
-  const int64_t lab = (u < label_lens[b]) ? labels[(int64_t)b * ldl + u] : -1;
+  const int64_t lab = (u < rnnt_label_len(label_lens, b, U1)) ? labels[(int64_t)b * ldl + u] : -1;
   for (int i = lane; i < V; i += 32) {
     float g = -tot * __expf(ld_f(x + i) - l);
     if (i == blank) g += vb;

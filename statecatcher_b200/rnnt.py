@@ -75,7 +75,7 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
     lab = labels.to(device=x.device, dtype=torch.int64).contiguous()
     B = lab.size(0)
     fl, _ = _lens(frames_lengths, x.device, B, "frames_lengths")
-    ll, _ = _lens(labels_lengths, x.device, B, "labels_lengths")
+    ll, ll_max = _lens(labels_lengths, x.device, B, "labels_lengths")
     if compact:
         if x.dim() != 2:
             raise ValueError("compact rnnt_loss expects (rows, V) log-probs")
@@ -90,6 +90,8 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, blank: int = 0,
     _, T, U1, V = x.shape
     if lab.dim() != 2 or x.size(0) != B or lab.size(1) < U1 - 1:
         raise ValueError("labels must be (B,U) with U >= log_probs.size(2)-1")
+    if ll_max is not None and ll_max > U1 - 1:              # list lengths (what model.py passes): checked on the host, as
+        raise ValueError(f"labels_lengths up to {ll_max} exceed the lattice width {U1 - 1}")   # warp_rnnt / torchaudio do
     return _reduce(_RNNTFn.apply(x, lab, fl, ll, int(blank), None, T, U1), reduction)
 
 
@@ -298,7 +300,9 @@ class RNNTFusedHead(nn.Module):
         tokens = tokens.to(device=enc_out.device, dtype=torch.int64).contiguous()
         prefix = torch.cat([torch.full((B, 1), blank_id, dtype=torch.int64, device=enc_out.device), tokens], dim=1)
         fl, _ = _lens(frames_lengths, enc_out.device, B, "frames_lengths")
-        ll, _ = _lens(labels_lengths, enc_out.device, B, "labels_lengths")
+        ll, ll_max = _lens(labels_lengths, enc_out.device, B, "labels_lengths")
+        if ll_max is not None and ll_max > tokens.size(1):
+            raise ValueError(f"labels_lengths up to {ll_max} exceed the {tokens.size(1)} tokens given")
         cd = _compute_dtype(enc_out, self.compute_dtype)
         pred_emb = self.embedding(prefix)
         nll = _RNNTFusedFn.apply(enc_out.contiguous(), pred_emb.contiguous(), tokens, fl, ll, int(blank_id),

@@ -59,6 +59,8 @@ def test_argument_errors(rec):
         sb.rnnt_loss(lp, torch.zeros(2, 3, dtype=torch.int64), [5], [2, 2])          # batch mismatch
     with pytest.raises(ValueError):
         sb.rnnt_loss(lp[0], torch.zeros(2, 3, dtype=torch.int64), [5, 5], [2, 2])    # not 4-D
+    with pytest.raises(ValueError):
+        sb.rnnt_loss(lp, torch.zeros(2, 5, dtype=torch.int64), [5, 5], [2, 4])       # a transcript longer than the lattice (U = 3)
     assert not rec
     with pytest.raises(ValueError):
         sb.rnnt_loss(lp, torch.zeros(2, 3, dtype=torch.int64), [5, 5], [2, 2], reduction="avg")
