@@ -14,7 +14,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libstatecatcher_b200.so")
+LIB_PATH = os.environ.get("SC_B200_LIB") or os.path.join(_HERE, "csrc", "libstatecatcher_b200.so")   # SC_B200_LIB: A/B builds
 
 SC_F32, SC_BF16 = 0, 1
 SC_SCAN_CKPT = 8

@@ -20,7 +20,11 @@
 namespace sc {
 
 constexpr int TC = SC_SCAN_CKPT;     // timesteps per stage == checkpoint interval
-constexpr int CB = 256;              // channels per CTA (bf16: 512-byte rows)
+#ifndef SC_SCAN_CB
+#define SC_SCAN_CB 256
+#endif
+constexpr int CB = SC_SCAN_CB;       // channels per CTA (bf16: 512-byte rows).  r02, -DSC_SCAN_CB=128 (512 CTAs of 2 warps, 5 per SM) against 256
+                                     // in alternating same-box steps: fwd 2.53 vs 2.46-2.74 ms, bwd 5.30-5.33 vs 5.14-5.18 ms per step: 256 stays
 // channels per thread (VEC) is a template parameter: 1 doubles the resident warps per SM (16
 // instead of 8), 2 halves the instruction count per channel
 
