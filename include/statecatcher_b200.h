@@ -154,7 +154,9 @@ int sc_lucy_scan_bwd(const void* G, int64_t ldg, const void* Hout, int64_t ldh,
  * sscan: S scan + second application; A[b,t,:] = addend[b,t,:] + s'_t where addend is the
  *        'h_pre' chunk (fused, lucyrnn.py:54) or u (unfused, lucyrnn.py:62).
  *        decay_mode 0 = learned sigmoid(q) (lucyrnn.py:124), 1 = prefix_sum with
- *        lambda_decay (lucyrnn.py:126-142; training path only).  S_all [B,T,H] fp32 saved.
+ *        lambda_decay (lucyrnn.py:126-142; training path only).  S_all, fp32, is what the backward needs:
+ *        decay_mode 0: [B, ceil(T/SC_SCAN_CKPT), H], S entering each interval (entry 0 = the initial state; the
+ *        backward recomputes S_t inside an interval); decay_mode 1: [B,T,H], every S_t.
  * hscan: c=tanh(An); zh=sigmoid(Zn); h_t=(1-zh)c+zh*h_{t-1}.
  * sscan_bwd's dsum (may be null): [3][H] fp32, the column sums of dk, dv, dq are ADDED to it (bias gradients). */
 int sc_lucy_sscan_fwd(const void* k, const void* v, const void* q, int64_t ldg,
@@ -187,8 +189,10 @@ int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn
  * to T; an utterance with U_b < 0 or U_b > Umax, or with a label outside [0, V), is reported infeasible
  * (nll = +inf, zero gradient row) instead of reading out of bounds.
  * Workspaces (caller-allocated, 16-byte aligned): lse [B,T] fp32, cshift [B,T] fp32 (per-frame shift
- * taken out of the lattice emissions: the largest of them, log2 units), lplat/alpha/beta [B,T,S] 4-byte
- * cells with S = 2*Umax+1 rounded up to a multiple of 4, and the opaque `ws` of
+ * taken out of the lattice emissions: the largest of them, log2 units), alpha/beta [B,T,S] 4-byte
+ * cells with S = 2*Umax+1 rounded up to a multiple of 8 (whole 32-byte sectors), lplat [B,T,sc_ctc_lplat_pitch(Umax)] 4-byte cells
+ * (>= S; wider for narrow lattices, whose emission rows keep the pitch of the recursion's shared-memory
+ * rows so that a block of them is one bulk copy), and the opaque `ws` of
  * sc_ctc_workspace_bytes(B, T, Umax) bytes (per-utterance format flags, per-direction likelihoods and range
  * records).  The CONTENT of lplat/alpha/beta is private to the three passes and depends on Umax:
  *   Umax <= 255: fp64 linear-domain recursion (csrc/sc_ctc_lin64.cuh) — lplat rows hold U+1 emission
@@ -200,6 +204,7 @@ int sc_lucy_hscan_bwd(const void* An, int64_t ldan, const void* Zn, int64_t ldzn
  * loss [1] = reduction of nll: reduction 0 none (loss untouched), 1 mean
  * = mean_b(nll_b/max(U_b,1)), 2 sum; infeasible utterances contribute 0 (zero_infinity). */
 int64_t sc_ctc_workspace_bytes(int64_t B, int64_t T, int64_t Umax);
+int64_t sc_ctc_lplat_pitch(int64_t Umax);
 int sc_ctc_fwd(const void* logits, int64_t stride_b, int64_t stride_t, int dtype,
                const int64_t* targets, int64_t ldt, const int64_t* in_lens,
                const int64_t* tgt_lens, int64_t B, int64_t T, int64_t V, int64_t Umax,

@@ -19,9 +19,9 @@ x = (torch.randn(B, T, V, generator=g, device="cuda") * 2).bfloat16()
 tok = tok.cuda()
 U = int(max(tgl))
 il, tl = torch.tensor(inl).cuda(), torch.tensor(tgl).cuda()
-S = (2 * U + 1 + 3) & ~3
+S = (2 * U + 1 + 7) & ~7
 f32 = dict(dtype=torch.float32, device="cuda")
-lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, S, **f32), torch.zeros(B, T, **f32)
+lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, load().sc_ctc_lplat_pitch(U), **f32), torch.zeros(B, T, **f32)
 alpha, beta = torch.zeros(B, T, S, **f32), torch.zeros(B, T, S, **f32)
 nll, loss, one = torch.zeros(B, **f32), torch.zeros((), **f32), torch.ones((), **f32)
 ws = torch.zeros(load().sc_ctc_workspace_bytes(B, T, U) // 8 + 1, dtype=torch.float64, device="cuda")

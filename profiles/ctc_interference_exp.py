@@ -19,12 +19,12 @@ x = (torch.randn(B, T, V, generator=g, device="cuda") * 2).bfloat16()
 tok = tok.cuda()
 U = int(max(tgl))
 il, tl = torch.tensor(inl).cuda(), torch.tensor(tgl).cuda()
-S = (2 * U + 1 + 3) & ~3
+S = (2 * U + 1 + 7) & ~7
 f32 = dict(dtype=torch.float32, device="cuda")
 
 
 def bufs():
-    return dict(lse=torch.zeros(B, T, **f32), lplat=torch.zeros(B, T, S, **f32), csh=torch.zeros(B, T, **f32),
+    return dict(lse=torch.zeros(B, T, **f32), lplat=torch.zeros(B, T, load().sc_ctc_lplat_pitch(U), **f32), csh=torch.zeros(B, T, **f32),
                 alpha=torch.zeros(B, T, S, **f32), beta=torch.zeros(B, T, S, **f32), nll=torch.zeros(B, **f32),
                 loss=torch.zeros((), **f32), dx=torch.empty_like(x),
                 ws=torch.zeros(load().sc_ctc_workspace_bytes(B, T, U) // 8 + 1, dtype=torch.float64, device="cuda"))

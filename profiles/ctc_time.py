@@ -10,7 +10,9 @@ import bench  # noqa: E402
 import statecatcher_b200 as sb  # noqa: E402
 from statecatcher_b200 import _lib  # noqa: E402
 
-W = bench.WORKLOADS["cfg2"]
+W = dict(bench.WORKLOADS["cfg2"])
+if os.environ.get("CTC_UMAX"):                 # lattice width study: transcripts of umax/2 .. umax labels
+    W["umax"] = int(os.environ["CTC_UMAX"]); W["umin"] = max(1, W["umax"] - 2)
 _, tok, inl, tgl = bench.synth_batch(W, 1234)
 g = torch.Generator(device="cuda").manual_seed(0)
 x = (torch.randn(W["B"], W["T"], W["V"], generator=g, device="cuda") * 2).bfloat16().requires_grad_(True)

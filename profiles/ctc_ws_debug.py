@@ -13,9 +13,9 @@ g = torch.Generator(device="cuda").manual_seed(0)
 x = (torch.randn(B, T, V, generator=g, device="cuda") * 2).bfloat16()
 tok = tok.cuda(); U = tok.size(1)
 il, tl = torch.tensor(inl).cuda(), torch.tensor(tgl).cuda()
-S = (2 * U + 1 + 3) & ~3
+S = (2 * U + 1 + 7) & ~7
 f32 = dict(dtype=torch.float32, device="cuda")
-lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, S, **f32), torch.zeros(B, T, **f32)
+lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, _lib.load().sc_ctc_lplat_pitch(U), **f32), torch.zeros(B, T, **f32)
 alpha, beta = torch.zeros(B, T, S, **f32), torch.zeros(B, T, S, **f32)
 nll, loss = torch.zeros(B, **f32), torch.zeros((), **f32)
 nb = _lib.load().sc_ctc_workspace_bytes(B, T, U)

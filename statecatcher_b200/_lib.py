@@ -45,6 +45,7 @@ SIGNATURES = {
     "sc_lucy_hscan_fwd": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I32, P],
     "sc_lucy_hscan_bwd": [P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I64, I64, I64, I32, P],
     "sc_ctc_workspace_bytes": [I64, I64, I64],
+    "sc_ctc_lplat_pitch": [I64],
     "sc_ctc_fwd": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, I32, P, P],
     "sc_ctc_emissions": [P, I64, I64, I32, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P],
     "sc_ctc_lattice": [P, P, P, I64, P, P, I64, I64, I64, I64, P, P, P, P, I32, P, P],
@@ -79,7 +80,7 @@ SIGNATURES = {
     "sc_frame_mask": [P, I64, I64, I64, I64, I64, F32, I64, P, P, P],
 }
 _RESTYPES = {"sc_error_string": c_char_p, "sc_gemm_workspace_bytes": I64, "sc_lucy_scan_chunked_work_bytes": I64,
-             "sc_ctc_workspace_bytes": I64, "sc_ctc_head_phases": I64,
+             "sc_ctc_workspace_bytes": I64, "sc_ctc_lplat_pitch": I64, "sc_ctc_head_phases": I64,
              "sc_frontend_tables_len": I64}
 
 _lib = None

@@ -426,7 +426,7 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   const int nwarps = (int)(blockDim.x >> 5);
   const double shift_sum = dir == 0 ? block_shift_sum(cshift + (int64_t)b * Tn, Tb, dred) : 0.0;
   float* ebuf = sm;
-  const int EP = FMT == 1 ? LP : Smax;                           // pitch of an emission row
+  const int EP = FMT == 1 ? lin_row_pitch(U) : Smax;             // pitch of an emission row (FMT 1: this utterance's, inside a region of LP words per frame)
   int* slots = reinterpret_cast<int*>(sm + 2 * (size_t)EB * EP);     // [nwarps][EB+1] x {value, tag}
   for (int k = i; k < nwarps * (EB + 1) * 2; k += blockDim.x) slots[k] = -1;
   if (i == 0) {
@@ -453,7 +453,7 @@ ctc_wave2_body(float* __restrict__ sm, const float* __restrict__ lplat, const fl
   const int eb_pos = FMT == 1 ? 0 : sb;
   const int el_pos = FMT == 1 ? (hasl ? (dir == 0 ? 1 + i : U - i) : 0) : sl;
   auto ld_e = [](const float* q) -> float { return FMT == 1 ? lin_word_to_log2(__float_as_uint(*q)) : *q; };
-  const float* lp_b = lplat + (int64_t)b * Tn * EP;
+  const float* lp_b = lplat + (int64_t)b * Tn * (FMT == 1 ? LP : Smax);
   float* out_b = (dir == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
   const int nvis = (Tb + EB - 1) / EB;
   auto blk_of = [&](int vi) { return dir == 0 ? vi : nvis - 1 - vi; };
@@ -789,7 +789,16 @@ static bool ctc_use_lin(int64_t Umax) {
   static const bool off = [] { const char* e = getenv("SC_CTC_LIN"); return e && e[0] == '0'; }();
   return !off && Umax + 1 <= 32 * LIN_MAXK;
 }
-static int ctc_lin_pitch(int64_t Umax) { return (int)((Umax + 1 + 4) & ~(int64_t)3); }   // U+1 emissions + at least one zero word (the last)
+static int ctc_lin_pitch(int64_t Umax) { return lin_row_pitch((int)Umax); }   // words reserved per frame: the widest utterance's row (U+1 emissions, a zero word, padding to 32 K + 4)
+
+// 4-byte words per frame the caller reserves for `lplat`: the lattice row (S = 2 Umax + 1 rounded up to 4) or, where the
+// fp64 kernel serves, the emission row at ITS pitch if that is wider (narrow lattices)
+extern "C" int64_t sc_ctc_lplat_pitch(int64_t Umax) {
+  if (Umax < 0) return 4;
+  const int64_t S = (2 * Umax + 1 + 7) & ~(int64_t)7;
+  const int64_t LP = ctc_use_lin(Umax) ? ctc_lin_pitch(Umax) : 0;
+  return S > LP ? S : LP;
+}
 
 extern "C" int64_t sc_ctc_workspace_bytes(int64_t B, int64_t T, int64_t Umax) {
   (void)Umax;
@@ -824,7 +833,7 @@ extern "C" int sc_ctc_emissions(const void* logits, int64_t stride_b, int64_t st
   SC_CHECK_ARG(dtype == SC_F32 || dtype == SC_BF16, SC_E_DTYPE);
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);      // row width of lplat/alpha/beta (16-B rows)
+  const int Smax = (int)((2 * Umax + 1 + 7) & ~(int64_t)7);      // row width of alpha/beta: whole 32-byte sectors
   if (ctc_use_lin(Umax))
     return launch_emissions_lin(logits, stride_b, stride_t, dtype, targets, ldt, in_lens, tgt_lens, B, T, V, Umax, blank,
                                 lse, lplat, cshift, 0, (int)T, st);
@@ -878,7 +887,7 @@ static int launch_lin64(const float* lplat, const int64_t* targets, int64_t ldt,
                         cudaStream_t st) {
   // alpha over frames [a0, a1), beta over [b0, b1) (a0, b0 multiples of LIN_EB); the whole segment: 0, T, 0, T
   const int Kmax = (int)((Umax + 32) >> 5);
-  auto need = [&](int nb) { return (2 * (size_t)LIN_EB * (32 * Kmax + 4) + (size_t)nb * LIN_ROWS * 64 * Kmax) * sizeof(uint32_t); };
+  auto need = [&](int nb) { return (2 * (size_t)LIN_EB * (32 * Kmax + LIN_EPAD) + (size_t)nb * LIN_ROWS * 64 * Kmax) * sizeof(uint32_t); };
   const bool deep = need(LIN_NB) <= 200 * 1024;                  // the widest lattices (7 or 8 pairs per lane) get the shorter ring
   const size_t smem = need(deep ? LIN_NB : LIN_NB_WIDE);
   auto kern = deep ? ctc_lin64_kernel<LIN_NB> : ctc_lin64_kernel<LIN_NB_WIDE>;
@@ -914,7 +923,7 @@ extern "C" int sc_ctc_lattice(const float* lplat, const float* cshift, const int
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31) && Umax < (1 << 20), SC_E_SHAPE);
   SC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 7) == 0, SC_E_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
+  const int Smax = (int)((2 * Umax + 1 + 7) & ~(int64_t)7);
   int rc = 0;
   if (ctc_use_lin(Umax)) {
     // fp64 linear-domain recursion -> range check -> log-domain recomputation of the utterances it flags
@@ -1005,7 +1014,7 @@ static int ctc_bwd_range(const void* logits, int64_t stride_b, int64_t stride_t,
   SC_CHECK_ARG(reduction >= 0 && reduction <= 2, SC_E_BADARG);
   SC_CHECK_ARG(B * T < ((int64_t)1 << 31), SC_E_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
+  const int Smax = (int)((2 * Umax + 1 + 7) & ~(int64_t)7);
   // rows are in the linear-domain format except for the utterances flagged in the workspace (same rule as the forward)
   const int* lossy = ctc_use_lin(Umax) ? ctc_ws_carve(const_cast<void*>(ws), B, T).lossy : nullptr;
 #define SC_CTC_GRAD(TI, TO) ctc_grad_by_width<TI, TO>(Smax, logits, stride_b, stride_t, targets, ldt, in_lens, tgt_lens, \
@@ -1109,7 +1118,7 @@ extern "C" int sc_ctc_head(const void* logits, int64_t stride_b, int64_t stride_
                          CTC_GRAD_ALL, stream);
   }
   SC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 7) == 0, SC_E_ALIGN);
-  const int Smax = (int)((2 * Umax + 1 + 3) & ~(int64_t)3);
+  const int Smax = (int)((2 * Umax + 1 + 7) & ~(int64_t)7);
   const int LP = ctc_lin_pitch(Umax);
   const CtcWs w = ctc_ws_carve(ws, B, T);
   const int64_t C = cdiv(T, P * LIN_EB) * LIN_EB;                // frames per chunk: whole emission blocks (every chunk non-empty: sc_ctc_head_phases)

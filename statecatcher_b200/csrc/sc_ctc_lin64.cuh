@@ -92,6 +92,10 @@ __device__ __forceinline__ float lin_word_to_log2(uint32_t w) {
   if (w == 0u) return -1e30f;
   return (float)((int)(w >> 20) - 1023) + lg2f(__uint_as_float(0x3f800000u | ((w & 0xfffffu) << 3)));
 }
+// words per emission row of an utterance with U labels, in global and in shared memory: 32 K + LIN_EPAD, K = pairs per lane
+// (>= U + 2: blank, labels, the zero word; a whole number of 32-byte sectors, so that rows do not straddle them in HBM)
+constexpr int LIN_EPAD = 8;
+__host__ __device__ __forceinline__ int lin_row_pitch(int U) { return 32 * ((U + 32) >> 5) + LIN_EPAD; }
 __device__ __forceinline__ double lin_hi2d(uint32_t w) { return __hiloint2double((int)w, 0); }
 __device__ __forceinline__ int lin_hi(double v) { return __double2hiint(v); }
 __device__ __forceinline__ double lin_rot(double v, int src) {
@@ -128,7 +132,7 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
     }
     const float l = warp_row_lse<T>(x, V, lane);
     if (lane == 0) lse[row] = l;
-    uint32_t* out = lplat + (int64_t)row * LP;
+    uint32_t* out = lplat + (int64_t)b * Tn * LP + (int64_t)t * lin_row_pitch(U);   // the pitch the recursion's shared-memory rows have
     float e[NL];
     float c = -INFINITY;
 #pragma unroll
@@ -190,7 +194,7 @@ struct LinBars {                            // shared-memory mbarriers of one CT
 template <int K, int DIR>
 struct Lin64 {
   static constexpr int SP = 64 * K;        // staging row pitch in words (>= 2*32*K)
-  static constexpr int EPW = 32 * K + 4;   // emission row pitch in shared memory, words (>= U+2 rounded up to 4)
+  static constexpr int EPW = 32 * K + LIN_EPAD;   // emission row pitch in shared (and global) memory, words
   double bv[K], lv[K];
   double nbv;                              // previous lane's last label of the previous column (0 for lane 0)
   double skipf[K];
@@ -374,19 +378,22 @@ __device__ __forceinline__ void
 ctc_lin64_io(uint32_t* __restrict__ ebuf, uint32_t* __restrict__ stage, LinBars* bars, const uint32_t* __restrict__ lp_b,
              int U, int lo, int hi, int K, int LP, int Smax, float* __restrict__ out_b) {
   const int lane = threadIdx.x & 31;
-  const int EPW = 32 * K + 4, SP = 64 * K;
+  const int EPW = 32 * K + LIN_EPAD, SP = 64 * K;
   const int blk_lo = lo / LIN_EB, blk_hi = (hi - 1) / LIN_EB;
   const int nvis = blk_hi - blk_lo + 1;
-  const uint32_t erow_bytes = (uint32_t)((U + 2 + 3) & ~3) * 4u;       // blank, U labels, the zero word
   const int rowchunks = (2 * U + 2 + 3) >> 2;                          // 16-byte chunks of an output row (nodes 0..2U, + the empty label slot)
+  // The emission rows of an utterance lie in global memory with the SAME pitch as in shared memory (EPW words: the
+  // emission pass writes them that way), so a block of up to LIN_EB rows is ONE bulk copy.  r02: issued row by row
+  // (64 copies per block from one thread, ~100 ns each) the copies of block k+2 held up the stores of block k+1's
+  // batches behind them until the staging ring was full: 0.36 -> 0.27 ms at cfg2, 0.30 -> 0.19 ms at U = 31.
   auto issue = [&](int vi) {                                           // lane 0 only
     const int blk = DIR == 0 ? blk_lo + vi : blk_hi - vi;
     const int r0 = max(lo, blk * LIN_EB) - blk * LIN_EB, r1 = min(hi, blk * LIN_EB + LIN_EB) - blk * LIN_EB;
     const uint32_t bar = smem_u32(&bars->efull[vi & 1]);
-    mbar_expect_tx(bar, erow_bytes * (uint32_t)(r1 - r0));
-    const uint32_t* src = lp_b + (int64_t)blk * LIN_EB * LP;
-    const uint32_t dst = smem_u32(ebuf + (size_t)(vi & 1) * LIN_EB * EPW);
-    for (int r = r0; r < r1; ++r) bulk_load_1d(dst + 4u * (uint32_t)(r * EPW), src + (int64_t)r * LP, erow_bytes, bar);
+    const uint32_t bytes = (uint32_t)((r1 - r0) * EPW) * 4u;
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(ebuf + (size_t)(vi & 1) * LIN_EB * EPW) + 4u * (uint32_t)(r0 * EPW),
+                 lp_b + ((int64_t)blk * LIN_EB + r0) * EPW, bytes, bar);
   };
   if (lane == 0) {
     issue(0);
@@ -459,9 +466,9 @@ ctc_lin64_body(uint32_t* __restrict__ lin_sm, LinBars* bars, const uint32_t* __r
   __syncthreads();
   const int K = (U + 32) >> 5;                                   // pairs per lane for this transcript
   const int Kmax = (Umax + 32) >> 5;
-  uint32_t* ebuf = lin_sm;                                       // 2 emission blocks of LIN_EB rows, pitch 32K+4 words
-  uint32_t* stage = lin_sm + 2 * (size_t)LIN_EB * (32 * Kmax + 4);   // LIN_NB staging batches of LIN_ROWS rows, pitch 64K words
-  const uint32_t* lp_b = lplat + (int64_t)b * Tn * LP;
+  uint32_t* ebuf = lin_sm;                                       // 2 emission blocks of LIN_EB rows, pitch 32K+LIN_EPAD words
+  uint32_t* stage = lin_sm + 2 * (size_t)LIN_EB * (32 * Kmax + LIN_EPAD);   // LIN_NB staging batches of LIN_ROWS rows, pitch 64K words
+  const uint32_t* lp_b = lplat + (int64_t)b * Tn * LP;           // the utterance's region (LP words per frame reserved); rows inside at pitch 32K+4
   float* out_b = (DIR == 0 ? alpha : beta) + (int64_t)b * Tn * Smax;
   if (tid >= 32) {
     ctc_lin64_io<DIR, NB>(ebuf, stage, bars, lp_b, U, lo, hi, K, LP, Smax, out_b);

@@ -263,6 +263,8 @@ sscan_fwd_kernel(const T* __restrict__ kk, const T* __restrict__ vv, const T* __
     const float k = ld_f(kk + r * ldg + ch), v = ld_f(vv + r * ldg + ch);
     const float d = sigmoidf_<PRECISE>(ld_f(qq + r * ldg + ch));
     const float kv = k * v;
+    // learned decay: S entering every SC_SCAN_CKPT-step interval (the backward recomputes inside an interval)
+    if (decay_mode == 0 && (t % SC_SCAN_CKPT) == 0) S_all[((int64_t)b * ((Tn + SC_SCAN_CKPT - 1) / SC_SCAN_CKPT) + t / SC_SCAN_CKPT) * H + ch] = S;
     if (decay_mode == 1) {
       logw += logf(expf(-lam * (float)t) + 1e-7f);
       const float w = expf(logw);
@@ -271,7 +273,7 @@ sscan_fwd_kernel(const T* __restrict__ kk, const T* __restrict__ vv, const T* __
     } else {
       S = fmaf(d, S, kv);
     }
-    S_all[r * H + ch] = S;
+    if (decay_mode == 1) S_all[r * H + ch] = S;      // prefix_sum: every S_t
     const float sp = train ? fmaf(d, S, kv) : S;
     st_f(A + r * lda + ch, ld_f(addend + r * ldadd + ch) + sp);
   }
@@ -291,31 +293,51 @@ sscan_bwd_kernel(const T* __restrict__ kk, const T* __restrict__ vv, const T* __
   const int64_t r0 = (int64_t)b * Tn;
   float ak = 0.f, av = 0.f, aq = 0.f;   // column sums (dsum: [3][H], may be null)
   float ds = 0.f;      // d_{t+1} * sigma_{t+1}
-  for (int t = Tn - 1; t >= 0; --t) {
-    const int64_t r = r0 + t;
-    const float k = ld_f(kk + r * ldg + ch), v = ld_f(vv + r * ldg + ch);
-    const float d = sigmoidf_<PRECISE>(ld_f(qq + r * ldg + ch));
-    const float da = ld_f(dA + r * ldda + ch);
-    const float St = S_all[r * H + ch];
-    float dkv, dd;
-    if (train) {
-      const float Sp = (t > 0) ? S_all[(r - 1) * H + ch] : 0.f;
-      const float sig = fmaf(d, da, ds);
-      dkv = da + sig;
-      dd = fmaf(St, da, Sp * sig);
-      ds = d * sig;
-    } else {
-      const float Sp = (t > 0) ? S_all[(r - 1) * H + ch] : s0[(int64_t)b * H + ch];
-      const float sig = da + ds;
-      dkv = sig;
-      dd = Sp * sig;
-      ds = d * sig;
+  const int nck = (Tn + SC_SCAN_CKPT - 1) / SC_SCAN_CKPT;
+  for (int c = nck - 1; c >= 0; --c) {
+    const int t0 = c * SC_SCAN_CKPT;
+    const int n = (Tn - t0 < SC_SCAN_CKPT) ? Tn - t0 : SC_SCAN_CKPT;
+    const float Sin = S_all[((int64_t)b * nck + c) * H + ch];   // S entering the interval (checkpoint of the forward)
+    float Sl[SC_SCAN_CKPT];
+    {
+      float S = Sin;
+#pragma unroll
+      for (int u = 0; u < SC_SCAN_CKPT; ++u) {
+        if (u < n) {
+          const int64_t r = r0 + t0 + u;
+          const float d = sigmoidf_<PRECISE>(ld_f(qq + r * ldg + ch));
+          S = fmaf(d, S, ld_f(kk + r * ldg + ch) * ld_f(vv + r * ldg + ch));
+        }
+        Sl[u] = S;
+      }
     }
-    const float o1 = dkv * v, o2 = dkv * k, o3 = dd * d * (1.f - d);
-    st_f(dk + r * lddg + ch, o1);
-    st_f(dv + r * lddg + ch, o2);
-    st_f(dq + r * lddg + ch, o3);
-    ak += o1; av += o2; aq += o3;
+#pragma unroll
+    for (int u = SC_SCAN_CKPT - 1; u >= 0; --u) {
+      if (u >= n) continue;
+      const int64_t r = r0 + t0 + u;
+      const float k = ld_f(kk + r * ldg + ch), v = ld_f(vv + r * ldg + ch);
+      const float d = sigmoidf_<PRECISE>(ld_f(qq + r * ldg + ch));
+      const float da = ld_f(dA + r * ldda + ch);
+      const float St = Sl[u];
+      const float Sp = (u > 0) ? Sl[u - 1] : Sin;    // Sin of interval 0 is the initial state (0 on the training path)
+      float dkv, dd;
+      if (train) {
+        const float sig = fmaf(d, da, ds);
+        dkv = da + sig;
+        dd = fmaf(St, da, Sp * sig);
+        ds = d * sig;
+      } else {
+        const float sig = da + ds;
+        dkv = sig;
+        dd = Sp * sig;
+        ds = d * sig;
+      }
+      const float o1 = dkv * v, o2 = dkv * k, o3 = dd * d * (1.f - d);
+      st_f(dk + r * lddg + ch, o1);
+      st_f(dv + r * lddg + ch, o2);
+      st_f(dq + r * lddg + ch, o3);
+      ak += o1; av += o2; aq += o3;
+    }
   }
   if (dsum != nullptr) { atomicAdd(dsum + ch, ak); atomicAdd(dsum + H + ch, av); atomicAdd(dsum + 2 * (int64_t)H + ch, aq); }
 }

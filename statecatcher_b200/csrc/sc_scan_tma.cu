@@ -445,13 +445,15 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
 #pragma unroll
   for (int i = 0; i < SV; ++i) S[i] = (TRAIN || !k.live) ? 0.f : s0[(int64_t)k.b * H + k.ch + i];
   T* ao = A + (int64_t)k.b * Tn * lda + k.ch;
-  float* so = S_all + (int64_t)k.b * Tn * H + k.ch;
   for (int c = 0; c < k.nchunk; ++c) {
     __syncthreads();
     if (k.tid == 0 && c + NST - 1 < k.nchunk) issue(c + NST - 1);
     mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
     const int t0 = c * TC;
+    // S entering the interval: all the backward needs (it recomputes inside an interval, as the fused kernel does);
+    // r01 saved every S_t as an fp32 row: 4 bytes per element written here and 4.5 read back
+    if (k.live) *reinterpret_cast<float2*>(S_all + ((int64_t)k.b * k.nchunk + c) * H + k.ch) = make_float2(S[0], S[1]);
     if (t0 + TC <= Tn) {
       // full interval: loads, decay activations and k*v of all steps first (scheduling fence), then the S chain
       float d[TC][SV], kv[TC][SV], ad[TC][SV];
@@ -474,10 +476,7 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
           S[i] = fmaf(d[u][i], S[i], kv[u][i]);
           out[i] = ad[u][i] + (TRAIN ? fmaf(d[u][i], S[i], kv[u][i]) : S[i]);
         }
-        if (k.live) {
-          stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
-          *reinterpret_cast<float2*>(so + (int64_t)(t0 + u) * H) = make_float2(S[0], S[1]);
-        }
+        if (k.live) stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
       }
       continue;
     }
@@ -496,10 +495,7 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
           S[i] = fmaf(d, S[i], kv);
           out[i] = ad[i] + (TRAIN ? fmaf(d, S[i], kv) : S[i]);
         }
-        if (k.live) {
-          stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
-          *reinterpret_cast<float2*>(so + (int64_t)(t0 + u) * H) = make_float2(S[0], S[1]);
-        }
+        if (k.live) stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
       }
     }
   }
@@ -509,21 +505,20 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
   }
 }
 
-// Reverse-time adjoint of the S scan.  Stage = k, v, q, dA boxes + an fp32 S box of TC+1 rows
-// starting one row early (S_{t-1} .. S_{t+TC-1}).
+// Reverse-time adjoint of the S scan.  Stage = k, v, q, dA boxes; S_t of an interval is recomputed forwards from the
+// interval's checkpoint (fetched one interval ahead), then the interval is walked backwards.
 template <typename T, int NST, bool TRAIN, bool PRECISE>
 __global__ void __launch_bounds__(SPLIT_THREADS)
 sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                      const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapDA,
-                     const __grid_constant__ CUtensorMap mapS, const float* __restrict__ s0,
+                     const float* __restrict__ Sck,
                      T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dq, int64_t lddg,
                      float* __restrict__ dsum, int Tn, int H, int cblocks) {
   // dsum (may be null): [3][H] column sums of dk, dv, dq over all rows, added atomically — the bias gradients of the
   // gate projection, which otherwise cost a pass over the whole gradient tensor (sc_colsum)
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int BOX = TC * CB * (int)sizeof(T);
-  constexpr int SBOX = (TC + 1) * CB * 4;
-  constexpr int STAGE = 4 * BOX + SBOX;
+  constexpr int STAGE = 4 * BOX;
   __shared__ __align__(8) uint64_t bars[NST];
   const ScanBlock k = scan_block(Tn, H, cblocks, smem);
   scan_bars_init<NST>(bars, k.tid);
@@ -538,54 +533,74 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     tma_load_2d(d + BOX, &mapV, bar, k.c0, row);
     tma_load_2d(d + 2 * BOX, &mapQ, bar, k.c0, row);
     tma_load_2d(d + 3 * BOX, &mapDA, bar, k.c0, row);
-    tma_load_2d(d + 4 * BOX, &mapS, bar, k.c0, row - 1);
   };
   if (k.tid == 0)
     for (int it = 0; it < NST - 1 && it < k.nchunk; ++it) issue(it);
-  float ds[SV], sfirst[SV], acc[3][SV];
+  float ds[SV], acc[3][SV], Snext[SV];
 #pragma unroll
   for (int i = 0; i < SV; ++i) {
     ds[i] = 0.f;
     acc[0][i] = 0.f; acc[1][i] = 0.f; acc[2][i] = 0.f;
-    sfirst[i] = (TRAIN || !k.live) ? 0.f : s0[(int64_t)k.b * H + k.ch + i];
+    Snext[i] = k.live ? Sck[((int64_t)k.b * k.nchunk + k.nchunk - 1) * H + k.ch + i] : 0.f;
   }
   const int64_t obase = (int64_t)k.b * Tn * lddg + k.ch;
   for (int it = 0; it < k.nchunk; ++it) {
     const int chunk = k.nchunk - 1 - it;
     __syncthreads();
     if (k.tid == 0 && it + NST - 1 < k.nchunk) issue(it + NST - 1);
+    float Sin[SV];
+#pragma unroll
+    for (int i = 0; i < SV; ++i) {
+      Sin[i] = Snext[i];
+      Snext[i] = (k.live && chunk > 0) ? Sck[((int64_t)k.b * k.nchunk + chunk - 1) * H + k.ch + i] : 0.f;
+    }
     mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
-    const uint8_t* sp = smem + (it % NST) * STAGE;
-    const T* st = reinterpret_cast<const T*>(sp);
-    const float* ss = reinterpret_cast<const float*>(sp + 4 * BOX);     // row r holds S_{t0-1+r}
+    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
     const int t0 = chunk * TC;
+    // pass 1: S_t and d_t across the interval (rows past the segment's end are zero-filled boxes: harmless)
+    float Sl[TC][SV], dl[TC][SV], kv[TC][SV];
+    {
+      float S[SV];
+#pragma unroll
+      for (int i = 0; i < SV; ++i) S[i] = Sin[i];
+#pragma unroll
+      for (int u = 0; u < TC; ++u) {
+        float kk[SV], vv[SV], qq[SV];
+        lds2(st + (0 * TC + u) * CB, k.tid, kk);
+        lds2(st + (1 * TC + u) * CB, k.tid, vv);
+        lds2(st + (2 * TC + u) * CB, k.tid, qq);
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          dl[u][i] = sigmoidf_<PRECISE>(qq[i]);
+          kv[u][i] = kk[i] * vv[i];
+          S[i] = fmaf(dl[u][i], S[i], kv[u][i]);
+          Sl[u][i] = S[i];
+        }
+      }
+    }
+    // pass 2: reverse time
 #pragma unroll
     for (int u = TC - 1; u >= 0; --u) {
       const int t = t0 + u;
       if (t < Tn) {
-        float kk[SV], vv[SV], qq[SV], da[SV], St[SV], Sp[SV], ok[SV], ov[SV], oq[SV];
+        float kk[SV], vv[SV], da[SV], ok[SV], ov[SV], oq[SV];
         lds2(st + (0 * TC + u) * CB, k.tid, kk);
         lds2(st + (1 * TC + u) * CB, k.tid, vv);
-        lds2(st + (2 * TC + u) * CB, k.tid, qq);
         lds2(st + (3 * TC + u) * CB, k.tid, da);
-        lds2(ss + (u + 1) * CB, k.tid, St);
-        lds2(ss + u * CB, k.tid, Sp);
-        if (t == 0) {
-#pragma unroll
-          for (int i = 0; i < SV; ++i) Sp[i] = sfirst[i];
-        }
 #pragma unroll
         for (int i = 0; i < SV; ++i) {
-          const float d = sigmoidf_<PRECISE>(qq[i]);
+          const float d = dl[u][i];
+          const float St = Sl[u][i];
+          const float Sp = (u > 0) ? Sl[u - 1][i] : Sin[i];
           float sig, dkv, dd;
           if (TRAIN) {
             sig = fmaf(d, da[i], ds[i]);
             dkv = da[i] + sig;
-            dd = fmaf(St[i], da[i], Sp[i] * sig);
+            dd = fmaf(St, da[i], Sp * sig);
           } else {
             sig = da[i] + ds[i];
             dkv = sig;
-            dd = Sp[i] * sig;
+            dd = Sp * sig;
           }
           ds[i] = d * sig;
           ok[i] = dkv * vv[i];
@@ -943,15 +958,15 @@ template <typename T, bool PRECISE>
 static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t ldg, const float* S_all, const float* s0,
                            const void* dA, int64_t ldda, void* dk, void* dv, void* dq, int64_t lddg, float* dsum, int64_t B,
                            int64_t Tn, int64_t H, int train, cudaStream_t st) {
-  if (!split_ok<T>({k, v, q, dA, S_all}, {ldg, ldda}, H, B, Tn) || (lddg % 2) ||
-      (((uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dq) & (2 * sizeof(T) - 1)))
+  (void)s0;                                                      // interval 0's checkpoint IS the initial state
+  if (!split_ok<T>({k, v, q, dA}, {ldg, ldda}, H, B, Tn) || (lddg % 2) ||
+      (((uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dq) & (2 * sizeof(T) - 1)) || ((uintptr_t)S_all & 7))
     return SC_E_UNSUP;
-  constexpr int NST = 3;
-  constexpr int smem = NST * (4 * TC * CB * (int)sizeof(T) + (TC + 1) * CB * 4);
-  CUtensorMap mk, mv, mq, mda, ms;
+  constexpr int NST = 4;
+  constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
+  CUtensorMap mk, mv, mq, mda;
   if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
-      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mda, dA, B * Tn, H, ldda, TC) ||
-      !make_scan_map<float>(&ms, S_all, B * Tn, H, H, TC + 1))
+      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mda, dA, B * Tn, H, ldda, TC))
     return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
   const unsigned grid = (unsigned)(B * cblocks);
@@ -959,8 +974,8 @@ static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t 
   auto ks = sscan_bwd_tma_kernel<T, NST, false, PRECISE>;
   int e = set_smem(kt, smem); if (e) return e;
   e = set_smem(ks, smem); if (e) return e;
-  if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
-  else       ks<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, ms, s0, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
+  if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, S_all, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
+  else       ks<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, S_all, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
   SC_LAUNCH_RET();
 }
 int sscan_bwd_tma_dispatch(const void* k, const void* v, const void* q, int64_t ldg, const float* S_all, const float* s0,

@@ -52,6 +52,14 @@ def _head_streams(device):
     return tuple(s.cuda_stream for s in _side_streams[key])
 
 
+def _lplat_pitch(Umax: int, S: int) -> int:
+    """Words per frame of the emission workspace (sc_ctc_lplat_pitch; S when the library is not there: host tests)."""
+    try:
+        return int(_lib.load().sc_ctc_lplat_pitch(Umax))
+    except (ImportError, OSError):
+        return S
+
+
 def _lens(v: LenT, device, B: int, name: str):
     """-> (int64 device tensor [B], host max or None)."""
     if isinstance(v, torch.Tensor):
@@ -72,10 +80,10 @@ class _CTCFn(torch.autograd.Function):
         # x: logical (T,B,V), V contiguous
         T, B, V = x.shape
         dev = x.device
-        S = (2 * Umax + 1 + 3) & ~3          # lattice row width, padded to 16-byte rows
+        S = (2 * Umax + 1 + 7) & ~7          # lattice row width, padded to whole 32-byte sectors
         f32 = dict(dtype=torch.float32, device=dev)
         lse = torch.empty(B, max(T, 1), **f32)
-        lplat = torch.empty(B, max(T, 1), S, **f32)
+        lplat = torch.empty(B, max(T, 1), _lplat_pitch(Umax, S), **f32)   # emission rows (>= S words per frame)
         cshift = torch.empty(B, max(T, 1), **f32)
         alpha = torch.empty(B, max(T, 1), S, **f32)
         beta = torch.empty(B, max(T, 1), S, **f32)

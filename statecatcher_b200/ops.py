@@ -200,7 +200,9 @@ def sscan_fwd(k, v, q, addend, s0, B, T, H, train_mode, decay_mode, lam):
     dev = k.device
     assert _ld(k) == _ld(v) == _ld(q)
     A = torch.empty(B * T, H, dtype=k.dtype, device=dev)
-    S_all = torch.empty(B * T, H, dtype=torch.float32, device=dev)
+    # saved for the backward: learned decay -> S entering every SC_SCAN_CKPT-step interval [B, ceil(T/8), H];
+    # prefix_sum -> every S_t [B*T, H]
+    S_all = torch.empty((B * max(n_ckpt(T), 1)) if decay_mode == 0 else B * T, H, dtype=torch.float32, device=dev)
     sT = None if train_mode else torch.empty(B, H, dtype=torch.float32, device=dev)
     call("sc_lucy_sscan_fwd", ptr(k), ptr(v), ptr(q), _ld(k), ptr(addend), _ld(addend), ptr(s0),
          ptr(A), H, ptr(S_all), ptr(sT), B, T, H, dt(k), int(train_mode), int(decay_mode), float(lam), stream())

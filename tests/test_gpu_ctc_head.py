@@ -33,9 +33,9 @@ def _run(x, tok, il, tl, U, phases, overlapped, red=1, out_dtype=None):
     from statecatcher_b200._lib import call, dt, ptr, stream, load
     from statecatcher_b200 import ctc
     B, T, V = x.shape
-    S = (2 * U + 1 + 3) & ~3
+    S = (2 * U + 1 + 7) & ~7
     f32 = dict(dtype=torch.float32, device="cuda")
-    lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, S, **f32), torch.zeros(B, T, **f32)
+    lse, lplat, csh = torch.zeros(B, T, **f32), torch.zeros(B, T, load().sc_ctc_lplat_pitch(U), **f32), torch.zeros(B, T, **f32)
     alpha, beta = torch.zeros(B, T, S, **f32), torch.zeros(B, T, S, **f32)
     nll, loss = torch.zeros(B, **f32), torch.zeros((), **f32)
     ws = torch.zeros(load().sc_ctc_workspace_bytes(B, T, U) // 8 + 1, dtype=torch.float64, device="cuda")
