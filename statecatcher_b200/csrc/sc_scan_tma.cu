@@ -557,36 +557,38 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
     const int t0 = chunk * TC;
-    // pass 1: S_t and d_t across the interval (rows past the segment's end are zero-filled boxes: harmless)
-    float Sl[TC][SV], dl[TC][SV], kv[TC][SV];
+    // pass 1: every load of the interval, d_t, and S_t forwards from the checkpoint (rows past the segment's end
+    // belong to the next stream or are zero-filled: computed, never stored)
+    float Sl[TC][SV], dl[TC][SV], kk[TC][SV], vv[TC][SV], da[TC][SV];
     {
       float S[SV];
 #pragma unroll
       for (int i = 0; i < SV; ++i) S[i] = Sin[i];
 #pragma unroll
       for (int u = 0; u < TC; ++u) {
-        float kk[SV], vv[SV], qq[SV];
-        lds2(st + (0 * TC + u) * CB, k.tid, kk);
-        lds2(st + (1 * TC + u) * CB, k.tid, vv);
+        float qq[SV];
+        lds2(st + (0 * TC + u) * CB, k.tid, kk[u]);
+        lds2(st + (1 * TC + u) * CB, k.tid, vv[u]);
         lds2(st + (2 * TC + u) * CB, k.tid, qq);
+        lds2(st + (3 * TC + u) * CB, k.tid, da[u]);
+#pragma unroll
+        for (int i = 0; i < SV; ++i) dl[u][i] = sigmoidf_<PRECISE>(qq[i]);
+      }
+      __syncwarp();                                    // scheduling fence: loads and activations stay in front of the chains
+#pragma unroll
+      for (int u = 0; u < TC; ++u)
 #pragma unroll
         for (int i = 0; i < SV; ++i) {
-          dl[u][i] = sigmoidf_<PRECISE>(qq[i]);
-          kv[u][i] = kk[i] * vv[i];
-          S[i] = fmaf(dl[u][i], S[i], kv[u][i]);
+          S[i] = fmaf(dl[u][i], S[i], kk[u][i] * vv[u][i]);
           Sl[u][i] = S[i];
         }
-      }
     }
     // pass 2: reverse time
 #pragma unroll
     for (int u = TC - 1; u >= 0; --u) {
       const int t = t0 + u;
       if (t < Tn) {
-        float kk[SV], vv[SV], da[SV], ok[SV], ov[SV], oq[SV];
-        lds2(st + (0 * TC + u) * CB, k.tid, kk);
-        lds2(st + (1 * TC + u) * CB, k.tid, vv);
-        lds2(st + (3 * TC + u) * CB, k.tid, da);
+        float ok[SV], ov[SV], oq[SV];
 #pragma unroll
         for (int i = 0; i < SV; ++i) {
           const float d = dl[u][i];
@@ -594,17 +596,17 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
           const float Sp = (u > 0) ? Sl[u - 1][i] : Sin[i];
           float sig, dkv, dd;
           if (TRAIN) {
-            sig = fmaf(d, da[i], ds[i]);
-            dkv = da[i] + sig;
-            dd = fmaf(St, da[i], Sp * sig);
+            sig = fmaf(d, da[u][i], ds[i]);
+            dkv = da[u][i] + sig;
+            dd = fmaf(St, da[u][i], Sp * sig);
           } else {
-            sig = da[i] + ds[i];
+            sig = da[u][i] + ds[i];
             dkv = sig;
             dd = Sp * sig;
           }
           ds[i] = d * sig;
-          ok[i] = dkv * vv[i];
-          ov[i] = dkv * kk[i];
+          ok[i] = dkv * vv[u][i];
+          ov[i] = dkv * kk[u][i];
           oq[i] = dd * d * (1.f - d);
           acc[0][i] += ok[i]; acc[1][i] += ov[i]; acc[2][i] += oq[i];
         }
