@@ -148,7 +148,7 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
 #pragma unroll
     for (int k = 0; k < NL; ++k)
       if (lane + 32 * k <= U) out[lane + 32 * k] = lin_word_of_log2(e[k] - c);
-    if (lane == 0) { cshift[row] = c; out[U + 1] = 0u; }        // the row's zero word: what a missing label reads
+    if (lane == 0) { cshift[row] = c; out[U + 1] = 0u; }        // the row's zero word: what a missing label reads (writing the row's padding as well, so that whole sectors leave: 0.156 vs 0.152 ms — not kept)
   }
 }
 
