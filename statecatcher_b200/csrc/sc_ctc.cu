@@ -636,19 +636,29 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
       int eb_[NP > 0 ? NP : 1], el_[NP > 0 ? NP : 1];
       int emax = -1;
       auto mant = [](uint32_t w) -> float { return __uint_as_float(0x3f800000u | ((w & 0xfffffu) << 3)); };
+      // every word of the lane's pairs is requested before any is looked at (indices clamped into the row, the words
+      // of absent nodes zeroed afterwards): written pair by pair with the loads inside `if (u <= U)` the compiler
+      // cannot move them over the branches and the frame pays one global-memory round trip per pair — a third of
+      // this kernel's stall samples sat on the first compare of a loaded word (r02, ncu source view)
+      uint2 aw_[NP > 0 ? NP : 1];
+      uint32_t cb_[NP > 0 ? NP : 1], cl_[NP > 0 ? NP : 1];
 #pragma unroll
       for (int kk = 0; kk < NP; ++kk) {
         const int u = lane + 32 * kk;
-        eb_[kk] = -1; el_[kk] = -1; wb[kk] = 0.f; wl[kk] = 0.f;
-        if (u <= U) {
-          const uint2 a = __ldg(aw + u);
-          const uint32_t cb = __ldg(bw + 2 * (U - u));           // beta row mirrored: node s at 2U - s
-          if (a.x != 0u && cb != 0u) { eb_[kk] = (int)(a.x >> 20) + (int)(cb >> 20); wb[kk] = mant(a.x) * mant(cb); }
-          if (u < U) {
-            const uint32_t cl = __ldg(bw + 2 * (U - u) - 1);
-            if (a.y != 0u && cl != 0u) { el_[kk] = (int)(a.y >> 20) + (int)(cl >> 20); wl[kk] = mant(a.y) * mant(cl); }
-          }
-        }
+        const int uc = u <= U ? u : U;                           // pair U always exists
+        aw_[kk] = __ldg(aw + uc);
+        cb_[kk] = __ldg(bw + 2 * (U - uc));                      // beta row mirrored: node s at 2U - s
+        cl_[kk] = __ldg(bw + (uc < U ? 2 * (U - uc) - 1 : 0));
+      }
+#pragma unroll
+      for (int kk = 0; kk < NP; ++kk) {
+        const int u = lane + 32 * kk;
+        const bool ob = u <= U && aw_[kk].x != 0u && cb_[kk] != 0u;
+        const bool ol = u < U && aw_[kk].y != 0u && cl_[kk] != 0u;
+        eb_[kk] = ob ? (int)(aw_[kk].x >> 20) + (int)(cb_[kk] >> 20) : -1;
+        el_[kk] = ol ? (int)(aw_[kk].y >> 20) + (int)(cl_[kk] >> 20) : -1;
+        wb[kk] = ob ? mant(aw_[kk].x) * mant(cb_[kk]) : 0.f;
+        wl[kk] = ol ? mant(aw_[kk].y) * mant(cl_[kk]) : 0.f;
         emax = max(emax, max(eb_[kk], el_[kk]));
       }
       emax = __reduce_max_sync(0xffffffffu, emax);
@@ -686,11 +696,14 @@ ctc_grad_row(float* __restrict__ sm, const unsigned row, const int warp, const i
     __syncwarp();                                     // softmax row complete before the scatter
     // Every other lattice node is the blank: its contributions are summed in registers and
     // added once; label nodes scatter with shared-memory atomics (labels may repeat).
+    int64_t lab[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int kk = 0; kk < NP; ++kk) { const int u = lane + 32 * kk; lab[kk] = u < U ? tg[u] : 0; }   // requested together, ahead of the atomics
 #pragma unroll
     for (int kk = 0; kk < NP; ++kk) {
       const int u = lane + 32 * kk;
       bsum += wb[kk] * inv;
-      if (u < U && wl[kk] != 0.f) atomicAdd(r + tg[u], -wl[kk] * inv);   // a label outside the vocabulary has occupancy 0
+      if (u < U && wl[kk] != 0.f) atomicAdd(r + lab[kk], -wl[kk] * inv);   // a label outside the vocabulary has occupancy 0
     }
   } else {
     for (int u = lane; u <= U; u += 32) {
