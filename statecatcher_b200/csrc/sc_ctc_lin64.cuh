@@ -82,10 +82,12 @@ inline int64_t ctc_ws_bytes(int64_t B, int64_t T) {
 
 // high word of 2^d (d <= 0, log2 units), mantissa rounded to 20 bits; 0 = probability zero
 __device__ __forceinline__ uint32_t lin_word_of_log2(float d) {
-  if (!(d > -1000.f)) return 0u;
-  const float fl = floorf(d);
-  const uint32_t mb = __float_as_uint(ex2f(d - fl));             // 2^frac in [1, 2]: exponent field 127 (128 when it rounds to 2)
-  return (uint32_t)((896 + (int)fl) << 20) + ((mb + 4u) >> 3);   // (1023 - 127 + fl) << 20, + the float's own exponent/mantissa >> 3
+  const bool dead = !(d > -1000.f);                              // (select, not a branch: the callers convert a handful of words per lane)
+  const float dd = dead ? 0.f : d;
+  const float fl = floorf(dd);
+  const uint32_t mb = __float_as_uint(ex2f(dd - fl));            // 2^frac in [1, 2]: exponent field 127 (128 when it rounds to 2)
+  const uint32_t w = (uint32_t)((896 + (int)fl) << 20) + ((mb + 4u) >> 3);   // (1023 - 127 + fl) << 20, + the float's own exponent/mantissa >> 3
+  return dead ? 0u : w;
 }
 // the reverse, for the log-domain kernels reading the same emission words
 __device__ __forceinline__ float lin_word_to_log2(uint32_t w) {
@@ -135,13 +137,19 @@ ctc_lse_gather_lin_kernel(const T* __restrict__ logits, int64_t stride_b, int64_
     uint32_t* out = lplat + (int64_t)b * Tn * LP + (int64_t)t * lin_row_pitch(U);   // the pitch the recursion's shared-memory rows have
     float e[NL];
     float c = -INFINITY;
+    // branch-free: the gathers (L1 hits: the row has just been read) are requested together, absent entries and labels
+    // outside the vocabulary (probability zero) selected away afterwards
+    float xv[NL];
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
-      e[k] = -INFINITY;
-      if (lane + 32 * k <= U) {
-        if (lab[k] >= 0 && lab[k] < V) e[k] = (ld_f(x + lab[k]) - l) * 1.4426950408889634f;   // a label outside the vocabulary is probability zero
-        c = fmaxf(c, e[k]);
-      }
+      const bool ok = lane + 32 * k <= U && lab[k] >= 0 && lab[k] < V;
+      xv[k] = ld_f(x + (ok ? lab[k] : 0));
+    }
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const bool ok = lane + 32 * k <= U && lab[k] >= 0 && lab[k] < V;
+      e[k] = ok ? (xv[k] - l) * 1.4426950408889634f : -INFINITY;
+      c = fmaxf(c, e[k]);
     }
     c = warp_max(c);
     if (!(c > -1e29f)) c = 0.f;                                  // every lattice emission is -inf: leave the row dead
