@@ -231,6 +231,10 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
 
 // ------------------------------------------------------------------ backward ---------
 // Stage = 5 gate boxes + dHout box + Hout box shifted one row back (h_{t-1}).
+// (r02, measured and dropped: a warp-specialised form — a fifth warp issuing the copies, the checkpoint row arriving with
+// the stage, per-warp full/empty mbarriers instead of the block barrier; ncu had 8 % of this kernel's stall samples on
+// the block barrier and 11 % on the first use of the prefetched checkpoint — bit-identical, 5.37-5.42 ms per step against
+// 5.03-5.09 in alternating same-box runs.)
 template <typename T, int VEC, int NST, bool TRAIN, bool PRECISE>
 __global__ void __launch_bounds__(CB / VEC)
 lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapH,
