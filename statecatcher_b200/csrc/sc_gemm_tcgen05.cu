@@ -42,6 +42,9 @@ constexpr int EPI_OFF = RING_BYTES + 256 /*barriers*/ + 2 * TN * 4 /*bias*/ + 25
 static_assert(EPI_OFF % 512 == 0, "store boxes must be 512-byte aligned (64-byte swizzle pattern)");
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
+#ifndef SC_GEMM_EPI_BUFS
+#define SC_GEMM_EPI_BUFS 2   // store boxes per epilogue warp in pair mode (3, with the third set also in the ring tail: no change in step, r02)
+#endif
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
@@ -79,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int B_BYTES = (PAIR ? TN / 2 : TN) * TK * 2;            // 16 KB / 32 KB
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGES = PAIR ? 5 : 4;
-  constexpr int EPI_BUFS = PAIR ? 2 : 1;                             // store boxes per epilogue warp (2nd set: tail of the ring region)
+  constexpr int EPI_BUFS = PAIR ? SC_GEMM_EPI_BUFS : 1;              // store boxes per epilogue warp (sets beyond the first: tail of the ring region)
   static_assert(STAGES * STAGE_BYTES + (EPI_BUFS - 1) * EPI_WARPS * EPI_STAGE_BYTES <= RING_BYTES, "ring region");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024-B aligned tiles
@@ -245,9 +248,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           // to the TMA engine — full 64-byte row segments instead of 32 scattered 16-byte stores
           // per instruction (measured 1.9 TB/s -> the store path was the fwd GEMM's bottleneck);
           // the tensor map clips rows >= I and columns >= J.
-          const uint32_t stg = (EPI_BUFS == 2 && (ebox & 1))
-                                   ? base + STAGES * STAGE_BYTES + (uint32_t)(warp - 2) * EPI_STAGE_BYTES
-                                   : base + EPI_OFF + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+          const uint32_t eslot = EPI_BUFS > 1 ? ebox % EPI_BUFS : 0u;
+          const uint32_t stg = eslot ? base + STAGES * STAGE_BYTES + ((eslot - 1) * EPI_WARPS + (uint32_t)(warp - 2)) * EPI_STAGE_BYTES
+                                     : base + EPI_OFF + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
           ++ebox;
           if (p.bias != nullptr) {
             const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
@@ -260,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               r[v * 4 + 3] = __float_as_uint(__uint_as_float(r[v * 4 + 3]) + b4.w);
             }
           }
-          if (lane == 0) { if (EPI_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0(); }   // the box written 1 (2) stores ago has left shared memory
+          if (lane == 0) bulk_wait_read<EPI_BUFS - 1>();         // the box written EPI_BUFS stores ago has left shared memory
           __syncwarp();
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
