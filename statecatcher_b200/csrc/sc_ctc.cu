@@ -4,20 +4,20 @@
 // zero_infinity=True), train.py:142), i.e. ATen's log_softmax / ctc_loss_gpu /
 // ctc_loss_backward_gpu chain.  Semantics: SURVEY.md Appendix B.
 //
-// Passes (all fp32 arithmetic, log space):
-//   1. ctc_lse_gather : one warp per frame (b,t<T_b): 128-bit coalesced sweep over the V
-//      logits -> lse[b,t]; the 2U+1 lattice emissions logit[l'_s]-lse are gathered into the
-//      compact lplat[b,t,s] while the row is still hot in L1, so the serial recursions never
-//      touch the V-wide tensor.
-//   2. ctc_alpha_beta : one CTA per (utterance, direction); lattice node s on thread s; the
-//      previous column lives in a double-buffered shared-memory line, one __syncthreads per
-//      timestep; the emission for step t+1 is prefetched before the barrier of step t.
-//   3. ctc_grad       : one warp per frame: occupancy = softmax over the lattice of alpha+beta
-//      (lattice nodes taken as (blank,label) pairs, one float2 load each from alpha and beta,
-//      kept in registers between the max, the sum and the scatter);
-//      dlogits = gout*scale_b*(softmax - occupancy), label occupancies scattered with
-//      shared-memory atomics; exact zeros for t>=T_b and for infeasible utterances.
-// Tried and rejected (r01): (a) a scaled linear-domain recursion, one warp per lattice with
+// Passes:
+//   1. emissions (ctc_lse_gather_lin / ctc_lse_gather): one warp per frame (b,t<T_b): 128-bit coalesced sweep over
+//      the V logits -> lse[b,t]; the frame's lattice emissions are gathered into a compact row while the row is
+//      still hot in L1, so the serial recursions never touch the V-wide tensor.
+//   2. lattice: for transcripts of up to 255 labels the alpha/beta recursions run in the LINEAR domain on fp64,
+//      one warp per (utterance, direction) plus an I/O warp (sc_ctc_lin64.cuh; range checks flag what fp64 cannot
+//      hold); flagged utterances and wider lattices take the log-domain kernels below (ctc_alpha_beta_wave2: pair
+//      per thread, wavefront hand-off between warps, no block barrier per step; ctc_alpha_beta: one node per thread,
+//      block barrier per step, any width).
+//   3. gradient (ctc_grad): one warp per frame: occupancy = normalised alpha*beta over the lattice (pairs kept in
+//      registers between the max, the sum and the scatter); dlogits = gout*scale_b*(softmax - occupancy), label
+//      occupancies scattered with shared-memory atomics; exact zeros for t>=T_b and for infeasible utterances.
+//   sc_ctc_head (opt-in) runs 1 and 3 on side streams under 2 cut into frame ranges.
+// Tried and rejected (r01; (a) was overtaken in r02 by doing it in fp64): (a) a scaled linear-domain recursion, one warp per lattice with
 // the column in registers — 6x shorter serial chain, but with T >> U the forward and backward
 // masses sit at opposite ends of the lattice and their overlap (the occupancy) lies 2^-125
 // and further below either column's maximum, outside fp32's range (measured on random
