@@ -2,6 +2,8 @@
 // LayerNorm forward/backward of lucyrnn.py:17-20 (nn.LayerNorm(H), eps=1e-5) used when
 // config.layer_norm=True.  All HBM-bound, coalesced along the contiguous dimension.
 #include "sc_common.cuh"
+#include "sc_tma.cuh"
+#include <stdlib.h>
 
 namespace sc {
 
@@ -341,6 +343,126 @@ layernorm_bwd_vec_kernel(const T* __restrict__ dY, int64_t lddy, const T* __rest
   }
 }
 
+// Staged form of the kernel above: what bounds it is BYTES IN FLIGHT — 255 registers allow 8 warps per SM, each with one
+// 4 KB row pair in flight: 32 KB per SM over ~1.3 us of latency = 3.6 TB/s, the measured rate (and a warp-pair form
+// with 12 warps of half rows, 24 KB in flight, measured slower: r02).  Here every warp owns a ring of LN_RING rows in
+// shared memory filled by bulk async copies issued LN_RING-1 rows ahead, so the bytes in flight no longer cost registers.
+#ifndef SC_LN_RING
+#define SC_LN_RING 3
+#endif
+constexpr int LN_RING = SC_LN_RING;
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_stage_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
+                           const float* __restrict__ w, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, T* __restrict__ dX, int64_t lddx,
+                           float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dxs, int64_t M, int H,
+                           int64_t rows_per_block) {
+  constexpr int ROWB = NV * 256 * (int)sizeof(T);       // bytes of one row of one tensor
+  extern __shared__ __align__(128) uint8_t dyn[];       // [3H floats: block partials][per warp: LN_RING x {dy row, x row}]
+  __shared__ __align__(8) uint64_t bars[LN_WARPS][LN_RING];
+  float* sm = reinterpret_cast<float*>(dyn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = dyn + ((3 * (size_t)H * sizeof(float) + 127) & ~(size_t)127) + (size_t)warp * LN_RING * 2 * ROWB;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  const int64_t first = m0 + warp;
+  const int nk = first < m1 ? (int)((m1 - first + LN_WARPS - 1) / LN_WARPS) : 0;   // rows of this warp
+  if (lane == 0) {
+    for (int i = 0; i < LN_RING; ++i) mbar_init(smem_u32(&bars[warp][i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int k) {                              // lane 0 only
+    const int slot = k % LN_RING;
+    const int64_t row = first + (int64_t)k * LN_WARPS;
+    const uint32_t bar = smem_u32(&bars[warp][slot]);
+    mbar_expect_tx(bar, 2 * ROWB);
+    bulk_load_1d(smem_u32(ring + (size_t)slot * 2 * ROWB), dY + row * lddy, ROWB, bar);
+    bulk_load_1d(smem_u32(ring + (size_t)slot * 2 * ROWB + ROWB), X + row * ldx, ROWB, bar);
+  };
+  if (lane == 0)
+    for (int k = 0; k < LN_RING - 1 && k < nk; ++k) issue(k);
+  float aw[NV][8], ab[NV][8], ax[NV][8], wv[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      aw[j][e] = 0.f; ab[j][e] = 0.f; ax[j][e] = 0.f;
+      wv[j][e] = w[(lane + 32 * j) * 8 + e];
+    }
+  float mu_n = nk > 0 ? mean[first] : 0.f, rs_n = nk > 0 ? rstd[first] : 0.f;
+  for (int k = 0; k < nk; ++k) {
+    const int64_t row = first + (int64_t)k * LN_WARPS;
+    __syncwarp();                                        // every lane has left the slot the next copy overwrites
+    if (lane == 0 && k + LN_RING - 1 < nk) issue(k + LN_RING - 1);
+    const float mu = mu_n, rs = rs_n;
+    if (k + 1 < nk) { mu_n = mean[row + LN_WARPS]; rs_n = rstd[row + LN_WARPS]; }   // one row ahead
+    mbar_wait(smem_u32(&bars[warp][k % LN_RING]), (uint32_t)((k / LN_RING) & 1));
+    const T* dy = reinterpret_cast<const T*>(ring + (size_t)(k % LN_RING) * 2 * ROWB);
+    const T* x = reinterpret_cast<const T*>(ring + (size_t)(k % LN_RING) * 2 * ROWB + ROWB);
+    float dyv[NV][8], xh[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if constexpr (sizeof(T) == 2) {
+        Vec<T, 8> a, b;
+        a.raw = *reinterpret_cast<const uint4*>(dy + (lane + 32 * j) * 8);
+        b.raw = *reinterpret_cast<const uint4*>(x + (lane + 32 * j) * 8);
+        unpack(a, dyv[j]); unpack(b, xh[j]);
+      } else {
+        const float4* pa = reinterpret_cast<const float4*>(dy + (lane + 32 * j) * 8);
+        const float4* pb = reinterpret_cast<const float4*>(x + (lane + 32 * j) * 8);
+        const float4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+        dyv[j][0] = a0.x; dyv[j][1] = a0.y; dyv[j][2] = a0.z; dyv[j][3] = a0.w; dyv[j][4] = a1.x; dyv[j][5] = a1.y; dyv[j][6] = a1.z; dyv[j][7] = a1.w;
+        xh[j][0] = b0.x; xh[j][1] = b0.y; xh[j][2] = b0.z; xh[j][3] = b0.w; xh[j][4] = b1.x; xh[j][5] = b1.y; xh[j][6] = b1.z; xh[j][7] = b1.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[j][e] = (xh[j][e] - mu) * rs;
+        const float g = dyv[j][e] * wv[j][e];
+        s1 += g; s2 = fmaf(g, xh[j][e], s2);
+      }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    T* dx = dX + row * lddx;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o[e] = rs * (dyv[j][e] * wv[j][e] - s1 - xh[j][e] * s2);
+        aw[j][e] = fmaf(dyv[j][e], xh[j][e], aw[j][e]);
+        ab[j][e] += dyv[j][e];
+        ax[j][e] += o[e];
+      }
+      st8<T>(dx + (lane + 32 * j) * 8, o);
+    }
+  }
+  float* sdw = sm;
+  float* sdb = sm + H;
+  float* sdx = sm + 2 * H;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(sdw + (lane + 32 * j) * 8 + e, aw[j][e]);
+      atomicAdd(sdb + (lane + 32 * j) * 8 + e, ab[j][e]);
+      if (dxs) atomicAdd(sdx + (lane + 32 * j) * 8 + e, ax[j][e]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dw + i, sdw[i]);
+    atomicAdd(db + i, sdb[i]);
+    if (dxs) atomicAdd(dxs + i, sdx[i]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const T* __restrict__ dY, int64_t lddy, const T* __restrict__ X, int64_t ldx,
@@ -402,6 +524,21 @@ static void launch_ln_bwd(const void* dY, int64_t lddy, const void* X, int64_t l
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_vec_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     layernorm_bwd_vec_kernel<T, NV><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
         (T*)dX, lddx, dw, db, dxs, M, H, rpb); } while (0)
+  static const bool stage_off = [] { const char* e = getenv("SC_LN_BWD_STAGE"); return e && e[0] == '0'; }();   // A/B switch
+#define SC_LN_BWD_S(NV) do { \
+    const size_t sm2 = ((smem + 127) & ~(size_t)127) + (size_t)LN_WARPS * LN_RING * 2 * (NV) * 256 * sizeof(T); \
+    if (sm2 > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_stage_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); \
+    layernorm_bwd_stage_kernel<T, NV><<<(unsigned)blocks, LN_WARPS * 32, sm2, st>>>((const T*)dY, lddy, (const T*)X, ldx, w, mean, rstd, \
+        (T*)dX, lddx, dw, db, dxs, M, H, rpb); } while (0)
+  if (vec_ok && !stage_off) {
+    switch (H / 256) {
+      case 1: SC_LN_BWD_S(1); return;
+      case 2: SC_LN_BWD_S(2); return;
+      case 3: SC_LN_BWD_S(3); return;
+      default: SC_LN_BWD_S(4); return;
+    }
+  }
+#undef SC_LN_BWD_S
   if (vec_ok) {
     switch (H / 256) {
       case 1: SC_LN_BWD_V(1); return;
