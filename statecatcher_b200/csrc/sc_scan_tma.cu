@@ -20,6 +20,27 @@
 namespace sc {
 
 constexpr int TC = SC_SCAN_CKPT;     // timesteps per stage == checkpoint interval
+// ring depths of the 16-bit kernels (stages of TC rows).  r02, deeper rings everywhere (fwd 5, bwd 4, split scans 6-8) in
+// alternating same-box steps: forward 2.50 vs 2.43-2.50 ms, backward 5.20-5.24 vs 5.26-5.36, split scans unchanged — the
+// ~100 KB per SM these depths keep in flight already cover the latency
+#ifndef SC_NST_FWD
+#define SC_NST_FWD 4
+#endif
+#ifndef SC_NST_BWD
+#define SC_NST_BWD 3
+#endif
+#ifndef SC_NST_SF
+#define SC_NST_SF 4
+#endif
+#ifndef SC_NST_SB
+#define SC_NST_SB 4
+#endif
+#ifndef SC_NST_HF
+#define SC_NST_HF 4
+#endif
+#ifndef SC_NST_HB
+#define SC_NST_HB 3
+#endif
 #ifndef SC_SCAN_CB
 #define SC_SCAN_CB 256
 #endif
@@ -857,7 +878,7 @@ template <typename T, int VEC, bool PRECISE>
 static int scan_fwd_tma(const void* G, int64_t ldg, const float* h0, const float* s0, void* Hout, int64_t ldh,
                         float* hT, float* sT, float* Sckpt, int64_t B, int64_t Tn, int64_t H, int train,
                         cudaStream_t st) {
-  constexpr int NST = 4;
+  constexpr int NST = sizeof(T) == 2 ? SC_NST_FWD : 4;     // ring depth (16-bit rows: see SC_NST_FWD above)
   constexpr int smem = NST * 5 * TC * CB * (int)sizeof(T);
   CUtensorMap mapG;
   if (!make_scan_map_gates<T>(&mapG, G, B * Tn, H, ldg, TC)) return SC_E_UNSUP;
@@ -879,7 +900,7 @@ template <typename T, int VEC, bool PRECISE>
 static int scan_bwd_tma(const void* G, int64_t ldg, const void* Hout, int64_t ldh, const float* h0,
                         const float* Sckpt, const void* dHout, int64_t lddh, void* dG, int64_t lddg,
                         float* dbias, int64_t B, int64_t Tn, int64_t H, int train, cudaStream_t st) {
-  constexpr int NST = 3;
+  constexpr int NST = sizeof(T) == 2 ? SC_NST_BWD : 3;     // ring depth (16-bit rows: see SC_NST_BWD above)
   constexpr int smem = NST * 7 * TC * CB * (int)sizeof(T);
   CUtensorMap mapG, mapH, mapDH;
   if (!make_scan_map<T>(&mapG, G, B * Tn, 5 * H, ldg, TC) || !make_scan_map<T>(&mapH, Hout, B * Tn, H, ldh, TC) ||
@@ -953,7 +974,7 @@ static int sscan_fwd_tma_t(const void* k, const void* v, const void* q, int64_t 
                            const float* s0, void* A, int64_t lda, float* S_all, float* sT, int64_t B, int64_t Tn,
                            int64_t H, int train, cudaStream_t st) {
   if (!split_ok<T>({k, v, q, addend, A, S_all}, {ldg, ldadd, lda}, H, B, Tn)) return SC_E_UNSUP;
-  constexpr int NST = 4;
+  constexpr int NST = sizeof(T) == 2 ? SC_NST_SF : 4;     // ring depth (16-bit rows: see SC_NST_SF above)
   constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
   CUtensorMap mk, mv, mq, ma;
   if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
@@ -985,7 +1006,7 @@ static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t 
   if (!split_ok<T>({k, v, q, dA}, {ldg, ldda}, H, B, Tn) || (lddg % 2) ||
       (((uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dq) & (2 * sizeof(T) - 1)) || ((uintptr_t)S_all & 7))
     return SC_E_UNSUP;
-  constexpr int NST = 4;
+  constexpr int NST = sizeof(T) == 2 ? SC_NST_SB : 4;     // ring depth (16-bit rows: see SC_NST_SB above)
   constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
   CUtensorMap mk, mv, mq, mda;
   if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
@@ -1013,7 +1034,7 @@ template <typename T, bool PRECISE>
 static int hscan_fwd_tma_t(const void* An, int64_t ldan, const void* Zn, int64_t ldzn, const float* h0, void* Hout,
                            int64_t ldh, float* hT, int64_t B, int64_t Tn, int64_t H, cudaStream_t st) {
   if (!split_ok<T>({An, Zn}, {ldan, ldzn}, H, B, Tn) || (ldh % 2) || ((uintptr_t)Hout & (2 * sizeof(T) - 1))) return SC_E_UNSUP;
-  constexpr int NST = 4;
+  constexpr int NST = sizeof(T) == 2 ? SC_NST_HF : 4;     // ring depth (16-bit rows: see SC_NST_HF above)
   constexpr int smem = NST * 2 * TC * CB * (int)sizeof(T);
   CUtensorMap ma, mz;
   if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TC) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TC)) return SC_E_UNSUP;
@@ -1037,7 +1058,7 @@ static int hscan_bwd_tma_t(const void* An, int64_t ldan, const void* Zn, int64_t
   if (!split_ok<T>({An, Zn, Hout, dHout}, {ldan, ldzn, ldh, lddh}, H, B, Tn) || (lddan % 2) || (lddzn % 2) ||
       (((uintptr_t)dAn | (uintptr_t)dZn) & (2 * sizeof(T) - 1)))
     return SC_E_UNSUP;
-  constexpr int NST = 3;
+  constexpr int NST = sizeof(T) == 2 ? SC_NST_HB : 3;     // ring depth (16-bit rows: see SC_NST_HB above)
   constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
   CUtensorMap ma, mz, mdh, mh;
   if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TC) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TC) ||
