@@ -187,6 +187,38 @@ def test_fused_scan_large_properties(cuda_device):
     assert torch.isfinite(dG.float()).all() and torch.isfinite(db).all()
 
 
+@pytest.mark.parametrize("H", [256, 1024])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_layernorm_bwd_many_rows_and_dx_colsum(cuda_device, dtype, H):
+    """Enough rows that every warp of the staged backward kernel walks its shared-memory ring several times
+    (M = 14 321 over 592 blocks of 4 warps: 6-7 rows per warp), strided operands as the module passes them (blocks of a
+    wider tensor), and the column sums of dx (`dxsum`, the bias gradient of the producing projection)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(19)
+    M = 14321
+    big_x = (torch.randn(M, 3 * H, generator=g) * 1.5 - 0.3).to(dtype)
+    big_dy = torch.randn(M, 2 * H, generator=g).to(dtype)
+    x, dy = big_x[:, H:2 * H], big_dy[:, H:]                       # row stride 3H / 2H
+    w = torch.randn(H, generator=g)
+    b = torch.randn(H, generator=g)
+    xd = x.double().requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd, (H,), wd, bd, 1e-5)
+    ref.backward(dy.double())
+    xg, dyg = big_x.cuda()[:, H:2 * H], big_dy.cuda()[:, H:]
+    y, mean, rstd = ops.layernorm_fwd(xg, w.cuda(), b.cuda())
+    _close(y, ref.detach(), dtype, "ln fwd")
+    big_dx = torch.zeros(M, 2 * H, dtype=dtype, device="cuda")
+    dxsum = torch.zeros(H, device="cuda")
+    dx, dw, db = ops.layernorm_bwd(dyg, xg, w.cuda(), mean, rstd, dx=big_dx[:, :H], dxsum=dxsum)
+    _close(dx, xd.grad, dtype, "ln dx")
+    assert not big_dx[:, H:].any()                                  # nothing written beside the block
+    for got, want, what in ((dw, wd.grad, "dw"), (db, bd.grad, "db"), (dxsum, xd.grad.sum(0), "dxsum")):
+        want = want.float()
+        tol = (2e-4 if dtype == torch.float32 else 2e-2) * max(1.0, float(want.abs().max()))
+        assert float((got.cpu() - want).abs().max()) <= tol, (what, float((got.cpu() - want).abs().max()), tol)
+
+
 # ------------------------------------------------------------------ K2' split scans --
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("mode", ["train", "step", "prefix"])
