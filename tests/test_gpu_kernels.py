@@ -187,6 +187,22 @@ def test_fused_scan_large_properties(cuda_device):
     assert torch.isfinite(dG.float()).all() and torch.isfinite(db).all()
 
 
+@pytest.mark.parametrize("rows,cols,pad", [(5120, 1032, 0), (77, 88, 8), (33, 30, 2), (5, 7, 0)])
+def test_split_bf16_hi_lo(cuda_device, rows, cols, pad):
+    """fp32 -> [hi | lo] bf16 expansion (what carries fp32 weight-space products through the bf16 tensor cores): bit-exact
+    against torch's round-to-nearest-even, the four-column kernel and the scalar one (odd widths / strides)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + cols)
+    big = torch.randn(rows, cols + pad, generator=g) * 3
+    src = big.cuda()[:, :cols] if pad else big.cuda()
+    out = ops.split_bf16(src)
+    hi = big[:, :cols].to(torch.bfloat16)
+    lo = (big[:, :cols] - hi.float()).to(torch.bfloat16)
+    assert out.shape == (rows, 2 * cols)
+    assert torch.equal(out[:, :cols].cpu().view(torch.int16), hi.view(torch.int16))
+    assert torch.equal(out[:, cols:].cpu().view(torch.int16), lo.view(torch.int16))
+
+
 @pytest.mark.parametrize("H", [256, 1024])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_layernorm_bwd_many_rows_and_dx_colsum(cuda_device, dtype, H):
