@@ -35,11 +35,11 @@ constexpr int TC = SC_SCAN_CKPT;     // timesteps per stage == checkpoint interv
 #ifndef SC_NST_SB
 #define SC_NST_SB 4
 #endif
-#ifndef SC_NST_HF
-#define SC_NST_HF 4
+#ifndef SC_HSCAN_FWD_ROWS
+#define SC_HSCAN_FWD_ROWS 32                 // rows per stage of the h-scan kernels (16-bit rows)
 #endif
-#ifndef SC_NST_HB
-#define SC_NST_HB 3
+#ifndef SC_HSCAN_BWD_ROWS
+#define SC_HSCAN_BWD_ROWS 16
 #endif
 #ifndef SC_SCAN_CB
 #define SC_SCAN_CB 256
@@ -669,23 +669,26 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
   }
 }
 
-// h scan.  Stage = An, Zn boxes.
-template <typename T, int NST, bool PRECISE>
+// h scan.  Stage = An, Zn boxes of TCH rows.  A stage of 8 rows made this kernel pay a block barrier, an mbarrier
+// wait and two copy issues per ~150 instructions of work (0.36 ms per [192000 x 1024] call = 3.3 TB/s of 1.18 GB, and
+// a deeper ring changed nothing): stages of TCH rows (32 for 16-bit rows) are walked as 8-step groups.
+template <typename T, int NST, bool PRECISE, int TCH>
 __global__ void __launch_bounds__(SPLIT_THREADS)
 hscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapZ,
                      const float* __restrict__ h0, T* __restrict__ Hout, int64_t ldh, float* __restrict__ hT,
                      int Tn, int H, int cblocks) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int BOX = TCH * CB * (int)sizeof(T);
   constexpr int STAGE = 2 * BOX;
   __shared__ __align__(8) uint64_t bars[NST];
-  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  k.nchunk = (Tn + TCH - 1) / TCH;
   scan_bars_init<NST>(bars, k.tid);
   auto issue = [&](int chunk) {
     const int st = chunk % NST;
     const uint32_t bar = smem_u32(&bars[st]);
     mbar_expect_tx(bar, STAGE);
-    const int row = k.b * Tn + chunk * TC;
+    const int row = k.b * Tn + chunk * TCH;
     tma_load_2d(k.sbase + st * STAGE, &mapA, bar, k.c0, row);
     tma_load_2d(k.sbase + st * STAGE + BOX, &mapZ, bar, k.c0, row);
   };
@@ -700,42 +703,48 @@ hscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (k.tid == 0 && c + NST - 1 < k.nchunk) issue(c + NST - 1);
     mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
     const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
-    const int t0 = c * TC;
-    if (t0 + TC <= Tn) {
-      // full interval: every step's loads and activations first, behind a scheduling fence, then the carried chain
-      // (same operations in the same order per element; see lucy_scan_fwd_tma_kernel)
-      float cc[TC][SV], zh[TC][SV];
+#pragma unroll 1
+    for (int sub = 0; sub < TCH / TC; ++sub) {
+      const int t0 = c * TCH + sub * TC;
+      if (t0 >= Tn) break;
+      const T* sa = st + (size_t)sub * TC * CB;          // An rows of this group
+      const T* sz = st + (size_t)(TCH + sub * TC) * CB;  // Zn rows
+      if (t0 + TC <= Tn) {
+        // full group: every step's loads and activations first, behind a scheduling fence, then the carried chain
+        // (same operations in the same order per element; see lucy_scan_fwd_tma_kernel)
+        float cc[TC][SV], zh[TC][SV];
 #pragma unroll
-      for (int u = 0; u < TC; ++u) {
-        float an[SV], zn[SV];
-        lds2(st + u * CB, k.tid, an);
-        lds2(st + (TC + u) * CB, k.tid, zn);
+        for (int u = 0; u < TC; ++u) {
+          float an[SV], zn[SV];
+          lds2(sa + u * CB, k.tid, an);
+          lds2(sz + u * CB, k.tid, zn);
 #pragma unroll
-        for (int i = 0; i < SV; ++i) { cc[u][i] = tanhf_<PRECISE>(an[i]); zh[u][i] = sigmoidf_<PRECISE>(zn[i]); }
-      }
-      __syncwarp();
+          for (int i = 0; i < SV; ++i) { cc[u][i] = tanhf_<PRECISE>(an[i]); zh[u][i] = sigmoidf_<PRECISE>(zn[i]); }
+        }
+        __syncwarp();
 #pragma unroll
-      for (int u = 0; u < TC; ++u) {
-        float out[SV];
+        for (int u = 0; u < TC; ++u) {
+          float out[SV];
 #pragma unroll
-        for (int i = 0; i < SV; ++i) { h[i] = fmaf(zh[u][i], h[i] - cc[u][i], cc[u][i]); out[i] = h[i]; }
-        if (k.live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < TC; ++u) {
-        if (t0 + u < Tn) {
-          float an[SV], zn[SV], out[SV];
-          lds2(st + u * CB, k.tid, an);
-          lds2(st + (TC + u) * CB, k.tid, zn);
-#pragma unroll
-          for (int i = 0; i < SV; ++i) {
-            const float cc = tanhf_<PRECISE>(an[i]);
-            const float zh = sigmoidf_<PRECISE>(zn[i]);
-            h[i] = fmaf(zh, h[i] - cc, cc);
-            out[i] = h[i];
-          }
+          for (int i = 0; i < SV; ++i) { h[i] = fmaf(zh[u][i], h[i] - cc[u][i], cc[u][i]); out[i] = h[i]; }
           if (k.live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < TC; ++u) {
+          if (t0 + u < Tn) {
+            float an[SV], zn[SV], out[SV];
+            lds2(sa + u * CB, k.tid, an);
+            lds2(sz + u * CB, k.tid, zn);
+#pragma unroll
+            for (int i = 0; i < SV; ++i) {
+              const float cc = tanhf_<PRECISE>(an[i]);
+              const float zh = sigmoidf_<PRECISE>(zn[i]);
+              h[i] = fmaf(zh, h[i] - cc, cc);
+              out[i] = h[i];
+            }
+            if (k.live) stg_vec<T>(ho + (int64_t)(t0 + u) * ldh, out);
+          }
         }
       }
     }
@@ -746,25 +755,27 @@ hscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
 }
 
-// Reverse-time adjoint of the h scan.  Stage = An, Zn, dHout boxes + Hout shifted one row back.
-template <typename T, int NST, bool PRECISE>
+// Reverse-time adjoint of the h scan.  Stage = An, Zn, dHout boxes + Hout shifted one row back, TCH rows each, walked
+// last 8-step group first.
+template <typename T, int NST, bool PRECISE, int TCH>
 __global__ void __launch_bounds__(SPLIT_THREADS)
 hscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapZ,
                      const __grid_constant__ CUtensorMap mapDH, const __grid_constant__ CUtensorMap mapH,
                      const float* __restrict__ h0, T* __restrict__ dAn, int64_t lddan, T* __restrict__ dZn,
                      int64_t lddzn, int Tn, int H, int cblocks) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int BOX = TCH * CB * (int)sizeof(T);
   constexpr int STAGE = 4 * BOX;
   __shared__ __align__(8) uint64_t bars[NST];
-  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  k.nchunk = (Tn + TCH - 1) / TCH;
   scan_bars_init<NST>(bars, k.tid);
   auto issue = [&](int it) {
     const int chunk = k.nchunk - 1 - it;
     const int st = it % NST;
     const uint32_t bar = smem_u32(&bars[st]);
     mbar_expect_tx(bar, STAGE);
-    const int row = k.b * Tn + chunk * TC;
+    const int row = k.b * Tn + chunk * TCH;
     const uint32_t d = k.sbase + st * STAGE;
     tma_load_2d(d, &mapA, bar, k.c0, row);
     tma_load_2d(d + BOX, &mapZ, bar, k.c0, row);
@@ -786,72 +797,77 @@ hscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     __syncthreads();
     if (k.tid == 0 && it + NST - 1 < k.nchunk) issue(it + NST - 1);
     mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
-    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
-    const int t0 = chunk * TC;
-    if (t0 + TC <= Tn && t0 > 0) {
-      // full interval that does not hold frame 0: activations and their products of all steps first (scheduling
-      // fence), then the carried chain gz -> gam; same operations in the same order per element
-      float zh[TC][SV], t1[TC][SV], hmc[TC][SV], go[TC][SV];
+    const T* stg = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
+#pragma unroll 1
+    for (int sub = TCH / TC - 1; sub >= 0; --sub) {
+      const int t0 = chunk * TCH + sub * TC;
+      if (t0 >= Tn) continue;
+      const T* st = stg + (size_t)sub * TC * CB;       // row u of box g of this group: st + (g * TCH + u) * CB
+      if (t0 + TC <= Tn && t0 > 0) {
+        // full group that does not hold frame 0: activations and their products of all steps first (scheduling
+        // fence), then the carried chain gz -> gam; same operations in the same order per element
+        float zh[TC][SV], t1[TC][SV], hmc[TC][SV], go[TC][SV];
+#pragma unroll
+        for (int u = TC - 1; u >= 0; --u) {
+          float an[SV], zn[SV], hp[SV];
+          lds2(st + u * CB, k.tid, an);
+          lds2(st + (TCH + u) * CB, k.tid, zn);
+          lds2(st + (2 * TCH + u) * CB, k.tid, go[u]);
+          lds2(st + (3 * TCH + u) * CB, k.tid, hp);
+#pragma unroll
+          for (int i = 0; i < SV; ++i) {
+            const float cc = tanhf_<PRECISE>(an[i]);
+            zh[u][i] = sigmoidf_<PRECISE>(zn[i]);
+            t1[u][i] = fmaf(-cc, cc, 1.f);
+            hmc[u][i] = hp[i] - cc;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = TC - 1; u >= 0; --u) {
+          float da[SV], dz[SV];
+#pragma unroll
+          for (int i = 0; i < SV; ++i) {
+            const float gam = go[u][i] + gz[i];
+            gz[i] = zh[u][i] * gam;
+            const float omz = 1.f - zh[u][i];
+            da[i] = gam * omz * t1[u][i];
+            dz[i] = gam * hmc[u][i] * zh[u][i] * omz;
+          }
+          if (k.live) {
+            stg_vec<T>(oa + (int64_t)(t0 + u) * lddan, da);
+            stg_vec<T>(oz + (int64_t)(t0 + u) * lddzn, dz);
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int u = TC - 1; u >= 0; --u) {
-        float an[SV], zn[SV], hp[SV];
-        lds2(st + u * CB, k.tid, an);
-        lds2(st + (TC + u) * CB, k.tid, zn);
-        lds2(st + (2 * TC + u) * CB, k.tid, go[u]);
-        lds2(st + (3 * TC + u) * CB, k.tid, hp);
+        const int t = t0 + u;
+        if (t < Tn) {
+          float an[SV], zn[SV], go[SV], hp[SV], da[SV], dz[SV];
+          lds2(st + u * CB, k.tid, an);
+          lds2(st + (TCH + u) * CB, k.tid, zn);
+          lds2(st + (2 * TCH + u) * CB, k.tid, go);
+          lds2(st + (3 * TCH + u) * CB, k.tid, hp);
+          if (t == 0) {
 #pragma unroll
-        for (int i = 0; i < SV; ++i) {
-          const float cc = tanhf_<PRECISE>(an[i]);
-          zh[u][i] = sigmoidf_<PRECISE>(zn[i]);
-          t1[u][i] = fmaf(-cc, cc, 1.f);
-          hmc[u][i] = hp[i] - cc;
-        }
-      }
-      __syncwarp();
+            for (int i = 0; i < SV; ++i) hp[i] = hfirst[i];
+          }
 #pragma unroll
-      for (int u = TC - 1; u >= 0; --u) {
-        float da[SV], dz[SV];
-#pragma unroll
-        for (int i = 0; i < SV; ++i) {
-          const float gam = go[u][i] + gz[i];
-          gz[i] = zh[u][i] * gam;
-          const float omz = 1.f - zh[u][i];
-          da[i] = gam * omz * t1[u][i];
-          dz[i] = gam * hmc[u][i] * zh[u][i] * omz;
-        }
-        if (k.live) {
-          stg_vec<T>(oa + (int64_t)(t0 + u) * lddan, da);
-          stg_vec<T>(oz + (int64_t)(t0 + u) * lddzn, dz);
-        }
-      }
-      continue;
-    }
-#pragma unroll
-    for (int u = TC - 1; u >= 0; --u) {
-      const int t = t0 + u;
-      if (t < Tn) {
-        float an[SV], zn[SV], go[SV], hp[SV], da[SV], dz[SV];
-        lds2(st + u * CB, k.tid, an);
-        lds2(st + (TC + u) * CB, k.tid, zn);
-        lds2(st + (2 * TC + u) * CB, k.tid, go);
-        lds2(st + (3 * TC + u) * CB, k.tid, hp);
-        if (t == 0) {
-#pragma unroll
-          for (int i = 0; i < SV; ++i) hp[i] = hfirst[i];
-        }
-#pragma unroll
-        for (int i = 0; i < SV; ++i) {
-          const float cc = tanhf_<PRECISE>(an[i]);
-          const float zh = sigmoidf_<PRECISE>(zn[i]);
-          const float gam = go[i] + gz[i];
-          gz[i] = zh * gam;
-          const float omz = 1.f - zh;
-          da[i] = gam * omz * fmaf(-cc, cc, 1.f);
-          dz[i] = gam * (hp[i] - cc) * zh * omz;
-        }
-        if (k.live) {
-          stg_vec<T>(oa + (int64_t)t * lddan, da);
-          stg_vec<T>(oz + (int64_t)t * lddzn, dz);
+          for (int i = 0; i < SV; ++i) {
+            const float cc = tanhf_<PRECISE>(an[i]);
+            const float zh = sigmoidf_<PRECISE>(zn[i]);
+            const float gam = go[i] + gz[i];
+            gz[i] = zh * gam;
+            const float omz = 1.f - zh;
+            da[i] = gam * omz * fmaf(-cc, cc, 1.f);
+            dz[i] = gam * (hp[i] - cc) * zh * omz;
+          }
+          if (k.live) {
+            stg_vec<T>(oa + (int64_t)t * lddan, da);
+            stg_vec<T>(oz + (int64_t)t * lddzn, dz);
+          }
         }
       }
     }
@@ -1034,12 +1050,13 @@ template <typename T, bool PRECISE>
 static int hscan_fwd_tma_t(const void* An, int64_t ldan, const void* Zn, int64_t ldzn, const float* h0, void* Hout,
                            int64_t ldh, float* hT, int64_t B, int64_t Tn, int64_t H, cudaStream_t st) {
   if (!split_ok<T>({An, Zn}, {ldan, ldzn}, H, B, Tn) || (ldh % 2) || ((uintptr_t)Hout & (2 * sizeof(T) - 1))) return SC_E_UNSUP;
-  constexpr int NST = sizeof(T) == 2 ? SC_NST_HF : 4;     // ring depth (16-bit rows: see SC_NST_HF above)
-  constexpr int smem = NST * 2 * TC * CB * (int)sizeof(T);
+  constexpr int TCH = sizeof(T) == 2 ? SC_HSCAN_FWD_ROWS : 16;    // rows per stage: 32 KB per stage either way
+  constexpr int NST = 3;
+  constexpr int smem = NST * 2 * TCH * CB * (int)sizeof(T);
   CUtensorMap ma, mz;
-  if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TC) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TC)) return SC_E_UNSUP;
+  if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TCH) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TCH)) return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
-  auto kk = hscan_fwd_tma_kernel<T, NST, PRECISE>;
+  auto kk = hscan_fwd_tma_kernel<T, NST, PRECISE, TCH>;
   int e = set_smem(kk, smem); if (e) return e;
   kk<<<(unsigned)(B * cblocks), SPLIT_THREADS, smem, st>>>(ma, mz, h0, (T*)Hout, ldh, hT, (int)Tn, (int)H, cblocks);
   SC_LAUNCH_RET();
@@ -1058,14 +1075,15 @@ static int hscan_bwd_tma_t(const void* An, int64_t ldan, const void* Zn, int64_t
   if (!split_ok<T>({An, Zn, Hout, dHout}, {ldan, ldzn, ldh, lddh}, H, B, Tn) || (lddan % 2) || (lddzn % 2) ||
       (((uintptr_t)dAn | (uintptr_t)dZn) & (2 * sizeof(T) - 1)))
     return SC_E_UNSUP;
-  constexpr int NST = sizeof(T) == 2 ? SC_NST_HB : 3;     // ring depth (16-bit rows: see SC_NST_HB above)
-  constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
+  constexpr int TCH = sizeof(T) == 2 ? SC_HSCAN_BWD_ROWS : 8;     // rows per stage: 32 KB per stage either way (two CTAs per SM)
+  constexpr int NST = 3;
+  constexpr int smem = NST * 4 * TCH * CB * (int)sizeof(T);
   CUtensorMap ma, mz, mdh, mh;
-  if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TC) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TC) ||
-      !make_scan_map<T>(&mdh, dHout, B * Tn, H, lddh, TC) || !make_scan_map<T>(&mh, Hout, B * Tn, H, ldh, TC))
+  if (!make_scan_map<T>(&ma, An, B * Tn, H, ldan, TCH) || !make_scan_map<T>(&mz, Zn, B * Tn, H, ldzn, TCH) ||
+      !make_scan_map<T>(&mdh, dHout, B * Tn, H, lddh, TCH) || !make_scan_map<T>(&mh, Hout, B * Tn, H, ldh, TCH))
     return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
-  auto kk = hscan_bwd_tma_kernel<T, NST, PRECISE>;
+  auto kk = hscan_bwd_tma_kernel<T, NST, PRECISE, TCH>;
   int e = set_smem(kk, smem); if (e) return e;
   kk<<<(unsigned)(B * cblocks), SPLIT_THREADS, smem, st>>>(ma, mz, mdh, mh, h0, (T*)dAn, lddan, (T*)dZn, lddzn, (int)Tn, (int)H, cblocks);
   SC_LAUNCH_RET();
