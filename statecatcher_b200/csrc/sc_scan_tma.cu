@@ -29,11 +29,8 @@ constexpr int TC = SC_SCAN_CKPT;     // timesteps per stage == checkpoint interv
 #ifndef SC_NST_BWD
 #define SC_NST_BWD 3
 #endif
-#ifndef SC_NST_SF
-#define SC_NST_SF 4
-#endif
-#ifndef SC_NST_SB
-#define SC_NST_SB 4
+#ifndef SC_SSCAN_ROWS
+#define SC_SSCAN_ROWS 16                     // rows per stage of the S-scan kernels (16-bit rows)
 #endif
 #ifndef SC_HSCAN_FWD_ROWS
 #define SC_HSCAN_FWD_ROWS 32                 // rows per stage of the h-scan kernels (16-bit rows)
@@ -458,23 +455,24 @@ __device__ __forceinline__ void scan_bars_init(uint64_t* bars, int tid) {
 
 // S scan + second application.  A = addend + s'.  Learned decay only (prefix_sum keeps the
 // simple kernel).  Stage = k, v, q, addend boxes.
-template <typename T, int NST, bool TRAIN, bool PRECISE>
+template <typename T, int NST, bool TRAIN, bool PRECISE, int ROWS>
 __global__ void __launch_bounds__(SPLIT_THREADS)
 sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                      const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapAdd,
                      const float* __restrict__ s0, T* __restrict__ A, int64_t lda, float* __restrict__ S_all,
                      float* __restrict__ sT, int Tn, int H, int cblocks) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int BOX = ROWS * CB * (int)sizeof(T);        // stages of ROWS rows, walked as 8-step groups (see the h scan)
   constexpr int STAGE = 4 * BOX;
   __shared__ __align__(8) uint64_t bars[NST];
-  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  const ScanBlock k = scan_block(Tn, H, cblocks, smem);   // k.nchunk: 8-step intervals (the checkpoints' index)
+  const int nstage = (Tn + ROWS - 1) / ROWS;
   scan_bars_init<NST>(bars, k.tid);
   auto issue = [&](int chunk) {
     const int st = chunk % NST;
     const uint32_t bar = smem_u32(&bars[st]);
     mbar_expect_tx(bar, STAGE);
-    const int row = k.b * Tn + chunk * TC;
+    const int row = k.b * Tn + chunk * ROWS;
     const uint32_t d = k.sbase + st * STAGE;
     tma_load_2d(d, &mapK, bar, k.c0, row);
     tma_load_2d(d + BOX, &mapV, bar, k.c0, row);
@@ -482,17 +480,21 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     tma_load_2d(d + 3 * BOX, &mapAdd, bar, k.c0, row);
   };
   if (k.tid == 0)
-    for (int c = 0; c < NST - 1 && c < k.nchunk; ++c) issue(c);
+    for (int c = 0; c < NST - 1 && c < nstage; ++c) issue(c);
   float S[SV];
 #pragma unroll
   for (int i = 0; i < SV; ++i) S[i] = (TRAIN || !k.live) ? 0.f : s0[(int64_t)k.b * H + k.ch + i];
   T* ao = A + (int64_t)k.b * Tn * lda + k.ch;
-  for (int c = 0; c < k.nchunk; ++c) {
+  for (int sc = 0; sc < nstage; ++sc) {
     __syncthreads();
-    if (k.tid == 0 && c + NST - 1 < k.nchunk) issue(c + NST - 1);
-    mbar_wait(smem_u32(&bars[c % NST]), (uint32_t)((c / NST) & 1));
-    const T* st = reinterpret_cast<const T*>(smem + (c % NST) * STAGE);
+    if (k.tid == 0 && sc + NST - 1 < nstage) issue(sc + NST - 1);
+    mbar_wait(smem_u32(&bars[sc % NST]), (uint32_t)((sc / NST) & 1));
+#pragma unroll 1
+   for (int sub = 0; sub < ROWS / TC; ++sub) {
+    const int c = sc * (ROWS / TC) + sub;                 // 8-step interval
     const int t0 = c * TC;
+    if (t0 >= Tn) break;
+    const T* st = reinterpret_cast<const T*>(smem + (sc % NST) * STAGE) + (size_t)sub * TC * CB;   // row u of box g: st + (g * ROWS + u) * CB
     // S entering the interval: all the backward needs (it recomputes inside an interval, as the fused kernel does);
     // r01 saved every S_t as an fp32 row: 4 bytes per element written here and 4.5 read back
     if (k.live) *reinterpret_cast<float2*>(S_all + ((int64_t)k.b * k.nchunk + c) * H + k.ch) = make_float2(S[0], S[1]);
@@ -502,10 +504,10 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
 #pragma unroll
       for (int u = 0; u < TC; ++u) {
         float kk[SV], vv[SV], qq[SV];
-        lds2(st + (0 * TC + u) * CB, k.tid, kk);
-        lds2(st + (1 * TC + u) * CB, k.tid, vv);
-        lds2(st + (2 * TC + u) * CB, k.tid, qq);
-        lds2(st + (3 * TC + u) * CB, k.tid, ad[u]);
+        lds2(st + (0 * ROWS + u) * CB, k.tid, kk);
+        lds2(st + (1 * ROWS + u) * CB, k.tid, vv);
+        lds2(st + (2 * ROWS + u) * CB, k.tid, qq);
+        lds2(st + (3 * ROWS + u) * CB, k.tid, ad[u]);
 #pragma unroll
         for (int i = 0; i < SV; ++i) { d[u][i] = sigmoidf_<PRECISE>(qq[i]); kv[u][i] = kk[i] * vv[i]; }
       }
@@ -526,10 +528,10 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     for (int u = 0; u < TC; ++u) {
       if (t0 + u < Tn) {
         float kk[SV], vv[SV], qq[SV], ad[SV], out[SV];
-        lds2(st + (0 * TC + u) * CB, k.tid, kk);
-        lds2(st + (1 * TC + u) * CB, k.tid, vv);
-        lds2(st + (2 * TC + u) * CB, k.tid, qq);
-        lds2(st + (3 * TC + u) * CB, k.tid, ad);
+        lds2(st + (0 * ROWS + u) * CB, k.tid, kk);
+        lds2(st + (1 * ROWS + u) * CB, k.tid, vv);
+        lds2(st + (2 * ROWS + u) * CB, k.tid, qq);
+        lds2(st + (3 * ROWS + u) * CB, k.tid, ad);
 #pragma unroll
         for (int i = 0; i < SV; ++i) {
           const float d = sigmoidf_<PRECISE>(qq[i]);
@@ -540,6 +542,7 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
         if (k.live) stg_vec<T>(ao + (int64_t)(t0 + u) * lda, out);
       }
     }
+   }
   }
   if (k.live && !TRAIN && sT != nullptr) {
 #pragma unroll
@@ -549,7 +552,7 @@ sscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
 
 // Reverse-time adjoint of the S scan.  Stage = k, v, q, dA boxes; S_t of an interval is recomputed forwards from the
 // interval's checkpoint (fetched one interval ahead), then the interval is walked backwards.
-template <typename T, int NST, bool TRAIN, bool PRECISE>
+template <typename T, int NST, bool TRAIN, bool PRECISE, int ROWS>
 __global__ void __launch_bounds__(SPLIT_THREADS)
 sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                      const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapDA,
@@ -559,17 +562,18 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
   // dsum (may be null): [3][H] column sums of dk, dv, dq over all rows, added atomically — the bias gradients of the
   // gate projection, which otherwise cost a pass over the whole gradient tensor (sc_colsum)
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int BOX = ROWS * CB * (int)sizeof(T);        // stages of ROWS rows, walked last 8-step group first
   constexpr int STAGE = 4 * BOX;
   __shared__ __align__(8) uint64_t bars[NST];
-  const ScanBlock k = scan_block(Tn, H, cblocks, smem);
+  const ScanBlock k = scan_block(Tn, H, cblocks, smem);   // k.nchunk: 8-step intervals (the checkpoints' index)
+  const int nstage = (Tn + ROWS - 1) / ROWS;
   scan_bars_init<NST>(bars, k.tid);
   auto issue = [&](int it) {
-    const int chunk = k.nchunk - 1 - it;
+    const int chunk = nstage - 1 - it;
     const int st = it % NST;
     const uint32_t bar = smem_u32(&bars[st]);
     mbar_expect_tx(bar, STAGE);
-    const int row = k.b * Tn + chunk * TC;
+    const int row = k.b * Tn + chunk * ROWS;
     const uint32_t d = k.sbase + st * STAGE;
     tma_load_2d(d, &mapK, bar, k.c0, row);
     tma_load_2d(d + BOX, &mapV, bar, k.c0, row);
@@ -577,7 +581,7 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     tma_load_2d(d + 3 * BOX, &mapDA, bar, k.c0, row);
   };
   if (k.tid == 0)
-    for (int it = 0; it < NST - 1 && it < k.nchunk; ++it) issue(it);
+    for (int it = 0; it < NST - 1 && it < nstage; ++it) issue(it);
   float ds[SV], acc[3][SV], Snext[SV];
 #pragma unroll
   for (int i = 0; i < SV; ++i) {
@@ -586,18 +590,22 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
     Snext[i] = k.live ? Sck[((int64_t)k.b * k.nchunk + k.nchunk - 1) * H + k.ch + i] : 0.f;
   }
   const int64_t obase = (int64_t)k.b * Tn * lddg + k.ch;
-  for (int it = 0; it < k.nchunk; ++it) {
-    const int chunk = k.nchunk - 1 - it;
+  for (int it = 0; it < nstage; ++it) {
+    const int stage_idx = nstage - 1 - it;
     __syncthreads();
-    if (k.tid == 0 && it + NST - 1 < k.nchunk) issue(it + NST - 1);
+    if (k.tid == 0 && it + NST - 1 < nstage) issue(it + NST - 1);
+    mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
+#pragma unroll 1
+   for (int sub = ROWS / TC - 1; sub >= 0; --sub) {
+    const int chunk = stage_idx * (ROWS / TC) + sub;      // 8-step interval
+    if (chunk >= k.nchunk) continue;
     float Sin[SV];
 #pragma unroll
     for (int i = 0; i < SV; ++i) {
       Sin[i] = Snext[i];
       Snext[i] = (k.live && chunk > 0) ? Sck[((int64_t)k.b * k.nchunk + chunk - 1) * H + k.ch + i] : 0.f;
     }
-    mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
-    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
+    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE) + (size_t)sub * TC * CB;   // row u of box g: st + (g * ROWS + u) * CB
     const int t0 = chunk * TC;
     // pass 1: every load of the interval, d_t, and S_t forwards from the checkpoint (rows past the segment's end
     // belong to the next stream or are zero-filled: computed, never stored)
@@ -609,10 +617,10 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
 #pragma unroll
       for (int u = 0; u < TC; ++u) {
         float qq[SV];
-        lds2(st + (0 * TC + u) * CB, k.tid, kk[u]);
-        lds2(st + (1 * TC + u) * CB, k.tid, vv[u]);
-        lds2(st + (2 * TC + u) * CB, k.tid, qq);
-        lds2(st + (3 * TC + u) * CB, k.tid, da[u]);
+        lds2(st + (0 * ROWS + u) * CB, k.tid, kk[u]);
+        lds2(st + (1 * ROWS + u) * CB, k.tid, vv[u]);
+        lds2(st + (2 * ROWS + u) * CB, k.tid, qq);
+        lds2(st + (3 * ROWS + u) * CB, k.tid, da[u]);
 #pragma unroll
         for (int i = 0; i < SV; ++i) dl[u][i] = sigmoidf_<PRECISE>(qq[i]);
       }
@@ -660,6 +668,7 @@ sscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_cons
         }
       }
     }
+   }
   }
   if (k.live && dsum != nullptr) {
 #pragma unroll
@@ -990,16 +999,17 @@ static int sscan_fwd_tma_t(const void* k, const void* v, const void* q, int64_t 
                            const float* s0, void* A, int64_t lda, float* S_all, float* sT, int64_t B, int64_t Tn,
                            int64_t H, int train, cudaStream_t st) {
   if (!split_ok<T>({k, v, q, addend, A, S_all}, {ldg, ldadd, lda}, H, B, Tn)) return SC_E_UNSUP;
-  constexpr int NST = sizeof(T) == 2 ? SC_NST_SF : 4;     // ring depth (16-bit rows: see SC_NST_SF above)
-  constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
+  constexpr int ROWS = sizeof(T) == 2 ? SC_SSCAN_ROWS : 8;        // rows per stage: 32 KB per stage either way
+  constexpr int NST = 3;
+  constexpr int smem = NST * 4 * ROWS * CB * (int)sizeof(T);
   CUtensorMap mk, mv, mq, ma;
-  if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
-      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, TC) || !make_scan_map<T>(&ma, addend, B * Tn, H, ldadd, TC))
+  if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, ROWS) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, ROWS) ||
+      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, ROWS) || !make_scan_map<T>(&ma, addend, B * Tn, H, ldadd, ROWS))
     return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
   const unsigned grid = (unsigned)(B * cblocks);
-  auto kt = sscan_fwd_tma_kernel<T, NST, true, PRECISE>;
-  auto ks = sscan_fwd_tma_kernel<T, NST, false, PRECISE>;
+  auto kt = sscan_fwd_tma_kernel<T, NST, true, PRECISE, ROWS>;
+  auto ks = sscan_fwd_tma_kernel<T, NST, false, PRECISE, ROWS>;
   int e = set_smem(kt, smem); if (e) return e;
   e = set_smem(ks, smem); if (e) return e;
   if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, ma, s0, (T*)A, lda, S_all, sT, (int)Tn, (int)H, cblocks);
@@ -1022,16 +1032,17 @@ static int sscan_bwd_tma_t(const void* k, const void* v, const void* q, int64_t 
   if (!split_ok<T>({k, v, q, dA}, {ldg, ldda}, H, B, Tn) || (lddg % 2) ||
       (((uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dq) & (2 * sizeof(T) - 1)) || ((uintptr_t)S_all & 7))
     return SC_E_UNSUP;
-  constexpr int NST = sizeof(T) == 2 ? SC_NST_SB : 4;     // ring depth (16-bit rows: see SC_NST_SB above)
-  constexpr int smem = NST * 4 * TC * CB * (int)sizeof(T);
+  constexpr int ROWS = sizeof(T) == 2 ? SC_SSCAN_ROWS : 8;        // rows per stage: 32 KB per stage either way
+  constexpr int NST = 3;
+  constexpr int smem = NST * 4 * ROWS * CB * (int)sizeof(T);
   CUtensorMap mk, mv, mq, mda;
-  if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, TC) ||
-      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, TC) || !make_scan_map<T>(&mda, dA, B * Tn, H, ldda, TC))
+  if (!make_scan_map<T>(&mk, k, B * Tn, H, ldg, ROWS) || !make_scan_map<T>(&mv, v, B * Tn, H, ldg, ROWS) ||
+      !make_scan_map<T>(&mq, q, B * Tn, H, ldg, ROWS) || !make_scan_map<T>(&mda, dA, B * Tn, H, ldda, ROWS))
     return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
   const unsigned grid = (unsigned)(B * cblocks);
-  auto kt = sscan_bwd_tma_kernel<T, NST, true, PRECISE>;
-  auto ks = sscan_bwd_tma_kernel<T, NST, false, PRECISE>;
+  auto kt = sscan_bwd_tma_kernel<T, NST, true, PRECISE, ROWS>;
+  auto ks = sscan_bwd_tma_kernel<T, NST, false, PRECISE, ROWS>;
   int e = set_smem(kt, smem); if (e) return e;
   e = set_smem(ks, smem); if (e) return e;
   if (train) kt<<<grid, SPLIT_THREADS, smem, st>>>(mk, mv, mq, mda, S_all, (T*)dk, (T*)dv, (T*)dq, lddg, dsum, (int)Tn, (int)H, cblocks);
