@@ -29,6 +29,11 @@ constexpr int TC = SC_SCAN_CKPT;     // timesteps per stage == checkpoint interv
 #ifndef SC_NST_BWD
 #define SC_NST_BWD 3
 #endif
+#ifndef SC_SCAN_BWD_ROWS
+#define SC_SCAN_BWD_ROWS 8                   // rows per stage of the fused backward (16-bit rows); 16 -> two stages of 56 KB: measured, no gain
+                                             // (5.10-5.11 against 5.02-5.03 ms per step, alternating same-box runs; the split kernels of the
+                                             // LayerNorm path did gain from 16/32-row stages - they carry 2-3 boxes per stage, this one seven)
+#endif
 #ifndef SC_SSCAN_ROWS
 #define SC_SSCAN_ROWS 16                     // rows per stage of the S-scan kernels (16-bit rows)
 #endif
@@ -253,14 +258,14 @@ lucy_scan_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const float* 
 // the stage, per-warp full/empty mbarriers instead of the block barrier; ncu had 8 % of this kernel's stall samples on
 // the block barrier and 11 % on the first use of the prefetched checkpoint — bit-identical, 5.37-5.42 ms per step against
 // 5.03-5.09 in alternating same-box runs.)
-template <typename T, int VEC, int NST, bool TRAIN, bool PRECISE>
+template <typename T, int VEC, int NST, bool TRAIN, bool PRECISE, int ROWS>
 __global__ void __launch_bounds__(CB / VEC)
 lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapH,
                          const __grid_constant__ CUtensorMap mapDH, const float* __restrict__ h0,
                          const float* __restrict__ Sckpt, T* __restrict__ dG, int64_t lddg,
                          float* __restrict__ dbias, int Tn, int H, int cblocks) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int BOX = TC * CB * (int)sizeof(T);
+  constexpr int BOX = ROWS * CB * (int)sizeof(T);         // stages of ROWS rows, walked last 8-step interval first
   constexpr int STAGE = 7 * BOX;
   __shared__ __align__(8) uint64_t bars[NST];
   const int tid = threadIdx.x;
@@ -268,7 +273,8 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
   const int c0 = (blockIdx.x % cblocks) * CB;
   const int ch = c0 + tid * VEC;
   const bool live = ch < H;
-  const int nchunk = (Tn + TC - 1) / TC;
+  const int nchunk = (Tn + TC - 1) / TC;                 // 8-step intervals (the checkpoints' index)
+  const int nstage = (Tn + ROWS - 1) / ROWS;
   const uint32_t sbase = smem_u32(smem);
 
   if (tid == 0) {
@@ -279,18 +285,18 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
 
   // chunks are visited last-to-first; "it" counts visits
   auto issue = [&](int it) {
-    const int chunk = nchunk - 1 - it;
+    const int chunk = nstage - 1 - it;
     const int st = it % NST;
     const uint32_t bar = smem_u32(&bars[st]);
     mbar_expect_tx(bar, STAGE);
-    const int row = b * Tn + chunk * TC;
+    const int row = b * Tn + chunk * ROWS;
 #pragma unroll
     for (int g = 0; g < 5; ++g) tma_load_2d(sbase + st * STAGE + g * BOX, &mapG, bar, g * H + c0, row);   // (one 3-D box of the five gates, as in the forward kernel: 5.06 vs 5.01 ms per step here)
     tma_load_2d(sbase + st * STAGE + 5 * BOX, &mapDH, bar, c0, row);
     tma_load_2d(sbase + st * STAGE + 6 * BOX, &mapH, bar, c0, row - 1);   // h_{t-1}; row -1 is OOB -> zeros
   };
   if (tid == 0)
-    for (int it = 0; it < NST - 1 && it < nchunk; ++it) issue(it);
+    for (int it = 0; it < NST - 1 && it < nstage; ++it) issue(it);
 
   float gz[VEC], ds[VEC], acc[5][VEC], hfirst[VEC];
 #pragma unroll
@@ -305,11 +311,16 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
 #pragma unroll
   for (int i = 0; i < VEC; ++i) Snext[i] = live ? Sckpt[((int64_t)b * nchunk + nchunk - 1) * H + ch + i] : 0.f;
 
-  for (int it = 0; it < nchunk; ++it) {
-    const int chunk = nchunk - 1 - it;
+  for (int it = 0; it < nstage; ++it) {
+    const int stage_idx = nstage - 1 - it;
     __syncthreads();
-    if (tid == 0 && it + NST - 1 < nchunk) issue(it + NST - 1);
-    // checkpoint of THIS interval was fetched one iteration ago; fetch the next one now so its
+    if (tid == 0 && it + NST - 1 < nstage) issue(it + NST - 1);
+    mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
+#pragma unroll 1
+   for (int sub = ROWS / TC - 1; sub >= 0; --sub) {
+    const int chunk = stage_idx * (ROWS / TC) + sub;
+    if (chunk >= nchunk) continue;
+    // checkpoint of THIS interval was fetched one interval ago; fetch the next one now so its
     // HBM latency hides behind this interval's work (it was 24 % of the stall samples)
     float Sin[VEC];
 #pragma unroll
@@ -317,8 +328,7 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
       Sin[i] = Snext[i];
       Snext[i] = (live && chunk > 0) ? Sckpt[((int64_t)b * nchunk + chunk - 1) * H + ch + i] : 0.f;
     }
-    mbar_wait(smem_u32(&bars[it % NST]), (uint32_t)((it / NST) & 1));
-    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE);
+    const T* st = reinterpret_cast<const T*>(smem + (it % NST) * STAGE) + (size_t)sub * TC * CB;   // row u of box g: st + (g * ROWS + u) * CB
     const int t0 = chunk * TC;
     // pass 1: recompute S_t and d_t across the interval
     float Sl[TC][VEC], dl[TC][VEC];
@@ -329,9 +339,9 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
 #pragma unroll
       for (int u = 0; u < TC; ++u) {
         float k[VEC], v[VEC], q[VEC];
-        lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
-        lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
-        lds2(st + (SC_GATE_Q * TC + u) * CB, tid, q);
+        lds2(st + (SC_GATE_K * ROWS + u) * CB, tid, k);
+        lds2(st + (SC_GATE_V * ROWS + u) * CB, tid, v);
+        lds2(st + (SC_GATE_Q * ROWS + u) * CB, tid, q);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           const float d = sigmoidf_<PRECISE>(q[i]);
@@ -350,12 +360,12 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
     T* rq = rz + (int64_t)SC_GATE_Q * H;
     auto step = [&](int u) {
       float z[VEC], k[VEC], v[VEC], p[VEC], go[VEC], hp[VEC];
-      lds2(st + (SC_GATE_Z * TC + u) * CB, tid, z);
-      lds2(st + (SC_GATE_K * TC + u) * CB, tid, k);
-      lds2(st + (SC_GATE_V * TC + u) * CB, tid, v);
-      lds2(st + (SC_GATE_P * TC + u) * CB, tid, p);
-      lds2(st + (5 * TC + u) * CB, tid, go);
-      lds2(st + (6 * TC + u) * CB, tid, hp);
+      lds2(st + (SC_GATE_Z * ROWS + u) * CB, tid, z);
+      lds2(st + (SC_GATE_K * ROWS + u) * CB, tid, k);
+      lds2(st + (SC_GATE_V * ROWS + u) * CB, tid, v);
+      lds2(st + (SC_GATE_P * ROWS + u) * CB, tid, p);
+      lds2(st + (5 * ROWS + u) * CB, tid, go);
+      lds2(st + (6 * ROWS + u) * CB, tid, hp);
       if (t0 + u == 0) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) hp[i] = hfirst[i];
@@ -413,6 +423,7 @@ lucy_scan_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_
         rz -= lddg; rk -= lddg; rv -= lddg; rp -= lddg; rq -= lddg;
       }
     }
+   }
   }
   if (live && dbias != nullptr) {
 #pragma unroll
@@ -925,16 +936,17 @@ template <typename T, int VEC, bool PRECISE>
 static int scan_bwd_tma(const void* G, int64_t ldg, const void* Hout, int64_t ldh, const float* h0,
                         const float* Sckpt, const void* dHout, int64_t lddh, void* dG, int64_t lddg,
                         float* dbias, int64_t B, int64_t Tn, int64_t H, int train, cudaStream_t st) {
-  constexpr int NST = sizeof(T) == 2 ? SC_NST_BWD : 3;     // ring depth (16-bit rows: see SC_NST_BWD above)
-  constexpr int smem = NST * 7 * TC * CB * (int)sizeof(T);
+  constexpr int ROWS = sizeof(T) == 2 ? SC_SCAN_BWD_ROWS : 8;      // rows per stage
+  constexpr int NST = ROWS == 8 ? (sizeof(T) == 2 ? SC_NST_BWD : 3) : 2;
+  constexpr int smem = NST * 7 * ROWS * CB * (int)sizeof(T);
   CUtensorMap mapG, mapH, mapDH;
-  if (!make_scan_map<T>(&mapG, G, B * Tn, 5 * H, ldg, TC) || !make_scan_map<T>(&mapH, Hout, B * Tn, H, ldh, TC) ||
-      !make_scan_map<T>(&mapDH, dHout, B * Tn, H, lddh, TC))
+  if (!make_scan_map<T>(&mapG, G, B * Tn, 5 * H, ldg, ROWS) || !make_scan_map<T>(&mapH, Hout, B * Tn, H, ldh, ROWS) ||
+      !make_scan_map<T>(&mapDH, dHout, B * Tn, H, lddh, ROWS))
     return SC_E_UNSUP;
   const int cblocks = (int)cdiv(H, CB);
   const unsigned grid = (unsigned)(B * cblocks);
-  auto kt = lucy_scan_bwd_tma_kernel<T, VEC, NST, true, PRECISE>;
-  auto ks = lucy_scan_bwd_tma_kernel<T, VEC, NST, false, PRECISE>;
+  auto kt = lucy_scan_bwd_tma_kernel<T, VEC, NST, true, PRECISE, ROWS>;
+  auto ks = lucy_scan_bwd_tma_kernel<T, VEC, NST, false, PRECISE, ROWS>;
   static std::atomic<uint64_t> attr_t{0}, attr_s{0};             // per (instantiation, device)
   {
     const cudaError_t e = train ? ensure_dyn_smem(kt, smem, attr_t) : ensure_dyn_smem(ks, smem, attr_s);
