@@ -18,9 +18,9 @@
 //              accumulator stages; tcgen05.commit (multicast to both CTAs) releases smem stages /
 //              publishes the accumulator through mbarriers
 //   warps 2-9: epilogue     — tcgen05.ld (32 lanes x 32 columns per instruction), bias add
-//              from a shared-memory copy staged once per tile, bf16 boxes through shared memory
-//              to a TMA store (or fp32 TMA reduce-add for split-R wgrad); both CTAs' epilogue
-//              warps release the accumulator on the leader's barrier
+//              (broadcast 16-byte loads through L1), bf16 [32 x 64] boxes of 128-byte rows through
+//              shared memory to a TMA store (or fp32 TMA reduce-add for split-R wgrad); both CTAs'
+//              epilogue warps release the accumulator on the leader's barrier
 // The epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM).
 #include "sc_common.cuh"
 #include "sc_tma.cuh"
@@ -37,13 +37,15 @@ constexpr int RING_BYTES = 192 * 1024;            // operand ring region: 4 stag
 constexpr int ATOM_BYTES = TK * 128;              // one [TK x 64-element] MN-major box = 8 KB
 constexpr int EPI_WARPS = 8;                     // two warps per TMEM lane quarter, 128 columns each
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int EPI_STAGE_BYTES = 32 * 32 * 2;      // per epilogue warp: one [32 rows x 32 cols] bf16 box for the TMA store
-constexpr int EPI_OFF = RING_BYTES + 256 /*barriers*/ + 2 * TN * 4 /*bias*/ + 256 /*pad: store boxes 512-B aligned for SWIZZLE_64B*/;
-static_assert(EPI_OFF % 512 == 0, "store boxes must be 512-byte aligned (64-byte swizzle pattern)");
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int EPI_STAGE_BYTES = 32 * 64 * 2;      // per epilogue warp: one [32 rows x 64 cols] bf16 box (128-byte rows) for the TMA store
+constexpr int EPI_OFF = RING_BYTES;               // first set of store boxes: right behind the ring (1024-B aligned: SWIZZLE_128B)
+constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;   // mbarriers + TMEM pointer
+static_assert(EPI_OFF % 1024 == 0 && EPI_STAGE_BYTES % 1024 == 0, "store boxes must be 1024-byte aligned (128-byte swizzle pattern)");
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + BAR_OFF + 256;
+static_assert(SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 constexpr uint32_t TMEM_COLS = 512;
 #ifndef SC_GEMM_EPI_BUFS
-#define SC_GEMM_EPI_BUFS 2   // store boxes per epilogue warp in pair mode (3, with the third set also in the ring tail: no change in step, r02)
+#define SC_GEMM_EPI_BUFS 2   // store boxes per epilogue warp in pair mode: the second set fills the 32 KB tail of the ring region
 #endif
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
@@ -86,7 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(STAGES * STAGE_BYTES + (EPI_BUFS - 1) * EPI_WARPS * EPI_STAGE_BYTES <= RING_BYTES, "ring region");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B: 1024-B aligned tiles
-  const uint32_t bar0 = base + RING_BYTES;
+  const uint32_t bar0 = base + BAR_OFF;
   // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then tmem ptr
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -94,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + RING_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + BAR_OFF + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -219,63 +221,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                   // which 128-column half of the tile
-    const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
-    float* sbias = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256);
+    // bias: every lane of a warp needs the same 32 values per chunk, so they come as broadcast 16-byte loads through L1
+    // (they used to be staged in 2 KB of shared memory behind a named barrier; the store boxes need that room now)
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    auto add_bias = [&](uint32_t (&r)[32], int64_t col) {
+      if (bias_vec && col + 32 <= p.J) {
+        const float4* bv = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float4 b4 = __ldg(bv + v);
+          r[v * 4 + 0] = __float_as_uint(__uint_as_float(r[v * 4 + 0]) + b4.x);
+          r[v * 4 + 1] = __float_as_uint(__uint_as_float(r[v * 4 + 1]) + b4.y);
+          r[v * 4 + 2] = __float_as_uint(__uint_as_float(r[v * 4 + 2]) + b4.z);
+          r[v * 4 + 3] = __float_as_uint(__uint_as_float(r[v * 4 + 3]) + b4.w);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 32; ++v)
+          if (col + v < p.J) r[v] = __float_as_uint(__uint_as_float(r[v]) + __ldg(p.bias + col + v));
+      }
+    };
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t ebox = 0;                                  // store boxes issued by this warp (selects the staging buffer)
     for (int64_t w = w0; w < total; w += wstep) {
       const int64_t tile = w % ((int64_t)pairs_i * p.tiles_j);
       const int tj = (int)(tile % p.tiles_j), ti = 2 * (int)(tile / p.tiles_j) + (int)rank;
       const int64_t col0 = (int64_t)tj * TN;
-      if (EPI != 2 && p.bias != nullptr) {
-        // stage this tile's bias once (double-buffered with the accumulator stage)
-        sbias[acc * TN + et] = (col0 + et < p.J) ? __ldg(p.bias + col0 + et) : 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      }
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const int64_t row = (int64_t)ti * TM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
+      if (EPI == 0) {
+        // bf16 output: bias, pack, stage the warp's [32 rows x 64 cols] box in shared memory and hand it to the TMA
+        // engine — full 128-byte row segments (r01: 32 scattered 16-byte stores per instruction, 1.9 TB/s; r02 first
+        // [32 x 32] boxes of 64-byte rows: a reduction-starved GEMM such as layer 0's K = 80 projection stored at 3.1
+        // TB/s, ~97 ns per box per SM whatever the eight warps did — the store engine's per-box / per-row cost — so
+        // the boxes carry twice the bytes now); the tensor map clips rows >= I and columns >= J.
 #pragma unroll 1
-      for (int cc = 0; cc < TN / 64; ++cc) {
-        const int c = half * (TN / 64) + cc;
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int64_t col = col0 + c * 32;
-        if (EPI == 0) {
-          // bf16 output: bias, pack, stage the warp's [32 x 32] box in shared memory and hand it
-          // to the TMA engine — full 64-byte row segments instead of 32 scattered 16-byte stores
-          // per instruction (measured 1.9 TB/s -> the store path was the fwd GEMM's bottleneck);
-          // the tensor map clips rows >= I and columns >= J.
+        for (int cc = 0; cc < TN / 128; ++cc) {
+          const int c = half * (TN / 64) + cc * 2;          // first of this box's two 32-column TMEM chunks
+          uint32_t ra[32], rb[32];
+          tmem_ld32(taddr + c * 32, ra);
+          tmem_ld32(taddr + (c + 1) * 32, rb);
+          tmem_ld_wait();
+          const int64_t col = col0 + c * 32;
+          if (p.bias != nullptr) { add_bias(ra, col); add_bias(rb, col + 32); }
           const uint32_t eslot = EPI_BUFS > 1 ? ebox % EPI_BUFS : 0u;
           const uint32_t stg = eslot ? base + STAGES * STAGE_BYTES + ((eslot - 1) * EPI_WARPS + (uint32_t)(warp - 2)) * EPI_STAGE_BYTES
                                      : base + EPI_OFF + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
           ++ebox;
-          if (p.bias != nullptr) {
-            const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const float4 b4 = bv[v];
-              r[v * 4 + 0] = __float_as_uint(__uint_as_float(r[v * 4 + 0]) + b4.x);
-              r[v * 4 + 1] = __float_as_uint(__uint_as_float(r[v * 4 + 1]) + b4.y);
-              r[v * 4 + 2] = __float_as_uint(__uint_as_float(r[v * 4 + 2]) + b4.z);
-              r[v * 4 + 3] = __float_as_uint(__uint_as_float(r[v * 4 + 3]) + b4.w);
-            }
-          }
           if (lane == 0) bulk_wait_read<EPI_BUFS - 1>();         // the box written EPI_BUFS stores ago has left shared memory
           __syncwarp();
+          // 128-byte rows, SWIZZLE_128B (16-byte chunk ^= row & 7): the 8 lanes of a store phase land in 8 different
+          // bank groups; unswizzled, rows 128 B apart would put all of them on the same four banks
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
+          for (int v = 0; v < 8; ++v) {
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+              const float f0 = __uint_as_float(v < 4 ? ra[v * 8 + 2 * e] : rb[(v - 4) * 8 + 2 * e]);
+              const float f1 = __uint_as_float(v < 4 ? ra[v * 8 + 2 * e + 1] : rb[(v - 4) * 8 + 2 * e + 1]);
+              __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
               pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            // 64-byte rows, SWIZZLE_64B (16-byte chunk ^= (row >> 1) & 3): the 8 lanes of a store phase land in 8
-            // different bank groups; unswizzled, rows 64 B apart gave a 4-way conflict on every store
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((v ^ ((lane >> 1) & 3)) * 16)), "r"(pk[0]), "r"(pk[1]),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((v ^ (lane & 7)) * 16)), "r"(pk[0]), "r"(pk[1]),
                          "r"(pk[2]), "r"(pk[3]) : "memory");
           }
           fence_async_smem();
@@ -284,7 +293,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tma_store_2d(&mapD, stg, (int)col, ti * TM + q * 32);
             bulk_commit();
           }
-        } else if (EPI == 2) {
+        }
+      } else {
+#pragma unroll 1
+      for (int cc = 0; cc < TN / 64; ++cc) {
+        const int c = half * (TN / 64) + cc;
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int64_t col = col0 + c * 32;
+        if (EPI == 2) {
           // split-R partial tile: fp32 TMA reduce-add of [32 rows x 16 cols] boxes (64-byte row
           // segments reduced in L2) instead of 32 scattered 4-byte atomics per lane per chunk
           const uint32_t stg = base + EPI_OFF + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
@@ -304,31 +322,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           }
         } else if (row < p.I && col < p.J) {
-          if (EPI != 2 && p.bias != nullptr) {
-            const float4* bv = reinterpret_cast<const float4*>(sbias + acc * TN + c * 32);
+          // EPI == 1: fp32 output, 16-byte stores straight from registers
+          if (p.bias != nullptr) add_bias(r, col);
+          float* out = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const float4 b4 = bv[v];
-              r[v * 4 + 0] = __float_as_uint(__uint_as_float(r[v * 4 + 0]) + b4.x);
-              r[v * 4 + 1] = __float_as_uint(__uint_as_float(r[v * 4 + 1]) + b4.y);
-              r[v * 4 + 2] = __float_as_uint(__uint_as_float(r[v * 4 + 2]) + b4.z);
-              r[v * 4 + 3] = __float_as_uint(__uint_as_float(r[v * 4 + 3]) + b4.w);
-            }
-          }
-          if (EPI == 0) {
-            // (bf16 output is written by the TMA-store branch above)
-          } else if (EPI == 1) {
-            float* out = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              if (col + v * 4 < p.J) {                  // J is a multiple of 4
-                *reinterpret_cast<float4*>(out + v * 4) =
-                    make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
-                                __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
-              }
+          for (int v = 0; v < 8; ++v) {
+            if (col + v * 4 < p.J) {                  // J is a multiple of 4
+              *reinterpret_cast<float4*>(out + v * 4) =
+                  make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
+                              __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
             }
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -362,16 +368,16 @@ static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   return r == CUDA_SUCCESS;
 }
 
-// bf16 output [rows, cols] (row stride ld): [32 x 32] store boxes (64-byte rows), 64-byte swizzle
+// bf16 output [rows, cols] (row stride ld): [32 x 64] store boxes (128-byte rows), 128-byte swizzle
 static bool make_store_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {64, 32};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -53,6 +53,23 @@ def test_tc_fwd_dgrad_wgrad(tc_ops, M, N, K):
         assert _rel(dw2, DY.T @ A + base.double().cpu()) < 2e-5
 
 
+def test_tc_bias_not_16_byte_aligned(tc_ops):
+    """The epilogue reads the bias with broadcast 16-byte loads when it can; a bias that is a view starting 4 bytes
+    into a buffer (and an N whose last store box is clipped) must take the scalar loads and give the same result."""
+    ops = tc_ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 300, 328, 96
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    w = (torch.randn(N, K, generator=g, device="cuda") / K ** 0.5).bfloat16()
+    big = torch.randn(N + 1, generator=g, device="cuda")
+    bias = big[1:]
+    assert bias.data_ptr() % 16 == 4
+    want = a.double().cpu() @ w.double().cpu().T + bias.double().cpu()
+    assert _rel(ops.gemm_fwd(a, w, bias), want) < 1e-2
+    assert _rel(ops.gemm_fwd(a, w, bias, out_dtype=torch.float32), want) < 2e-5
+    assert torch.equal(ops.gemm_fwd(a, w, bias), ops.gemm_fwd(a, w, bias.clone()))
+
+
 def test_tc_column_block_views(tc_ops):
     """Operands/outputs that are column blocks of wider buffers (ld != width), as the layer
     code passes them (gate blocks of G, rows H.. of W_fused)."""
