@@ -284,6 +284,10 @@ layernorm_fwd_vec_kernel(const T* __restrict__ X, int64_t ldx, const float* __re
   }
 }
 
+// (r02, measured and dropped: a persistent form of the forward — 3-4 blocks per SM, each warp walking rows W apart with
+// the rows of the next two visits requested ahead as raw 16-byte words, 128 registers — is bit-identical and no faster:
+// 3.54-3.56 ms for the 18 calls of a cfg2 LayerNorm step against 3.47-3.52 ms, alternating same-box runs,
+// profiles/r02_call69.sh.  Bytes in flight are not what holds this kernel at ~4 TB/s inside the power-capped step.)
 // (r02, measured and dropped: reading the row twice — a first sweep for the two row sums, a second for dX and the
 // column sums — with the gain vector re-read per row brings the kernel from 255 to 168 registers and 3 blocks per SM
 // instead of 2, and is SLOWER: 18 calls of the cfg2 LayerNorm step 7.6 ms against 6.1 ms.)
