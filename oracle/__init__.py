@@ -16,7 +16,8 @@ Parity status
 * RNN-T (rnnt_oracle.py): PARITY UNPINNED by the reference (warp_rnnt is absent,
   not in requirements.txt, and its call site model.py:97-105 matches no
   published API).  Restates the Graves-2012 transducer DP and is cross-checked
-  against ``torchaudio.functional.rnnt_loss``.
+  against ``torchaudio.functional.rnnt_loss`` and against the known-answer vector
+  warp-transducer / warp-rnnt publish in their own tests (``rnnt_oracle.WARP_KAT_*``).
 * Glue around the encoder: ``lucy_oracle.detach_states`` + the CTC composition, the RNN-T
   predictor/joiner (joiner_oracle.py, with a hand backward) and the greedy decoder
   (decoder_oracle.py) are PINNED on tests/golden/glue_cases.npz, produced by running the

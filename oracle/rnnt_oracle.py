@@ -98,3 +98,20 @@ def rnnt_loss_and_grad_logits(logits, labels, frame_lens, label_lens, blank=0):
     nll, g = rnnt_loss_and_grad(lp, labels, frame_lens, label_lens, blank)
     dx = g - np.exp(lp) * g.sum(-1, keepdims=True)
     return nll, dx
+
+
+# The known-answer vector the transducer-loss packages publish in their own test suites (HawkAaron/warp-transducer
+# `test.py` "small test", reused by 1ytic/warp-rnnt — the package the reference imports, train.py:39 — in
+# `pytorch_binding/warp_rnnt/test.py` with `log_softmax(acts)` as input, and by torchaudio's `get_basic_data`):
+# B=1, T=2, U=2, V=5, blank 0, labels [1, 2]; cost and d cost / d acts as printed there (written here from those
+# published tests — no copy of either package is in this image; torchaudio 2.11 reproduces every digit).
+WARP_KAT_ACTS = [[[[0.1, 0.6, 0.1, 0.1, 0.1], [0.1, 0.1, 0.6, 0.1, 0.1], [0.1, 0.1, 0.2, 0.8, 0.1]],
+                  [[0.1, 0.6, 0.1, 0.1, 0.1], [0.1, 0.1, 0.2, 0.1, 0.1], [0.7, 0.1, 0.2, 0.1, 0.1]]]]
+WARP_KAT_LABELS = [[1, 2]]
+WARP_KAT_COST = 4.495666
+WARP_KAT_GRADS = [[[[-0.13116688, -0.3999269, 0.17703125, 0.17703125, 0.17703125],
+                    [-0.18572757, 0.12247056, -0.18168412, 0.12247056, 0.12247056],
+                    [-0.32091254, 0.06269141, 0.06928472, 0.12624499, 0.06269141]],
+                   [[0.05456069, -0.21824276, 0.05456069, 0.05456069, 0.05456069],
+                    [0.12073959, 0.12073959, -0.48295835, 0.12073959, 0.12073959],
+                    [-0.6925882, 0.16871116, 0.18645467, 0.16871116, 0.16871116]]]]

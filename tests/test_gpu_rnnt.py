@@ -24,6 +24,18 @@ def test_rnnt_golden_torchaudio(cuda_device, case):
     np.testing.assert_allclose(logits.grad.cpu().numpy(), G[case + "/grad"], rtol=2e-4, atol=2e-6)
 
 
+def test_rnnt_published_warp_transducer_vector(cuda_device):
+    """The known-answer vector of the warp-transducer / warp-rnnt test suites (oracle/rnnt_oracle.py, WARP_KAT_*)
+    through the keyword call of model.py:97-105: `log_probs` = log_softmax(acts), blank 0."""
+    import statecatcher_b200 as sb
+    acts = torch.tensor(rnnt_oracle.WARP_KAT_ACTS, dtype=torch.float32).cuda().requires_grad_(True)
+    loss = sb.RNNTLoss(log_probs=acts.log_softmax(-1), labels=torch.tensor(rnnt_oracle.WARP_KAT_LABELS).cuda(),
+                       frames_lengths=[2], labels_lengths=[2], blank_id=0, compact=False, gather=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), rnnt_oracle.WARP_KAT_COST, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(acts.grad.cpu().numpy(), np.array(rnnt_oracle.WARP_KAT_GRADS), rtol=0, atol=2e-6)
+
+
 @pytest.mark.parametrize("B,T,U,V", [(1, 1, 0, 3), (2, 5, 1, 4), (3, 37, 9, 11), (2, 70, 40, 6), (4, 33, 17, 29)])
 def test_rnnt_random_vs_oracle(cuda_device, B, T, U, V):
     import statecatcher_b200 as sb

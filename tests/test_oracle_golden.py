@@ -126,6 +126,15 @@ def test_rnnt_oracle_matches_torchaudio_golden(case):
     np.testing.assert_allclose(dx, G[case + "/grad"], rtol=1e-4, atol=1e-6)
 
 
+def test_rnnt_oracle_matches_published_warp_transducer_vector():
+    """The loss VALUE and gradient the warp-transducer / warp-rnnt test suites publish (oracle/rnnt_oracle.py,
+    WARP_KAT_*): the nearest thing to a pin the reference's absent `warp_rnnt` dependency offers."""
+    acts = np.array(rnnt_oracle.WARP_KAT_ACTS, dtype=np.float64)
+    nll, dx = rnnt_oracle.rnnt_loss_and_grad_logits(acts, np.array(rnnt_oracle.WARP_KAT_LABELS), [2], [2])
+    np.testing.assert_allclose(nll, [rnnt_oracle.WARP_KAT_COST], rtol=0, atol=1e-6)        # printed to seven digits
+    np.testing.assert_allclose(dx, np.array(rnnt_oracle.WARP_KAT_GRADS), rtol=0, atol=2e-7)   # printed from an fp32 run
+
+
 @pytest.mark.parametrize("seed", range(12))
 @pytest.mark.parametrize("reduction", ["mean", "sum"])
 def test_ctc_oracle_matches_live_torch_on_random_ragged_batches(seed, reduction):
