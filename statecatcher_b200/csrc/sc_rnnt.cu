@@ -348,6 +348,11 @@ joint_bwd_vec_kernel(const T* __restrict__ dJ, const T* __restrict__ enc, int64_
   }
 }
 
+// (r02, measured and dropped: ONE pass over dJ — a block per (b, 8 frames), d_enc completed in the block, per-block partial
+// d_pred rows through an fp32 workspace and a fixed-order reduction kernel, so dJ is read and the tanh evaluated once.
+// Bit-identical d_enc, 128 registers, two 8-warp blocks per SM and 512 blocks for a 64-frame block of configs[3]:
+// 0.49 ms per block against 0.40 ms for the two passes above (22.9 vs 18.8 ms per step, profiles/r02_call71.sh) — the
+// 64 accumulator registers of the frame tile leave too few warps to cover the loads.)
 template <typename T, bool REDUCE_U>
 __global__ void joint_bwd_kernel(const T* __restrict__ dJ, const T* __restrict__ enc, int64_t enc_sb, int64_t enc_st,
                                  const T* __restrict__ pred, int64_t pred_sb, int64_t pred_su,

@@ -202,3 +202,34 @@ def test_rnnt_fused_head_keep_vs_recompute(cuda_device):
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("B,Tc,U1,J", [(3, 13, 7, 512), (2, 64, 151, 512), (2, 9, 5, 64), (2, 8, 3, 96)])
+def test_joint_bwd_against_fp64(cuda_device, dtype, B, Tc, U1, J):
+    """sc_joint_bwd on its own (the fused head tests only see it through the whole backward): d_enc written for a frame
+    block of a longer tensor, d_pred accumulated onto what earlier blocks left, both against an fp64 evaluation of
+    d_pre = dJ (1 - tanh^2(enc + pred)); reproducible bit for bit; J = 96 takes the scalar kernels."""
+    from statecatcher_b200 import _lib
+    from statecatcher_b200._lib import call, ptr, stream
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Tc)
+    big_enc = torch.randn(B, Tc + 3, J, generator=g, device="cuda").to(dtype)
+    enc = big_enc[:, 2:2 + Tc]                                                   # a frame block of a longer tensor
+    pred = torch.randn(B, U1, J, generator=g, device="cuda").to(dtype)
+    dJ = torch.randn(B * Tc * U1, J, generator=g, device="cuda").to(dtype)
+    base = torch.randn(B, U1, J, generator=g, device="cuda")                     # d_pred accumulates across blocks
+    outs = []
+    for _ in range(2):
+        d_enc = torch.zeros(B, Tc + 1, J, dtype=dtype, device="cuda")
+        d_pred = base.clone()
+        call("sc_joint_bwd", ptr(dJ), ptr(enc), enc.stride(0), enc.stride(1), ptr(pred), pred.stride(0), pred.stride(1),
+             ptr(d_enc), d_enc.stride(0), d_enc.stride(1), ptr(d_pred), B, Tc, U1, J, _lib.dt(dJ), stream())
+        assert not d_enc[:, Tc].any()                                            # nothing written past the block
+        outs.append((d_enc, d_pred))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    jt = torch.tanh(enc.double()[:, :, None, :] + pred.double()[:, None, :, :])
+    d_pre = dJ.double().view(B, Tc, U1, J) * (1 - jt * jt)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4                              # bf16: tanh.approx, bf16 d_enc
+    want_p, want_e = base.double() + d_pre.sum(1), d_pre.sum(2)
+    assert float((outs[0][1].double() - want_p).abs().max()) <= tol * float(want_p.abs().max())
+    assert float((outs[0][0][:, :Tc].double() - want_e).abs().max()) <= tol * float(want_e.abs().max())
