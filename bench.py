@@ -437,6 +437,18 @@ def main():
     _lib.profile = []
     ms = timed(step_resident, args.steps)
     prof, _lib.profile = _lib.profile, None
+    # N > 1: what each rank's OWN kernels took (CUDA events per call) and how long its gradient all-reduce lasted including
+    # the wait for the slowest rank to enter it — tells a straggler GPU (max over ranks of the first) from a slow
+    # collective (min over ranks of the second)
+    ranks_info = None
+    if world > 1:
+        own = sum(e0.elapsed_time(e1) for n, _w, e0, e1, _s in prof if n != "nccl_all_reduce") / args.steps
+        ar = sum(e0.elapsed_time(e1) for n, _w, e0, e1, _s in prof if n == "nccl_all_reduce") / args.steps
+        t = torch.tensor([own, ar], device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ranks_info = {"own_kernels_ms_per_step": [round(float(x[0]), 2) for x in allt],
+                      "allreduce_incl_wait_ms_per_step": [round(float(x[1]), 2) for x in allt]}
     launches = _lib.kernels if trainer is None else kernels_per_replay * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = frames_step * world * args.steps / (ms * 1e-3)
@@ -582,6 +594,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "cpu_baseline": cpu,
+        "ranks": ranks_info,
         "roofline": roofline,
         "roofline_by_kernel": {k: compact(v) for k, v in roofs.items()},
     }

@@ -175,6 +175,12 @@ class StreamDataParallel(nn.Module):
         # NCCL averages inside the collective; gloo (CPU tests) only sums
         b.avg_in_collective = self.average and dist.get_backend(self.pg) == "nccl"
         op = dist.ReduceOp.AVG if b.avg_in_collective else dist.ReduceOp.SUM
+        b.ev0 = None
+        if dev.type == "cuda":
+            from . import _lib as _l
+            if _l.profile is not None:           # bench.py's timed region: bracket the collective with events on the compute stream
+                b.ev0 = torch.cuda.Event(enable_timing=True)
+                b.ev0.record()
         b.work = dist.all_reduce(b.flat, op=op, group=self.pg, async_op=True)
         b.live = live
         self.n_allreduce += 1
@@ -189,6 +195,13 @@ class StreamDataParallel(nn.Module):
             if b.work is None:
                 continue
             b.work.wait()
+            if getattr(b, "ev0", None) is not None:
+                from . import _lib as _l
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()                     # after the compute stream has been made to wait for the collective:
+                if _l.profile is not None:       # the collective itself + the wait for the slowest rank to enter it
+                    _l.profile.append(("nccl_all_reduce", 0.0, b.ev0, ev1, ()))
+                b.ev0 = None
             scale = 1.0 / self.world if (self.average and not b.avg_in_collective) else 1.0
             grads = [p.grad for p, _ in b.live]
             esz = b.flat.element_size()
