@@ -11,7 +11,7 @@
 //
 // Structure (one persistent CTA per SM, 320 threads, clusters of two CTAs = one MMA pair):
 //   warp 0   : TMA producer — cp.async.bulk.tensor 128B-swizzled tiles into the operand ring
-//              (pair mode: 6 stages of [A 128x64 | half of B 128x64]; both CTAs' bytes are counted
+//              (pair mode: 5 stages of [A 128x64 | half of B 128x64]; both CTAs' bytes are counted
 //              on the leader's mbarrier)
 //   warp 1   : MMA issuer   — one thread of the LEADER CTA issues tcgen05.mma.cta_group::2
 //              (M=256 over the two SMs, N=256, K=16, bf16->fp32) into one of two 256-column TMEM
@@ -75,7 +75,7 @@ struct GemmParams {
 // PAIR: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256 across the two
 // SMs, N = 256): each CTA stages its own 128 rows of A and only HALF of the B tile — the tensor
 // cores read the other half from the peer's shared memory — so a stage is 32 KB instead of 48 KB
-// (shared-memory write and operand-read traffic per flop drop by a third, six stages fit).
+// (shared-memory write and operand-read traffic per flop drop by a third, five stages and the second set of store boxes fit in the ring region).
 // !PAIR: each CTA issues its own M = 128 MMA on a full copy of the B tile (TMA multicast).
 template <bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
