@@ -114,6 +114,9 @@ __global__ void zero_kernel(float* __restrict__ p, int64_t n) {
 }
 
 // out[n] += sum over a chunk of rows; one thread per column, coalesced across columns
+// (r02, measured and dropped: a bf16 form with 16-byte loads — a thread owns 8 adjacent columns, 8 rows in flight, 592 blocks
+// of 1024 columns — took 0.202 ms for the [192000 x 1024] dlogits of a cfg2 step against 0.128 ms for this kernel,
+// profiles/r02_call78.sh; not investigated further: the pass is 0.4 % of the step.)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, int64_t ldx, float* __restrict__ out,
                               int64_t M, int64_t N, int64_t rows_per_block) {

@@ -203,6 +203,25 @@ def test_split_bf16_hi_lo(cuda_device, rows, cols, pad):
     assert torch.equal(out[:, cols:].cpu().view(torch.int16), lo.view(torch.int16))
 
 
+@pytest.mark.parametrize("N", [1024, 1032, 264])
+def test_colsum_bf16_many_rows(cuda_device, N):
+    """Many rows (M = 10 001: ragged against the 4-row unroll and the row chunks of the column-sum kernel), widths that
+    are not a multiple of its 128-column block, a column block of a wider tensor, and accumulation onto an existing
+    vector."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(23)
+    M = 10001
+    big = torch.randn(M, N + 16, generator=g).bfloat16()
+    x = big.cuda()[:, 8:8 + N]                                       # row stride N + 16, 16-byte aligned start
+    want = big[:, 8:8 + N].double().sum(0)
+    got = ops.colsum(x)
+    assert float((got.cpu().double() - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-3
+    base = torch.randn(N, generator=g)
+    out = base.cuda().clone()
+    ops.colsum(x, out=out, accumulate=True)
+    assert float((out.cpu().double() - (want + base.double())).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-3
+
+
 @pytest.mark.parametrize("H", [256, 1024])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_layernorm_bwd_many_rows_and_dx_colsum(cuda_device, dtype, H):
