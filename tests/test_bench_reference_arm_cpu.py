@@ -1,0 +1,30 @@
+"""CPU: `bench.py --impl reference` (the reference's own CPU algorithm on the host cores) runs without a GPU and prints
+the one JSON line the driver parses: same metric / unit / config as the CUDA arm, `impl: "reference"`, a `cpu_baseline`
+describing the run and an `e2e` that repeats the line's own value with zero copies."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    assert d["metric"] == "train_frames_per_sec" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert "configs[1]" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert "B=8 T=300" in cb["sample"]                       # the fixed reduced shape of BASELINE.md section 4
+    if os.path.isdir("/root/reference"):
+        assert cb["kind"] == "reference"                      # the unmodified reference is imported where it is mounted
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
