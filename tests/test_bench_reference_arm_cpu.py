@@ -28,3 +28,18 @@ def test_reference_arm_json_line():
         assert cb["kind"] == "reference"                      # the unmodified reference is imported where it is mounted
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """Launched the way the driver launches N > 1 (torchrun, one process per GPU), rank 0 alone runs the arm and prints
+    it; the other ranks exit 0 without work."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["n_gpus"] == 2
